@@ -1,0 +1,407 @@
+#!/usr/bin/env python
+"""Benchmark of the sliced-OT hot path (BASELINE.json metric: OT iterations/sec at conv4_1 of a 1024^2 image).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--mode cdf|sort|chol|pca|sym] [--impl ours|reference]
+
+A "step" is one OT iteration  out = hist_match(P R, S R, mode) R^T  (optex.py:167-177) on one synthetic
+feature block P, S = [1, 128, 128, 512] fp32 (N_p = N_s = 16384 pixels, C = 512 channels), rotation drawn
+per step.  One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
+
+  value       device-resident inputs, CUDA-event timed, whole-job aggregate over all ranks (weak scaling:
+              every rank transports its own independent feature block - no data-path collective)
+  e2e         the same step through the host-buffer C-ABI call (optex_ot_step_host): pinned host memory in,
+              host memory out, H2D + D2H inside the timed region
+  roofline    the dominant kernel of the step: algorithmic bytes or flops / its event-timed duration
+  cpu_baseline / --impl reference
+              the CPU port of the reference (oracle/, pinned bit-exactly to the reference's own outputs)
+              on the host cores of the same box, rotation draw included as the reference does (optex.py:168)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "ot_iters_per_sec_conv4_1_1024"
+UNIT = "it/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="cdf", choices=["cdf", "sort", "chol", "pca", "sym"])
+    ap.add_argument("--gemm", default="auto", choices=["auto", "fp32", "tf32x3", "tf32"])
+    ap.add_argument("--hw", type=int, default=128, help="feature-map side: conv4_1 of a 1024^2 image = 128")
+    ap.add_argument("--channels", type=int, default=512)
+    ap.add_argument("--sets", type=int, default=4, help="distinct input sets cycled so inputs exceed L2")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--all-modes", action="store_true", help="also time the other hist modes (extra keys)")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"ot_step conv4_1@{a.hw * 8}^2: P,S=[1,{a.hw},{a.hw},{a.channels}] fp32 "
+            f"(N_p=N_s={a.hw * a.hw}, C={a.channels}), hist_mode={a.mode}, rotation drawn per step")
+
+
+def step_work(n_p, n_s, c):
+    """algorithmic work of one OT iteration."""
+    return {"flops": 2.0 * c * c * (2 * n_p + n_s), "bytes": 4.0 * c * (2 * n_p + n_s) + 4.0 * c * c}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_inputs(torch, a, seed, device):
+    """SURVEY.md 8(d) synthetic input: P = relu(randn), S = relu(1.3 randn + 0.2), fp32 NHWC."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    shape = (1, a.hw, a.hw, a.channels)
+    p = torch.relu(torch.randn(shape, generator=g))
+    s = torch.relu(1.3 * torch.randn(shape, generator=g) + 0.2)
+    return p.to(device), s.to(device)
+
+
+# ------------------------------------------------------------------------------------------- reference arm
+def cpu_reference_rate(a, steps, warmup, budget_s=None):
+    """The reference's algorithm on the host cores: oracle port (bit-exact with the reference's outputs,
+    tests/test_oracle_golden.py) including the per-iteration scipy-style rotation draw (optex.py:149,168)."""
+    import numpy as np
+    import torch
+
+    from oracle import ot_oracle, rotation as rot_oracle, sort_oracle
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    p, s = make_inputs(torch, a, 0, "cpu")
+    rng = np.random.RandomState(0)
+
+    def one(p):
+        r = torch.tensor(rot_oracle.haar_rotation_qr(a.channels, rng))          # float64 like optex.py:149
+        if a.mode == "sort":
+            return sort_oracle.ot_step_sort(p, s, r)
+        return ot_oracle.ot_step(p, s, r, a.mode)
+
+    for _ in range(warmup):
+        p = one(p)
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        p = one(p)
+        done += 1
+        if budget_s is not None and time.perf_counter() - t0 > budget_s and done >= 2:
+            break
+    dt = time.perf_counter() - t0
+    return done / dt, dt / done * 1e3, done, cores
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rate, ms, done, cores = cpu_reference_rate(a, a.steps, a.warmup)
+    sample = f"{done} full-size steps ({workload_name(a)}), oracle port incl. rotation draw, torch {cores} threads"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": a.gpus, "steps": done,
+        "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": {"workload": workload_name(a)},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - optimaltextures_b200 has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    from optimaltextures_b200 import build as _build
+
+    if rank == 0:
+        _build.build()
+    if world > 1:
+        dist.barrier()
+    import optimaltextures_b200 as ob
+    from optimaltextures_b200 import _lib
+    from optimaltextures_b200._runtime import call, ptr, stream_ptr, workspace
+
+    lib = _lib.lib()
+    _lib.check(lib.optex_device_check())
+    ob.set_gemm_mode(a.gemm)
+    K, W = a.steps, a.warmup
+    n = a.hw * a.hw
+    c = a.channels
+    mode = _lib.mode_id(a.mode)
+    sets = [make_inputs(torch, a, 1000 * rank + i, device) for i in range(a.sets)]
+    outs = [torch.empty_like(sets[0][0]) for _ in range(2)]
+    ws = workspace(device, lib.optex_ot_workspace_bytes(n, n, c, mode))
+    rot_ws = torch.empty(lib.optex_rotations_workspace_bytes(c, K), dtype=torch.uint8, device=device)
+    rots = torch.empty(K, c, c, dtype=torch.float32, device=device)
+    st = stream_ptr(device)
+
+    def gen_rotations(count, first):
+        call("optex_random_rotations", ptr(rots), c, count, 1234 + rank, first, None, ptr(rot_ws), rot_ws.numel(), st)
+
+    def step(i):
+        p, s = sets[i % a.sets]
+        call("optex_ot_step", ptr(p), ptr(s), ptr(rots[i % K]), ptr(outs[i % 2]), 1, n, 1, n, c, mode, 1.0, None,
+             0.0, ptr(ws), ws.numel(), st)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- value: device-resident inputs
+    gen_rotations(min(K, max(W, 1)), 0)
+    for i in range(W):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = lib.optex_launch_count()
+    barrier()
+    e0.record()
+    gen_rotations(K, W)                       # the per-step rotation draw, batched (as optex_ot_loop does)
+    for i in range(K):
+        step(i)
+    e1.record()
+    barrier()
+    launches = lib.optex_launch_count() - launches0
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total / K
+    value = world * K / (ms_total * 1e-3)
+
+    # ---- breakdown: the step's stages through the exported building blocks, event-timed in the same loop
+    stages = {}
+    if rank == 0:
+        per_channel = a.mode in ("cdf", "sort")
+        if per_channel:
+            rp = torch.empty(c, n, dtype=torch.float32, device=device)
+            rs = torch.empty(c, n, dtype=torch.float32, device=device)
+            names = ["rotate_forward_P", "rotate_forward_S", f"{a.mode}_match", "rotate_inverse"]
+            ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(K)]
+            mws = workspace(device, max(lib.optex_cdf_match_workspace_bytes(c, 256), 256))
+            for i in range(K):
+                p, s = sets[i % a.sets]
+                r = rots[i % K]
+                ev[i][0].record()
+                call("optex_rotate_forward", ptr(p), ptr(r), ptr(rp), n, c, st)
+                ev[i][1].record()
+                call("optex_rotate_forward", ptr(s), ptr(r), ptr(rs), n, c, st)
+                ev[i][2].record()
+                if a.mode == "cdf":
+                    call("optex_cdf_match", ptr(rp), ptr(rs), ptr(rp), c, n, n, 256, None, ptr(mws), mws.numel(), st)
+                else:
+                    call("optex_sort_match", ptr(rp), ptr(rs), ptr(rp), c, n, n, None, None, 0, st)
+                ev[i][3].record()
+                call("optex_rotate_inverse", ptr(rp), ptr(r), ptr(outs[i % 2]), n, c, None, 0.0, st)
+                ev[i][4].record()
+            torch.cuda.synchronize()
+            for j, name in enumerate(names):
+                stages[name] = statistics.mean(ev[i][j].elapsed_time(ev[i][j + 1]) for i in range(K))
+
+    # ---- e2e: host buffers through optex_ot_step_host (H2D + step + D2H per call)
+    e2e = None
+    if not a.no_e2e:
+        hp = [torch.empty(1, a.hw, a.hw, c).pin_memory() for _ in range(2)]
+        hs = [torch.empty(1, a.hw, a.hw, c).pin_memory() for _ in range(2)]
+        ho = torch.empty(1, a.hw, a.hw, c).pin_memory()
+        for i in range(2):
+            hp[i].copy_(sets[i % a.sets][0]); hs[i].copy_(sets[i % a.sets][1])
+        Ke = max(3, min(K, 30))
+        for i in range(2):
+            ob.optimal_transport_host(hp[i % 2], hs[i % 2], None, a.mode, out=ho, seed=99, counter=i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(Ke):
+            ob.optimal_transport_host(hp[i % 2], hs[i % 2], None, a.mode, out=ho, seed=99, counter=2 + i)
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": world * Ke / dt, "unit": UNIT, "h2d_bytes_per_step": 2 * 4 * n * c,
+               "d2h_bytes_per_step": 4 * n * c, "steps": Ke, "ms_per_step": dt / Ke * 1e3,
+               "api": "optex_ot_step_host (C-ABI, pinned host buffers, rotation drawn on device)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel
+    pk = peaks()
+    work = step_work(n, n, c)
+    roofline = None
+    kernels = {}
+    if stages:
+        alg = {
+            "rotate_forward_P": ("tensor", 2.0 * c * c * n), "rotate_forward_S": ("tensor", 2.0 * c * c * n),
+            "rotate_inverse": ("tensor", 2.0 * c * c * n),
+            f"{a.mode}_match": ("hbm", 4.0 * c * (n + n) + 4.0 * c * n),
+        }
+        for name, ms in stages.items():
+            bound, amount = alg[name]
+            if bound == "tensor":
+                ach, peak, unit = amount / (ms * 1e-3) / 1e12, pk["bf16_tflops_sustained"], "TFLOP/s"
+            else:
+                ach, peak, unit = amount / (ms * 1e-3) / 1e9, pk["hbm_gbs"], "GB/s"
+            kernels[name] = {"ms": ms, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak}
+        top = max(stages, key=stages.get)
+        k = kernels[top]
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(f"{top}:{a.mode}:{a.gemm}")
+        roofline = {"kernel": top, "bound": k["bound"], "achieved": k["achieved"], "peak": k["peak"], "unit": k["unit"],
+                    "frac": k["frac"], "traffic": traffic, "peak_source": pk["source"] +
+                    (" bf16 sustained (tf32 tensor peak is nominally half of it)" if k["bound"] == "tensor" else " copy")}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "gemm": a.gemm,
+                   "l2": f"inputs cycle over {a.sets} distinct (P,S) sets = {a.sets * 2 * 4 * n * c / 1e6:.0f} MB > 126 MB L2",
+                   "sharding": "independent feature blocks per rank, no data-path collective"},
+        "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline, "kernels": kernels,
+        "step_roofline": {"hbm_frac": work["bytes"] / (ms_step * 1e-3) / 1e9 / pk["hbm_gbs"],
+                          "tensor_frac": work["flops"] / (ms_step * 1e-3) / 1e12 / pk["bf16_tflops_sustained"],
+                          "flops": work["flops"], "bytes": work["bytes"]},
+    }
+    if world == 1 and not a.no_cpu_baseline:
+        rate, ms, done, cores = cpu_reference_rate(a, steps=12, warmup=1, budget_s=20.0)
+        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "ms_per_step": ms,
+                                "sample": f"{done} full-size steps of the same workload (oracle port incl. rotation "
+                                          f"draw, torch {cores} threads)"}
+    if a.all_modes and world == 1:
+        extra = {}
+        for m in ("cdf", "sort", "chol", "pca", "sym"):
+            if m == a.mode:
+                continue
+            try:
+                mid = _lib.mode_id(m)
+                w2 = workspace(device, lib.optex_ot_workspace_bytes(n, n, c, mid))
+                def st2(i):
+                    p, s = sets[i % a.sets]
+                    call("optex_ot_step", ptr(p), ptr(s), ptr(rots[i % K]), ptr(outs[i % 2]), 1, n, 1, n, c, mid,
+                         1.0, None, 0.0, ptr(w2), w2.numel(), st)
+                for i in range(3):
+                    st2(i)
+                torch.cuda.synchronize()
+                e0.record()
+                for i in range(K):
+                    st2(i)
+                e1.record()
+                torch.cuda.synchronize()
+                extra[m] = K / (e0.elapsed_time(e1) * 1e-3)
+            except Exception as exc:  # noqa: BLE001
+                extra[m] = f"error: {exc}"
+        line["other_modes_it_s"] = extra
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

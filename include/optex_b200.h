@@ -1,0 +1,184 @@
+/*
+ * optex_b200.h - C-ABI of the B200-native sliced-optimal-transport step.
+ *
+ * This is the drop-in boundary for the hot path of JCBrouwer/OptimalTextures
+ * (reference commit f201bfa).  Every entry point replaces one reference
+ * function; the citation after "replaces:" is file:line in the reference tree.
+ *
+ * Conventions
+ *   - plain C, no torch types; device pointers are raw CUDA pointers (fp32),
+ *     `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - every function ENQUEUES on `stream` and returns without synchronising,
+ *     except the *_host entry points (host buffers in, host buffers out) which
+ *     synchronise `stream` before returning.
+ *   - return value: OPTEX_OK (0) or an OPTEX_E* code; optex_last_error() gives
+ *     a thread-local message.  Nothing aborts the process, nothing falls back
+ *     to the CPU: on a non-sm_100 device every compute call returns
+ *     OPTEX_EDEVICE.
+ *   - feature blocks are "NHWC flattened": row-major [n, c] with c contiguous
+ *     (n = b*h*w), exactly the memory the reference hands to `@ rotation`
+ *     (optex.py:170-171).  "channel-major" means row-major [c, n].
+ *   - inputs are never written; outputs never alias inputs.
+ */
+#ifndef OPTEX_B200_H
+#define OPTEX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OPTEX_ABI_VERSION 1
+
+/* status codes */
+#define OPTEX_OK 0
+#define OPTEX_EINVAL 1     /* bad argument (shape, NULL pointer, unknown mode) */
+#define OPTEX_EDEVICE 2    /* current device is not sm_100 (no fallback exists)  */
+#define OPTEX_ECUDA 3      /* a CUDA runtime call or kernel launch failed        */
+#define OPTEX_EWORKSPACE 4 /* workspace pointer NULL or too small                */
+#define OPTEX_ESIZE 5      /* size outside what the kernels support              */
+
+/* hist modes: histmatch.py:5 `mode`; OPTEX_MODE_SORT is the north-star's exact
+ * 1-D OT (not in the reference, defined by oracle/sort_oracle.py).            */
+#define OPTEX_MODE_CHOL 0
+#define OPTEX_MODE_PCA 1
+#define OPTEX_MODE_SYM 2
+#define OPTEX_MODE_CDF 3
+#define OPTEX_MODE_SORT 4
+
+/* rotation GEMM arithmetic */
+#define OPTEX_GEMM_AUTO 0    /* tcgen05 3xTF32 when shapes allow, else fp32 SIMT */
+#define OPTEX_GEMM_FP32 1    /* fp32 FFMA tiles (SIMT)                            */
+#define OPTEX_GEMM_TF32X3 2  /* tcgen05 kind::tf32, 3-term split, fp32-grade      */
+#define OPTEX_GEMM_TF32 3    /* tcgen05 kind::tf32, single pass (reference's own
+                                CUDA default, optex.py:248-249)                   */
+
+/* ---- library / device ------------------------------------------------------ */
+int optex_abi_version(void);
+const char *optex_last_error(void);
+/* 0 if the CURRENT cuda device is sm_100 (B200), else OPTEX_EDEVICE. */
+int optex_device_check(void);
+/* Counts kernels launched by this library since load (bench.py `gpu_launches`). */
+uint64_t optex_launch_count(void);
+/* Select the rotation-GEMM arithmetic (OPTEX_GEMM_*), process-wide. */
+int optex_set_gemm_mode(int gemm_mode);
+int optex_get_gemm_mode(void);
+
+/* ---- the OT step -----------------------------------------------------------
+ * replaces: optimal_transport()  optex.py:167-177  (+ the content blend of the
+ *           inner loop, optex.py:115-117, as a fused epilogue)
+ *
+ *   out[n_p, c] = hist_match(P @ R, S @ R, mode) @ R^T      (then, if content:
+ *   out += content_strength * (content - out))
+ *
+ * P [b_p*hw_p, c], S [b_s*hw_s, c], R [c, c] row-major, out [b_p*hw_p, c].
+ * b_* / hw_* : batch and pixels-per-sample; the covariance modes take their
+ * means per sample (histmatch.py:16,20) and need b_s == 1 or b_s == b_p
+ * (histmatch.py:44); cdf/sort pool everything (histmatch.py:11).
+ * eps: histmatch.py:5 (the reference always uses 1).
+ * content may be NULL.  workspace: optex_ot_workspace_bytes().
+ */
+size_t optex_ot_workspace_bytes(int64_t n_p, int64_t n_s, int c, int mode);
+int optex_ot_step(const float *P, const float *S, const float *R, float *out,
+                  int b_p, int64_t hw_p, int b_s, int64_t hw_s, int c, int mode,
+                  float eps, const float *content, float content_strength,
+                  void *workspace, size_t workspace_bytes, void *stream);
+
+/* Same step with HOST buffers (pageable or pinned): H2D of P, S, R (and
+ * content), the step, D2H of out, one stream sync.  Device scratch is owned by
+ * the library and grows on demand.  R may be NULL: the rotation is then drawn on
+ * the device from (seed, counter) like optex_random_rotation - the reference
+ * also draws it inside the call (optex.py:168). */
+int optex_ot_step_host(const float *P, const float *S, const float *R, float *out,
+                       int b_p, int64_t hw_p, int b_s, int64_t hw_s, int c,
+                       int mode, float eps, const float *content,
+                       float content_strength, uint64_t seed, uint64_t counter,
+                       void *stream);
+
+/* ---- the inner loop --------------------------------------------------------
+ * replaces: optex.py:112-117  (`for _ in range(iters): optimal_transport; blend`)
+ * feat [n_p, c] is updated IN PLACE `iters` times.  Rotations: if R_all != NULL
+ * it holds iters matrices [iters, c, c]; else they are generated on the device
+ * from (seed, first_counter + i)  (optex_random_rotation).
+ */
+int optex_ot_loop(float *feat, const float *S, const float *R_all, int iters,
+                  uint64_t seed, uint64_t first_counter, int b_p, int64_t hw_p,
+                  int b_s, int64_t hw_s, int c, int mode, float eps,
+                  const float *content, float content_strength, void *workspace,
+                  size_t workspace_bytes, void *stream);
+size_t optex_ot_loop_workspace_bytes(int64_t n_p, int64_t n_s, int c, int mode);
+
+/* ---- histogram matching without rotation -----------------------------------
+ * replaces: hist_match()  histmatch.py:5-46  (called directly by
+ *           mix_style_features, optex.py:200-201)
+ * target [b_t*hw_t, c] and source [b_s*hw_s, c] NHWC-flattened -> out like target.
+ */
+size_t optex_hist_match_workspace_bytes(int64_t n_t, int64_t n_s, int c, int mode);
+int optex_hist_match(const float *target, const float *source, float *out,
+                     int b_t, int64_t hw_t, int b_s, int64_t hw_s, int c, int mode,
+                     float eps, void *workspace, size_t workspace_bytes,
+                     void *stream);
+
+/* ---- per-channel matchers on channel-major data ----------------------------
+ * replaces: cdf_match()  histmatch.py:49-69  and  interp()  histmatch.py:72-92
+ * target [c, n_t], source [c, n_s] -> out [c, n_t].  Bit-exact with torch-CPU
+ * (histc / linspace / cumsum / searchsorted semantics, see oracle/cdf_explicit.py).
+ * `tables` (optional, may be NULL): [c, 2, bins] fp32 receiving the upper bin
+ * edges and the remapped CDF of every channel (parity hook).  bins <= 1024.
+ */
+size_t optex_cdf_match_workspace_bytes(int c, int bins);
+int optex_cdf_match(const float *target, const float *source, float *out, int c,
+                    int64_t n_t, int64_t n_s, int bins, float *tables,
+                    void *workspace, size_t workspace_bytes, void *stream);
+/* interp(x, xp, fp): x [n], xp/fp [len] -> out [n]  (histmatch.py:72-92). */
+int optex_interp(const float *x, const float *xp, const float *fp, float *out,
+                 int64_t n, int len, void *stream);
+
+/* Exact 1-D OT per channel (north-star `sort` mode; oracle/sort_oracle.py):
+ * stable argsort of target, ascending sort of source, rank r receives
+ * sorted_source[((2r+1)*n_s)/(2*n_t)].  `perm` (optional, may be NULL): [c, n_t]
+ * int32 receiving the stable sort permutation (parity hook: bit-exact). */
+size_t optex_sort_match_workspace_bytes(int c, int64_t n_t, int64_t n_s);
+int optex_sort_match(const float *target, const float *source, float *out, int c,
+                     int64_t n_t, int64_t n_s, int32_t *perm, void *workspace,
+                     size_t workspace_bytes, void *stream);
+
+/* ---- rotations --------------------------------------------------------------
+ * replaces: random_rotation()  optex.py:142-164
+ * Haar-distributed SO(c) matrix, generated on the device: Philox4x32-10
+ * Gaussians keyed by (seed, counter) -> Stewart's Householder construction
+ * (the reference's impl="torch" branch, optex.py:151-164) in fp64, stored fp32.
+ * If `gauss` != NULL it supplies the normals instead ([c-1, c] fp64, row n uses
+ * columns n..c-1) - the parity hook against oracle/rotation.py.
+ * R [c, c] row-major.  workspace: optex_rotation_workspace_bytes(c).
+ */
+size_t optex_rotation_workspace_bytes(int c);
+int optex_random_rotation(float *R, int c, uint64_t seed, uint64_t counter,
+                          const double *gauss, void *workspace,
+                          size_t workspace_bytes, void *stream);
+
+/* `count` rotations R[count][c][c] from counters first_counter .. +count-1 in
+ * one batched launch pair (what optex_ot_loop uses: a single matrix is latency
+ * bound, a batch fills the machine).  gauss (optional): [count, c-1, c] fp64. */
+size_t optex_rotations_workspace_bytes(int c, int count);
+int optex_random_rotations(float *R, int c, int count, uint64_t seed,
+                           uint64_t first_counter, const double *gauss,
+                           void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- rotation GEMMs (building blocks of the step, exported for tests) -------
+ * optex.py:170-171:  Xt[c, n] = (X @ R)^T     X [n, c], R [c, c]
+ * optex.py:175    :  out[n, c] = Mt^T @ R^T   Mt [c, n] channel-major
+ *                    (+ optional content blend, optex.py:117)
+ */
+int optex_rotate_forward(const float *X, const float *R, float *Xt, int64_t n,
+                         int c, void *stream);
+int optex_rotate_inverse(const float *Mt, const float *R, float *out, int64_t n,
+                         int c, const float *content, float content_strength,
+                         void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OPTEX_B200_H */

@@ -1,0 +1,361 @@
+// C-ABI of liboptex_b200 (include/optex_b200.h): library state, argument checking and the
+// composition of the kernels into the reference's call surface
+//   optimal_transport()  optex.py:167-177      -> optex_ot_step / optex_ot_step_host
+//   inner loop           optex.py:112-117      -> optex_ot_loop
+//   hist_match()         histmatch.py:5-46     -> optex_hist_match
+#include <atomic>
+#include <cstdarg>
+#include <cstring>
+#include <mutex>
+
+#include "common.cuh"
+#include "gemm_tc.cuh"
+
+namespace optex {
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+static std::atomic<int> g_gemm_mode{OPTEX_GEMM_AUTO};
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char *what) {
+    set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+    return OPTEX_ECUDA;
+}
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+static int g_dev_ok[64];  // 0 unknown, 1 sm_100, -1 other
+static int g_dev_sms[64];
+int require_sm100() {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+        cuda_fail(e, "cudaGetDevice (is there a GPU?)");
+        return OPTEX_EDEVICE;
+    }
+    if (dev < 0 || dev >= 64) dev = 63;
+    if (g_dev_ok[dev] == 0) {
+        int major = 0, minor = 0, sms = 0;
+        cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+        cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        g_dev_sms[dev] = sms > 0 ? sms : 148;
+        g_dev_ok[dev] = (major == 10 && minor == 0) ? 1 : -1;
+        if (g_dev_ok[dev] < 0)
+            set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only and has no fallback",
+                      dev, major, minor);
+    }
+    if (g_dev_ok[dev] < 0) {
+        if (!g_err[0]) set_error("current device is not sm_100 (B200); no fallback exists");
+        return OPTEX_EDEVICE;
+    }
+    return OPTEX_OK;
+}
+int sm_count() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    return g_dev_sms[dev] > 0 ? g_dev_sms[dev] : 148;
+}
+
+// ---- rotation GEMMs -----------------------------------------------------------
+static bool want_tc(bool &forced) {
+    int m = g_gemm_mode.load();
+    forced = (m == OPTEX_GEMM_TF32X3 || m == OPTEX_GEMM_TF32);
+    return m != OPTEX_GEMM_FP32;
+}
+static int tc_terms() { return g_gemm_mode.load() == OPTEX_GEMM_TF32 ? 1 : 3; }
+
+// Xt[c, n] = (X R)^T   or  XR[n, c] = X R            optex.py:170-171
+static int rotate_forward(const float *X, const float *R, float *dst, int64_t n, int c, bool transposed,
+                          cudaStream_t st) {
+    bool forced;
+    if (want_tc(forced)) {
+        int rc = gemm_tc_rotate_forward(X, R, dst, n, c, transposed, tc_terms(), st);
+        if (rc != OPTEX_ENOTSUP) return rc;
+        if (forced) return OPTEX_ESIZE;
+    }
+    // D[m = pixel, n = channel] = sum_k X[m, k] R[k, n]
+    return sgemm_simt(X, c, true, R, c, false, dst, transposed ? n : c, transposed, n, c, c, nullptr, 0.f, 1.f, st);
+}
+// out[n, j] = sum_c M(n, c) R[j, c]  (+ blend)         optex.py:175, :117
+static int rotate_inverse(const float *M, bool m_channel_major, const float *R, float *out, int64_t n, int c,
+                          const float *content, float strength, cudaStream_t st) {
+    bool forced;
+    if (want_tc(forced)) {
+        int rc = gemm_tc_rotate_inverse(M, m_channel_major, R, out, n, c, content, strength, tc_terms(), st);
+        if (rc != OPTEX_ENOTSUP) return rc;
+        if (forced) return OPTEX_ESIZE;
+    }
+    return sgemm_simt(M, m_channel_major ? n : c, !m_channel_major, R, c, true, out, c, false, n, c, c, content,
+                      strength, 1.f, st);
+}
+
+static bool per_channel(int mode) { return mode == OPTEX_MODE_CDF || mode == OPTEX_MODE_SORT; }
+static bool valid_mode(int mode) { return mode >= OPTEX_MODE_CHOL && mode <= OPTEX_MODE_SORT; }
+
+static size_t match_ws_bytes(int64_t n_p, int64_t n_s, int c, int mode) {
+    if (mode == OPTEX_MODE_CDF) return optex_cdf_match_workspace_bytes(c, 256);
+    if (mode == OPTEX_MODE_SORT) return optex_sort_match_workspace_bytes(c, n_p, n_s);
+    return cov_match_ws_bytes(n_p, n_s, c, mode);
+}
+
+static int check_step_args(const char *fn, const void *P, const void *S, const void *out, int b_p, int64_t hw_p,
+                           int b_s, int64_t hw_s, int c, int mode) {
+    if (!P || !S || !out) {
+        set_error("%s: NULL feature pointer", fn);
+        return OPTEX_EINVAL;
+    }
+    if (b_p < 1 || b_s < 1 || hw_p < 1 || hw_s < 1 || c < 1) {
+        set_error("%s: empty or negative shape (b_p=%d hw_p=%lld b_s=%d hw_s=%lld c=%d)", fn, b_p,
+                  (long long)hw_p, b_s, (long long)hw_s, c);
+        return OPTEX_EINVAL;
+    }
+    if (!valid_mode(mode)) {
+        set_error("%s: unknown mode %d", fn, mode);
+        return OPTEX_EINVAL;
+    }
+    if (!per_channel(mode) && !(b_s == 1 || b_s == b_p)) {
+        set_error("%s: covariance modes need b_s == 1 or b_s == b_p (histmatch.py:44 broadcast), got %d vs %d",
+                  fn, b_s, b_p);
+        return OPTEX_EINVAL;
+    }
+    return OPTEX_OK;
+}
+
+// The step proper.  P may alias out (P is dead once the forward rotation has run).
+static int ot_step_impl(const float *P, const float *S, const float *R, float *out, int b_p, int64_t hw_p,
+                        int b_s, int64_t hw_s, int c, int mode, float eps, const float *content, float strength,
+                        void *ws, size_t ws_bytes, cudaStream_t st) {
+    const int64_t n_p = (int64_t)b_p * hw_p, n_s = (int64_t)b_s * hw_s;
+    Arena ar(ws, ws_bytes);
+    float *rp = ar.take<float>((size_t)n_p * c);
+    float *rs = ar.take<float>((size_t)n_s * c);
+    float *mt = per_channel(mode) ? rp : ar.take<float>((size_t)n_p * c);
+    size_t mws = match_ws_bytes(n_p, n_s, c, mode);
+    void *mw = ar.take<char>(mws);
+    if (!ar.ok()) {
+        set_error("optex_ot_step: workspace %zu < %zu bytes", ws_bytes, optex_ot_workspace_bytes(n_p, n_s, c, mode));
+        return OPTEX_EWORKSPACE;
+    }
+    if (per_channel(mode)) {
+        OPTEX_TRY(rotate_forward(P, R, rp, n_p, c, true, st));
+        OPTEX_TRY(rotate_forward(S, R, rs, n_s, c, true, st));
+        if (mode == OPTEX_MODE_CDF)
+            OPTEX_TRY(optex_cdf_match(rp, rs, mt, c, n_p, n_s, 256, nullptr, mw, mws, st));
+        else
+            OPTEX_TRY(optex_sort_match(rp, rs, mt, c, n_p, n_s, nullptr, mw, mws, st));
+        return rotate_inverse(mt, true, R, out, n_p, c, content, strength, st);
+    }
+    OPTEX_TRY(rotate_forward(P, R, rp, n_p, c, false, st));
+    OPTEX_TRY(rotate_forward(S, R, rs, n_s, c, false, st));
+    OPTEX_TRY(cov_match_nhwc(rp, rs, mt, b_p, hw_p, b_s, hw_s, c, mode, eps, mw, mws, st));
+    return rotate_inverse(mt, false, R, out, n_p, c, content, strength, st);
+}
+
+// library-owned device scratch for the *_host entry points
+struct HostScratch {
+    std::mutex mu;
+    void *buf = nullptr;
+    size_t cap = 0;
+    int dev = -1;
+    int ensure(size_t bytes) {
+        int d = 0;
+        OPTEX_CUDA(cudaGetDevice(&d));
+        if (buf && (d != dev || cap < bytes)) {
+            cudaFree(buf);
+            buf = nullptr;
+            cap = 0;
+        }
+        if (!buf) {
+            OPTEX_CUDA(cudaMalloc(&buf, bytes));
+            cap = bytes;
+            dev = d;
+        }
+        return OPTEX_OK;
+    }
+};
+static HostScratch g_host;
+
+}  // namespace optex
+
+using namespace optex;
+
+extern "C" int optex_abi_version(void) { return OPTEX_ABI_VERSION; }
+extern "C" const char *optex_last_error(void) { return g_err; }
+extern "C" int optex_device_check(void) { return require_sm100(); }
+extern "C" uint64_t optex_launch_count(void) { return g_launches.load(); }
+extern "C" int optex_set_gemm_mode(int m) {
+    if (m < OPTEX_GEMM_AUTO || m > OPTEX_GEMM_TF32) {
+        set_error("optex_set_gemm_mode: unknown mode %d", m);
+        return OPTEX_EINVAL;
+    }
+    g_gemm_mode.store(m);
+    return OPTEX_OK;
+}
+extern "C" int optex_get_gemm_mode(void) { return g_gemm_mode.load(); }
+
+extern "C" size_t optex_ot_workspace_bytes(int64_t n_p, int64_t n_s, int c, int mode) {
+    if (n_p < 1 || n_s < 1 || c < 1 || !valid_mode(mode)) return 0;
+    size_t b = align_up(sizeof(float) * (size_t)n_p * c, 256) + align_up(sizeof(float) * (size_t)n_s * c, 256);
+    if (!per_channel(mode)) b += align_up(sizeof(float) * (size_t)n_p * c, 256);
+    return b + align_up(match_ws_bytes(n_p, n_s, c, mode), 256);
+}
+
+extern "C" int optex_ot_step(const float *P, const float *S, const float *R, float *out, int b_p, int64_t hw_p,
+                             int b_s, int64_t hw_s, int c, int mode, float eps, const float *content,
+                             float content_strength, void *workspace, size_t workspace_bytes, void *stream) {
+    OPTEX_TRY(require_sm100());
+    OPTEX_TRY(check_step_args("optex_ot_step", P, S, out, b_p, hw_p, b_s, hw_s, c, mode));
+    if (!R) {
+        set_error("optex_ot_step: NULL rotation");
+        return OPTEX_EINVAL;
+    }
+    if (out == P || out == S) {
+        set_error("optex_ot_step: out must not alias an input (use optex_ot_loop for in-place iteration)");
+        return OPTEX_EINVAL;
+    }
+    return ot_step_impl(P, S, R, out, b_p, hw_p, b_s, hw_s, c, mode, eps, content, content_strength, workspace,
+                        workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int optex_ot_step_host(const float *P, const float *S, const float *R, float *out, int b_p,
+                                  int64_t hw_p, int b_s, int64_t hw_s, int c, int mode, float eps,
+                                  const float *content, float content_strength, uint64_t seed,
+                                  uint64_t counter, void *stream) {
+    OPTEX_TRY(require_sm100());
+    OPTEX_TRY(check_step_args("optex_ot_step_host", P, S, out, b_p, hw_p, b_s, hw_s, c, mode));
+    const int64_t n_p = (int64_t)b_p * hw_p, n_s = (int64_t)b_s * hw_s;
+    const size_t bp = align_up(sizeof(float) * (size_t)n_p * c, 256), bs = align_up(sizeof(float) * (size_t)n_s * c, 256);
+    const size_t br = align_up(sizeof(float) * (size_t)c * c, 256);
+    const size_t step_ws = optex_ot_workspace_bytes(n_p, n_s, c, mode);
+    const size_t rot_ws = R ? 0 : align_up(rotation_ws_bytes(c, 1), 256);
+    const size_t ws = step_ws + rot_ws;
+    std::lock_guard<std::mutex> lock(g_host.mu);
+    OPTEX_TRY(g_host.ensure(2 * bp + bs + br + (content ? bp : 0) + ws));
+    char *base = (char *)g_host.buf;
+    float *dP = (float *)base, *dO = (float *)(base + bp), *dS = (float *)(base + 2 * bp);
+    float *dR = (float *)(base + 2 * bp + bs);
+    float *dC = content ? (float *)(base + 2 * bp + bs + br) : nullptr;
+    void *dW = base + 2 * bp + bs + br + (content ? bp : 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    OPTEX_CUDA(cudaMemcpyAsync(dP, P, sizeof(float) * n_p * c, cudaMemcpyHostToDevice, st));
+    OPTEX_CUDA(cudaMemcpyAsync(dS, S, sizeof(float) * n_s * c, cudaMemcpyHostToDevice, st));
+    if (R)
+        OPTEX_CUDA(cudaMemcpyAsync(dR, R, sizeof(float) * (size_t)c * c, cudaMemcpyHostToDevice, st));
+    else
+        OPTEX_TRY(random_rotations(dR, c, 1, seed, counter, nullptr, (char *)dW + step_ws, rot_ws, st));
+    if (content) OPTEX_CUDA(cudaMemcpyAsync(dC, content, sizeof(float) * n_p * c, cudaMemcpyHostToDevice, st));
+    OPTEX_TRY(ot_step_impl(dP, dS, dR, dO, b_p, hw_p, b_s, hw_s, c, mode, eps, dC, content_strength, dW, step_ws, st));
+    OPTEX_CUDA(cudaMemcpyAsync(out, dO, sizeof(float) * n_p * c, cudaMemcpyDeviceToHost, st));
+    OPTEX_CUDA(cudaStreamSynchronize(st));
+    return OPTEX_OK;
+}
+
+static const int kRotChunk = 16;
+
+extern "C" size_t optex_ot_loop_workspace_bytes(int64_t n_p, int64_t n_s, int c, int mode) {
+    size_t step = optex_ot_workspace_bytes(n_p, n_s, c, mode);
+    if (!step) return 0;
+    return step + align_up(sizeof(float) * (size_t)kRotChunk * c * c, 256) + align_up(rotation_ws_bytes(c, kRotChunk), 256);
+}
+
+extern "C" int optex_ot_loop(float *feat, const float *S, const float *R_all, int iters, uint64_t seed,
+                             uint64_t first_counter, int b_p, int64_t hw_p, int b_s, int64_t hw_s, int c,
+                             int mode, float eps, const float *content, float content_strength, void *workspace,
+                             size_t workspace_bytes, void *stream) {
+    OPTEX_TRY(require_sm100());
+    OPTEX_TRY(check_step_args("optex_ot_loop", feat, S, feat, b_p, hw_p, b_s, hw_s, c, mode));
+    if (iters < 0) {
+        set_error("optex_ot_loop: iters < 0");
+        return OPTEX_EINVAL;
+    }
+    const int64_t n_p = (int64_t)b_p * hw_p, n_s = (int64_t)b_s * hw_s;
+    const size_t step_ws = optex_ot_workspace_bytes(n_p, n_s, c, mode);
+    Arena ar(workspace, workspace_bytes);
+    void *sw = ar.take<char>(step_ws);
+    float *rbuf = ar.take<float>((size_t)kRotChunk * c * c);
+    size_t rws_bytes = rotation_ws_bytes(c, kRotChunk);
+    void *rws = ar.take<char>(rws_bytes);
+    if (!ar.ok()) {
+        set_error("optex_ot_loop: workspace %zu < %zu bytes", workspace_bytes,
+                  optex_ot_loop_workspace_bytes(n_p, n_s, c, mode));
+        return OPTEX_EWORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int i = 0; i < iters; ++i) {
+        const float *R;
+        if (R_all) {
+            R = R_all + (size_t)i * c * c;
+        } else {
+            if (i % kRotChunk == 0) {
+                int nb = iters - i < kRotChunk ? iters - i : kRotChunk;
+                OPTEX_TRY(random_rotations(rbuf, c, nb, seed, first_counter + (uint64_t)i, nullptr, rws, rws_bytes, st));
+            }
+            R = rbuf + (size_t)(i % kRotChunk) * c * c;
+        }
+        OPTEX_TRY(ot_step_impl(feat, S, R, feat, b_p, hw_p, b_s, hw_s, c, mode, eps, content, content_strength, sw,
+                               step_ws, st));
+    }
+    return OPTEX_OK;
+}
+
+extern "C" size_t optex_hist_match_workspace_bytes(int64_t n_t, int64_t n_s, int c, int mode) {
+    if (n_t < 1 || n_s < 1 || c < 1 || !valid_mode(mode)) return 0;
+    if (per_channel(mode))
+        return align_up(sizeof(float) * (size_t)n_t * c, 256) + align_up(sizeof(float) * (size_t)n_s * c, 256) +
+               align_up(match_ws_bytes(n_t, n_s, c, mode), 256);
+    return align_up(cov_match_ws_bytes(n_t, n_s, c, mode), 256);
+}
+
+extern "C" int optex_hist_match(const float *target, const float *source, float *out, int b_t, int64_t hw_t,
+                                int b_s, int64_t hw_s, int c, int mode, float eps, void *workspace,
+                                size_t workspace_bytes, void *stream) {
+    OPTEX_TRY(require_sm100());
+    OPTEX_TRY(check_step_args("optex_hist_match", target, source, out, b_t, hw_t, b_s, hw_s, c, mode));
+    const int64_t n_t = (int64_t)b_t * hw_t, n_s = (int64_t)b_s * hw_s;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!per_channel(mode))
+        return cov_match_nhwc(target, source, out, b_t, hw_t, b_s, hw_s, c, mode, eps, workspace, workspace_bytes, st);
+    // per-channel modes work channel-major (histmatch.py:6-8 permutes to [c, b, h, w])
+    Arena ar(workspace, workspace_bytes);
+    float *tt = ar.take<float>((size_t)n_t * c);
+    float *ts = ar.take<float>((size_t)n_s * c);
+    size_t mws = match_ws_bytes(n_t, n_s, c, mode);
+    void *mw = ar.take<char>(mws);
+    if (!ar.ok()) {
+        set_error("optex_hist_match: workspace %zu < %zu bytes", workspace_bytes,
+                  optex_hist_match_workspace_bytes(n_t, n_s, c, mode));
+        return OPTEX_EWORKSPACE;
+    }
+    OPTEX_TRY(transpose_f32(target, tt, n_t, c, st));
+    OPTEX_TRY(transpose_f32(source, ts, n_s, c, st));
+    if (mode == OPTEX_MODE_CDF)
+        OPTEX_TRY(optex_cdf_match(tt, ts, tt, c, n_t, n_s, 256, nullptr, mw, mws, st));
+    else
+        OPTEX_TRY(optex_sort_match(tt, ts, tt, c, n_t, n_s, nullptr, mw, mws, st));
+    return transpose_f32(tt, out, c, n_t, st);
+}
+
+extern "C" int optex_rotate_forward(const float *X, const float *R, float *Xt, int64_t n, int c, void *stream) {
+    OPTEX_TRY(require_sm100());
+    if (!X || !R || !Xt || n < 1 || c < 1) {
+        set_error("optex_rotate_forward: NULL pointer or empty shape");
+        return OPTEX_EINVAL;
+    }
+    return rotate_forward(X, R, Xt, n, c, true, (cudaStream_t)stream);
+}
+
+extern "C" int optex_rotate_inverse(const float *Mt, const float *R, float *out, int64_t n, int c,
+                                    const float *content, float content_strength, void *stream) {
+    OPTEX_TRY(require_sm100());
+    if (!Mt || !R || !out || n < 1 || c < 1) {
+        set_error("optex_rotate_inverse: NULL pointer or empty shape");
+        return OPTEX_EINVAL;
+    }
+    return rotate_inverse(Mt, true, R, out, n, c, content, content_strength, (cudaStream_t)stream);
+}

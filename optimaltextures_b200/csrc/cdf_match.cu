@@ -1,0 +1,383 @@
+// Per-channel 256-bin CDF matching on channel-major data, bit-exact with the
+// reference's torch-CPU arithmetic.
+//
+//   reference: cdf_match()  histmatch.py:49-69,  interp()  histmatch.py:72-92
+//   arithmetic restated in oracle/cdf_explicit.py (histc / linspace / cumsum /
+//   searchsorted rules of torch 2.11 CPU); every fp32 operation below uses the
+//   round-to-nearest intrinsics so nvcc can neither fuse nor reorder them.
+//
+// The reference runs a Python loop over channels with ~25 launches and >= 2 host
+// syncs per channel.  Here: 4 launches for ALL channels (init, range, histogram,
+// apply), no host sync, grid = (splits, C) sized to fill 148 SMs at any (C, N).
+//
+// Histogramming avoids shared-memory atomics (2 cycles/lane on Blackwell): every
+// thread owns a private byte-counter histogram laid out bank-conflict-free
+// (word w of thread t at [w*NT + t]); counters are flushed with packed 16-bit
+// adds before they can overflow.
+#include "common.cuh"
+
+namespace optex {
+namespace {
+
+constexpr int NT = 256;
+constexpr int MAX_BINS = 1024;
+constexpr int PRIV_MAX_BINS = 512;  // private byte histograms: bins * NT bytes of smem
+
+// ---- element iteration ------------------------------------------------------
+// Calls f(x) for every element of row[beg, end) with 128-bit loads when possible.
+template <typename F>
+__device__ __forceinline__ void for_each(const float *__restrict__ row, int64_t beg, int64_t end,
+                                         bool vec, F f) {
+    if (vec) {  // row 16B-aligned, beg % 4 == 0
+        int64_t nv = (end - beg) >> 2;
+        const float4 *p = reinterpret_cast<const float4 *>(row + beg);
+        for (int64_t i = threadIdx.x; i < nv; i += NT) {
+            float4 v = __ldg(p + i);
+            f(v.x); f(v.y); f(v.z); f(v.w);
+        }
+        for (int64_t i = beg + (nv << 2) + threadIdx.x; i < end; i += NT) f(__ldg(row + i));
+    } else {
+        for (int64_t i = beg + threadIdx.x; i < end; i += NT) f(__ldg(row + i));
+    }
+}
+
+__device__ __forceinline__ void slice_of(int64_t n, int part, int nparts, int64_t &beg, int64_t &end) {
+    int64_t len = ((n + nparts - 1) / nparts + 3) & ~int64_t(3);
+    beg = len * part;
+    end = beg + len;
+    if (beg > n) beg = n;
+    if (end > n) end = n;
+}
+
+// ---- the torch arithmetic ---------------------------------------------------
+// torch.histc bin rule (CPU): int64((x - lo) * bins / (hi - lo)), bin == bins -> bins-1;
+// a degenerate range [v, v] becomes [v-1, v+1].
+struct HistRange {
+    float lo, width, fbins;
+    int bins;
+    __device__ HistRange(float lo_, float hi_, int bins_) : bins(bins_) {
+        if (lo_ == hi_) {
+            lo_ = __fsub_rn(lo_, 1.f);
+            hi_ = __fadd_rn(hi_, 1.f);
+        }
+        lo = lo_;
+        width = __fsub_rn(hi_, lo_);
+        fbins = (float)bins_;
+    }
+    __device__ __forceinline__ int bin(float x) const {
+        float q = __fdiv_rn(__fmul_rn(__fsub_rn(x, lo), fbins), width);
+        int b = (int)q;  // truncation, like the int64 cast
+        b = b >= bins ? bins - 1 : b;
+        return b < 0 ? 0 : b;  // memory safety for NaN only
+    }
+};
+
+// torch.linspace(lo, hi, bins+1)[i], i in 1..bins  (CPU kernel: symmetric, FMA-rounded)
+__device__ __forceinline__ float linspace_at(float lo, float hi, float step, int i, int bins) {
+    int half = (bins + 1) / 2;
+    return i < half ? fmaf(step, (float)i, lo) : fmaf(-step, (float)(bins - i), hi);
+}
+
+// torch.searchsorted(xp, x) (right=False): identical bisection to ATen's cus_lower_bound.
+__device__ __forceinline__ int lower_bound(const float *xp, int len, float x) {
+    int start = 0, end = len;
+    while (start < end) {
+        int mid = start + ((end - start) >> 1);
+        if (!(xp[mid] >= x)) start = mid + 1;
+        else end = mid;
+    }
+    return start;
+}
+
+__device__ __forceinline__ bool finite_f(float f) { return fabsf(f) <= 3.402823466e+38f; }
+
+// histmatch.py:72-92 for one x, given i = searchsorted(xp, x).
+__device__ __forceinline__ float interp_at(float x, const float *xp, const float *fp, int len, int i) {
+    int last = len - 1;
+    i = i > last ? last : i;  // never taken on valid data (x <= xp[last]); memory safety
+    int j = i + 1 > last ? last : i + 1;
+    float xi = xp[i], xj = xp[j], fi = fp[i], fj = fp[j];
+    float slope = __fdiv_rn(__fsub_rn(fj, fi), __fsub_rn(xj, xi));
+    float f = __fadd_rn(__fmul_rn(slope, __fsub_rn(x, xi)), fi);
+    if (!finite_f(f)) {
+        f = __fadd_rn(__fmul_rn(slope, __fsub_rn(x, xj)), fj);
+        if (!finite_f(f)) f = fi;
+    }
+    return f;
+}
+
+// ---- kernels ----------------------------------------------------------------
+__global__ void cdf_init_kernel(uint32_t *minmax, uint32_t *hist, int c, int bins) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 2 * (int64_t)c) minmax[i] = (i & 1) ? 0u : 0xffffffffu;  // [c][0]=min, [c][1]=max
+    if (i < 2 * (int64_t)c * bins) hist[i] = 0u;
+}
+
+// lo = min(t.min(), s.min()); hi = max(t.max(), s.max())     histmatch.py:52-53
+__global__ void __launch_bounds__(NT)
+cdf_range_kernel(const float *__restrict__ t, const float *__restrict__ s, int64_t n_t, int64_t n_s,
+                 uint32_t *__restrict__ minmax, int t_vec, int s_vec) {
+    const int ch = blockIdx.y;
+    float mn = INFINITY, mx = -INFINITY;
+    auto upd = [&](float x) { mn = fminf(mn, x); mx = fmaxf(mx, x); };
+    int64_t b, e;
+    slice_of(n_t, blockIdx.x, gridDim.x, b, e);
+    for_each(t + (int64_t)ch * n_t, b, e, t_vec, upd);
+    slice_of(n_s, blockIdx.x, gridDim.x, b, e);
+    for_each(s + (int64_t)ch * n_s, b, e, s_vec, upd);
+    mn = warp_min(mn);
+    mx = warp_max(mx);
+    __shared__ float smn[NT / 32], smx[NT / 32];
+    if ((threadIdx.x & 31) == 0) { smn[threadIdx.x >> 5] = mn; smx[threadIdx.x >> 5] = mx; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        mn = threadIdx.x < NT / 32 ? smn[threadIdx.x] : INFINITY;
+        mx = threadIdx.x < NT / 32 ? smx[threadIdx.x] : -INFINITY;
+        mn = warp_min(mn);
+        mx = warp_max(mx);
+        if (threadIdx.x == 0 && mn <= mx) {
+            atomicMin(&minmax[2 * ch], f2ord(mn));
+            atomicMax(&minmax[2 * ch + 1], f2ord(mx));
+        }
+    }
+}
+
+// Accumulate one row slice into the block's u32 histogram `acc` (smem, `bins` entries).
+template <bool PRIV>
+__device__ __forceinline__ void hist_slice(const float *__restrict__ row, int64_t beg, int64_t end,
+                                           bool vec, const HistRange &hr, uint32_t *priv,
+                                           uint32_t *acc) {
+    const int tid = threadIdx.x;
+    if (!PRIV) {
+        for_each(row, beg, end, vec, [&](float x) { atomicAdd(&acc[hr.bin(x)], 1u); });
+        return;
+    }
+    const int words = hr.bins >> 2;  // bins % 4 == 0 on this path
+    // 255 elements per thread between flushes: 63 float4 iterations (252) on the vector path
+    const int64_t chunk = (int64_t)NT * 252;
+    for (int64_t cb = beg; cb < end; cb += chunk) {
+        int64_t ce = cb + chunk < end ? cb + chunk : end;
+        for (int w = 0; w < words; ++w) priv[w * NT + tid] = 0u;
+        for_each(row, cb, ce, vec, [&](float x) {
+            int b = hr.bin(x);
+            priv[(b >> 2) * NT + tid] += 1u << ((b & 3) * 8);
+        });
+        __syncthreads();
+        // packed reduce: thread (part, w) sums word w over NT/parts owners, 2 x 16-bit lanes x2
+        const int parts = NT / words >= 1 ? NT / words : 1;
+        for (int item = tid; item < words * parts; item += NT) {
+            int w = item % words, part = item / words;
+            int per = NT / parts;
+            uint32_t even = 0, odd = 0;
+            for (int it = 0; it < per; ++it) {
+                int j = part * per + ((it + (tid & 31)) % per);
+                uint32_t v = priv[w * NT + j];
+                even += v & 0x00ff00ffu;
+                odd += (v >> 8) & 0x00ff00ffu;
+            }
+            atomicAdd(&acc[4 * w + 0], even & 0xffffu);
+            atomicAdd(&acc[4 * w + 1], odd & 0xffffu);
+            atomicAdd(&acc[4 * w + 2], even >> 16);
+            atomicAdd(&acc[4 * w + 3], odd >> 16);
+        }
+        __syncthreads();
+    }
+}
+
+// th = histc(t, bins, lo, hi), sh = histc(s, bins, lo, hi)     histmatch.py:57-58
+template <bool PRIV>
+__global__ void __launch_bounds__(NT)
+cdf_hist_kernel(const float *__restrict__ t, const float *__restrict__ s, int64_t n_t, int64_t n_s,
+                const uint32_t *__restrict__ minmax, uint32_t *__restrict__ hist, int bins, int t_vec,
+                int s_vec) {
+    extern __shared__ uint32_t smem_u32[];
+    uint32_t *acc = smem_u32;             // [2][bins]
+    uint32_t *priv = smem_u32 + 2 * bins;  // [bins/4][NT]  (PRIV only)
+    const int ch = blockIdx.y;
+    for (int i = threadIdx.x; i < 2 * bins; i += NT) acc[i] = 0u;
+    __syncthreads();
+    HistRange hr(ord2f(minmax[2 * ch]), ord2f(minmax[2 * ch + 1]), bins);
+    int64_t b, e;
+    slice_of(n_t, blockIdx.x, gridDim.x, b, e);
+    hist_slice<PRIV>(t + (int64_t)ch * n_t, b, e, t_vec, hr, priv, acc);
+    slice_of(n_s, blockIdx.x, gridDim.x, b, e);
+    hist_slice<PRIV>(s + (int64_t)ch * n_s, b, e, s_vec, hr, priv, acc + bins);
+    __syncthreads();
+    uint32_t *gh = hist + (int64_t)ch * 2 * bins;
+    for (int i = threadIdx.x; i < 2 * bins; i += NT)
+        if (acc[i]) atomicAdd(&gh[i], acc[i]);
+}
+
+// Build edges / CDFs / remap in shared memory from the channel's two histograms.
+//   xs: edges[bins], rm: remap[bins]; scratch tc[bins], sc[bins] (float), cnt[2*bins] (u32)
+__device__ void build_tables(const uint32_t *__restrict__ gh, float lo, float hi, int bins,
+                             float *edges, float *remap, float *tc, float *sc, uint32_t *cnt) {
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 2 * bins; i += NT) cnt[i] = gh[i];
+    __syncthreads();
+    // inclusive prefix sums (exact integers; torch's fp32 cumsum is exact below 2^24)
+    for (int off = 1; off < bins; off <<= 1) {
+        uint32_t a[2 * MAX_BINS / NT];
+        int k = 0;
+        for (int i = tid; i < 2 * bins; i += NT, ++k) {
+            int pos = i >= bins ? i - bins : i;
+            a[k] = pos >= off ? cnt[i - off] : 0u;
+        }
+        __syncthreads();
+        k = 0;
+        for (int i = tid; i < 2 * bins; i += NT, ++k) cnt[i] += a[k];
+        __syncthreads();
+    }
+    const float tot_t = (float)cnt[bins - 1], tot_s = (float)cnt[2 * bins - 1];
+    const float step = __fdiv_rn(__fsub_rn(hi, lo), (float)bins);
+    for (int i = tid; i < bins; i += NT) {
+        tc[i] = __fdiv_rn((float)cnt[i], tot_t);          // histmatch.py:61-62
+        sc[i] = __fdiv_rn((float)cnt[bins + i], tot_s);   // histmatch.py:64-65
+        edges[i] = linspace_at(lo, hi, step, i + 1, bins);  // histmatch.py:59
+    }
+    __syncthreads();
+    for (int i = tid; i < bins; i += NT)                   // histmatch.py:67
+        remap[i] = interp_at(tc[i], sc, edges, bins, lower_bound(sc, bins, tc[i]));
+    __syncthreads();
+}
+
+// matched = interp(t, edges, remap)     histmatch.py:68
+__global__ void __launch_bounds__(NT)
+cdf_apply_kernel(const float *__restrict__ t, float *__restrict__ out, int64_t n_t,
+                 const uint32_t *__restrict__ minmax, const uint32_t *__restrict__ hist, int bins,
+                 float *__restrict__ tables, int vec) {
+    extern __shared__ float smem_f32[];
+    float *edges = smem_f32, *remap = edges + bins, *tc = remap + bins, *sc = tc + bins;
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(sc + bins);
+    const int ch = blockIdx.y;
+    const float lo = ord2f(minmax[2 * ch]), hi = ord2f(minmax[2 * ch + 1]);
+    build_tables(hist + (int64_t)ch * 2 * bins, lo, hi, bins, edges, remap, tc, sc, cnt);
+    if (tables && blockIdx.x == 0)
+        for (int i = threadIdx.x; i < bins; i += NT) {
+            tables[((int64_t)ch * 2 + 0) * bins + i] = edges[i];
+            tables[((int64_t)ch * 2 + 1) * bins + i] = remap[i];
+        }
+    int64_t b, e;
+    slice_of(n_t, blockIdx.x, gridDim.x, b, e);
+    const float *row = t + (int64_t)ch * n_t;
+    float *orow = out + (int64_t)ch * n_t;
+    auto one = [&](float x) { return interp_at(x, edges, remap, bins, lower_bound(edges, bins, x)); };
+    if (vec) {
+        int64_t nv = (e - b) >> 2;
+        const float4 *p = reinterpret_cast<const float4 *>(row + b);
+        float4 *q = reinterpret_cast<float4 *>(orow + b);
+        for (int64_t i = threadIdx.x; i < nv; i += NT) {
+            float4 v = __ldg(p + i);
+            q[i] = make_float4(one(v.x), one(v.y), one(v.z), one(v.w));
+        }
+        for (int64_t i = b + (nv << 2) + threadIdx.x; i < e; i += NT) orow[i] = one(__ldg(row + i));
+    } else {
+        for (int64_t i = b + threadIdx.x; i < e; i += NT) orow[i] = one(__ldg(row + i));
+    }
+}
+
+__global__ void interp_kernel(const float *__restrict__ x, const float *__restrict__ xp,
+                              const float *__restrict__ fp, float *__restrict__ out, int64_t n, int len) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = interp_at(x[i], xp, fp, len, lower_bound(xp, len, x[i]));
+}
+
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+int cdf_splits(int c, int64_t n) {
+    // enough CTAs for ~4 resident blocks on each of the SMs, at least 8K elements per CTA
+    int64_t want = (4LL * sm_count() + c - 1) / c;
+    int64_t cap = (n + 8191) / 8192;
+    int64_t s = want < cap ? want : cap;
+    return (int)(s < 1 ? 1 : s);
+}
+
+}  // namespace optex
+
+using namespace optex;
+
+extern "C" size_t optex_cdf_match_workspace_bytes(int c, int bins) {
+    if (c <= 0 || bins <= 0) return 0;
+    return align_up(sizeof(uint32_t) * 2 * (size_t)c, 256) + align_up(sizeof(uint32_t) * 2 * (size_t)c * bins, 256);
+}
+
+extern "C" int optex_cdf_match(const float *target, const float *source, float *out, int c, int64_t n_t,
+                               int64_t n_s, int bins, float *tables, void *workspace,
+                               size_t workspace_bytes, void *stream) {
+    OPTEX_TRY(require_sm100());
+    if (!target || !source || !out || c < 0 || n_t < 0 || n_s < 0) {
+        set_error("optex_cdf_match: NULL pointer or negative size");
+        return OPTEX_EINVAL;
+    }
+    if (bins < 1 || bins > MAX_BINS) {
+        set_error("optex_cdf_match: bins=%d outside [1, %d]", bins, MAX_BINS);
+        return OPTEX_EINVAL;
+    }
+    if (c == 0 || n_t == 0) return OPTEX_OK;  // empty target: nothing to write (torch: empty loop / empty rows)
+    if (n_s == 0) {
+        set_error("optex_cdf_match: empty source (the reference raises on min() of an empty tensor)");
+        return OPTEX_EINVAL;
+    }
+    if (n_t >= (1 << 24) || n_s >= (1 << 24)) {
+        set_error("optex_cdf_match: n >= 2^24 per channel (fp32 cumsum of the reference stops being exact)");
+        return OPTEX_ESIZE;
+    }
+    if (c > 65535) {
+        set_error("optex_cdf_match: c > 65535");
+        return OPTEX_ESIZE;
+    }
+    Arena ar(workspace, workspace_bytes);
+    uint32_t *minmax = ar.take<uint32_t>(2 * (size_t)c);
+    uint32_t *hist = ar.take<uint32_t>(2 * (size_t)c * bins);
+    if (!ar.ok()) {
+        set_error("optex_cdf_match: workspace %zu < %zu", workspace_bytes, optex_cdf_match_workspace_bytes(c, bins));
+        return OPTEX_EWORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int t_vec = aligned16(target) && (n_t % 4 == 0);
+    const int s_vec = aligned16(source) && (n_s % 4 == 0);
+    const int o_vec = t_vec && aligned16(out);
+    const int64_t n_big = n_t > n_s ? n_t : n_s;
+    dim3 grid((unsigned)cdf_splits(c, n_big), (unsigned)c);
+
+    int64_t init_n = 2LL * c * bins;
+    cdf_init_kernel<<<(unsigned)((init_n + 255) / 256), 256, 0, st>>>(minmax, hist, c, bins);
+    OPTEX_LAUNCH_CHECK("cdf_init_kernel");
+    cdf_range_kernel<<<grid, NT, 0, st>>>(target, source, n_t, n_s, minmax, t_vec, s_vec);
+    OPTEX_LAUNCH_CHECK("cdf_range_kernel");
+    const bool priv = (bins % 4 == 0) && bins <= PRIV_MAX_BINS;
+    if (priv) {
+        size_t smem = sizeof(uint32_t) * (2 * (size_t)bins + (size_t)(bins / 4) * NT);
+        static bool attr_done = false;
+        if (!attr_done) {
+            OPTEX_CUDA(cudaFuncSetAttribute(cdf_hist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)(sizeof(uint32_t) * (2 * PRIV_MAX_BINS + (PRIV_MAX_BINS / 4) * NT))));
+            attr_done = true;
+        }
+        cdf_hist_kernel<true><<<grid, NT, smem, st>>>(target, source, n_t, n_s, minmax, hist, bins, t_vec, s_vec);
+    } else {
+        cdf_hist_kernel<false><<<grid, NT, sizeof(uint32_t) * 2 * bins, st>>>(target, source, n_t, n_s, minmax,
+                                                                             hist, bins, t_vec, s_vec);
+    }
+    OPTEX_LAUNCH_CHECK("cdf_hist_kernel");
+    dim3 grid_a((unsigned)cdf_splits(c, n_t), (unsigned)c);
+    cdf_apply_kernel<<<grid_a, NT, sizeof(float) * 6 * bins, st>>>(target, out, n_t, minmax, hist, bins, tables,
+                                                                  o_vec);
+    OPTEX_LAUNCH_CHECK("cdf_apply_kernel");
+    return OPTEX_OK;
+}
+
+extern "C" int optex_interp(const float *x, const float *xp, const float *fp, float *out, int64_t n, int len,
+                            void *stream) {
+    OPTEX_TRY(require_sm100());
+    if (!x || !xp || !fp || !out || n < 0 || len < 1) {
+        set_error("optex_interp: NULL pointer, n < 0 or len < 1");
+        return OPTEX_EINVAL;
+    }
+    if (n == 0) return OPTEX_OK;
+    interp_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, xp, fp, out, n, len);
+    OPTEX_LAUNCH_CHECK("interp_kernel");
+    return OPTEX_OK;
+}

@@ -1,0 +1,110 @@
+// Shared helpers for the optex_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/optex_b200.h"
+
+namespace optex {
+
+// ---- error plumbing ---------------------------------------------------------
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what);  // records + returns OPTEX_ECUDA
+void count_launch(int n = 1);
+int require_sm100();  // OPTEX_OK or OPTEX_EDEVICE
+int sm_count();
+
+#define OPTEX_CUDA(call)                                           \
+    do {                                                           \
+        cudaError_t _e = (call);                                   \
+        if (_e != cudaSuccess) return optex::cuda_fail(_e, #call); \
+    } while (0)
+
+#define OPTEX_LAUNCH_CHECK(name)                                   \
+    do {                                                           \
+        optex::count_launch();                                     \
+        cudaError_t _e = cudaGetLastError();                       \
+        if (_e != cudaSuccess) return optex::cuda_fail(_e, name);  \
+    } while (0)
+
+#define OPTEX_TRY(expr)                   \
+    do {                                  \
+        int _rc = (expr);                 \
+        if (_rc != OPTEX_OK) return _rc;  \
+    } while (0)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Bump allocator over the caller's workspace.
+struct Arena {
+    char *base;
+    size_t cap, off;
+    Arena(void *p, size_t n) : base((char *)p), cap(n), off(0) {}
+    template <typename T>
+    T *take(size_t count) {
+        size_t bytes = align_up(count * sizeof(T), 256);
+        T *r = (T *)(base + off);
+        off += bytes;
+        return r;
+    }
+    bool ok() const { return base != nullptr && off <= cap; }
+};
+
+// ---- device helpers ---------------------------------------------------------
+// Order-preserving float <-> uint32 (for atomicMin/Max and radix/bitonic keys).
+__device__ __forceinline__ uint32_t f2ord(float f) {
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---- internal entry points shared between translation units ------------------
+// GEMM:  D[m, n] = sum_k A(m,k) * B(k,n)
+//   a_kmajor : A(m,k) = A[m*lda + k]  else A[k*lda + m]
+//   b_kmajor : B(k,n) = B[n*ldb + k]  else B[k*ldb + n]
+//   d_trans  : D(m,n) -> D[n*ldd + m] else D[m*ldd + n]
+//   blend    : if non-null (same indexing as D, not transposed):
+//              d += strength * (blend - d)          (optex.py:117)
+int sgemm_simt(const float *A, int64_t lda, bool a_kmajor, const float *B, int64_t ldb,
+               bool b_kmajor, float *D, int64_t ldd, bool d_trans, int64_t M, int64_t N,
+               int64_t K, const float *blend, float strength, float alpha, cudaStream_t st);
+
+int transpose_f32(const float *in, float *out, int64_t rows, int64_t cols, cudaStream_t st);
+
+// rotation.cu: a batch of Haar SO(c) matrices R[batch][c][c] from (seed, first_counter + b)
+size_t rotation_ws_bytes(int c, int batch);
+int random_rotations(float *R, int c, int batch, uint64_t seed, uint64_t first_counter, const double *gauss,
+                     void *workspace, size_t workspace_bytes, cudaStream_t st);
+
+// cov_match.cu: closed-form Gaussian matching (histmatch.py:13-44) on NHWC-flattened data.
+//   out[n, c] = (X - mu_t) T^T + mu_s ;  T from chol / pca / sym of the two covariances
+size_t cov_match_ws_bytes(int64_t n_t, int64_t n_s, int c, int mode);
+int cov_match_nhwc(const float *target, const float *source, float *out, int b_t, int64_t hw_t, int b_s,
+                   int64_t hw_s, int c, int mode, float eps, void *workspace, size_t workspace_bytes,
+                   cudaStream_t st);
+
+}  // namespace optex

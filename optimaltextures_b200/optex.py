@@ -1,0 +1,208 @@
+"""Drop-in for the hot-path functions of the reference's ``optex`` module (/root/reference/optex.py).
+
+    optimal_transport(pastiche_feature, style_feature, hist_mode)   optex.py:167-177
+    random_rotation(N, device, impl)                                optex.py:142-164
+    ot_loop(...)                                                    optex.py:112-117 (the inner loop)
+
+Additive keyword arguments (the reference draws its rotation internally from numpy's global RNG,
+which makes value parity impossible): ``rotation=`` injects the matrix, ``content=`` /
+``content_strength=`` fuse the in-loop content blend (optex.py:115-117) into the inverse rotation.
+``hist_mode="sort"`` selects the exact per-channel 1-D OT (not in the reference).
+
+`install(module)` rebinds a loaded reference ``optex`` module to these functions.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import itertools
+from typing import Optional
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from . import histmatch as _histmatch
+from ._runtime import call, f32c, ptr, require_cuda, stream_ptr, workspace
+
+_seed = 0
+_counter = itertools.count()
+
+
+def manual_seed(seed: int) -> None:
+    """Seed the on-device rotation stream (Philox key).  The reference's --seed does NOT control its
+    rotations (numpy's global RNG, optex.py:149 vs :253); here it does."""
+    global _seed, _counter
+    _seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    _counter = itertools.count()
+
+
+def set_gemm_mode(mode: str) -> None:
+    """Rotation-GEMM arithmetic: "auto" | "fp32" (SIMT FFMA) | "tf32x3" (tcgen05, fp32-grade) | "tf32"."""
+    call("optex_set_gemm_mode", _lib.GEMM_MODES[mode])
+
+
+def random_rotation(N: int, device="cuda", impl: str = "device", seed: Optional[int] = None,
+                    counter: Optional[int] = None, gauss: Optional[Tensor] = None) -> Tensor:
+    """reference: optex.py:142-164.  Haar SO(N) matrix, fp32 [N, N] on `device`.
+
+    impl="device" (default): Philox normals + Householder construction in fp64 on the GPU (the
+    reference's impl="torch" algorithm).  impl="scipy": the reference's live branch, on the host,
+    for callers that want scipy's stream (slow: 35 ms at N=512)."""
+    dev = torch.device(device)
+    if impl == "scipy":
+        from scipy.stats import special_ortho_group
+
+        return torch.tensor(special_ortho_group.rvs(N), device=dev).float()
+    if dev.type != "cuda":
+        raise RuntimeError("random_rotation(impl='device') generates on a B200; pass a cuda device")
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    out = torch.empty(N, N, dtype=torch.float32, device=dev)
+    nbytes = _lib.lib().optex_rotation_workspace_bytes(N)
+    wsb = workspace(dev, nbytes)
+    g = None
+    if gauss is not None:
+        g = gauss.to(device=dev, dtype=torch.float64).contiguous()
+        if tuple(g.shape) != (max(N - 1, 0), N):
+            raise ValueError(f"gauss must be [N-1, N], got {tuple(g.shape)}")
+    with torch.cuda.device(dev):
+        call("optex_random_rotation", ptr(out), N, _seed if seed is None else int(seed),
+             next(_counter) if counter is None else int(counter), ptr(g), ptr(wsb), wsb.numel(), stream_ptr(dev))
+    return out
+
+
+def _nhwc_dims(x: Tensor):
+    if x.dim() != 4:
+        raise ValueError(f"expected an NHWC feature tensor [b,h,w,c], got shape {tuple(x.shape)}")
+    b, h, w, c = x.shape
+    return b, h * w, c
+
+
+def optimal_transport(pastiche_feature: Tensor, style_feature: Tensor, hist_mode: str, *,
+                      rotation: Optional[Tensor] = None, content: Optional[Tensor] = None,
+                      content_strength: float = 0.0, eps: float = 1.0) -> Tensor:
+    """reference: optex.py:167-177.  One sliced-OT step; returns a NEW contiguous [b,h,w,c] tensor."""
+    dev = require_cuda(pastiche_feature, style_feature, rotation, content)
+    b, hw, c = _nhwc_dims(pastiche_feature)
+    bs, hws, cs = _nhwc_dims(style_feature)
+    if cs != c:
+        raise ValueError(f"channel mismatch: pastiche {c} vs style {cs}")
+    p, s = f32c(pastiche_feature), f32c(style_feature)
+    if rotation is None:
+        rotation = random_rotation(c, dev)
+    r = f32c(rotation)  # `.to(pastiche_feature)` in the reference: float64 scipy matrix -> fp32
+    if tuple(r.shape) != (c, c):
+        raise ValueError(f"rotation must be [{c}, {c}], got {tuple(r.shape)}")
+    ct = None
+    if content is not None:
+        if content.shape != pastiche_feature.shape:
+            raise ValueError("content must have the pastiche's shape")
+        ct = f32c(content)
+    out = torch.empty_like(p)
+    m = _lib.mode_id(hist_mode)
+    nbytes = _lib.lib().optex_ot_workspace_bytes(b * hw, bs * hws, c, m)
+    wsb = workspace(dev, nbytes)
+    with torch.cuda.device(dev):
+        call("optex_ot_step", ptr(p), ptr(s), ptr(r), ptr(out), b, hw, bs, hws, c, m, float(eps), ptr(ct),
+             float(content_strength), ptr(wsb), wsb.numel(), stream_ptr(dev))
+    return out.to(pastiche_feature.dtype)
+
+
+def ot_loop(pastiche_feature: Tensor, style_feature: Tensor, hist_mode: str, iters: int, *,
+            rotations: Optional[Tensor] = None, content: Optional[Tensor] = None, content_strength: float = 0.0,
+            eps: float = 1.0, seed: Optional[int] = None, first_counter: Optional[int] = None) -> Tensor:
+    """reference: optex.py:112-117 - `iters` OT steps (+ content blend) as one native call.
+
+    rotations: optional [iters, c, c]; otherwise generated on the device, `iters` at a time."""
+    dev = require_cuda(pastiche_feature, style_feature, rotations, content)
+    b, hw, c = _nhwc_dims(pastiche_feature)
+    bs, hws, _ = _nhwc_dims(style_feature)
+    feat = f32c(pastiche_feature).clone()
+    s = f32c(style_feature)
+    r = None
+    if rotations is not None:
+        r = f32c(rotations)
+        if tuple(r.shape) != (iters, c, c):
+            raise ValueError(f"rotations must be [{iters}, {c}, {c}]")
+    ct = f32c(content) if content is not None else None
+    m = _lib.mode_id(hist_mode)
+    nbytes = _lib.lib().optex_ot_loop_workspace_bytes(b * hw, bs * hws, c, m)
+    wsb = workspace(dev, nbytes)
+    if first_counter is None:
+        first_counter = next(_counter)
+        for _ in range(max(iters - 1, 0)):
+            next(_counter)
+    with torch.cuda.device(dev):
+        call("optex_ot_loop", ptr(feat), ptr(s), ptr(r), int(iters), _seed if seed is None else int(seed),
+             int(first_counter), b, hw, bs, hws, c, m, float(eps), ptr(ct), float(content_strength), ptr(wsb),
+             wsb.numel(), stream_ptr(dev))
+    return feat
+
+
+def random_rotations(N: int, count: int, device="cuda", seed: Optional[int] = None,
+                     first_counter: int = 0) -> Tensor:
+    """`count` Haar SO(N) matrices [count, N, N] in one batched launch pair (see `random_rotation`)."""
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("random_rotations generates on a B200; pass a cuda device")
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    out = torch.empty(count, N, N, dtype=torch.float32, device=dev)
+    wsb = workspace(dev, _lib.lib().optex_rotations_workspace_bytes(N, count))
+    with torch.cuda.device(dev):
+        call("optex_random_rotations", ptr(out), N, count, _seed if seed is None else int(seed), int(first_counter),
+             None, ptr(wsb), wsb.numel(), stream_ptr(dev))
+    return out
+
+
+def optimal_transport_host(pastiche, style, rotation, hist_mode: str, content=None, content_strength: float = 0.0,
+                           eps: float = 1.0, out=None, seed: Optional[int] = None, counter: int = 0):
+    """The same step through the HOST-buffer entry point (`optex_ot_step_host`): CPU tensors in,
+    CPU tensor out, H2D/D2H inside the call.  This is what a non-torch caller of the C-ABI gets.
+    rotation=None draws the rotation on the device from (seed, counter), like the reference draws its own."""
+    for t in (pastiche, style, rotation, content):
+        if t is not None and (t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous()):
+            raise ValueError("optimal_transport_host takes contiguous fp32 CPU tensors")
+    b, hw, c = _nhwc_dims(pastiche)
+    bs, hws, _ = _nhwc_dims(style)
+    if out is None:
+        out = torch.empty_like(pastiche)
+    call("optex_ot_step_host", ptr(pastiche), ptr(style), ptr(rotation), ptr(out), b, hw, bs, hws, c,
+         _lib.mode_id(hist_mode), float(eps), ptr(content), float(content_strength),
+         _seed if seed is None else int(seed), int(counter), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    return out
+
+
+def rotate_forward(x: Tensor, rotation: Tensor) -> Tensor:
+    """(x @ R)^T as channel-major [c, n] (optex.py:170-171 + the permute of histmatch.py:6-8)."""
+    dev = require_cuda(x, rotation)
+    xc, r = f32c(x), f32c(rotation)
+    c = xc.shape[-1]
+    n = xc.numel() // c
+    out = torch.empty(c, n, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        call("optex_rotate_forward", ptr(xc), ptr(r), ptr(out), n, c, stream_ptr(dev))
+    return out
+
+
+def rotate_inverse(mt: Tensor, rotation: Tensor, content: Optional[Tensor] = None,
+                   content_strength: float = 0.0) -> Tensor:
+    """mt [c, n] channel-major -> (mt^T @ R^T) [n, c] (optex.py:175), optional blend (optex.py:117)."""
+    dev = require_cuda(mt, rotation, content)
+    m, r = f32c(mt), f32c(rotation)
+    c, n = m.shape
+    out = torch.empty(n, c, dtype=torch.float32, device=dev)
+    ct = f32c(content) if content is not None else None
+    with torch.cuda.device(dev):
+        call("optex_rotate_inverse", ptr(m), ptr(r), ptr(out), n, c, ptr(ct), float(content_strength),
+             stream_ptr(dev))
+    return out
+
+
+def install(reference_optex_module) -> None:
+    """Rebind a loaded reference ``optex`` module to the B200 path.  Both names must be patched:
+    ``optex`` did `from histmatch import hist_match` (optex.py:9), so patching ``histmatch`` alone
+    would not reach `mix_style_features` (optex.py:200-201)."""
+    reference_optex_module.optimal_transport = optimal_transport
+    reference_optex_module.hist_match = _histmatch.hist_match
+    reference_optex_module.random_rotation = random_rotation

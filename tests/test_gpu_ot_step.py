@@ -1,0 +1,168 @@
+"""GPU parity: rotation GEMMs, the whole OT step, the inner loop and the rotation generator."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ot_oracle, rotation as rot_oracle, sort_oracle
+
+pytestmark = pytest.mark.gpu
+
+T = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+OT_CASES = ["sq16", "ragged23", "batch2", "batch2_s1", "wide64", "rgb_ties"]
+GEMM_MODES = ["fp32", "auto"]
+
+# fp32 tolerance of one OT step on unit-scale features (stated here, used below):
+#   rotation GEMMs: |err| <= 2e-5 * scale  (fp32 accumulation-order differences only)
+#   per-channel modes are DISCONTINUOUS in their input at bin edges / rank swaps, so a last-bit
+#   difference in a rotated value can move one output by a whole bin: the bulk must agree to
+#   BULK_TOL and at most OUTLIER_FRAC of the elements may differ by more.
+GEMM_TOL = 2e-5
+BULK_TOL = 2e-4
+OUTLIER_FRAC = 5e-3
+COV_TOL = 5e-4
+
+
+@pytest.fixture(scope="module")
+def ob():
+    import optimaltextures_b200 as ob
+
+    return ob
+
+
+@pytest.fixture(params=GEMM_MODES)
+def gemm_mode(request, ob):
+    ob.set_gemm_mode(request.param)
+    yield request.param
+    ob.set_gemm_mode("auto")
+
+
+def close_in_bulk(out, ref, tol=BULK_TOL, frac=OUTLIER_FRAC):
+    out, ref = np.asarray(out, dtype=np.float64), np.asarray(ref, dtype=np.float64)
+    scale = max(1.0, float(np.abs(ref).max()))
+    bad = np.abs(out - ref) > tol * scale
+    assert bad.mean() <= frac, f"{bad.mean():.4%} of elements differ by more than {tol * scale:g}"
+
+
+@pytest.mark.parametrize("n,c", [(64, 16), (120, 23), (4096, 64), (16384, 512), (1000, 181), (333, 3)])
+def test_rotation_gemms_match_fp32_matmul(ob, gemm_mode, n, c):
+    g = torch.Generator().manual_seed(n + c)
+    x = torch.relu(torch.randn(n, c, generator=g))
+    r = T(rot_oracle.haar_rotation_qr(c, 1)).float()
+    ref = (x.double() @ r.double())
+    xt = ob.rotate_forward(x.cuda(), r.cuda())
+    assert xt.shape == (c, n)
+    scale = float(ref.abs().max())
+    assert float((xt.cpu().double().T - ref).abs().max()) <= GEMM_TOL * scale
+    back = ob.rotate_inverse(xt, r.cuda())
+    assert float((back.cpu().double() - ref @ r.double().T).abs().max()) <= 2 * GEMM_TOL * scale
+    # fused content blend (optex.py:117)
+    content = torch.randn(n, c, generator=g)
+    blended = ob.rotate_inverse(xt, r.cuda(), content=content.cuda(), content_strength=0.25)
+    expect = back.cpu() + 0.25 * (content - back.cpu())
+    np.testing.assert_array_equal(blended.cpu().numpy(), expect.numpy())
+
+
+@pytest.mark.parametrize("name", OT_CASES)
+def test_ot_step_cdf_vs_reference_golden(ob, golden, gemm_mode, name):
+    g = golden("ot_step")
+    t, s, rot = T(g[f"{name}_t"]), T(g[f"{name}_s"]), T(g[f"{name}_rot"])
+    out = ob.optimal_transport(t.cuda(), s.cuda(), "cdf", rotation=rot.cuda())
+    assert out.shape == t.shape and out.is_contiguous()
+    close_in_bulk(out.cpu().numpy(), g[f"{name}_out_cdf"])
+
+
+@pytest.mark.parametrize("name", OT_CASES)
+def test_ot_step_cdf_is_bit_exact_given_the_same_rotated_features(ob, golden, name):
+    """Decomposed parity: GPU rotate -> (GPU cdf vs CPU oracle cdf on the SAME rotated values)."""
+    g = golden("ot_step")
+    t, s, rot = T(g[f"{name}_t"]), T(g[f"{name}_s"]), T(g[f"{name}_rot"]).float()
+    rp, rs = ob.rotate_forward(t.cuda(), rot.cuda()), ob.rotate_forward(s.cuda(), rot.cuda())
+    got = ob.cdf_match(rp, rs).cpu()
+    ref = ot_oracle.cdf_match_channels(rp.cpu(), rs.cpu())
+    np.testing.assert_array_equal(got.numpy(), ref.numpy())
+
+
+@pytest.mark.parametrize("name", OT_CASES)
+def test_ot_step_sort_vs_oracle(ob, golden, gemm_mode, name):
+    g = golden("ot_step")
+    t, s, rot = T(g[f"{name}_t"]), T(g[f"{name}_s"]), T(g[f"{name}_rot"])
+    out = ob.optimal_transport(t.cuda(), s.cuda(), "sort", rotation=rot.cuda())
+    close_in_bulk(out.cpu().numpy(), sort_oracle.ot_step_sort(t, s, rot).numpy())
+
+
+@pytest.mark.parametrize("mode", ["cdf", "sort"])
+def test_inner_loop_with_content(ob, golden, mode):
+    g = golden("inner_loop")
+    t, s, content, rots = T(g["t"]), T(g["s"]), T(g["content"]), T(g["rots"])
+    strength = ot_oracle.content_strength_for_layer(0.2, 1)
+    got = ob.ot_loop(t.cuda(), s.cuda(), mode, 3, rotations=rots.float().cuda(), content=content.cuda(),
+                     content_strength=strength)
+    # step-by-step through optimal_transport gives the identical result (same kernels, same order)
+    p = t.cuda()
+    for r in rots:
+        p = ob.optimal_transport(p, s.cuda(), mode, rotation=r.cuda(), content=content.cuda(),
+                                 content_strength=strength)
+    assert torch.equal(got, p)
+    if mode == "cdf":
+        close_in_bulk(got.cpu().numpy(), g["out_cdf"], tol=5e-4, frac=2e-2)
+
+
+def test_ot_step_host_buffers(ob, golden):
+    g = golden("ot_step")
+    t, s, rot = T(g["wide64_t"]), T(g["wide64_s"]), T(g["wide64_rot"]).float()
+    dev_out = ob.optimal_transport(t.cuda(), s.cuda(), "cdf", rotation=rot.cuda())
+    host_out = ob.optimal_transport_host(t, s, rot, "cdf")
+    assert not host_out.is_cuda
+    assert torch.equal(host_out, dev_out.cpu())
+
+
+def test_headline_shape_properties(ob):
+    """conv4_1 @ 1024^2 (N = 16384, C = 512): properties that hold at any size."""
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    p = torch.relu(torch.randn(1, 128, 128, 512, device="cuda", generator=gen))
+    s = torch.relu(1.3 * torch.randn(1, 128, 128, 512, device="cuda", generator=gen) + 0.2)
+    r = ob.random_rotation(512, "cuda", seed=1, counter=0)
+    for mode in ("cdf", "sort"):
+        out = ob.optimal_transport(p, s, mode, rotation=r)
+        assert torch.isfinite(out).all()
+        # sliced-OT property: along every rotated direction the output's marginal is the style's
+        ro, rs = (out.reshape(-1, 512) @ r), (s.reshape(-1, 512) @ r)
+        q = torch.tensor([0.1, 0.5, 0.9], device="cuda")
+        err = (torch.quantile(ro[:, :8], q, dim=0) - torch.quantile(rs[:, :8], q, dim=0)).abs().max()
+        assert float(err) < (0.05 if mode == "cdf" else 2e-3)
+    # identity rotation + matching a block to itself with `sort` is the identity map
+    same = ob.optimal_transport(p, p, "sort", rotation=torch.eye(512, device="cuda"))
+    assert torch.equal(same, p)
+
+
+# ------------------------------------------------------------------ rotations
+@pytest.mark.parametrize("n", [1, 2, 3, 23, 64, 181, 512])
+def test_rotation_matches_householder_oracle(ob, n):
+    rng = np.random.RandomState(n)
+    gauss = rng.normal(size=(max(n - 1, 0), n))
+    got = ob.random_rotation(n, "cuda", gauss=T(gauss)).cpu().double().numpy()
+    ref = rot_oracle.haar_rotation_householder(gauss) if n > 1 else np.ones((1, 1))
+    np.testing.assert_allclose(got, ref, atol=1e-6)      # fp64 construction, fp32 storage
+
+
+@pytest.mark.parametrize("n", [3, 64, 512])
+def test_rotation_is_special_orthogonal_and_reproducible(ob, n):
+    a = ob.random_rotation(n, "cuda", seed=7, counter=3)
+    b = ob.random_rotation(n, "cuda", seed=7, counter=3)
+    c = ob.random_rotation(n, "cuda", seed=7, counter=4)
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    ad = a.double()
+    assert float((ad @ ad.T - torch.eye(n, device="cuda", dtype=torch.float64)).abs().max()) < 5e-7
+    assert abs(float(torch.linalg.det(ad)) - 1.0) < 1e-5
+
+
+def test_rotation_haar_statistics(ob):
+    """Distributional parity with scipy's special_ortho_group (optex.py:149): for Haar SO(n) every
+    entry has mean 0 and variance 1/n, and E[trace] = 0."""
+    n, reps = 16, 400
+    mats = torch.stack([ob.random_rotation(n, "cuda", seed=11, counter=i) for i in range(reps)]).double()
+    assert abs(float(mats.mean())) < 3.0 / np.sqrt(reps * n * n * n)
+    assert abs(float(mats.var()) * n - 1.0) < 0.02
+    tr = mats.diagonal(dim1=1, dim2=2).sum(1)
+    assert abs(float(tr.mean())) < 4.0 / np.sqrt(reps)
+    assert abs(float(tr.var()) - 1.0) < 0.3        # Var[trace] = 1 for Haar O(n)/SO(n)
