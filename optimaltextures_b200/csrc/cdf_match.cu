@@ -167,11 +167,11 @@ __device__ __forceinline__ void hist_slice(const float *__restrict__ row, int64_
         const int parts = NT / words >= 1 ? NT / words : 1;
         for (int item = tid; item < words * parts; item += NT) {
             int w = item % words, part = item / words;
-            int per = NT / parts;
+            int per = (NT + parts - 1) / parts;  // <= 256 owners x 255 counts fits the 16-bit lanes
             uint32_t even = 0, odd = 0;
             for (int it = 0; it < per; ++it) {
                 int j = part * per + ((it + (tid & 31)) % per);
-                uint32_t v = priv[w * NT + j];
+                uint32_t v = j < NT ? priv[w * NT + j] : 0u;
                 even += v & 0x00ff00ffu;
                 odd += (v >> 8) & 0x00ff00ffu;
             }
@@ -307,8 +307,8 @@ extern "C" int optex_cdf_match(const float *target, const float *source, float *
                                int64_t n_s, int bins, float *tables, void *workspace,
                                size_t workspace_bytes, void *stream) {
     OPTEX_TRY(require_sm100());
-    if (!target || !source || !out || c < 0 || n_t < 0 || n_s < 0) {
-        set_error("optex_cdf_match: NULL pointer or negative size");
+    if (c < 0 || n_t < 0 || n_s < 0) {
+        set_error("optex_cdf_match: negative size");
         return OPTEX_EINVAL;
     }
     if (bins < 1 || bins > MAX_BINS) {
@@ -318,6 +318,10 @@ extern "C" int optex_cdf_match(const float *target, const float *source, float *
     if (c == 0 || n_t == 0) return OPTEX_OK;  // empty target: nothing to write (torch: empty loop / empty rows)
     if (n_s == 0) {
         set_error("optex_cdf_match: empty source (the reference raises on min() of an empty tensor)");
+        return OPTEX_EINVAL;
+    }
+    if (!target || !source || !out) {
+        set_error("optex_cdf_match: NULL pointer");
         return OPTEX_EINVAL;
     }
     if (n_t >= (1 << 24) || n_s >= (1 << 24)) {

@@ -1,10 +1,502 @@
+// Rotation GEMMs on the 5th-generation tensor cores (tcgen05, sm_100a).
+//
+//   forward  optex.py:170-171   D[pixel, c_out] = sum_k X[pixel, k] R[k, c_out]
+//   inverse  optex.py:175       D[pixel, j]     = sum_c M(pixel, c) R[j, c]   (+ blend, optex.py:117)
+//
+// Structure (one CTA per 128 x BLOCK_N output tile, 192 threads):
+//   warp 0   TMA producer : cp.async.bulk.tensor -> 128B-swizzled smem stages, mbarrier expect_tx
+//   warp 1   MMA issuer   : one elected lane issues tcgen05.mma.kind::tf32, fp32 accumulator in TMEM,
+//                           tcgen05.commit releases the smem stage / publishes the accumulator
+//   warps 2-5 epilogue    : tcgen05.ld (TMEM -> registers) -> coalesced global stores
+//                           (channel-major for the forward rotation, NHWC + content blend for the inverse)
+//
+// Precision: kind::tf32 keeps 10 mantissa bits.  terms == 3 runs the 3xTF32 split
+//   a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi   (a_hi = tf32(a), a_lo = tf32(a - a_hi), fp32 accumulate)
+// which restores fp32-grade products (the parity tests hold it to the fp32 tolerance);
+// terms == 1 is plain TF32, the reference's own CUDA default (optex.py:248-249).
+//
+// Both operand majors are used without any transposition pass:
+//   K-major  (X[n, k], R[j, c])   : 2-D tensor map, box {32 k, rows}            -> canonical K-major SW128
+//   MN-major (R[k, c_out], Mt[c, n]): 3-D tensor map {32 mn, k, mn/32}, box {32, 32, rows/32}
+//                                     -> canonical MN-major SW128 (LBO = 4 KB between 32-wide mn blocks)
+#include <cuda.h>
+
+#include <mutex>
+
 #include "gemm_tc.cuh"
+
 namespace optex {
-int gemm_tc_rotate_forward(const float *, const float *, float *, int64_t, int, bool, int, cudaStream_t) {
-    return OPTEX_ENOTSUP;
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 32;  // 32 tf32 = 128 B = one swizzle row
+constexpr int UMMA_K = 8;    // 32 B of K per tcgen05.mma.kind::tf32
+constexpr int MAX_STAGES = 8;
+constexpr int NTHREADS = 192;
+constexpr int SMEM_BUDGET = 227 * 1024 - 4096;  // tiles; + 1 KB alignment slack + ~1 KB static (barriers)
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(pred));
+    return pred != 0;
 }
-int gemm_tc_rotate_inverse(const float *, bool, const float *, float *, int64_t, int, const float *, float, int,
-                           cudaStream_t) {
-    return OPTEX_ENOTSUP;
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done = 0;
+    const uint32_t addr = smem_u32(bar);
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred P;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, P;\n\t}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint64_t *bar, void *dst, int x, int y) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap *map, uint64_t *bar, void *dst, int x, int y, int z) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor), version 1.
+//   K-major operands : LayoutType::SWIZZLE_128B (2), 8-row x 128 B atoms, SBO = 1024 B
+//   MN-major tf32    : LayoutType::SWIZZLE_128B_BASE32B (1) - the ONLY layout the tensor core accepts for
+//                      32-bit MN-major operands: 4 k-rows x 128 B atoms whose 32 B chunks are XOR-ed with the
+//                      row index (TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B), SBO = 512 B, LBO = mn-block pitch
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout_type = 2) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fff);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+    d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+    d |= (uint64_t)layout_type << 61;
+    return d;
+}
+
+struct Params {
+    float *D;
+    int64_t ldd;
+    int64_t M, N, K;
+    const float *blend;
+    float strength;
+    int terms;
+    int stages;
+};
+
+// ------------------------------------------------------------------ the kernel
+template <int BLOCK_N, bool A_MN, bool B_MN, bool D_TRANS>
+__global__ void __launch_bounds__(NTHREADS, 1)
+rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                   const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                   const Params p) {
+    constexpr uint32_t A_TILE = BLOCK_M * BLOCK_K * 4;  // 16 KB
+    constexpr uint32_t B_TILE = BLOCK_N * BLOCK_K * 4;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], accum_bar;
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * BLOCK_M, n0 = blockIdx.y * BLOCK_N;
+    const int nterm_tiles = p.terms == 3 ? 2 : 1;  // hi (+ lo) tiles per operand
+    const uint32_t stage_bytes = nterm_tiles * (A_TILE + B_TILE);
+    const int num_kb = (int)((p.K + BLOCK_K - 1) / BLOCK_K);
+    // 1024-byte alignment of the dynamic smem base (SWIZZLE_128B atoms)
+    uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~uintptr_t(1023));
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA_hi);
+        prefetch_tmap(&tmB_hi);
+        if (p.terms == 3) {
+            prefetch_tmap(&tmA_lo);
+            prefetch_tmap(&tmB_lo);
+        }
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(&accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                         smem_u32(&tmem_base_smem)),
+                     "r"((uint32_t)BLOCK_N)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 0) {
+        // ===== TMA producer
+        if (elect_one()) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % p.stages;
+                const uint32_t ph = (kb / p.stages) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                uint8_t *st = tiles + (size_t)s * stage_bytes;
+                mbar_expect_tx(&full_bar[s], stage_bytes);
+                const int k0 = kb * BLOCK_K;
+                for (int t = 0; t < nterm_tiles; ++t) {
+                    const CUtensorMap *ma = t ? &tmA_lo : &tmA_hi;
+                    const CUtensorMap *mb = t ? &tmB_lo : &tmB_hi;
+                    uint8_t *a_dst = st + t * A_TILE;
+                    uint8_t *b_dst = st + nterm_tiles * A_TILE + t * B_TILE;
+                    if (A_MN) tma_load_3d(ma, &full_bar[s], a_dst, 0, k0, m0 / 32);
+                    else tma_load_2d(ma, &full_bar[s], a_dst, k0, m0);
+                    if (B_MN) tma_load_3d(mb, &full_bar[s], b_dst, 0, k0, n0 / 32);
+                    else tma_load_2d(mb, &full_bar[s], b_dst, k0, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) |
+                               ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BLOCK_N >> 3) << 17) |
+                               ((uint32_t)(BLOCK_M >> 4) << 24);
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const int s = kb % p.stages;
+            const uint32_t ph = (kb / p.stages) & 1;
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t st = smem_u32(tiles + (size_t)s * stage_bytes);
+                const uint32_t a_hi = st, a_lo = st + A_TILE;
+                const uint32_t b_hi = st + nterm_tiles * A_TILE, b_lo = b_hi + B_TILE;
+#pragma unroll
+                for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
+                    // K-major: +32 B per K step inside the 128 B swizzle row; MN-major: +8 k-rows = 1 KB
+                    const uint32_t a_off = A_MN ? kk * 1024u : kk * 32u;
+                    const uint32_t b_off = B_MN ? kk * 1024u : kk * 32u;
+                    const uint32_t a_lbo = A_MN ? 4096u : 16u, b_lbo = B_MN ? 4096u : 16u;
+                    const uint32_t a_sbo = A_MN ? 512u : 1024u, b_sbo = B_MN ? 512u : 1024u;
+                    const uint32_t a_lt = A_MN ? 1u : 2u, b_lt = B_MN ? 1u : 2u;
+                    uint64_t da = make_desc(a_hi + a_off, a_lbo, a_sbo, a_lt);
+                    uint64_t db = make_desc(b_hi + b_off, b_lbo, b_sbo, b_lt);
+                    umma_tf32(tmem_base, da, db, idesc, (kb | kk) != 0);
+                    if (p.terms == 3) {
+                        uint64_t dal = make_desc(a_lo + a_off, a_lbo, a_sbo, a_lt);
+                        uint64_t dbl = make_desc(b_lo + b_off, b_lbo, b_sbo, b_lt);
+                        umma_tf32(tmem_base, da, dbl, idesc, 1u);
+                        umma_tf32(tmem_base, dal, db, idesc, 1u);
+                    }
+                }
+                umma_commit(&empty_bar[s]);                     // smem stage free once these MMAs retire
+                if (kb == num_kb - 1) umma_commit(&accum_bar);  // accumulator complete
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===== epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31
+        const int q = warp & 3;
+        mbar_wait(&accum_bar, 0);
+        tc_fence_after();
+        const int64_t row = (int64_t)m0 + q * 32 + lane;
+#pragma unroll 1
+        for (int col = 0; col < BLOCK_N; col += 32) {
+            if (n0 + col >= p.N) break;
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col, v);
+            if (D_TRANS) {
+                if (row < p.M) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        int64_t n = (int64_t)n0 + col + j;
+                        if (n < p.N) p.D[n * p.ldd + row] = __uint_as_float(v[j]);
+                    }
+                }
+            } else if (row < p.M) {
+                float *dp = p.D + row * p.ldd + n0 + col;
+                const float *bp = p.blend ? p.blend + row * p.ldd + n0 + col : nullptr;
+                if (n0 + col + 32 <= p.N) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                               __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                        if (bp) {
+                            float4 c = __ldg(reinterpret_cast<const float4 *>(bp + j));
+                            o.x = __fadd_rn(o.x, __fmul_rn(p.strength, __fsub_rn(c.x, o.x)));
+                            o.y = __fadd_rn(o.y, __fmul_rn(p.strength, __fsub_rn(c.y, o.y)));
+                            o.z = __fadd_rn(o.z, __fmul_rn(p.strength, __fsub_rn(c.z, o.z)));
+                            o.w = __fadd_rn(o.w, __fmul_rn(p.strength, __fsub_rn(c.w, o.w)));
+                        }
+                        *reinterpret_cast<float4 *>(dp + j) = o;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (n0 + col + j < p.N) {
+                            float o = __uint_as_float(v[j]);
+                            if (bp) o = __fadd_rn(o, __fmul_rn(p.strength, __fsub_rn(__ldg(bp + j), o)));
+                            dp[j] = o;
+                        }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BLOCK_N)
+                     : "memory");
+    }
+}
+
+// a -> (tf32(a), tf32(a - tf32(a)))   round-to-nearest split, both halves exactly representable in tf32
+__global__ void split_tf32_kernel(const float4 *__restrict__ x, float4 *__restrict__ hi, float4 *__restrict__ lo,
+                                  int64_t n4) {
+    auto split = [](float a, float &h, float &l) {
+        uint32_t hb;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(a));
+        h = __uint_as_float(hb);
+        float r = __fsub_rn(a, h);
+        uint32_t lb;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(r));
+        l = __uint_as_float(lb);
+    };
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 v = __ldg(x + i), h, l;
+        split(v.x, h.x, l.x);
+        split(v.y, h.y, l.y);
+        split(v.z, h.z, l.z);
+        split(v.w, h.w, l.w);
+        hi[i] = h;
+        lo[i] = l;
+    }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)sym;
+    });
+    return fn;
+}
+
+// K-major operand: row-major [rows, K]; box {32 k, box_rows}
+int make_map_kmajor(CUtensorMap *map, const float *base, int64_t rows, int64_t K, int box_rows) {
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 4};
+    cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, es,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (K-major [%lld, %lld]) failed: %d", (long long)rows, (long long)K, (int)r);
+        return OPTEX_ECUDA;
+    }
+    return OPTEX_OK;
+}
+// MN-major operand: row-major [K, MN] (MN contiguous, MN % 32 == 0) viewed as {32, K, MN/32}; box {32, 32, box_mn/32}
+int make_map_mnmajor(CUtensorMap *map, const float *base, int64_t K, int64_t MN, int box_mn) {
+    cuuint64_t dims[3] = {32, (cuuint64_t)K, (cuuint64_t)(MN / 32)};
+    cuuint64_t strides[2] = {(cuuint64_t)MN * 4, 128};
+    cuuint32_t box[3] = {32, 32, (cuuint32_t)(box_mn / 32)};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)base, dims, strides, box, es,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (MN-major [%lld, %lld]) failed: %d", (long long)K, (long long)MN, (int)r);
+        return OPTEX_ECUDA;
+    }
+    return OPTEX_OK;
+}
+
+// grow-only device scratch for the hi/lo halves (one per device; calls are stream-ordered on the caller's stream,
+// concurrent use from several streams of one device is not supported)
+struct Scratch {
+    void *buf = nullptr;
+    size_t cap = 0;
+};
+Scratch g_scratch[64];
+std::mutex g_scratch_mu;
+
+int scratch(size_t bytes, float **out) {
+    int dev = 0;
+    OPTEX_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) dev = 63;
+    std::lock_guard<std::mutex> lock(g_scratch_mu);
+    Scratch &s = g_scratch[dev];
+    if (s.cap < bytes) {
+        if (s.buf) {
+            OPTEX_CUDA(cudaDeviceSynchronize());
+            OPTEX_CUDA(cudaFree(s.buf));
+            s.buf = nullptr;
+            s.cap = 0;
+        }
+        OPTEX_CUDA(cudaMalloc(&s.buf, bytes));
+        s.cap = bytes;
+    }
+    *out = (float *)s.buf;
+    return OPTEX_OK;
+}
+
+int split(const float *x, float *hi, float *lo, int64_t n, cudaStream_t st) {
+    int64_t n4 = n / 4;  // callers guarantee n % 4 == 0
+    int blocks = (int)((n4 + 255) / 256);
+    int cap = sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    split_tf32_kernel<<<blocks, 256, 0, st>>>((const float4 *)x, (float4 *)hi, (float4 *)lo, n4);
+    OPTEX_LAUNCH_CHECK("split_tf32_kernel");
+    return OPTEX_OK;
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN, bool D_TRANS>
+int launch(const CUtensorMap &ah, const CUtensorMap &al, const CUtensorMap &bh, const CUtensorMap &bl, Params p,
+           cudaStream_t st) {
+    const uint32_t stage_bytes = (p.terms == 3 ? 2 : 1) * (BLOCK_M * BLOCK_K * 4 + BLOCK_N * BLOCK_K * 4);
+    int stages = SMEM_BUDGET / (int)stage_bytes;
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    p.stages = stages;
+    size_t smem = (size_t)stages * stage_bytes + 1024;
+    auto kern = rotate_gemm_kernel<BLOCK_N, A_MN, B_MN, D_TRANS>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        OPTEX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + 1024));
+        attr_done = true;
+    }
+    dim3 grid((unsigned)((p.M + BLOCK_M - 1) / BLOCK_M), (unsigned)((p.N + BLOCK_N - 1) / BLOCK_N));
+    kern<<<grid, NTHREADS, smem, st>>>(ah, al, bh, bl, p);
+    OPTEX_LAUNCH_CHECK("rotate_gemm_kernel");
+    return OPTEX_OK;
+}
+
+template <bool A_MN, bool B_MN, bool D_TRANS>
+int launch_n(int block_n, const CUtensorMap &ah, const CUtensorMap &al, const CUtensorMap &bh, const CUtensorMap &bl,
+             Params p, cudaStream_t st) {
+    if (block_n == 64) return launch<64, A_MN, B_MN, D_TRANS>(ah, al, bh, bl, p, st);
+    if (block_n == 128) return launch<128, A_MN, B_MN, D_TRANS>(ah, al, bh, bl, p, st);
+    return launch<256, A_MN, B_MN, D_TRANS>(ah, al, bh, bl, p, st);
+}
+
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+inline int pick_block_n(int c) { return c <= 64 ? 64 : (c <= 128 ? 128 : 256); }
+
+}  // namespace
+
+int gemm_tc_rotate_forward(const float *X, const float *R, float *dst, int64_t n, int c, bool transposed, int terms,
+                           cudaStream_t st) {
+    // A = X [n, c] K-major; B = R [k, c_out] MN-major (needs c % 32 == 0)
+    if (c % 32 != 0 || c < 32 || !aligned16(X) || !aligned16(R) || !aligned16(dst) || n < 1 ||
+        n > 0x7fffffffLL / 2 || !encode_fn())
+        return OPTEX_ENOTSUP;
+    const int bn = pick_block_n(c);
+    const float *xh = X, *xl = X, *rh = R, *rl = R;
+    if (terms == 3) {
+        float *buf;
+        size_t nx = (size_t)n * c, nr = (size_t)c * c;
+        OPTEX_TRY(scratch((2 * nx + 2 * nr) * sizeof(float), &buf));
+        float *bxh = buf, *bxl = buf + nx, *brh = buf + 2 * nx, *brl = brh + nr;
+        OPTEX_TRY(split(X, bxh, bxl, (int64_t)nx, st));
+        OPTEX_TRY(split(R, brh, brl, (int64_t)nr, st));
+        xh = bxh; xl = bxl; rh = brh; rl = brl;
+    }
+    CUtensorMap ah, al, bh, bl;
+    OPTEX_TRY(make_map_kmajor(&ah, xh, n, c, BLOCK_M));
+    OPTEX_TRY(make_map_kmajor(&al, xl, n, c, BLOCK_M));
+    OPTEX_TRY(make_map_mnmajor(&bh, rh, c, c, bn));
+    OPTEX_TRY(make_map_mnmajor(&bl, rl, c, c, bn));
+    Params p{dst, transposed ? n : (int64_t)c, n, c, c, nullptr, 0.f, terms, 0};
+    if (transposed) return launch_n<false, true, true>(bn, ah, al, bh, bl, p, st);
+    return launch_n<false, true, false>(bn, ah, al, bh, bl, p, st);
+}
+
+int gemm_tc_rotate_inverse(const float *M, bool m_channel_major, const float *R, float *out, int64_t n, int c,
+                           const float *content, float strength, int terms, cudaStream_t st) {
+    // B(j, k = c) = R[j, c] K-major; A = Mt [c, n] MN-major (needs n % 32 == 0) or M [n, c] K-major
+    if (c % 32 != 0 || c < 32 || !aligned16(M) || !aligned16(R) || !aligned16(out) || (content && !aligned16(content)) ||
+        n < 1 || n > 0x7fffffffLL / 2 || !encode_fn())
+        return OPTEX_ENOTSUP;
+    if (m_channel_major && n % 32 != 0) return OPTEX_ENOTSUP;
+    const int bn = pick_block_n(c);
+    const float *mh = M, *ml = M, *rh = R, *rl = R;
+    if (terms == 3) {
+        float *buf;
+        size_t nx = (size_t)n * c, nr = (size_t)c * c;
+        OPTEX_TRY(scratch((2 * nx + 2 * nr) * sizeof(float), &buf));
+        float *bmh = buf, *bml = buf + nx, *brh = buf + 2 * nx, *brl = brh + nr;
+        OPTEX_TRY(split(M, bmh, bml, (int64_t)nx, st));
+        OPTEX_TRY(split(R, brh, brl, (int64_t)nr, st));
+        mh = bmh; ml = bml; rh = brh; rl = brl;
+    }
+    CUtensorMap ah, al, bh, bl;
+    if (m_channel_major) {
+        OPTEX_TRY(make_map_mnmajor(&ah, mh, c, n, BLOCK_M));
+        OPTEX_TRY(make_map_mnmajor(&al, ml, c, n, BLOCK_M));
+    } else {
+        OPTEX_TRY(make_map_kmajor(&ah, mh, n, c, BLOCK_M));
+        OPTEX_TRY(make_map_kmajor(&al, ml, n, c, BLOCK_M));
+    }
+    OPTEX_TRY(make_map_kmajor(&bh, rh, c, c, bn));
+    OPTEX_TRY(make_map_kmajor(&bl, rl, c, c, bn));
+    Params p{out, (int64_t)c, n, c, c, content, strength, terms, 0};
+    if (m_channel_major) return launch_n<true, false, false>(bn, ah, al, bh, bl, p, st);
+    return launch_n<false, false, false>(bn, ah, al, bh, bl, p, st);
+}
+
 }  // namespace optex

@@ -173,13 +173,17 @@ extern "C" int optex_sort_match(const float *target, const float *source, float 
                                 void *stream) {
     (void)workspace; (void)workspace_bytes;
     OPTEX_TRY(require_sm100());
-    if (!target || !source || !out || c < 0 || n_t < 0 || n_s < 0) {
-        set_error("optex_sort_match: NULL pointer or negative size");
+    if (c < 0 || n_t < 0 || n_s < 0) {
+        set_error("optex_sort_match: negative size");
         return OPTEX_EINVAL;
     }
     if (c == 0 || n_t == 0) return OPTEX_OK;
     if (n_s == 0) {
         set_error("optex_sort_match: empty source");
+        return OPTEX_EINVAL;
+    }
+    if (!target || !source || !out) {
+        set_error("optex_sort_match: NULL pointer");
         return OPTEX_EINVAL;
     }
     int64_t n = n_t > n_s ? n_t : n_s;

@@ -9,7 +9,7 @@ pytestmark = pytest.mark.gpu
 
 T = lambda a: torch.from_numpy(np.ascontiguousarray(a))
 OT_CASES = ["sq16", "ragged23", "batch2", "batch2_s1", "wide64", "rgb_ties"]
-GEMM_MODES = ["fp32", "auto"]
+GEMM_MODES = ["fp32", "auto"]   # auto = tcgen05 3xTF32 where the shape allows, fp32 SIMT otherwise
 
 # fp32 tolerance of one OT step on unit-scale features (stated here, used below):
 #   rotation GEMMs: |err| <= 2e-5 * scale  (fp32 accumulation-order differences only)
@@ -60,6 +60,31 @@ def test_rotation_gemms_match_fp32_matmul(ob, gemm_mode, n, c):
     blended = ob.rotate_inverse(xt, r.cuda(), content=content.cuda(), content_strength=0.25)
     expect = back.cpu() + 0.25 * (content - back.cpu())
     np.testing.assert_array_equal(blended.cpu().numpy(), expect.numpy())
+
+
+@pytest.mark.parametrize("n,c", [(128, 32), (4096, 64), (16384, 512), (4096, 320)])
+def test_tf32_single_pass_mode(ob, n, c):
+    """OPTEX_GEMM_TF32 = the reference's own CUDA default (allow_tf32, optex.py:248-249): 10-bit mantissas."""
+    g = torch.Generator().manual_seed(n + c)
+    x = torch.relu(torch.randn(n, c, generator=g))
+    r = T(rot_oracle.haar_rotation_qr(c, 1)).float()
+    ref = x.double() @ r.double()
+    ob.set_gemm_mode("tf32")
+    try:
+        xt = ob.rotate_forward(x.cuda(), r.cuda())
+    finally:
+        ob.set_gemm_mode("auto")
+    err = float((xt.cpu().double().T - ref).abs().max()) / float(ref.abs().max())
+    assert 1e-5 < err < 3e-3      # really TF32 (not fp32), and no worse than TF32
+
+
+def test_forced_tensor_core_mode_rejects_unsupported_shapes(ob):
+    ob.set_gemm_mode("tf32x3")
+    try:
+        with pytest.raises(ValueError):
+            ob.rotate_forward(torch.zeros(64, 23).cuda(), torch.eye(23).cuda())     # C % 32 != 0
+    finally:
+        ob.set_gemm_mode("auto")
 
 
 @pytest.mark.parametrize("name", OT_CASES)
