@@ -132,29 +132,25 @@ static int ot_step_impl(const float *P, const float *S, const float *R, float *o
                         int b_s, int64_t hw_s, int c, int mode, float eps, const float *content, float strength,
                         void *ws, size_t ws_bytes, cudaStream_t st) {
     const int64_t n_p = (int64_t)b_p * hw_p, n_s = (int64_t)b_s * hw_s;
+    if (!per_channel(mode))  // closed-form modes: rotation folded into C x C products (cov_match.cu)
+        return cov_ot_step(P, S, R, out, b_p, hw_p, b_s, hw_s, c, mode, eps, content, strength, ws, ws_bytes, st);
     Arena ar(ws, ws_bytes);
     float *rp = ar.take<float>((size_t)n_p * c);
     float *rs = ar.take<float>((size_t)n_s * c);
-    float *mt = per_channel(mode) ? rp : ar.take<float>((size_t)n_p * c);
+    float *mt = rp;
     size_t mws = match_ws_bytes(n_p, n_s, c, mode);
     void *mw = ar.take<char>(mws);
     if (!ar.ok()) {
         set_error("optex_ot_step: workspace %zu < %zu bytes", ws_bytes, optex_ot_workspace_bytes(n_p, n_s, c, mode));
         return OPTEX_EWORKSPACE;
     }
-    if (per_channel(mode)) {
-        OPTEX_TRY(rotate_forward(P, R, rp, n_p, c, true, st));
-        OPTEX_TRY(rotate_forward(S, R, rs, n_s, c, true, st));
-        if (mode == OPTEX_MODE_CDF)
-            OPTEX_TRY(optex_cdf_match(rp, rs, mt, c, n_p, n_s, 256, nullptr, mw, mws, st));
-        else
-            OPTEX_TRY(optex_sort_match(rp, rs, mt, c, n_p, n_s, nullptr, mw, mws, st));
-        return rotate_inverse(mt, true, R, out, n_p, c, content, strength, st);
-    }
-    OPTEX_TRY(rotate_forward(P, R, rp, n_p, c, false, st));
-    OPTEX_TRY(rotate_forward(S, R, rs, n_s, c, false, st));
-    OPTEX_TRY(cov_match_nhwc(rp, rs, mt, b_p, hw_p, b_s, hw_s, c, mode, eps, mw, mws, st));
-    return rotate_inverse(mt, false, R, out, n_p, c, content, strength, st);
+    OPTEX_TRY(rotate_forward(P, R, rp, n_p, c, true, st));
+    OPTEX_TRY(rotate_forward(S, R, rs, n_s, c, true, st));
+    if (mode == OPTEX_MODE_CDF)
+        OPTEX_TRY(optex_cdf_match(rp, rs, mt, c, n_p, n_s, 256, nullptr, mw, mws, st));
+    else
+        OPTEX_TRY(optex_sort_match(rp, rs, mt, c, n_p, n_s, nullptr, mw, mws, st));
+    return rotate_inverse(mt, true, R, out, n_p, c, content, strength, st);
 }
 
 // library-owned device scratch for the *_host entry points
@@ -201,8 +197,8 @@ extern "C" int optex_get_gemm_mode(void) { return g_gemm_mode.load(); }
 
 extern "C" size_t optex_ot_workspace_bytes(int64_t n_p, int64_t n_s, int c, int mode) {
     if (n_p < 1 || n_s < 1 || c < 1 || !valid_mode(mode)) return 0;
+    if (!per_channel(mode)) return align_up(cov_match_ws_bytes(n_p, n_s, c, mode), 256);
     size_t b = align_up(sizeof(float) * (size_t)n_p * c, 256) + align_up(sizeof(float) * (size_t)n_s * c, 256);
-    if (!per_channel(mode)) b += align_up(sizeof(float) * (size_t)n_p * c, 256);
     return b + align_up(match_ws_bytes(n_p, n_s, c, mode), 256);
 }
 
@@ -261,7 +257,9 @@ static const int kRotChunk = 16;
 extern "C" size_t optex_ot_loop_workspace_bytes(int64_t n_p, int64_t n_s, int c, int mode) {
     size_t step = optex_ot_workspace_bytes(n_p, n_s, c, mode);
     if (!step) return 0;
-    return step + align_up(sizeof(float) * (size_t)kRotChunk * c * c, 256) + align_up(rotation_ws_bytes(c, kRotChunk), 256);
+    size_t alt = per_channel(mode) ? 0 : align_up(sizeof(float) * (size_t)n_p * c, 256);  // ping-pong feature block
+    return step + alt + align_up(sizeof(float) * (size_t)kRotChunk * c * c, 256) +
+           align_up(rotation_ws_bytes(c, kRotChunk), 256);
 }
 
 extern "C" int optex_ot_loop(float *feat, const float *S, const float *R_all, int iters, uint64_t seed,
@@ -278,6 +276,7 @@ extern "C" int optex_ot_loop(float *feat, const float *S, const float *R_all, in
     const size_t step_ws = optex_ot_workspace_bytes(n_p, n_s, c, mode);
     Arena ar(workspace, workspace_bytes);
     void *sw = ar.take<char>(step_ws);
+    float *alt = per_channel(mode) ? nullptr : ar.take<float>((size_t)n_p * c);
     float *rbuf = ar.take<float>((size_t)kRotChunk * c * c);
     size_t rws_bytes = rotation_ws_bytes(c, kRotChunk);
     void *rws = ar.take<char>(rws_bytes);
@@ -298,9 +297,15 @@ extern "C" int optex_ot_loop(float *feat, const float *S, const float *R_all, in
             }
             R = rbuf + (size_t)(i % kRotChunk) * c * c;
         }
-        OPTEX_TRY(ot_step_impl(feat, S, R, feat, b_p, hw_p, b_s, hw_s, c, mode, eps, content, content_strength, sw,
+        // per-channel modes run in place (P is dead after the forward rotation); the closed-form modes read
+        // P in their last GEMM, so they ping-pong between feat and alt
+        float *src = (alt && (i & 1)) ? alt : feat;
+        float *dst = alt ? ((i & 1) ? feat : alt) : feat;
+        OPTEX_TRY(ot_step_impl(src, S, R, dst, b_p, hw_p, b_s, hw_s, c, mode, eps, content, content_strength, sw,
                                step_ws, st));
     }
+    if (alt && (iters & 1))
+        OPTEX_CUDA(cudaMemcpyAsync(feat, alt, sizeof(float) * (size_t)n_p * c, cudaMemcpyDeviceToDevice, st));
     return OPTEX_OK;
 }
 

@@ -93,6 +93,18 @@ int sgemm_simt(const float *A, int64_t lda, bool a_kmajor, const float *B, int64
                bool b_kmajor, float *D, int64_t ldd, bool d_trans, int64_t M, int64_t N,
                int64_t K, const float *blend, float strength, float alpha, cudaStream_t st);
 
+struct SimtOpts {
+    const float *bias = nullptr;  // + bias[(m / bias_hw) * bias_ld + n]
+    int64_t bias_hw = 1, bias_ld = 0;
+    bool accumulate = false;      // D += alpha * acc  instead of  D = alpha * acc
+    int split_k = 1;              // blockIdx.z splits K; partials at D + z * d_z_stride
+    int64_t d_z_stride = 0;
+    const int *skip = nullptr;    // device flag: non-zero -> no-op
+};
+int sgemm_simt_ex(const float *A, int64_t lda, bool a_kmajor, const float *B, int64_t ldb, bool b_kmajor, float *D,
+                  int64_t ldd, bool d_trans, int64_t M, int64_t N, int64_t K, const float *blend, float strength,
+                  float alpha, const SimtOpts &o, cudaStream_t st);
+
 int transpose_f32(const float *in, float *out, int64_t rows, int64_t cols, cudaStream_t st);
 
 // rotation.cu: a batch of Haar SO(c) matrices R[batch][c][c] from (seed, first_counter + b)
@@ -103,6 +115,10 @@ int random_rotations(float *R, int c, int batch, uint64_t seed, uint64_t first_c
 // cov_match.cu: closed-form Gaussian matching (histmatch.py:13-44) on NHWC-flattened data.
 //   out[n, c] = (X - mu_t) T^T + mu_s ;  T from chol / pca / sym of the two covariances
 size_t cov_match_ws_bytes(int64_t n_t, int64_t n_s, int c, int mode);
+// the whole OT step for the covariance modes (rotation folded algebraically, see cov_match.cu); R may be null
+int cov_ot_step(const float *P, const float *S, const float *R, float *out, int b_p, int64_t hw_p, int b_s,
+                int64_t hw_s, int c, int mode, float eps, const float *content, float strength, void *workspace,
+                size_t workspace_bytes, cudaStream_t st);
 int cov_match_nhwc(const float *target, const float *source, float *out, int b_t, int64_t hw_t, int b_s,
                    int64_t hw_s, int c, int mode, float eps, void *workspace, size_t workspace_bytes,
                    cudaStream_t st);

