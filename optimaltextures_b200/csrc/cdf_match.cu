@@ -24,20 +24,20 @@ constexpr int MAX_BINS = 1024;
 constexpr int PRIV_MAX_BINS = 512;  // private byte histograms: bins * NT bytes of smem
 
 // ---- element iteration ------------------------------------------------------
-// Calls f(x) for every element of row[beg, end) with 128-bit loads when possible.
-template <typename F>
+// Calls f(x) for every element of row[beg, end) with 128-bit loads when possible (block of NTH threads).
+template <int NTH, typename F>
 __device__ __forceinline__ void for_each(const float *__restrict__ row, int64_t beg, int64_t end,
                                          bool vec, F f) {
     if (vec) {  // row 16B-aligned, beg % 4 == 0
         int64_t nv = (end - beg) >> 2;
         const float4 *p = reinterpret_cast<const float4 *>(row + beg);
-        for (int64_t i = threadIdx.x; i < nv; i += NT) {
+        for (int64_t i = threadIdx.x; i < nv; i += NTH) {
             float4 v = __ldg(p + i);
             f(v.x); f(v.y); f(v.z); f(v.w);
         }
-        for (int64_t i = beg + (nv << 2) + threadIdx.x; i < end; i += NT) f(__ldg(row + i));
+        for (int64_t i = beg + (nv << 2) + threadIdx.x; i < end; i += NTH) f(__ldg(row + i));
     } else {
-        for (int64_t i = beg + threadIdx.x; i < end; i += NT) f(__ldg(row + i));
+        for (int64_t i = beg + threadIdx.x; i < end; i += NTH) f(__ldg(row + i));
     }
 }
 
@@ -122,9 +122,9 @@ cdf_range_kernel(const float *__restrict__ t, const float *__restrict__ s, int64
     auto upd = [&](float x) { mn = fminf(mn, x); mx = fmaxf(mx, x); };
     int64_t b, e;
     slice_of(n_t, blockIdx.x, gridDim.x, b, e);
-    for_each(t + (int64_t)ch * n_t, b, e, t_vec, upd);
+    for_each<NT>(t + (int64_t)ch * n_t, b, e, t_vec, upd);
     slice_of(n_s, blockIdx.x, gridDim.x, b, e);
-    for_each(s + (int64_t)ch * n_s, b, e, s_vec, upd);
+    for_each<NT>(s + (int64_t)ch * n_s, b, e, s_vec, upd);
     mn = warp_min(mn);
     mx = warp_max(mx);
     __shared__ float smn[NT / 32], smx[NT / 32];
@@ -143,35 +143,38 @@ cdf_range_kernel(const float *__restrict__ t, const float *__restrict__ s, int64
 }
 
 // Accumulate one row slice into the block's u32 histogram `acc` (smem, `bins` entries).
-template <bool PRIV>
+// PRIV: every thread counts into its own byte-counter histogram (word w of thread t at priv[w*NTH + t]: no bank
+// conflicts, no atomics); after at most 252 elements per thread the counters are folded into `acc` with packed
+// 16-bit adds.  NTH is small (128) on purpose: the fold costs ~bins/4 words per thread, so a thread must count a
+// few hundred elements per fold for it to amortise (N = 16384 per channel at conv4_1 1024^2 = 128 per thread).
+template <bool PRIV, int NTH>
 __device__ __forceinline__ void hist_slice(const float *__restrict__ row, int64_t beg, int64_t end,
                                            bool vec, const HistRange &hr, uint32_t *priv,
                                            uint32_t *acc) {
     const int tid = threadIdx.x;
     if (!PRIV) {
-        for_each(row, beg, end, vec, [&](float x) { atomicAdd(&acc[hr.bin(x)], 1u); });
+        for_each<NTH>(row, beg, end, vec, [&](float x) { atomicAdd(&acc[hr.bin(x)], 1u); });
         return;
     }
     const int words = hr.bins >> 2;  // bins % 4 == 0 on this path
-    // 255 elements per thread between flushes: 63 float4 iterations (252) on the vector path
-    const int64_t chunk = (int64_t)NT * 252;
+    const int64_t chunk = (int64_t)NTH * 252;  // 63 float4 per thread: byte counters stay <= 252
     for (int64_t cb = beg; cb < end; cb += chunk) {
         int64_t ce = cb + chunk < end ? cb + chunk : end;
-        for (int w = 0; w < words; ++w) priv[w * NT + tid] = 0u;
-        for_each(row, cb, ce, vec, [&](float x) {
+        for (int w = 0; w < words; ++w) priv[w * NTH + tid] = 0u;
+        for_each<NTH>(row, cb, ce, vec, [&](float x) {
             int b = hr.bin(x);
-            priv[(b >> 2) * NT + tid] += 1u << ((b & 3) * 8);
+            priv[(b >> 2) * NTH + tid] += 1u << ((b & 3) * 8);
         });
         __syncthreads();
-        // packed reduce: thread (part, w) sums word w over NT/parts owners, 2 x 16-bit lanes x2
-        const int parts = NT / words >= 1 ? NT / words : 1;
-        for (int item = tid; item < words * parts; item += NT) {
+        // packed fold: item (part, w) sums word w over `per` owners in two 2x16-bit accumulators
+        const int parts = NTH / words >= 1 ? NTH / words : 1;
+        const int per = (NTH + parts - 1) / parts;  // <= 256 owners x 255 counts fits 16 bits
+        for (int item = tid; item < words * parts; item += NTH) {
             int w = item % words, part = item / words;
-            int per = (NT + parts - 1) / parts;  // <= 256 owners x 255 counts fits the 16-bit lanes
             uint32_t even = 0, odd = 0;
             for (int it = 0; it < per; ++it) {
                 int j = part * per + ((it + (tid & 31)) % per);
-                uint32_t v = j < NT ? priv[w * NT + j] : 0u;
+                uint32_t v = j < NTH ? priv[w * NTH + j] : 0u;
                 even += v & 0x00ff00ffu;
                 odd += (v >> 8) & 0x00ff00ffu;
             }
@@ -184,28 +187,38 @@ __device__ __forceinline__ void hist_slice(const float *__restrict__ row, int64_
     }
 }
 
+constexpr int NTH_HIST = 128;
+
 // th = histc(t, bins, lo, hi), sh = histc(s, bins, lo, hi)     histmatch.py:57-58
 template <bool PRIV>
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NTH_HIST, 6)
 cdf_hist_kernel(const float *__restrict__ t, const float *__restrict__ s, int64_t n_t, int64_t n_s,
                 const uint32_t *__restrict__ minmax, uint32_t *__restrict__ hist, int bins, int t_vec,
                 int s_vec) {
     extern __shared__ uint32_t smem_u32[];
-    uint32_t *acc = smem_u32;             // [2][bins]
-    uint32_t *priv = smem_u32 + 2 * bins;  // [bins/4][NT]  (PRIV only)
+    uint32_t *acc = smem_u32;          // [bins]
+    uint32_t *priv = smem_u32 + bins;  // [bins/4][NTH]  (PRIV only)
     const int ch = blockIdx.y;
-    for (int i = threadIdx.x; i < 2 * bins; i += NT) acc[i] = 0u;
+    for (int i = threadIdx.x; i < bins; i += NTH_HIST) acc[i] = 0u;
     __syncthreads();
     HistRange hr(ord2f(minmax[2 * ch]), ord2f(minmax[2 * ch + 1]), bins);
+    // blockIdx.z == 0 counts the target slice, 1 the source slice (twice the warps in flight)
     int64_t b, e;
-    slice_of(n_t, blockIdx.x, gridDim.x, b, e);
-    hist_slice<PRIV>(t + (int64_t)ch * n_t, b, e, t_vec, hr, priv, acc);
-    slice_of(n_s, blockIdx.x, gridDim.x, b, e);
-    hist_slice<PRIV>(s + (int64_t)ch * n_s, b, e, s_vec, hr, priv, acc + bins);
+    if (blockIdx.z == 0) {
+        slice_of(n_t, blockIdx.x, gridDim.x, b, e);
+        hist_slice<PRIV, NTH_HIST>(t + (int64_t)ch * n_t, b, e, t_vec, hr, priv, acc);
+    } else {
+        slice_of(n_s, blockIdx.x, gridDim.x, b, e);
+        hist_slice<PRIV, NTH_HIST>(s + (int64_t)ch * n_s, b, e, s_vec, hr, priv, acc);
+    }
     __syncthreads();
-    uint32_t *gh = hist + (int64_t)ch * 2 * bins;
-    for (int i = threadIdx.x; i < 2 * bins; i += NT)
-        if (acc[i]) atomicAdd(&gh[i], acc[i]);
+    uint32_t *gh = hist + ((int64_t)ch * 2 + blockIdx.z) * bins;
+    if (gridDim.x == 1) {
+        for (int i = threadIdx.x; i < bins; i += NTH_HIST) gh[i] = acc[i];
+    } else {
+        for (int i = threadIdx.x; i < bins; i += NTH_HIST)
+            if (acc[i]) atomicAdd(&gh[i], acc[i]);
+    }
 }
 
 // Build edges / CDFs / remap in shared memory from the channel's two histograms.
@@ -241,38 +254,86 @@ __device__ void build_tables(const uint32_t *__restrict__ gh, float lo, float hi
     __syncthreads();
 }
 
-// matched = interp(t, edges, remap)     histmatch.py:68
+// One CTA per channel: edges / remap / slope tables -> tbl[ch][4][bins]  ([3][0] = edges are non-decreasing)
 __global__ void __launch_bounds__(NT)
-cdf_apply_kernel(const float *__restrict__ t, float *__restrict__ out, int64_t n_t,
-                 const uint32_t *__restrict__ minmax, const uint32_t *__restrict__ hist, int bins,
-                 float *__restrict__ tables, int vec) {
+cdf_tables_kernel(const uint32_t *__restrict__ minmax, const uint32_t *__restrict__ hist, int bins,
+                  float *__restrict__ tbl, float *__restrict__ tables_out) {
     extern __shared__ float smem_f32[];
     float *edges = smem_f32, *remap = edges + bins, *tc = remap + bins, *sc = tc + bins;
     uint32_t *cnt = reinterpret_cast<uint32_t *>(sc + bins);
-    const int ch = blockIdx.y;
+    const int ch = blockIdx.x;
     const float lo = ord2f(minmax[2 * ch]), hi = ord2f(minmax[2 * ch + 1]);
     build_tables(hist + (int64_t)ch * 2 * bins, lo, hi, bins, edges, remap, tc, sc, cnt);
-    if (tables && blockIdx.x == 0)
-        for (int i = threadIdx.x; i < bins; i += NT) {
-            tables[((int64_t)ch * 2 + 0) * bins + i] = edges[i];
-            tables[((int64_t)ch * 2 + 1) * bins + i] = remap[i];
+    float *o = tbl + (int64_t)ch * 4 * bins;
+    const int last = bins - 1;
+    int mono = 1;
+    for (int i = threadIdx.x; i < bins; i += NT) {
+        const int j = i + 1 > last ? last : i + 1;
+        o[i] = edges[i];
+        o[bins + i] = remap[i];
+        o[2 * bins + i] = __fdiv_rn(__fsub_rn(remap[j], remap[i]), __fsub_rn(edges[j], edges[i]));  // histmatch.py:79
+        if (!(edges[i] <= edges[j])) mono = 0;
+        if (tables_out) {
+            tables_out[((int64_t)ch * 2 + 0) * bins + i] = edges[i];
+            tables_out[((int64_t)ch * 2 + 1) * bins + i] = remap[i];
         }
+    }
+    mono = __syncthreads_and(mono);
+    if (threadIdx.x == 0) o[3 * bins] = mono ? 1.f : 0.f;
+}
+
+// matched = interp(t, edges, remap)     histmatch.py:68
+// searchsorted(edges, x) is found from an arithmetic estimate of the bin plus an exact fix-up against the edges
+// (identical to the bisection whenever the edges are non-decreasing; otherwise the bisection itself runs).
+__global__ void __launch_bounds__(NT)
+cdf_apply_kernel(const float *t, float *out, int64_t n_t, const uint32_t *__restrict__ minmax,
+                 const float *__restrict__ tbl, int bins, int vec) {
+    __shared__ float tb[3 * MAX_BINS];
+    const int ch = blockIdx.y;
+    const float *g = tbl + (int64_t)ch * 4 * bins;
+    for (int i = threadIdx.x; i < 3 * bins; i += NT) tb[i] = g[i];
+    const bool mono = g[3 * bins] != 0.f;
+    __syncthreads();
+    const float *edges = tb, *remap = tb + bins, *slope = tb + 2 * bins;
+    const float lo = ord2f(minmax[2 * ch]), hi = ord2f(minmax[2 * ch + 1]);
+    const float inv = hi > lo ? (float)bins / (hi - lo) : 0.f;
+    const int last = bins - 1;
+    auto one = [&](float x) {
+        int i;
+        if (mono) {
+            i = (int)((x - lo) * inv);
+            i = i < 0 ? 0 : (i > last ? last : i);
+            while (i > 0 && edges[i - 1] >= x) --i;
+            while (i < last && edges[i] < x) ++i;
+            if (x != x) i = last;
+        } else {
+            i = lower_bound(edges, bins, x);
+            i = i > last ? last : i;
+        }
+        const float xi = edges[i], fi = remap[i], sl = slope[i];
+        float f = __fadd_rn(__fmul_rn(sl, __fsub_rn(x, xi)), fi);
+        if (!finite_f(f)) {
+            const int j = i + 1 > last ? last : i + 1;
+            f = __fadd_rn(__fmul_rn(sl, __fsub_rn(x, edges[j])), remap[j]);
+            if (!finite_f(f)) f = fi;
+        }
+        return f;
+    };
     int64_t b, e;
     slice_of(n_t, blockIdx.x, gridDim.x, b, e);
-    const float *row = t + (int64_t)ch * n_t;
+    const float *row = t + (int64_t)ch * n_t;  // may alias out (in-place): every element is read before it is written
     float *orow = out + (int64_t)ch * n_t;
-    auto one = [&](float x) { return interp_at(x, edges, remap, bins, lower_bound(edges, bins, x)); };
     if (vec) {
         int64_t nv = (e - b) >> 2;
         const float4 *p = reinterpret_cast<const float4 *>(row + b);
         float4 *q = reinterpret_cast<float4 *>(orow + b);
         for (int64_t i = threadIdx.x; i < nv; i += NT) {
-            float4 v = __ldg(p + i);
+            float4 v = p[i];
             q[i] = make_float4(one(v.x), one(v.y), one(v.z), one(v.w));
         }
-        for (int64_t i = b + (nv << 2) + threadIdx.x; i < e; i += NT) orow[i] = one(__ldg(row + i));
+        for (int64_t i = b + (nv << 2) + threadIdx.x; i < e; i += NT) orow[i] = one(row[i]);
     } else {
-        for (int64_t i = b + threadIdx.x; i < e; i += NT) orow[i] = one(__ldg(row + i));
+        for (int64_t i = b + threadIdx.x; i < e; i += NT) orow[i] = one(row[i]);
     }
 }
 
@@ -300,7 +361,8 @@ using namespace optex;
 
 extern "C" size_t optex_cdf_match_workspace_bytes(int c, int bins) {
     if (c <= 0 || bins <= 0) return 0;
-    return align_up(sizeof(uint32_t) * 2 * (size_t)c, 256) + align_up(sizeof(uint32_t) * 2 * (size_t)c * bins, 256);
+    return align_up(sizeof(uint32_t) * 2 * (size_t)c, 256) + align_up(sizeof(uint32_t) * 2 * (size_t)c * bins, 256) +
+           align_up(sizeof(float) * (4 * (size_t)c * bins + 4), 256);
 }
 
 extern "C" int optex_cdf_match(const float *target, const float *source, float *out, int c, int64_t n_t,
@@ -335,6 +397,7 @@ extern "C" int optex_cdf_match(const float *target, const float *source, float *
     Arena ar(workspace, workspace_bytes);
     uint32_t *minmax = ar.take<uint32_t>(2 * (size_t)c);
     uint32_t *hist = ar.take<uint32_t>(2 * (size_t)c * bins);
+    float *tbl = ar.take<float>(4 * (size_t)c * bins + 4);
     if (!ar.ok()) {
         set_error("optex_cdf_match: workspace %zu < %zu", workspace_bytes, optex_cdf_match_workspace_bytes(c, bins));
         return OPTEX_EWORKSPACE;
@@ -352,23 +415,27 @@ extern "C" int optex_cdf_match(const float *target, const float *source, float *
     cdf_range_kernel<<<grid, NT, 0, st>>>(target, source, n_t, n_s, minmax, t_vec, s_vec);
     OPTEX_LAUNCH_CHECK("cdf_range_kernel");
     const bool priv = (bins % 4 == 0) && bins <= PRIV_MAX_BINS;
+    // histogram grid: one CTA per channel unless that leaves SMs idle and the slices stay long
+    int64_t hs = (2LL * sm_count() + c - 1) / c, hcap = (n_big + 32767) / 32768;
+    dim3 grid_h((unsigned)(hs < hcap ? (hs < 1 ? 1 : hs) : (hcap < 1 ? 1 : hcap)), (unsigned)c, 2);
     if (priv) {
-        size_t smem = sizeof(uint32_t) * (2 * (size_t)bins + (size_t)(bins / 4) * NT);
+        size_t smem = sizeof(uint32_t) * (2 * (size_t)bins + (size_t)(bins / 4) * NTH_HIST);
         static bool attr_done = false;
         if (!attr_done) {
             OPTEX_CUDA(cudaFuncSetAttribute(cdf_hist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)(sizeof(uint32_t) * (2 * PRIV_MAX_BINS + (PRIV_MAX_BINS / 4) * NT))));
+                                            (int)(sizeof(uint32_t) * (2 * PRIV_MAX_BINS + (PRIV_MAX_BINS / 4) * NTH_HIST))));
             attr_done = true;
         }
-        cdf_hist_kernel<true><<<grid, NT, smem, st>>>(target, source, n_t, n_s, minmax, hist, bins, t_vec, s_vec);
+        cdf_hist_kernel<true><<<grid_h, NTH_HIST, smem, st>>>(target, source, n_t, n_s, minmax, hist, bins, t_vec, s_vec);
     } else {
-        cdf_hist_kernel<false><<<grid, NT, sizeof(uint32_t) * 2 * bins, st>>>(target, source, n_t, n_s, minmax,
-                                                                             hist, bins, t_vec, s_vec);
+        cdf_hist_kernel<false><<<grid_h, NTH_HIST, sizeof(uint32_t) * 2 * bins, st>>>(target, source, n_t, n_s, minmax,
+                                                                                   hist, bins, t_vec, s_vec);
     }
     OPTEX_LAUNCH_CHECK("cdf_hist_kernel");
+    cdf_tables_kernel<<<c, NT, sizeof(float) * 6 * bins, st>>>(minmax, hist, bins, tbl, tables);
+    OPTEX_LAUNCH_CHECK("cdf_tables_kernel");
     dim3 grid_a((unsigned)cdf_splits(c, n_t), (unsigned)c);
-    cdf_apply_kernel<<<grid_a, NT, sizeof(float) * 6 * bins, st>>>(target, out, n_t, minmax, hist, bins, tables,
-                                                                  o_vec);
+    cdf_apply_kernel<<<grid_a, NT, 0, st>>>(target, out, n_t, minmax, tbl, bins, o_vec);
     OPTEX_LAUNCH_CHECK("cdf_apply_kernel");
     return OPTEX_OK;
 }
