@@ -49,6 +49,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--all-modes", action="store_true", help="also time the other hist modes (extra keys)")
+    ap.add_argument("--sharded", action="store_true",
+                    help="N > 1: ONE feature block, rotated channels sharded over the ranks + NCCL all-gather "
+                         "(strong scaling) instead of one independent block per rank")
     return ap.parse_args()
 
 
@@ -222,10 +225,20 @@ def run_ours(a):
     st = stream_ptr(device)
 
     def gen_rotations(count, first):
-        call("optex_random_rotations", ptr(rots), c, count, 1234 + rank, first, None, ptr(rot_ws), rot_ws.numel(), st)
+        call("optex_random_rotations", ptr(rots), c, count, 1234 + (0 if a.sharded else rank), first, None, ptr(rot_ws), rot_ws.numel(), st)
+
+    sharded = a.sharded and world > 1
+    if sharded:
+        from optimaltextures_b200 import parallel
+
+        sets = [make_inputs(torch, a, i, device) for i in range(a.sets)]      # replicated inputs
+        shard_ops = parallel.cuda_ops()
 
     def step(i):
         p, s = sets[i % a.sets]
+        if sharded:
+            parallel.optimal_transport_sharded(p, s, a.mode, rots[i % K], ops=shard_ops)
+            return
         call("optex_ot_step", ptr(p), ptr(s), ptr(rots[i % K]), ptr(outs[i % 2]), 1, n, 1, n, c, mode, 1.0, None,
              0.0, ptr(ws), ws.numel(), st)
 
@@ -262,7 +275,7 @@ def run_ours(a):
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / K
-    value = world * K / (ms_total * 1e-3)
+    value = (1 if sharded else world) * K / (ms_total * 1e-3)
 
     # ---- breakdown: the step's stages through the exported building blocks, event-timed in the same loop
     stages = {}
@@ -350,11 +363,12 @@ def run_ours(a):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if sharded else "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a), "gemm": a.gemm,
                    "l2": f"inputs cycle over {a.sets} distinct (P,S) sets = {a.sets * 2 * 4 * n * c / 1e6:.0f} MB > 126 MB L2",
-                   "sharding": "independent feature blocks per rank, no data-path collective"},
+                   "sharding": ("one block, rotated channels sharded over ranks + NCCL all-gather" if sharded else
+                                "independent feature blocks per rank, no data-path collective")},
         "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline, "kernels": kernels,
         "step_roofline": {"hbm_frac": work["bytes"] / (ms_step * 1e-3) / 1e9 / pk["hbm_gbs"],
                           "tensor_frac": work["flops"] / (ms_step * 1e-3) / 1e12 / pk["bf16_tflops_sustained"],

@@ -174,6 +174,10 @@ int optex_random_rotations(float *R, int c, int count, uint64_t seed,
  */
 int optex_rotate_forward(const float *X, const float *R, float *Xt, int64_t n,
                          int c, void *stream);
+/* Channel block of the forward rotation - the unit of the multi-GPU sharding (one block of rotated channels
+ * per rank):  Xt[nc, n] = (X @ R[:, c0:c0+nc])^T */
+int optex_rotate_forward_block(const float *X, const float *R, float *Xt, int64_t n,
+                               int c, int c0, int nc, void *stream);
 int optex_rotate_inverse(const float *Mt, const float *R, float *out, int64_t n,
                          int c, const float *content, float content_strength,
                          void *stream);

@@ -47,6 +47,7 @@ SIGNATURES = {
     "optex_rotations_workspace_bytes": (_z, [_i, _i]),
     "optex_random_rotations": (_i, [_p, _i, _i, _u, _u, _p, _p, _z, _p]),
     "optex_rotate_forward": (_i, [_p, _p, _p, _l, _i, _p]),
+    "optex_rotate_forward_block": (_i, [_p, _p, _p, _l, _i, _i, _i, _p]),
     "optex_rotate_inverse": (_i, [_p, _p, _p, _l, _i, _p, _f, _p]),
 }
 

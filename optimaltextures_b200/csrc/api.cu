@@ -72,15 +72,21 @@ static int tc_terms() { return g_gemm_mode.load() == OPTEX_GEMM_TF32 ? 1 : 3; }
 
 // Xt[c, n] = (X R)^T   or  XR[n, c] = X R            optex.py:170-171
 static int rotate_forward(const float *X, const float *R, float *dst, int64_t n, int c, bool transposed,
-                          cudaStream_t st) {
+                          cudaStream_t st, int c0 = 0, int nc = -1) {
+    if (nc < 0) nc = c;
     bool forced;
     if (want_tc(forced)) {
-        int rc = gemm_tc_rotate_forward(X, R, dst, n, c, transposed, tc_terms(), st);
+        int rc = gemm_tc_rotate_forward(X, R, dst, n, c, transposed, tc_terms(), st, c0, nc);
         if (rc != OPTEX_ENOTSUP) return rc;
-        if (forced) return OPTEX_ESIZE;
+        if (forced) {
+            set_error("rotation GEMM: shape (n=%lld, c=%d, block %d+%d) is outside the tensor-core path's TMA "
+                      "constraints (c %% 32, 16-byte alignment); use gemm mode auto or fp32", (long long)n, c, c0, nc);
+            return OPTEX_ESIZE;
+        }
     }
-    // D[m = pixel, n = channel] = sum_k X[m, k] R[k, n]
-    return sgemm_simt(X, c, true, R, c, false, dst, transposed ? n : c, transposed, n, c, c, nullptr, 0.f, 1.f, st);
+    // D[m = pixel, j] = sum_k X[m, k] R[k, c0 + j]
+    return sgemm_simt(X, c, true, R + c0, c, false, dst, transposed ? n : nc, transposed, n, nc, c, nullptr, 0.f, 1.f,
+                      st);
 }
 // out[n, j] = sum_c M(n, c) R[j, c]  (+ blend)         optex.py:175, :117
 static int rotate_inverse(const float *M, bool m_channel_major, const float *R, float *out, int64_t n, int c,
@@ -89,7 +95,11 @@ static int rotate_inverse(const float *M, bool m_channel_major, const float *R, 
     if (want_tc(forced)) {
         int rc = gemm_tc_rotate_inverse(M, m_channel_major, R, out, n, c, content, strength, tc_terms(), st);
         if (rc != OPTEX_ENOTSUP) return rc;
-        if (forced) return OPTEX_ESIZE;
+        if (forced) {
+            set_error("rotation GEMM: shape (n=%lld, c=%d) is outside the tensor-core path's TMA constraints "
+                      "(c %% 32, n %% 32, 16-byte alignment); use gemm mode auto or fp32", (long long)n, c);
+            return OPTEX_ESIZE;
+        }
     }
     return sgemm_simt(M, m_channel_major ? n : c, !m_channel_major, R, c, true, out, c, false, n, c, c, content,
                       strength, 1.f, st);
@@ -353,6 +363,16 @@ extern "C" int optex_rotate_forward(const float *X, const float *R, float *Xt, i
         return OPTEX_EINVAL;
     }
     return rotate_forward(X, R, Xt, n, c, true, (cudaStream_t)stream);
+}
+
+extern "C" int optex_rotate_forward_block(const float *X, const float *R, float *Xt, int64_t n, int c, int c0, int nc,
+                                          void *stream) {
+    OPTEX_TRY(require_sm100());
+    if (!X || !R || !Xt || n < 1 || c < 1 || c0 < 0 || nc < 1 || c0 + nc > c) {
+        set_error("optex_rotate_forward_block: NULL pointer, empty shape or channel block outside [0, c)");
+        return OPTEX_EINVAL;
+    }
+    return rotate_forward(X, R, Xt, n, c, true, (cudaStream_t)stream, c0, nc);
 }
 
 extern "C" int optex_rotate_inverse(const float *Mt, const float *R, float *out, int64_t n, int c,

@@ -18,6 +18,8 @@ struct TcGemm {
     bool a_mn;
     const float *B;
     bool b_mn;
+    int64_t ldb;  // MN-major B only: row pitch when B is a column block of a wider matrix (0 = dense)
+    int64_t b_col0;  // ... and the first column of that block (B points at the full matrix)
     float *D;
     int64_t ldd;
     bool d_trans;
@@ -37,7 +39,7 @@ int gemm_tc(const TcGemm &g, cudaStream_t st);
 
 // dst = X R  (transposed: dst[c, n], else dst[n, c]);  terms = 1 (TF32) or 3 (3xTF32 split)
 int gemm_tc_rotate_forward(const float *X, const float *R, float *dst, int64_t n, int c, bool transposed,
-                           int terms, cudaStream_t st);
+                           int terms, cudaStream_t st, int c0 = 0, int nc = -1);
 // out[n, j] = sum_c M(n, c) R[j, c] (+ content blend);  M channel-major [c, n] or NHWC [n, c]
 int gemm_tc_rotate_inverse(const float *M, bool m_channel_major, const float *R, float *out, int64_t n, int c,
                            const float *content, float strength, int terms, cudaStream_t st);

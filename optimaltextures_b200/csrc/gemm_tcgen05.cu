@@ -369,9 +369,9 @@ int make_map_kmajor(CUtensorMap *map, const float *base, int64_t rows, int64_t K
     return OPTEX_OK;
 }
 // MN-major operand: row-major [K, MN] (MN contiguous, MN % 32 == 0) viewed as {32, K, MN/32}; box {32, 32, box_mn/32}
-int make_map_mnmajor(CUtensorMap *map, const float *base, int64_t K, int64_t MN, int box_mn) {
+int make_map_mnmajor(CUtensorMap *map, const float *base, int64_t K, int64_t MN, int box_mn, int64_t ld = 0) {
     cuuint64_t dims[3] = {32, (cuuint64_t)K, (cuuint64_t)(MN / 32)};
-    cuuint64_t strides[2] = {(cuuint64_t)MN * 4, 128};
+    cuuint64_t strides[2] = {(cuuint64_t)(ld > 0 ? ld : MN) * 4, 128};
     cuuint32_t box[3] = {32, 32, (cuuint32_t)(box_mn / 32)};
     cuuint32_t es[3] = {1, 1, 1};
     CUresult r = encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)base, dims, strides, box, es,
@@ -475,6 +475,9 @@ int gemm_tc(const TcGemm &g, cudaStream_t st) {
     if (g.a_mn ? (g.M % 32 != 0) : (g.K % 4 != 0)) return OPTEX_ENOTSUP;
     if (g.b_mn ? (g.N % 32 != 0) : (g.K % 4 != 0)) return OPTEX_ENOTSUP;
     if (g.d_trans && !(g.b_mn && !g.a_mn)) return OPTEX_ENOTSUP;
+    const int64_t ldb = g.ldb > 0 ? g.ldb : g.N;  // B = columns [0, N) of a row-major [K, ldb] matrix
+    if ((ldb != g.N || g.b_col0 != 0) && (!g.b_mn || ldb % 4 != 0 || g.b_col0 % 4 != 0 || g.b_col0 + g.N > ldb))
+        return OPTEX_ENOTSUP;
     if (g.d_trans && (g.blend || g.bias)) return OPTEX_ENOTSUP;
     if (!g.d_trans && g.ldd % 4 != 0) return OPTEX_ENOTSUP;
     int nz = g.split_k > 1 ? g.split_k : 1;
@@ -486,7 +489,7 @@ int gemm_tc(const TcGemm &g, cudaStream_t st) {
     const int bn = pick_block_n(g.M, g.N, nz);
     const float *ah_p = g.A, *al_p = g.A, *bh_p = g.B, *bl_p = g.B;
     if (g.terms == 3) {
-        const size_t na = (size_t)g.M * g.K, nb = (size_t)g.N * g.K;
+        const size_t na = (size_t)g.M * g.K, nb = (size_t)ldb * g.K;
         const bool shared = (g.A == g.B && g.a_mn == g.b_mn && g.M == g.N);
         float *buf;
         OPTEX_TRY(scratch((2 * na + (shared ? 0 : 2 * nb)) * sizeof(float), &buf));
@@ -501,6 +504,8 @@ int gemm_tc(const TcGemm &g, cudaStream_t st) {
             bh_p = b_hi; bl_p = b_lo;
         }
     }
+    bh_p += g.b_col0;  // column block of a wider B (16-byte aligned: b_col0 % 4 == 0)
+    bl_p += g.b_col0;
     CUtensorMap ah, al, bh, bl;
     if (g.a_mn) {
         OPTEX_TRY(make_map_mnmajor(&ah, ah_p, g.K, g.M, BLOCK_M));
@@ -510,8 +515,8 @@ int gemm_tc(const TcGemm &g, cudaStream_t st) {
         OPTEX_TRY(make_map_kmajor(&al, al_p, g.M, g.K, BLOCK_M));
     }
     if (g.b_mn) {
-        OPTEX_TRY(make_map_mnmajor(&bh, bh_p, g.K, g.N, bn));
-        OPTEX_TRY(make_map_mnmajor(&bl, bl_p, g.K, g.N, bn));
+        OPTEX_TRY(make_map_mnmajor(&bh, bh_p, g.K, g.N, bn, ldb));
+        OPTEX_TRY(make_map_mnmajor(&bl, bl_p, g.K, g.N, bn, ldb));
     } else {
         OPTEX_TRY(make_map_kmajor(&bh, bh_p, g.N, g.K, bn));
         OPTEX_TRY(make_map_kmajor(&bl, bl_p, g.N, g.K, bn));
@@ -530,11 +535,14 @@ int gemm_tc(const TcGemm &g, cudaStream_t st) {
 }
 
 int gemm_tc_rotate_forward(const float *X, const float *R, float *dst, int64_t n, int c, bool transposed, int terms,
-                           cudaStream_t st) {
-    // A = X [n, c] K-major; B = R [k, c_out] MN-major (needs c % 32 == 0)
+                           cudaStream_t st, int c0, int nc) {
+    // A = X [n, c] K-major; B = R[:, c0:c0+nc] MN-major (needs nc % 32 == 0, c0 % 4 == 0)
+    if (nc < 0) nc = c;
+    if (c0 % 4 != 0) return OPTEX_ENOTSUP;
     TcGemm g{};
-    g.A = X; g.a_mn = false; g.B = R; g.b_mn = true; g.D = dst; g.ldd = transposed ? n : (int64_t)c;
-    g.d_trans = transposed; g.M = n; g.N = c; g.K = c; g.terms = terms; g.alpha = 1.f;
+    g.A = X; g.a_mn = false; g.B = R; g.b_col0 = c0; g.b_mn = true; g.ldb = c; g.D = dst;
+    g.ldd = transposed ? n : (int64_t)nc;
+    g.d_trans = transposed; g.M = n; g.N = nc; g.K = c; g.terms = terms; g.alpha = 1.f;
     return gemm_tc(g, st);
 }
 

@@ -1,0 +1,113 @@
+"""Multi-GPU form of the OT step: rotated-channel sharding + one all-gather.
+
+The reference has no distributed code at all.  After the rotation the C channels are independent 1-D
+problems (histmatch.py:51 loops over them), so for the per-channel modes (`cdf`, `sort`):
+
+    rank g                                                   (one process per GPU, torch.distributed / NCCL)
+      Xt_g  = (P @ R[:, blk_g])^T      [C/G, N_p]   forward rotation of its channel block only (1/G of the FLOPs)
+      St_g  = (S @ R[:, blk_g])^T      [C/G, N_s]
+      Mt_g  = match(Xt_g, St_g)        [C/G, N_p]   cdf_match / sort_match on its channels
+      Mt    = all_gather(Mt_g)         [C,   N_p]   channel-major => each rank's block is one contiguous slab
+      out   = Mt^T @ R^T               [N_p, C]     full inverse rotation, redundantly on every rank
+
+P, S and R are replicated (R: same seed/counter on every rank), and `out` is bit-identical on every rank and
+identical to the 1-GPU result: no reduction is involved, so no summation order changes.  It pays only where one
+GPU saturates (conv1_1 / conv2_1 at >= 1024^2, everything at 2048^2): the all-gather moves 4*N_p*C*(G-1)/G bytes.
+
+The covariance modes (chol / pca / sym) run replicated - their per-step work after the algebraic folding
+(cov_match.cu) is two N x C x C GEMMs, which a pixel-sharded Gram + all-reduce would split (next round).
+
+`ops` makes the device kernels pluggable so the sharding logic itself is tested on CPU with gloo (tests/
+test_parallel_gloo.py drives it with the oracle's matchers); the default ops are the CUDA kernels.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+from torch import Tensor
+
+
+def channel_blocks(c: int, world: int, align: int = 32) -> List[Tuple[int, int]]:
+    """Contiguous (start, count) channel blocks, one per rank.  Starts are multiples of `align` (the tensor-core
+    path wants 32-wide blocks); trailing ranks may own nothing when c is small."""
+    units = (c + align - 1) // align
+    per, extra = divmod(units, world)
+    blocks, start = [], 0
+    for r in range(world):
+        n_units = per + (1 if r < extra else 0)
+        count = max(0, min(c, start + n_units * align) - start)
+        blocks.append((start, count))
+        start += count
+    assert start == c
+    return blocks
+
+
+@dataclass
+class Ops:
+    """The three device operations of the sharded step."""
+    rotate_forward_block: Callable[[Tensor, Tensor, int, int], Tensor]   # (x[n,c], R, c0, nc) -> [nc, n]
+    match: Callable[[Tensor, Tensor, str], Tensor]                        # (t[nc,n], s[nc,m], mode) -> [nc, n]
+    rotate_inverse: Callable[[Tensor, Tensor, Optional[Tensor], float], Tensor]  # (mt[c,n], R, content, w) -> [n,c]
+
+
+def cuda_ops() -> Ops:
+    from . import _lib, histmatch
+    from ._runtime import call, f32c, ptr, stream_ptr
+    from .optex import rotate_inverse
+
+    def fwd(x: Tensor, r: Tensor, c0: int, nc: int) -> Tensor:
+        xc, rc = f32c(x), f32c(r)
+        c = xc.shape[-1]
+        n = xc.numel() // c
+        out = torch.empty(nc, n, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            call("optex_rotate_forward_block", ptr(xc), ptr(rc), ptr(out), n, c, c0, nc, stream_ptr(x.device))
+        return out
+
+    def match(t: Tensor, s: Tensor, mode: str) -> Tensor:
+        return histmatch.sort_match(t, s) if mode == "sort" else histmatch.cdf_match(t, s)
+
+    return Ops(fwd, match, rotate_inverse)
+
+
+def optimal_transport_sharded(pastiche_feature: Tensor, style_feature: Tensor, hist_mode: str, rotation: Tensor,
+                              content: Optional[Tensor] = None, content_strength: float = 0.0,
+                              group=None, ops: Optional[Ops] = None) -> Tensor:
+    """optex.py:167-177 over the ranks of `group` (see module docstring).  Every rank passes the same replicated
+    tensors and receives the same full result."""
+    if hist_mode not in ("cdf", "sort"):
+        raise ValueError("channel sharding applies to the per-channel modes cdf / sort; run chol / pca / sym "
+                         "through optimal_transport (replicated)")
+    ops = ops or cuda_ops()
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    c = pastiche_feature.shape[-1]
+    n = pastiche_feature.numel() // c
+    blocks = channel_blocks(c, world)
+    c0, nc = blocks[rank]
+    mt = torch.empty(c, n, dtype=torch.float32, device=pastiche_feature.device)
+    if nc > 0:
+        xt = ops.rotate_forward_block(pastiche_feature.reshape(n, c), rotation, c0, nc)
+        st = ops.rotate_forward_block(style_feature.reshape(-1, c), rotation, c0, nc)
+        mine = ops.match(xt, st, hist_mode)
+    else:
+        mine = mt[:0]
+    if len({b[1] for b in blocks}) == 1:
+        dist.all_gather_into_tensor(mt, mine.contiguous(), group=group)           # equal slabs: one collective
+    else:
+        slabs = [mt[s:s + k] for s, k in blocks]
+        pad = max(k for _, k in blocks)
+        if all(k == pad for _, k in blocks):
+            dist.all_gather(slabs, mine.contiguous(), group=group)
+        else:                                                                     # ragged tail: pad to equal slabs
+            buf = torch.zeros(world, pad, n, dtype=torch.float32, device=mt.device)
+            send = torch.zeros(pad, n, dtype=torch.float32, device=mt.device)
+            send[:nc] = mine
+            dist.all_gather_into_tensor(buf.view(world * pad, n), send, group=group)
+            for r, (s, k) in enumerate(blocks):
+                mt[s:s + k] = buf[r, :k]
+    out = ops.rotate_inverse(mt, rotation, content.reshape(n, c) if content is not None else None, content_strength)
+    return out.reshape(pastiche_feature.shape)
