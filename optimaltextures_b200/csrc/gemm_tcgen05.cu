@@ -123,6 +123,15 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
     return d;
 }
 
+// a -> (tf32(a), tf32(a - tf32(a))): round-to-nearest split, both halves exactly representable in tf32
+__device__ __forceinline__ void split_tf32(float a, float &h, float &l) {
+    uint32_t hb, lb;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(a));
+    h = __uint_as_float(hb);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(__fsub_rn(a, h)));
+    l = __uint_as_float(lb);
+}
+
 struct Params {
     float *D;
     int64_t ldd;
@@ -137,6 +146,7 @@ struct Params {
     int64_t bias_hw, bias_ld;
     float alpha;          // D = alpha * acc (+ bias) (then blend)
     const int *skip;      // device flag: non-zero -> the whole launch is a no-op (converged iterations)
+    int conv_a;           // terms == 3: A arrives raw (tmA_hi) and warps 2-5 split it into hi/lo in shared memory
 };
 
 // ------------------------------------------------------------------ the kernel
@@ -148,7 +158,7 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     constexpr uint32_t A_TILE = BLOCK_M * BLOCK_K * 4;  // 16 KB
     constexpr uint32_t B_TILE = BLOCK_N * BLOCK_K * 4;
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], accum_bar;
+    __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], raw_bar[MAX_STAGES], accum_bar;
     __shared__ uint32_t tmem_base_smem;
 
     if (p.skip && *p.skip) return;  // uniform over the grid
@@ -167,12 +177,13 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         prefetch_tmap(&tmA_hi);
         prefetch_tmap(&tmB_hi);
         if (p.terms == 3) {
-            prefetch_tmap(&tmA_lo);
+            if (!p.conv_a) prefetch_tmap(&tmA_lo);
             prefetch_tmap(&tmB_lo);
         }
         for (int s = 0; s < p.stages; ++s) {
-            mbar_init(&full_bar[s], 1);
+            mbar_init(&full_bar[s], p.conv_a ? 4 : 1);  // conv_a: one arrival per converter warp
             mbar_init(&empty_bar[s], 1);
+            mbar_init(&raw_bar[s], 1);
         }
         mbar_init(&accum_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -197,17 +208,22 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                 const uint32_t ph = (kb / p.stages) & 1;
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 uint8_t *st = tiles + (size_t)s * stage_bytes;
-                mbar_expect_tx(&full_bar[s], stage_bytes);
+                // conv_a: the raw A tile lands in the hi slot and signals the converter warps (raw_bar);
+                // otherwise hi and lo halves of both operands arrive pre-split and signal the MMA warp directly
+                uint64_t *bar = p.conv_a ? &raw_bar[s] : &full_bar[s];
+                mbar_expect_tx(bar, p.conv_a ? A_TILE + nterm_tiles * B_TILE : stage_bytes);
                 const int k0 = (int)k_begin + kb * BLOCK_K;
                 for (int t = 0; t < nterm_tiles; ++t) {
                     const CUtensorMap *ma = t ? &tmA_lo : &tmA_hi;
                     const CUtensorMap *mb = t ? &tmB_lo : &tmB_hi;
                     uint8_t *a_dst = st + t * A_TILE;
                     uint8_t *b_dst = st + nterm_tiles * A_TILE + t * B_TILE;
-                    if (A_MN) tma_load_3d(ma, &full_bar[s], a_dst, 0, k0, m0 / 32);
-                    else tma_load_2d(ma, &full_bar[s], a_dst, k0, m0);
-                    if (B_MN) tma_load_3d(mb, &full_bar[s], b_dst, 0, k0, n0 / 32);
-                    else tma_load_2d(mb, &full_bar[s], b_dst, k0, n0);
+                    if (t == 0 || !p.conv_a) {
+                        if (A_MN) tma_load_3d(ma, bar, a_dst, 0, k0, m0 / 32);
+                        else tma_load_2d(ma, bar, a_dst, k0, m0);
+                    }
+                    if (B_MN) tma_load_3d(mb, bar, b_dst, 0, k0, n0 / 32);
+                    else tma_load_2d(mb, bar, b_dst, k0, n0);
                 }
             }
         }
@@ -249,6 +265,32 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
             __syncwarp();
         }
     } else {
+        // ===== converter (3xTF32): split the raw A tile of every stage into tf32 hi / lo halves, element-wise in
+        // place (independent of the swizzle), then hand the stage to the MMA warp
+        if (p.conv_a) {
+            const int ct = threadIdx.x - 64;  // 0..127
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % p.stages;
+                const uint32_t ph = (kb / p.stages) & 1;
+                mbar_wait(&raw_bar[s], ph);
+                float4 *hi = reinterpret_cast<float4 *>(tiles + (size_t)s * stage_bytes);
+                float4 *lo = reinterpret_cast<float4 *>(tiles + (size_t)s * stage_bytes + A_TILE);
+#pragma unroll
+                for (int i = 0; i < (int)(A_TILE / 16 / 128); ++i) {
+                    float4 v = hi[i * 128 + ct], h, l;
+                    split_tf32(v.x, h.x, l.x);
+                    split_tf32(v.y, h.y, l.y);
+                    split_tf32(v.z, h.z, l.z);
+                    split_tf32(v.w, h.w, l.w);
+                    hi[i * 128 + ct] = h;
+                    lo[i * 128 + ct] = l;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> UMMA reads
+                __syncwarp();
+                if (lane == 0)
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full_bar[s])) : "memory");
+            }
+        }
         // ===== epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31
         const int q = warp & 3;
         mbar_wait(&accum_bar, 0);
@@ -315,15 +357,7 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
 // a -> (tf32(a), tf32(a - tf32(a)))   round-to-nearest split, both halves exactly representable in tf32
 __global__ void split_tf32_kernel(const float4 *__restrict__ x, float4 *__restrict__ hi, float4 *__restrict__ lo,
                                   int64_t n4) {
-    auto split = [](float a, float &h, float &l) {
-        uint32_t hb;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(a));
-        h = __uint_as_float(hb);
-        float r = __fsub_rn(a, h);
-        uint32_t lb;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(r));
-        l = __uint_as_float(lb);
-    };
+    auto split = [](float a, float &h, float &l) { split_tf32(a, h, l); };
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
         float4 v = __ldg(x + i), h, l;
         split(v.x, h.x, l.x);
@@ -490,19 +524,14 @@ int gemm_tc(const TcGemm &g, cudaStream_t st) {
     const float *ah_p = g.A, *al_p = g.A, *bh_p = g.B, *bl_p = g.B;
     if (g.terms == 3) {
         const size_t na = (size_t)g.M * g.K, nb = (size_t)ldb * g.K;
-        const bool shared = (g.A == g.B && g.a_mn == g.b_mn && g.M == g.N);
+        // A is split inside the kernel (converter warps); only B (the small operand of the rotations: R) is
+        // pre-split by an element-wise pass
+        (void)na;
         float *buf;
-        OPTEX_TRY(scratch((2 * na + (shared ? 0 : 2 * nb)) * sizeof(float), &buf));
-        float *a_hi = buf, *a_lo = buf + na;
-        OPTEX_TRY(split(g.A, a_hi, a_lo, (int64_t)na, st));
-        ah_p = a_hi; al_p = a_lo;
-        if (shared) {
-            bh_p = a_hi; bl_p = a_lo;
-        } else {
-            float *b_hi = buf + 2 * na, *b_lo = b_hi + nb;
-            OPTEX_TRY(split(g.B, b_hi, b_lo, (int64_t)nb, st));
-            bh_p = b_hi; bl_p = b_lo;
-        }
+        OPTEX_TRY(scratch(2 * nb * sizeof(float), &buf));
+        float *b_hi = buf, *b_lo = b_hi + nb;
+        OPTEX_TRY(split(g.B, b_hi, b_lo, (int64_t)nb, st));
+        bh_p = b_hi; bl_p = b_lo;
     }
     bh_p += g.b_col0;  // column block of a wider B (16-byte aligned: b_col0 % 4 == 0)
     bl_p += g.b_col0;
@@ -526,7 +555,7 @@ int gemm_tc(const TcGemm &g, cudaStream_t st) {
     p.blend = g.blend; p.strength = g.strength; p.terms = g.terms == 3 ? 3 : 1;
     p.k_per_z = k_per_z; p.d_z_stride = g.d_z_stride;
     p.bias = g.bias; p.bias_hw = g.bias_hw > 0 ? g.bias_hw : 1; p.bias_ld = g.bias_ld;
-    p.alpha = g.alpha; p.skip = g.skip;
+    p.alpha = g.alpha; p.skip = g.skip; p.conv_a = p.terms == 3 ? 1 : 0;
     if (g.d_trans) return launch_n<false, true, true>(bn, ah, al, bh, bl, p, nz, st);
     if (!g.a_mn && !g.b_mn) return launch_n<false, false, false>(bn, ah, al, bh, bl, p, nz, st);
     if (!g.a_mn && g.b_mn) return launch_n<false, true, false>(bn, ah, al, bh, bl, p, nz, st);
