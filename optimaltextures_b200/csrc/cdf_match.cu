@@ -53,7 +53,7 @@ __device__ __forceinline__ void slice_of(int64_t n, int part, int nparts, int64_
 // torch.histc bin rule (CPU): int64((x - lo) * bins / (hi - lo)), bin == bins -> bins-1;
 // a degenerate range [v, v] becomes [v-1, v+1].
 struct HistRange {
-    float lo, width, fbins;
+    float lo, width, fbins, rcp;
     int bins;
     __device__ HistRange(float lo_, float hi_, int bins_) : bins(bins_) {
         if (lo_ == hi_) {
@@ -63,9 +63,16 @@ struct HistRange {
         lo = lo_;
         width = __fsub_rn(hi_, lo_);
         fbins = (float)bins_;
+        rcp = 1.f / width;
     }
+    // Exact trunc(fdiv_rn(a, width)) without dividing every element: a * rcp is within a few ulp (< 1e-4 absolute
+    // for quotients <= 1024) of the true quotient, so it has the same integer part unless it lies within 1e-3 of an
+    // integer - only those elements (about 0.2 %) take the IEEE division.
     __device__ __forceinline__ int bin(float x) const {
-        float q = __fdiv_rn(__fmul_rn(__fsub_rn(x, lo), fbins), width);
+        const float a = __fmul_rn(__fsub_rn(x, lo), fbins);
+        float q = a * rcp;
+        const float r = __fsub_rn(__fadd_rn(q, 12582912.f), 12582912.f);  // nearest integer (|q| < 2^22)
+        if (!(fabsf(q - r) >= 1e-3f)) q = __fdiv_rn(a, width);           // also taken for NaN / huge q
         int b = (int)q;  // truncation, like the int64 cast
         b = b >= bins ? bins - 1 : b;
         return b < 0 ? 0 : b;  // memory safety for NaN only
@@ -172,8 +179,10 @@ __device__ __forceinline__ void hist_slice(const float *__restrict__ row, int64_
         for (int item = tid; item < words * parts; item += NTH) {
             int w = item % words, part = item / words;
             uint32_t even = 0, odd = 0;
+            int rot = (tid & 31) % per;  // start each lane on a different owner: distinct banks
             for (int it = 0; it < per; ++it) {
-                int j = part * per + ((it + (tid & 31)) % per);
+                int j = part * per + rot;
+                rot = rot + 1 == per ? 0 : rot + 1;
                 uint32_t v = j < NTH ? priv[w * NTH + j] : 0u;
                 even += v & 0x00ff00ffu;
                 odd += (v >> 8) & 0x00ff00ffu;
@@ -187,11 +196,11 @@ __device__ __forceinline__ void hist_slice(const float *__restrict__ row, int64_
     }
 }
 
-constexpr int NTH_HIST = 128;
+constexpr int NTH_HIST = 96;  // 24.6 KB of private counters per CTA: all 2C CTAs of C = 512 resident in one wave
 
 // th = histc(t, bins, lo, hi), sh = histc(s, bins, lo, hi)     histmatch.py:57-58
 template <bool PRIV>
-__global__ void __launch_bounds__(NTH_HIST, 6)
+__global__ void __launch_bounds__(NTH_HIST, 9)
 cdf_hist_kernel(const float *__restrict__ t, const float *__restrict__ s, int64_t n_t, int64_t n_s,
                 const uint32_t *__restrict__ minmax, uint32_t *__restrict__ hist, int bins, int t_vec,
                 int s_vec) {

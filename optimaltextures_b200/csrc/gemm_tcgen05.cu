@@ -147,6 +147,7 @@ struct Params {
     float alpha;          // D = alpha * acc (+ bias) (then blend)
     const int *skip;      // device flag: non-zero -> the whole launch is a no-op (converged iterations)
     int conv_a;           // terms == 3: A arrives raw (tmA_hi) and warps 2-5 split it into hi/lo in shared memory
+    int conv_b;           // same for B (small problems, where a pre-split pass per GEMM would dominate)
 };
 
 // ------------------------------------------------------------------ the kernel
@@ -211,7 +212,7 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                 // conv_a: the raw A tile lands in the hi slot and signals the converter warps (raw_bar);
                 // otherwise hi and lo halves of both operands arrive pre-split and signal the MMA warp directly
                 uint64_t *bar = p.conv_a ? &raw_bar[s] : &full_bar[s];
-                mbar_expect_tx(bar, p.conv_a ? A_TILE + nterm_tiles * B_TILE : stage_bytes);
+                mbar_expect_tx(bar, p.conv_a ? A_TILE + (p.conv_b ? 1 : nterm_tiles) * B_TILE : stage_bytes);
                 const int k0 = (int)k_begin + kb * BLOCK_K;
                 for (int t = 0; t < nterm_tiles; ++t) {
                     const CUtensorMap *ma = t ? &tmA_lo : &tmA_hi;
@@ -222,8 +223,10 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                         if (A_MN) tma_load_3d(ma, bar, a_dst, 0, k0, m0 / 32);
                         else tma_load_2d(ma, bar, a_dst, k0, m0);
                     }
-                    if (B_MN) tma_load_3d(mb, bar, b_dst, 0, k0, n0 / 32);
-                    else tma_load_2d(mb, bar, b_dst, k0, n0);
+                    if (t == 0 || !p.conv_b) {
+                        if (B_MN) tma_load_3d(mb, bar, b_dst, 0, k0, n0 / 32);
+                        else tma_load_2d(mb, bar, b_dst, k0, n0);
+                    }
                 }
             }
         }
@@ -285,6 +288,20 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                     hi[i * 128 + ct] = h;
                     lo[i * 128 + ct] = l;
                 }
+                if (p.conv_b) {
+                    float4 *bh = reinterpret_cast<float4 *>(tiles + (size_t)s * stage_bytes + 2 * A_TILE);
+                    float4 *bl = reinterpret_cast<float4 *>(tiles + (size_t)s * stage_bytes + 2 * A_TILE + B_TILE);
+#pragma unroll 4
+                    for (int i = 0; i < (int)(B_TILE / 16 / 128); ++i) {
+                        float4 v = bh[i * 128 + ct], h, l;
+                        split_tf32(v.x, h.x, l.x);
+                        split_tf32(v.y, h.y, l.y);
+                        split_tf32(v.z, h.z, l.z);
+                        split_tf32(v.w, h.w, l.w);
+                        bh[i * 128 + ct] = h;
+                        bl[i * 128 + ct] = l;
+                    }
+                }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> UMMA reads
                 __syncwarp();
                 if (lane == 0)
@@ -320,18 +337,25 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                     v[j] = __float_as_uint(o);
                 }
                 if (n0 + col + 32 <= p.N) {
+                    // 256-bit accesses: every store is one full 32-byte sector of this thread's output row
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                               __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                    for (int j = 0; j < 32; j += 8) {
+                        float o[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(v[j + e]);
                         if (bp) {
-                            float4 c = __ldg(reinterpret_cast<const float4 *>(bp + j));
-                            o.x = __fadd_rn(o.x, __fmul_rn(p.strength, __fsub_rn(c.x, o.x)));
-                            o.y = __fadd_rn(o.y, __fmul_rn(p.strength, __fsub_rn(c.y, o.y)));
-                            o.z = __fadd_rn(o.z, __fmul_rn(p.strength, __fsub_rn(c.z, o.z)));
-                            o.w = __fadd_rn(o.w, __fmul_rn(p.strength, __fsub_rn(c.w, o.w)));
+                            float c[8];
+                            asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                                         : "=f"(c[0]), "=f"(c[1]), "=f"(c[2]), "=f"(c[3]), "=f"(c[4]), "=f"(c[5]),
+                                           "=f"(c[6]), "=f"(c[7])
+                                         : "l"(bp + j));
+#pragma unroll
+                            for (int e = 0; e < 8; ++e)
+                                o[e] = __fadd_rn(o[e], __fmul_rn(p.strength, __fsub_rn(c[e], o[e])));
                         }
-                        *reinterpret_cast<float4 *>(dp + j) = o;
+                        asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dp + j), "f"(o[0]),
+                                     "f"(o[1]), "f"(o[2]), "f"(o[3]), "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7])
+                                     : "memory");
                     }
                 } else {
 #pragma unroll
@@ -513,7 +537,9 @@ int gemm_tc(const TcGemm &g, cudaStream_t st) {
     if ((ldb != g.N || g.b_col0 != 0) && (!g.b_mn || ldb % 4 != 0 || g.b_col0 % 4 != 0 || g.b_col0 + g.N > ldb))
         return OPTEX_ENOTSUP;
     if (g.d_trans && (g.blend || g.bias)) return OPTEX_ENOTSUP;
-    if (!g.d_trans && g.ldd % 4 != 0) return OPTEX_ENOTSUP;
+    if (!g.d_trans && (g.ldd % 8 != 0 || (reinterpret_cast<uintptr_t>(g.D) & 31) != 0 ||
+                       (g.blend && (reinterpret_cast<uintptr_t>(g.blend) & 31) != 0)))
+        return OPTEX_ENOTSUP;
     int nz = g.split_k > 1 ? g.split_k : 1;
     int64_t k_per_z = 0;
     if (nz > 1) {
@@ -522,16 +548,20 @@ int gemm_tc(const TcGemm &g, cudaStream_t st) {
     }
     const int bn = pick_block_n(g.M, g.N, nz);
     const float *ah_p = g.A, *al_p = g.A, *bh_p = g.B, *bl_p = g.B;
+    bool conv_b = false;
     if (g.terms == 3) {
         const size_t na = (size_t)g.M * g.K, nb = (size_t)ldb * g.K;
         // A is split inside the kernel (converter warps); only B (the small operand of the rotations: R) is
         // pre-split by an element-wise pass
         (void)na;
-        float *buf;
-        OPTEX_TRY(scratch(2 * nb * sizeof(float), &buf));
-        float *b_hi = buf, *b_lo = b_hi + nb;
-        OPTEX_TRY(split(g.B, b_hi, b_lo, (int64_t)nb, st));
-        bh_p = b_hi; bl_p = b_lo;
+        conv_b = g.M <= 4096;  // few M tiles share B: splitting it in the kernel beats an extra pass + launch
+        if (!conv_b) {
+            float *buf;
+            OPTEX_TRY(scratch(2 * nb * sizeof(float), &buf));
+            float *b_hi = buf, *b_lo = b_hi + nb;
+            OPTEX_TRY(split(g.B, b_hi, b_lo, (int64_t)nb, st));
+            bh_p = b_hi; bl_p = b_lo;
+        }
     }
     bh_p += g.b_col0;  // column block of a wider B (16-byte aligned: b_col0 % 4 == 0)
     bl_p += g.b_col0;
@@ -555,7 +585,7 @@ int gemm_tc(const TcGemm &g, cudaStream_t st) {
     p.blend = g.blend; p.strength = g.strength; p.terms = g.terms == 3 ? 3 : 1;
     p.k_per_z = k_per_z; p.d_z_stride = g.d_z_stride;
     p.bias = g.bias; p.bias_hw = g.bias_hw > 0 ? g.bias_hw : 1; p.bias_ld = g.bias_ld;
-    p.alpha = g.alpha; p.skip = g.skip; p.conv_a = p.terms == 3 ? 1 : 0;
+    p.alpha = g.alpha; p.skip = g.skip; p.conv_a = p.terms == 3 ? 1 : 0; p.conv_b = conv_b ? 1 : 0;
     if (g.d_trans) return launch_n<false, true, true>(bn, ah, al, bh, bl, p, nz, st);
     if (!g.a_mn && !g.b_mn) return launch_n<false, false, false>(bn, ah, al, bh, bl, p, nz, st);
     if (!g.a_mn && g.b_mn) return launch_n<false, true, false>(bn, ah, al, bh, bl, p, nz, st);
