@@ -29,10 +29,10 @@ namespace optex {
 namespace {
 
 constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 32;  // 32 tf32 = 128 B = one swizzle row
+constexpr int BLOCK_K = 32;  // K granularity of split-K slices (both stage depths divide it)
 constexpr int UMMA_K = 8;    // 32 B of K per tcgen05.mma.kind::tf32
 constexpr int MAX_STAGES = 8;
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 320;  // producer, MMA, 4 converter and 4 epilogue warps
 constexpr int SMEM_BUDGET = 227 * 1024 - 4096;  // tiles; + 1 KB alignment slack + ~1 KB static (barriers)
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -76,6 +76,13 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap *map, uint64_t *ba
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z)
         : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *map, int x, int y) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap *map, int x, int y, int z) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(map), "r"(x), "r"(y), "r"(z)
+                 : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -147,31 +154,40 @@ struct Params {
     float alpha;          // D = alpha * acc (+ bias) (then blend)
     const int *skip;      // device flag: non-zero -> the whole launch is a no-op (converged iterations)
     int conv_a;           // terms == 3: A arrives raw (tmA_hi) and warps 2-5 split it into hi/lo in shared memory
+    int nz;               // number of split-K slices (tiles enumerate z as well)
     int conv_b;           // same for B (small problems, where a pre-split pass per GEMM would dominate)
 };
 
 // ------------------------------------------------------------------ the kernel
-template <int BLOCK_N, bool A_MN, bool B_MN, bool D_TRANS>
+// Persistent, warp-specialised: grid = min(#tiles, #SMs); every CTA walks tiles  t = blockIdx.x, += gridDim.x.
+//   warp 0      TMA producer        raw/full barriers per smem stage (expect_tx)
+//   warp 1      MMA issuer          tcgen05.mma into one of TWO TMEM accumulators (2 x BLOCK_N columns)
+//   warps 2-5   converters (3xTF32) split the raw tiles of every stage into tf32 hi / lo halves in shared memory
+//   warps 6-9   epilogue            tcgen05.ld -> global stores of tile i while the MMA warp already runs tile i+1
+// so the prologue (barrier init, TMEM alloc) is paid once per SM and the epilogue is hidden behind the next
+// tile's main loop (the non-persistent version spent ~45 % of its time outside the MMA loop).
+// BK = K elements per pipeline stage: 32 (128-byte swizzle rows) or 16 (64-byte rows, half-size stages).
+template <int BLOCK_N, bool A_MN, bool B_MN, bool D_TRANS, int BK>
 __global__ void __launch_bounds__(NTHREADS, 1)
 rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                    const Params p) {
-    constexpr uint32_t A_TILE = BLOCK_M * BLOCK_K * 4;  // 16 KB
-    constexpr uint32_t B_TILE = BLOCK_N * BLOCK_K * 4;
+    constexpr uint32_t A_TILE = BLOCK_M * BK * 4;
+    constexpr uint32_t B_TILE = BLOCK_N * BK * 4;
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], raw_bar[MAX_STAGES], accum_bar;
+    __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], raw_bar[MAX_STAGES];
+    __shared__ __align__(8) uint64_t tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_smem;
 
     if (p.skip && *p.skip) return;  // uniform over the grid
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * BLOCK_M, n0 = blockIdx.y * BLOCK_N;
     const int nterm_tiles = p.terms == 3 ? 2 : 1;  // hi (+ lo) tiles per operand
     const uint32_t stage_bytes = nterm_tiles * (A_TILE + B_TILE);
-    const int64_t k_begin = (int64_t)blockIdx.z * p.k_per_z;
-    const int64_t k_len = p.k_per_z > 0 ? (p.K - k_begin < p.k_per_z ? p.K - k_begin : p.k_per_z) : p.K;
-    const int num_kb = (int)((k_len + BLOCK_K - 1) / BLOCK_K);
-    float *const Dz = p.D + (int64_t)blockIdx.z * p.d_z_stride;
-    // 1024-byte alignment of the dynamic smem base (SWIZZLE_128B atoms)
+    const int n_tiles_n = (int)((p.N + BLOCK_N - 1) / BLOCK_N);
+    const int n_tiles_m = (int)((p.M + BLOCK_M - 1) / BLOCK_M);
+    const int tiles_per_z = n_tiles_m * n_tiles_n;
+    const int num_tiles = tiles_per_z * p.nz;
+    // 1024-byte alignment of the dynamic smem base (swizzle atoms)
     uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~uintptr_t(1023));
 
     if (warp == 0 && lane == 0) {
@@ -179,20 +195,23 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         prefetch_tmap(&tmB_hi);
         if (p.terms == 3) {
             if (!p.conv_a) prefetch_tmap(&tmA_lo);
-            prefetch_tmap(&tmB_lo);
+            if (!p.conv_b) prefetch_tmap(&tmB_lo);
         }
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(&full_bar[s], p.conv_a ? 4 : 1);  // conv_a: one arrival per converter warp
             mbar_init(&empty_bar[s], 1);
             mbar_init(&raw_bar[s], 1);
         }
-        mbar_init(&accum_bar, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull_bar[a], 1);   // tcgen05.commit of the tile's last MMA
+            mbar_init(&tempty_bar[a], 4);  // one arrival per epilogue warp
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                          smem_u32(&tmem_base_smem)),
-                     "r"((uint32_t)BLOCK_N)
+                     "r"((uint32_t)(2 * BLOCK_N))
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -201,32 +220,52 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
 
+    // tile -> (z, m, n): n fastest, so CTAs running side by side share the rows of the big A operand in L2
+    auto tile_coords = [&](int tile, int &m0, int &n0, int &z) {
+        z = tile / tiles_per_z;
+        const int r = tile - z * tiles_per_z;
+        m0 = (r / n_tiles_n) * BLOCK_M;
+        n0 = (r % n_tiles_n) * BLOCK_N;
+    };
+    auto k_range = [&](int z, int64_t &k_begin, int &num_kb) {
+        k_begin = (int64_t)z * p.k_per_z;
+        const int64_t k_len = p.k_per_z > 0 ? (p.K - k_begin < p.k_per_z ? p.K - k_begin : p.k_per_z) : p.K;
+        num_kb = (int)((k_len + BK - 1) / BK);
+    };
+
     if (warp == 0) {
         // ===== TMA producer
         if (elect_one()) {
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % p.stages;
-                const uint32_t ph = (kb / p.stages) & 1;
-                mbar_wait(&empty_bar[s], ph ^ 1);
-                uint8_t *st = tiles + (size_t)s * stage_bytes;
-                // conv_a: the raw A tile lands in the hi slot and signals the converter warps (raw_bar);
-                // otherwise hi and lo halves of both operands arrive pre-split and signal the MMA warp directly
-                uint64_t *bar = p.conv_a ? &raw_bar[s] : &full_bar[s];
-                mbar_expect_tx(bar, p.conv_a ? A_TILE + (p.conv_b ? 1 : nterm_tiles) * B_TILE : stage_bytes);
-                const int k0 = (int)k_begin + kb * BLOCK_K;
-                for (int t = 0; t < nterm_tiles; ++t) {
-                    const CUtensorMap *ma = t ? &tmA_lo : &tmA_hi;
-                    const CUtensorMap *mb = t ? &tmB_lo : &tmB_hi;
-                    uint8_t *a_dst = st + t * A_TILE;
-                    uint8_t *b_dst = st + nterm_tiles * A_TILE + t * B_TILE;
-                    if (t == 0 || !p.conv_a) {
-                        if (A_MN) tma_load_3d(ma, bar, a_dst, 0, k0, m0 / 32);
-                        else tma_load_2d(ma, bar, a_dst, k0, m0);
+            int s = 0;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                int m0, n0, z, num_kb;
+                int64_t k_begin;
+                tile_coords(tile, m0, n0, z);
+                k_range(z, k_begin, num_kb);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    uint8_t *st = tiles + (size_t)s * stage_bytes;
+                    // conv_a: the raw A tile lands in the hi slot and signals the converter warps (raw_bar);
+                    // otherwise hi and lo halves of both operands arrive pre-split and signal the MMA warp directly
+                    uint64_t *bar = p.conv_a ? &raw_bar[s] : &full_bar[s];
+                    mbar_expect_tx(bar, p.conv_a ? A_TILE + (p.conv_b ? 1 : nterm_tiles) * B_TILE : stage_bytes);
+                    const int k0 = (int)k_begin + kb * BK;
+                    for (int t = 0; t < nterm_tiles; ++t) {
+                        const CUtensorMap *ma = t ? &tmA_lo : &tmA_hi;
+                        const CUtensorMap *mb = t ? &tmB_lo : &tmB_hi;
+                        uint8_t *a_dst = st + t * A_TILE;
+                        uint8_t *b_dst = st + nterm_tiles * A_TILE + t * B_TILE;
+                        if (t == 0 || !p.conv_a) {
+                            if (A_MN) tma_load_3d(ma, bar, a_dst, 0, k0, m0 / 32);
+                            else tma_load_2d(ma, bar, a_dst, k0, m0);
+                        }
+                        if (t == 0 || !p.conv_b) {
+                            if (B_MN) tma_load_3d(mb, bar, b_dst, 0, k0, n0 / 32);
+                            else tma_load_2d(mb, bar, b_dst, k0, n0);
+                        }
                     }
-                    if (t == 0 || !p.conv_b) {
-                        if (B_MN) tma_load_3d(mb, bar, b_dst, 0, k0, n0 / 32);
-                        else tma_load_2d(mb, bar, b_dst, k0, n0);
-                    }
+                    if (++s == p.stages) { s = 0; ph ^= 1; }
                 }
             }
         }
@@ -235,145 +274,184 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) |
                                ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BLOCK_N >> 3) << 17) |
                                ((uint32_t)(BLOCK_M >> 4) << 24);
-        for (int kb = 0; kb < num_kb; ++kb) {
-            const int s = kb % p.stages;
-            const uint32_t ph = (kb / p.stages) & 1;
-            mbar_wait(&full_bar[s], ph);
+        int s = 0;
+        uint32_t ph = 0;
+        int titer = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++titer) {
+            int m0, n0, z, num_kb;
+            int64_t k_begin;
+            tile_coords(tile, m0, n0, z);
+            k_range(z, k_begin, num_kb);
+            const int acc = titer & 1;
+            const uint32_t aph = (titer >> 1) & 1;
+            mbar_wait(&tempty_bar[acc], aph ^ 1);  // the epilogue has drained this accumulator
             tc_fence_after();
-            if (elect_one()) {
-                const uint32_t st = smem_u32(tiles + (size_t)s * stage_bytes);
-                const uint32_t a_hi = st, a_lo = st + A_TILE;
-                const uint32_t b_hi = st + nterm_tiles * A_TILE, b_lo = b_hi + B_TILE;
+            const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t st = smem_u32(tiles + (size_t)s * stage_bytes);
+                    const uint32_t a_hi = st, a_lo = st + A_TILE;
+                    const uint32_t b_hi = st + nterm_tiles * A_TILE, b_lo = b_hi + B_TILE;
 #pragma unroll
-                for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
-                    // K-major: +32 B per K step inside the 128 B swizzle row; MN-major: +8 k-rows = 1 KB
-                    const uint32_t a_off = A_MN ? kk * 1024u : kk * 32u;
-                    const uint32_t b_off = B_MN ? kk * 1024u : kk * 32u;
-                    const uint32_t a_lbo = A_MN ? 4096u : 16u, b_lbo = B_MN ? 4096u : 16u;
-                    const uint32_t a_sbo = A_MN ? 512u : 1024u, b_sbo = B_MN ? 512u : 1024u;
-                    const uint32_t a_lt = A_MN ? 1u : 2u, b_lt = B_MN ? 1u : 2u;
-                    uint64_t da = make_desc(a_hi + a_off, a_lbo, a_sbo, a_lt);
-                    uint64_t db = make_desc(b_hi + b_off, b_lbo, b_sbo, b_lt);
-                    umma_tf32(tmem_base, da, db, idesc, (kb | kk) != 0);
-                    if (p.terms == 3) {
-                        uint64_t dal = make_desc(a_lo + a_off, a_lbo, a_sbo, a_lt);
-                        uint64_t dbl = make_desc(b_lo + b_off, b_lbo, b_sbo, b_lt);
-                        umma_tf32(tmem_base, da, dbl, idesc, 1u);
-                        umma_tf32(tmem_base, dal, db, idesc, 1u);
+                    for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+                        // K-major: +32 B per K step inside the swizzle row; MN-major: +8 k-rows = 1 KB
+                        const uint32_t a_off = A_MN ? kk * 1024u : kk * 32u;
+                        const uint32_t b_off = B_MN ? kk * 1024u : kk * 32u;
+                        // MN-major: 32-wide mn blocks of BK k-rows x 128 B (LBO), 4-row BASE32B atoms (SBO 512 B)
+                        // K-major : 8-row atoms of BK*4-byte rows: SWIZZLE_128B (BK = 32) or SWIZZLE_64B (BK = 16)
+                        constexpr uint32_t kmaj_sbo = BK == 32 ? 1024u : 512u, kmaj_lt = BK == 32 ? 2u : 4u;
+                        const uint32_t a_lbo = A_MN ? BK * 128u : 16u, b_lbo = B_MN ? BK * 128u : 16u;
+                        const uint32_t a_sbo = A_MN ? 512u : kmaj_sbo, b_sbo = B_MN ? 512u : kmaj_sbo;
+                        const uint32_t a_lt = A_MN ? 1u : kmaj_lt, b_lt = B_MN ? 1u : kmaj_lt;
+                        uint64_t da = make_desc(a_hi + a_off, a_lbo, a_sbo, a_lt);
+                        uint64_t db = make_desc(b_hi + b_off, b_lbo, b_sbo, b_lt);
+                        umma_tf32(tmem_d, da, db, idesc, (kb | kk) != 0);
+                        if (p.terms == 3) {
+                            uint64_t dal = make_desc(a_lo + a_off, a_lbo, a_sbo, a_lt);
+                            uint64_t dbl = make_desc(b_lo + b_off, b_lbo, b_sbo, b_lt);
+                            umma_tf32(tmem_d, da, dbl, idesc, 1u);
+                            umma_tf32(tmem_d, dal, db, idesc, 1u);
+                        }
                     }
+                    umma_commit(&empty_bar[s]);                          // smem stage free once these MMAs retire
+                    if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete
                 }
-                umma_commit(&empty_bar[s]);                     // smem stage free once these MMAs retire
-                if (kb == num_kb - 1) umma_commit(&accum_bar);  // accumulator complete
+                __syncwarp();
+                if (++s == p.stages) { s = 0; ph ^= 1; }
             }
-            __syncwarp();
         }
-    } else {
-        // ===== converter (3xTF32): split the raw A tile of every stage into tf32 hi / lo halves, element-wise in
+    } else if (warp < 6) {
+        // ===== converters (3xTF32): split the raw tiles of every stage into tf32 hi / lo halves, element-wise in
         // place (independent of the swizzle), then hand the stage to the MMA warp
         if (p.conv_a) {
             const int ct = threadIdx.x - 64;  // 0..127
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % p.stages;
-                const uint32_t ph = (kb / p.stages) & 1;
-                mbar_wait(&raw_bar[s], ph);
-                float4 *hi = reinterpret_cast<float4 *>(tiles + (size_t)s * stage_bytes);
-                float4 *lo = reinterpret_cast<float4 *>(tiles + (size_t)s * stage_bytes + A_TILE);
+            int s = 0;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                int m0, n0, z, num_kb;
+                int64_t k_begin;
+                tile_coords(tile, m0, n0, z);
+                k_range(z, k_begin, num_kb);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&raw_bar[s], ph);
+                    float4 *hi = reinterpret_cast<float4 *>(tiles + (size_t)s * stage_bytes);
+                    float4 *lo = reinterpret_cast<float4 *>(tiles + (size_t)s * stage_bytes + A_TILE);
 #pragma unroll
-                for (int i = 0; i < (int)(A_TILE / 16 / 128); ++i) {
-                    float4 v = hi[i * 128 + ct], h, l;
-                    split_tf32(v.x, h.x, l.x);
-                    split_tf32(v.y, h.y, l.y);
-                    split_tf32(v.z, h.z, l.z);
-                    split_tf32(v.w, h.w, l.w);
-                    hi[i * 128 + ct] = h;
-                    lo[i * 128 + ct] = l;
-                }
-                if (p.conv_b) {
-                    float4 *bh = reinterpret_cast<float4 *>(tiles + (size_t)s * stage_bytes + 2 * A_TILE);
-                    float4 *bl = reinterpret_cast<float4 *>(tiles + (size_t)s * stage_bytes + 2 * A_TILE + B_TILE);
-#pragma unroll 4
-                    for (int i = 0; i < (int)(B_TILE / 16 / 128); ++i) {
-                        float4 v = bh[i * 128 + ct], h, l;
+                    for (int i = 0; i < (int)(A_TILE / 16 / 128); ++i) {
+                        float4 v = hi[i * 128 + ct], h, l;
                         split_tf32(v.x, h.x, l.x);
                         split_tf32(v.y, h.y, l.y);
                         split_tf32(v.z, h.z, l.z);
                         split_tf32(v.w, h.w, l.w);
-                        bh[i * 128 + ct] = h;
-                        bl[i * 128 + ct] = l;
+                        hi[i * 128 + ct] = h;
+                        lo[i * 128 + ct] = l;
                     }
+                    if (p.conv_b) {
+                        float4 *bh = reinterpret_cast<float4 *>(tiles + (size_t)s * stage_bytes + 2 * A_TILE);
+                        float4 *bl = reinterpret_cast<float4 *>(tiles + (size_t)s * stage_bytes + 2 * A_TILE + B_TILE);
+#pragma unroll 4
+                        for (int i = 0; i < (int)(B_TILE / 16 / 128); ++i) {
+                            float4 v = bh[i * 128 + ct], h, l;
+                            split_tf32(v.x, h.x, l.x);
+                            split_tf32(v.y, h.y, l.y);
+                            split_tf32(v.z, h.z, l.z);
+                            split_tf32(v.w, h.w, l.w);
+                            bh[i * 128 + ct] = h;
+                            bl[i * 128 + ct] = l;
+                        }
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> UMMA reads
+                    __syncwarp();
+                    if (lane == 0)
+                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full_bar[s]))
+                                     : "memory");
+                    if (++s == p.stages) { s = 0; ph ^= 1; }
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> UMMA reads
-                __syncwarp();
-                if (lane == 0)
-                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full_bar[s])) : "memory");
             }
         }
+    } else {
         // ===== epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31
         const int q = warp & 3;
-        mbar_wait(&accum_bar, 0);
-        tc_fence_after();
-        const int64_t row = (int64_t)m0 + q * 32 + lane;
+        int titer = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++titer) {
+            int m0, n0, z;
+            tile_coords(tile, m0, n0, z);
+            const int acc = titer & 1;
+            const uint32_t aph = (titer >> 1) & 1;
+            float *const Dz = p.D + (int64_t)z * p.d_z_stride;
+            mbar_wait(&tfull_bar[acc], aph);
+            tc_fence_after();
+            const int64_t row = (int64_t)m0 + q * 32 + lane;
 #pragma unroll 1
-        for (int col = 0; col < BLOCK_N; col += 32) {
-            if (n0 + col >= p.N) break;
-            uint32_t v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col, v);
-            if (D_TRANS) {
-                if (row < p.M) {
+            for (int col = 0; col < BLOCK_N; col += 32) {
+                if (n0 + col >= p.N) break;
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + col), v);
+                if (D_TRANS) {
+                    if (row < p.M) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            int64_t n = (int64_t)n0 + col + j;
+                            if (n < p.N) Dz[n * p.ldd + row] = p.alpha * __uint_as_float(v[j]);
+                        }
+                    }
+                } else if (row < p.M) {
+                    float *dp = Dz + row * p.ldd + n0 + col;
+                    const float *bp = p.blend ? p.blend + row * p.ldd + n0 + col : nullptr;
+                    const float *bias = p.bias ? p.bias + (row / p.bias_hw) * p.bias_ld + n0 + col : nullptr;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        int64_t n = (int64_t)n0 + col + j;
-                        if (n < p.N) Dz[n * p.ldd + row] = p.alpha * __uint_as_float(v[j]);
+                        float o = p.alpha * __uint_as_float(v[j]);
+                        if (bias && n0 + col + j < p.N) o = __fadd_rn(o, __ldg(bias + j));
+                        v[j] = __float_as_uint(o);
                     }
-                }
-            } else if (row < p.M) {
-                float *dp = Dz + row * p.ldd + n0 + col;
-                const float *bp = p.blend ? p.blend + row * p.ldd + n0 + col : nullptr;
-                const float *bias = p.bias ? p.bias + (row / p.bias_hw) * p.bias_ld + n0 + col : nullptr;
+                    if (n0 + col + 32 <= p.N) {
+                        // 256-bit accesses: every store is one full 32-byte sector of this thread's output row
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float o = p.alpha * __uint_as_float(v[j]);
-                    if (bias && n0 + col + j < p.N) o = __fadd_rn(o, __ldg(bias + j));
-                    v[j] = __float_as_uint(o);
-                }
-                if (n0 + col + 32 <= p.N) {
-                    // 256-bit accesses: every store is one full 32-byte sector of this thread's output row
+                        for (int j = 0; j < 32; j += 8) {
+                            float o[8];
 #pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        float o[8];
+                            for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(v[j + e]);
+                            if (bp) {
+                                float c[8];
+                                asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                                             : "=f"(c[0]), "=f"(c[1]), "=f"(c[2]), "=f"(c[3]), "=f"(c[4]), "=f"(c[5]),
+                                               "=f"(c[6]), "=f"(c[7])
+                                             : "l"(bp + j));
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(v[j + e]);
-                        if (bp) {
-                            float c[8];
-                            asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                                         : "=f"(c[0]), "=f"(c[1]), "=f"(c[2]), "=f"(c[3]), "=f"(c[4]), "=f"(c[5]),
-                                           "=f"(c[6]), "=f"(c[7])
-                                         : "l"(bp + j));
-#pragma unroll
-                            for (int e = 0; e < 8; ++e)
-                                o[e] = __fadd_rn(o[e], __fmul_rn(p.strength, __fsub_rn(c[e], o[e])));
+                                for (int e = 0; e < 8; ++e)
+                                    o[e] = __fadd_rn(o[e], __fmul_rn(p.strength, __fsub_rn(c[e], o[e])));
+                            }
+                            asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dp + j), "f"(o[0]),
+                                         "f"(o[1]), "f"(o[2]), "f"(o[3]), "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7])
+                                         : "memory");
                         }
-                        asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dp + j), "f"(o[0]),
-                                     "f"(o[1]), "f"(o[2]), "f"(o[3]), "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7])
-                                     : "memory");
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (n0 + col + j < p.N) {
+                                float o = __uint_as_float(v[j]);
+                                if (bp) o = __fadd_rn(o, __fmul_rn(p.strength, __fsub_rn(__ldg(bp + j), o)));
+                                dp[j] = o;
+                            }
                     }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (n0 + col + j < p.N) {
-                            float o = __uint_as_float(v[j]);
-                            if (bp) o = __fadd_rn(o, __fmul_rn(p.strength, __fsub_rn(__ldg(bp + j), o)));
-                            dp[j] = o;
-                        }
                 }
             }
+            // all of this warp's TMEM reads have completed (tcgen05.wait::ld in tmem_ld32): release the accumulator
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0)
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tempty_bar[acc])) : "memory");
         }
-        tc_fence_before();
     }
+    tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BLOCK_N)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                     "r"((uint32_t)(2 * BLOCK_N))
                      : "memory");
     }
 }
@@ -412,13 +490,14 @@ EncodeTiledFn encode_fn() {
 }
 
 // K-major operand: row-major [rows, K]; box {32 k, box_rows}
-int make_map_kmajor(CUtensorMap *map, const float *base, int64_t rows, int64_t K, int box_rows) {
+int make_map_kmajor(CUtensorMap *map, const float *base, int64_t rows, int64_t K, int box_rows, int bk = 32) {
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)K * 4};
-    cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)box_rows};
     cuuint32_t es[2] = {1, 1};
     CUresult r = encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, es,
-                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled (K-major [%lld, %lld]) failed: %d", (long long)rows, (long long)K, (int)r);
@@ -427,10 +506,11 @@ int make_map_kmajor(CUtensorMap *map, const float *base, int64_t rows, int64_t K
     return OPTEX_OK;
 }
 // MN-major operand: row-major [K, MN] (MN contiguous, MN % 32 == 0) viewed as {32, K, MN/32}; box {32, 32, box_mn/32}
-int make_map_mnmajor(CUtensorMap *map, const float *base, int64_t K, int64_t MN, int box_mn, int64_t ld = 0) {
+int make_map_mnmajor(CUtensorMap *map, const float *base, int64_t K, int64_t MN, int box_mn, int64_t ld = 0,
+                     int bk = 32) {
     cuuint64_t dims[3] = {32, (cuuint64_t)K, (cuuint64_t)(MN / 32)};
     cuuint64_t strides[2] = {(cuuint64_t)(ld > 0 ? ld : MN) * 4, 128};
-    cuuint32_t box[3] = {32, 32, (cuuint32_t)(box_mn / 32)};
+    cuuint32_t box[3] = {32, (cuuint32_t)bk, (cuuint32_t)(box_mn / 32)};
     cuuint32_t es[3] = {1, 1, 1};
     CUresult r = encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)base, dims, strides, box, es,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
@@ -481,21 +561,23 @@ int split(const float *x, float *hi, float *lo, int64_t n, cudaStream_t st) {
     return OPTEX_OK;
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN, bool D_TRANS>
+template <int BLOCK_N, bool A_MN, bool B_MN, bool D_TRANS, int BK>
 int launch(const CUtensorMap &ah, const CUtensorMap &al, const CUtensorMap &bh, const CUtensorMap &bl, Params p,
            int nz, cudaStream_t st) {
-    const uint32_t stage_bytes = (p.terms == 3 ? 2 : 1) * (BLOCK_M * BLOCK_K * 4 + BLOCK_N * BLOCK_K * 4);
+    const uint32_t stage_bytes = (p.terms == 3 ? 2 : 1) * (BLOCK_M * BK * 4 + BLOCK_N * BK * 4);
     int stages = SMEM_BUDGET / (int)stage_bytes;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     p.stages = stages;
     size_t smem = (size_t)stages * stage_bytes + 1024;
-    auto kern = rotate_gemm_kernel<BLOCK_N, A_MN, B_MN, D_TRANS>;
+    auto kern = rotate_gemm_kernel<BLOCK_N, A_MN, B_MN, D_TRANS, BK>;
     static bool attr_done = false;
     if (!attr_done) {
         OPTEX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + 1024));
         attr_done = true;
     }
-    dim3 grid((unsigned)((p.M + BLOCK_M - 1) / BLOCK_M), (unsigned)((p.N + BLOCK_N - 1) / BLOCK_N), (unsigned)nz);
+    const int64_t num_tiles = ((p.M + BLOCK_M - 1) / BLOCK_M) * ((p.N + BLOCK_N - 1) / BLOCK_N) * nz;
+    const int sms = sm_count();
+    dim3 grid((unsigned)(num_tiles < sms ? num_tiles : sms));  // persistent: one CTA per SM walks the tile list
     kern<<<grid, NTHREADS, smem, st>>>(ah, al, bh, bl, p);
     OPTEX_LAUNCH_CHECK("rotate_gemm_kernel");
     return OPTEX_OK;
@@ -504,9 +586,10 @@ int launch(const CUtensorMap &ah, const CUtensorMap &al, const CUtensorMap &bh, 
 template <bool A_MN, bool B_MN, bool D_TRANS>
 int launch_n(int block_n, const CUtensorMap &ah, const CUtensorMap &al, const CUtensorMap &bh, const CUtensorMap &bl,
              Params p, int nz, cudaStream_t st) {
-    if (block_n == 64) return launch<64, A_MN, B_MN, D_TRANS>(ah, al, bh, bl, p, nz, st);
-    if (block_n == 128) return launch<128, A_MN, B_MN, D_TRANS>(ah, al, bh, bl, p, nz, st);
-    return launch<256, A_MN, B_MN, D_TRANS>(ah, al, bh, bl, p, nz, st);
+    // (a BK = 16 / 4-stage variant of the 3xTF32 wide tile exists as a template option; it measured slower: 64 vs 59 us)
+    if (block_n == 64) return launch<64, A_MN, B_MN, D_TRANS, 32>(ah, al, bh, bl, p, nz, st);
+    if (block_n == 128) return launch<128, A_MN, B_MN, D_TRANS, 32>(ah, al, bh, bl, p, nz, st);
+    return launch<256, A_MN, B_MN, D_TRANS, 32>(ah, al, bh, bl, p, nz, st);
 }
 
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -547,6 +630,7 @@ int gemm_tc(const TcGemm &g, cudaStream_t st) {
         nz = (int)((g.K + k_per_z - 1) / k_per_z);
     }
     const int bn = pick_block_n(g.M, g.N, nz);
+    const int bk = 32;  // must match launch_n()
     const float *ah_p = g.A, *al_p = g.A, *bh_p = g.B, *bl_p = g.B;
     bool conv_b = false;
     if (g.terms == 3) {
@@ -567,18 +651,18 @@ int gemm_tc(const TcGemm &g, cudaStream_t st) {
     bl_p += g.b_col0;
     CUtensorMap ah, al, bh, bl;
     if (g.a_mn) {
-        OPTEX_TRY(make_map_mnmajor(&ah, ah_p, g.K, g.M, BLOCK_M));
-        OPTEX_TRY(make_map_mnmajor(&al, al_p, g.K, g.M, BLOCK_M));
+        OPTEX_TRY(make_map_mnmajor(&ah, ah_p, g.K, g.M, BLOCK_M, 0, bk));
+        OPTEX_TRY(make_map_mnmajor(&al, al_p, g.K, g.M, BLOCK_M, 0, bk));
     } else {
-        OPTEX_TRY(make_map_kmajor(&ah, ah_p, g.M, g.K, BLOCK_M));
-        OPTEX_TRY(make_map_kmajor(&al, al_p, g.M, g.K, BLOCK_M));
+        OPTEX_TRY(make_map_kmajor(&ah, ah_p, g.M, g.K, BLOCK_M, bk));
+        OPTEX_TRY(make_map_kmajor(&al, al_p, g.M, g.K, BLOCK_M, bk));
     }
     if (g.b_mn) {
-        OPTEX_TRY(make_map_mnmajor(&bh, bh_p, g.K, g.N, bn, ldb));
-        OPTEX_TRY(make_map_mnmajor(&bl, bl_p, g.K, g.N, bn, ldb));
+        OPTEX_TRY(make_map_mnmajor(&bh, bh_p, g.K, g.N, bn, ldb, bk));
+        OPTEX_TRY(make_map_mnmajor(&bl, bl_p, g.K, g.N, bn, ldb, bk));
     } else {
-        OPTEX_TRY(make_map_kmajor(&bh, bh_p, g.N, g.K, bn));
-        OPTEX_TRY(make_map_kmajor(&bl, bl_p, g.N, g.K, bn));
+        OPTEX_TRY(make_map_kmajor(&bh, bh_p, g.N, g.K, bn, bk));
+        OPTEX_TRY(make_map_kmajor(&bl, bl_p, g.N, g.K, bn, bk));
     }
     Params p{};
     p.D = g.D; p.ldd = g.ldd; p.M = g.M; p.N = g.N; p.K = g.K;
@@ -586,6 +670,7 @@ int gemm_tc(const TcGemm &g, cudaStream_t st) {
     p.k_per_z = k_per_z; p.d_z_stride = g.d_z_stride;
     p.bias = g.bias; p.bias_hw = g.bias_hw > 0 ? g.bias_hw : 1; p.bias_ld = g.bias_ld;
     p.alpha = g.alpha; p.skip = g.skip; p.conv_a = p.terms == 3 ? 1 : 0; p.conv_b = conv_b ? 1 : 0;
+    p.nz = nz;
     if (g.d_trans) return launch_n<false, true, true>(bn, ah, al, bh, bl, p, nz, st);
     if (!g.a_mn && !g.b_mn) return launch_n<false, false, false>(bn, ah, al, bh, bl, p, nz, st);
     if (!g.a_mn && g.b_mn) return launch_n<false, true, false>(bn, ah, al, bh, bl, p, nz, st);
