@@ -286,7 +286,8 @@ def run_ours(a):
             rs = torch.empty(c, n, dtype=torch.float32, device=device)
             names = ["rotate_forward_P", "rotate_forward_S", f"{a.mode}_match", "rotate_inverse"]
             ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(K)]
-            mws = workspace(device, max(lib.optex_cdf_match_workspace_bytes(c, 256), 256))
+            mws = torch.empty(max(lib.optex_cdf_match_workspace_bytes(c, 256),
+                                  lib.optex_sort_match_workspace_bytes(c, n, n), 256), dtype=torch.uint8, device=device)
             for i in range(K):
                 p, s = sets[i % a.sets]
                 r = rots[i % K]
@@ -298,7 +299,7 @@ def run_ours(a):
                 if a.mode == "cdf":
                     call("optex_cdf_match", ptr(rp), ptr(rs), ptr(rp), c, n, n, 256, None, ptr(mws), mws.numel(), st)
                 else:
-                    call("optex_sort_match", ptr(rp), ptr(rs), ptr(rp), c, n, n, None, None, 0, st)
+                    call("optex_sort_match", ptr(rp), ptr(rs), ptr(rp), c, n, n, None, ptr(mws), mws.numel(), st)
                 ev[i][3].record()
                 call("optex_rotate_inverse", ptr(rp), ptr(r), ptr(outs[i % 2]), n, c, None, 0.0, st)
                 ev[i][4].record()

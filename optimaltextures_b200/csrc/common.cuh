@@ -112,6 +112,10 @@ size_t rotation_ws_bytes(int c, int batch);
 int random_rotations(float *R, int c, int batch, uint64_t seed, uint64_t first_counter, const double *gauss,
                      void *workspace, size_t workspace_bytes, cudaStream_t st);
 
+// sort_match.cu: exact 1-D OT per channel; `source_scratch` [c, n_s] is sorted in place
+int sort_match_inplace(const float *target, float *source_scratch, float *out, int c, int64_t n_t, int64_t n_s,
+                       int32_t *perm, cudaStream_t st);
+
 // cov_match.cu: closed-form Gaussian matching (histmatch.py:13-44) on NHWC-flattened data.
 //   out[n, c] = (X - mu_t) T^T + mu_s ;  T from chol / pca / sym of the two covariances
 size_t cov_match_ws_bytes(int64_t n_t, int64_t n_s, int c, int mode);

@@ -5,136 +5,186 @@
 //     idx = stable argsort(target_c);  ss = sort(source_c)
 //     out[idx[r]] = ss[((2r+1)*n_s) / (2*n_t)]
 //
-// One CTA per channel.  The whole channel lives in REGISTERS for the duration of
-// the sort (512 threads x up to 32 elements): a bitonic network whose
-// compare-exchange distance selects the exchange medium -
-//     distance <  E        : between registers of one thread (no memory traffic)
-//     distance <  32*E     : warp shuffles
-//     distance >= 32*E     : one bank-conflict-free round trip through shared memory
-// The target is sorted as 64-bit (ordered-key << 32 | pixel index) words, which makes
-// the network's result identical to a STABLE sort (ties broken by index, -0.0 == +0.0,
-// NaN last - torch.sort semantics), so the permutation is bit-exact.
+// One CTA per channel and per array, the whole channel on chip (512 threads x up to 32 items in registers):
+// a stable LSD radix sort, 6 bits per pass -
+//   count   : every thread counts the digits of its blocked chunk into private packed 16-bit counters
+//             (bank-conflict free, no atomics) and remembers each item's rank among its own equal digits
+//   scan    : one block-wide exclusive scan over the packed counters in (digit, thread) order
+//   scatter : item -> scanned base + local rank, through a swizzled shared-memory buffer, then back to registers
+// The target is sorted as 64-bit (ordered key << 32 | pixel index) words by its key only; LSD stability on the
+// blocked (index-ordered) arrangement makes ties come out in index order, so the permutation is bit-exact with
+// torch.sort(stable=True) (-0.0 == +0.0, NaN last).  The source is sorted keys-only, in place (it is scratch).
 #include "common.cuh"
 
 namespace optex {
 namespace {
 
 constexpr int NT = 512;
-constexpr int MAX_LOG_E = 5;  // 512 * 32 = 16384 elements per channel in registers
+constexpr int MAX_LOG_E = 5;   // 512 threads x 32 items = 16384 elements per channel
+constexpr int RB = 6;          // radix bits per pass: 64 digits, 6 passes over the 32-bit key
+constexpr int ROWS = 32;       // packed counter rows: row r holds digit r (low 16 bits) and digit r + 32 (high 16)
+constexpr int PASSES = 6;
 
 __device__ __forceinline__ uint32_t sort_key(float x) {
     if (x != x) return 0xffc00000u;  // canonical NaN sorts after +inf
     return f2ord(x + 0.0f);          // -0.0 + 0.0 == +0.0 : ties with +0.0 like torch
 }
 
-template <typename T>
-__device__ __forceinline__ T tmin(T a, T b) { return a < b ? a : b; }
-template <typename T>
-__device__ __forceinline__ T tmax(T a, T b) { return a < b ? b : a; }
-
-template <int LOG_E, int J, typename T>
-__device__ __forceinline__ void reg_stage(T (&v)[1 << LOG_E], int k, int gbase) {
+// counter array index with one pad word per 32: both the [row][thread] accesses of the counting phase and the
+// 32-consecutive-word segments of the raking scan are bank-conflict free
+__device__ __forceinline__ int cphys(int L) { return L + (L >> 5); }
+// item buffer index: position p = t*E + r is stored at t*E + (r ^ (t mod E)), so that the "thread t reads its
+// blocked chunk" accesses (fixed r across a warp) spread over all banks
+template <int LOG_E>
+__device__ __forceinline__ int bphys(int p) {
     constexpr int E = 1 << LOG_E;
-#pragma unroll
-    for (int r = 0; r < E; ++r) {
-        if ((r & J) == 0) {
-            bool up = (((gbase | r) & k) == 0);
-            T a = v[r], b = v[r | J];
-            T lo = tmin(a, b), hi = tmax(a, b);
-            v[r] = up ? lo : hi;
-            v[r | J] = up ? hi : lo;
-        }
-    }
+    return (p & ~(E - 1)) | ((p ^ (p >> LOG_E)) & (E - 1));
 }
 
-// Sort N2 = NT << LOG_E elements held as v[r] at global position (tid << LOG_E) | r, ascending.
-// xbuf: shared scratch of N2 elements of T.
+template <typename T>
+__device__ __forceinline__ uint32_t key_of(T v);
+template <>
+__device__ __forceinline__ uint32_t key_of<uint32_t>(uint32_t v) { return v; }
+template <>
+__device__ __forceinline__ uint32_t key_of<uint64_t>(uint64_t v) { return (uint32_t)(v >> 32); }
+
+// LSD radix sort of the CTA's NT << LOG_E items (blocked arrangement: thread t holds positions t*E .. t*E+E-1 in
+// v[]), stable, ascending by the 32-bit key.  On return the sorted sequence is in `buf` (swizzled by bphys) AND,
+// if `reload_last`, back in v[] in blocked arrangement.
+//   cnt : (ROWS * NT) * 33 / 32 words of packed 16-bit counters,  wsum : 32 words
 template <int LOG_E, typename T>
-__device__ __forceinline__ void bitonic_sort(T (&v)[1 << LOG_E], T *xbuf) {
+__device__ __forceinline__ void radix_sort_blocked(T (&v)[1 << LOG_E], T *buf, uint32_t *cnt, uint32_t *wsum,
+                                                   bool reload_last) {
     constexpr int E = 1 << LOG_E;
-    constexpr int N2 = NT * E;
-    const int tid = threadIdx.x;
-    const int gbase = tid << LOG_E;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #pragma unroll 1
-    for (int k = 2; k <= N2; k <<= 1) {
-        int j = k >> 1;
-        const bool up = ((gbase & k) == 0);  // valid whenever k >= E (bit k is above the register bits)
-#pragma unroll 1
-        for (; j >= 32 * E; j >>= 1) {
-            const int partner = tid ^ (j >> LOG_E);
-            const bool keep_min = (((gbase & j) == 0) == up);
+    for (int pass = 0; pass < PASSES; ++pass) {
+        const int shift = pass * RB;
+        // ---- count this thread's digits; remember every item's rank among the thread's equal digits
 #pragma unroll
-            for (int r = 0; r < E; ++r) xbuf[r * NT + tid] = v[r];
-            __syncthreads();
+        for (int r = 0; r < ROWS; ++r) cnt[cphys(r * NT + tid)] = 0u;
+        uint32_t local[(E + 3) / 4];
 #pragma unroll
-            for (int r = 0; r < E; ++r) {
-                T o = xbuf[r * NT + partner];
-                v[r] = keep_min ? tmin(v[r], o) : tmax(v[r], o);
+        for (int i = 0; i < (E + 3) / 4; ++i) local[i] = 0u;
+#pragma unroll
+        for (int i = 0; i < E; ++i) {
+            const uint32_t d = (key_of<T>(v[i]) >> shift) & 63u;
+            const int a = cphys((int)(d & 31u) * NT + tid);
+            const uint32_t sh = (d >> 5) * 16u;
+            const uint32_t c = cnt[a];
+            local[i >> 2] |= ((c >> sh) & 0xffu) << ((i & 3) * 8);  // < E <= 32
+            cnt[a] = c + (1u << sh);
+        }
+        __syncthreads();
+        // ---- exclusive scan of the packed counters in (row, thread) order = (digit, thread) order per 16-bit lane
+        {
+            const int base = tid * 32;  // this thread rakes linear entries [base, base + 32)
+            uint32_t sum = 0;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) sum += cnt[cphys(base + k)];
+            uint32_t incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += n;
             }
+            if (lane == 31) wsum[warp] = incl;
+            __syncthreads();
+            uint32_t woff = 0, total = 0;
+#pragma unroll
+            for (int w = 0; w < NT / 32; ++w) {
+                const uint32_t x = wsum[w];
+                if (w < warp) woff += x;
+                total += x;
+            }
+            // digits 32..63 (high lanes) come after all of digits 0..31 (the low-lane total)
+            uint32_t run = woff + incl - sum + (total << 16);
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                const int a = cphys(base + k);
+                const uint32_t c = cnt[a];
+                cnt[a] = run;
+                run += c;
+            }
+        }
+        __syncthreads();
+        // ---- scatter to the item's global rank for this digit
+#pragma unroll
+        for (int i = 0; i < E; ++i) {
+            const uint32_t d = (key_of<T>(v[i]) >> shift) & 63u;
+            const uint32_t basep = (cnt[cphys((int)(d & 31u) * NT + tid)] >> ((d >> 5) * 16u)) & 0xffffu;
+            const int pos = (int)(basep + ((local[i >> 2] >> ((i & 3) * 8)) & 0xffu));
+            buf[bphys<LOG_E>(pos)] = v[i];
+        }
+        __syncthreads();
+        if (pass + 1 < PASSES || reload_last) {
+#pragma unroll
+            for (int i = 0; i < E; ++i) v[i] = buf[bphys<LOG_E>(tid * E + i)];
             __syncthreads();
         }
-#pragma unroll 1
-        for (; j >= E; j >>= 1) {
-            const int lm = j >> LOG_E;
-            const bool keep_min = (((gbase & j) == 0) == up);
-#pragma unroll
-            for (int r = 0; r < E; ++r) {
-                T o = __shfl_xor_sync(0xffffffffu, v[r], lm);
-                v[r] = keep_min ? tmin(v[r], o) : tmax(v[r], o);
-            }
-        }
-        if (LOG_E >= 5) { if (j >= 16) { reg_stage<LOG_E, (LOG_E >= 5 ? 16 : 0)>(v, k, gbase); j >>= 1; } }
-        if (LOG_E >= 4) { if (j >= 8) { reg_stage<LOG_E, (LOG_E >= 4 ? 8 : 0)>(v, k, gbase); j >>= 1; } }
-        if (LOG_E >= 3) { if (j >= 4) { reg_stage<LOG_E, (LOG_E >= 3 ? 4 : 0)>(v, k, gbase); j >>= 1; } }
-        if (LOG_E >= 2) { if (j >= 2) { reg_stage<LOG_E, (LOG_E >= 2 ? 2 : 0)>(v, k, gbase); j >>= 1; } }
-        if (LOG_E >= 1) { if (j >= 1) { reg_stage<LOG_E, (LOG_E >= 1 ? 1 : 0)>(v, k, gbase); } }
     }
 }
 
+// smem carve-up shared by both kernels: [buf: N2 items of T][cnt: ROWS*NT*33/32 words][wsum: 32 words]
+template <int LOG_E, typename T>
+__host__ __device__ constexpr size_t radix_smem_bytes() {
+    return (size_t)(NT << LOG_E) * sizeof(T) + (size_t)(ROWS * NT / 32 * 33 + 32) * 4;
+}
+
+// ascending sort of every source channel, in place (values rewritten as floats in sorted order)
 template <int LOG_E>
 __global__ void __launch_bounds__(NT, 1)
-sort_match_kernel(const float *target, const float *__restrict__ source, float *out, int64_t n_t,
-                  int64_t n_s, int32_t *__restrict__ perm) {
+sort_source_kernel(float *src, int64_t n_s) {
     constexpr int E = 1 << LOG_E;
     constexpr int N2 = NT * E;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint64_t *xbuf = reinterpret_cast<uint64_t *>(smem_raw);                 // N2 x 8 B
-    uint32_t *ss = reinterpret_cast<uint32_t *>(smem_raw + (size_t)N2 * 8);  // N2 x 4 B
+    uint32_t *buf = reinterpret_cast<uint32_t *>(smem_raw);
+    uint32_t *cnt = buf + N2;
+    uint32_t *wsum = cnt + ROWS * NT / 32 * 33;
+    const int tid = threadIdx.x;
+    float *row = src + (int64_t)blockIdx.x * n_s;
+    for (int i = tid; i < N2; i += NT) buf[bphys<LOG_E>(i)] = i < n_s ? sort_key(row[i]) : 0xffffffffu;
+    __syncthreads();
+    uint32_t v[E];
+#pragma unroll
+    for (int i = 0; i < E; ++i) v[i] = buf[bphys<LOG_E>(tid * E + i)];
+    __syncthreads();
+    radix_sort_blocked<LOG_E, uint32_t>(v, buf, cnt, wsum, false);
+    for (int i = tid; i < n_s; i += NT) row[i] = ord2f(buf[bphys<LOG_E>(i)]);
+}
+
+// stable argsort of every target channel, then rank r receives sorted_source[((2r+1) n_s) / (2 n_t)]
+template <int LOG_E>
+__global__ void __launch_bounds__(NT, 1)
+sort_target_kernel(const float *target, const float *__restrict__ sorted_source, float *out, int64_t n_t, int64_t n_s,
+                   int32_t *__restrict__ perm) {
+    constexpr int E = 1 << LOG_E;
+    constexpr int N2 = NT * E;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t *buf = reinterpret_cast<uint64_t *>(smem_raw);
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(buf + N2);
+    uint32_t *wsum = cnt + ROWS * NT / 32 * 33;
     const int tid = threadIdx.x;
     const int ch = blockIdx.x;
-    const int gbase = tid << LOG_E;
-
-    {   // ---- ascending sort of the source channel (keys only)
-        const float *srow = source + (int64_t)ch * n_s;
-        uint32_t v[E];
-#pragma unroll
-        for (int r = 0; r < E; ++r) {
-            int i = r * NT + tid;
-            v[r] = i < n_s ? sort_key(__ldg(srow + i)) : 0xffffffffu;
-        }
-        bitonic_sort<LOG_E, uint32_t>(v, reinterpret_cast<uint32_t *>(xbuf));
-#pragma unroll
-        for (int r = 0; r < E; ++r) ss[gbase + r] = v[r];
-    }
-    // ---- stable argsort of the target channel
     const float *trow = target + (int64_t)ch * n_t;
+    for (int i = tid; i < N2; i += NT)
+        buf[bphys<LOG_E>(i)] = i < n_t ? ((uint64_t)sort_key(trow[i]) << 32) | (uint32_t)i : ~0ull;
+    __syncthreads();
     uint64_t v[E];
 #pragma unroll
-    for (int r = 0; r < E; ++r) {
-        int i = r * NT + tid;
-        v[r] = i < n_t ? ((uint64_t)sort_key(trow[i]) << 32) | (uint32_t)i : ~0ull;
-    }
-    bitonic_sort<LOG_E, uint64_t>(v, xbuf);
-    __syncthreads();  // ss visible; xbuf free
-    // ---- rank r of the target receives the mid-point quantile of the sorted source
-    float *stage = reinterpret_cast<float *>(xbuf);
+    for (int i = 0; i < E; ++i) v[i] = buf[bphys<LOG_E>(tid * E + i)];
+    __syncthreads();
+    radix_sort_blocked<LOG_E, uint64_t>(v, buf, cnt, wsum, true);
+    // ---- rank g = tid*E + i ; buf is free again (everything was reloaded and synchronised)
+    float *stage = reinterpret_cast<float *>(buf);
+    const float *ss = sorted_source + (int64_t)ch * n_s;
 #pragma unroll
-    for (int r = 0; r < E; ++r) {
-        int g = gbase + r;
+    for (int i = 0; i < E; ++i) {
+        const int g = tid * E + i;
         if (g < n_t) {
-            uint32_t idx = (uint32_t)v[r];
-            int64_t q = ((2 * (int64_t)g + 1) * n_s) / (2 * n_t);
-            stage[idx] = ord2f(ss[q]);
+            const uint32_t idx = (uint32_t)v[i];
+            const int64_t q = ((2 * (int64_t)g + 1) * n_s) / (2 * n_t);
+            stage[idx] = __ldg(ss + q);
             if (perm) perm[(int64_t)ch * n_t + g] = (int32_t)idx;
         }
     }
@@ -144,17 +194,22 @@ sort_match_kernel(const float *target, const float *__restrict__ source, float *
 }
 
 template <int LOG_E>
-int launch_sort(const float *t, const float *s, float *out, int c, int64_t n_t, int64_t n_s, int32_t *perm,
+int launch_sort(const float *t, float *s_sorted, float *out, int c, int64_t n_t, int64_t n_s, int32_t *perm,
                 cudaStream_t st) {
-    size_t smem = (size_t)(NT << LOG_E) * 12;
+    constexpr size_t smem_s = radix_smem_bytes<LOG_E, uint32_t>();
+    constexpr size_t smem_t = radix_smem_bytes<LOG_E, uint64_t>();
     static bool attr_done = false;
     if (!attr_done) {
-        OPTEX_CUDA(cudaFuncSetAttribute(sort_match_kernel<LOG_E>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem));
+        OPTEX_CUDA(cudaFuncSetAttribute(sort_source_kernel<LOG_E>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem_s));
+        OPTEX_CUDA(cudaFuncSetAttribute(sort_target_kernel<LOG_E>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem_t));
         attr_done = true;
     }
-    sort_match_kernel<LOG_E><<<c, NT, smem, st>>>(t, s, out, n_t, n_s, perm);
-    OPTEX_LAUNCH_CHECK("sort_match_kernel");
+    sort_source_kernel<LOG_E><<<c, NT, smem_s, st>>>(s_sorted, n_s);
+    OPTEX_LAUNCH_CHECK("sort_source_kernel");
+    sort_target_kernel<LOG_E><<<c, NT, smem_t, st>>>(t, s_sorted, out, n_t, n_s, perm);
+    OPTEX_LAUNCH_CHECK("sort_target_kernel");
     return OPTEX_OK;
 }
 
@@ -164,14 +219,37 @@ int launch_sort(const float *t, const float *s, float *out, int c, int64_t n_t, 
 using namespace optex;
 
 extern "C" size_t optex_sort_match_workspace_bytes(int c, int64_t n_t, int64_t n_s) {
-    (void)c; (void)n_t; (void)n_s;
-    return 0;  // the in-register path needs no global scratch
+    (void)n_t;
+    if (c <= 0 || n_s <= 0) return 0;
+    return align_up(sizeof(float) * (size_t)c * (size_t)n_s, 256);  // sorted copy of the source
 }
+
+namespace optex {
+// `source_scratch` is sorted IN PLACE (the OT step hands over its own rotated-style buffer)
+int sort_match_inplace(const float *target, float *source_scratch, float *out, int c, int64_t n_t, int64_t n_s,
+                       int32_t *perm, cudaStream_t st) {
+    int64_t n = n_t > n_s ? n_t : n_s;
+    if (n > (int64_t)NT << MAX_LOG_E) {
+        set_error("optex_sort_match: %lld elements per channel exceed the on-chip sort capacity (%d)",
+                  (long long)n, NT << MAX_LOG_E);
+        return OPTEX_ESIZE;
+    }
+    int log_e = 0;
+    while (((int64_t)NT << log_e) < n) ++log_e;
+    switch (log_e) {
+        case 0: return launch_sort<0>(target, source_scratch, out, c, n_t, n_s, perm, st);
+        case 1: return launch_sort<1>(target, source_scratch, out, c, n_t, n_s, perm, st);
+        case 2: return launch_sort<2>(target, source_scratch, out, c, n_t, n_s, perm, st);
+        case 3: return launch_sort<3>(target, source_scratch, out, c, n_t, n_s, perm, st);
+        case 4: return launch_sort<4>(target, source_scratch, out, c, n_t, n_s, perm, st);
+        default: return launch_sort<5>(target, source_scratch, out, c, n_t, n_s, perm, st);
+    }
+}
+}  // namespace optex
 
 extern "C" int optex_sort_match(const float *target, const float *source, float *out, int c, int64_t n_t,
                                 int64_t n_s, int32_t *perm, void *workspace, size_t workspace_bytes,
                                 void *stream) {
-    (void)workspace; (void)workspace_bytes;
     OPTEX_TRY(require_sm100());
     if (c < 0 || n_t < 0 || n_s < 0) {
         set_error("optex_sort_match: negative size");
@@ -186,21 +264,12 @@ extern "C" int optex_sort_match(const float *target, const float *source, float 
         set_error("optex_sort_match: NULL pointer");
         return OPTEX_EINVAL;
     }
-    int64_t n = n_t > n_s ? n_t : n_s;
-    if (n > (int64_t)NT << MAX_LOG_E) {
-        set_error("optex_sort_match: %lld elements per channel exceed the on-chip sort capacity (%d)",
-                  (long long)n, NT << MAX_LOG_E);
-        return OPTEX_ESIZE;
+    const size_t need = optex_sort_match_workspace_bytes(c, n_t, n_s);
+    if (!workspace || workspace_bytes < need) {
+        set_error("optex_sort_match: workspace %zu < %zu bytes", workspace_bytes, need);
+        return OPTEX_EWORKSPACE;
     }
-    int log_e = 0;
-    while (((int64_t)NT << log_e) < n) ++log_e;
     cudaStream_t st = (cudaStream_t)stream;
-    switch (log_e) {
-        case 0: return launch_sort<0>(target, source, out, c, n_t, n_s, perm, st);
-        case 1: return launch_sort<1>(target, source, out, c, n_t, n_s, perm, st);
-        case 2: return launch_sort<2>(target, source, out, c, n_t, n_s, perm, st);
-        case 3: return launch_sort<3>(target, source, out, c, n_t, n_s, perm, st);
-        case 4: return launch_sort<4>(target, source, out, c, n_t, n_s, perm, st);
-        default: return launch_sort<5>(target, source, out, c, n_t, n_s, perm, st);
-    }
+    OPTEX_CUDA(cudaMemcpyAsync(workspace, source, sizeof(float) * (size_t)c * (size_t)n_s, cudaMemcpyDeviceToDevice, st));
+    return sort_match_inplace(target, (float *)workspace, out, c, n_t, n_s, perm, st);
 }
