@@ -11,7 +11,7 @@
 //             (bank-conflict free, no atomics) and remembers each item's rank among its own equal digits
 //   scan    : one block-wide exclusive scan over the packed counters in (digit, thread) order
 //   scatter : item -> scanned base + local rank, through a swizzled shared-memory buffer, then back to registers
-// The target is sorted as 64-bit (ordered key << 32 | pixel index) words by its key only; LSD stability on the
+// The target carries its 16-bit pixel index as a payload and is sorted by the key only; LSD stability on the
 // blocked (index-ordered) arrangement makes ties come out in index order, so the permutation is bit-exact with
 // torch.sort(stable=True) (-0.0 == +0.0, NaN last).  The source is sorted keys-only, in place (it is scratch).
 #include "common.cuh"
@@ -19,11 +19,14 @@
 namespace optex {
 namespace {
 
+// 512 threads x 32 items, 6-bit digits.  (A 1024 x 16 / 5-bit / 7-pass configuration was measured: 489 vs 427 us.)
 constexpr int NT = 512;
 constexpr int MAX_LOG_E = 5;   // 512 threads x 32 items = 16384 elements per channel
 constexpr int RB = 6;          // radix bits per pass: 64 digits, 6 passes over the 32-bit key
-constexpr int ROWS = 32;       // packed counter rows: row r holds digit r (low 16 bits) and digit r + 32 (high 16)
-constexpr int PASSES = 6;
+constexpr int DIG = 1 << RB;
+constexpr int ROWS = DIG / 2;  // packed counter rows: row r holds digit r (low 16 bits) and digit r + ROWS (high 16)
+constexpr int PASSES = (32 + RB - 1) / RB;
+constexpr int SEG = ROWS;      // linear counter entries (ROWS * NT) raked per thread
 
 __device__ __forceinline__ uint32_t sort_key(float x) {
     if (x != x) return 0xffc00000u;  // canonical NaN sorts after +inf
@@ -41,19 +44,13 @@ __device__ __forceinline__ int bphys(int p) {
     return (p & ~(E - 1)) | ((p ^ (p >> LOG_E)) & (E - 1));
 }
 
-template <typename T>
-__device__ __forceinline__ uint32_t key_of(T v);
-template <>
-__device__ __forceinline__ uint32_t key_of<uint32_t>(uint32_t v) { return v; }
-template <>
-__device__ __forceinline__ uint32_t key_of<uint64_t>(uint64_t v) { return (uint32_t)(v >> 32); }
-
-// LSD radix sort of the CTA's NT << LOG_E items (blocked arrangement: thread t holds positions t*E .. t*E+E-1 in
-// v[]), stable, ascending by the 32-bit key.  On return the sorted sequence is in `buf` (swizzled by bphys) AND,
-// if `reload_last`, back in v[] in blocked arrangement.
+// LSD radix sort of the CTA's NT << LOG_E items (blocked arrangement: thread t holds positions t*E .. t*E+E-1),
+// stable, ascending by the 32-bit key k[]; PAYLOAD carries a 16-bit value (the pixel index) along, two per register.
+// On return the sorted sequence is in kbuf / pbuf (swizzled by bphys) AND, if `reload_last`, back in k[] / pl[].
 //   cnt : (ROWS * NT) * 33 / 32 words of packed 16-bit counters,  wsum : 32 words
-template <int LOG_E, typename T>
-__device__ __forceinline__ void radix_sort_blocked(T (&v)[1 << LOG_E], T *buf, uint32_t *cnt, uint32_t *wsum,
+template <int LOG_E, bool PAYLOAD>
+__device__ __forceinline__ void radix_sort_blocked(uint32_t (&k)[1 << LOG_E], uint32_t (&pl)[((1 << LOG_E) + 1) / 2],
+                                                   uint32_t *kbuf, uint16_t *pbuf, uint32_t *cnt, uint32_t *wsum,
                                                    bool reload_last) {
     constexpr int E = 1 << LOG_E;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -68,9 +65,9 @@ __device__ __forceinline__ void radix_sort_blocked(T (&v)[1 << LOG_E], T *buf, u
         for (int i = 0; i < (E + 3) / 4; ++i) local[i] = 0u;
 #pragma unroll
         for (int i = 0; i < E; ++i) {
-            const uint32_t d = (key_of<T>(v[i]) >> shift) & 63u;
-            const int a = cphys((int)(d & 31u) * NT + tid);
-            const uint32_t sh = (d >> 5) * 16u;
+            const uint32_t d = (k[i] >> shift) & (DIG - 1);
+            const int a = cphys((int)(d & (ROWS - 1)) * NT + tid);
+            const uint32_t sh = (d / ROWS) * 16u;
             const uint32_t c = cnt[a];
             local[i >> 2] |= ((c >> sh) & 0xffu) << ((i & 3) * 8);  // < E <= 32
             cnt[a] = c + (1u << sh);
@@ -78,10 +75,10 @@ __device__ __forceinline__ void radix_sort_blocked(T (&v)[1 << LOG_E], T *buf, u
         __syncthreads();
         // ---- exclusive scan of the packed counters in (row, thread) order = (digit, thread) order per 16-bit lane
         {
-            const int base = tid * 32;  // this thread rakes linear entries [base, base + 32)
+            const int base = tid * SEG;  // this thread rakes linear entries [base, base + SEG)
             uint32_t sum = 0;
 #pragma unroll
-            for (int k = 0; k < 32; ++k) sum += cnt[cphys(base + k)];
+            for (int j = 0; j < SEG; ++j) sum += cnt[cphys(base + j)];
             uint32_t incl = sum;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -97,11 +94,11 @@ __device__ __forceinline__ void radix_sort_blocked(T (&v)[1 << LOG_E], T *buf, u
                 if (w < warp) woff += x;
                 total += x;
             }
-            // digits 32..63 (high lanes) come after all of digits 0..31 (the low-lane total)
+            // the high-lane digits come after all of the low-lane digits (the low-lane total)
             uint32_t run = woff + incl - sum + (total << 16);
 #pragma unroll
-            for (int k = 0; k < 32; ++k) {
-                const int a = cphys(base + k);
+            for (int j = 0; j < SEG; ++j) {
+                const int a = cphys(base + j);
                 const uint32_t c = cnt[a];
                 cnt[a] = run;
                 run += c;
@@ -111,24 +108,31 @@ __device__ __forceinline__ void radix_sort_blocked(T (&v)[1 << LOG_E], T *buf, u
         // ---- scatter to the item's global rank for this digit
 #pragma unroll
         for (int i = 0; i < E; ++i) {
-            const uint32_t d = (key_of<T>(v[i]) >> shift) & 63u;
-            const uint32_t basep = (cnt[cphys((int)(d & 31u) * NT + tid)] >> ((d >> 5) * 16u)) & 0xffffu;
-            const int pos = (int)(basep + ((local[i >> 2] >> ((i & 3) * 8)) & 0xffu));
-            buf[bphys<LOG_E>(pos)] = v[i];
+            const uint32_t d = (k[i] >> shift) & (DIG - 1);
+            const uint32_t basep = (cnt[cphys((int)(d & (ROWS - 1)) * NT + tid)] >> ((d / ROWS) * 16u)) & 0xffffu;
+            const int pos = bphys<LOG_E>((int)(basep + ((local[i >> 2] >> ((i & 3) * 8)) & 0xffu)));
+            kbuf[pos] = k[i];
+            if (PAYLOAD) pbuf[pos] = (uint16_t)(pl[i >> 1] >> ((i & 1) * 16));
         }
         __syncthreads();
         if (pass + 1 < PASSES || reload_last) {
 #pragma unroll
-            for (int i = 0; i < E; ++i) v[i] = buf[bphys<LOG_E>(tid * E + i)];
+            for (int i = 0; i < (E + 1) / 2; ++i) pl[i] = 0u;
+#pragma unroll
+            for (int i = 0; i < E; ++i) {
+                const int pos = bphys<LOG_E>(tid * E + i);
+                k[i] = kbuf[pos];
+                if (PAYLOAD) pl[i >> 1] |= (uint32_t)pbuf[pos] << ((i & 1) * 16);
+            }
             __syncthreads();
         }
     }
 }
 
-// smem carve-up shared by both kernels: [buf: N2 items of T][cnt: ROWS*NT*33/32 words][wsum: 32 words]
-template <int LOG_E, typename T>
+// smem carve-up: [kbuf: N2 u32][cnt: ROWS*NT*33/32 words][wsum: 32 words][pbuf: N2 u16 (payload only)]
+template <int LOG_E, bool PAYLOAD>
 __host__ __device__ constexpr size_t radix_smem_bytes() {
-    return (size_t)(NT << LOG_E) * sizeof(T) + (size_t)(ROWS * NT / 32 * 33 + 32) * 4;
+    return (size_t)(NT << LOG_E) * (PAYLOAD ? 6 : 4) + (size_t)(ROWS * NT / 32 * 33 + 32) * 4;
 }
 
 // ascending sort of every source channel, in place (values rewritten as floats in sorted order)
@@ -138,19 +142,19 @@ sort_source_kernel(float *src, int64_t n_s) {
     constexpr int E = 1 << LOG_E;
     constexpr int N2 = NT * E;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint32_t *buf = reinterpret_cast<uint32_t *>(smem_raw);
-    uint32_t *cnt = buf + N2;
+    uint32_t *kbuf = reinterpret_cast<uint32_t *>(smem_raw);
+    uint32_t *cnt = kbuf + N2;
     uint32_t *wsum = cnt + ROWS * NT / 32 * 33;
     const int tid = threadIdx.x;
     float *row = src + (int64_t)blockIdx.x * n_s;
-    for (int i = tid; i < N2; i += NT) buf[bphys<LOG_E>(i)] = i < n_s ? sort_key(row[i]) : 0xffffffffu;
+    for (int i = tid; i < N2; i += NT) kbuf[bphys<LOG_E>(i)] = i < n_s ? sort_key(row[i]) : 0xffffffffu;
     __syncthreads();
-    uint32_t v[E];
+    uint32_t k[E], pl[(E + 1) / 2];
 #pragma unroll
-    for (int i = 0; i < E; ++i) v[i] = buf[bphys<LOG_E>(tid * E + i)];
+    for (int i = 0; i < E; ++i) k[i] = kbuf[bphys<LOG_E>(tid * E + i)];
     __syncthreads();
-    radix_sort_blocked<LOG_E, uint32_t>(v, buf, cnt, wsum, false);
-    for (int i = tid; i < n_s; i += NT) row[i] = ord2f(buf[bphys<LOG_E>(i)]);
+    radix_sort_blocked<LOG_E, false>(k, pl, kbuf, nullptr, cnt, wsum, false);
+    for (int i = tid; i < n_s; i += NT) row[i] = ord2f(kbuf[bphys<LOG_E>(i)]);
 }
 
 // stable argsort of every target channel, then rank r receives sorted_source[((2r+1) n_s) / (2 n_t)]
@@ -161,28 +165,33 @@ sort_target_kernel(const float *target, const float *__restrict__ sorted_source,
     constexpr int E = 1 << LOG_E;
     constexpr int N2 = NT * E;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint64_t *buf = reinterpret_cast<uint64_t *>(smem_raw);
-    uint32_t *cnt = reinterpret_cast<uint32_t *>(buf + N2);
+    uint32_t *kbuf = reinterpret_cast<uint32_t *>(smem_raw);
+    uint32_t *cnt = kbuf + N2;
     uint32_t *wsum = cnt + ROWS * NT / 32 * 33;
+    uint16_t *pbuf = reinterpret_cast<uint16_t *>(wsum + 32);
     const int tid = threadIdx.x;
     const int ch = blockIdx.x;
     const float *trow = target + (int64_t)ch * n_t;
-    for (int i = tid; i < N2; i += NT)
-        buf[bphys<LOG_E>(i)] = i < n_t ? ((uint64_t)sort_key(trow[i]) << 32) | (uint32_t)i : ~0ull;
+    for (int i = tid; i < N2; i += NT) kbuf[bphys<LOG_E>(i)] = i < n_t ? sort_key(trow[i]) : 0xffffffffu;
     __syncthreads();
-    uint64_t v[E];
+    uint32_t k[E], pl[(E + 1) / 2];
 #pragma unroll
-    for (int i = 0; i < E; ++i) v[i] = buf[bphys<LOG_E>(tid * E + i)];
+    for (int i = 0; i < (E + 1) / 2; ++i) pl[i] = 0u;
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+        k[i] = kbuf[bphys<LOG_E>(tid * E + i)];
+        pl[i >> 1] |= (uint32_t)((tid * E + i) & 0xffff) << ((i & 1) * 16);  // pixel index < 16384
+    }
     __syncthreads();
-    radix_sort_blocked<LOG_E, uint64_t>(v, buf, cnt, wsum, true);
-    // ---- rank g = tid*E + i ; buf is free again (everything was reloaded and synchronised)
-    float *stage = reinterpret_cast<float *>(buf);
+    radix_sort_blocked<LOG_E, true>(k, pl, kbuf, pbuf, cnt, wsum, true);
+    // ---- rank g = tid*E + i ; kbuf is free again (everything was reloaded and synchronised)
+    float *stage = reinterpret_cast<float *>(kbuf);
     const float *ss = sorted_source + (int64_t)ch * n_s;
 #pragma unroll
     for (int i = 0; i < E; ++i) {
         const int g = tid * E + i;
         if (g < n_t) {
-            const uint32_t idx = (uint32_t)v[i];
+            const uint32_t idx = (pl[i >> 1] >> ((i & 1) * 16)) & 0xffffu;
             const int64_t q = ((2 * (int64_t)g + 1) * n_s) / (2 * n_t);
             stage[idx] = __ldg(ss + q);
             if (perm) perm[(int64_t)ch * n_t + g] = (int32_t)idx;
@@ -196,8 +205,8 @@ sort_target_kernel(const float *target, const float *__restrict__ sorted_source,
 template <int LOG_E>
 int launch_sort(const float *t, float *s_sorted, float *out, int c, int64_t n_t, int64_t n_s, int32_t *perm,
                 cudaStream_t st) {
-    constexpr size_t smem_s = radix_smem_bytes<LOG_E, uint32_t>();
-    constexpr size_t smem_t = radix_smem_bytes<LOG_E, uint64_t>();
+    constexpr size_t smem_s = radix_smem_bytes<LOG_E, false>();
+    constexpr size_t smem_t = radix_smem_bytes<LOG_E, true>();
     static bool attr_done = false;
     if (!attr_done) {
         OPTEX_CUDA(cudaFuncSetAttribute(sort_source_kernel<LOG_E>, cudaFuncAttributeMaxDynamicSharedMemorySize,
