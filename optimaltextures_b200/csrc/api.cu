@@ -71,12 +71,16 @@ static bool want_tc(bool &forced) {
 static int tc_terms() { return g_gemm_mode.load() == OPTEX_GEMM_TF32 ? 1 : 3; }
 
 // Xt[c, n] = (X R)^T   or  XR[n, c] = X R            optex.py:170-171
+// colrange (optional): fold the per-channel range into the GEMM epilogue; *range_done reports whether it happened
 static int rotate_forward(const float *X, const float *R, float *dst, int64_t n, int c, bool transposed,
-                          cudaStream_t st, int c0 = 0, int nc = -1) {
+                          cudaStream_t st, int c0 = 0, int nc = -1, uint32_t *colrange = nullptr,
+                          bool *range_done = nullptr) {
     if (nc < 0) nc = c;
+    if (range_done) *range_done = false;
     bool forced;
     if (want_tc(forced)) {
-        int rc = gemm_tc_rotate_forward(X, R, dst, n, c, transposed, tc_terms(), st, c0, nc);
+        int rc = gemm_tc_rotate_forward(X, R, dst, n, c, transposed, tc_terms(), st, c0, nc, colrange);
+        if (rc == OPTEX_OK && range_done) *range_done = colrange != nullptr;
         if (rc != OPTEX_ENOTSUP) return rc;
         if (forced) {
             set_error("rotation GEMM: shape (n=%lld, c=%d, block %d+%d) is outside the tensor-core path's TMA "
@@ -153,6 +157,16 @@ static int ot_step_impl(const float *P, const float *S, const float *R, float *o
     if (!ar.ok()) {
         set_error("optex_ot_step: workspace %zu < %zu bytes", ws_bytes, optex_ot_workspace_bytes(n_p, n_s, c, mode));
         return OPTEX_EWORKSPACE;
+    }
+    if (mode == OPTEX_MODE_CDF) {
+        // the forward rotations fold the per-channel range (histmatch.py:52-53) into their epilogues
+        uint32_t *minmax = (uint32_t *)mw;
+        bool r1 = false, r2 = false;
+        OPTEX_TRY(fill_u32(minmax, 2 * (int64_t)c, 0xffffffffu, st));
+        OPTEX_TRY(rotate_forward(P, R, rp, n_p, c, true, st, 0, -1, minmax, &r1));
+        OPTEX_TRY(rotate_forward(S, R, rs, n_s, c, true, st, 0, -1, minmax, &r2));
+        OPTEX_TRY(cdf_match_core(rp, rs, mt, c, n_p, n_s, 256, nullptr, mw, mws, r1 && r2, st));
+        return rotate_inverse(mt, true, R, out, n_p, c, content, strength, st);
     }
     OPTEX_TRY(rotate_forward(P, R, rp, n_p, c, true, st));
     OPTEX_TRY(rotate_forward(S, R, rs, n_s, c, true, st));

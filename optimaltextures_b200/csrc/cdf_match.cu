@@ -114,11 +114,11 @@ __device__ __forceinline__ float interp_at(float x, const float *xp, const float
 }
 
 // ---- kernels ----------------------------------------------------------------
-__global__ void cdf_init_kernel(uint32_t *minmax, uint32_t *hist, int c, int bins) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < 2 * (int64_t)c) minmax[i] = (i & 1) ? 0u : 0xffffffffu;  // [c][0]=min, [c][1]=max
-    if (i < 2 * (int64_t)c * bins) hist[i] = 0u;
-}
+// Per-channel range slots minmax[c][2]: [0] = f2ord(min), [1] = ~f2ord(max).  Both are folded with atomicMin, so
+// the whole array initialises with one cudaMemsetAsync(0xFF) and the forward-rotation GEMM can produce the range
+// in its epilogue (gemm_tcgen05.cu), saving a full read pass over the rotated features.
+__device__ __forceinline__ float range_lo(const uint32_t *minmax, int ch) { return ord2f(minmax[2 * ch]); }
+__device__ __forceinline__ float range_hi(const uint32_t *minmax, int ch) { return ord2f(~minmax[2 * ch + 1]); }
 
 // lo = min(t.min(), s.min()); hi = max(t.max(), s.max())     histmatch.py:52-53
 __global__ void __launch_bounds__(NT)
@@ -144,7 +144,7 @@ cdf_range_kernel(const float *__restrict__ t, const float *__restrict__ s, int64
         mx = warp_max(mx);
         if (threadIdx.x == 0 && mn <= mx) {
             atomicMin(&minmax[2 * ch], f2ord(mn));
-            atomicMax(&minmax[2 * ch + 1], f2ord(mx));
+            atomicMin(&minmax[2 * ch + 1], ~f2ord(mx));
         }
     }
 }
@@ -210,7 +210,7 @@ cdf_hist_kernel(const float *__restrict__ t, const float *__restrict__ s, int64_
     const int ch = blockIdx.y;
     for (int i = threadIdx.x; i < bins; i += NTH_HIST) acc[i] = 0u;
     __syncthreads();
-    HistRange hr(ord2f(minmax[2 * ch]), ord2f(minmax[2 * ch + 1]), bins);
+    HistRange hr(range_lo(minmax, ch), range_hi(minmax, ch), bins);
     // blockIdx.z == 0 counts the target slice, 1 the source slice (twice the warps in flight)
     int64_t b, e;
     if (blockIdx.z == 0) {
@@ -271,7 +271,7 @@ cdf_tables_kernel(const uint32_t *__restrict__ minmax, const uint32_t *__restric
     float *edges = smem_f32, *remap = edges + bins, *tc = remap + bins, *sc = tc + bins;
     uint32_t *cnt = reinterpret_cast<uint32_t *>(sc + bins);
     const int ch = blockIdx.x;
-    const float lo = ord2f(minmax[2 * ch]), hi = ord2f(minmax[2 * ch + 1]);
+    const float lo = range_lo(minmax, ch), hi = range_hi(minmax, ch);
     build_tables(hist + (int64_t)ch * 2 * bins, lo, hi, bins, edges, remap, tc, sc, cnt);
     float *o = tbl + (int64_t)ch * 4 * bins;
     const int last = bins - 1;
@@ -304,7 +304,7 @@ cdf_apply_kernel(const float *t, float *out, int64_t n_t, const uint32_t *__rest
     const bool mono = g[3 * bins] != 0.f;
     __syncthreads();
     const float *edges = tb, *remap = tb + bins, *slope = tb + 2 * bins;
-    const float lo = ord2f(minmax[2 * ch]), hi = ord2f(minmax[2 * ch + 1]);
+    const float lo = range_lo(minmax, ch), hi = range_hi(minmax, ch);
     const float inv = hi > lo ? (float)bins / (hi - lo) : 0.f;
     const int last = bins - 1;
     auto one = [&](float x) {
@@ -374,6 +374,82 @@ extern "C" size_t optex_cdf_match_workspace_bytes(int c, int bins) {
            align_up(sizeof(float) * (4 * (size_t)c * bins + 4), 256);
 }
 
+namespace optex {
+size_t cdf_minmax_bytes(int c) { return sizeof(uint32_t) * 2 * (size_t)c; }
+
+namespace {
+__global__ void fill_u32_kernel(uint32_t *p, int64_t n, uint32_t v) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+}  // namespace
+// (a plain kernel: cudaMemsetAsync on a few KB measured ~10x slower than this launch)
+int fill_u32(uint32_t *p, int64_t n, uint32_t v, cudaStream_t st) {
+    if (n <= 0) return OPTEX_OK;
+    fill_u32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, n, v);
+    OPTEX_LAUNCH_CHECK("fill_u32_kernel");
+    return OPTEX_OK;
+}
+
+// have_range: minmax (the first 2c words of `workspace`, initialised to 0xFF bytes by the caller) already holds
+// the per-channel range - the forward-rotation GEMM folded it in its epilogue.
+int cdf_match_core(const float *target, const float *source, float *out, int c, int64_t n_t, int64_t n_s, int bins,
+                   float *tables, void *workspace, size_t workspace_bytes, bool have_range, cudaStream_t st) {
+    if (n_t >= (1 << 24) || n_s >= (1 << 24)) {
+        set_error("optex_cdf_match: n >= 2^24 per channel (fp32 cumsum of the reference stops being exact)");
+        return OPTEX_ESIZE;
+    }
+    if (c > 65535) {
+        set_error("optex_cdf_match: c > 65535");
+        return OPTEX_ESIZE;
+    }
+    Arena ar(workspace, workspace_bytes);
+    uint32_t *minmax = ar.take<uint32_t>(2 * (size_t)c);
+    uint32_t *hist = ar.take<uint32_t>(2 * (size_t)c * bins);
+    float *tbl = ar.take<float>(4 * (size_t)c * bins + 4);
+    if (!ar.ok()) {
+        set_error("optex_cdf_match: workspace %zu < %zu", workspace_bytes, optex_cdf_match_workspace_bytes(c, bins));
+        return OPTEX_EWORKSPACE;
+    }
+    const int t_vec = aligned16(target) && (n_t % 4 == 0);
+    const int s_vec = aligned16(source) && (n_s % 4 == 0);
+    const int o_vec = t_vec && aligned16(out);
+    const int64_t n_big = n_t > n_s ? n_t : n_s;
+    if (!have_range) {
+        OPTEX_TRY(fill_u32(minmax, 2 * (int64_t)c, 0xffffffffu, st));
+        dim3 grid((unsigned)cdf_splits(c, n_big), (unsigned)c);
+        cdf_range_kernel<<<grid, NT, 0, st>>>(target, source, n_t, n_s, minmax, t_vec, s_vec);
+        OPTEX_LAUNCH_CHECK("cdf_range_kernel");
+    }
+    const bool priv = (bins % 4 == 0) && bins <= PRIV_MAX_BINS;
+    // histogram grid: one CTA per channel and array unless that leaves SMs idle and the slices stay long
+    int64_t hs = (2LL * sm_count() + c - 1) / c, hcap = (n_big + 32767) / 32768;
+    dim3 grid_h((unsigned)(hs < hcap ? (hs < 1 ? 1 : hs) : (hcap < 1 ? 1 : hcap)), (unsigned)c, 2);
+    if (grid_h.x > 1)  // several CTAs add into one histogram: it has to start at zero
+        OPTEX_TRY(fill_u32(hist, 2 * (int64_t)c * bins, 0u, st));
+    if (priv) {
+        size_t smem = sizeof(uint32_t) * (2 * (size_t)bins + (size_t)(bins / 4) * NTH_HIST);
+        static bool attr_done = false;
+        if (!attr_done) {
+            OPTEX_CUDA(cudaFuncSetAttribute(cdf_hist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)(sizeof(uint32_t) * (2 * PRIV_MAX_BINS + (PRIV_MAX_BINS / 4) * NTH_HIST))));
+            attr_done = true;
+        }
+        cdf_hist_kernel<true><<<grid_h, NTH_HIST, smem, st>>>(target, source, n_t, n_s, minmax, hist, bins, t_vec, s_vec);
+    } else {
+        cdf_hist_kernel<false><<<grid_h, NTH_HIST, sizeof(uint32_t) * 2 * bins, st>>>(target, source, n_t, n_s, minmax,
+                                                                                   hist, bins, t_vec, s_vec);
+    }
+    OPTEX_LAUNCH_CHECK("cdf_hist_kernel");
+    cdf_tables_kernel<<<c, NT, sizeof(float) * 6 * bins, st>>>(minmax, hist, bins, tbl, tables);
+    OPTEX_LAUNCH_CHECK("cdf_tables_kernel");
+    dim3 grid_a((unsigned)cdf_splits(c, n_t), (unsigned)c);
+    cdf_apply_kernel<<<grid_a, NT, 0, st>>>(target, out, n_t, minmax, tbl, bins, o_vec);
+    OPTEX_LAUNCH_CHECK("cdf_apply_kernel");
+    return OPTEX_OK;
+}
+}  // namespace optex
+
 extern "C" int optex_cdf_match(const float *target, const float *source, float *out, int c, int64_t n_t,
                                int64_t n_s, int bins, float *tables, void *workspace,
                                size_t workspace_bytes, void *stream) {
@@ -395,58 +471,8 @@ extern "C" int optex_cdf_match(const float *target, const float *source, float *
         set_error("optex_cdf_match: NULL pointer");
         return OPTEX_EINVAL;
     }
-    if (n_t >= (1 << 24) || n_s >= (1 << 24)) {
-        set_error("optex_cdf_match: n >= 2^24 per channel (fp32 cumsum of the reference stops being exact)");
-        return OPTEX_ESIZE;
-    }
-    if (c > 65535) {
-        set_error("optex_cdf_match: c > 65535");
-        return OPTEX_ESIZE;
-    }
-    Arena ar(workspace, workspace_bytes);
-    uint32_t *minmax = ar.take<uint32_t>(2 * (size_t)c);
-    uint32_t *hist = ar.take<uint32_t>(2 * (size_t)c * bins);
-    float *tbl = ar.take<float>(4 * (size_t)c * bins + 4);
-    if (!ar.ok()) {
-        set_error("optex_cdf_match: workspace %zu < %zu", workspace_bytes, optex_cdf_match_workspace_bytes(c, bins));
-        return OPTEX_EWORKSPACE;
-    }
-    cudaStream_t st = (cudaStream_t)stream;
-    const int t_vec = aligned16(target) && (n_t % 4 == 0);
-    const int s_vec = aligned16(source) && (n_s % 4 == 0);
-    const int o_vec = t_vec && aligned16(out);
-    const int64_t n_big = n_t > n_s ? n_t : n_s;
-    dim3 grid((unsigned)cdf_splits(c, n_big), (unsigned)c);
-
-    int64_t init_n = 2LL * c * bins;
-    cdf_init_kernel<<<(unsigned)((init_n + 255) / 256), 256, 0, st>>>(minmax, hist, c, bins);
-    OPTEX_LAUNCH_CHECK("cdf_init_kernel");
-    cdf_range_kernel<<<grid, NT, 0, st>>>(target, source, n_t, n_s, minmax, t_vec, s_vec);
-    OPTEX_LAUNCH_CHECK("cdf_range_kernel");
-    const bool priv = (bins % 4 == 0) && bins <= PRIV_MAX_BINS;
-    // histogram grid: one CTA per channel unless that leaves SMs idle and the slices stay long
-    int64_t hs = (2LL * sm_count() + c - 1) / c, hcap = (n_big + 32767) / 32768;
-    dim3 grid_h((unsigned)(hs < hcap ? (hs < 1 ? 1 : hs) : (hcap < 1 ? 1 : hcap)), (unsigned)c, 2);
-    if (priv) {
-        size_t smem = sizeof(uint32_t) * (2 * (size_t)bins + (size_t)(bins / 4) * NTH_HIST);
-        static bool attr_done = false;
-        if (!attr_done) {
-            OPTEX_CUDA(cudaFuncSetAttribute(cdf_hist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)(sizeof(uint32_t) * (2 * PRIV_MAX_BINS + (PRIV_MAX_BINS / 4) * NTH_HIST))));
-            attr_done = true;
-        }
-        cdf_hist_kernel<true><<<grid_h, NTH_HIST, smem, st>>>(target, source, n_t, n_s, minmax, hist, bins, t_vec, s_vec);
-    } else {
-        cdf_hist_kernel<false><<<grid_h, NTH_HIST, sizeof(uint32_t) * 2 * bins, st>>>(target, source, n_t, n_s, minmax,
-                                                                                   hist, bins, t_vec, s_vec);
-    }
-    OPTEX_LAUNCH_CHECK("cdf_hist_kernel");
-    cdf_tables_kernel<<<c, NT, sizeof(float) * 6 * bins, st>>>(minmax, hist, bins, tbl, tables);
-    OPTEX_LAUNCH_CHECK("cdf_tables_kernel");
-    dim3 grid_a((unsigned)cdf_splits(c, n_t), (unsigned)c);
-    cdf_apply_kernel<<<grid_a, NT, 0, st>>>(target, out, n_t, minmax, tbl, bins, o_vec);
-    OPTEX_LAUNCH_CHECK("cdf_apply_kernel");
-    return OPTEX_OK;
+    return cdf_match_core(target, source, out, c, n_t, n_s, bins, tables, workspace, workspace_bytes, false,
+                          (cudaStream_t)stream);
 }
 
 extern "C" int optex_interp(const float *x, const float *xp, const float *fp, float *out, int64_t n, int len,

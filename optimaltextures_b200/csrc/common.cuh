@@ -112,6 +112,13 @@ size_t rotation_ws_bytes(int c, int batch);
 int random_rotations(float *R, int c, int batch, uint64_t seed, uint64_t first_counter, const double *gauss,
                      void *workspace, size_t workspace_bytes, cudaStream_t st);
 
+// cdf_match.cu: workspace = [minmax: 2c u32][hist][tables]; have_range: the forward GEMMs already folded the
+// per-channel range into minmax (which the caller initialised to 0xFF bytes)
+size_t cdf_minmax_bytes(int c);
+int fill_u32(uint32_t *p, int64_t n, uint32_t v, cudaStream_t st);
+int cdf_match_core(const float *target, const float *source, float *out, int c, int64_t n_t, int64_t n_s, int bins,
+                   float *tables, void *workspace, size_t workspace_bytes, bool have_range, cudaStream_t st);
+
 // sort_match.cu: exact 1-D OT per channel; `source_scratch` [c, n_s] is sorted in place
 int sort_match_inplace(const float *target, float *source_scratch, float *out, int c, int64_t n_t, int64_t n_s,
                        int32_t *perm, cudaStream_t st);

@@ -33,13 +33,14 @@ struct TcGemm {
     int64_t bias_hw, bias_ld;
     float alpha;
     const int *skip;
+    uint32_t *colrange;  // d_trans only: per output column, atomicMin of (f2ord(v), ~f2ord(v)) - see cdf_match.cu
 };
 // OPTEX_OK, OPTEX_ENOTSUP (shape/alignment outside the TMA constraints) or an error
 int gemm_tc(const TcGemm &g, cudaStream_t st);
 
 // dst = X R  (transposed: dst[c, n], else dst[n, c]);  terms = 1 (TF32) or 3 (3xTF32 split)
 int gemm_tc_rotate_forward(const float *X, const float *R, float *dst, int64_t n, int c, bool transposed,
-                           int terms, cudaStream_t st, int c0 = 0, int nc = -1);
+                           int terms, cudaStream_t st, int c0 = 0, int nc = -1, uint32_t *colrange = nullptr);
 // out[n, j] = sum_c M(n, c) R[j, c] (+ content blend);  M channel-major [c, n] or NHWC [n, c]
 int gemm_tc_rotate_inverse(const float *M, bool m_channel_major, const float *R, float *out, int64_t n, int c,
                            const float *content, float strength, int terms, cudaStream_t st);

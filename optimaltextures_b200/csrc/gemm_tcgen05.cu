@@ -155,6 +155,7 @@ struct Params {
     const int *skip;      // device flag: non-zero -> the whole launch is a no-op (converged iterations)
     int conv_a;           // terms == 3: A arrives raw (tmA_hi) and warps 2-5 split it into hi/lo in shared memory
     int nz;               // number of split-K slices (tiles enumerate z as well)
+    uint32_t *colrange;   // D_TRANS only: per output column [2]: atomicMin of f2ord(v) and of ~f2ord(v) (range fold)
     int conv_b;           // same for B (small problems, where a pre-split pass per GEMM would dominate)
 };
 
@@ -395,6 +396,24 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                         for (int j = 0; j < 32; ++j) {
                             int64_t n = (int64_t)n0 + col + j;
                             if (n < p.N) Dz[n * p.ldd + row] = p.alpha * __uint_as_float(v[j]);
+                        }
+                    }
+                    if (p.colrange) {
+                        // per-channel min / max of the rotated features (histmatch.py:52-53), folded here so the
+                        // matcher does not have to re-read them: warp REDUX over the 32 pixels of every column,
+                        // then lane j publishes column j
+                        uint32_t mn = 0xffffffffu, mxn = 0xffffffffu;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const uint32_t u = f2ord(p.alpha * __uint_as_float(v[j]));
+                            const uint32_t a = __reduce_min_sync(0xffffffffu, row < p.M ? u : 0xffffffffu);
+                            const uint32_t b = __reduce_min_sync(0xffffffffu, row < p.M ? ~u : 0xffffffffu);
+                            if (lane == j) { mn = a; mxn = b; }
+                        }
+                        const int64_t n = (int64_t)n0 + col + lane;
+                        if (n < p.N) {
+                            atomicMin(p.colrange + 2 * n, mn);
+                            atomicMin(p.colrange + 2 * n + 1, mxn);
                         }
                     }
                 } else if (row < p.M) {
@@ -671,6 +690,7 @@ int gemm_tc(const TcGemm &g, cudaStream_t st) {
     p.bias = g.bias; p.bias_hw = g.bias_hw > 0 ? g.bias_hw : 1; p.bias_ld = g.bias_ld;
     p.alpha = g.alpha; p.skip = g.skip; p.conv_a = p.terms == 3 ? 1 : 0; p.conv_b = conv_b ? 1 : 0;
     p.nz = nz;
+    p.colrange = g.d_trans ? g.colrange : nullptr;
     if (g.d_trans) return launch_n<false, true, true>(bn, ah, al, bh, bl, p, nz, st);
     if (!g.a_mn && !g.b_mn) return launch_n<false, false, false>(bn, ah, al, bh, bl, p, nz, st);
     if (!g.a_mn && g.b_mn) return launch_n<false, true, false>(bn, ah, al, bh, bl, p, nz, st);
@@ -679,14 +699,14 @@ int gemm_tc(const TcGemm &g, cudaStream_t st) {
 }
 
 int gemm_tc_rotate_forward(const float *X, const float *R, float *dst, int64_t n, int c, bool transposed, int terms,
-                           cudaStream_t st, int c0, int nc) {
+                           cudaStream_t st, int c0, int nc, uint32_t *colrange) {
     // A = X [n, c] K-major; B = R[:, c0:c0+nc] MN-major (needs nc % 32 == 0, c0 % 4 == 0)
     if (nc < 0) nc = c;
     if (c0 % 4 != 0) return OPTEX_ENOTSUP;
     TcGemm g{};
     g.A = X; g.a_mn = false; g.B = R; g.b_col0 = c0; g.b_mn = true; g.ldb = c; g.D = dst;
     g.ldd = transposed ? n : (int64_t)nc;
-    g.d_trans = transposed; g.M = n; g.N = nc; g.K = c; g.terms = terms; g.alpha = 1.f;
+    g.d_trans = transposed; g.M = n; g.N = nc; g.K = c; g.terms = terms; g.alpha = 1.f; g.colrange = colrange;
     return gemm_tc(g, st);
 }
 
