@@ -55,8 +55,13 @@ def parse():
     return ap.parse_args()
 
 
+LAYERS = {(64, 512): "conv5_1", (128, 512): "conv4_1", (256, 256): "conv3_1", (512, 128): "conv2_1", (1024, 64): "conv1_1"}
+
+
 def workload_name(a):
-    return (f"ot_step conv4_1@{a.hw * 8}^2: P,S=[1,{a.hw},{a.hw},{a.channels}] fp32 "
+    layer = LAYERS.get((a.hw, a.channels))
+    where = f"{layer}@1024^2" if layer else "custom block"
+    return (f"ot_step {where}: P,S=[1,{a.hw},{a.hw},{a.channels}] fp32 "
             f"(N_p=N_s={a.hw * a.hw}, C={a.channels}), hist_mode={a.mode}, rotation drawn per step")
 
 
@@ -404,6 +409,24 @@ def run_ours(a):
             except Exception as exc:  # noqa: BLE001
                 extra[m] = f"error: {exc}"
         line["other_modes_it_s"] = extra
+        gm = {}
+        for g in ("tf32", "fp32"):       # rotation-GEMM arithmetic variants of the headline mode
+            try:
+                ob.set_gemm_mode(g)
+                for i in range(3):
+                    step(i)
+                torch.cuda.synchronize()
+                e0.record()
+                for i in range(K):
+                    step(i)
+                e1.record()
+                torch.cuda.synchronize()
+                gm[g] = K / (e0.elapsed_time(e1) * 1e-3)
+            except Exception as exc:  # noqa: BLE001
+                gm[g] = f"error: {exc}"
+            finally:
+                ob.set_gemm_mode(a.gemm)
+        line["other_gemm_modes_it_s"] = gm
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

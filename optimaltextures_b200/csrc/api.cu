@@ -114,7 +114,7 @@ static bool valid_mode(int mode) { return mode >= OPTEX_MODE_CHOL && mode <= OPT
 
 static size_t match_ws_bytes(int64_t n_p, int64_t n_s, int c, int mode) {
     if (mode == OPTEX_MODE_CDF) return optex_cdf_match_workspace_bytes(c, 256);
-    if (mode == OPTEX_MODE_SORT) return 256;  // the step sorts its own rotated-style buffer in place
+    if (mode == OPTEX_MODE_SORT) return sort_match_scratch_bytes(c, n_p, n_s) + 256;  // rs itself is sorted in place
     return cov_match_ws_bytes(n_p, n_s, c, mode);
 }
 
@@ -173,7 +173,7 @@ static int ot_step_impl(const float *P, const float *S, const float *R, float *o
     if (mode == OPTEX_MODE_CDF)
         OPTEX_TRY(optex_cdf_match(rp, rs, mt, c, n_p, n_s, 256, nullptr, mw, mws, st));
     else
-        OPTEX_TRY(sort_match_inplace(rp, rs, mt, c, n_p, n_s, nullptr, st));  // rs is scratch: sorted in place
+        OPTEX_TRY(sort_match_inplace(rp, rs, mt, c, n_p, n_s, nullptr, mw, mws, st));  // rs is scratch: sorted in place
     return rotate_inverse(mt, true, R, out, n_p, c, content, strength, st);
 }
 
@@ -366,7 +366,7 @@ extern "C" int optex_hist_match(const float *target, const float *source, float 
     if (mode == OPTEX_MODE_CDF)
         OPTEX_TRY(optex_cdf_match(tt, ts, tt, c, n_t, n_s, 256, nullptr, mw, mws, st));
     else
-        OPTEX_TRY(sort_match_inplace(tt, ts, tt, c, n_t, n_s, nullptr, st));
+        OPTEX_TRY(sort_match_inplace(tt, ts, tt, c, n_t, n_s, nullptr, mw, mws, st));
     return transpose_f32(tt, out, c, n_t, st);
 }
 

@@ -120,8 +120,9 @@ int cdf_match_core(const float *target, const float *source, float *out, int c, 
                    float *tables, void *workspace, size_t workspace_bytes, bool have_range, cudaStream_t st);
 
 // sort_match.cu: exact 1-D OT per channel; `source_scratch` [c, n_s] is sorted in place
+size_t sort_match_scratch_bytes(int c, int64_t n_t, int64_t n_s);  // 0 while channels fit on chip (<= 16384)
 int sort_match_inplace(const float *target, float *source_scratch, float *out, int c, int64_t n_t, int64_t n_s,
-                       int32_t *perm, cudaStream_t st);
+                       int32_t *perm, void *ws, size_t ws_bytes, cudaStream_t st);
 
 // cov_match.cu: closed-form Gaussian matching (histmatch.py:13-44) on NHWC-flattened data.
 //   out[n, c] = (X - mu_t) T^T + mu_s ;  T from chol / pca / sym of the two covariances

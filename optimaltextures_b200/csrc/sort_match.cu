@@ -203,22 +203,180 @@ sort_target_kernel(const float *target, const float *__restrict__ sorted_source,
 }
 
 template <int LOG_E>
-int launch_sort(const float *t, float *s_sorted, float *out, int c, int64_t n_t, int64_t n_s, int32_t *perm,
-                cudaStream_t st) {
+int launch_source_sort(float *s_sorted, int c, int64_t n_s, cudaStream_t st) {
     constexpr size_t smem_s = radix_smem_bytes<LOG_E, false>();
-    constexpr size_t smem_t = radix_smem_bytes<LOG_E, true>();
     static bool attr_done = false;
     if (!attr_done) {
         OPTEX_CUDA(cudaFuncSetAttribute(sort_source_kernel<LOG_E>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)smem_s));
-        OPTEX_CUDA(cudaFuncSetAttribute(sort_target_kernel<LOG_E>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem_t));
         attr_done = true;
     }
     sort_source_kernel<LOG_E><<<c, NT, smem_s, st>>>(s_sorted, n_s);
     OPTEX_LAUNCH_CHECK("sort_source_kernel");
+    return OPTEX_OK;
+}
+template <int LOG_E>
+int launch_target_sort(const float *t, const float *s_sorted, float *out, int c, int64_t n_t, int64_t n_s,
+                       int32_t *perm, cudaStream_t st) {
+    constexpr size_t smem_t = radix_smem_bytes<LOG_E, true>();
+    static bool attr_done = false;
+    if (!attr_done) {
+        OPTEX_CUDA(cudaFuncSetAttribute(sort_target_kernel<LOG_E>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem_t));
+        attr_done = true;
+    }
     sort_target_kernel<LOG_E><<<c, NT, smem_t, st>>>(t, s_sorted, out, n_t, n_s, perm);
     OPTEX_LAUNCH_CHECK("sort_target_kernel");
+    return OPTEX_OK;
+}
+
+// ------------------------------------------------------------------ channels longer than the on-chip capacity
+// 16384-element chunks are sorted on chip (same radix kernel), then merged pairwise - run length doubling per
+// pass - by a stable merge-path kernel (ties take the earlier run first, so the overall order stays the stable
+// argsort).  Keys travel as ordered u32, the pixel index as a second u32 array.
+constexpr int CHUNK = NT << MAX_LOG_E;
+constexpr int MT = 256, ME = 16, TM = MT * ME;  // merge tile: 4096 outputs per CTA
+
+template <bool PAYLOAD>
+__global__ void __launch_bounds__(NT, 1)
+sort_chunks_kernel(const float *__restrict__ src, int64_t n, uint32_t *__restrict__ K, uint32_t *__restrict__ I) {
+    constexpr int LOG_E = MAX_LOG_E, E = 1 << LOG_E, N2 = NT * E;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t *kbuf = reinterpret_cast<uint32_t *>(smem_raw);
+    uint32_t *cnt = kbuf + N2;
+    uint32_t *wsum = cnt + ROWS * NT / 32 * 33;
+    uint16_t *pbuf = reinterpret_cast<uint16_t *>(wsum + 32);
+    const int tid = threadIdx.x;
+    const int64_t base = (int64_t)blockIdx.x * CHUNK;
+    const int64_t rowoff = (int64_t)blockIdx.y * n;
+    const int64_t valid = n - base < CHUNK ? n - base : CHUNK;
+    for (int i = tid; i < N2; i += NT) kbuf[bphys<LOG_E>(i)] = i < valid ? sort_key(src[rowoff + base + i]) : 0xffffffffu;
+    __syncthreads();
+    uint32_t k[E], pl[(E + 1) / 2];
+#pragma unroll
+    for (int i = 0; i < (E + 1) / 2; ++i) pl[i] = 0u;
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+        k[i] = kbuf[bphys<LOG_E>(tid * E + i)];
+        pl[i >> 1] |= (uint32_t)((tid * E + i) & 0xffff) << ((i & 1) * 16);
+    }
+    __syncthreads();
+    radix_sort_blocked<LOG_E, PAYLOAD>(k, pl, kbuf, pbuf, cnt, wsum, false);
+    for (int i = tid; i < valid; i += NT) {  // pads sorted last: the first `valid` entries are the real ones
+        K[rowoff + base + i] = kbuf[bphys<LOG_E>(i)];
+        if (PAYLOAD) I[rowoff + base + i] = (uint32_t)(base + pbuf[bphys<LOG_E>(i)]);
+    }
+}
+
+// number of elements taken from A among the first d outputs of merge(A, B), ties to A
+__device__ __forceinline__ int merge_path(const uint32_t *A, int na, const uint32_t *B, int nb, int d) {
+    int lo = d - nb > 0 ? d - nb : 0, hi = d < na ? d : na;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (A[mid] <= B[d - 1 - mid]) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+template <bool PAYLOAD>
+__global__ void __launch_bounds__(MT)
+merge_pass_kernel(const uint32_t *__restrict__ Kin, const uint32_t *__restrict__ Iin, uint32_t *__restrict__ Kout,
+                  uint32_t *__restrict__ Iout, int64_t n, int64_t L) {
+    extern __shared__ uint32_t msm[];
+    uint32_t *sK = msm, *sI = msm + TM, *oK = msm + 2 * TM, *oI = msm + 3 * TM;
+    __shared__ int part[2];
+    const int tid = threadIdx.x;
+    const int64_t rowoff = (int64_t)blockIdx.y * n;
+    const int64_t o0 = (int64_t)blockIdx.x * TM;
+    if (o0 >= n) return;
+    const int64_t pbase = (o0 / (2 * L)) * (2 * L);
+    const int na = (int)(n - pbase < L ? n - pbase : L);
+    const int nb = (int)(n - pbase - L < 0 ? 0 : (n - pbase - L < L ? n - pbase - L : L));
+    const uint32_t *A = Kin + rowoff + pbase, *B = A + L;
+    const int d0 = (int)(o0 - pbase);
+    const int d1 = d0 + TM < na + nb ? d0 + TM : na + nb;
+    if (tid < 2) part[tid] = merge_path(A, na, B, nb, tid ? d1 : d0);
+    __syncthreads();
+    const int a0 = part[0], a1 = part[1], b0 = d0 - a0, b1 = d1 - a1;
+    const int ca = a1 - a0, cb = b1 - b0, cnt = ca + cb;
+    for (int i = tid; i < cnt; i += MT) {
+        const int64_t g = i < ca ? pbase + a0 + i : pbase + L + b0 + (i - ca);
+        sK[i] = Kin[rowoff + g];
+        if (PAYLOAD) sI[i] = Iin[rowoff + g];
+    }
+    __syncthreads();
+    {
+        const uint32_t *sA = sK, *sB = sK + ca;
+        const int d = tid * ME;
+        if (d < cnt) {
+            int i = merge_path(sA, ca, sB, cb, d), j = d - i;
+#pragma unroll
+            for (int e = 0; e < ME; ++e) {
+                if (d + e < cnt) {
+                    const bool takeA = j >= cb || (i < ca && sA[i] <= sB[j]);
+                    const int src = takeA ? i : ca + j;
+                    oK[d + e] = sK[src];
+                    if (PAYLOAD) oI[d + e] = sI[src];
+                    if (takeA) ++i; else ++j;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < cnt; i += MT) {
+        Kout[rowoff + o0 + i] = oK[i];
+        if (PAYLOAD) Iout[rowoff + o0 + i] = oI[i];
+    }
+}
+
+__global__ void keys_to_float_kernel(const uint32_t *__restrict__ K, float *__restrict__ out, int64_t total) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = ord2f(K[i]);
+}
+// rank r of the target receives sorted_source[((2r+1) n_s) / (2 n_t)]
+__global__ void sort_finalize_kernel(const uint32_t *__restrict__ I, const float *__restrict__ ss, float *__restrict__ out,
+                                     int32_t *__restrict__ perm, int64_t n_t, int64_t n_s) {
+    const int64_t rt = (int64_t)blockIdx.y * n_t, rs = (int64_t)blockIdx.y * n_s;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_t; r += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t idx = I[rt + r];
+        const int64_t q = ((2 * r + 1) * n_s) / (2 * n_t);
+        out[rt + idx] = __ldg(ss + rs + q);
+        if (perm) perm[rt + r] = (int32_t)idx;
+    }
+}
+
+template <bool PAYLOAD>
+int large_sort(const float *src, int c, int64_t n, uint32_t *Ka, uint32_t *Ia, uint32_t *Kb, uint32_t *Ib,
+               uint32_t **Kres, uint32_t **Ires, cudaStream_t st) {
+    constexpr size_t smem_c = radix_smem_bytes<MAX_LOG_E, true>();
+    constexpr size_t smem_m = sizeof(uint32_t) * 4 * TM;
+    static bool attr_done = false;
+    if (!attr_done) {
+        OPTEX_CUDA(cudaFuncSetAttribute(sort_chunks_kernel<PAYLOAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem_c));
+        OPTEX_CUDA(cudaFuncSetAttribute(merge_pass_kernel<PAYLOAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem_m));
+        attr_done = true;
+    }
+    const int64_t chunks = (n + CHUNK - 1) / CHUNK;
+    if (chunks > 0x7fffffffLL || c > 65535) {
+        set_error("optex_sort_match: problem too large for the grid");
+        return OPTEX_ESIZE;
+    }
+    sort_chunks_kernel<PAYLOAD><<<dim3((unsigned)chunks, (unsigned)c), NT, smem_c, st>>>(src, n, Ka, Ia);
+    OPTEX_LAUNCH_CHECK("sort_chunks_kernel");
+    uint32_t *kin = Ka, *iin = Ia, *kout = Kb, *iout = Ib;
+    const unsigned tiles = (unsigned)((n + TM - 1) / TM);
+    for (int64_t L = CHUNK; L < n; L *= 2) {
+        merge_pass_kernel<PAYLOAD><<<dim3(tiles, (unsigned)c), MT, smem_m, st>>>(kin, iin, kout, iout, n, L);
+        OPTEX_LAUNCH_CHECK("merge_pass_kernel");
+        uint32_t *t;
+        t = kin; kin = kout; kout = t;
+        t = iin; iin = iout; iout = t;
+    }
+    *Kres = kin;
+    if (Ires) *Ires = iin;
     return OPTEX_OK;
 }
 
@@ -227,32 +385,76 @@ int launch_sort(const float *t, float *s_sorted, float *out, int c, int64_t n_t,
 
 using namespace optex;
 
+// scratch of the large-channel path: source phase (two key arrays) and target phase (two key + two index arrays)
+// run one after the other and share the workspace
+static size_t sort_large_bytes(int c, int64_t n_t, int64_t n_s) {
+    size_t src = n_s > CHUNK ? 2 * align_up(sizeof(uint32_t) * (size_t)c * n_s, 256) : 0;
+    size_t tgt = n_t > CHUNK ? 4 * align_up(sizeof(uint32_t) * (size_t)c * n_t, 256) : 0;
+    return src > tgt ? src : tgt;
+}
+
 extern "C" size_t optex_sort_match_workspace_bytes(int c, int64_t n_t, int64_t n_s) {
-    (void)n_t;
-    if (c <= 0 || n_s <= 0) return 0;
-    return align_up(sizeof(float) * (size_t)c * (size_t)n_s, 256);  // sorted copy of the source
+    if (c <= 0 || n_s <= 0 || n_t < 0) return 0;
+    return align_up(sizeof(float) * (size_t)c * (size_t)n_s, 256) + sort_large_bytes(c, n_t, n_s);
 }
 
 namespace optex {
-// `source_scratch` is sorted IN PLACE (the OT step hands over its own rotated-style buffer)
+size_t sort_match_scratch_bytes(int c, int64_t n_t, int64_t n_s) { return sort_large_bytes(c, n_t, n_s); }
+
+// `source_scratch` is sorted IN PLACE (the OT step hands over its own rotated-style buffer); `ws` is only needed
+// when a channel exceeds the on-chip capacity (sort_match_scratch_bytes)
 int sort_match_inplace(const float *target, float *source_scratch, float *out, int c, int64_t n_t, int64_t n_s,
-                       int32_t *perm, cudaStream_t st) {
-    int64_t n = n_t > n_s ? n_t : n_s;
-    if (n > (int64_t)NT << MAX_LOG_E) {
-        set_error("optex_sort_match: %lld elements per channel exceed the on-chip sort capacity (%d)",
-                  (long long)n, NT << MAX_LOG_E);
+                       int32_t *perm, void *ws, size_t ws_bytes, cudaStream_t st) {
+    if (n_t >= (1LL << 31) || n_s >= (1LL << 31)) {
+        set_error("optex_sort_match: more than 2^31 elements per channel");
         return OPTEX_ESIZE;
     }
-    int log_e = 0;
-    while (((int64_t)NT << log_e) < n) ++log_e;
-    switch (log_e) {
-        case 0: return launch_sort<0>(target, source_scratch, out, c, n_t, n_s, perm, st);
-        case 1: return launch_sort<1>(target, source_scratch, out, c, n_t, n_s, perm, st);
-        case 2: return launch_sort<2>(target, source_scratch, out, c, n_t, n_s, perm, st);
-        case 3: return launch_sort<3>(target, source_scratch, out, c, n_t, n_s, perm, st);
-        case 4: return launch_sort<4>(target, source_scratch, out, c, n_t, n_s, perm, st);
-        default: return launch_sort<5>(target, source_scratch, out, c, n_t, n_s, perm, st);
+    if (ws_bytes < sort_large_bytes(c, n_t, n_s) || (sort_large_bytes(c, n_t, n_s) && !ws)) {
+        set_error("optex_sort_match: scratch %zu < %zu bytes", ws_bytes, sort_large_bytes(c, n_t, n_s));
+        return OPTEX_EWORKSPACE;
     }
+    // ---- source: ascending values, in place
+    if (n_s <= CHUNK) {
+        int log_e = 0;
+        while (((int64_t)NT << log_e) < n_s) ++log_e;
+        switch (log_e) {
+            case 0: OPTEX_TRY(launch_source_sort<0>(source_scratch, c, n_s, st)); break;
+            case 1: OPTEX_TRY(launch_source_sort<1>(source_scratch, c, n_s, st)); break;
+            case 2: OPTEX_TRY(launch_source_sort<2>(source_scratch, c, n_s, st)); break;
+            case 3: OPTEX_TRY(launch_source_sort<3>(source_scratch, c, n_s, st)); break;
+            case 4: OPTEX_TRY(launch_source_sort<4>(source_scratch, c, n_s, st)); break;
+            default: OPTEX_TRY(launch_source_sort<5>(source_scratch, c, n_s, st)); break;
+        }
+    } else {
+        const size_t one = align_up(sizeof(uint32_t) * (size_t)c * n_s, 256);
+        uint32_t *Ka = (uint32_t *)ws, *Kb = (uint32_t *)((char *)ws + one), *Kres = nullptr;
+        OPTEX_TRY(large_sort<false>(source_scratch, c, n_s, Ka, nullptr, Kb, nullptr, &Kres, nullptr, st));
+        const int64_t total = (int64_t)c * n_s;
+        keys_to_float_kernel<<<(unsigned)(sm_count() * 8), 256, 0, st>>>(Kres, source_scratch, total);
+        OPTEX_LAUNCH_CHECK("keys_to_float_kernel");
+    }
+    // ---- target: stable argsort, then the quantile assignment
+    if (n_t <= CHUNK) {
+        int log_e = 0;
+        while (((int64_t)NT << log_e) < n_t) ++log_e;
+        switch (log_e) {
+            case 0: return launch_target_sort<0>(target, source_scratch, out, c, n_t, n_s, perm, st);
+            case 1: return launch_target_sort<1>(target, source_scratch, out, c, n_t, n_s, perm, st);
+            case 2: return launch_target_sort<2>(target, source_scratch, out, c, n_t, n_s, perm, st);
+            case 3: return launch_target_sort<3>(target, source_scratch, out, c, n_t, n_s, perm, st);
+            case 4: return launch_target_sort<4>(target, source_scratch, out, c, n_t, n_s, perm, st);
+            default: return launch_target_sort<5>(target, source_scratch, out, c, n_t, n_s, perm, st);
+        }
+    }
+    const size_t one = align_up(sizeof(uint32_t) * (size_t)c * n_t, 256);
+    char *w = (char *)ws;
+    uint32_t *Ka = (uint32_t *)w, *Kb = (uint32_t *)(w + one), *Ia = (uint32_t *)(w + 2 * one),
+             *Ib = (uint32_t *)(w + 3 * one), *Kres = nullptr, *Ires = nullptr;
+    OPTEX_TRY(large_sort<true>(target, c, n_t, Ka, Ia, Kb, Ib, &Kres, &Ires, st));
+    const unsigned gx = (unsigned)((n_t + 255) / 256 < 1024 ? (n_t + 255) / 256 : 1024);
+    sort_finalize_kernel<<<dim3(gx, (unsigned)c), 256, 0, st>>>(Ires, source_scratch, out, perm, n_t, n_s);
+    OPTEX_LAUNCH_CHECK("sort_finalize_kernel");
+    return OPTEX_OK;
 }
 }  // namespace optex
 
@@ -279,6 +481,8 @@ extern "C" int optex_sort_match(const float *target, const float *source, float 
         return OPTEX_EWORKSPACE;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    const size_t copy_bytes = align_up(sizeof(float) * (size_t)c * (size_t)n_s, 256);
     OPTEX_CUDA(cudaMemcpyAsync(workspace, source, sizeof(float) * (size_t)c * (size_t)n_s, cudaMemcpyDeviceToDevice, st));
-    return sort_match_inplace(target, (float *)workspace, out, c, n_t, n_s, perm, st);
+    return sort_match_inplace(target, (float *)workspace, out, c, n_t, n_s, perm, (char *)workspace + copy_bytes,
+                              workspace_bytes - copy_bytes, st);
 }

@@ -158,6 +158,18 @@ def test_sort_match_full_size_properties(ob):
     assert torch.equal(torch.gather(out, 1, perm.long()), torch.sort(s, dim=1).values)
 
 
-def test_sort_match_too_large_is_an_error_not_a_fallback(ob):
-    with pytest.raises(ValueError, match="capacity"):
-        ob.sort_match(torch.zeros(1, 20000).cuda(), torch.zeros(1, 8).cuda())
+LARGE_SORT_SHAPES = [(3, 16385, 16384), (2, 40000, 70001), (2, 65536, 65536), (1, 300000, 1000), (2, 1000, 100000),
+                     (1, 1048576, 1048576)]
+
+
+@pytest.mark.parametrize("c,n,m", LARGE_SORT_SHAPES)
+def test_sort_match_large_channels_bit_exact(ob, c, n, m):
+    """Channels longer than the on-chip capacity (16384): chunk sort + stable merge passes."""
+    g = torch.Generator().manual_seed(n + m)
+    t = torch.randn(c, n, generator=g)
+    t[:, ::7] = torch.round(t[:, ::7] * 4) / 4          # ties across chunk boundaries
+    s = torch.relu(torch.randn(c, m, generator=g) * 1.3 + 0.2)
+    ref, idx = sort_oracle.sort_match_channels(t, s)
+    out, perm = ob.sort_match(dev(t), dev(s), return_perm=True)
+    np.testing.assert_array_equal(perm.cpu().numpy().astype(np.int64), idx.numpy())
+    np.testing.assert_array_equal(out.cpu().numpy(), ref.numpy())
