@@ -97,6 +97,16 @@ int optex_ot_step_host(const float *P, const float *S, const float *R, float *ou
                        float content_strength, uint64_t seed, uint64_t counter,
                        void *stream);
 
+/* The same without the final synchronisation, for callers that pipeline independent steps: `slot` (0 or 1)
+ * selects one of two library-owned device scratch sets, so step i+1 (slot 1, stream B) can upload while step i
+ * (slot 0, stream A) still computes / downloads.  Use PINNED host buffers and one stream per slot; the caller
+ * synchronises the stream before reading `out` or reusing the slot. */
+int optex_ot_step_host_async(const float *P, const float *S, const float *R, float *out,
+                             int b_p, int64_t hw_p, int b_s, int64_t hw_s, int c,
+                             int mode, float eps, const float *content,
+                             float content_strength, uint64_t seed, uint64_t counter,
+                             int slot, void *stream);
+
 /* ---- the inner loop --------------------------------------------------------
  * replaces: optex.py:112-117  (`for _ in range(iters): optimal_transport; blend`)
  * feat [n_p, c] is updated IN PLACE `iters` times.  Rotations: if R_all != NULL

@@ -33,6 +33,7 @@ SIGNATURES = {
     "optex_ot_workspace_bytes": (_z, [_l, _l, _i, _i]),
     "optex_ot_step": (_i, [_p, _p, _p, _p, _i, _l, _i, _l, _i, _i, _f, _p, _f, _p, _z, _p]),
     "optex_ot_step_host": (_i, [_p, _p, _p, _p, _i, _l, _i, _l, _i, _i, _f, _p, _f, _u, _u, _p]),
+    "optex_ot_step_host_async": (_i, [_p, _p, _p, _p, _i, _l, _i, _l, _i, _i, _f, _p, _f, _u, _u, _i, _p]),
     "optex_ot_loop": (_i, [_p, _p, _p, _i, _u, _u, _i, _l, _i, _l, _i, _i, _f, _p, _f, _p, _z, _p]),
     "optex_ot_loop_workspace_bytes": (_z, [_l, _l, _i, _i]),
     "optex_hist_match_workspace_bytes": (_z, [_l, _l, _i, _i]),

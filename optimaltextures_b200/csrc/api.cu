@@ -199,7 +199,7 @@ struct HostScratch {
         return OPTEX_OK;
     }
 };
-static HostScratch g_host;
+static HostScratch g_host[2];  // one per pipeline slot of optex_ot_step_host_async
 
 }  // namespace optex
 
@@ -243,10 +243,10 @@ extern "C" int optex_ot_step(const float *P, const float *S, const float *R, flo
                         workspace_bytes, (cudaStream_t)stream);
 }
 
-extern "C" int optex_ot_step_host(const float *P, const float *S, const float *R, float *out, int b_p,
-                                  int64_t hw_p, int b_s, int64_t hw_s, int c, int mode, float eps,
-                                  const float *content, float content_strength, uint64_t seed,
-                                  uint64_t counter, void *stream) {
+static int ot_step_host_impl(const float *P, const float *S, const float *R, float *out, int b_p, int64_t hw_p,
+                             int b_s, int64_t hw_s, int c, int mode, float eps, const float *content,
+                             float content_strength, uint64_t seed, uint64_t counter, int slot, bool sync,
+                             cudaStream_t st) {
     OPTEX_TRY(require_sm100());
     OPTEX_TRY(check_step_args("optex_ot_step_host", P, S, out, b_p, hw_p, b_s, hw_s, c, mode));
     const int64_t n_p = (int64_t)b_p * hw_p, n_s = (int64_t)b_s * hw_s;
@@ -255,14 +255,15 @@ extern "C" int optex_ot_step_host(const float *P, const float *S, const float *R
     const size_t step_ws = optex_ot_workspace_bytes(n_p, n_s, c, mode);
     const size_t rot_ws = R ? 0 : align_up(rotation_ws_bytes(c, 1), 256);
     const size_t ws = step_ws + rot_ws;
-    std::lock_guard<std::mutex> lock(g_host.mu);
-    OPTEX_TRY(g_host.ensure(2 * bp + bs + br + (content ? bp : 0) + ws));
-    char *base = (char *)g_host.buf;
+    HostScratch &hs = g_host[slot & 1];
+    std::lock_guard<std::mutex> lock(hs.mu);
+    OPTEX_TRY(hs.ensure(2 * bp + bs + br + (content ? bp : 0) + ws));
+    char *base = (char *)hs.buf;
     float *dP = (float *)base, *dO = (float *)(base + bp), *dS = (float *)(base + 2 * bp);
     float *dR = (float *)(base + 2 * bp + bs);
     float *dC = content ? (float *)(base + 2 * bp + bs + br) : nullptr;
     void *dW = base + 2 * bp + bs + br + (content ? bp : 0);
-    cudaStream_t st = (cudaStream_t)stream;
+    gemm_tc_set_scratch_slot(slot);
     OPTEX_CUDA(cudaMemcpyAsync(dP, P, sizeof(float) * n_p * c, cudaMemcpyHostToDevice, st));
     OPTEX_CUDA(cudaMemcpyAsync(dS, S, sizeof(float) * n_s * c, cudaMemcpyHostToDevice, st));
     if (R)
@@ -270,10 +271,32 @@ extern "C" int optex_ot_step_host(const float *P, const float *S, const float *R
     else
         OPTEX_TRY(random_rotations(dR, c, 1, seed, counter, nullptr, (char *)dW + step_ws, rot_ws, st));
     if (content) OPTEX_CUDA(cudaMemcpyAsync(dC, content, sizeof(float) * n_p * c, cudaMemcpyHostToDevice, st));
-    OPTEX_TRY(ot_step_impl(dP, dS, dR, dO, b_p, hw_p, b_s, hw_s, c, mode, eps, dC, content_strength, dW, step_ws, st));
+    int rc = ot_step_impl(dP, dS, dR, dO, b_p, hw_p, b_s, hw_s, c, mode, eps, dC, content_strength, dW, step_ws, st);
+    gemm_tc_set_scratch_slot(0);
+    OPTEX_TRY(rc);
     OPTEX_CUDA(cudaMemcpyAsync(out, dO, sizeof(float) * n_p * c, cudaMemcpyDeviceToHost, st));
-    OPTEX_CUDA(cudaStreamSynchronize(st));
+    if (sync) OPTEX_CUDA(cudaStreamSynchronize(st));
     return OPTEX_OK;
+}
+
+extern "C" int optex_ot_step_host(const float *P, const float *S, const float *R, float *out, int b_p,
+                                  int64_t hw_p, int b_s, int64_t hw_s, int c, int mode, float eps,
+                                  const float *content, float content_strength, uint64_t seed,
+                                  uint64_t counter, void *stream) {
+    return ot_step_host_impl(P, S, R, out, b_p, hw_p, b_s, hw_s, c, mode, eps, content, content_strength, seed,
+                             counter, 0, true, (cudaStream_t)stream);
+}
+
+extern "C" int optex_ot_step_host_async(const float *P, const float *S, const float *R, float *out, int b_p,
+                                        int64_t hw_p, int b_s, int64_t hw_s, int c, int mode, float eps,
+                                        const float *content, float content_strength, uint64_t seed,
+                                        uint64_t counter, int slot, void *stream) {
+    if (slot != 0 && slot != 1) {
+        set_error("optex_ot_step_host_async: slot must be 0 or 1");
+        return OPTEX_EINVAL;
+    }
+    return ot_step_host_impl(P, S, R, out, b_p, hw_p, b_s, hw_s, c, mode, eps, content, content_strength, seed,
+                             counter, slot, false, (cudaStream_t)stream);
 }
 
 static const int kRotChunk = 16;

@@ -35,6 +35,8 @@ struct TcGemm {
     const int *skip;
     uint32_t *colrange;  // d_trans only: per output column, atomicMin of (f2ord(v), ~f2ord(v)) - see cdf_match.cu
 };
+// selects which of the two library-owned hi/lo scratch buffers the calling thread's GEMMs use (pipelined callers)
+void gemm_tc_set_scratch_slot(int slot);
 // OPTEX_OK, OPTEX_ENOTSUP (shape/alignment outside the TMA constraints) or an error
 int gemm_tc(const TcGemm &g, cudaStream_t st);
 

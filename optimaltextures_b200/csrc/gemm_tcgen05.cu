@@ -21,6 +21,7 @@
 //                                     -> canonical MN-major SW128 (LBO = 4 KB between 32-wide mn blocks)
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
 
 #include "gemm_tc.cuh"
@@ -547,15 +548,16 @@ struct Scratch {
     void *buf = nullptr;
     size_t cap = 0;
 };
-Scratch g_scratch[64];
+Scratch g_scratch[64][2];  // [device][slot]: two independent pipelines (optex_ot_step_host_async) may be in flight
 std::mutex g_scratch_mu;
+thread_local int g_scratch_slot = 0;
 
 int scratch(size_t bytes, float **out) {
     int dev = 0;
     OPTEX_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) dev = 63;
     std::lock_guard<std::mutex> lock(g_scratch_mu);
-    Scratch &s = g_scratch[dev];
+    Scratch &s = g_scratch[dev][g_scratch_slot & 1];
     if (s.cap < bytes) {
         if (s.buf) {
             OPTEX_CUDA(cudaDeviceSynchronize());
@@ -617,6 +619,8 @@ inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 
 inline int pick_block_n(int64_t M, int64_t N, int nz) {
     const int64_t mt = (M + BLOCK_M - 1) / BLOCK_M;
     const int64_t want = sm_count();
+    static const char *force = getenv("OPTEX_FORCE_BN");
+    if (force) return atoi(force);
     for (int bn : {256, 128}) {
         if (N <= bn / 2) continue;
         if (mt * ((N + bn - 1) / bn) * nz >= want) return bn;
@@ -626,6 +630,8 @@ inline int pick_block_n(int64_t M, int64_t N, int nz) {
 }
 
 }  // namespace
+
+void gemm_tc_set_scratch_slot(int slot) { g_scratch_slot = slot & 1; }
 
 int gemm_tc(const TcGemm &g, cudaStream_t st) {
     if (!encode_fn() || g.M < 1 || g.N < 1 || g.K < 1 || g.M > 0x3fffffffLL || g.N > 0x3fffffffLL || g.K > 0x3fffffffLL)
@@ -657,7 +663,8 @@ int gemm_tc(const TcGemm &g, cudaStream_t st) {
         // A is split inside the kernel (converter warps); only B (the small operand of the rotations: R) is
         // pre-split by an element-wise pass
         (void)na;
-        conv_b = g.M <= 4096;  // few M tiles share B: splitting it in the kernel beats an extra pass + launch
+        static const char *force_cb = getenv("OPTEX_FORCE_CONVB");
+        conv_b = force_cb ? atoi(force_cb) != 0 : g.M <= 4096;  // few M tiles share B: split it in the kernel
         if (!conv_b) {
             float *buf;
             OPTEX_TRY(scratch(2 * nb * sizeof(float), &buf));

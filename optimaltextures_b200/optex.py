@@ -156,10 +156,13 @@ def random_rotations(N: int, count: int, device="cuda", seed: Optional[int] = No
 
 
 def optimal_transport_host(pastiche, style, rotation, hist_mode: str, content=None, content_strength: float = 0.0,
-                           eps: float = 1.0, out=None, seed: Optional[int] = None, counter: int = 0):
+                           eps: float = 1.0, out=None, seed: Optional[int] = None, counter: int = 0,
+                           slot: Optional[int] = None, stream=None):
     """The same step through the HOST-buffer entry point (`optex_ot_step_host`): CPU tensors in,
     CPU tensor out, H2D/D2H inside the call.  This is what a non-torch caller of the C-ABI gets.
-    rotation=None draws the rotation on the device from (seed, counter), like the reference draws its own."""
+    rotation=None draws the rotation on the device from (seed, counter), like the reference draws its own.
+    slot=0/1 + stream=: the asynchronous, double-buffered form (`optex_ot_step_host_async`) for pipelining
+    independent steps - step i+1 uploads while step i computes / downloads."""
     for t in (pastiche, style, rotation, content):
         if t is not None and (t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous()):
             raise ValueError("optimal_transport_host takes contiguous fp32 CPU tensors")
@@ -167,9 +170,15 @@ def optimal_transport_host(pastiche, style, rotation, hist_mode: str, content=No
     bs, hws, _ = _nhwc_dims(style)
     if out is None:
         out = torch.empty_like(pastiche)
-    call("optex_ot_step_host", ptr(pastiche), ptr(style), ptr(rotation), ptr(out), b, hw, bs, hws, c,
-         _lib.mode_id(hist_mode), float(eps), ptr(content), float(content_strength),
-         _seed if seed is None else int(seed), int(counter), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    st = C.c_void_p((stream or torch.cuda.current_stream()).cuda_stream)
+    if slot is None:
+        call("optex_ot_step_host", ptr(pastiche), ptr(style), ptr(rotation), ptr(out), b, hw, bs, hws, c,
+             _lib.mode_id(hist_mode), float(eps), ptr(content), float(content_strength),
+             _seed if seed is None else int(seed), int(counter), st)
+    else:  # pipelined: no synchronisation - the caller syncs `stream` before reading `out` (pinned buffers!)
+        call("optex_ot_step_host_async", ptr(pastiche), ptr(style), ptr(rotation), ptr(out), b, hw, bs, hws, c,
+             _lib.mode_id(hist_mode), float(eps), ptr(content), float(content_strength),
+             _seed if seed is None else int(seed), int(counter), int(slot), st)
     return out
 
 

@@ -141,6 +141,21 @@ def test_ot_step_host_buffers(ob, golden):
     assert torch.equal(host_out, dev_out.cpu())
 
 
+def test_ot_step_host_async_double_buffered(ob, golden):
+    """Two pipelined slots on two streams give the same results as the synchronous call."""
+    g = golden("ot_step")
+    t, s, rot = T(g["wide64_t"]).pin_memory(), T(g["wide64_s"]).pin_memory(), T(g["wide64_rot"]).float().pin_memory()
+    ref = {m: ob.optimal_transport_host(t, s, rot, m) for m in ("cdf", "chol")}
+    streams = [torch.cuda.Stream() for _ in range(2)]
+    outs = [torch.empty_like(t).pin_memory() for _ in range(2)]
+    for rep in range(3):
+        for i, m in enumerate(("cdf", "chol")):
+            ob.optimal_transport_host(t, s, rot, m, out=outs[i], slot=i, stream=streams[i])
+        torch.cuda.synchronize()
+        for i, m in enumerate(("cdf", "chol")):
+            assert torch.equal(outs[i], ref[m])
+
+
 def test_headline_shape_properties(ob):
     """conv4_1 @ 1024^2 (N = 16384, C = 512): properties that hold at any size."""
     gen = torch.Generator(device="cuda").manual_seed(0)
