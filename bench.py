@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--all-modes", action="store_true", help="also time the other hist modes (extra keys)")
+    ap.add_argument("--no-pdl", action="store_true", help="launch the kernels without programmatic dependent launch")
     ap.add_argument("--sharded", action="store_true",
                     help="N > 1: ONE feature block, rotated channels sharded over the ranks + NCCL all-gather "
                          "(strong scaling) instead of one independent block per rank")
@@ -218,6 +219,7 @@ def run_ours(a):
     lib = _lib.lib()
     _lib.check(lib.optex_device_check())
     ob.set_gemm_mode(a.gemm)
+    lib.optex_set_pdl(0 if a.no_pdl else 1)
     K, W = a.steps, a.warmup
     n = a.hw * a.hw
     c = a.channels
@@ -270,10 +272,12 @@ def run_ours(a):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = lib.optex_launch_count()
     barrier()
+    fence = torch.zeros(1, device=device)
     e0.record()
     gen_rotations(K, W)                       # the per-step rotation draw, batched (as optex_ot_loop does)
     for i in range(K):
         step(i)
+    fence.add_(1)      # an ordinary kernel: it starts only after the last (PDL-launched) kernel has fully drained
     e1.record()
     barrier()
     launches = lib.optex_launch_count() - launches0
@@ -293,6 +297,7 @@ def run_ours(a):
             ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(K)]
             mws = torch.empty(max(lib.optex_cdf_match_workspace_bytes(c, 256),
                                   lib.optex_sort_match_workspace_bytes(c, n, n), 256), dtype=torch.uint8, device=device)
+            lib.optex_set_pdl(0)      # events between kernels need ordinary stream serialisation
             for i in range(K):
                 p, s = sets[i % a.sets]
                 r = rots[i % K]
@@ -309,6 +314,7 @@ def run_ours(a):
                 call("optex_rotate_inverse", ptr(rp), ptr(r), ptr(outs[i % 2]), n, c, None, 0.0, st)
                 ev[i][4].record()
             torch.cuda.synchronize()
+            lib.optex_set_pdl(0 if a.no_pdl else 1)
             for j, name in enumerate(names):
                 stages[name] = statistics.mean(ev[i][j].elapsed_time(ev[i][j + 1]) for i in range(K))
 

@@ -65,6 +65,9 @@ uint64_t optex_launch_count(void);
 /* Select the rotation-GEMM arithmetic (OPTEX_GEMM_*), process-wide. */
 int optex_set_gemm_mode(int gemm_mode);
 int optex_get_gemm_mode(void);
+/* Programmatic dependent launch between the library's kernels (default on).  Turn it off to time individual
+ * kernels with CUDA events: under PDL a kernel may start before its predecessor has drained. */
+int optex_set_pdl(int enable);
 
 /* ---- the OT step -----------------------------------------------------------
  * replaces: optimal_transport()  optex.py:167-177  (+ the content blend of the

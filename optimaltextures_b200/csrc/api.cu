@@ -16,6 +16,8 @@ namespace optex {
 static thread_local char g_err[512] = "";
 static std::atomic<uint64_t> g_launches{0};
 static std::atomic<int> g_gemm_mode{OPTEX_GEMM_AUTO};
+static std::atomic<int> g_pdl{1};
+bool pdl_enabled() { return g_pdl.load(std::memory_order_relaxed) != 0; }
 
 void set_error(const char *fmt, ...) {
     va_list ap;
@@ -152,17 +154,30 @@ static int ot_step_impl(const float *P, const float *S, const float *R, float *o
     float *rp = ar.take<float>((size_t)n_p * c);
     float *rs = ar.take<float>((size_t)n_s * c);
     float *mt = rp;
+    float *r_hi = ar.take<float>((size_t)c * c), *r_lo = ar.take<float>((size_t)c * c);
     size_t mws = match_ws_bytes(n_p, n_s, c, mode);
     void *mw = ar.take<char>(mws);
     if (!ar.ok()) {
         set_error("optex_ot_step: workspace %zu < %zu bytes", ws_bytes, optex_ot_workspace_bytes(n_p, n_s, c, mode));
         return OPTEX_EWORKSPACE;
     }
+    // One preparation launch per step: split R into its tf32 hi / lo halves ONCE for the three rotation GEMMs and
+    // reset the cdf range slots; the GEMMs pick the halves up through the pre-split registry.
+    struct PresplitGuard {
+        ~PresplitGuard() { gemm_tc_set_presplit(nullptr, nullptr, nullptr); }
+    } presplit_guard;
+    bool forced_tc;
+    const bool tc3 = want_tc(forced_tc) && tc_terms() == 3 && c % 4 == 0;
+    if (tc3) {
+        OPTEX_TRY(gemm_tc_split_and_fill(R, r_hi, r_lo, (int64_t)c * c, mode == OPTEX_MODE_CDF ? (uint32_t *)mw : nullptr,
+                                         mode == OPTEX_MODE_CDF ? 2 * (int64_t)c : 0, 0xffffffffu, st));
+        gemm_tc_set_presplit(R, r_hi, r_lo);
+    }
     if (mode == OPTEX_MODE_CDF) {
         // the forward rotations fold the per-channel range (histmatch.py:52-53) into their epilogues
         uint32_t *minmax = (uint32_t *)mw;
         bool r1 = false, r2 = false;
-        OPTEX_TRY(fill_u32(minmax, 2 * (int64_t)c, 0xffffffffu, st));
+        if (!tc3) OPTEX_TRY(fill_u32(minmax, 2 * (int64_t)c, 0xffffffffu, st));
         OPTEX_TRY(rotate_forward(P, R, rp, n_p, c, true, st, 0, -1, minmax, &r1));
         OPTEX_TRY(rotate_forward(S, R, rs, n_s, c, true, st, 0, -1, minmax, &r2));
         OPTEX_TRY(cdf_match_core(rp, rs, mt, c, n_p, n_s, 256, nullptr, mw, mws, r1 && r2, st));
@@ -218,11 +233,16 @@ extern "C" int optex_set_gemm_mode(int m) {
     return OPTEX_OK;
 }
 extern "C" int optex_get_gemm_mode(void) { return g_gemm_mode.load(); }
+extern "C" int optex_set_pdl(int enable) {
+    g_pdl.store(enable ? 1 : 0);
+    return OPTEX_OK;
+}
 
 extern "C" size_t optex_ot_workspace_bytes(int64_t n_p, int64_t n_s, int c, int mode) {
     if (n_p < 1 || n_s < 1 || c < 1 || !valid_mode(mode)) return 0;
     if (!per_channel(mode)) return align_up(cov_match_ws_bytes(n_p, n_s, c, mode), 256);
     size_t b = align_up(sizeof(float) * (size_t)n_p * c, 256) + align_up(sizeof(float) * (size_t)n_s * c, 256);
+    b += 2 * align_up(sizeof(float) * (size_t)c * c, 256);  // tf32 hi / lo halves of the rotation
     return b + align_up(match_ws_bytes(n_p, n_s, c, mode), 256);
 }
 
@@ -304,9 +324,75 @@ static const int kRotChunk = 16;
 extern "C" size_t optex_ot_loop_workspace_bytes(int64_t n_p, int64_t n_s, int c, int mode) {
     size_t step = optex_ot_workspace_bytes(n_p, n_s, c, mode);
     if (!step) return 0;
-    size_t alt = per_channel(mode) ? 0 : align_up(sizeof(float) * (size_t)n_p * c, 256);  // ping-pong feature block
-    return step + alt + align_up(sizeof(float) * (size_t)kRotChunk * c * c, 256) +
+    // a second feature block: ping-pong partner (closed-form modes) / second channel-major buffer (fused loop)
+    size_t alt = align_up(sizeof(float) * (size_t)n_p * c, 256);
+    return step + alt + align_up(sizeof(float) * (size_t)(kRotChunk + 2) * c * c, 256) +
            align_up(rotation_ws_bytes(c, kRotChunk), 256);
+}
+
+// Per-channel modes without a content blend: the un-rotated pastiche between two iterations is never needed, so
+// "rotate back with R_i, rotate forward with R_{i+1}" (optex.py:175 then :170) becomes ONE rotation of the
+// channel-major block by Q = R_i^T R_{i+1} - two N x C x C GEMMs per iteration instead of three.  Same maths as
+// the step-by-step loop up to fp32 rounding (tests/test_gpu_ot_step.py::test_ot_loop_fused_rotations).
+static int tc_must(int rc) {
+    if (rc != OPTEX_ENOTSUP) return rc;
+    set_error("optex_ot_loop: internal - fused rotation rejected by the tensor-core path");
+    return OPTEX_ESIZE;
+}
+static int ot_loop_fused(float *feat, const float *S, const float *R_all, int iters, uint64_t seed,
+                         uint64_t first_counter, int64_t n_p, int64_t n_s, int c, int mode, void *sw, size_t step_ws,
+                         float *alt, float *rbuf, void *rws, size_t rws_bytes, cudaStream_t st) {
+    Arena ar(sw, step_ws);
+    float *rp = ar.take<float>((size_t)n_p * c);
+    float *rs = ar.take<float>((size_t)n_s * c);
+    size_t mws = match_ws_bytes(n_p, n_s, c, mode);
+    void *mw = ar.take<char>(mws);
+    uint32_t *minmax = (uint32_t *)mw;
+    float *Q = rbuf + (size_t)(kRotChunk + 1) * c * c;
+    const bool cdf = mode == OPTEX_MODE_CDF;
+    const int terms = tc_terms();
+    float *cur = rp, *nxt = alt;
+    const float *R = nullptr;
+    for (int i = 0; i < iters; ++i) {
+        // R_i lives in slot 1 + (i % chunk); slot 0 keeps the last matrix of the previous chunk
+        const float *Rprev = R;
+        if (R_all) {
+            R = R_all + (size_t)i * c * c;
+        } else {
+            if (i % kRotChunk == 0) {
+                if (i > 0) {
+                    OPTEX_CUDA(cudaMemcpyAsync(rbuf, Rprev, sizeof(float) * (size_t)c * c, cudaMemcpyDeviceToDevice, st));
+                    Rprev = rbuf;
+                }
+                int nb = iters - i < kRotChunk ? iters - i : kRotChunk;
+                OPTEX_TRY(random_rotations(rbuf + (size_t)c * c, c, nb, seed, first_counter + (uint64_t)i, nullptr, rws,
+                                           rws_bytes, st));
+            }
+            R = rbuf + (size_t)(1 + i % kRotChunk) * c * c;
+        }
+        if (cdf) OPTEX_TRY(fill_u32(minmax, 2 * (int64_t)c, 0xffffffffu, st));
+        bool r1 = false, r2 = false;
+        if (i == 0) {
+            OPTEX_TRY(rotate_forward(feat, R, cur, n_p, c, true, st, 0, -1, cdf ? minmax : nullptr, &r1));
+        } else {
+            TcGemm q{};  // Q = R_{i-1}^T R_i
+            q.A = Rprev; q.a_mn = true; q.B = R; q.b_mn = true; q.D = Q; q.ldd = c; q.M = q.N = q.K = c;
+            q.terms = terms; q.alpha = 1.f;
+            OPTEX_TRY(tc_must(gemm_tc(q, st)));
+            TcGemm g{};  // next[c_out, n] = sum_k Q[k, c_out] cur[k, n]
+            g.A = Q; g.a_mn = true; g.B = cur; g.b_mn = true; g.D = nxt; g.ldd = n_p; g.M = c; g.N = n_p; g.K = c;
+            g.terms = terms; g.alpha = 1.f; g.rowrange = cdf ? minmax : nullptr; g.presplit_b = true;
+            OPTEX_TRY(tc_must(gemm_tc(g, st)));
+            float *t = cur; cur = nxt; nxt = t;
+            r1 = true;
+        }
+        OPTEX_TRY(rotate_forward(S, R, rs, n_s, c, true, st, 0, -1, cdf ? minmax : nullptr, &r2));
+        if (cdf)
+            OPTEX_TRY(cdf_match_core(cur, rs, cur, c, n_p, n_s, 256, nullptr, mw, mws, r1 && r2, st));
+        else
+            OPTEX_TRY(sort_match_inplace(cur, rs, cur, c, n_p, n_s, nullptr, mw, mws, st));
+    }
+    return rotate_inverse(cur, true, R, feat, n_p, c, nullptr, 0.f, st);
 }
 
 extern "C" int optex_ot_loop(float *feat, const float *S, const float *R_all, int iters, uint64_t seed,
@@ -323,8 +409,8 @@ extern "C" int optex_ot_loop(float *feat, const float *S, const float *R_all, in
     const size_t step_ws = optex_ot_workspace_bytes(n_p, n_s, c, mode);
     Arena ar(workspace, workspace_bytes);
     void *sw = ar.take<char>(step_ws);
-    float *alt = per_channel(mode) ? nullptr : ar.take<float>((size_t)n_p * c);
-    float *rbuf = ar.take<float>((size_t)kRotChunk * c * c);
+    float *alt = ar.take<float>((size_t)n_p * c);
+    float *rbuf = ar.take<float>((size_t)(kRotChunk + 2) * c * c);
     size_t rws_bytes = rotation_ws_bytes(c, kRotChunk);
     void *rws = ar.take<char>(rws_bytes);
     if (!ar.ok()) {
@@ -333,6 +419,14 @@ extern "C" int optex_ot_loop(float *feat, const float *S, const float *R_all, in
         return OPTEX_EWORKSPACE;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    {
+        bool forced;
+        if (per_channel(mode) && !content && iters >= 2 && want_tc(forced) && c % 32 == 0 && n_p % 32 == 0 &&
+            (mode != OPTEX_MODE_SORT || sort_match_scratch_bytes(c, n_p, n_s) == 0))
+            return ot_loop_fused(feat, S, R_all, iters, seed, first_counter, n_p, n_s, c, mode, sw, step_ws, alt, rbuf,
+                                 rws, rws_bytes, st);
+    }
+    if (per_channel(mode)) alt = nullptr;
     for (int i = 0; i < iters; ++i) {
         const float *R;
         if (R_all) {

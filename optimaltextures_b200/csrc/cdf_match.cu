@@ -124,6 +124,7 @@ __device__ __forceinline__ float range_hi(const uint32_t *minmax, int ch) { retu
 __global__ void __launch_bounds__(NT)
 cdf_range_kernel(const float *__restrict__ t, const float *__restrict__ s, int64_t n_t, int64_t n_s,
                  uint32_t *__restrict__ minmax, int t_vec, int s_vec) {
+    pdl_wait();
     const int ch = blockIdx.y;
     float mn = INFINITY, mx = -INFINITY;
     auto upd = [&](float x) { mn = fminf(mn, x); mx = fmaxf(mx, x); };
@@ -204,6 +205,7 @@ __global__ void __launch_bounds__(NTH_HIST, 9)
 cdf_hist_kernel(const float *__restrict__ t, const float *__restrict__ s, int64_t n_t, int64_t n_s,
                 const uint32_t *__restrict__ minmax, uint32_t *__restrict__ hist, int bins, int t_vec,
                 int s_vec) {
+    pdl_wait();
     extern __shared__ uint32_t smem_u32[];
     uint32_t *acc = smem_u32;          // [bins]
     uint32_t *priv = smem_u32 + bins;  // [bins/4][NTH]  (PRIV only)
@@ -267,6 +269,7 @@ __device__ void build_tables(const uint32_t *__restrict__ gh, float lo, float hi
 __global__ void __launch_bounds__(NT)
 cdf_tables_kernel(const uint32_t *__restrict__ minmax, const uint32_t *__restrict__ hist, int bins,
                   float *__restrict__ tbl, float *__restrict__ tables_out) {
+    pdl_wait();
     extern __shared__ float smem_f32[];
     float *edges = smem_f32, *remap = edges + bins, *tc = remap + bins, *sc = tc + bins;
     uint32_t *cnt = reinterpret_cast<uint32_t *>(sc + bins);
@@ -297,6 +300,7 @@ cdf_tables_kernel(const uint32_t *__restrict__ minmax, const uint32_t *__restric
 __global__ void __launch_bounds__(NT)
 cdf_apply_kernel(const float *t, float *out, int64_t n_t, const uint32_t *__restrict__ minmax,
                  const float *__restrict__ tbl, int bins, int vec) {
+    pdl_wait();
     __shared__ float tb[3 * MAX_BINS];
     const int ch = blockIdx.y;
     const float *g = tbl + (int64_t)ch * 4 * bins;
@@ -379,6 +383,7 @@ size_t cdf_minmax_bytes(int c) { return sizeof(uint32_t) * 2 * (size_t)c; }
 
 namespace {
 __global__ void fill_u32_kernel(uint32_t *p, int64_t n, uint32_t v) {
+    pdl_wait();
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
 }
@@ -386,7 +391,7 @@ __global__ void fill_u32_kernel(uint32_t *p, int64_t n, uint32_t v) {
 // (a plain kernel: cudaMemsetAsync on a few KB measured ~10x slower than this launch)
 int fill_u32(uint32_t *p, int64_t n, uint32_t v, cudaStream_t st) {
     if (n <= 0) return OPTEX_OK;
-    fill_u32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, n, v);
+    launch_pdl(fill_u32_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, p, n, v);
     OPTEX_LAUNCH_CHECK("fill_u32_kernel");
     return OPTEX_OK;
 }
@@ -418,7 +423,7 @@ int cdf_match_core(const float *target, const float *source, float *out, int c, 
     if (!have_range) {
         OPTEX_TRY(fill_u32(minmax, 2 * (int64_t)c, 0xffffffffu, st));
         dim3 grid((unsigned)cdf_splits(c, n_big), (unsigned)c);
-        cdf_range_kernel<<<grid, NT, 0, st>>>(target, source, n_t, n_s, minmax, t_vec, s_vec);
+        launch_pdl(cdf_range_kernel, grid, dim3(NT), 0, st, target, source, n_t, n_s, minmax, t_vec, s_vec);
         OPTEX_LAUNCH_CHECK("cdf_range_kernel");
     }
     const bool priv = (bins % 4 == 0) && bins <= PRIV_MAX_BINS;
@@ -435,16 +440,19 @@ int cdf_match_core(const float *target, const float *source, float *out, int c, 
                                             (int)(sizeof(uint32_t) * (2 * PRIV_MAX_BINS + (PRIV_MAX_BINS / 4) * NTH_HIST))));
             attr_done = true;
         }
-        cdf_hist_kernel<true><<<grid_h, NTH_HIST, smem, st>>>(target, source, n_t, n_s, minmax, hist, bins, t_vec, s_vec);
+        launch_pdl(cdf_hist_kernel<true>, grid_h, dim3(NTH_HIST), smem, st, target, source, n_t, n_s,
+                   (const uint32_t *)minmax, hist, bins, t_vec, s_vec);
     } else {
-        cdf_hist_kernel<false><<<grid_h, NTH_HIST, sizeof(uint32_t) * 2 * bins, st>>>(target, source, n_t, n_s, minmax,
-                                                                                   hist, bins, t_vec, s_vec);
+        launch_pdl(cdf_hist_kernel<false>, grid_h, dim3(NTH_HIST), sizeof(uint32_t) * 2 * bins, st, target, source, n_t,
+                   n_s, (const uint32_t *)minmax, hist, bins, t_vec, s_vec);
     }
     OPTEX_LAUNCH_CHECK("cdf_hist_kernel");
-    cdf_tables_kernel<<<c, NT, sizeof(float) * 6 * bins, st>>>(minmax, hist, bins, tbl, tables);
+    launch_pdl(cdf_tables_kernel, dim3((unsigned)c), dim3(NT), sizeof(float) * 6 * bins, st, (const uint32_t *)minmax,
+               (const uint32_t *)hist, bins, tbl, tables);
     OPTEX_LAUNCH_CHECK("cdf_tables_kernel");
     dim3 grid_a((unsigned)cdf_splits(c, n_t), (unsigned)c);
-    cdf_apply_kernel<<<grid_a, NT, 0, st>>>(target, out, n_t, minmax, tbl, bins, o_vec);
+    launch_pdl(cdf_apply_kernel, grid_a, dim3(NT), 0, st, target, out, n_t, (const uint32_t *)minmax, (const float *)tbl,
+               bins, o_vec);
     OPTEX_LAUNCH_CHECK("cdf_apply_kernel");
     return OPTEX_OK;
 }

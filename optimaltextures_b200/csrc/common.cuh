@@ -51,6 +51,35 @@ struct Arena {
     bool ok() const { return base != nullptr && off <= cap; }
 };
 
+// ---- programmatic dependent launch (PDL) --------------------------------------
+// Every kernel of the step waits on griddepcontrol.wait before it touches memory and is launched with
+// programmaticStreamSerializationAllowed: the next kernel's launch is processed while its predecessor still runs
+// (a dependent-launch boundary otherwise costs ~5 us of idle GPU), and the wait returns once the predecessor's
+// memory is visible.  Kernels launched this way MUST call pdl_wait() first.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool pdl_enabled();  // optex_set_pdl(); defined in api.cu
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args... args) {
+    if (!pdl_enabled()) {
+        kern<<<grid, block, smem, st>>>(static_cast<KArgs>(args)...);
+        return cudaSuccess;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ---- device helpers ---------------------------------------------------------
 // Order-preserving float <-> uint32 (for atomicMin/Max and radix/bitonic keys).
 __device__ __forceinline__ uint32_t f2ord(float f) {

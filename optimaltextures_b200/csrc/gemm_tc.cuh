@@ -33,10 +33,17 @@ struct TcGemm {
     int64_t bias_hw, bias_ld;
     float alpha;
     const int *skip;
+    bool presplit_b;     // 3xTF32: split B with an element-wise pass even though M is small (B is the big operand)
+    uint32_t *rowrange;  // !d_trans: per output row, the same fold (rows = channels in the fused loop)
     uint32_t *colrange;  // d_trans only: per output column, atomicMin of (f2ord(v), ~f2ord(v)) - see cdf_match.cu
 };
 // selects which of the two library-owned hi/lo scratch buffers the calling thread's GEMMs use (pipelined callers)
 void gemm_tc_set_scratch_slot(int slot);
+// 3xTF32 with a pre-split B: while registered (thread-local), gemm_tc() calls whose B pointer equals `src` use the
+// given hi / lo halves instead of splitting B again (src == nullptr clears it)
+void gemm_tc_set_presplit(const float *src, const float *hi, const float *lo);
+int gemm_tc_split_and_fill(const float *x, float *hi, float *lo, int64_t n, uint32_t *fill, int64_t fill_n,
+                           uint32_t fill_v, cudaStream_t st);
 // OPTEX_OK, OPTEX_ENOTSUP (shape/alignment outside the TMA constraints) or an error
 int gemm_tc(const TcGemm &g, cudaStream_t st);
 

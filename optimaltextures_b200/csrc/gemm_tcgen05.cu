@@ -157,6 +157,7 @@ struct Params {
     int conv_a;           // terms == 3: A arrives raw (tmA_hi) and warps 2-5 split it into hi/lo in shared memory
     int nz;               // number of split-K slices (tiles enumerate z as well)
     uint32_t *colrange;   // D_TRANS only: per output column [2]: atomicMin of f2ord(v) and of ~f2ord(v) (range fold)
+    uint32_t *rowrange;   // !D_TRANS: the same per output ROW (rows = channels in the fused loop's mid rotation)
     int conv_b;           // same for B (small problems, where a pre-split pass per GEMM would dominate)
 };
 
@@ -181,6 +182,7 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     __shared__ __align__(8) uint64_t tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_smem;
 
+    pdl_wait();
     if (p.skip && *p.skip) return;  // uniform over the grid
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nterm_tiles = p.terms == 3 ? 2 : 1;  // hi (+ lo) tiles per operand
@@ -386,6 +388,7 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
             mbar_wait(&tfull_bar[acc], aph);
             tc_fence_after();
             const int64_t row = (int64_t)m0 + q * 32 + lane;
+            uint32_t rmn = 0xffffffffu, rmx = 0xffffffffu;  // this thread's row: f2ord(min), ~f2ord(max)
 #pragma unroll 1
             for (int col = 0; col < BLOCK_N; col += 32) {
                 if (n0 + col >= p.N) break;
@@ -426,6 +429,11 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                         float o = p.alpha * __uint_as_float(v[j]);
                         if (bias && n0 + col + j < p.N) o = __fadd_rn(o, __ldg(bias + j));
                         v[j] = __float_as_uint(o);
+                        if (p.rowrange && n0 + col + j < p.N) {
+                            const uint32_t u = f2ord(o);
+                            rmn = u < rmn ? u : rmn;
+                            rmx = ~u < rmx ? ~u : rmx;
+                        }
                     }
                     if (n0 + col + 32 <= p.N) {
                         // 256-bit accesses: every store is one full 32-byte sector of this thread's output row
@@ -459,6 +467,10 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                     }
                 }
             }
+            if (!D_TRANS && p.rowrange && row < p.M) {
+                atomicMin(p.rowrange + 2 * row, rmn);
+                atomicMin(p.rowrange + 2 * row + 1, rmx);
+            }
             // all of this warp's TMEM reads have completed (tcgen05.wait::ld in tmem_ld32): release the accumulator
             tc_fence_before();
             __syncwarp();
@@ -479,6 +491,7 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
 // a -> (tf32(a), tf32(a - tf32(a)))   round-to-nearest split, both halves exactly representable in tf32
 __global__ void split_tf32_kernel(const float4 *__restrict__ x, float4 *__restrict__ hi, float4 *__restrict__ lo,
                                   int64_t n4) {
+    pdl_wait();
     auto split = [](float a, float &h, float &l) { split_tf32(a, h, l); };
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
         float4 v = __ldg(x + i), h, l;
@@ -489,6 +502,22 @@ __global__ void split_tf32_kernel(const float4 *__restrict__ x, float4 *__restri
         hi[i] = h;
         lo[i] = l;
     }
+}
+
+__global__ void split_fill_kernel(const float4 *__restrict__ x, float4 *__restrict__ hi, float4 *__restrict__ lo,
+                                  int64_t n4, uint32_t *__restrict__ fill, int64_t fill_n, uint32_t fill_v) {
+    pdl_wait();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n4) {
+        float4 v = __ldg(x + i), h, l;
+        split_tf32(v.x, h.x, l.x);
+        split_tf32(v.y, h.y, l.y);
+        split_tf32(v.z, h.z, l.z);
+        split_tf32(v.w, h.w, l.w);
+        hi[i] = h;
+        lo[i] = l;
+    }
+    if (i < fill_n) fill[i] = fill_v;
 }
 
 // ------------------------------------------------------------------ host side
@@ -551,6 +580,10 @@ struct Scratch {
 Scratch g_scratch[64][2];  // [device][slot]: two independent pipelines (optex_ot_step_host_async) may be in flight
 std::mutex g_scratch_mu;
 thread_local int g_scratch_slot = 0;
+struct Presplit {
+    const float *src, *hi, *lo;
+};
+thread_local Presplit g_presplit = {nullptr, nullptr, nullptr};
 
 int scratch(size_t bytes, float **out) {
     int dev = 0;
@@ -577,7 +610,7 @@ int split(const float *x, float *hi, float *lo, int64_t n, cudaStream_t st) {
     int blocks = (int)((n4 + 255) / 256);
     int cap = sm_count() * 8;
     if (blocks > cap) blocks = cap;
-    split_tf32_kernel<<<blocks, 256, 0, st>>>((const float4 *)x, (float4 *)hi, (float4 *)lo, n4);
+    launch_pdl(split_tf32_kernel, dim3(blocks), dim3(256), 0, st, (const float4 *)x, (float4 *)hi, (float4 *)lo, n4);
     OPTEX_LAUNCH_CHECK("split_tf32_kernel");
     return OPTEX_OK;
 }
@@ -599,7 +632,7 @@ int launch(const CUtensorMap &ah, const CUtensorMap &al, const CUtensorMap &bh, 
     const int64_t num_tiles = ((p.M + BLOCK_M - 1) / BLOCK_M) * ((p.N + BLOCK_N - 1) / BLOCK_N) * nz;
     const int sms = sm_count();
     dim3 grid((unsigned)(num_tiles < sms ? num_tiles : sms));  // persistent: one CTA per SM walks the tile list
-    kern<<<grid, NTHREADS, smem, st>>>(ah, al, bh, bl, p);
+    launch_pdl(kern, grid, dim3(NTHREADS), smem, st, ah, al, bh, bl, p);
     OPTEX_LAUNCH_CHECK("rotate_gemm_kernel");
     return OPTEX_OK;
 }
@@ -633,6 +666,21 @@ inline int pick_block_n(int64_t M, int64_t N, int nz) {
 
 void gemm_tc_set_scratch_slot(int slot) { g_scratch_slot = slot & 1; }
 
+void gemm_tc_set_presplit(const float *src, const float *hi, const float *lo) { g_presplit = {src, hi, lo}; }
+
+// hi/lo split of x (n floats, n % 4 == 0) and, in the same launch, fill of a small u32 array (the cdf range slots)
+int gemm_tc_split_and_fill(const float *x, float *hi, float *lo, int64_t n, uint32_t *fill, int64_t fill_n,
+                           uint32_t fill_v, cudaStream_t st) {
+    const int64_t n4 = n / 4;
+    int64_t work = n4 > fill_n ? n4 : fill_n;
+    int blocks = (int)((work + 255) / 256);
+    if (blocks < 1) blocks = 1;
+    launch_pdl(split_fill_kernel, dim3(blocks), dim3(256), 0, st, (const float4 *)x, (float4 *)hi, (float4 *)lo, n4, fill,
+               fill_n, fill_v);
+    OPTEX_LAUNCH_CHECK("split_fill_kernel");
+    return OPTEX_OK;
+}
+
 int gemm_tc(const TcGemm &g, cudaStream_t st) {
     if (!encode_fn() || g.M < 1 || g.N < 1 || g.K < 1 || g.M > 0x3fffffffLL || g.N > 0x3fffffffLL || g.K > 0x3fffffffLL)
         return OPTEX_ENOTSUP;
@@ -664,8 +712,13 @@ int gemm_tc(const TcGemm &g, cudaStream_t st) {
         // pre-split by an element-wise pass
         (void)na;
         static const char *force_cb = getenv("OPTEX_FORCE_CONVB");
-        conv_b = force_cb ? atoi(force_cb) != 0 : g.M <= 4096;  // few M tiles share B: split it in the kernel
-        if (!conv_b) {
+        // few M tiles share B: split it in the kernel - unless B is the big operand (presplit_b), where converting
+        // it in shared memory would make the kernel smem-bandwidth bound
+        conv_b = force_cb ? atoi(force_cb) != 0 : (g.M <= 4096 && !g.presplit_b);
+        if (!conv_b && g_presplit.src == g.B && g.B != nullptr) {
+            bh_p = g_presplit.hi;  // the caller split this operand once for several GEMMs (the step's rotation R)
+            bl_p = g_presplit.lo;
+        } else if (!conv_b) {
             float *buf;
             OPTEX_TRY(scratch(2 * nb * sizeof(float), &buf));
             float *b_hi = buf, *b_lo = b_hi + nb;
@@ -698,6 +751,7 @@ int gemm_tc(const TcGemm &g, cudaStream_t st) {
     p.alpha = g.alpha; p.skip = g.skip; p.conv_a = p.terms == 3 ? 1 : 0; p.conv_b = conv_b ? 1 : 0;
     p.nz = nz;
     p.colrange = g.d_trans ? g.colrange : nullptr;
+    p.rowrange = g.d_trans ? nullptr : g.rowrange;
     if (g.d_trans) return launch_n<false, true, true>(bn, ah, al, bh, bl, p, nz, st);
     if (!g.a_mn && !g.b_mn) return launch_n<false, false, false>(bn, ah, al, bh, bl, p, nz, st);
     if (!g.a_mn && g.b_mn) return launch_n<false, true, false>(bn, ah, al, bh, bl, p, nz, st);

@@ -139,6 +139,7 @@ __host__ __device__ constexpr size_t radix_smem_bytes() {
 template <int LOG_E>
 __global__ void __launch_bounds__(NT, 1)
 sort_source_kernel(float *src, int64_t n_s) {
+    pdl_wait();
     constexpr int E = 1 << LOG_E;
     constexpr int N2 = NT * E;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -162,6 +163,7 @@ template <int LOG_E>
 __global__ void __launch_bounds__(NT, 1)
 sort_target_kernel(const float *target, const float *__restrict__ sorted_source, float *out, int64_t n_t, int64_t n_s,
                    int32_t *__restrict__ perm) {
+    pdl_wait();
     constexpr int E = 1 << LOG_E;
     constexpr int N2 = NT * E;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -211,7 +213,7 @@ int launch_source_sort(float *s_sorted, int c, int64_t n_s, cudaStream_t st) {
                                         (int)smem_s));
         attr_done = true;
     }
-    sort_source_kernel<LOG_E><<<c, NT, smem_s, st>>>(s_sorted, n_s);
+    launch_pdl(sort_source_kernel<LOG_E>, dim3((unsigned)c), dim3(NT), smem_s, st, s_sorted, n_s);
     OPTEX_LAUNCH_CHECK("sort_source_kernel");
     return OPTEX_OK;
 }
@@ -225,7 +227,8 @@ int launch_target_sort(const float *t, const float *s_sorted, float *out, int c,
                                         (int)smem_t));
         attr_done = true;
     }
-    sort_target_kernel<LOG_E><<<c, NT, smem_t, st>>>(t, s_sorted, out, n_t, n_s, perm);
+    launch_pdl(sort_target_kernel<LOG_E>, dim3((unsigned)c), dim3(NT), smem_t, st, t, (const float *)s_sorted, out, n_t, n_s,
+               perm);
     OPTEX_LAUNCH_CHECK("sort_target_kernel");
     return OPTEX_OK;
 }

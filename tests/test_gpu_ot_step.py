@@ -132,6 +132,47 @@ def test_inner_loop_with_content(ob, golden, mode):
         close_in_bulk(got.cpu().numpy(), g["out_cdf"], tol=5e-4, frac=2e-2)
 
 
+@pytest.mark.parametrize("mode", ["cdf", "sort"])
+@pytest.mark.parametrize("device_rotations", [False, True])
+def test_ot_loop_fused_rotations(ob, mode, device_rotations):
+    """ot_loop without content fuses `un-rotate with R_i, rotate with R_{i+1}` into one rotation by R_i^T R_{i+1}
+    (two GEMMs per iteration instead of three).  A chain of matcher steps amplifies last-bit differences (the cdf
+    map is discontinuous at bin edges and the next rotation spreads a flipped bin over all channels; SURVEY H4:
+    parity is a per-step notion), so the criterion is self-calibrating: the fused loop must be no further from the
+    step-by-step loop than the step-by-step loop is from ITSELF under a different fp32-grade GEMM arithmetic
+    (fp32 FFMA vs 3xTF32)."""
+    c = 64
+    g = torch.Generator().manual_seed(3)
+    p = torch.relu(torch.randn(1, 64, 64, c, generator=g)).cuda()
+    s = torch.relu(1.3 * torch.randn(1, 48, 80, c, generator=g) + 0.2).cuda()
+
+    def stepwise(rots):
+        ref = p
+        for r in rots:
+            ref = ob.optimal_transport(ref, s, mode, rotation=r)
+        return ref
+
+    for iters in (2, 5):
+        rots = ob.random_rotations(c, iters, "cuda", seed=21, first_counter=100)
+        if device_rotations:
+            got = ob.ot_loop(p, s, mode, iters, seed=21, first_counter=100)
+        else:
+            got = ob.ot_loop(p, s, mode, iters, rotations=rots)
+        ref = stepwise(rots)
+        ob.set_gemm_mode("fp32")
+        try:
+            ref_fp32 = stepwise(rots)
+        finally:
+            ob.set_gemm_mode("auto")
+        dist = lambda x, y: float((x - y).abs().mean())
+        assert dist(got, ref) <= 1.5 * dist(ref, ref_fp32) + 1e-6, (iters, dist(got, ref), dist(ref, ref_fp32))
+        # and it is a real transport: the result's marginals along the last rotation are the style's
+        q = torch.tensor([0.1, 0.5, 0.9], device="cuda")
+        a = torch.quantile((got.reshape(-1, c) @ rots[-1])[:, :8], q, dim=0)
+        b = torch.quantile((s.reshape(-1, c) @ rots[-1])[:, :8], q, dim=0)
+        assert float((a - b).abs().max()) < (0.05 if mode == "cdf" else 5e-3)
+
+
 def test_ot_step_host_buffers(ob, golden):
     g = golden("ot_step")
     t, s, rot = T(g["wide64_t"]), T(g["wide64_s"]), T(g["wide64_rot"]).float()
