@@ -5,6 +5,7 @@
 //   hist_match()         histmatch.py:5-46     -> optex_hist_match
 #include <atomic>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -421,7 +422,8 @@ extern "C" int optex_ot_loop(float *feat, const float *S, const float *R_all, in
     cudaStream_t st = (cudaStream_t)stream;
     {
         bool forced;
-        if (per_channel(mode) && !content && iters >= 2 && want_tc(forced) && c % 32 == 0 && n_p % 32 == 0 &&
+        static const char *no_fuse = getenv("OPTEX_NO_LOOP_FUSION");
+        if (!no_fuse && per_channel(mode) && !content && iters >= 2 && want_tc(forced) && c % 32 == 0 && n_p % 32 == 0 &&
             (mode != OPTEX_MODE_SORT || sort_match_scratch_bytes(c, n_p, n_s) == 0))
             return ot_loop_fused(feat, S, R_all, iters, seed, first_counter, n_p, n_s, c, mode, sw, step_ws, alt, rbuf,
                                  rws, rws_bytes, st);
