@@ -68,6 +68,9 @@ int optex_get_gemm_mode(void);
 /* Programmatic dependent launch between the library's kernels (default on).  Turn it off to time individual
  * kernels with CUDA events: under PDL a kernel may start before its predecessor has drained. */
 int optex_set_pdl(int enable);
+/* Debug aid: CTA 0 of every following rotation GEMM writes 64 clock64() stamps (16 k-blocks x {TMA issue, tile
+ * landed, hi/lo split done, MMA start}) of its first tile into device_buf (NULL = off). */
+int optex_debug_gemm_trace(void *device_buf);
 
 /* ---- the OT step -----------------------------------------------------------
  * replaces: optimal_transport()  optex.py:167-177  (+ the content blend of the

@@ -234,6 +234,10 @@ extern "C" int optex_set_gemm_mode(int m) {
     return OPTEX_OK;
 }
 extern "C" int optex_get_gemm_mode(void) { return g_gemm_mode.load(); }
+extern "C" int optex_debug_gemm_trace(void *device_buf) {
+    gemm_tc_set_trace((unsigned long long *)device_buf);
+    return OPTEX_OK;
+}
 extern "C" int optex_set_pdl(int enable) {
     g_pdl.store(enable ? 1 : 0);
     return OPTEX_OK;

@@ -33,12 +33,14 @@ struct TcGemm {
     int64_t bias_hw, bias_ld;
     float alpha;
     const int *skip;
+    bool stream_a;       // A is not needed again after this GEMM: load it with L2 evict-first priority
     bool presplit_b;     // 3xTF32: split B with an element-wise pass even though M is small (B is the big operand)
     uint32_t *rowrange;  // !d_trans: per output row, the same fold (rows = channels in the fused loop)
     uint32_t *colrange;  // d_trans only: per output column, atomicMin of (f2ord(v), ~f2ord(v)) - see cdf_match.cu
 };
 // selects which of the two library-owned hi/lo scratch buffers the calling thread's GEMMs use (pipelined callers)
 void gemm_tc_set_scratch_slot(int slot);
+void gemm_tc_set_trace(unsigned long long *device_buf);  // debug: 64 x u64 clock stamps of CTA 0's first tile
 // 3xTF32 with a pre-split B: while registered (thread-local), gemm_tc() calls whose B pointer equals `src` use the
 // given hi / lo halves instead of splitting B again (src == nullptr clears it)
 void gemm_tc_set_presplit(const float *src, const float *hi, const float *lo);

@@ -33,7 +33,11 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 32;  // K granularity of split-K slices (both stage depths divide it)
 constexpr int UMMA_K = 8;    // 32 B of K per tcgen05.mma.kind::tf32
 constexpr int MAX_STAGES = 8;
-constexpr int NTHREADS = 320;  // producer, MMA, 4 converter and 4 epilogue warps
+// The epilogue (TMEM -> registers -> global) of a 128 x 256 tile took 20 k cycles with 4 warps - as long as a whole
+// plain-TF32 main loop and exposed after the last tile; EPI_GROUPS groups of 4 warps (one warp per TMEM lane quadrant)
+// split the tile's columns between them.
+constexpr int EPI_GROUPS = 4;
+constexpr int NTHREADS = 192 + EPI_GROUPS * 128;  // producer, MMA, 4 converter warps, 4 x EPI_GROUPS epilogue warps
 constexpr int SMEM_BUDGET = 227 * 1024 - 4096;  // tiles; + 1 KB alignment slack + ~1 KB static (barriers)
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -66,16 +70,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
             : "memory");
     }
 }
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint64_t *bar, void *dst, int x, int y) {
+// L2 eviction-priority hints for TMA loads (the encodings CUTLASS uses for createpolicy results)
+constexpr uint64_t L2_EVICT_NORMAL = 0x1000000000000000ull;
+constexpr uint64_t L2_EVICT_FIRST = 0x12F0000000000000ull;  // streamed once: do not displace the step's intermediates
+constexpr uint64_t L2_EVICT_LAST = 0x14F0000000000000ull;   // re-read by every tile (the rotation matrix)
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint64_t *bar, void *dst, int x, int y,
+                                            uint64_t hint) {
     asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "l"(hint)
         : "memory");
 }
-__device__ __forceinline__ void tma_load_3d(const CUtensorMap *map, uint64_t *bar, void *dst, int x, int y, int z) {
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap *map, uint64_t *bar, void *dst, int x, int y, int z,
+                                            uint64_t hint) {
     asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z)
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z), "l"(hint)
         : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *map, int x, int y) {
@@ -157,6 +169,8 @@ struct Params {
     int conv_a;           // terms == 3: A arrives raw (tmA_hi) and warps 2-5 split it into hi/lo in shared memory
     int nz;               // number of split-K slices (tiles enumerate z as well)
     uint32_t *colrange;   // D_TRANS only: per output column [2]: atomicMin of f2ord(v) and of ~f2ord(v) (range fold)
+    uint64_t a_hint, b_hint;    // L2 eviction priority of the operand loads
+    unsigned long long *trace;  // debug: CTA 0 records clock stamps of its first tile's pipeline events (or null)
     uint32_t *rowrange;   // !D_TRANS: the same per output ROW (rows = channels in the fused loop's mid rotation)
     int conv_b;           // same for B (small problems, where a pre-split pass per GEMM would dominate)
 };
@@ -182,7 +196,9 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     __shared__ __align__(8) uint64_t tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_smem;
 
+    if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[64] = clock64();
     pdl_wait();
+    if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[65] = clock64();
     if (p.skip && *p.skip) return;  // uniform over the grid
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nterm_tiles = p.terms == 3 ? 2 : 1;  // hi (+ lo) tiles per operand
@@ -208,7 +224,7 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);   // tcgen05.commit of the tile's last MMA
-            mbar_init(&tempty_bar[a], 4);  // one arrival per epilogue warp
+            mbar_init(&tempty_bar[a], 4 * EPI_GROUPS);  // one arrival per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -223,6 +239,7 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
+    if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[66] = clock64();
 
     // tile -> (z, m, n): n fastest, so CTAs running side by side share the rows of the big A operand in L2
     auto tile_coords = [&](int tile, int &m0, int &n0, int &z) {
@@ -249,6 +266,7 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                 k_range(z, k_begin, num_kb);
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[s], ph ^ 1);
+                    if (p.trace && blockIdx.x == 0 && tile == (int)blockIdx.x && kb < 16) p.trace[kb * 4 + 0] = clock64();
                     uint8_t *st = tiles + (size_t)s * stage_bytes;
                     // conv_a: the raw A tile lands in the hi slot and signals the converter warps (raw_bar);
                     // otherwise hi and lo halves of both operands arrive pre-split and signal the MMA warp directly
@@ -261,12 +279,12 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                         uint8_t *a_dst = st + t * A_TILE;
                         uint8_t *b_dst = st + nterm_tiles * A_TILE + t * B_TILE;
                         if (t == 0 || !p.conv_a) {
-                            if (A_MN) tma_load_3d(ma, bar, a_dst, 0, k0, m0 / 32);
-                            else tma_load_2d(ma, bar, a_dst, k0, m0);
+                            if (A_MN) tma_load_3d(ma, bar, a_dst, 0, k0, m0 / 32, p.a_hint);
+                            else tma_load_2d(ma, bar, a_dst, k0, m0, p.a_hint);
                         }
                         if (t == 0 || !p.conv_b) {
-                            if (B_MN) tma_load_3d(mb, bar, b_dst, 0, k0, n0 / 32);
-                            else tma_load_2d(mb, bar, b_dst, k0, n0);
+                            if (B_MN) tma_load_3d(mb, bar, b_dst, 0, k0, n0 / 32, p.b_hint);
+                            else tma_load_2d(mb, bar, b_dst, k0, n0, p.b_hint);
                         }
                     }
                     if (++s == p.stages) { s = 0; ph ^= 1; }
@@ -294,6 +312,8 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
             for (int kb = 0; kb < num_kb; ++kb) {
                 mbar_wait(&full_bar[s], ph);
                 tc_fence_after();
+                if (p.trace && blockIdx.x == 0 && tile == (int)blockIdx.x && kb < 16 && lane == 0) p.trace[kb * 4 + 3] = clock64();
+                if (p.trace && blockIdx.x == 0 && tile != (int)blockIdx.x && (kb == 0 || kb == num_kb - 1) && lane == 0) p.trace[76 + (kb ? 1 : 0)] = clock64();
                 if (elect_one()) {
                     const uint32_t st = smem_u32(tiles + (size_t)s * stage_bytes);
                     const uint32_t a_hi = st, a_lo = st + A_TILE;
@@ -340,6 +360,7 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                 k_range(z, k_begin, num_kb);
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&raw_bar[s], ph);
+                    if (p.trace && blockIdx.x == 0 && tile == (int)blockIdx.x && kb < 16 && ct == 0) p.trace[kb * 4 + 1] = clock64();
                     float4 *hi = reinterpret_cast<float4 *>(tiles + (size_t)s * stage_bytes);
                     float4 *lo = reinterpret_cast<float4 *>(tiles + (size_t)s * stage_bytes + A_TILE);
 #pragma unroll
@@ -371,6 +392,7 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                     if (lane == 0)
                         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full_bar[s]))
                                      : "memory");
+                    if (p.trace && blockIdx.x == 0 && tile == (int)blockIdx.x && kb < 16 && ct == 0) p.trace[kb * 4 + 2] = clock64();
                     if (++s == p.stages) { s = 0; ph ^= 1; }
                 }
             }
@@ -378,6 +400,8 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     } else {
         // ===== epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31
         const int q = warp & 3;
+        const int egrp = (warp - 6) >> 2;                     // which column slice of the tile this warp drains
+        constexpr int EPI_COLS = BLOCK_N / EPI_GROUPS < 32 ? 32 : BLOCK_N / EPI_GROUPS;
         int titer = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++titer) {
             int m0, n0, z;
@@ -387,10 +411,11 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
             float *const Dz = p.D + (int64_t)z * p.d_z_stride;
             mbar_wait(&tfull_bar[acc], aph);
             tc_fence_after();
+            if (p.trace && blockIdx.x == 0 && warp == 6 && lane == 0 && titer < 4) p.trace[68 + titer * 2] = clock64();
             const int64_t row = (int64_t)m0 + q * 32 + lane;
             uint32_t rmn = 0xffffffffu, rmx = 0xffffffffu;  // this thread's row: f2ord(min), ~f2ord(max)
 #pragma unroll 1
-            for (int col = 0; col < BLOCK_N; col += 32) {
+            for (int col = egrp * EPI_COLS; col < (egrp + 1) * EPI_COLS && col < BLOCK_N; col += 32) {
                 if (n0 + col >= p.N) break;
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + col), v);
@@ -474,12 +499,14 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
             // all of this warp's TMEM reads have completed (tcgen05.wait::ld in tmem_ld32): release the accumulator
             tc_fence_before();
             __syncwarp();
+            if (p.trace && blockIdx.x == 0 && warp == 6 && lane == 0 && titer < 4) p.trace[69 + titer * 2] = clock64();
             if (lane == 0)
                 asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tempty_bar[acc])) : "memory");
         }
     }
     tc_fence_before();
     __syncthreads();
+    if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[67] = clock64();
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
@@ -664,6 +691,9 @@ inline int pick_block_n(int64_t M, int64_t N, int nz) {
 
 }  // namespace
 
+unsigned long long *g_trace = nullptr;
+void gemm_tc_set_trace(unsigned long long *t) { g_trace = t; }
+
 void gemm_tc_set_scratch_slot(int slot) { g_scratch_slot = slot & 1; }
 
 void gemm_tc_set_presplit(const float *src, const float *hi, const float *lo) { g_presplit = {src, hi, lo}; }
@@ -752,6 +782,10 @@ int gemm_tc(const TcGemm &g, cudaStream_t st) {
     p.nz = nz;
     p.colrange = g.d_trans ? g.colrange : nullptr;
     p.rowrange = g.d_trans ? nullptr : g.rowrange;
+    p.trace = g_trace;
+    // a big A operand is streamed exactly once (n_tiles_n CTAs read it at the same time); B is re-read by every tile
+    p.a_hint = (g.M > 4096 && g.stream_a) ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
+    p.b_hint = g.M > 4096 ? L2_EVICT_LAST : L2_EVICT_NORMAL;
     if (g.d_trans) return launch_n<false, true, true>(bn, ah, al, bh, bl, p, nz, st);
     if (!g.a_mn && !g.b_mn) return launch_n<false, false, false>(bn, ah, al, bh, bl, p, nz, st);
     if (!g.a_mn && g.b_mn) return launch_n<false, true, false>(bn, ah, al, bh, bl, p, nz, st);
@@ -768,6 +802,7 @@ int gemm_tc_rotate_forward(const float *X, const float *R, float *dst, int64_t n
     g.A = X; g.a_mn = false; g.B = R; g.b_col0 = c0; g.b_mn = true; g.ldb = c; g.D = dst;
     g.ldd = transposed ? n : (int64_t)nc;
     g.d_trans = transposed; g.M = n; g.N = nc; g.K = c; g.terms = terms; g.alpha = 1.f; g.colrange = colrange;
+    g.stream_a = true;  // the un-rotated block is not touched again in this step
     return gemm_tc(g, st);
 }
 
@@ -777,6 +812,7 @@ int gemm_tc_rotate_inverse(const float *M, bool m_channel_major, const float *R,
     TcGemm g{};
     g.A = M; g.a_mn = m_channel_major; g.B = R; g.b_mn = false; g.D = out; g.ldd = c;
     g.M = n; g.N = c; g.K = c; g.terms = terms; g.alpha = 1.f; g.blend = content; g.strength = strength;
+    g.stream_a = true;  // the matched block is consumed here
     return gemm_tc(g, st);
 }
 

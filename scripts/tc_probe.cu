@@ -29,8 +29,8 @@ probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const uint32_t tmem_base = tmem_base_smem;
     if (threadIdx.x == 0) {
         mbar_expect_tx(&full_bar, 16384 + 8192);
-        if (a_mn) tma_load_3d(&tmA, &full_bar, a_dst, 0, 0, 0); else tma_load_2d(&tmA, &full_bar, a_dst, 0, 0);
-        tma_load_2d(&tmB, &full_bar, b_dst, 0, 0);
+        if (a_mn) tma_load_3d(&tmA, &full_bar, a_dst, 0, 0, 0, L2_EVICT_NORMAL); else tma_load_2d(&tmA, &full_bar, a_dst, 0, 0, L2_EVICT_NORMAL);
+        tma_load_2d(&tmB, &full_bar, b_dst, 0, 0, L2_EVICT_NORMAL);
     }
     mbar_wait(&full_bar, 0);
     // dump smem: first 256 floats of A tile, first 256 floats of B tile
