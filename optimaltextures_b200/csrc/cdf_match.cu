@@ -77,6 +77,16 @@ struct HistRange {
         b = b >= bins ? bins - 1 : b;
         return b < 0 ? 0 : b;  // memory safety for NaN only
     }
+    // same rule, but x == hi is reported as bin `bins` (the caller folds it into bins - 1); values are in [lo, hi]
+    // by construction (lo / hi are the data's own extrema), NaN converts to 0
+    __device__ __forceinline__ int bin_unclamped(float x) const {
+        const float a = __fmul_rn(__fsub_rn(x, lo), fbins);
+        float q = a * rcp;
+        const float r = __fsub_rn(__fadd_rn(q, 12582912.f), 12582912.f);
+        if (!(fabsf(q - r) >= 1e-3f)) q = __fdiv_rn(a, width);
+        const unsigned b = (unsigned)(int)q;
+        return (int)(b > (unsigned)bins ? (unsigned)bins : b);  // one unsigned min: memory safety only
+    }
 };
 
 // torch.linspace(lo, hi, bins+1)[i], i in 1..bins  (CPU kernel: symmetric, FMA-rounded)
@@ -164,34 +174,73 @@ __device__ __forceinline__ void hist_slice(const float *__restrict__ row, int64_
         for_each<NTH>(row, beg, end, vec, [&](float x) { atomicAdd(&acc[hr.bin(x)], 1u); });
         return;
     }
-    const int words = hr.bins >> 2;  // bins % 4 == 0 on this path
+    // byte counters, [bin][thread] (bins + 1 rows: the closed right edge x == hi lands in row `bins` and is folded
+    // into the last bin, like torch).  One LDS.U8 / IADD / STS.U8 per element, no shifts or masks; the 32 lanes of a
+    // warp touch 8 consecutive words of one or several rows.
+    uint8_t *pb = reinterpret_cast<uint8_t *>(priv);
+    const int rows = hr.bins + 1;
     const int64_t chunk = (int64_t)NTH * 252;  // 63 float4 per thread: byte counters stay <= 252
     for (int64_t cb = beg; cb < end; cb += chunk) {
         int64_t ce = cb + chunk < end ? cb + chunk : end;
-        for (int w = 0; w < words; ++w) priv[w * NTH + tid] = 0u;
-        for_each<NTH>(row, cb, ce, vec, [&](float x) {
-            int b = hr.bin(x);
-            priv[(b >> 2) * NTH + tid] += 1u << ((b & 3) * 8);
-        });
+        for (int i = tid; i < rows * (NTH / 4); i += NTH) priv[i] = 0u;
         __syncthreads();
-        // packed fold: item (part, w) sums word w over `per` owners in two 2x16-bit accumulators
-        const int parts = NTH / words >= 1 ? NTH / words : 1;
-        const int per = (NTH + parts - 1) / parts;  // <= 256 owners x 255 counts fits 16 bits
-        for (int item = tid; item < words * parts; item += NTH) {
-            int w = item % words, part = item / words;
+        auto one = [&](float x) {
+            const int a = hr.bin_unclamped(x) * NTH + tid;
+            pb[a] = (uint8_t)(pb[a] + 1);
+        };
+        if (vec) {
+            // four elements per step with their four counter loads in flight together (a read-modify-write chain per
+            // element would expose the shared-memory latency 4x); equal addresses are resolved in registers and
+            // the stores keep program order
+            const int64_t nv = (ce - cb) >> 2;
+            const float4 *p4 = reinterpret_cast<const float4 *>(row + cb);
+            // 4 vector loads in flight per thread (the loop is otherwise bound by one L2 / HBM round trip per step)
+            constexpr int PF = 4;
+            float4 ring[PF];
+#pragma unroll
+            for (int k = 0; k < PF; ++k) {
+                const int64_t j = tid + (int64_t)k * NTH;
+                ring[k] = j < nv ? __ldg(p4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            for (int64_t i = tid; i < nv; i += (int64_t)PF * NTH) {
+#pragma unroll
+              for (int k = 0; k < PF; ++k) {
+                const int64_t cur = i + (int64_t)k * NTH;
+                if (cur >= nv) break;
+                const float4 v = ring[k];
+                const int64_t nxt = cur + (int64_t)PF * NTH;
+                if (nxt < nv) ring[k] = __ldg(p4 + nxt);
+                const int a0 = hr.bin_unclamped(v.x) * NTH + tid, a1 = hr.bin_unclamped(v.y) * NTH + tid;
+                const int a2 = hr.bin_unclamped(v.z) * NTH + tid, a3 = hr.bin_unclamped(v.w) * NTH + tid;
+                const uint32_t c0 = pb[a0], c1 = pb[a1], c2 = pb[a2], c3 = pb[a3];
+                const uint32_t n0 = c0 + 1;
+                const uint32_t n1 = (a1 == a0 ? n0 : c1) + 1;
+                const uint32_t n2 = (a2 == a1 ? n1 : (a2 == a0 ? n0 : c2)) + 1;
+                const uint32_t n3 = (a3 == a2 ? n2 : (a3 == a1 ? n1 : (a3 == a0 ? n0 : c3))) + 1;
+                pb[a0] = (uint8_t)n0;
+                pb[a1] = (uint8_t)n1;
+                pb[a2] = (uint8_t)n2;
+                pb[a3] = (uint8_t)n3;
+              }
+            }
+            for (int64_t i = cb + (nv << 2) + tid; i < ce; i += NTH) one(__ldg(row + i));
+        } else {
+            for (int64_t i = cb + tid; i < ce; i += NTH) one(__ldg(row + i));
+        }
+        __syncthreads();
+        // fold: thread t sums the NTH byte counters of rows t, t + NTH, ... with packed 16-bit adds
+        constexpr int WPR = NTH / 4;  // words per row
+        for (int r = tid; r < rows; r += NTH) {
             uint32_t even = 0, odd = 0;
-            int rot = (tid & 31) % per;  // start each lane on a different owner: distinct banks
-            for (int it = 0; it < per; ++it) {
-                int j = part * per + rot;
-                rot = rot + 1 == per ? 0 : rot + 1;
-                uint32_t v = j < NTH ? priv[w * NTH + j] : 0u;
+            int w = (tid & 31) % WPR;  // start each lane on a different word: distinct banks
+            for (int it = 0; it < WPR; ++it) {
+                const uint32_t v = priv[r * WPR + w];
+                w = w + 1 == WPR ? 0 : w + 1;
                 even += v & 0x00ff00ffu;
                 odd += (v >> 8) & 0x00ff00ffu;
             }
-            atomicAdd(&acc[4 * w + 0], even & 0xffffu);
-            atomicAdd(&acc[4 * w + 1], odd & 0xffffu);
-            atomicAdd(&acc[4 * w + 2], even >> 16);
-            atomicAdd(&acc[4 * w + 3], odd >> 16);
+            const uint32_t total = (even & 0xffffu) + (even >> 16) + (odd & 0xffffu) + (odd >> 16);
+            if (total) atomicAdd(&acc[r < hr.bins ? r : hr.bins - 1], total);
         }
         __syncthreads();
     }
@@ -433,11 +482,11 @@ int cdf_match_core(const float *target, const float *source, float *out, int c, 
     if (grid_h.x > 1)  // several CTAs add into one histogram: it has to start at zero
         OPTEX_TRY(fill_u32(hist, 2 * (int64_t)c * bins, 0u, st));
     if (priv) {
-        size_t smem = sizeof(uint32_t) * (2 * (size_t)bins + (size_t)(bins / 4) * NTH_HIST);
+        size_t smem = sizeof(uint32_t) * (size_t)bins + (size_t)(bins + 1) * NTH_HIST;
         static bool attr_done = false;
         if (!attr_done) {
             OPTEX_CUDA(cudaFuncSetAttribute(cdf_hist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)(sizeof(uint32_t) * (2 * PRIV_MAX_BINS + (PRIV_MAX_BINS / 4) * NTH_HIST))));
+                                            (int)(sizeof(uint32_t) * PRIV_MAX_BINS + (PRIV_MAX_BINS + 1) * NTH_HIST)));
             attr_done = true;
         }
         launch_pdl(cdf_hist_kernel<true>, grid_h, dim3(NTH_HIST), smem, st, target, source, n_t, n_s,
