@@ -37,7 +37,14 @@ constexpr int MAX_STAGES = 8;
 // plain-TF32 main loop and exposed after the last tile; EPI_GROUPS groups of 4 warps (one warp per TMEM lane quadrant)
 // split the tile's columns between them.
 constexpr int EPI_GROUPS = 4;
-constexpr int NTHREADS = 192 + EPI_GROUPS * 128;  // producer, MMA, 4 converter warps, 4 x EPI_GROUPS epilogue warps
+// warp roles are aligned to warpgroups (setmaxnreg works on 4 warps at a time):
+//   warps 0-3: TMA producer, MMA issuer, two idle | warps 4-7: converters | warps 8..: 4 x EPI_GROUPS epilogue warps
+constexpr int EPI_WARP0 = 8;
+constexpr int NTHREADS = EPI_WARP0 * 32 + EPI_GROUPS * 128;
+// A-via-TMEM (3xTF32, see the kernel comment): the accumulator keeps columns [0, BLOCK_N), the tf32 hi / lo halves of
+// the A tile live in a ring of TMEM stages behind it (32 + 32 columns per stage)
+constexpr int A_TMEM_COL0 = 256;
+constexpr int A_TMEM_STAGES = 4;
 constexpr int SMEM_BUDGET = 227 * 1024 - 4096;  // tiles; + 1 KB alignment slack + ~1 KB static (barriers)
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -114,6 +121,43 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// A operand from tensor memory (lane = row of the tile, one 32-bit column per k), B from shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -173,16 +217,26 @@ struct Params {
     unsigned long long *trace;  // debug: CTA 0 records clock stamps of its first tile's pipeline events (or null)
     uint32_t *rowrange;   // !D_TRANS: the same per output ROW (rows = channels in the fused loop's mid rotation)
     int conv_b;           // same for B (small problems, where a pre-split pass per GEMM would dominate)
+    int a_tmem;           // conv_a && !conv_b: the converters write the hi / lo halves of A to TENSOR memory
+    int stages_a;         // a_tmem: depth of the raw-A shared-memory ring (p.stages is the B ring then)
 };
 
 // ------------------------------------------------------------------ the kernel
 // Persistent, warp-specialised: grid = min(#tiles, #SMs); every CTA walks tiles  t = blockIdx.x, += gridDim.x.
 //   warp 0      TMA producer        raw/full barriers per smem stage (expect_tx)
-//   warp 1      MMA issuer          tcgen05.mma into one of TWO TMEM accumulators (2 x BLOCK_N columns)
-//   warps 2-5   converters (3xTF32) split the raw tiles of every stage into tf32 hi / lo halves in shared memory
-//   warps 6-9   epilogue            tcgen05.ld -> global stores of tile i while the MMA warp already runs tile i+1
-// so the prologue (barrier init, TMEM alloc) is paid once per SM and the epilogue is hidden behind the next
-// tile's main loop (the non-persistent version spent ~45 % of its time outside the MMA loop).
+//   warp 1      MMA issuer          tcgen05.mma into a TMEM accumulator
+//   warps 4-7   converters (3xTF32) split the raw A tile of every stage into tf32 hi / lo halves
+//   warps 8-23  epilogue            tcgen05.ld of the whole tile into registers, accumulator released at once, then
+//                                   the global stores run while the MMA warp is already in the next tile
+// so the prologue (barrier init, TMEM alloc) is paid once per SM and the epilogue is hidden behind the next tile's
+// main loop.  Three operand paths:
+//   terms == 1            plain TF32: raw fp32 tiles go straight from TMA to the tensor core
+//   conv_a (+ conv_b)     3xTF32, hi / lo halves written back to SHARED memory (small problems: B converted too)
+//   a_tmem                3xTF32, hi / lo halves of A written to TENSOR memory and fed to tcgen05.mma as the TMEM A
+//                         operand.  The SS form is shared-memory-bandwidth bound: per 32-wide k block of a 128 x 256
+//                         tile TMA writes 80 KB, the converters move 48 KB and the three MMAs read 144 KB = 272 KB at
+//                         128 B/clk = 2100 clk against 1536 clk of tensor-pipe time; with A in TMEM the converters
+//                         only read (16 KB) and the MMAs only fetch B (96 KB): 192 KB = 1500 clk.
 // BK = K elements per pipeline stage: 32 (128-byte swizzle rows) or 16 (64-byte rows, half-size stages).
 template <int BLOCK_N, bool A_MN, bool B_MN, bool D_TRANS, int BK>
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -191,8 +245,11 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                    const Params p) {
     constexpr uint32_t A_TILE = BLOCK_M * BK * 4;
     constexpr uint32_t B_TILE = BLOCK_N * BK * 4;
+    static_assert(BK == 32 || BK == 16, "stage depth");
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], raw_bar[MAX_STAGES];
+    __shared__ __align__(8) uint64_t afree_bar[MAX_STAGES];                            // a_tmem: raw A slot consumed
+    __shared__ __align__(8) uint64_t ta_full_bar[A_TMEM_STAGES], ta_empty_bar[A_TMEM_STAGES];  // a_tmem: TMEM A ring
     __shared__ __align__(8) uint64_t tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_smem;
 
@@ -201,14 +258,20 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[65] = clock64();
     if (p.skip && *p.skip) return;  // uniform over the grid
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool a_tmem = p.a_tmem != 0;
     const int nterm_tiles = p.terms == 3 ? 2 : 1;  // hi (+ lo) tiles per operand
-    const uint32_t stage_bytes = nterm_tiles * (A_TILE + B_TILE);
+    // a_tmem: a stage of the main ring holds the hi / lo tiles of B only; raw A tiles have their own ring behind it
+    const uint32_t stage_bytes = a_tmem ? 2 * B_TILE : nterm_tiles * (A_TILE + B_TILE);
     const int n_tiles_n = (int)((p.N + BLOCK_N - 1) / BLOCK_N);
     const int n_tiles_m = (int)((p.M + BLOCK_M - 1) / BLOCK_M);
     const int tiles_per_z = n_tiles_m * n_tiles_n;
     const int num_tiles = tiles_per_z * p.nz;
     // 1024-byte alignment of the dynamic smem base (swizzle atoms)
     uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~uintptr_t(1023));
+    uint8_t *a_ring = tiles + (size_t)p.stages * stage_bytes;
+    // a_tmem: ONE accumulator (the other 256 columns hold the A ring); the epilogue frees it as soon as the tile
+    // sits in registers.  Otherwise two accumulators alternate.
+    const uint32_t tmem_cols = a_tmem ? 512u : (uint32_t)(2 * BLOCK_N);
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA_hi);
@@ -218,9 +281,19 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
             if (!p.conv_b) prefetch_tmap(&tmB_lo);
         }
         for (int s = 0; s < p.stages; ++s) {
-            mbar_init(&full_bar[s], p.conv_a ? 4 : 1);  // conv_a: one arrival per converter warp
+            mbar_init(&full_bar[s], (p.conv_a && !a_tmem) ? 4 : 1);  // conv_a: one arrival per converter warp
             mbar_init(&empty_bar[s], 1);
             mbar_init(&raw_bar[s], 1);
+        }
+        if (a_tmem) {
+            for (int s = 0; s < p.stages_a; ++s) {
+                mbar_init(&raw_bar[s], 1);
+                mbar_init(&afree_bar[s], 4);
+            }
+            for (int s = 0; s < A_TMEM_STAGES; ++s) {
+                mbar_init(&ta_full_bar[s], 4);
+                mbar_init(&ta_empty_bar[s], 1);
+            }
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);   // tcgen05.commit of the tile's last MMA
@@ -231,7 +304,7 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                          smem_u32(&tmem_base_smem)),
-                     "r"((uint32_t)(2 * BLOCK_N))
+                     "r"(tmem_cols)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -253,104 +326,215 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         const int64_t k_len = p.k_per_z > 0 ? (p.K - k_begin < p.k_per_z ? p.K - k_begin : p.k_per_z) : p.K;
         num_kb = (int)((k_len + BK - 1) / BK);
     };
+    // which accumulator / barrier phase the i-th tile of this CTA uses
+    auto acc_of = [&](int titer, int &acc, uint32_t &aph) {
+        acc = a_tmem ? 0 : (titer & 1);
+        aph = a_tmem ? (uint32_t)(titer & 1) : (uint32_t)((titer >> 1) & 1);
+    };
 
-    if (warp == 0) {
-        // ===== TMA producer
-        if (elect_one()) {
-            int s = 0;
-            uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                int m0, n0, z, num_kb;
-                int64_t k_begin;
-                tile_coords(tile, m0, n0, z);
-                k_range(z, k_begin, num_kb);
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&empty_bar[s], ph ^ 1);
-                    if (p.trace && blockIdx.x == 0 && tile == (int)blockIdx.x && kb < 16) p.trace[kb * 4 + 0] = clock64();
-                    uint8_t *st = tiles + (size_t)s * stage_bytes;
-                    // conv_a: the raw A tile lands in the hi slot and signals the converter warps (raw_bar);
-                    // otherwise hi and lo halves of both operands arrive pre-split and signal the MMA warp directly
-                    uint64_t *bar = p.conv_a ? &raw_bar[s] : &full_bar[s];
-                    mbar_expect_tx(bar, p.conv_a ? A_TILE + (p.conv_b ? 1 : nterm_tiles) * B_TILE : stage_bytes);
-                    const int k0 = (int)k_begin + kb * BK;
-                    for (int t = 0; t < nterm_tiles; ++t) {
-                        const CUtensorMap *ma = t ? &tmA_lo : &tmA_hi;
-                        const CUtensorMap *mb = t ? &tmB_lo : &tmB_hi;
-                        uint8_t *a_dst = st + t * A_TILE;
-                        uint8_t *b_dst = st + nterm_tiles * A_TILE + t * B_TILE;
-                        if (t == 0 || !p.conv_a) {
-                            if (A_MN) tma_load_3d(ma, bar, a_dst, 0, k0, m0 / 32, p.a_hint);
-                            else tma_load_2d(ma, bar, a_dst, k0, m0, p.a_hint);
+    if (warp < 4) {
+        setmaxnreg_dec<48>();
+        if (warp == 0) {
+            // ===== TMA producer
+            if (elect_one()) {
+                int s = 0, sa = 0;
+                uint32_t ph = 0, pha = 0;
+                for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                    int m0, n0, z, num_kb;
+                    int64_t k_begin;
+                    tile_coords(tile, m0, n0, z);
+                    k_range(z, k_begin, num_kb);
+                    for (int kb = 0; kb < num_kb; ++kb) {
+                        const int k0 = (int)k_begin + kb * BK;
+                        const bool tr = p.trace && blockIdx.x == 0 && tile == (int)blockIdx.x && kb < 16;
+                        if (a_tmem) {
+                            // raw A -> its own ring (freed by the converters as soon as they have read it)
+                            mbar_wait(&afree_bar[sa], pha ^ 1);
+                            if (tr) p.trace[kb * 4 + 0] = clock64();
+                            uint8_t *a_dst = a_ring + (size_t)sa * A_TILE;
+                            mbar_expect_tx(&raw_bar[sa], A_TILE);
+                            if (A_MN) tma_load_3d(&tmA_hi, &raw_bar[sa], a_dst, 0, k0, m0 / 32, p.a_hint);
+                            else tma_load_2d(&tmA_hi, &raw_bar[sa], a_dst, k0, m0, p.a_hint);
+                            if (++sa == p.stages_a) { sa = 0; pha ^= 1; }
+                            // pre-split B hi / lo -> the main ring (freed by the MMAs)
+                            mbar_wait(&empty_bar[s], ph ^ 1);
+                            uint8_t *b_dst = tiles + (size_t)s * stage_bytes;
+                            mbar_expect_tx(&full_bar[s], 2 * B_TILE);
+                            for (int t = 0; t < 2; ++t) {
+                                const CUtensorMap *mb = t ? &tmB_lo : &tmB_hi;
+                                if (B_MN) tma_load_3d(mb, &full_bar[s], b_dst + t * B_TILE, 0, k0, n0 / 32, p.b_hint);
+                                else tma_load_2d(mb, &full_bar[s], b_dst + t * B_TILE, k0, n0, p.b_hint);
+                            }
+                            if (++s == p.stages) { s = 0; ph ^= 1; }
+                            continue;
                         }
-                        if (t == 0 || !p.conv_b) {
-                            if (B_MN) tma_load_3d(mb, bar, b_dst, 0, k0, n0 / 32, p.b_hint);
-                            else tma_load_2d(mb, bar, b_dst, k0, n0, p.b_hint);
+                        mbar_wait(&empty_bar[s], ph ^ 1);
+                        if (tr) p.trace[kb * 4 + 0] = clock64();
+                        uint8_t *st = tiles + (size_t)s * stage_bytes;
+                        // conv_a: the raw A tile lands in the hi slot and signals the converter warps (raw_bar);
+                        // otherwise hi and lo halves of both operands arrive pre-split and signal the MMA warp directly
+                        uint64_t *bar = p.conv_a ? &raw_bar[s] : &full_bar[s];
+                        mbar_expect_tx(bar, p.conv_a ? A_TILE + (p.conv_b ? 1 : nterm_tiles) * B_TILE : stage_bytes);
+                        for (int t = 0; t < nterm_tiles; ++t) {
+                            const CUtensorMap *ma = t ? &tmA_lo : &tmA_hi;
+                            const CUtensorMap *mb = t ? &tmB_lo : &tmB_hi;
+                            uint8_t *a_dst = st + t * A_TILE;
+                            uint8_t *b_dst = st + nterm_tiles * A_TILE + t * B_TILE;
+                            if (t == 0 || !p.conv_a) {
+                                if (A_MN) tma_load_3d(ma, bar, a_dst, 0, k0, m0 / 32, p.a_hint);
+                                else tma_load_2d(ma, bar, a_dst, k0, m0, p.a_hint);
+                            }
+                            if (t == 0 || !p.conv_b) {
+                                if (B_MN) tma_load_3d(mb, bar, b_dst, 0, k0, n0 / 32, p.b_hint);
+                                else tma_load_2d(mb, bar, b_dst, k0, n0, p.b_hint);
+                            }
                         }
+                        if (++s == p.stages) { s = 0; ph ^= 1; }
                     }
-                    if (++s == p.stages) { s = 0; ph ^= 1; }
                 }
             }
-        }
-    } else if (warp == 1) {
-        // ===== MMA issuer
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) |
-                               ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BLOCK_N >> 3) << 17) |
-                               ((uint32_t)(BLOCK_M >> 4) << 24);
-        int s = 0;
-        uint32_t ph = 0;
-        int titer = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++titer) {
-            int m0, n0, z, num_kb;
-            int64_t k_begin;
-            tile_coords(tile, m0, n0, z);
-            k_range(z, k_begin, num_kb);
-            const int acc = titer & 1;
-            const uint32_t aph = (titer >> 1) & 1;
-            mbar_wait(&tempty_bar[acc], aph ^ 1);  // the epilogue has drained this accumulator
-            tc_fence_after();
-            const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
-            for (int kb = 0; kb < num_kb; ++kb) {
-                mbar_wait(&full_bar[s], ph);
+        } else if (warp == 1) {
+            // ===== MMA issuer  (the TMEM A operand is always "K-major": lane = row, column = k)
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (((A_MN && !a_tmem) ? 1u : 0u) << 15) |
+                                   ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BLOCK_N >> 3) << 17) |
+                                   ((uint32_t)(BLOCK_M >> 4) << 24);
+            int s = 0, sta = 0;
+            uint32_t ph = 0, phta = 0;
+            int titer = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++titer) {
+                int m0, n0, z, num_kb, acc;
+                int64_t k_begin;
+                uint32_t aph;
+                tile_coords(tile, m0, n0, z);
+                k_range(z, k_begin, num_kb);
+                acc_of(titer, acc, aph);
+                mbar_wait(&tempty_bar[acc], aph ^ 1);  // the epilogue has drained this accumulator
                 tc_fence_after();
-                if (p.trace && blockIdx.x == 0 && tile == (int)blockIdx.x && kb < 16 && lane == 0) p.trace[kb * 4 + 3] = clock64();
-                if (p.trace && blockIdx.x == 0 && tile != (int)blockIdx.x && (kb == 0 || kb == num_kb - 1) && lane == 0) p.trace[76 + (kb ? 1 : 0)] = clock64();
-                if (elect_one()) {
-                    const uint32_t st = smem_u32(tiles + (size_t)s * stage_bytes);
-                    const uint32_t a_hi = st, a_lo = st + A_TILE;
-                    const uint32_t b_hi = st + nterm_tiles * A_TILE, b_lo = b_hi + B_TILE;
-#pragma unroll
-                    for (int kk = 0; kk < BK / UMMA_K; ++kk) {
-                        // K-major: +32 B per K step inside the swizzle row; MN-major: +8 k-rows = 1 KB
-                        const uint32_t a_off = A_MN ? kk * 1024u : kk * 32u;
-                        const uint32_t b_off = B_MN ? kk * 1024u : kk * 32u;
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[s], ph);
+                    if (a_tmem) mbar_wait(&ta_full_bar[sta], phta);
+                    tc_fence_after();
+                    if (p.trace && blockIdx.x == 0 && tile == (int)blockIdx.x && kb < 16 && lane == 0) p.trace[kb * 4 + 3] = clock64();
+                    if (p.trace && blockIdx.x == 0 && tile != (int)blockIdx.x && (kb == 0 || kb == num_kb - 1) && lane == 0) p.trace[76 + (kb ? 1 : 0)] = clock64();
+                    if (elect_one()) {
+                        const uint32_t st = smem_u32(tiles + (size_t)s * stage_bytes);
                         // MN-major: 32-wide mn blocks of BK k-rows x 128 B (LBO), 4-row BASE32B atoms (SBO 512 B)
                         // K-major : 8-row atoms of BK*4-byte rows: SWIZZLE_128B (BK = 32) or SWIZZLE_64B (BK = 16)
                         constexpr uint32_t kmaj_sbo = BK == 32 ? 1024u : 512u, kmaj_lt = BK == 32 ? 2u : 4u;
                         const uint32_t a_lbo = A_MN ? BK * 128u : 16u, b_lbo = B_MN ? BK * 128u : 16u;
                         const uint32_t a_sbo = A_MN ? 512u : kmaj_sbo, b_sbo = B_MN ? 512u : kmaj_sbo;
                         const uint32_t a_lt = A_MN ? 1u : kmaj_lt, b_lt = B_MN ? 1u : kmaj_lt;
-                        uint64_t da = make_desc(a_hi + a_off, a_lbo, a_sbo, a_lt);
-                        uint64_t db = make_desc(b_hi + b_off, b_lbo, b_sbo, b_lt);
-                        umma_tf32(tmem_d, da, db, idesc, (kb | kk) != 0);
-                        if (p.terms == 3) {
-                            uint64_t dal = make_desc(a_lo + a_off, a_lbo, a_sbo, a_lt);
-                            uint64_t dbl = make_desc(b_lo + b_off, b_lbo, b_sbo, b_lt);
-                            umma_tf32(tmem_d, da, dbl, idesc, 1u);
-                            umma_tf32(tmem_d, dal, db, idesc, 1u);
+                        if (a_tmem) {
+                            const uint32_t b_hi = st, b_lo = st + B_TILE;
+                            const uint32_t ta_hi = tmem_base + (uint32_t)(A_TMEM_COL0 + sta * 2 * BK), ta_lo = ta_hi + BK;
+#pragma unroll
+                            for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+                                const uint32_t b_off = B_MN ? kk * 1024u : kk * 32u;
+                                const uint64_t db = make_desc(b_hi + b_off, b_lbo, b_sbo, b_lt);
+                                const uint64_t dbl = make_desc(b_lo + b_off, b_lbo, b_sbo, b_lt);
+                                umma_tf32_ts(tmem_d, ta_hi + kk * UMMA_K, db, idesc, (kb | kk) != 0);
+                                umma_tf32_ts(tmem_d, ta_hi + kk * UMMA_K, dbl, idesc, 1u);
+                                umma_tf32_ts(tmem_d, ta_lo + kk * UMMA_K, db, idesc, 1u);
+                            }
+                            umma_commit(&ta_empty_bar[sta]);  // TMEM A stage free once these MMAs retire
+                        } else {
+                            const uint32_t a_hi = st, a_lo = st + A_TILE;
+                            const uint32_t b_hi = st + nterm_tiles * A_TILE, b_lo = b_hi + B_TILE;
+#pragma unroll
+                            for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+                                // K-major: +32 B per K step inside the swizzle row; MN-major: +8 k-rows = 1 KB
+                                const uint32_t a_off = A_MN ? kk * 1024u : kk * 32u;
+                                const uint32_t b_off = B_MN ? kk * 1024u : kk * 32u;
+                                uint64_t da = make_desc(a_hi + a_off, a_lbo, a_sbo, a_lt);
+                                uint64_t db = make_desc(b_hi + b_off, b_lbo, b_sbo, b_lt);
+                                umma_tf32(tmem_d, da, db, idesc, (kb | kk) != 0);
+                                if (p.terms == 3) {
+                                    uint64_t dal = make_desc(a_lo + a_off, a_lbo, a_sbo, a_lt);
+                                    uint64_t dbl = make_desc(b_lo + b_off, b_lbo, b_sbo, b_lt);
+                                    umma_tf32(tmem_d, da, dbl, idesc, 1u);
+                                    umma_tf32(tmem_d, dal, db, idesc, 1u);
+                                }
+                            }
                         }
+                        umma_commit(&empty_bar[s]);                          // smem stage free once these MMAs retire
+                        if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete
                     }
-                    umma_commit(&empty_bar[s]);                          // smem stage free once these MMAs retire
-                    if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete
+                    __syncwarp();
+                    if (++s == p.stages) { s = 0; ph ^= 1; }
+                    if (a_tmem && ++sta == A_TMEM_STAGES) { sta = 0; phta ^= 1; }
                 }
-                __syncwarp();
-                if (++s == p.stages) { s = 0; ph ^= 1; }
             }
         }
-    } else if (warp < 6) {
-        // ===== converters (3xTF32): split the raw tiles of every stage into tf32 hi / lo halves, element-wise in
-        // place (independent of the swizzle), then hand the stage to the MMA warp
-        if (p.conv_a) {
-            const int ct = threadIdx.x - 64;  // 0..127
+    } else if (warp < EPI_WARP0) {
+        setmaxnreg_dec<72>();
+        const int ct = threadIdx.x - 128;  // 0..127
+        if (a_tmem) {
+            // ===== converters, TMEM form: thread = one row of the A tile (warp w owns TMEM lanes 32*(w%4) .. +31).
+            // Read the row's BK raw values from shared memory, split, tcgen05.st the halves into the TMEM ring.
+            const int q = warp & 3;
+            const int r = q * 32 + lane;
+            int sa = 0, sta = 0;
+            uint32_t pha = 0, phta = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                int m0, n0, z, num_kb;
+                int64_t k_begin;
+                tile_coords(tile, m0, n0, z);
+                k_range(z, k_begin, num_kb);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    const bool tr = p.trace && blockIdx.x == 0 && tile == (int)blockIdx.x && kb < 16 && ct == 0;
+                    mbar_wait(&raw_bar[sa], pha);
+                    if (tr) p.trace[kb * 4 + 1] = clock64();
+                    const uint8_t *raw = a_ring + (size_t)sa * A_TILE;
+                    float v[BK];
+                    if (A_MN) {
+                        // [mn block q][k][32 mn]: 128-byte k rows, 32-byte chunks XOR-ed with (k & 3)
+                        const uint8_t *blk = raw + (size_t)q * (BK * 128);
+#pragma unroll
+                        for (int k = 0; k < BK; ++k)
+                            v[k] = *reinterpret_cast<const float *>(blk + k * 128 + ((((lane >> 3) ^ (k & 3)) << 5) |
+                                                                                 ((lane & 7) << 2)));
+                    } else {
+                        // [row][BK k]: 16-byte chunks XOR-ed with the row index inside the 8-row swizzle atom
+                        const uint8_t *rowp = raw + (size_t)r * (BK * 4);
+                        const int sw = BK == 32 ? (r & 7) : ((r >> 1) & 3);
+#pragma unroll
+                        for (int c = 0; c < BK / 4; ++c) {
+                            const float4 t = *reinterpret_cast<const float4 *>(rowp + ((c ^ sw) << 4));
+                            v[c * 4 + 0] = t.x; v[c * 4 + 1] = t.y; v[c * 4 + 2] = t.z; v[c * 4 + 3] = t.w;
+                        }
+                    }
+                    // the values are in registers: hand the raw slot back to the producer
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&afree_bar[sa]);
+                    if (++sa == p.stages_a) { sa = 0; pha ^= 1; }
+                    mbar_wait(&ta_empty_bar[sta], phta ^ 1);
+                    tc_fence_after();
+                    const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(A_TMEM_COL0 + sta * 2 * BK);
+#pragma unroll
+                    for (int h = 0; h < BK / 16; ++h) {
+                        uint32_t hi[16], lo[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            float fh, fl;
+                            split_tf32(v[h * 16 + j], fh, fl);
+                            hi[j] = __float_as_uint(fh);
+                            lo[j] = __float_as_uint(fl);
+                        }
+                        tmem_st16(ta + h * 16, hi);
+                        tmem_st16(ta + BK + h * 16, lo);
+                    }
+                    tmem_wait_st();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&ta_full_bar[sta]);
+                    if (tr) p.trace[kb * 4 + 2] = clock64();
+                    if (++sta == A_TMEM_STAGES) { sta = 0; phta ^= 1; }
+                }
+            }
+        } else if (p.conv_a) {
+            // ===== converters, shared-memory form: split the raw tiles of every stage into tf32 hi / lo halves,
+            // element-wise in place (independent of the swizzle), then hand the stage to the MMA warp
             int s = 0;
             uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -389,36 +573,50 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> UMMA reads
                     __syncwarp();
-                    if (lane == 0)
-                        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full_bar[s]))
-                                     : "memory");
+                    if (lane == 0) mbar_arrive(&full_bar[s]);
                     if (p.trace && blockIdx.x == 0 && tile == (int)blockIdx.x && kb < 16 && ct == 0) p.trace[kb * 4 + 2] = clock64();
                     if (++s == p.stages) { s = 0; ph ^= 1; }
                 }
             }
         }
     } else {
+        setmaxnreg_inc<88>();  // pool = 768 x 80 allocated at launch: 128 x 48 + 128 x 72 + 512 x 88 <= 61440
         // ===== epilogue: warp w may touch TMEM lanes 32*(w%4) .. +31
         const int q = warp & 3;
-        const int egrp = (warp - 6) >> 2;                     // which column slice of the tile this warp drains
+        const int egrp = (warp - EPI_WARP0) >> 2;             // which column slice of the tile this warp drains
         constexpr int EPI_COLS = BLOCK_N / EPI_GROUPS < 32 ? 32 : BLOCK_N / EPI_GROUPS;
+        constexpr int NCH = EPI_COLS / 32;
+        const bool active = egrp * EPI_COLS < BLOCK_N;
         int titer = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++titer) {
-            int m0, n0, z;
+            int m0, n0, z, acc;
+            uint32_t aph;
             tile_coords(tile, m0, n0, z);
-            const int acc = titer & 1;
-            const uint32_t aph = (titer >> 1) & 1;
+            acc_of(titer, acc, aph);
             float *const Dz = p.D + (int64_t)z * p.d_z_stride;
             mbar_wait(&tfull_bar[acc], aph);
             tc_fence_after();
-            if (p.trace && blockIdx.x == 0 && warp == 6 && lane == 0 && titer < 4) p.trace[68 + titer * 2] = clock64();
+            if (p.trace && blockIdx.x == 0 && warp == EPI_WARP0 && lane == 0 && titer < 4) p.trace[68 + titer * 2] = clock64();
+            // the warp's whole slice of the tile -> registers, then the accumulator goes back to the MMA warp
+            uint32_t vv[NCH][32];
+            if (active) {
+#pragma unroll
+                for (int ch = 0; ch < NCH; ++ch)
+                    tmem_ld32_nowait(tmem_base + ((uint32_t)(q * 32) << 16) +
+                                         (uint32_t)(acc * BLOCK_N + egrp * EPI_COLS + ch * 32), vv[ch]);
+                tmem_wait_ld();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (p.trace && blockIdx.x == 0 && warp == EPI_WARP0 && lane == 0 && titer < 4) p.trace[69 + titer * 2] = clock64();
             const int64_t row = (int64_t)m0 + q * 32 + lane;
             uint32_t rmn = 0xffffffffu, rmx = 0xffffffffu;  // this thread's row: f2ord(min), ~f2ord(max)
-#pragma unroll 1
-            for (int col = egrp * EPI_COLS; col < (egrp + 1) * EPI_COLS && col < BLOCK_N; col += 32) {
-                if (n0 + col >= p.N) break;
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + col), v);
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) {
+                const int col = egrp * EPI_COLS + ch * 32;
+                if (!active || n0 + col >= p.N) break;
+                uint32_t (&v)[32] = vv[ch];
                 if (D_TRANS) {
                     if (row < p.M) {
 #pragma unroll
@@ -496,12 +694,6 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                 atomicMin(p.rowrange + 2 * row, rmn);
                 atomicMin(p.rowrange + 2 * row + 1, rmx);
             }
-            // all of this warp's TMEM reads have completed (tcgen05.wait::ld in tmem_ld32): release the accumulator
-            tc_fence_before();
-            __syncwarp();
-            if (p.trace && blockIdx.x == 0 && warp == 6 && lane == 0 && titer < 4) p.trace[69 + titer * 2] = clock64();
-            if (lane == 0)
-                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tempty_bar[acc])) : "memory");
         }
     }
     tc_fence_before();
@@ -509,8 +701,7 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[67] = clock64();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                     "r"((uint32_t)(2 * BLOCK_N))
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols)
                      : "memory");
     }
 }
@@ -645,11 +836,24 @@ int split(const float *x, float *hi, float *lo, int64_t n, cudaStream_t st) {
 template <int BLOCK_N, bool A_MN, bool B_MN, bool D_TRANS, int BK>
 int launch(const CUtensorMap &ah, const CUtensorMap &al, const CUtensorMap &bh, const CUtensorMap &bl, Params p,
            int nz, cudaStream_t st) {
-    const uint32_t stage_bytes = (p.terms == 3 ? 2 : 1) * (BLOCK_M * BK * 4 + BLOCK_N * BK * 4);
-    int stages = SMEM_BUDGET / (int)stage_bytes;
-    if (stages > MAX_STAGES) stages = MAX_STAGES;
-    p.stages = stages;
-    size_t smem = (size_t)stages * stage_bytes + 1024;
+    constexpr int A_TILE = BLOCK_M * BK * 4, B_TILE = BLOCK_N * BK * 4;
+    size_t smem;
+    if (p.a_tmem) {
+        // main ring: hi + lo tiles of B; the rest of shared memory: raw A tiles (at least 4 in flight)
+        int stages = (SMEM_BUDGET - 4 * A_TILE) / (2 * B_TILE);
+        if (stages > MAX_STAGES) stages = MAX_STAGES;
+        int stages_a = (SMEM_BUDGET - stages * 2 * B_TILE) / A_TILE;
+        if (stages_a > MAX_STAGES) stages_a = MAX_STAGES;
+        p.stages = stages;
+        p.stages_a = stages_a;
+        smem = (size_t)stages * 2 * B_TILE + (size_t)stages_a * A_TILE + 1024;
+    } else {
+        const uint32_t stage_bytes = (p.terms == 3 ? 2 : 1) * (A_TILE + B_TILE);
+        int stages = SMEM_BUDGET / (int)stage_bytes;
+        if (stages > MAX_STAGES) stages = MAX_STAGES;
+        p.stages = stages;
+        smem = (size_t)stages * stage_bytes + 1024;
+    }
     auto kern = rotate_gemm_kernel<BLOCK_N, A_MN, B_MN, D_TRANS, BK>;
     static bool attr_done = false;
     if (!attr_done) {
@@ -779,6 +983,8 @@ int gemm_tc(const TcGemm &g, cudaStream_t st) {
     p.k_per_z = k_per_z; p.d_z_stride = g.d_z_stride;
     p.bias = g.bias; p.bias_hw = g.bias_hw > 0 ? g.bias_hw : 1; p.bias_ld = g.bias_ld;
     p.alpha = g.alpha; p.skip = g.skip; p.conv_a = p.terms == 3 ? 1 : 0; p.conv_b = conv_b ? 1 : 0;
+    static const char *no_atmem = getenv("OPTEX_NO_A_TMEM");
+    p.a_tmem = (p.conv_a && !p.conv_b && !(no_atmem && atoi(no_atmem))) ? 1 : 0;
     p.nz = nz;
     p.colrange = g.d_trans ? g.colrange : nullptr;
     p.rowrange = g.d_trans ? nullptr : g.rowrange;

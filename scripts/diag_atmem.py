@@ -1,0 +1,34 @@
+"""A-via-TMEM 3xTF32 GEMM: accuracy against fp64 and hot timing (forward transposed, inverse from channel-major)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import optimaltextures_b200 as ob
+from optimaltextures_b200._runtime import call, ptr, stream_ptr
+dev = torch.device("cuda", 0)
+torch.manual_seed(0)
+mode = sys.argv[1] if len(sys.argv) > 1 else "auto"
+ob.set_gemm_mode(mode)
+for (n, c) in [(16384, 512), (16384 + 96, 256), (65536, 128), (8192, 512)]:
+    x = torch.randn(n, c, device=dev) * 3 + 1
+    r = ob.random_rotation(c, device=dev)
+    out = torch.full((c, n), 7.0, device=dev)
+    call("optex_rotate_forward", ptr(x), ptr(r), ptr(out), n, c, stream_ptr(dev))
+    torch.cuda.synchronize()
+    ref = (x.double() @ r.double()).T
+    print(f"fwd n={n} c={c}: err={float((out - ref).abs().max()):.3e} sevens={int((out == 7).sum())}", flush=True)
+    o2 = torch.full((n, c), 7.0, device=dev)
+    call("optex_rotate_inverse", ptr(out), ptr(r), ptr(o2), n, c, None, 0.0, stream_ptr(dev))
+    torch.cuda.synchronize()
+    ref2 = out.double().T @ r.double().T
+    print(f"inv n={n} c={c}: err={float((o2 - ref2).abs().max()):.3e} roundtrip={float((o2 - x).abs().max()):.3e}", flush=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for name, fn in (("fwd", lambda: call("optex_rotate_forward", ptr(x), ptr(r), ptr(out), n, c, stream_ptr(dev))),
+                     ("inv", lambda: call("optex_rotate_inverse", ptr(out), ptr(r), ptr(o2), n, c, None, 0.0, stream_ptr(dev)))):
+        for _ in range(5):
+            fn()
+        e0.record()
+        for _ in range(50):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"  {name} hot {e0.elapsed_time(e1) / 50 * 1e3:.1f} us", flush=True)
