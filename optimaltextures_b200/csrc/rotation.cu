@@ -8,11 +8,11 @@
 // Parity: distributional only (the reference draws from numpy's global RNG); with the
 // normals injected (`gauss`) it matches oracle/rotation.py::haar_rotation_householder.
 //
-// Two kernels for a whole BATCH of rotations (one per OT iteration of a layer):
-//   rot_vectors : one warp per reflection n - normals -> normalised Householder vector v_n
-//   rot_apply   : one warp per row of H - the row stays in registers while the c-1
-//                 reflections H[i, n:] -= (H[i, n:] . v_n) v_n are applied in sequence
-//                 (rows are independent, so no inter-CTA synchronisation is needed).
+// Three kernels for a whole BATCH of rotations (one per OT iteration of a layer):
+//   rot_vectors : one warp per reflection n - normals -> normalised Householder vector v_n (zero-padded rows)
+//   rot_gram    : one warp per block of NB consecutive reflections - the NB(NB-1)/2 products v_a . v_b
+//   rot_apply   : a warp keeps RW rows of H in registers and applies the reflections NB at a time in compact-WY
+//                 form (rows are independent, so no inter-CTA synchronisation is needed).
 #include "common.cuh"
 
 namespace optex {
@@ -50,14 +50,26 @@ __device__ __forceinline__ double philox_normal(uint64_t seed, uint64_t counter,
     return (k & 1) ? r * s : r * co;
 }
 
+constexpr int NB = 4;  // reflections per compact-WY block (divides 32, so a block never straddles a 32-column chunk)
+
+// columns of the zero-padded V rows = the width PL * 32 of the rot_apply instantiation that serves c
+__host__ __device__ inline int padded_cols(int c) { return c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : c <= 512 ? 512 : 1024; }
+__host__ __device__ inline int padded_rows(int c) { return (c - 1 + NB - 1) / NB * NB + NB; }
+
 // v[b][n][k] (k >= n; zero for k < n) and signs d[b][n]     optex.py:154-160
+// V is stored zero-padded, [b][padded_rows(c)][padded_cols(c)], so that rot_apply needs no bounds checks.
 __global__ void rot_vectors_kernel(double *__restrict__ V, double *__restrict__ D, int c, uint64_t seed,
                                    uint64_t first_counter, const double *__restrict__ gauss) {
     const int lane = threadIdx.x & 31;
     const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int b = blockIdx.y;
-    if (n >= c - 1) return;
-    double *v = V + ((int64_t)b * (c - 1) + n) * c;
+    const int cp = padded_cols(c), rp = padded_rows(c);
+    if (n >= rp) return;
+    double *v = V + ((int64_t)b * rp + n) * cp;
+    if (n >= c - 1) {  // padding rows: reflections that do not exist
+        for (int k = lane; k < cp; k += 32) v[k] = 0.0;
+        return;
+    }
     double x[PER_LANE];
     double norm2 = 0.0;
 #pragma unroll
@@ -84,72 +96,231 @@ __global__ void rot_vectors_kernel(double *__restrict__ V, double *__restrict__ 
 #pragma unroll
     for (int i = 0; i < PER_LANE; ++i) {
         int k = i * 32 + lane;
-        if (k < c) v[k] = (k == n ? x0n : x[i]) * scale;
+        if (k < cp) v[k] = (k == n ? x0n : x[i]) * scale;   // x is zero outside [n, c)
     }
     if (lane == 0) D[(int64_t)b * c + n] = dn;
 }
 
-// R[b][i][:] = D[i] * (e_i * prod_n (I - v_n v_n^T))        optex.py:153,161-163
-template <int PL>
-__global__ void __launch_bounds__(128)
-rot_apply_kernel(const double *__restrict__ V, const double *__restrict__ D, float *__restrict__ R, int c) {
+// G[b][block][a * NB + a2] = v_{n0+a} . v_{n0+a2}  (a < a2) for every block of NB consecutive reflections
+__global__ void rot_gram_kernel(const double *__restrict__ V, double *__restrict__ G, int c) {
     const int lane = threadIdx.x & 31;
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int cp = padded_cols(c), rp = padded_rows(c);
+    const int blk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int b = blockIdx.y;
-    if (row >= c) return;
-    const double *Vb = V + (int64_t)b * (c - 1) * c;
-    double h[PL];
+    if (blk >= rp / NB) return;
+    const double *v = V + ((int64_t)b * rp + (int64_t)blk * NB) * cp;
+    double g[NB * NB];
 #pragma unroll
-    for (int i = 0; i < PL; ++i) h[i] = (i * 32 + lane == row) ? 1.0 : 0.0;
-    double vn[PL], vnext[PL];
+    for (int j = 0; j < NB * NB; ++j) g[j] = 0.0;
+    for (int k = lane; k < cp; k += 32) {
+        double va[NB];
 #pragma unroll
-    for (int i = 0; i < PL; ++i) {
-        int k = i * 32 + lane;
-        vnext[i] = (c > 1 && k < c) ? Vb[k] : 0.0;
+        for (int a = 0; a < NB; ++a) va[a] = v[(int64_t)a * cp + k];
+#pragma unroll
+        for (int a = 0; a < NB; ++a)
+#pragma unroll
+            for (int a2 = a + 1; a2 < NB; ++a2) g[a * NB + a2] = fma(va[a], va[a2], g[a * NB + a2]);
     }
-    for (int n = 0; n < c - 1; ++n) {
 #pragma unroll
-        for (int i = 0; i < PL; ++i) vn[i] = vnext[i];
-        if (n + 1 < c - 1) {
-            const double *vp = Vb + (int64_t)(n + 1) * c;
+    for (int a = 0; a < NB; ++a)
 #pragma unroll
-            for (int i = 0; i < PL; ++i) {
-                int k = i * 32 + lane;
-                vnext[i] = k < c ? vp[k] : 0.0;
+        for (int a2 = a + 1; a2 < NB; ++a2) {
+            const double t = warp_sum(g[a * NB + a2]);
+            if (lane == 0) G[((int64_t)b * (rp / NB) + blk) * (NB * NB) + a * NB + a2] = t;
+        }
+}
+
+// R[b][i][:] = D[i] * (e_i * prod_n (I - v_n v_n^T))        optex.py:153,161-163
+// A warp keeps RW rows of H in registers and streams the reflections past them NB at a time.  For a block
+// v_0..v_{NB-1} and a row h:   d_a = h . v_a  (all NB dot products of the UNMODIFIED row, one combined reduction),
+//   t_0 = d_0,  t_a = d_a - sum_{a' < a} t_a' (v_a' . v_a)      (what the sequential reflections would have seen)
+//   h  -= sum_a t_a v_a
+// i.e. NB times fewer latency-bound reduction chains than reflection-by-reflection, v fetched once per RW rows
+// (one row per warp was bound by L1 bandwidth), and since v_n is zero below k = n the 32-column chunks left of the
+// block are skipped (the phase loop is unrolled, so the chunk loops have constant bounds) - half of the FP64 work.
+constexpr int ROT_STAGES = 4;  // shared-memory ring of v blocks (cp.async)
+
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// first 32-column chunk that block j of NB reflections can touch, rounded down to the phase granularity PS
+template <int PS>
+__device__ __forceinline__ int block_chunk0(int j) { return ((j * NB) >> 5) / PS * PS; }
+
+// stage block j (rows j*NB .. +NB-1 of V, columns from its phase's first chunk on) into ring slot j % ROT_STAGES
+template <int PL, int PS>
+__device__ __forceinline__ void rot_fetch(double *ring, const double *__restrict__ Vg, int j, int nblk, int tid) {
+    constexpr int cp = PL * 32;
+    if (j < nblk) {
+        const int col0 = block_chunk0<PS>(j) * 32;
+        const int per_row = (cp - col0) >> 1;  // 16-byte pieces per row
+        double *dst = ring + (size_t)(j % ROT_STAGES) * NB * cp;
+        const double *src = Vg + (int64_t)j * NB * cp;
+#pragma unroll
+        for (int a = 0; a < NB; ++a)
+            for (int q = tid; q < per_row; q += 128) cp_async16(dst + a * cp + col0 + 2 * q, src + a * cp + col0 + 2 * q);
+    }
+    cp_async_commit();  // one group per block index, empty or not, so that wait_group counts stay uniform
+}
+
+// The reflections whose first column lies in chunks [I0, I0 + PS) of 32 columns, NB at a time; the chunk loops
+// start at the CONSTANT I0 (v_n is zero left of n) and carry no bounds checks (V is zero-padded to PL * 32 columns),
+// so they are straight-line code.  PS trades skipped work for code size: one loop body per phase.
+template <int PL, int RW, int PS, int I0>
+__device__ __forceinline__ void rot_phase(double (&h)[RW][PL], double *ring, const double *__restrict__ Vg,
+                                          const double *__restrict__ Gb, int c, int nblk, int lane, int tid) {
+    if constexpr (I0 < PL) {
+        constexpr int cp = PL * 32;
+        if (I0 * 32 >= c - 1) return;
+        for (int n0 = I0 * 32; n0 < (I0 + PS) * 32 && n0 < c - 1; n0 += NB) {
+            const int j = n0 / NB;
+            // v_a . v_a' of this block (needed only after the reduction: the latency hides behind the dot pass)
+            const double *g = Gb + (int64_t)j * (NB * NB);
+            double gv[NB * NB];
+#pragma unroll
+            for (int a = 1; a < NB; ++a)
+#pragma unroll
+                for (int a2 = 0; a2 < a; ++a2) gv[a2 * NB + a] = __ldg(g + a2 * NB + a);
+            cp_async_wait<ROT_STAGES - 2>();   // block j has landed (this thread's copies) ...
+            __syncthreads();                   // ... and everybody's; everybody is also done with block j - 1
+            rot_fetch<PL, PS>(ring, Vg, j + ROT_STAGES - 1, nblk, tid);
+            const double *vb = ring + (size_t)(j % ROT_STAGES) * NB * cp + lane;
+            constexpr int NV = RW * NB;
+            double d[NV];  // d[r * NB + a]
+#pragma unroll
+            for (int q = 0; q < NV; ++q) d[q] = 0.0;
+#pragma unroll
+            for (int i = I0; i < PL; ++i) {
+                // keep at most two chunks of v loads in flight (unrestrained hoisting spills the h registers)
+                if (((i - I0) & 1) == 0) asm volatile("" ::: "memory");
+                double va[NB];
+#pragma unroll
+                for (int a = 0; a < NB; ++a) va[a] = vb[a * cp + i * 32];
+#pragma unroll
+                for (int r = 0; r < RW; ++r)
+#pragma unroll
+                    for (int a = 0; a < NB; ++a) d[r * NB + a] = fma(h[r][i], va[a], d[r * NB + a]);
+            }
+            // transpose-reduce: halve the number of live values at every butterfly level; value q ends up (summed
+            // over the warp) in the lanes with  lane * NV / 32 == q
+#pragma unroll
+            for (int w = NV / 2, o = 16; w >= 1; w >>= 1, o >>= 1) {
+                const bool up = (lane & o) != 0;
+#pragma unroll
+                for (int q = 0; q < w; ++q) {
+                    const double send = up ? d[q] : d[q + w];
+                    const double keep = up ? d[q + w] : d[q];
+                    d[q] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                }
+            }
+#pragma unroll
+            for (int o = 16 / NV; o >= 1; o >>= 1) d[0] += __shfl_xor_sync(0xffffffffu, d[0], o);
+            const double mine = d[0];
+            double t[NV];
+#pragma unroll
+            for (int q = 0; q < NV; ++q) t[q] = __shfl_sync(0xffffffffu, mine, q * (32 / NV));
+            // what the sequential reflections would have seen
+#pragma unroll
+            for (int a = 1; a < NB; ++a)
+#pragma unroll
+                for (int a2 = 0; a2 < a; ++a2)
+#pragma unroll
+                    for (int r = 0; r < RW; ++r) t[r * NB + a] = fma(-t[r * NB + a2], gv[a2 * NB + a], t[r * NB + a]);
+#pragma unroll
+            for (int i = I0; i < PL; ++i) {
+                // keep at most two chunks of v loads in flight (unrestrained hoisting spills the h registers)
+                if (((i - I0) & 1) == 0) asm volatile("" ::: "memory");
+                double va[NB];
+#pragma unroll
+                for (int a = 0; a < NB; ++a) va[a] = vb[a * cp + i * 32];
+#pragma unroll
+                for (int r = 0; r < RW; ++r)
+#pragma unroll
+                    for (int a = 0; a < NB; ++a) h[r][i] = fma(-t[r * NB + a], va[a], h[r][i]);
             }
         }
-        double dot = 0.0;
-#pragma unroll
-        for (int i = 0; i < PL; ++i) dot = fma(h[i], vn[i], dot);
-        dot = warp_sum(dot);
-#pragma unroll
-        for (int i = 0; i < PL; ++i) h[i] = fma(-dot, vn[i], h[i]);
+        rot_phase<PL, RW, PS, I0 + PS>(h, ring, Vg, Gb, c, nblk, lane, tid);
     }
+}
+
+template <int PL>
+struct RotCfg {
+    static constexpr int PS = PL >= 16 ? PL / 4 : (PL >= 4 ? PL / 2 : PL);
+    static constexpr size_t SMEM = (size_t)ROT_STAGES * NB * PL * 32 * sizeof(double);
+};
+
+template <int PL, int RW>
+__global__ void __launch_bounds__(128)
+rot_apply_kernel(const double *__restrict__ V, const double *__restrict__ G, const double *__restrict__ D,
+                 float *__restrict__ R, int c) {
+    static_assert(RW * NB == 16 || RW * NB == 8 || RW * NB == 4, "the transpose-reduce wants a power of two <= 16");
+    extern __shared__ __align__(16) double rot_ring[];
+    const int tid = threadIdx.x, lane = tid & 31;
+    // no early exit: every warp of the CTA takes part in the cp.async ring and its barriers (rows >= c are not stored)
+    const int row0 = (blockIdx.x * (blockDim.x >> 5) + (tid >> 5)) * RW;
+    const int b = blockIdx.y;
+    constexpr int cp = PL * 32;
+    constexpr int PS = RotCfg<PL>::PS;
+    const int rp = padded_rows(c);
+    const int nblk = (c - 1 + NB - 1) / NB;
+    const double *Vg = V + (int64_t)b * rp * cp;
+    const double *Gb = G + (int64_t)b * (rp / NB) * (NB * NB);
+    double h[RW][PL];
+#pragma unroll
+    for (int r = 0; r < RW; ++r)
+#pragma unroll
+        for (int i = 0; i < PL; ++i) h[r][i] = (i * 32 + lane == row0 + r) ? 1.0 : 0.0;
+#pragma unroll
+    for (int j = 0; j < ROT_STAGES - 1; ++j) rot_fetch<PL, PS>(rot_ring, Vg, j, nblk, tid);
+    rot_phase<PL, RW, PS, 0>(h, rot_ring, Vg, Gb, c, nblk, lane, tid);
+    cp_async_wait<0>();
     // D[-1] = (-1)^(c-1) * prod(D[:-1])                     optex.py:162
-    double d;
-    if (row < c - 1) {
-        d = D[(int64_t)b * c + row];
-    } else {
-        double p = 1.0;
-        for (int k = lane; k < c - 1; k += 32) p *= D[(int64_t)b * c + k];
+    double plast = 1.0;
+    if (row0 + RW > c - 1) {
+        for (int k = lane; k < c - 1; k += 32) plast *= D[(int64_t)b * c + k];
 #pragma unroll
-        for (int o = 16; o; o >>= 1) p *= __shfl_xor_sync(0xffffffffu, p, o);
-        d = ((c - 1) & 1) ? -p : p;
+        for (int o = 16; o; o >>= 1) plast *= __shfl_xor_sync(0xffffffffu, plast, o);
+        plast = ((c - 1) & 1) ? -plast : plast;
     }
-    float *out = R + ((int64_t)b * c + row) * c;
 #pragma unroll
-    for (int i = 0; i < PL; ++i) {
-        int k = i * 32 + lane;
-        if (k < c) out[k] = (float)(d * h[i]);
+    for (int r = 0; r < RW; ++r) {
+        const int row = row0 + r;
+        if (row >= c) break;
+        const double dd = row < c - 1 ? D[(int64_t)b * c + row] : plast;
+        float *out = R + ((int64_t)b * c + row) * c;
+#pragma unroll
+        for (int i = 0; i < PL; ++i) {
+            const int k = i * 32 + lane;
+            if (k < c) out[k] = (float)(dd * h[r][i]);
+        }
     }
+}
+
+template <int PL, int RW>
+int launch_rot_apply(const double *V, const double *G, const double *D, float *R, int c, int batch, cudaStream_t st) {
+    auto kern = rot_apply_kernel<PL, RW>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        OPTEX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RotCfg<PL>::SMEM));
+        attr_done = true;
+    }
+    dim3 g((unsigned)((c + 4 * RW - 1) / (4 * RW)), (unsigned)batch);
+    kern<<<g, 128, RotCfg<PL>::SMEM, st>>>(V, G, D, R, c);
+    return OPTEX_OK;
 }
 
 }  // namespace
 
 size_t rotation_ws_bytes(int c, int batch) {
     if (c <= 0 || batch <= 0) return 0;
-    return align_up(sizeof(double) * (size_t)batch * (c > 1 ? c - 1 : 1) * c, 256) +
-           align_up(sizeof(double) * (size_t)batch * c, 256);
+    const size_t rp = padded_rows(c), cp = padded_cols(c);
+    return align_up(sizeof(double) * (size_t)batch * rp * cp, 256) + align_up(sizeof(double) * (size_t)batch * c, 256) +
+           align_up(sizeof(double) * (size_t)batch * (rp / NB) * NB * NB, 256);
 }
 
 int random_rotations(float *R, int c, int batch, uint64_t seed, uint64_t first_counter, const double *gauss,
@@ -166,25 +337,40 @@ int random_rotations(float *R, int c, int batch, uint64_t seed, uint64_t first_c
         set_error("random_rotation: batch > 65535");
         return OPTEX_ESIZE;
     }
+    const int rp = padded_rows(c), cp = padded_cols(c);
     Arena ar(workspace, workspace_bytes);
-    double *V = ar.take<double>((size_t)batch * (c > 1 ? c - 1 : 1) * c);
+    double *V = ar.take<double>((size_t)batch * rp * cp);
     double *D = ar.take<double>((size_t)batch * c);
+    double *G = ar.take<double>((size_t)batch * (rp / NB) * NB * NB);
     if (!ar.ok()) {
         set_error("random_rotation: workspace %zu < %zu", workspace_bytes, rotation_ws_bytes(c, batch));
         return OPTEX_EWORKSPACE;
     }
-    if (c > 1) {
-        dim3 g1((unsigned)((c - 1 + 3) / 4), (unsigned)batch);
+    {
+        dim3 g1((unsigned)((rp + 3) / 4), (unsigned)batch);
         rot_vectors_kernel<<<g1, 128, 0, st>>>(V, D, c, seed, first_counter, gauss);
         OPTEX_LAUNCH_CHECK("rot_vectors_kernel");
+        dim3 g3((unsigned)((rp / NB + 3) / 4), (unsigned)batch);
+        rot_gram_kernel<<<g3, 128, 0, st>>>(V, G, c);
+        OPTEX_LAUNCH_CHECK("rot_gram_kernel");
     }
-    dim3 g2((unsigned)((c + 3) / 4), (unsigned)batch);
-    int pl = (c + 31) / 32;
-    if (pl <= 2) rot_apply_kernel<2><<<g2, 128, 0, st>>>(V, D, R, c);
-    else if (pl <= 4) rot_apply_kernel<4><<<g2, 128, 0, st>>>(V, D, R, c);
-    else if (pl <= 8) rot_apply_kernel<8><<<g2, 128, 0, st>>>(V, D, R, c);
-    else if (pl <= 16) rot_apply_kernel<16><<<g2, 128, 0, st>>>(V, D, R, c);
-    else rot_apply_kernel<32><<<g2, 128, 0, st>>>(V, D, R, c);
+    const int pl = (c + 31) / 32;
+    // rows per warp: as many as the register file takes next to the two v_n buffers
+    // rows per warp: 4 amortise the v fetches best, fewer put a small batch on more SMs (latency of a single draw)
+    const int64_t want = sm_count();
+    const int rw = (int64_t)((c + 15) / 16) * batch >= want ? 4 : ((int64_t)((c + 7) / 8) * batch >= want ? 2 : 1);
+#define OPTEX_ROT(PL_)                                                                         \
+    do {                                                                                       \
+        if (rw == 4 && PL_ <= 16) OPTEX_TRY((launch_rot_apply<PL_, (PL_ <= 16 ? 4 : 2)>(V, G, D, R, c, batch, st))); \
+        else if (rw >= 2) OPTEX_TRY((launch_rot_apply<PL_, 2>(V, G, D, R, c, batch, st)));     \
+        else OPTEX_TRY((launch_rot_apply<PL_, 1>(V, G, D, R, c, batch, st)));                  \
+    } while (0)
+    if (pl <= 2) OPTEX_ROT(2);
+    else if (pl <= 4) OPTEX_ROT(4);
+    else if (pl <= 8) OPTEX_ROT(8);
+    else if (pl <= 16) OPTEX_ROT(16);
+    else OPTEX_ROT(32);
+#undef OPTEX_ROT
     OPTEX_LAUNCH_CHECK("rot_apply_kernel");
     return OPTEX_OK;
 }

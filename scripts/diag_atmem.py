@@ -32,3 +32,21 @@ for (n, c) in [(16384, 512), (16384 + 96, 256), (65536, 128), (8192, 512)]:
         e1.record()
         torch.cuda.synchronize()
         print(f"  {name} hot {e0.elapsed_time(e1) / 50 * 1e3:.1f} us", flush=True)
+
+# cold inputs: cycle over 8 distinct A operands (8 x 32 MB > L2) at the headline shape
+n, c = 16384, 512
+xs = [torch.randn(n, c, device=dev) for _ in range(8)]
+outs = [torch.empty(c, n, device=dev) for _ in range(8)]
+o2s = [torch.empty(n, c, device=dev) for _ in range(2)]
+r = ob.random_rotation(c, device=dev)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+for name, fn in (("fwd", lambda i: call("optex_rotate_forward", ptr(xs[i % 8]), ptr(r), ptr(outs[i % 8]), n, c, stream_ptr(dev))),
+                 ("inv", lambda i: call("optex_rotate_inverse", ptr(outs[i % 8]), ptr(r), ptr(o2s[i % 2]), n, c, None, 0.0, stream_ptr(dev)))):
+    for i in range(8):
+        fn(i)
+    e0.record()
+    for i in range(48):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"  {name} cold (8 operand sets) {e0.elapsed_time(e1) / 48 * 1e3:.1f} us", flush=True)
