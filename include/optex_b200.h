@@ -68,6 +68,12 @@ int optex_get_gemm_mode(void);
 /* Programmatic dependent launch between the library's kernels (default on).  Turn it off to time individual
  * kernels with CUDA events: under PDL a kernel may start before its predecessor has drained. */
 int optex_set_pdl(int enable);
+/* Arithmetic of the Householder construction behind optex_random_rotation(s): 1 = fp64 (default; what the
+ * reference's live scipy branch computes in before `.to(pastiche_feature)`, optex.py:147,168), 0 = fp32 (what its
+ * impl="torch" branch computes in, optex.py:150-164; 2x faster, |R R^T - I| ~ 1e-6 instead of 1e-8 at c = 512).
+ * Returns the previous setting. */
+int optex_set_rotation_precision(int fp64);
+int optex_get_rotation_precision(void);
 /* Debug aid: CTA 0 of every following rotation GEMM writes 64 clock64() stamps (16 k-blocks x {TMA issue, tile
  * landed, hi/lo split done, MMA start}) of its first tile into device_buf (NULL = off). */
 int optex_debug_gemm_trace(void *device_buf);

@@ -31,6 +31,8 @@ SIGNATURES = {
     "optex_set_gemm_mode": (_i, [_i]),
     "optex_get_gemm_mode": (_i, []),
     "optex_set_pdl": (_i, [_i]),
+    "optex_set_rotation_precision": (_i, [_i]),
+    "optex_get_rotation_precision": (_i, []),
     "optex_debug_gemm_trace": (_i, [_p]),
     "optex_ot_workspace_bytes": (_z, [_l, _l, _i, _i]),
     "optex_ot_step": (_i, [_p, _p, _p, _p, _i, _l, _i, _l, _i, _i, _f, _p, _f, _p, _z, _p]),

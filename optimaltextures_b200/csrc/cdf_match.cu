@@ -165,11 +165,16 @@ cdf_range_kernel(const float *__restrict__ t, const float *__restrict__ s, int64
 // conflicts, no atomics); after at most 252 elements per thread the counters are folded into `acc` with packed
 // 16-bit adds.  NTH is small (128) on purpose: the fold costs ~bins/4 words per thread, so a thread must count a
 // few hundred elements per fold for it to amortise (N = 16384 per channel at conv4_1 1024^2 = 128 per thread).
+// `tid` / `bar`: the NTH threads that share `priv` and `acc` synchronise on hardware barrier `bar` (0 = the whole
+// CTA), so two groups of one CTA can count two arrays side by side (cdf_channel_kernel).
+__device__ __forceinline__ void group_sync(int bar, int nth) {
+    asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(nth) : "memory");
+}
+
 template <bool PRIV, int NTH>
 __device__ __forceinline__ void hist_slice(const float *__restrict__ row, int64_t beg, int64_t end,
                                            bool vec, const HistRange &hr, uint32_t *priv,
-                                           uint32_t *acc) {
-    const int tid = threadIdx.x;
+                                           uint32_t *acc, int tid, int bar) {
     if (!PRIV) {
         for_each<NTH>(row, beg, end, vec, [&](float x) { atomicAdd(&acc[hr.bin(x)], 1u); });
         return;
@@ -183,7 +188,7 @@ __device__ __forceinline__ void hist_slice(const float *__restrict__ row, int64_
     for (int64_t cb = beg; cb < end; cb += chunk) {
         int64_t ce = cb + chunk < end ? cb + chunk : end;
         for (int i = tid; i < rows * (NTH / 4); i += NTH) priv[i] = 0u;
-        __syncthreads();
+        group_sync(bar, NTH);
         auto one = [&](float x) {
             const int a = hr.bin_unclamped(x) * NTH + tid;
             pb[a] = (uint8_t)(pb[a] + 1);
@@ -227,7 +232,7 @@ __device__ __forceinline__ void hist_slice(const float *__restrict__ row, int64_
         } else {
             for (int64_t i = cb + tid; i < ce; i += NTH) one(__ldg(row + i));
         }
-        __syncthreads();
+        group_sync(bar, NTH);
         // fold: thread t sums the NTH byte counters of rows t, t + NTH, ... with packed 16-bit adds
         constexpr int WPR = NTH / 4;  // words per row
         for (int r = tid; r < rows; r += NTH) {
@@ -242,7 +247,7 @@ __device__ __forceinline__ void hist_slice(const float *__restrict__ row, int64_
             const uint32_t total = (even & 0xffffu) + (even >> 16) + (odd & 0xffffu) + (odd >> 16);
             if (total) atomicAdd(&acc[r < hr.bins ? r : hr.bins - 1], total);
         }
-        __syncthreads();
+        group_sync(bar, NTH);
     }
 }
 
@@ -266,10 +271,10 @@ cdf_hist_kernel(const float *__restrict__ t, const float *__restrict__ s, int64_
     int64_t b, e;
     if (blockIdx.z == 0) {
         slice_of(n_t, blockIdx.x, gridDim.x, b, e);
-        hist_slice<PRIV, NTH_HIST>(t + (int64_t)ch * n_t, b, e, t_vec, hr, priv, acc);
+        hist_slice<PRIV, NTH_HIST>(t + (int64_t)ch * n_t, b, e, t_vec, hr, priv, acc, threadIdx.x, 0);
     } else {
         slice_of(n_s, blockIdx.x, gridDim.x, b, e);
-        hist_slice<PRIV, NTH_HIST>(s + (int64_t)ch * n_s, b, e, s_vec, hr, priv, acc);
+        hist_slice<PRIV, NTH_HIST>(s + (int64_t)ch * n_s, b, e, s_vec, hr, priv, acc, threadIdx.x, 0);
     }
     __syncthreads();
     uint32_t *gh = hist + ((int64_t)ch * 2 + blockIdx.z) * bins;
@@ -283,14 +288,15 @@ cdf_hist_kernel(const float *__restrict__ t, const float *__restrict__ s, int64_
 
 // Build edges / CDFs / remap in shared memory from the channel's two histograms.
 //   xs: edges[bins], rm: remap[bins]; scratch tc[bins], sc[bins] (float), cnt[2*bins] (u32)
-__device__ void build_tables(const uint32_t *__restrict__ gh, float lo, float hi, int bins,
+template <int NT>
+__device__ void build_tables(const uint32_t *gh, float lo, float hi, int bins,
                              float *edges, float *remap, float *tc, float *sc, uint32_t *cnt) {
     const int tid = threadIdx.x;
     for (int i = tid; i < 2 * bins; i += NT) cnt[i] = gh[i];
     __syncthreads();
     // inclusive prefix sums (exact integers; torch's fp32 cumsum is exact below 2^24)
     for (int off = 1; off < bins; off <<= 1) {
-        uint32_t a[2 * MAX_BINS / NT];
+        uint32_t a[(2 * MAX_BINS + NT - 1) / NT];
         int k = 0;
         for (int i = tid; i < 2 * bins; i += NT, ++k) {
             int pos = i >= bins ? i - bins : i;
@@ -324,7 +330,7 @@ cdf_tables_kernel(const uint32_t *__restrict__ minmax, const uint32_t *__restric
     uint32_t *cnt = reinterpret_cast<uint32_t *>(sc + bins);
     const int ch = blockIdx.x;
     const float lo = range_lo(minmax, ch), hi = range_hi(minmax, ch);
-    build_tables(hist + (int64_t)ch * 2 * bins, lo, hi, bins, edges, remap, tc, sc, cnt);
+    build_tables<NT>(hist + (int64_t)ch * 2 * bins, lo, hi, bins, edges, remap, tc, sc, cnt);
     float *o = tbl + (int64_t)ch * 4 * bins;
     const int last = bins - 1;
     int mono = 1;
@@ -343,24 +349,15 @@ cdf_tables_kernel(const uint32_t *__restrict__ minmax, const uint32_t *__restric
     if (threadIdx.x == 0) o[3 * bins] = mono ? 1.f : 0.f;
 }
 
-// matched = interp(t, edges, remap)     histmatch.py:68
+// matched = interp(x, edges, remap)     histmatch.py:68
 // searchsorted(edges, x) is found from an arithmetic estimate of the bin plus an exact fix-up against the edges
 // (identical to the bisection whenever the edges are non-decreasing; otherwise the bisection itself runs).
-__global__ void __launch_bounds__(NT)
-cdf_apply_kernel(const float *t, float *out, int64_t n_t, const uint32_t *__restrict__ minmax,
-                 const float *__restrict__ tbl, int bins, int vec) {
-    pdl_wait();
-    __shared__ float tb[3 * MAX_BINS];
-    const int ch = blockIdx.y;
-    const float *g = tbl + (int64_t)ch * 4 * bins;
-    for (int i = threadIdx.x; i < 3 * bins; i += NT) tb[i] = g[i];
-    const bool mono = g[3 * bins] != 0.f;
-    __syncthreads();
-    const float *edges = tb, *remap = tb + bins, *slope = tb + 2 * bins;
-    const float lo = range_lo(minmax, ch), hi = range_hi(minmax, ch);
-    const float inv = hi > lo ? (float)bins / (hi - lo) : 0.f;
-    const int last = bins - 1;
-    auto one = [&](float x) {
+struct ApplyRule {
+    const float *edges, *remap, *slope;
+    float lo, inv;
+    int bins, last;
+    bool mono;
+    __device__ __forceinline__ float operator()(float x) const {
         int i;
         if (mono) {
             i = (int)((x - lo) * inv);
@@ -380,7 +377,21 @@ cdf_apply_kernel(const float *t, float *out, int64_t n_t, const uint32_t *__rest
             if (!finite_f(f)) f = fi;
         }
         return f;
-    };
+    }
+};
+
+__global__ void __launch_bounds__(NT)
+cdf_apply_kernel(const float *t, float *out, int64_t n_t, const uint32_t *__restrict__ minmax,
+                 const float *__restrict__ tbl, int bins, int vec) {
+    pdl_wait();
+    __shared__ float tb[3 * MAX_BINS];
+    const int ch = blockIdx.y;
+    const float *g = tbl + (int64_t)ch * 4 * bins;
+    for (int i = threadIdx.x; i < 3 * bins; i += NT) tb[i] = g[i];
+    const bool mono = g[3 * bins] != 0.f;
+    __syncthreads();
+    const float lo = range_lo(minmax, ch), hi = range_hi(minmax, ch);
+    const ApplyRule one{tb, tb + bins, tb + 2 * bins, lo, hi > lo ? (float)bins / (hi - lo) : 0.f, bins, bins - 1, mono};
     int64_t b, e;
     slice_of(n_t, blockIdx.x, gridDim.x, b, e);
     const float *row = t + (int64_t)ch * n_t;  // may alias out (in-place): every element is read before it is written
@@ -396,6 +407,67 @@ cdf_apply_kernel(const float *t, float *out, int64_t n_t, const uint32_t *__rest
         for (int64_t i = b + (nv << 2) + threadIdx.x; i < e; i += NT) orow[i] = one(row[i]);
     } else {
         for (int64_t i = b + threadIdx.x; i < e; i += NT) orow[i] = one(row[i]);
+    }
+}
+
+// The whole matcher for ONE channel in one CTA - histograms of both arrays (two groups of NTH_HIST threads side by
+// side), tables, apply - for the many-channel / short-row regime (conv4_1, conv5_1): the histograms and tables never
+// leave shared memory, the second pass over the target row hits L1 / L2, and the three launches with their
+// dependency bubbles become one wave of C CTAs whose phases overlap each other on every SM.
+constexpr int NT_CH = 2 * NTH_HIST;
+__global__ void __launch_bounds__(NT_CH, 4)
+cdf_channel_kernel(const float *t, const float *__restrict__ s, float *out, int64_t n_t, int64_t n_s,
+                   const uint32_t *__restrict__ minmax, int bins, int t_vec, int s_vec, int o_vec,
+                   float *__restrict__ tables_out) {
+    pdl_wait();
+    extern __shared__ uint32_t smem_u32[];
+    uint32_t *acc = smem_u32;                              // [2][bins]: target, source counts
+    uint32_t *priv = smem_u32 + 2 * bins;                  // [2][(bins + 1) * NTH_HIST bytes]
+    const int priv_words = (bins + 1) * (NTH_HIST / 4);
+    const int ch = blockIdx.x;
+    for (int i = threadIdx.x; i < 2 * bins; i += NT_CH) acc[i] = 0u;
+    __syncthreads();
+    const float lo = range_lo(minmax, ch), hi = range_hi(minmax, ch);
+    {
+        HistRange hr(lo, hi, bins);
+        const int g = threadIdx.x >= NTH_HIST ? 1 : 0, tid = threadIdx.x - g * NTH_HIST;
+        if (g == 0)
+            hist_slice<true, NTH_HIST>(t + (int64_t)ch * n_t, 0, n_t, t_vec, hr, priv, acc, tid, 1);
+        else
+            hist_slice<true, NTH_HIST>(s + (int64_t)ch * n_s, 0, n_s, s_vec, hr, priv + priv_words, acc + bins, tid, 2);
+    }
+    __syncthreads();
+    // tables in the (now free) private-counter space
+    float *edges = reinterpret_cast<float *>(priv), *remap = edges + bins, *slope = remap + bins;
+    float *tc = slope + bins, *sc = tc + bins;
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(sc + bins);
+    build_tables<NT_CH>(acc, lo, hi, bins, edges, remap, tc, sc, cnt);
+    const int last = bins - 1;
+    int mono = 1;
+    for (int i = threadIdx.x; i < bins; i += NT_CH) {
+        const int j = i + 1 > last ? last : i + 1;
+        slope[i] = __fdiv_rn(__fsub_rn(remap[j], remap[i]), __fsub_rn(edges[j], edges[i]));  // histmatch.py:79
+        if (!(edges[i] <= edges[j])) mono = 0;
+        if (tables_out) {
+            tables_out[((int64_t)ch * 2 + 0) * bins + i] = edges[i];
+            tables_out[((int64_t)ch * 2 + 1) * bins + i] = remap[i];
+        }
+    }
+    mono = __syncthreads_and(mono);
+    const ApplyRule one{edges, remap, slope, lo, hi > lo ? (float)bins / (hi - lo) : 0.f, bins, last, mono != 0};
+    const float *row = t + (int64_t)ch * n_t;  // may alias out (in-place): every element is read before it is written
+    float *orow = out + (int64_t)ch * n_t;
+    if (o_vec) {
+        const int64_t nv = n_t >> 2;
+        const float4 *p = reinterpret_cast<const float4 *>(row);
+        float4 *q = reinterpret_cast<float4 *>(orow);
+        for (int64_t i = threadIdx.x; i < nv; i += NT_CH) {
+            const float4 v = p[i];
+            q[i] = make_float4(one(v.x), one(v.y), one(v.z), one(v.w));
+        }
+        for (int64_t i = (nv << 2) + threadIdx.x; i < n_t; i += NT_CH) orow[i] = one(row[i]);
+    } else {
+        for (int64_t i = threadIdx.x; i < n_t; i += NT_CH) orow[i] = one(row[i]);
     }
 }
 
@@ -476,6 +548,21 @@ int cdf_match_core(const float *target, const float *source, float *out, int c, 
         OPTEX_LAUNCH_CHECK("cdf_range_kernel");
     }
     const bool priv = (bins % 4 == 0) && bins <= PRIV_MAX_BINS;
+    // many channels, short rows: one CTA per channel does the whole match (see cdf_channel_kernel)
+    static const char *no_fused = getenv("OPTEX_NO_CDF_FUSED");
+    if (priv && n_big <= 32768 && c >= 2 * sm_count() && !(no_fused && atoi(no_fused))) {
+        const size_t smem = sizeof(uint32_t) * 2 * (size_t)bins + 2 * (size_t)(bins + 1) * NTH_HIST;
+        static bool attr_done = false;
+        if (!attr_done) {
+            OPTEX_CUDA(cudaFuncSetAttribute(cdf_channel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)(sizeof(uint32_t) * 2 * PRIV_MAX_BINS + 2 * (PRIV_MAX_BINS + 1) * NTH_HIST)));
+            attr_done = true;
+        }
+        launch_pdl(cdf_channel_kernel, dim3((unsigned)c), dim3(NT_CH), smem, st, target, source, out, n_t, n_s,
+                   (const uint32_t *)minmax, bins, t_vec, s_vec, o_vec, tables);
+        OPTEX_LAUNCH_CHECK("cdf_channel_kernel");
+        return OPTEX_OK;
+    }
     // histogram grid: one CTA per channel and array unless that leaves SMs idle and the slices stay long
     int64_t hs = (2LL * sm_count() + c - 1) / c, hcap = (n_big + 32767) / 32768;
     dim3 grid_h((unsigned)(hs < hcap ? (hs < 1 ? 1 : hs) : (hcap < 1 ? 1 : hcap)), (unsigned)c, 2);

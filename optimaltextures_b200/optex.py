@@ -41,6 +41,16 @@ def set_gemm_mode(mode: str) -> None:
     call("optex_set_gemm_mode", _lib.GEMM_MODES[mode])
 
 
+def set_rotation_precision(precision: str) -> str:
+    """Arithmetic of the on-device Householder construction: "fp64" (default, like the reference's scipy branch
+    before `.to(pastiche_feature)`) or "fp32" (like its impl="torch" branch, optex.py:150-164).  Returns the
+    previous setting."""
+    if precision not in ("fp64", "fp32"):
+        raise ValueError(f"rotation precision must be 'fp64' or 'fp32', got {precision!r}")
+    prev = _lib.lib().optex_set_rotation_precision(1 if precision == "fp64" else 0)
+    return "fp64" if prev else "fp32"
+
+
 def random_rotation(N: int, device="cuda", impl: str = "device", seed: Optional[int] = None,
                     counter: Optional[int] = None, gauss: Optional[Tensor] = None) -> Tensor:
     """reference: optex.py:142-164.  Haar SO(N) matrix, fp32 [N, N] on `device`.
