@@ -34,6 +34,29 @@ def manual_seed(seed: int) -> None:
     global _seed, _counter
     _seed = int(seed) & 0xFFFFFFFFFFFFFFFF
     _counter = itertools.count()
+    _rotation_pool.clear()
+
+
+# optimal_transport() draws its own rotation like the reference does (optex.py:168).  One draw is latency-bound
+# (117 us at N = 512), a batch costs 29 us per matrix, so the implicit draws come out of a small per-(device, N)
+# pool filled 16 at a time; the stream stays a pure function of manual_seed() and the order of the calls.
+_POOL = 16
+_rotation_pool = {}
+
+
+def _pooled_rotation(N: int, dev) -> Tensor:
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    key = (dev.index, N)
+    ent = _rotation_pool.get(key)
+    if ent is None or ent[1] >= _POOL or ent[2] != stream or ent[3] != _seed:
+        first = next(_counter)
+        for _ in range(_POOL - 1):
+            next(_counter)
+        ent = [random_rotations(N, _POOL, dev, seed=_seed, first_counter=first), 0, stream, _seed]
+        _rotation_pool[key] = ent
+    r = ent[0][ent[1]]
+    ent[1] += 1
+    return r
 
 
 def set_gemm_mode(mode: str) -> None:
@@ -99,7 +122,7 @@ def optimal_transport(pastiche_feature: Tensor, style_feature: Tensor, hist_mode
         raise ValueError(f"channel mismatch: pastiche {c} vs style {cs}")
     p, s = f32c(pastiche_feature), f32c(style_feature)
     if rotation is None:
-        rotation = random_rotation(c, dev)
+        rotation = _pooled_rotation(c, dev)
     r = f32c(rotation)  # `.to(pastiche_feature)` in the reference: float64 scipy matrix -> fp32
     if tuple(r.shape) != (c, c):
         raise ValueError(f"rotation must be [{c}, {c}], got {tuple(r.shape)}")

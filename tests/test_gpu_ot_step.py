@@ -272,3 +272,22 @@ def test_rotation_haar_statistics(ob):
     tr = mats.diagonal(dim1=1, dim2=2).sum(1)
     assert abs(float(tr.mean())) < 4.0 / np.sqrt(reps)
     assert abs(float(tr.var()) - 1.0) < 0.3        # Var[trace] = 1 for Haar O(n)/SO(n)
+
+
+def test_implicit_rotation_stream_is_pooled_and_reproducible(ob):
+    """optimal_transport() without rotation= draws like the reference (optex.py:168); the draws come from a pool
+    filled 16 at a time, and the stream is a pure function of manual_seed() and the call order."""
+    g = torch.Generator(device="cpu").manual_seed(1)
+    p = torch.relu(torch.randn(1, 16, 16, 64, generator=g)).cuda()
+    s = torch.relu(torch.randn(1, 16, 16, 64, generator=g)).cuda()
+    ob.manual_seed(11)
+    a = [ob.optimal_transport(p, s, "cdf") for _ in range(18)]        # crosses a pool refill
+    ob.manual_seed(11)
+    b = [ob.optimal_transport(p, s, "cdf") for _ in range(18)]
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+    assert not torch.equal(a[0], a[1])
+    rots = ob.random_rotations(64, 16, "cuda", seed=11, first_counter=0)
+    for i in (0, 5, 15):
+        assert torch.equal(a[i], ob.optimal_transport(p, s, "cdf", rotation=rots[i]))
+    rots2 = ob.random_rotations(64, 2, "cuda", seed=11, first_counter=16)
+    assert torch.equal(a[17], ob.optimal_transport(p, s, "cdf", rotation=rots2[1]))
