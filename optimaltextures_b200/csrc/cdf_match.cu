@@ -53,7 +53,7 @@ __device__ __forceinline__ void slice_of(int64_t n, int part, int nparts, int64_
 // torch.histc bin rule (CPU): int64((x - lo) * bins / (hi - lo)), bin == bins -> bins-1;
 // a degenerate range [v, v] becomes [v-1, v+1].
 struct HistRange {
-    float lo, width, fbins, rcp;
+    float lo, width, fbins, rcp, scale;
     int bins;
     __device__ HistRange(float lo_, float hi_, int bins_) : bins(bins_) {
         if (lo_ == hi_) {
@@ -64,6 +64,7 @@ struct HistRange {
         width = __fsub_rn(hi_, lo_);
         fbins = (float)bins_;
         rcp = 1.f / width;
+        scale = fbins * rcp;
     }
     // Exact trunc(fdiv_rn(a, width)) without dividing every element: a * rcp is within a few ulp (< 1e-4 absolute
     // for quotients <= 1024) of the true quotient, so it has the same integer part unless it lies within 1e-3 of an
@@ -80,10 +81,10 @@ struct HistRange {
     // same rule, but x == hi is reported as bin `bins` (the caller folds it into bins - 1); values are in [lo, hi]
     // by construction (lo / hi are the data's own extrema), NaN converts to 0
     __device__ __forceinline__ int bin_unclamped(float x) const {
-        const float a = __fmul_rn(__fsub_rn(x, lo), fbins);
-        float q = a * rcp;
+        const float d = __fsub_rn(x, lo);
+        float q = d * scale;   // one multiply on the common path (scale = bins / width, a few ulp like a * rcp)
         const float r = __fsub_rn(__fadd_rn(q, 12582912.f), 12582912.f);
-        if (!(fabsf(q - r) >= 1e-3f)) q = __fdiv_rn(a, width);
+        if (!(fabsf(q - r) >= 1e-3f)) q = __fdiv_rn(__fmul_rn(d, fbins), width);
         const unsigned b = (unsigned)(int)q;
         return (int)(b > (unsigned)bins ? (unsigned)bins : b);  // one unsigned min: memory safety only
     }
@@ -359,17 +360,31 @@ struct ApplyRule {
     bool mono;
     __device__ __forceinline__ float operator()(float x) const {
         int i;
+        float xi;
         if (mono) {
-            i = (int)((x - lo) * inv);
-            i = i < 0 ? 0 : (i > last ? last : i);
-            while (i > 0 && edges[i - 1] >= x) --i;
-            while (i < last && edges[i] < x) ++i;
-            if (x != x) i = last;
+            // the estimate k is the answer iff edges[k-1] < x <= edges[k] (k = last: no upper test, like the clamp of
+            // searchsorted's result) - one predictable branch on the common path; everything else (exact ties with an
+            // edge, rounding next to one, NaN, repeated edges) walks from k exactly as the bisection would land
+            int k = (int)((x - lo) * inv);
+            k = k < 0 ? 0 : (k > last ? last : k);
+            const float t1 = edges[k];
+            const float t0 = edges[k > 0 ? k - 1 : 0];
+            if ((k == 0 || t0 < x) && (x <= t1 || k == last)) {
+                i = k;
+                xi = t1;
+            } else {
+                i = k;
+                while (i > 0 && edges[i - 1] >= x) --i;
+                while (i < last && edges[i] < x) ++i;
+                if (x != x) i = last;
+                xi = edges[i];
+            }
         } else {
             i = lower_bound(edges, bins, x);
             i = i > last ? last : i;
+            xi = edges[i];
         }
-        const float xi = edges[i], fi = remap[i], sl = slope[i];
+        const float fi = remap[i], sl = slope[i];
         float f = __fadd_rn(__fmul_rn(sl, __fsub_rn(x, xi)), fi);
         if (!finite_f(f)) {
             const int j = i + 1 > last ? last : i + 1;
