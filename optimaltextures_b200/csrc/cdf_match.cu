@@ -395,6 +395,39 @@ struct ApplyRule {
     }
 };
 
+// out[b, e) = rule(row[b, e)) for a block of NTH threads; 128-bit accesses with PF loads in flight per thread (one
+// L2 round trip per step otherwise).  row may alias out: a thread only ever writes elements it has already read.
+template <int NTH>
+__device__ __forceinline__ void apply_slice(const ApplyRule &one, const float *row, float *orow, int64_t b, int64_t e,
+                                            bool vec) {
+    if (vec) {
+        const int64_t nv = (e - b) >> 2;
+        const float4 *p = reinterpret_cast<const float4 *>(row + b);
+        float4 *q = reinterpret_cast<float4 *>(orow + b);
+        constexpr int PF = 4;
+        float4 ring[PF];
+#pragma unroll
+        for (int k = 0; k < PF; ++k) {
+            const int64_t j = threadIdx.x + (int64_t)k * NTH;
+            ring[k] = j < nv ? p[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        for (int64_t i = threadIdx.x; i < nv; i += (int64_t)PF * NTH) {
+#pragma unroll
+            for (int k = 0; k < PF; ++k) {
+                const int64_t cur = i + (int64_t)k * NTH;
+                if (cur >= nv) break;
+                const float4 v = ring[k];
+                const int64_t nxt = cur + (int64_t)PF * NTH;
+                if (nxt < nv) ring[k] = p[nxt];
+                q[cur] = make_float4(one(v.x), one(v.y), one(v.z), one(v.w));
+            }
+        }
+        for (int64_t i = b + (nv << 2) + threadIdx.x; i < e; i += NTH) orow[i] = one(row[i]);
+    } else {
+        for (int64_t i = b + threadIdx.x; i < e; i += NTH) orow[i] = one(row[i]);
+    }
+}
+
 __global__ void __launch_bounds__(NT)
 cdf_apply_kernel(const float *t, float *out, int64_t n_t, const uint32_t *__restrict__ minmax,
                  const float *__restrict__ tbl, int bins, int vec) {
@@ -409,20 +442,7 @@ cdf_apply_kernel(const float *t, float *out, int64_t n_t, const uint32_t *__rest
     const ApplyRule one{tb, tb + bins, tb + 2 * bins, lo, hi > lo ? (float)bins / (hi - lo) : 0.f, bins, bins - 1, mono};
     int64_t b, e;
     slice_of(n_t, blockIdx.x, gridDim.x, b, e);
-    const float *row = t + (int64_t)ch * n_t;  // may alias out (in-place): every element is read before it is written
-    float *orow = out + (int64_t)ch * n_t;
-    if (vec) {
-        int64_t nv = (e - b) >> 2;
-        const float4 *p = reinterpret_cast<const float4 *>(row + b);
-        float4 *q = reinterpret_cast<float4 *>(orow + b);
-        for (int64_t i = threadIdx.x; i < nv; i += NT) {
-            float4 v = p[i];
-            q[i] = make_float4(one(v.x), one(v.y), one(v.z), one(v.w));
-        }
-        for (int64_t i = b + (nv << 2) + threadIdx.x; i < e; i += NT) orow[i] = one(row[i]);
-    } else {
-        for (int64_t i = b + threadIdx.x; i < e; i += NT) orow[i] = one(row[i]);
-    }
+    apply_slice<NT>(one, t + (int64_t)ch * n_t, out + (int64_t)ch * n_t, b, e, vec != 0);
 }
 
 // The whole matcher for ONE channel in one CTA - histograms of both arrays (two groups of NTH_HIST threads side by
@@ -470,20 +490,7 @@ cdf_channel_kernel(const float *t, const float *__restrict__ s, float *out, int6
     }
     mono = __syncthreads_and(mono);
     const ApplyRule one{edges, remap, slope, lo, hi > lo ? (float)bins / (hi - lo) : 0.f, bins, last, mono != 0};
-    const float *row = t + (int64_t)ch * n_t;  // may alias out (in-place): every element is read before it is written
-    float *orow = out + (int64_t)ch * n_t;
-    if (o_vec) {
-        const int64_t nv = n_t >> 2;
-        const float4 *p = reinterpret_cast<const float4 *>(row);
-        float4 *q = reinterpret_cast<float4 *>(orow);
-        for (int64_t i = threadIdx.x; i < nv; i += NT_CH) {
-            const float4 v = p[i];
-            q[i] = make_float4(one(v.x), one(v.y), one(v.z), one(v.w));
-        }
-        for (int64_t i = (nv << 2) + threadIdx.x; i < n_t; i += NT_CH) orow[i] = one(row[i]);
-    } else {
-        for (int64_t i = threadIdx.x; i < n_t; i += NT_CH) orow[i] = one(row[i]);
-    }
+    apply_slice<NT_CH>(one, t + (int64_t)ch * n_t, out + (int64_t)ch * n_t, 0, n_t, o_vec != 0);
 }
 
 __global__ void interp_kernel(const float *__restrict__ x, const float *__restrict__ xp,
