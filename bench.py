@@ -331,8 +331,9 @@ def run_ours(a):
         if per_channel:
             rp = torch.empty(c, n, dtype=torch.float32, device=device)
             rs = torch.empty(c, n, dtype=torch.float32, device=device)
-            names = ["rotate_forward_P", "rotate_forward_S", f"{a.mode}_match", "rotate_inverse"]
-            ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(K)]
+            names = ["split_R", "rotate_forward_P", "rotate_forward_S", f"{a.mode}_match", "rotate_inverse"]
+            ev = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(K)]
+            pws = torch.empty(lib.optex_rotation_prepare_workspace_bytes(c), dtype=torch.uint8, device=device)
             mws = torch.empty(max(lib.optex_cdf_match_workspace_bytes(c, 256),
                                   lib.optex_sort_match_workspace_bytes(c, n, n), 256), dtype=torch.uint8, device=device)
             lib.optex_set_pdl(0)      # events between kernels need ordinary stream serialisation
@@ -340,17 +341,22 @@ def run_ours(a):
                 p, s = sets[i % a.sets]
                 r = rots[i % K]
                 ev[i][0].record()
-                call("optex_rotate_forward", ptr(p), ptr(r), ptr(rp), n, c, st)
+                # R -> tf32 hi / lo once for the three GEMMs, as optex_ot_step does (so each rotate_* stage below is
+                # exactly one GEMM launch)
+                call("optex_rotation_prepare", ptr(r), c, ptr(pws), pws.numel(), st)
                 ev[i][1].record()
-                call("optex_rotate_forward", ptr(s), ptr(r), ptr(rs), n, c, st)
+                call("optex_rotate_forward", ptr(p), ptr(r), ptr(rp), n, c, st)
                 ev[i][2].record()
+                call("optex_rotate_forward", ptr(s), ptr(r), ptr(rs), n, c, st)
+                ev[i][3].record()
                 if a.mode == "cdf":
                     call("optex_cdf_match", ptr(rp), ptr(rs), ptr(rp), c, n, n, 256, None, ptr(mws), mws.numel(), st)
                 else:
                     call("optex_sort_match", ptr(rp), ptr(rs), ptr(rp), c, n, n, None, ptr(mws), mws.numel(), st)
-                ev[i][3].record()
-                call("optex_rotate_inverse", ptr(rp), ptr(r), ptr(outs[i % 2]), n, c, None, 0.0, st)
                 ev[i][4].record()
+                call("optex_rotate_inverse", ptr(rp), ptr(r), ptr(outs[i % 2]), n, c, None, 0.0, st)
+                ev[i][5].record()
+            call("optex_rotation_prepare", None, 0, None, 0, None)
             torch.cuda.synchronize()
             lib.optex_set_pdl(0 if a.no_pdl else 1)
             for j, name in enumerate(names):
@@ -410,6 +416,7 @@ def run_ours(a):
             "rotate_forward_P": ("tensor", 2.0 * c * c * n), "rotate_forward_S": ("tensor", 2.0 * c * c * n),
             "rotate_inverse": ("tensor", 2.0 * c * c * n),
             f"{a.mode}_match": ("hbm", 4.0 * c * (n + n) + 4.0 * c * n),
+            "split_R": ("hbm", 4.0 * c * c * 3),
         }
         for name, ms in stages.items():
             bound, amount = alg[name]
@@ -423,7 +430,7 @@ def run_ours(a):
         single = {k_: v for k_, v in stages.items() if k_.startswith("rotate_")}
         top = max(single, key=single.get)
         for name in kernels:
-            kernels[name]["launches"] = 1 if name.startswith("rotate_") else (3 if a.mode == "cdf" else 2)
+            kernels[name]["launches"] = 1 if (name.startswith("rotate_") or name == "split_R") else (3 if a.mode == "cdf" else 2)
         k = kernels[top]
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")

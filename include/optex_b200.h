@@ -189,6 +189,13 @@ int optex_random_rotations(float *R, int c, int count, uint64_t seed,
                            uint64_t first_counter, const double *gauss,
                            void *workspace, size_t workspace_bytes, void *stream);
 
+/* Optional: split R [c,c] into its tf32 hi / lo halves ONCE for the optex_rotate_* calls that follow on this host
+ * thread with the same R pointer (3xTF32 arithmetic; optex_ot_step does this internally for its three GEMMs, the
+ * three `@` of optex.py:170,171,175 share one R).  The halves live in `workspace` (query the size); the association
+ * ends with the next optex_rotation_prepare call - pass R = NULL to release it - and R must not change meanwhile. */
+size_t optex_rotation_prepare_workspace_bytes(int c);
+int optex_rotation_prepare(const float *R, int c, void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---- rotation GEMMs (building blocks of the step, exported for tests) -------
  * optex.py:170-171:  Xt[c, n] = (X @ R)^T     X [n, c], R [c, c]
  * optex.py:175    :  out[n, c] = Mt^T @ R^T   Mt [c, n] channel-major

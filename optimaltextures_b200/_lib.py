@@ -49,6 +49,8 @@ SIGNATURES = {
     "optex_sort_match": (_i, [_p, _p, _p, _i, _l, _l, _p, _p, _z, _p]),
     "optex_rotation_workspace_bytes": (_z, [_i]),
     "optex_random_rotation": (_i, [_p, _i, _u, _u, _p, _p, _z, _p]),
+    "optex_rotation_prepare_workspace_bytes": (_z, [_i]),
+    "optex_rotation_prepare": (_i, [_p, _i, _p, _z, _p]),
     "optex_rotations_workspace_bytes": (_z, [_i, _i]),
     "optex_random_rotations": (_i, [_p, _i, _i, _u, _u, _p, _p, _z, _p]),
     "optex_rotate_forward": (_i, [_p, _p, _p, _l, _i, _p]),

@@ -502,6 +502,33 @@ extern "C" int optex_rotate_forward(const float *X, const float *R, float *Xt, i
     return rotate_forward(X, R, Xt, n, c, true, (cudaStream_t)stream);
 }
 
+// Split R into its tf32 hi / lo halves once (3xTF32 arithmetic) for the optex_rotate_* calls that follow on this
+// host thread with the same R pointer; optex_ot_step does the same internally for its three GEMMs.
+extern "C" size_t optex_rotation_prepare_workspace_bytes(int c) {
+    return c > 0 ? align_up(sizeof(float) * 2 * (size_t)c * c, 256) : 0;
+}
+
+extern "C" int optex_rotation_prepare(const float *R, int c, void *workspace, size_t workspace_bytes, void *stream) {
+    OPTEX_TRY(require_sm100());
+    gemm_tc_set_presplit(nullptr, nullptr, nullptr);
+    if (!R) return OPTEX_OK;  // release only
+    if (c < 1 || c % 4 != 0) {
+        set_error("optex_rotation_prepare: c must be a positive multiple of 4 (the tensor-core path's constraint)");
+        return OPTEX_EINVAL;
+    }
+    if (!workspace || workspace_bytes < optex_rotation_prepare_workspace_bytes(c)) {
+        set_error("optex_rotation_prepare: workspace %zu < %zu bytes", workspace_bytes,
+                  optex_rotation_prepare_workspace_bytes(c));
+        return OPTEX_EWORKSPACE;
+    }
+    bool forced_tc;
+    if (!(want_tc(forced_tc) && tc_terms() == 3)) return OPTEX_OK;  // fp32 / single-pass tf32: nothing to split
+    float *hi = (float *)workspace, *lo = hi + (size_t)c * c;
+    OPTEX_TRY(gemm_tc_split_and_fill(R, hi, lo, (int64_t)c * c, nullptr, 0, 0u, (cudaStream_t)stream));
+    gemm_tc_set_presplit(R, hi, lo);
+    return OPTEX_OK;
+}
+
 extern "C" int optex_rotate_forward_block(const float *X, const float *R, float *Xt, int64_t n, int c, int c0, int nc,
                                           void *stream) {
     OPTEX_TRY(require_sm100());

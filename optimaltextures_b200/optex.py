@@ -104,6 +104,32 @@ def random_rotation(N: int, device="cuda", impl: str = "device", seed: Optional[
     return out
 
 
+class prepared_rotation:
+    """Context manager: split `rotation` into its tf32 hi / lo halves once (`optex_rotation_prepare`) for the
+    `rotate_forward` / `rotate_inverse` calls inside the block that use the same tensor - what `optimal_transport`
+    does internally for the three `@` of optex.py:170,171,175.  No-op for shapes the tensor-core path does not take."""
+
+    def __init__(self, rotation: Tensor):
+        self.r = f32c(rotation)
+        self.ws = None
+
+    def __enter__(self):
+        r = self.r
+        c = r.shape[-1]
+        if r.is_cuda and r.dim() == 2 and c % 4 == 0:
+            lib = _lib.lib()
+            self.ws = torch.empty(lib.optex_rotation_prepare_workspace_bytes(c), dtype=torch.uint8, device=r.device)
+            with torch.cuda.device(r.device):
+                call("optex_rotation_prepare", ptr(r), c, ptr(self.ws), self.ws.numel(), stream_ptr(r.device))
+        return r
+
+    def __exit__(self, *exc):
+        if self.ws is not None:
+            call("optex_rotation_prepare", None, 0, None, 0, None)
+            self.ws = None
+        return False
+
+
 def _nhwc_dims(x: Tensor):
     if x.dim() != 4:
         raise ValueError(f"expected an NHWC feature tensor [b,h,w,c], got shape {tuple(x.shape)}")

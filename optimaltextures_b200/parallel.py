@@ -22,6 +22,7 @@ test_parallel_gloo.py drives it with the oracle's matchers); the default ops are
 """
 from __future__ import annotations
 
+import contextlib
 from dataclasses import dataclass
 from typing import Callable, List, Optional, Tuple
 
@@ -51,12 +52,13 @@ class Ops:
     rotate_forward_block: Callable[[Tensor, Tensor, int, int], Tensor]   # (x[n,c], R, c0, nc) -> [nc, n]
     match: Callable[[Tensor, Tensor, str], Tensor]                        # (t[nc,n], s[nc,m], mode) -> [nc, n]
     rotate_inverse: Callable[[Tensor, Tensor, Optional[Tensor], float], Tensor]  # (mt[c,n], R, content, w) -> [n,c]
+    prepare: Optional[Callable[[Tensor], object]] = None   # context manager factory: R shared by the three GEMMs
 
 
 def cuda_ops() -> Ops:
     from . import _lib, histmatch
     from ._runtime import call, f32c, ptr, stream_ptr
-    from .optex import rotate_inverse
+    from .optex import prepared_rotation, rotate_inverse
 
     def fwd(x: Tensor, r: Tensor, c0: int, nc: int) -> Tensor:
         xc, rc = f32c(x), f32c(r)
@@ -70,7 +72,7 @@ def cuda_ops() -> Ops:
     def match(t: Tensor, s: Tensor, mode: str) -> Tensor:
         return histmatch.sort_match(t, s) if mode == "sort" else histmatch.cdf_match(t, s)
 
-    return Ops(fwd, match, rotate_inverse)
+    return Ops(fwd, match, rotate_inverse, prepared_rotation)
 
 
 def optimal_transport_sharded(pastiche_feature: Tensor, style_feature: Tensor, hist_mode: str, rotation: Tensor,
@@ -88,26 +90,27 @@ def optimal_transport_sharded(pastiche_feature: Tensor, style_feature: Tensor, h
     n = pastiche_feature.numel() // c
     blocks = channel_blocks(c, world)
     c0, nc = blocks[rank]
-    mt = torch.empty(c, n, dtype=torch.float32, device=pastiche_feature.device)
-    if nc > 0:
-        xt = ops.rotate_forward_block(pastiche_feature.reshape(n, c), rotation, c0, nc)
-        st = ops.rotate_forward_block(style_feature.reshape(-1, c), rotation, c0, nc)
-        mine = ops.match(xt, st, hist_mode)
-    else:
-        mine = mt[:0]
-    if len({b[1] for b in blocks}) == 1:
-        dist.all_gather_into_tensor(mt, mine.contiguous(), group=group)           # equal slabs: one collective
-    else:
-        slabs = [mt[s:s + k] for s, k in blocks]
-        pad = max(k for _, k in blocks)
-        if all(k == pad for _, k in blocks):
-            dist.all_gather(slabs, mine.contiguous(), group=group)
-        else:                                                                     # ragged tail: pad to equal slabs
-            buf = torch.zeros(world, pad, n, dtype=torch.float32, device=mt.device)
-            send = torch.zeros(pad, n, dtype=torch.float32, device=mt.device)
-            send[:nc] = mine
-            dist.all_gather_into_tensor(buf.view(world * pad, n), send, group=group)
-            for r, (s, k) in enumerate(blocks):
-                mt[s:s + k] = buf[r, :k]
-    out = ops.rotate_inverse(mt, rotation, content.reshape(n, c) if content is not None else None, content_strength)
+    with (ops.prepare(rotation) if ops.prepare is not None else contextlib.nullcontext(rotation)) as rotation:
+        mt = torch.empty(c, n, dtype=torch.float32, device=pastiche_feature.device)
+        if nc > 0:
+            xt = ops.rotate_forward_block(pastiche_feature.reshape(n, c), rotation, c0, nc)
+            st = ops.rotate_forward_block(style_feature.reshape(-1, c), rotation, c0, nc)
+            mine = ops.match(xt, st, hist_mode)
+        else:
+            mine = mt[:0]
+        if len({b[1] for b in blocks}) == 1:
+            dist.all_gather_into_tensor(mt, mine.contiguous(), group=group)           # equal slabs: one collective
+        else:
+            slabs = [mt[s:s + k] for s, k in blocks]
+            pad = max(k for _, k in blocks)
+            if all(k == pad for _, k in blocks):
+                dist.all_gather(slabs, mine.contiguous(), group=group)
+            else:                                                                     # ragged tail: pad to equal slabs
+                buf = torch.zeros(world, pad, n, dtype=torch.float32, device=mt.device)
+                send = torch.zeros(pad, n, dtype=torch.float32, device=mt.device)
+                send[:nc] = mine
+                dist.all_gather_into_tensor(buf.view(world * pad, n), send, group=group)
+                for r, (s, k) in enumerate(blocks):
+                    mt[s:s + k] = buf[r, :k]
+        out = ops.rotate_inverse(mt, rotation, content.reshape(n, c) if content is not None else None, content_strength)
     return out.reshape(pastiche_feature.shape)

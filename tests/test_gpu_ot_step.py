@@ -3,6 +3,7 @@ import numpy as np
 import pytest
 import torch
 
+from optimaltextures_b200 import _lib
 from oracle import ot_oracle, rotation as rot_oracle, sort_oracle
 
 pytestmark = pytest.mark.gpu
@@ -291,3 +292,25 @@ def test_implicit_rotation_stream_is_pooled_and_reproducible(ob):
         assert torch.equal(a[i], ob.optimal_transport(p, s, "cdf", rotation=rots[i]))
     rots2 = ob.random_rotations(64, 2, "cuda", seed=11, first_counter=16)
     assert torch.equal(a[17], ob.optimal_transport(p, s, "cdf", rotation=rots2[1]))
+
+
+def test_prepared_rotation_is_bit_identical(ob):
+    """optex_rotation_prepare only moves the hi / lo split of R out of the GEMM calls: same bits, fewer launches."""
+    g = torch.Generator(device="cpu").manual_seed(2)
+    x = torch.randn(8192, 256, generator=g).cuda()
+    r = ob.random_rotation(256, "cuda", seed=3, counter=0)
+    lib = _lib.lib()
+    plain_f = ob.rotate_forward(x, r)
+    plain_i = ob.rotate_inverse(plain_f, r)
+    n0 = lib.optex_launch_count()
+    ob.rotate_forward(x, r); ob.rotate_inverse(plain_f, r)
+    unprepared = lib.optex_launch_count() - n0
+    with ob.prepared_rotation(r) as rr:
+        n0 = lib.optex_launch_count()
+        prep_f = ob.rotate_forward(x, rr)
+        prep_i = ob.rotate_inverse(prep_f, rr)
+        prepared = lib.optex_launch_count() - n0
+    assert torch.equal(plain_f, prep_f) and torch.equal(plain_i, prep_i)
+    assert prepared == unprepared - 2          # the two per-call split kernels are gone
+    after = ob.rotate_forward(x, r)            # released: back to the self-contained call
+    assert torch.equal(after, plain_f)
