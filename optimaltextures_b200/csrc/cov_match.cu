@@ -22,6 +22,8 @@
 //               residual |ZY - I|_max below 3e-4 switch the remaining launches off through a device flag.
 //   chol      : blocked right-looking Cholesky (64-wide panels factored in shared memory, trailing update by
 //               GEMM) and a warp-per-row triangular solve for  T = L_s L_t^-1  (histmatch.py:25-27).
+#include <mutex>
+
 #include "common.cuh"
 #include "gemm_tc.cuh"
 
@@ -38,6 +40,7 @@ constexpr int B_MAX = 64;  // samples per batch (per-sample means, histmatch.py:
 // part[b][split][c] = sum over the split's rows of X[b*hw + r, c]
 __global__ void colsum_partial_kernel(const float *__restrict__ X, float *__restrict__ part, int64_t hw, int c,
                                       int splits) {
+    pdl_wait();
     __shared__ float red[8][33];
     const int ch = blockIdx.x * 32 + threadIdx.x;
     const int split = blockIdx.y, b = blockIdx.z;
@@ -58,6 +61,7 @@ __global__ void colsum_partial_kernel(const float *__restrict__ X, float *__rest
 // mu[b][c] = (sum over splits) / hw                       histmatch.py:16,20
 __global__ void colmean_final_kernel(const float *__restrict__ part, float *__restrict__ mu, int64_t hw, int c,
                                      int splits, int nb) {
+    pdl_wait();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nb * c) return;
     int b = i / c, ch = i % c;
@@ -68,6 +72,7 @@ __global__ void colmean_final_kernel(const float *__restrict__ part, float *__re
 // Sig = (sum_z part_z) / n - sum_b (hw/n) mu_b mu_b^T  (+ eps on the diagonal)      histmatch.py:17-18
 __global__ void gram_reduce_kernel(const float *__restrict__ part, int nz, int64_t zstride, const float *__restrict__ mu,
                                    int nb, int64_t hw, int c, float eps, float *__restrict__ Sig) {
+    pdl_wait();
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)c * c) return;
     int r = (int)(i / c), q = (int)(i % c);
@@ -81,12 +86,14 @@ __global__ void gram_reduce_kernel(const float *__restrict__ part, int nz, int64
     Sig[i] = v;
 }
 __global__ void add_diag_kernel(float *A, int c, float eps) {
+    pdl_wait();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < c) A[(int64_t)i * c + i] += eps;
 }
 // bias[b][j] = mu_s[bs(b)][j] - sum_c G[j][c] mu_p[b][c]            (means folded through the map)
 __global__ void bias_kernel(const float *__restrict__ G, const float *__restrict__ mu_p, const float *__restrict__ mu_s,
                             int b_s, int c, float *__restrict__ bias) {
+    pdl_wait();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.y;
     if (warp >= c) return;
@@ -100,6 +107,7 @@ __global__ void bias_kernel(const float *__restrict__ G, const float *__restrict
 // one block: norm2[0] = sum A^2 (deterministic), flags[0..] = 0, resid[..] = 0
 __global__ void ns_prepare_kernel(const float *__restrict__ A, int64_t n, float *__restrict__ norm2, int *flags,
                                   float *resid, int iters) {
+    pdl_wait();
     __shared__ float red[32];
     float acc = 0.f;
     for (int64_t i = threadIdx.x; i < n; i += blockDim.x) acc = fmaf(A[i], A[i], acc);
@@ -119,6 +127,7 @@ __global__ void ns_prepare_kernel(const float *__restrict__ A, int64_t n, float 
 // Y = A / |A|_F, Z = I
 __global__ void ns_init_kernel(const float *__restrict__ A, const float *__restrict__ norm2, float *__restrict__ Y,
                                float *__restrict__ Z, int c) {
+    pdl_wait();
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)c * c) return;
     const float inv = 1.f / sqrtf(norm2[0]);
@@ -128,6 +137,7 @@ __global__ void ns_init_kernel(const float *__restrict__ A, const float *__restr
 // T = 1.5 I - 0.5 T0 ;  resid[it] = max |T0 - I|
 __global__ void ns_t_kernel(const float *__restrict__ T0, float *__restrict__ T, int c, float *resid, int it,
                             const int *flags) {
+    pdl_wait();
     if (flags[it]) return;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     float d = 0.f;
@@ -144,6 +154,7 @@ __global__ void ns_t_kernel(const float *__restrict__ T0, float *__restrict__ T,
 // Y <- Ynew, Z <- Znew ; flags[it+1] = converged
 __global__ void ns_commit_kernel(float *__restrict__ Y, const float *__restrict__ Yn, float *__restrict__ Z,
                                  const float *__restrict__ Zn, int c, const float *resid, int it, int *flags) {
+    pdl_wait();
     if (flags[it]) {
         if (blockIdx.x == 0 && threadIdx.x == 0) flags[it + 1] = 1;
         return;
@@ -157,6 +168,7 @@ __global__ void ns_commit_kernel(float *__restrict__ Y, const float *__restrict_
 }
 // Y *= |A|_F^(1/2), Z /= |A|_F^(1/2)
 __global__ void ns_finish_kernel(float *__restrict__ Y, float *__restrict__ Z, const float *__restrict__ norm2, int c) {
+    pdl_wait();
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)c * c) return;
     const float rs = sqrtf(sqrtf(norm2[0]));
@@ -170,6 +182,7 @@ __global__ void ns_finish_kernel(float *__restrict__ Y, float *__restrict__ Z, c
 // L_rj = A_rj L_jj^-T for its 64 rows below.
 __global__ void __launch_bounds__(256)
 potrf_panel_kernel(float *__restrict__ A, int c, int j0) {
+    pdl_wait();
     __shared__ float Ljj[PANEL][PANEL + 1];
     __shared__ float Arow[PANEL][PANEL + 1];
     const int w = c - j0 < PANEL ? c - j0 : PANEL;
@@ -219,6 +232,7 @@ potrf_panel_kernel(float *__restrict__ A, int c, int j0) {
 }
 // zero the strict upper triangle (the trailing updates touch the full square)
 __global__ void tril_kernel(float *A, int c) {
+    pdl_wait();
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < (int64_t)c * c && i % c > i / c) A[i] = 0.f;
 }
@@ -226,6 +240,7 @@ __global__ void tril_kernel(float *A, int c) {
 template <int PL>
 __global__ void __launch_bounds__(128)
 trsm_right_kernel(const float *__restrict__ Ls, const float *__restrict__ Ut, float *__restrict__ T, int c) {
+    pdl_wait();
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= c) return;
@@ -276,7 +291,14 @@ inline unsigned cdiv(int64_t a, int64_t b) { return (unsigned)((a + b - 1) / b);
 
 struct Ws {
     float *mu_p, *mu_s, *bias, *part_mean, *part_gram;
-    float *m[14];  // c x c matrices
+    float *m[19];  // c x c matrices
+    float *norm2, *resid;   // Newton-Schulz state of chain 0; chain 1 (side stream) at +NS_STATE
+    int *flags;
+};
+constexpr int NS_STATE = NS_MAX_ITERS + 8;  // floats / ints per chain
+
+// Newton-Schulz state of one chain
+struct NsState {
     float *norm2, *resid;
     int *flags;
 };
@@ -292,10 +314,10 @@ size_t ws_layout(int64_t n_t, int64_t n_s, int c, int b_max, Ws *w, void *base, 
     l.bias = ar.take<float>((size_t)b_max * c);
     l.part_mean = ar.take<float>((size_t)b_max * kMeanSplits * c);
     l.part_gram = ar.take<float>((size_t)kGramSplits * cc);
-    for (int i = 0; i < 14; ++i) l.m[i] = ar.take<float>(cc);
-    l.norm2 = ar.take<float>(4);
-    l.resid = ar.take<float>(NS_MAX_ITERS + 2);
-    l.flags = ar.take<int>(NS_MAX_ITERS + 2);
+    for (int i = 0; i < 19; ++i) l.m[i] = ar.take<float>(cc);
+    l.norm2 = ar.take<float>(2 * NS_STATE);
+    l.resid = ar.take<float>(2 * NS_STATE);
+    l.flags = ar.take<int>(2 * NS_STATE);
     if (w) *w = l;
     if (ok) *ok = ar.ok();
     (void)n_t; (void)n_s;
@@ -306,9 +328,9 @@ size_t ws_layout(int64_t n_t, int64_t n_s, int c, int b_max, Ws *w, void *base, 
 int moments(const float *X, int nb, int64_t hw, int c, float eps, float *mu, float *Sig, Ws &w, cudaStream_t st) {
     const int64_t n = (int64_t)nb * hw;
     int splits = (int)(hw < kMeanSplits ? hw : kMeanSplits);
-    colsum_partial_kernel<<<dim3(cdiv(c, 32), splits, nb), dim3(32, 8), 0, st>>>(X, w.part_mean, hw, c, splits);
+    launch_pdl(colsum_partial_kernel, dim3(cdiv(c, 32), splits, nb), dim3(32, 8), 0, st, X, w.part_mean, hw, c, splits);
     OPTEX_LAUNCH_CHECK("colsum_partial_kernel");
-    colmean_final_kernel<<<cdiv((int64_t)nb * c, 256), 256, 0, st>>>(w.part_mean, mu, hw, c, splits, nb);
+    launch_pdl(colmean_final_kernel, dim3((unsigned)(cdiv((int64_t)nb * c, 256))), dim3(256), 0, st, w.part_mean, mu, hw, c, splits, nb);
     OPTEX_LAUNCH_CHECK("colmean_final_kernel");
     // Gram X^T X: A = X^T (stored [K = n, M = c]) and B = X (stored [K = n, N = c]), split over K
     int nz = (int)(n / 512 < 1 ? 1 : (n / 512 > kGramSplits ? kGramSplits : n / 512));
@@ -335,31 +357,31 @@ int moments(const float *X, int nb, int64_t hw, int c, float eps, float *mu, flo
             nz = (int)((n + kz - 1) / kz);
         }
     }
-    gram_reduce_kernel<<<cdiv((int64_t)c * c, 256), 256, 0, st>>>(w.part_gram, nz, zstride, mu, nb, hw, c, eps, Sig);
+    launch_pdl(gram_reduce_kernel, dim3((unsigned)(cdiv((int64_t)c * c, 256))), dim3(256), 0, st, w.part_gram, nz, zstride, mu, nb, hw, c, eps, Sig);
     OPTEX_LAUNCH_CHECK("gram_reduce_kernel");
     return OPTEX_OK;
 }
 
 // Y = A^(1/2), Z = A^(-1/2) for SPD A (coupled Newton-Schulz); t0, t, yn, zn: scratch
-int ns_sqrt(const float *A, float *Y, float *Z, float *t0, float *t, float *yn, float *zn, int c, Ws &w,
+int ns_sqrt(const float *A, float *Y, float *Z, float *t0, float *t, float *yn, float *zn, int c, const NsState &w,
             cudaStream_t st) {
     const int64_t cc = (int64_t)c * c;
     const unsigned nb = cdiv(cc, 256);
-    ns_prepare_kernel<<<1, 1024, 0, st>>>(A, cc, w.norm2, w.flags, w.resid, NS_MAX_ITERS);
+    launch_pdl(ns_prepare_kernel, dim3((unsigned)(1)), dim3(1024), 0, st, A, cc, w.norm2, w.flags, w.resid, NS_MAX_ITERS);
     OPTEX_LAUNCH_CHECK("ns_prepare_kernel");
-    ns_init_kernel<<<nb, 256, 0, st>>>(A, w.norm2, Y, Z, c);
+    launch_pdl(ns_init_kernel, dim3((unsigned)(nb)), dim3(256), 0, st, A, w.norm2, Y, Z, c);
     OPTEX_LAUNCH_CHECK("ns_init_kernel");
     for (int it = 0; it < NS_MAX_ITERS; ++it) {
         const int *skip = w.flags + it;
         OPTEX_TRY(mm(Z, false, Y, false, t0, c, 1.f, skip, st));
-        ns_t_kernel<<<nb, 256, 0, st>>>(t0, t, c, w.resid, it, w.flags);
+        launch_pdl(ns_t_kernel, dim3((unsigned)(nb)), dim3(256), 0, st, t0, t, c, w.resid, it, w.flags);
         OPTEX_LAUNCH_CHECK("ns_t_kernel");
         OPTEX_TRY(mm(Y, false, t, false, yn, c, 1.f, skip, st));
         OPTEX_TRY(mm(t, false, Z, false, zn, c, 1.f, skip, st));
-        ns_commit_kernel<<<nb, 256, 0, st>>>(Y, yn, Z, zn, c, w.resid, it, w.flags);
+        launch_pdl(ns_commit_kernel, dim3((unsigned)(nb)), dim3(256), 0, st, Y, yn, Z, zn, c, w.resid, it, w.flags);
         OPTEX_LAUNCH_CHECK("ns_commit_kernel");
     }
-    ns_finish_kernel<<<nb, 256, 0, st>>>(Y, Z, w.norm2, c);
+    launch_pdl(ns_finish_kernel, dim3((unsigned)(nb)), dim3(256), 0, st, Y, Z, w.norm2, c);
     OPTEX_LAUNCH_CHECK("ns_finish_kernel");
     return OPTEX_OK;
 }
@@ -368,7 +390,7 @@ int ns_sqrt(const float *A, float *Y, float *Z, float *t0, float *t, float *yn, 
 int cholesky(float *A, int c, cudaStream_t st) {
     for (int j0 = 0; j0 < c; j0 += PANEL) {
         const int below = c - j0 - PANEL > 0 ? c - j0 - PANEL : 0;
-        potrf_panel_kernel<<<1 + cdiv(below, PANEL), 256, 0, st>>>(A, c, j0);
+        launch_pdl(potrf_panel_kernel, dim3((unsigned)(1 + cdiv(below, PANEL))), dim3(256), 0, st, A, c, j0);
         OPTEX_LAUNCH_CHECK("potrf_panel_kernel");
         if (below > 0) {  // A22 -= L21 L21^T  (full square; the upper triangle is discarded at the end)
             const float *L21 = A + (int64_t)(j0 + PANEL) * c + j0;
@@ -379,7 +401,7 @@ int cholesky(float *A, int c, cudaStream_t st) {
                                     o, st));
         }
     }
-    tril_kernel<<<cdiv((int64_t)c * c, 256), 256, 0, st>>>(A, c);
+    launch_pdl(tril_kernel, dim3((unsigned)(cdiv((int64_t)c * c, 256))), dim3(256), 0, st, A, c);
     OPTEX_LAUNCH_CHECK("tril_kernel");
     return OPTEX_OK;
 }
@@ -387,12 +409,37 @@ int cholesky(float *A, int c, cudaStream_t st) {
 int trsm_right(const float *Ls, const float *Ut, float *T, int c, cudaStream_t st) {
     const unsigned grid = cdiv(c, 4);
     const int pl = (c + 31) / 32;
-    if (pl <= 2) trsm_right_kernel<2><<<grid, 128, 0, st>>>(Ls, Ut, T, c);
-    else if (pl <= 4) trsm_right_kernel<4><<<grid, 128, 0, st>>>(Ls, Ut, T, c);
-    else if (pl <= 8) trsm_right_kernel<8><<<grid, 128, 0, st>>>(Ls, Ut, T, c);
-    else if (pl <= 16) trsm_right_kernel<16><<<grid, 128, 0, st>>>(Ls, Ut, T, c);
-    else trsm_right_kernel<32><<<grid, 128, 0, st>>>(Ls, Ut, T, c);
+    if (pl <= 2) launch_pdl(trsm_right_kernel<2>, grid, dim3(128), 0, st, Ls, Ut, T, c);
+    else if (pl <= 4) launch_pdl(trsm_right_kernel<4>, grid, dim3(128), 0, st, Ls, Ut, T, c);
+    else if (pl <= 8) launch_pdl(trsm_right_kernel<8>, grid, dim3(128), 0, st, Ls, Ut, T, c);
+    else if (pl <= 16) launch_pdl(trsm_right_kernel<16>, grid, dim3(128), 0, st, Ls, Ut, T, c);
+    else launch_pdl(trsm_right_kernel<32>, grid, dim3(128), 0, st, Ls, Ut, T, c);
     OPTEX_LAUNCH_CHECK("trsm_right_kernel");
+    return OPTEX_OK;
+}
+
+// The pastiche-side and the style-side factorisations are independent, latency-bound chains of small launches:
+// the style side runs on a library-owned side stream, forked from and joined back into the caller's stream with
+// events (so the call stays asynchronous and ordered on the caller's stream, and remains graph-capturable).
+struct SideStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+SideStream g_side[64];
+std::mutex g_side_mu;
+
+int side_stream(SideStream **out) {
+    int dev = 0;
+    OPTEX_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) dev = 63;
+    std::lock_guard<std::mutex> lock(g_side_mu);
+    SideStream &s = g_side[dev];
+    if (!s.stream) {
+        OPTEX_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        OPTEX_CUDA(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));
+        OPTEX_CUDA(cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming));
+    }
+    *out = &s;
     return OPTEX_OK;
 }
 
@@ -428,34 +475,58 @@ int cov_ot_step(const float *P, const float *S, const float *R, float *out, int 
     float *sig_t = w.m[0], *sig_s = w.m[1], *tmp = w.m[2], *T = w.m[3], *G = w.m[4];
     float *Y = w.m[5], *Z = w.m[6], *t0 = w.m[7], *t = w.m[8], *yn = w.m[9], *zn = w.m[10], *Y2 = w.m[11],
           *Z2 = w.m[12], *aux = w.m[13];
-    const unsigned nbcc = cdiv((int64_t)c * c, 256);
+    float *tmp_b = w.m[14], *t0_b = w.m[15], *t_b = w.m[16], *yn_b = w.m[17], *zn_b = w.m[18];  // side-stream scratch
+    const NsState ns_a{w.norm2, w.resid, w.flags};
+    const NsState ns_b{w.norm2 + NS_STATE, w.resid + NS_STATE, w.flags + NS_STATE};
     // moments in the un-rotated frame; eps is added after the rotation like the reference (histmatch.py:18,22)
     OPTEX_TRY(moments(P, b_p, hw_p, c, R ? 0.f : eps, w.mu_p, sig_t, w, st));
     OPTEX_TRY(moments(S, b_s, hw_s, c, R ? 0.f : eps, w.mu_s, sig_s, w, st));
-    if (R) {  // Sig' = R^T Sig R + eps I
-        OPTEX_TRY(mm(sig_t, false, R, false, tmp, c, 1.f, nullptr, st));
-        OPTEX_TRY(mm(R, true, tmp, false, sig_t, c, 1.f, nullptr, st));
-        OPTEX_TRY(mm(sig_s, false, R, false, tmp, c, 1.f, nullptr, st));
-        OPTEX_TRY(mm(R, true, tmp, false, sig_s, c, 1.f, nullptr, st));
-        add_diag_kernel<<<cdiv(c, 256), 256, 0, st>>>(sig_t, c, eps);
-        OPTEX_LAUNCH_CHECK("add_diag_kernel");
-        add_diag_kernel<<<cdiv(c, 256), 256, 0, st>>>(sig_s, c, eps);
-        OPTEX_LAUNCH_CHECK("add_diag_kernel");
-    }
+    // ---- fork: the style-side chain (sandwich, factorisation) on the side stream
+    SideStream *side;
+    OPTEX_TRY(side_stream(&side));
+    cudaStream_t sb = side->stream;
+    OPTEX_CUDA(cudaEventRecord(side->fork, st));
+    OPTEX_CUDA(cudaStreamWaitEvent(sb, side->fork, 0));
+    int rc_b = OPTEX_OK;
+    auto side_chain = [&]() -> int {
+        if (R) {  // Sig_s' = R^T Sig_s R + eps I
+            OPTEX_TRY(mm(sig_s, false, R, false, tmp_b, c, 1.f, nullptr, sb));
+            OPTEX_TRY(mm(R, true, tmp_b, false, sig_s, c, 1.f, nullptr, sb));
+            launch_pdl(add_diag_kernel, dim3((unsigned)(cdiv(c, 256))), dim3(256), 0, sb, sig_s, c, eps);
+            OPTEX_LAUNCH_CHECK("add_diag_kernel");
+        }
+        if (mode == OPTEX_MODE_CHOL) return cholesky(sig_s, c, sb);
+        if (mode == OPTEX_MODE_PCA) return ns_sqrt(sig_s, Y2, Z2, t0_b, t_b, yn_b, zn_b, c, ns_b, sb);
+        return OPTEX_OK;  // sym: the second square root needs the first one
+    };
+    rc_b = side_chain();
+    // always join, also on an error above: the side stream must not be left forked inside a capture
+    cudaError_t join_err = cudaEventRecord(side->join, sb);
+    // ---- the pastiche-side chain on the caller's stream
+    auto main_chain = [&]() -> int {
+        if (R) {  // Sig_t' = R^T Sig_t R + eps I
+            OPTEX_TRY(mm(sig_t, false, R, false, tmp, c, 1.f, nullptr, st));
+            OPTEX_TRY(mm(R, true, tmp, false, sig_t, c, 1.f, nullptr, st));
+            launch_pdl(add_diag_kernel, dim3((unsigned)(cdiv(c, 256))), dim3(256), 0, st, sig_t, c, eps);
+            OPTEX_LAUNCH_CHECK("add_diag_kernel");
+        }
+        if (mode == OPTEX_MODE_CHOL) return cholesky(sig_t, c, st);
+        return ns_sqrt(sig_t, Y, Z, t0, t, yn, zn, c, ns_a, st);
+    };
+    const int rc_a = main_chain();
+    if (join_err == cudaSuccess) join_err = cudaStreamWaitEvent(st, side->join, 0);
+    OPTEX_CUDA(join_err);
+    OPTEX_TRY(rc_b);
+    OPTEX_TRY(rc_a);
     if (mode == OPTEX_MODE_CHOL) {  // T = L_s L_t^-1                      histmatch.py:25-27
-        OPTEX_TRY(cholesky(sig_t, c, st));
-        OPTEX_TRY(cholesky(sig_s, c, st));
         OPTEX_TRY(transpose_f32(sig_t, tmp, c, c, st));
         OPTEX_TRY(trsm_right(sig_s, tmp, T, c, st));
     } else if (mode == OPTEX_MODE_PCA) {  // T = Sig_s^(1/2) Sig_t^(-1/2)   histmatch.py:29-34
-        OPTEX_TRY(ns_sqrt(sig_t, Y, Z, t0, t, yn, zn, c, w, st));
-        OPTEX_TRY(ns_sqrt(sig_s, Y2, Z2, t0, t, yn, zn, c, w, st));
         OPTEX_TRY(mm(Y2, false, Z, false, T, c, 1.f, nullptr, st));
     } else {  // sym: T = Qt^-1 (Qt Sig_s Qt)^(1/2) Qt^-1                   histmatch.py:36-42
-        OPTEX_TRY(ns_sqrt(sig_t, Y, Z, t0, t, yn, zn, c, w, st));
         OPTEX_TRY(mm(Y, false, sig_s, false, tmp, c, 1.f, nullptr, st));
         OPTEX_TRY(mm(tmp, false, Y, false, aux, c, 1.f, nullptr, st));
-        OPTEX_TRY(ns_sqrt(aux, Y2, Z2, t0, t, yn, zn, c, w, st));
+        OPTEX_TRY(ns_sqrt(aux, Y2, Z2, t0, t, yn, zn, c, ns_a, st));
         OPTEX_TRY(mm(Z, false, Y2, false, tmp, c, 1.f, nullptr, st));
         OPTEX_TRY(mm(tmp, false, Z, false, T, c, 1.f, nullptr, st));
     }
@@ -465,10 +536,9 @@ int cov_ot_step(const float *P, const float *S, const float *R, float *out, int 
         OPTEX_TRY(mm(tmp, false, R, true, G, c, 1.f, nullptr, st));
         Gp = G;
     }
-    bias_kernel<<<dim3(cdiv((int64_t)c * 32, 128), b_p), 128, 0, st>>>(Gp, w.mu_p, w.mu_s, b_s, c, w.bias);
+    launch_pdl(bias_kernel, dim3(cdiv((int64_t)c * 32, 128), b_p), dim3(128), 0, st, Gp, w.mu_p, w.mu_s, b_s, c, w.bias);
     OPTEX_LAUNCH_CHECK("bias_kernel");
     // out[n, j] = sum_c P[n, c] G[j, c] + bias[b(n), j]   (+ content blend)
-    (void)nbcc;
     int rc = OPTEX_ENOTSUP;
     if (g_want_tc()) {
         TcGemm g{};
