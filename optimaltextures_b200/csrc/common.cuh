@@ -129,6 +129,8 @@ struct SimtOpts {
     int split_k = 1;              // blockIdx.z splits K; partials at D + z * d_z_stride
     int64_t d_z_stride = 0;
     const int *skip = nullptr;    // device flag: non-zero -> no-op
+    const float *skip_below = nullptr;  // device value: *skip_below < skip_tol -> no-op
+    float skip_tol = 0.f;
 };
 int sgemm_simt_ex(const float *A, int64_t lda, bool a_kmajor, const float *B, int64_t ldb, bool b_kmajor, float *D,
                   int64_t ldd, bool d_trans, int64_t M, int64_t N, int64_t K, const float *blend, float strength,

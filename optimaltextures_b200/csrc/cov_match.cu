@@ -104,9 +104,15 @@ __global__ void bias_kernel(const float *__restrict__ G, const float *__restrict
 }
 
 // ------------------------------------------------------------------ Newton-Schulz helpers
-// one block: norm2[0] = sum A^2 (deterministic), flags[0..] = 0, resid[..] = 0
-__global__ void ns_prepare_kernel(const float *__restrict__ A, int64_t n, float *__restrict__ norm2, int *flags,
-                                  float *resid, int iters) {
+// Coupled Newton-Schulz for A^(1/2), A^(-1/2).  Convergence is tracked on the device without flags: resid[it] is the
+// max |Z Y - I| seen by iteration `it` (0 while the iteration has not run); iteration it is a no-op when
+// resid[it-1] < NS_TOL - either iteration it-1 converged (its update is still applied) or it was itself skipped (its
+// slot kept the initial 0) - and every kernel of an iteration tests that one value.  Y / Z ping-pong between two
+// buffers, so the state after the last executed iteration k-1 sits in buffer k & 1.
+
+// one block: norm2[0] = sum A^2 (deterministic), resid[..] = 0
+__global__ void ns_prepare_kernel(const float *__restrict__ A, int64_t n, float *__restrict__ norm2, float *resid,
+                                  int iters) {
     pdl_wait();
     __shared__ float red[32];
     float acc = 0.f;
@@ -119,10 +125,7 @@ __global__ void ns_prepare_kernel(const float *__restrict__ A, int64_t n, float 
         acc = warp_sum(acc);
         if (threadIdx.x == 0) norm2[0] = acc;
     }
-    for (int i = threadIdx.x; i <= iters; i += blockDim.x) {
-        flags[i] = 0;
-        resid[i] = 0.f;
-    }
+    for (int i = threadIdx.x; i <= iters; i += blockDim.x) resid[i] = 0.f;
 }
 // Y = A / |A|_F, Z = I
 __global__ void ns_init_kernel(const float *__restrict__ A, const float *__restrict__ norm2, float *__restrict__ Y,
@@ -134,11 +137,10 @@ __global__ void ns_init_kernel(const float *__restrict__ A, const float *__restr
     Y[i] = A[i] * inv;
     Z[i] = (i / c == i % c) ? 1.f : 0.f;
 }
-// T = 1.5 I - 0.5 T0 ;  resid[it] = max |T0 - I|
-__global__ void ns_t_kernel(const float *__restrict__ T0, float *__restrict__ T, int c, float *resid, int it,
-                            const int *flags) {
+// T = 1.5 I - 0.5 T0 ;  resid[it] = max |T0 - I|   (only when the GEMM could not fuse it into its epilogue)
+__global__ void ns_t_kernel(const float *__restrict__ T0, float *__restrict__ T, int c, float *resid, int it) {
     pdl_wait();
-    if (flags[it]) return;
+    if (it > 0 && resid[it - 1] < NS_TOL) return;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     float d = 0.f;
     if (i < (int64_t)c * c) {
@@ -151,29 +153,21 @@ __global__ void ns_t_kernel(const float *__restrict__ T0, float *__restrict__ T,
     d = warp_max(d);
     if ((threadIdx.x & 31) == 0 && d > 0.f) atomicMax(reinterpret_cast<unsigned int *>(resid + it), __float_as_uint(d));
 }
-// Y <- Ynew, Z <- Znew ; flags[it+1] = converged
-__global__ void ns_commit_kernel(float *__restrict__ Y, const float *__restrict__ Yn, float *__restrict__ Z,
-                                 const float *__restrict__ Zn, int c, const float *resid, int it, int *flags) {
-    pdl_wait();
-    if (flags[it]) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) flags[it + 1] = 1;
-        return;
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) flags[it + 1] = resid[it] < NS_TOL ? 1 : 0;
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < (int64_t)c * c) {
-        Y[i] = Yn[i];
-        Z[i] = Zn[i];
-    }
-}
-// Y *= |A|_F^(1/2), Z /= |A|_F^(1/2)
-__global__ void ns_finish_kernel(float *__restrict__ Y, float *__restrict__ Z, const float *__restrict__ norm2, int c) {
+// Y = Y_k |A|_F^(1/2), Z = Z_k / |A|_F^(1/2), k = the first skipped iteration (buffer k & 1 holds the final state)
+__global__ void ns_finish_kernel(const float *__restrict__ Y0, const float *__restrict__ Y1,
+                                 const float *__restrict__ Z0, const float *__restrict__ Z1, float *__restrict__ Y,
+                                 float *__restrict__ Z, const float *__restrict__ norm2,
+                                 const float *__restrict__ resid, int iters, int c) {
     pdl_wait();
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)c * c) return;
+    int k = iters;
+    for (int it = 1; it < iters; ++it)
+        if (resid[it - 1] < NS_TOL) { k = it; break; }
     const float rs = sqrtf(sqrtf(norm2[0]));
-    Y[i] *= rs;
-    Z[i] /= rs;
+    const float y = (k & 1) ? Y1[i] : Y0[i], z = (k & 1) ? Z1[i] : Z0[i];
+    Y[i] = y * rs;
+    Z[i] = z / rs;
 }
 
 // ------------------------------------------------------------------ Cholesky
@@ -362,26 +356,61 @@ int moments(const float *X, int nb, int64_t hw, int c, float eps, float *mu, flo
     return OPTEX_OK;
 }
 
-// Y = A^(1/2), Z = A^(-1/2) for SPD A (coupled Newton-Schulz); t0, t, yn, zn: scratch
+// T = 1.5 I - 0.5 Z Y and resid[it] = max |Z Y - I|: fused into the tensor-core GEMM's epilogue, or GEMM + ns_t_kernel
+int ns_t_step(const float *Z, const float *Y, float *t0, float *t, int c, float *resid, int it, cudaStream_t st) {
+    const float *skip_below = it > 0 ? resid + it - 1 : nullptr;
+    if (g_want_tc()) {
+        TcGemm g{};
+        g.A = Z; g.a_mn = false; g.B = Y; g.b_mn = true; g.D = t; g.ldd = c;
+        g.M = g.N = g.K = c; g.terms = g_terms(); g.alpha = -0.5f; g.diag = 1.5f; g.resid_max = resid + it;
+        g.skip_below = skip_below; g.skip_tol = NS_TOL;
+        int rc = gemm_tc(g, st);
+        if (rc != OPTEX_ENOTSUP) return rc;
+    }
+    SimtOpts o;
+    o.skip_below = skip_below;
+    o.skip_tol = NS_TOL;
+    OPTEX_TRY(sgemm_simt_ex(Z, c, true, Y, c, false, t0, c, false, c, c, c, nullptr, 0.f, 1.f, o, st));
+    launch_pdl(ns_t_kernel, dim3(cdiv((int64_t)c * c, 256)), dim3(256), 0, st, (const float *)t0, t, c, resid, it);
+    OPTEX_LAUNCH_CHECK("ns_t_kernel");
+    return OPTEX_OK;
+}
+
+// D = A B (all [c, c] row-major), a no-op once the chain has converged
+int ns_mm(const float *A, const float *B, float *D, int c, const float *skip_below, cudaStream_t st) {
+    if (g_want_tc()) {
+        TcGemm g{};
+        g.A = A; g.a_mn = false; g.B = B; g.b_mn = true; g.D = D; g.ldd = c;
+        g.M = g.N = g.K = c; g.terms = g_terms(); g.alpha = 1.f; g.skip_below = skip_below; g.skip_tol = NS_TOL;
+        int rc = gemm_tc(g, st);
+        if (rc != OPTEX_ENOTSUP) return rc;
+    }
+    SimtOpts o;
+    o.skip_below = skip_below;
+    o.skip_tol = NS_TOL;
+    return sgemm_simt_ex(A, c, true, B, c, false, D, c, false, c, c, c, nullptr, 0.f, 1.f, o, st);
+}
+
+// Y = A^(1/2), Z = A^(-1/2) for SPD A (coupled Newton-Schulz); t0, t, yn, zn: scratch.  3 launches per iteration.
 int ns_sqrt(const float *A, float *Y, float *Z, float *t0, float *t, float *yn, float *zn, int c, const NsState &w,
             cudaStream_t st) {
     const int64_t cc = (int64_t)c * c;
     const unsigned nb = cdiv(cc, 256);
-    launch_pdl(ns_prepare_kernel, dim3((unsigned)(1)), dim3(1024), 0, st, A, cc, w.norm2, w.flags, w.resid, NS_MAX_ITERS);
+    launch_pdl(ns_prepare_kernel, dim3(1), dim3(1024), 0, st, A, cc, w.norm2, w.resid, NS_MAX_ITERS);
     OPTEX_LAUNCH_CHECK("ns_prepare_kernel");
-    launch_pdl(ns_init_kernel, dim3((unsigned)(nb)), dim3(256), 0, st, A, w.norm2, Y, Z, c);
+    launch_pdl(ns_init_kernel, dim3(nb), dim3(256), 0, st, A, (const float *)w.norm2, Y, Z, c);
     OPTEX_LAUNCH_CHECK("ns_init_kernel");
+    float *Yb[2] = {Y, yn}, *Zb[2] = {Z, zn};
     for (int it = 0; it < NS_MAX_ITERS; ++it) {
-        const int *skip = w.flags + it;
-        OPTEX_TRY(mm(Z, false, Y, false, t0, c, 1.f, skip, st));
-        launch_pdl(ns_t_kernel, dim3((unsigned)(nb)), dim3(256), 0, st, t0, t, c, w.resid, it, w.flags);
-        OPTEX_LAUNCH_CHECK("ns_t_kernel");
-        OPTEX_TRY(mm(Y, false, t, false, yn, c, 1.f, skip, st));
-        OPTEX_TRY(mm(t, false, Z, false, zn, c, 1.f, skip, st));
-        launch_pdl(ns_commit_kernel, dim3((unsigned)(nb)), dim3(256), 0, st, Y, yn, Z, zn, c, w.resid, it, w.flags);
-        OPTEX_LAUNCH_CHECK("ns_commit_kernel");
+        const int cur = it & 1, nxt = cur ^ 1;
+        const float *skip_below = it > 0 ? w.resid + it - 1 : nullptr;
+        OPTEX_TRY(ns_t_step(Zb[cur], Yb[cur], t0, t, c, w.resid, it, st));
+        OPTEX_TRY(ns_mm(Yb[cur], t, Yb[nxt], c, skip_below, st));
+        OPTEX_TRY(ns_mm(t, Zb[cur], Zb[nxt], c, skip_below, st));
     }
-    launch_pdl(ns_finish_kernel, dim3((unsigned)(nb)), dim3(256), 0, st, Y, Z, w.norm2, c);
+    launch_pdl(ns_finish_kernel, dim3(nb), dim3(256), 0, st, (const float *)Yb[0], (const float *)Yb[1],
+               (const float *)Zb[0], (const float *)Zb[1], Y, Z, (const float *)w.norm2, (const float *)w.resid,
+               NS_MAX_ITERS, c);
     OPTEX_LAUNCH_CHECK("ns_finish_kernel");
     return OPTEX_OK;
 }

@@ -65,6 +65,8 @@ struct SimtExtra {
     int accumulate;
     int64_t k_per_z, d_z_stride;
     const int *skip;
+    const float *skip_below;  // *skip_below < skip_tol -> no-op
+    float skip_tol;
 };
 
 template <bool A_KMAJOR, bool B_KMAJOR, bool D_TRANS>
@@ -74,6 +76,7 @@ sgemm_kernel(const float *__restrict__ A, int64_t lda, const float *__restrict__
              const float *__restrict__ blend, float strength, float alpha, int a_vec, int b_vec,
              int d_vec, SimtExtra ex) {
     if (ex.skip && *ex.skip) return;
+    if (ex.skip_below && *ex.skip_below < ex.skip_tol) return;
     __shared__ __align__(16) float As[2][BK][LDS_];
     __shared__ __align__(16) float Bs[2][BK][LDS_];
 
@@ -231,6 +234,7 @@ int sgemm_simt_ex(const float *A, int64_t lda, bool a_kmajor, const float *B, in
     SimtExtra ex{};
     ex.bias = o.bias; ex.bias_hw = o.bias_hw > 0 ? o.bias_hw : 1; ex.bias_ld = o.bias_ld;
     ex.accumulate = o.accumulate ? 1 : 0; ex.skip = o.skip; ex.d_z_stride = o.d_z_stride;
+    ex.skip_below = o.skip_below; ex.skip_tol = o.skip_tol;
     int nz = 1;
     if (o.split_k > 1) {
         ex.k_per_z = ((K + o.split_k - 1) / o.split_k + BK - 1) / BK * BK;

@@ -37,6 +37,11 @@ struct TcGemm {
     bool presplit_b;     // 3xTF32: split B with an element-wise pass even though M is small (B is the big operand)
     uint32_t *rowrange;  // !d_trans: per output row, the same fold (rows = channels in the fused loop)
     uint32_t *colrange;  // d_trans only: per output column, atomicMin of (f2ord(v), ~f2ord(v)) - see cdf_match.cu
+    // Newton-Schulz epilogue (cov_match.cu): D = alpha * acc + diag * I, and atomicMax(resid_max, max |acc - I|)
+    float diag;
+    float *resid_max;
+    const float *skip_below;  // device value: *skip_below < skip_tol -> the whole launch is a no-op
+    float skip_tol;
 };
 // selects which of the two library-owned hi/lo scratch buffers the calling thread's GEMMs use (pipelined callers)
 void gemm_tc_set_scratch_slot(int slot);

@@ -217,6 +217,10 @@ struct Params {
     unsigned long long *trace;  // debug: CTA 0 records clock stamps of its first tile's pipeline events (or null)
     uint32_t *rowrange;   // !D_TRANS: the same per output ROW (rows = channels in the fused loop's mid rotation)
     int conv_b;           // same for B (small problems, where a pre-split pass per GEMM would dominate)
+    float diag;           // !D_TRANS: + diag on the main diagonal (after alpha), Newton-Schulz T = 1.5 I - 0.5 Z Y
+    float *resid_max;     // !D_TRANS: atomicMax of max |acc - I| over the output (acc before alpha)
+    const float *skip_below;  // *skip_below < skip_tol -> no-op launch (a converged Newton-Schulz chain)
+    float skip_tol;
     int a_tmem;           // conv_a && !conv_b: the converters write the hi / lo halves of A to TENSOR memory
     int stages_a;         // a_tmem: depth of the raw-A shared-memory ring (p.stages is the B ring then)
 };
@@ -257,6 +261,7 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     pdl_wait();
     if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[65] = clock64();
     if (p.skip && *p.skip) return;  // uniform over the grid
+    if (p.skip_below && *p.skip_below < p.skip_tol) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool a_tmem = p.a_tmem != 0;
     const int nterm_tiles = p.terms == 3 ? 2 : 1;  // hi (+ lo) tiles per operand
@@ -612,6 +617,7 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
             if (p.trace && blockIdx.x == 0 && warp == EPI_WARP0 && lane == 0 && titer < 4) p.trace[69 + titer * 2] = clock64();
             const int64_t row = (int64_t)m0 + q * 32 + lane;
             uint32_t rmn = 0xffffffffu, rmx = 0xffffffffu;  // this thread's row: f2ord(min), ~f2ord(max)
+            float rres = 0.f;                                // max |acc - I| of this thread's part of the tile
 #pragma unroll
             for (int ch = 0; ch < NCH; ++ch) {
                 const int col = egrp * EPI_COLS + ch * 32;
@@ -650,6 +656,12 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         float o = p.alpha * __uint_as_float(v[j]);
+                        if (p.resid_max && n0 + col + j < p.N) {
+                            float d = fabsf(__uint_as_float(v[j]) - (row == (int64_t)n0 + col + j ? 1.f : 0.f));
+                            if (!(d == d)) d = INFINITY;
+                            rres = fmaxf(rres, d);
+                        }
+                        if (p.diag != 0.f && row == (int64_t)n0 + col + j) o = __fadd_rn(o, p.diag);
                         if (bias && n0 + col + j < p.N) o = __fadd_rn(o, __ldg(bias + j));
                         v[j] = __float_as_uint(o);
                         if (p.rowrange && n0 + col + j < p.N) {
@@ -693,6 +705,10 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
             if (!D_TRANS && p.rowrange && row < p.M) {
                 atomicMin(p.rowrange + 2 * row, rmn);
                 atomicMin(p.rowrange + 2 * row + 1, rmx);
+            }
+            if (!D_TRANS && p.resid_max) {
+                rres = warp_max(rres);
+                if (lane == 0 && rres > 0.f) atomicMax(reinterpret_cast<unsigned int *>(p.resid_max), __float_as_uint(rres));
             }
         }
     }
@@ -982,6 +998,8 @@ int gemm_tc(const TcGemm &g, cudaStream_t st) {
     p.blend = g.blend; p.strength = g.strength; p.terms = g.terms == 3 ? 3 : 1;
     p.k_per_z = k_per_z; p.d_z_stride = g.d_z_stride;
     p.bias = g.bias; p.bias_hw = g.bias_hw > 0 ? g.bias_hw : 1; p.bias_ld = g.bias_ld;
+    p.diag = g.d_trans ? 0.f : g.diag; p.resid_max = g.d_trans ? nullptr : g.resid_max;
+    p.skip_below = g.skip_below; p.skip_tol = g.skip_tol;
     p.alpha = g.alpha; p.skip = g.skip; p.conv_a = p.terms == 3 ? 1 : 0; p.conv_b = conv_b ? 1 : 0;
     static const char *no_atmem = getenv("OPTEX_NO_A_TMEM");
     p.a_tmem = (p.conv_a && !p.conv_b && !(no_atmem && atoi(no_atmem))) ? 1 : 0;
