@@ -391,28 +391,83 @@ int ns_mm(const float *A, const float *B, float *D, int c, const float *skip_bel
     return sgemm_simt_ex(A, c, true, B, c, false, D, c, false, c, c, c, nullptr, 0.f, 1.f, o, st);
 }
 
-// Y = A^(1/2), Z = A^(-1/2) for SPD A (coupled Newton-Schulz); t0, t, yn, zn: scratch.  3 launches per iteration.
-int ns_sqrt(const float *A, float *Y, float *Z, float *t0, float *t, float *yn, float *zn, int c, const NsState &w,
-            cudaStream_t st) {
+// One Newton-Schulz chain: Y = A^(1/2), Z = A^(-1/2) for SPD A; t0, t, yn, zn: scratch
+struct NsChain {
+    const float *A;
+    float *Y, *Z, *t0, *t, *yn, *zn;
+    NsState w;
+};
+
+// Up to two independent chains in lockstep.  Per iteration: ONE batched launch for the T steps of all chains and ONE
+// for their 2 x nch update products (gemm_tc batch mode; a converged chain contributes no tiles), i.e. 2 launches
+// instead of 3 per chain; shapes outside the tensor-core path fall back to per-chain launches.
+int ns_sqrt_multi(const NsChain *ch, int nch, int c, cudaStream_t st) {
     const int64_t cc = (int64_t)c * c;
     const unsigned nb = cdiv(cc, 256);
-    launch_pdl(ns_prepare_kernel, dim3(1), dim3(1024), 0, st, A, cc, w.norm2, w.resid, NS_MAX_ITERS);
-    OPTEX_LAUNCH_CHECK("ns_prepare_kernel");
-    launch_pdl(ns_init_kernel, dim3(nb), dim3(256), 0, st, A, (const float *)w.norm2, Y, Z, c);
-    OPTEX_LAUNCH_CHECK("ns_init_kernel");
-    float *Yb[2] = {Y, yn}, *Zb[2] = {Z, zn};
+    for (int k = 0; k < nch; ++k) {
+        launch_pdl(ns_prepare_kernel, dim3(1), dim3(1024), 0, st, ch[k].A, cc, ch[k].w.norm2, ch[k].w.resid,
+                   NS_MAX_ITERS);
+        OPTEX_LAUNCH_CHECK("ns_prepare_kernel");
+        launch_pdl(ns_init_kernel, dim3(nb), dim3(256), 0, st, ch[k].A, (const float *)ch[k].w.norm2, ch[k].Y, ch[k].Z, c);
+        OPTEX_LAUNCH_CHECK("ns_init_kernel");
+    }
+    bool batched = g_want_tc() && nch >= 1 && 2 * nch <= 4;
     for (int it = 0; it < NS_MAX_ITERS; ++it) {
         const int cur = it & 1, nxt = cur ^ 1;
-        const float *skip_below = it > 0 ? w.resid + it - 1 : nullptr;
-        OPTEX_TRY(ns_t_step(Zb[cur], Yb[cur], t0, t, c, w.resid, it, st));
-        OPTEX_TRY(ns_mm(Yb[cur], t, Yb[nxt], c, skip_below, st));
-        OPTEX_TRY(ns_mm(t, Zb[cur], Zb[nxt], c, skip_below, st));
+        auto Yb = [&](int k, int i) { return i ? ch[k].yn : ch[k].Y; };
+        auto Zb = [&](int k, int i) { return i ? ch[k].zn : ch[k].Z; };
+        auto skip_of = [&](int k) -> const float * { return it > 0 ? ch[k].w.resid + it - 1 : nullptr; };
+        bool done = false;
+        if (batched) {
+            TcGemm g{};
+            g.batch = nch; g.b_mn = true; g.ldd = c; g.M = g.N = g.K = c; g.terms = g_terms();
+            g.alpha = -0.5f; g.diag = 1.5f; g.skip_tol = NS_TOL;
+            for (int k = 0; k < nch; ++k) {
+                g.A_z[k] = Zb(k, cur); g.B_z[k] = Yb(k, cur); g.D_z[k] = ch[k].t;
+                g.resid_z[k] = ch[k].w.resid + it; g.skip_z[k] = skip_of(k);
+            }
+            const int rc = gemm_tc(g, st);
+            if (rc == OPTEX_OK) done = true;
+            else if (rc != OPTEX_ENOTSUP) return rc;
+            else batched = false;
+        }
+        if (!done)
+            for (int k = 0; k < nch; ++k)
+                OPTEX_TRY(ns_t_step(Zb(k, cur), Yb(k, cur), ch[k].t0, ch[k].t, c, ch[k].w.resid, it, st));
+        done = false;
+        if (batched) {
+            TcGemm g{};
+            g.batch = 2 * nch; g.b_mn = true; g.ldd = c; g.M = g.N = g.K = c; g.terms = g_terms();
+            g.alpha = 1.f; g.skip_tol = NS_TOL;
+            for (int k = 0; k < nch; ++k) {
+                g.A_z[2 * k] = Yb(k, cur); g.B_z[2 * k] = ch[k].t; g.D_z[2 * k] = Yb(k, nxt);
+                g.A_z[2 * k + 1] = ch[k].t; g.B_z[2 * k + 1] = Zb(k, cur); g.D_z[2 * k + 1] = Zb(k, nxt);
+                g.skip_z[2 * k] = g.skip_z[2 * k + 1] = skip_of(k);
+            }
+            const int rc = gemm_tc(g, st);
+            if (rc == OPTEX_OK) done = true;
+            else if (rc != OPTEX_ENOTSUP) return rc;
+            else batched = false;
+        }
+        if (!done)
+            for (int k = 0; k < nch; ++k) {
+                OPTEX_TRY(ns_mm(Yb(k, cur), ch[k].t, Yb(k, nxt), c, skip_of(k), st));
+                OPTEX_TRY(ns_mm(ch[k].t, Zb(k, cur), Zb(k, nxt), c, skip_of(k), st));
+            }
     }
-    launch_pdl(ns_finish_kernel, dim3(nb), dim3(256), 0, st, (const float *)Yb[0], (const float *)Yb[1],
-               (const float *)Zb[0], (const float *)Zb[1], Y, Z, (const float *)w.norm2, (const float *)w.resid,
-               NS_MAX_ITERS, c);
-    OPTEX_LAUNCH_CHECK("ns_finish_kernel");
+    for (int k = 0; k < nch; ++k) {
+        launch_pdl(ns_finish_kernel, dim3(nb), dim3(256), 0, st, (const float *)ch[k].Y, (const float *)ch[k].yn,
+                   (const float *)ch[k].Z, (const float *)ch[k].zn, ch[k].Y, ch[k].Z, (const float *)ch[k].w.norm2,
+                   (const float *)ch[k].w.resid, NS_MAX_ITERS, c);
+        OPTEX_LAUNCH_CHECK("ns_finish_kernel");
+    }
     return OPTEX_OK;
+}
+
+int ns_sqrt(const float *A, float *Y, float *Z, float *t0, float *t, float *yn, float *zn, int c, const NsState &w,
+            cudaStream_t st) {
+    const NsChain ch{A, Y, Z, t0, t, yn, zn, w};
+    return ns_sqrt_multi(&ch, 1, c, st);
 }
 
 // in-place lower Cholesky factor of SPD A [c, c]
@@ -525,8 +580,7 @@ int cov_ot_step(const float *P, const float *S, const float *R, float *out, int 
             OPTEX_LAUNCH_CHECK("add_diag_kernel");
         }
         if (mode == OPTEX_MODE_CHOL) return cholesky(sig_s, c, sb);
-        if (mode == OPTEX_MODE_PCA) return ns_sqrt(sig_s, Y2, Z2, t0_b, t_b, yn_b, zn_b, c, ns_b, sb);
-        return OPTEX_OK;  // sym: the second square root needs the first one
+        return OPTEX_OK;  // pca: both square roots run as one batched chain below; sym: the second needs the first
     };
     rc_b = side_chain();
     // always join, also on an error above: the side stream must not be left forked inside a capture
@@ -540,6 +594,7 @@ int cov_ot_step(const float *P, const float *S, const float *R, float *out, int 
             OPTEX_LAUNCH_CHECK("add_diag_kernel");
         }
         if (mode == OPTEX_MODE_CHOL) return cholesky(sig_t, c, st);
+        if (mode == OPTEX_MODE_PCA) return OPTEX_OK;
         return ns_sqrt(sig_t, Y, Z, t0, t, yn, zn, c, ns_a, st);
     };
     const int rc_a = main_chain();
@@ -551,6 +606,8 @@ int cov_ot_step(const float *P, const float *S, const float *R, float *out, int 
         OPTEX_TRY(transpose_f32(sig_t, tmp, c, c, st));
         OPTEX_TRY(trsm_right(sig_s, tmp, T, c, st));
     } else if (mode == OPTEX_MODE_PCA) {  // T = Sig_s^(1/2) Sig_t^(-1/2)   histmatch.py:29-34
+        const NsChain chains[2] = {{sig_t, Y, Z, t0, t, yn, zn, ns_a}, {sig_s, Y2, Z2, t0_b, t_b, yn_b, zn_b, ns_b}};
+        OPTEX_TRY(ns_sqrt_multi(chains, 2, c, st));
         OPTEX_TRY(mm(Y2, false, Z, false, T, c, 1.f, nullptr, st));
     } else {  // sym: T = Qt^-1 (Qt Sig_s Qt)^(1/2) Qt^-1                   histmatch.py:36-42
         OPTEX_TRY(mm(Y, false, sig_s, false, tmp, c, 1.f, nullptr, st));

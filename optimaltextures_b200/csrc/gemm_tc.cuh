@@ -42,6 +42,15 @@ struct TcGemm {
     float *resid_max;
     const float *skip_below;  // device value: *skip_below < skip_tol -> the whole launch is a no-op
     float skip_tol;
+    // batch > 0: `batch` (<= 4) independent problems of the same shape in ONE launch (A K-major, B either major, no
+    // split-K / blend / bias).  A, B, D above are ignored; the operands of all problems must lie in one arena each
+    // at whole-matrix distances (the tensor maps span the arena).  resid_z / skip_z: per-problem resid_max /
+    // skip_below (a skipped problem contributes no tiles).
+    int batch;
+    const float *A_z[4], *B_z[4];
+    float *D_z[4];
+    float *resid_z[4];
+    const float *skip_z[4];
 };
 // selects which of the two library-owned hi/lo scratch buffers the calling thread's GEMMs use (pipelined callers)
 void gemm_tc_set_scratch_slot(int slot);

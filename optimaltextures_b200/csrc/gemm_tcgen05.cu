@@ -33,6 +33,7 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 32;  // K granularity of split-K slices (both stage depths divide it)
 constexpr int UMMA_K = 8;    // 32 B of K per tcgen05.mma.kind::tf32
 constexpr int MAX_STAGES = 8;
+constexpr int MAX_BATCH = 4;     // independent problems per launch (gemm_tc batch mode)
 // The epilogue (TMEM -> registers -> global) of a 128 x 256 tile took 20 k cycles with 4 warps - as long as a whole
 // plain-TF32 main loop and exposed after the last tile; EPI_GROUPS groups of 4 warps (one warp per TMEM lane quadrant)
 // split the tile's columns between them.
@@ -221,6 +222,13 @@ struct Params {
     float *resid_max;     // !D_TRANS: atomicMax of max |acc - I| over the output (acc before alpha)
     const float *skip_below;  // *skip_below < skip_tol -> no-op launch (a converged Newton-Schulz chain)
     float skip_tol;
+    // batch > 0: tiles enumerate `batch` independent problems (z) whose operands are matrices of one arena each:
+    // row offsets into the A / B tensor maps, element offset of D, per-problem residual slot and skip value
+    int batch;
+    int a_off[MAX_BATCH], b_off[MAX_BATCH];
+    int64_t d_off[MAX_BATCH];
+    float *resid_z[MAX_BATCH];
+    const float *skip_z[MAX_BATCH];
     int a_tmem;           // conv_a && !conv_b: the converters write the hi / lo halves of A to TENSOR memory
     int stages_a;         // a_tmem: depth of the raw-A shared-memory ring (p.stages is the B ring then)
 };
@@ -331,6 +339,10 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         const int64_t k_len = p.k_per_z > 0 ? (p.K - k_begin < p.k_per_z ? p.K - k_begin : p.k_per_z) : p.K;
         num_kb = (int)((k_len + BK - 1) / BK);
     };
+    // batch mode: a problem whose chain has converged contributes no tiles (every role skips them alike)
+    auto z_skipped = [&](int z) -> bool {
+        return p.batch > 0 && p.skip_z[z] != nullptr && *p.skip_z[z] < p.skip_tol;
+    };
     // which accumulator / barrier phase the i-th tile of this CTA uses
     auto acc_of = [&](int titer, int &acc, uint32_t &aph) {
         acc = a_tmem ? 0 : (titer & 1);
@@ -349,6 +361,9 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                     int64_t k_begin;
                     tile_coords(tile, m0, n0, z);
                     k_range(z, k_begin, num_kb);
+                    if (z_skipped(z)) continue;
+                    // batch mode: the problem's operands sit a_off / b_off rows into the arena the maps describe
+                    const int ao = p.batch > 0 ? p.a_off[z] : 0, bo = p.batch > 0 ? p.b_off[z] : 0;
                     for (int kb = 0; kb < num_kb; ++kb) {
                         const int k0 = (int)k_begin + kb * BK;
                         const bool tr = p.trace && blockIdx.x == 0 && tile == (int)blockIdx.x && kb < 16;
@@ -358,8 +373,8 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                             if (tr) p.trace[kb * 4 + 0] = clock64();
                             uint8_t *a_dst = a_ring + (size_t)sa * A_TILE;
                             mbar_expect_tx(&raw_bar[sa], A_TILE);
-                            if (A_MN) tma_load_3d(&tmA_hi, &raw_bar[sa], a_dst, 0, k0, m0 / 32, p.a_hint);
-                            else tma_load_2d(&tmA_hi, &raw_bar[sa], a_dst, k0, m0, p.a_hint);
+                            if (A_MN) tma_load_3d(&tmA_hi, &raw_bar[sa], a_dst, 0, k0 + ao, m0 / 32, p.a_hint);
+                            else tma_load_2d(&tmA_hi, &raw_bar[sa], a_dst, k0, m0 + ao, p.a_hint);
                             if (++sa == p.stages_a) { sa = 0; pha ^= 1; }
                             // pre-split B hi / lo -> the main ring (freed by the MMAs)
                             mbar_wait(&empty_bar[s], ph ^ 1);
@@ -367,8 +382,8 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                             mbar_expect_tx(&full_bar[s], 2 * B_TILE);
                             for (int t = 0; t < 2; ++t) {
                                 const CUtensorMap *mb = t ? &tmB_lo : &tmB_hi;
-                                if (B_MN) tma_load_3d(mb, &full_bar[s], b_dst + t * B_TILE, 0, k0, n0 / 32, p.b_hint);
-                                else tma_load_2d(mb, &full_bar[s], b_dst + t * B_TILE, k0, n0, p.b_hint);
+                                if (B_MN) tma_load_3d(mb, &full_bar[s], b_dst + t * B_TILE, 0, k0 + bo, n0 / 32, p.b_hint);
+                                else tma_load_2d(mb, &full_bar[s], b_dst + t * B_TILE, k0, n0 + bo, p.b_hint);
                             }
                             if (++s == p.stages) { s = 0; ph ^= 1; }
                             continue;
@@ -386,12 +401,12 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                             uint8_t *a_dst = st + t * A_TILE;
                             uint8_t *b_dst = st + nterm_tiles * A_TILE + t * B_TILE;
                             if (t == 0 || !p.conv_a) {
-                                if (A_MN) tma_load_3d(ma, bar, a_dst, 0, k0, m0 / 32, p.a_hint);
-                                else tma_load_2d(ma, bar, a_dst, k0, m0, p.a_hint);
+                                if (A_MN) tma_load_3d(ma, bar, a_dst, 0, k0 + ao, m0 / 32, p.a_hint);
+                                else tma_load_2d(ma, bar, a_dst, k0, m0 + ao, p.a_hint);
                             }
                             if (t == 0 || !p.conv_b) {
-                                if (B_MN) tma_load_3d(mb, bar, b_dst, 0, k0, n0 / 32, p.b_hint);
-                                else tma_load_2d(mb, bar, b_dst, k0, n0, p.b_hint);
+                                if (B_MN) tma_load_3d(mb, bar, b_dst, 0, k0 + bo, n0 / 32, p.b_hint);
+                                else tma_load_2d(mb, bar, b_dst, k0, n0 + bo, p.b_hint);
                             }
                         }
                         if (++s == p.stages) { s = 0; ph ^= 1; }
@@ -406,13 +421,14 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
             int s = 0, sta = 0;
             uint32_t ph = 0, phta = 0;
             int titer = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++titer) {
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 int m0, n0, z, num_kb, acc;
                 int64_t k_begin;
                 uint32_t aph;
                 tile_coords(tile, m0, n0, z);
                 k_range(z, k_begin, num_kb);
-                acc_of(titer, acc, aph);
+                if (z_skipped(z)) continue;
+                acc_of(titer++, acc, aph);
                 mbar_wait(&tempty_bar[acc], aph ^ 1);  // the epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
@@ -486,6 +502,7 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                 int64_t k_begin;
                 tile_coords(tile, m0, n0, z);
                 k_range(z, k_begin, num_kb);
+                if (z_skipped(z)) continue;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     const bool tr = p.trace && blockIdx.x == 0 && tile == (int)blockIdx.x && kb < 16 && ct == 0;
                     mbar_wait(&raw_bar[sa], pha);
@@ -547,6 +564,7 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                 int64_t k_begin;
                 tile_coords(tile, m0, n0, z);
                 k_range(z, k_begin, num_kb);
+                if (z_skipped(z)) continue;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&raw_bar[s], ph);
                     if (p.trace && blockIdx.x == 0 && tile == (int)blockIdx.x && kb < 16 && ct == 0) p.trace[kb * 4 + 1] = clock64();
@@ -593,15 +611,18 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         constexpr int NCH = EPI_COLS / 32;
         const bool active = egrp * EPI_COLS < BLOCK_N;
         int titer = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++titer) {
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             int m0, n0, z, acc;
             uint32_t aph;
             tile_coords(tile, m0, n0, z);
-            acc_of(titer, acc, aph);
-            float *const Dz = p.D + (int64_t)z * p.d_z_stride;
+            if (z_skipped(z)) continue;
+            const int tcur = titer++;
+            acc_of(tcur, acc, aph);
+            float *const Dz = p.D + (p.batch > 0 ? p.d_off[z] : (int64_t)z * p.d_z_stride);
+            float *const resid_max = p.batch > 0 ? p.resid_z[z] : p.resid_max;
             mbar_wait(&tfull_bar[acc], aph);
             tc_fence_after();
-            if (p.trace && blockIdx.x == 0 && warp == EPI_WARP0 && lane == 0 && titer < 4) p.trace[68 + titer * 2] = clock64();
+            if (p.trace && blockIdx.x == 0 && warp == EPI_WARP0 && lane == 0 && tcur < 4) p.trace[68 + tcur * 2] = clock64();
             // the warp's whole slice of the tile -> registers, then the accumulator goes back to the MMA warp
             uint32_t vv[NCH][32];
             if (active) {
@@ -614,7 +635,7 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-            if (p.trace && blockIdx.x == 0 && warp == EPI_WARP0 && lane == 0 && titer < 4) p.trace[69 + titer * 2] = clock64();
+            if (p.trace && blockIdx.x == 0 && warp == EPI_WARP0 && lane == 0 && tcur < 4) p.trace[69 + tcur * 2] = clock64();
             const int64_t row = (int64_t)m0 + q * 32 + lane;
             uint32_t rmn = 0xffffffffu, rmx = 0xffffffffu;  // this thread's row: f2ord(min), ~f2ord(max)
             float rres = 0.f;                                // max |acc - I| of this thread's part of the tile
@@ -656,7 +677,7 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         float o = p.alpha * __uint_as_float(v[j]);
-                        if (p.resid_max && n0 + col + j < p.N) {
+                        if (resid_max && n0 + col + j < p.N) {
                             float d = fabsf(__uint_as_float(v[j]) - (row == (int64_t)n0 + col + j ? 1.f : 0.f));
                             if (!(d == d)) d = INFINITY;
                             rres = fmaxf(rres, d);
@@ -706,9 +727,9 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                 atomicMin(p.rowrange + 2 * row, rmn);
                 atomicMin(p.rowrange + 2 * row + 1, rmx);
             }
-            if (!D_TRANS && p.resid_max) {
+            if (!D_TRANS && resid_max) {
                 rres = warp_max(rres);
-                if (lane == 0 && rres > 0.f) atomicMax(reinterpret_cast<unsigned int *>(p.resid_max), __float_as_uint(rres));
+                if (lane == 0 && rres > 0.f) atomicMax(reinterpret_cast<unsigned int *>(resid_max), __float_as_uint(rres));
             }
         }
     }
@@ -931,7 +952,60 @@ int gemm_tc_split_and_fill(const float *x, float *hi, float *lo, int64_t n, uint
     return OPTEX_OK;
 }
 
+// batch mode of gemm_tc (see TcGemm::batch)
+static int gemm_tc_batched(const TcGemm &g, cudaStream_t st) {
+    const int nb = g.batch;
+    if (nb > MAX_BATCH || g.a_mn || g.d_trans || g.blend || g.bias || g.split_k > 1 || g.ldb > 0 || g.b_col0 != 0)
+        return OPTEX_ENOTSUP;
+    if (g.K % 32 != 0 || g.N % 32 != 0 || g.ldd % 8 != 0 || g.ldd != g.N) return OPTEX_ENOTSUP;
+    const float *a0 = g.A_z[0], *b0 = g.B_z[0];
+    float *d0 = g.D_z[0];
+    for (int i = 1; i < nb; ++i) {
+        if (g.A_z[i] < a0) a0 = g.A_z[i];
+        if (g.B_z[i] < b0) b0 = g.B_z[i];
+        if (g.D_z[i] < d0) d0 = g.D_z[i];
+    }
+    if (!aligned16(a0) || !aligned16(b0) || (reinterpret_cast<uintptr_t>(d0) & 31) != 0) return OPTEX_ENOTSUP;
+    Params p{};
+    // A: [rows, K] K-major arena; B: MN-major [k rows, N] or K-major [n rows, K] arena
+    const int64_t a_row = g.K, b_row = g.b_mn ? g.N : g.K;
+    int64_t a_rows = 0, b_rows = 0;
+    for (int i = 0; i < nb; ++i) {
+        const int64_t da = g.A_z[i] - a0, db = g.B_z[i] - b0, dd = g.D_z[i] - d0;
+        if (da % a_row != 0 || db % b_row != 0 || dd % 8 != 0) return OPTEX_ENOTSUP;
+        p.a_off[i] = (int)(da / a_row);
+        p.b_off[i] = (int)(db / b_row);
+        p.d_off[i] = dd;
+        p.resid_z[i] = g.resid_z[i];
+        p.skip_z[i] = g.skip_z[i];
+        if (p.a_off[i] + g.M > a_rows) a_rows = p.a_off[i] + g.M;
+        const int64_t bext = p.b_off[i] + (g.b_mn ? g.K : g.N);
+        if (bext > b_rows) b_rows = bext;
+    }
+    if (a_rows > 0x3fffffffLL || b_rows > 0x3fffffffLL) return OPTEX_ENOTSUP;
+    const int bn = pick_block_n(g.M, g.N, nb);
+    CUtensorMap ah, bh;
+    OPTEX_TRY(make_map_kmajor(&ah, a0, a_rows, g.K, BLOCK_M, 32));
+    if (g.b_mn) OPTEX_TRY(make_map_mnmajor(&bh, b0, b_rows, g.N, bn, g.N, 32));
+    else OPTEX_TRY(make_map_kmajor(&bh, b0, b_rows, g.K, bn, 32));
+    p.D = d0; p.ldd = g.ldd; p.M = g.M; p.N = g.N; p.K = g.K;
+    p.terms = g.terms == 3 ? 3 : 1;
+    p.alpha = g.alpha; p.diag = g.diag; p.skip = g.skip; p.skip_tol = g.skip_tol;
+    // both operands are split inside the kernel (C x C problems: a pre-split pass per launch would dominate)
+    p.conv_a = p.terms == 3 ? 1 : 0; p.conv_b = p.conv_a; p.a_tmem = 0;
+    p.batch = nb; p.nz = nb;
+    p.bias_hw = 1;
+    p.a_hint = p.b_hint = L2_EVICT_NORMAL;
+    p.trace = nullptr;
+    if (!g.b_mn) return launch_n<false, false, false>(bn, ah, ah, bh, bh, p, nb, st);
+    return launch_n<false, true, false>(bn, ah, ah, bh, bh, p, nb, st);
+}
+
 int gemm_tc(const TcGemm &g, cudaStream_t st) {
+    if (g.batch > 0) {
+        if (!encode_fn() || g.M < 1 || g.N < 1 || g.K < 1) return OPTEX_ENOTSUP;
+        return gemm_tc_batched(g, st);
+    }
     if (!encode_fn() || g.M < 1 || g.N < 1 || g.K < 1 || g.M > 0x3fffffffLL || g.N > 0x3fffffffLL || g.K > 0x3fffffffLL)
         return OPTEX_ENOTSUP;
     if (!aligned16(g.A) || !aligned16(g.B) || !aligned16(g.D) || (g.blend && !aligned16(g.blend))) return OPTEX_ENOTSUP;
