@@ -147,10 +147,11 @@ static int check_step_args(const char *fn, const void *P, const void *S, const v
 // The step proper.  P may alias out (P is dead once the forward rotation has run).
 static int ot_step_impl(const float *P, const float *S, const float *R, float *out, int b_p, int64_t hw_p,
                         int b_s, int64_t hw_s, int c, int mode, float eps, const float *content, float strength,
-                        void *ws, size_t ws_bytes, cudaStream_t st) {
+                        void *ws, size_t ws_bytes, cudaStream_t st, int style_reuse = 0) {
     const int64_t n_p = (int64_t)b_p * hw_p, n_s = (int64_t)b_s * hw_s;
     if (!per_channel(mode))  // closed-form modes: rotation folded into C x C products (cov_match.cu)
-        return cov_ot_step(P, S, R, out, b_p, hw_p, b_s, hw_s, c, mode, eps, content, strength, ws, ws_bytes, st);
+        return cov_ot_step(P, S, R, out, b_p, hw_p, b_s, hw_s, c, mode, eps, content, strength, ws, ws_bytes, st,
+                           style_reuse);
     Arena ar(ws, ws_bytes);
     float *rp = ar.take<float>((size_t)n_p * c);
     float *rs = ar.take<float>((size_t)n_s * c);
@@ -433,11 +434,13 @@ extern "C" int optex_ot_loop(float *feat, const float *S, const float *R_all, in
                                  rws, rws_bytes, st);
     }
     if (per_channel(mode)) alt = nullptr;
+    // pca / sym do not depend on the rotation (cov_match.cu): no draw at all
+    const bool needs_rotation = per_channel(mode) || mode == OPTEX_MODE_CHOL;
     for (int i = 0; i < iters; ++i) {
-        const float *R;
+        const float *R = nullptr;
         if (R_all) {
             R = R_all + (size_t)i * c * c;
-        } else {
+        } else if (needs_rotation) {
             if (i % kRotChunk == 0) {
                 int nb = iters - i < kRotChunk ? iters - i : kRotChunk;
                 OPTEX_TRY(random_rotations(rbuf, c, nb, seed, first_counter + (uint64_t)i, nullptr, rws, rws_bytes, st));
@@ -448,8 +451,9 @@ extern "C" int optex_ot_loop(float *feat, const float *S, const float *R_all, in
         // P in their last GEMM, so they ping-pong between feat and alt
         float *src = (alt && (i & 1)) ? alt : feat;
         float *dst = alt ? ((i & 1) ? feat : alt) : feat;
+        // the style side of the closed-form modes (moments, pca square root) is computed by the first iteration only
         OPTEX_TRY(ot_step_impl(src, S, R, dst, b_p, hw_p, b_s, hw_s, c, mode, eps, content, content_strength, sw,
-                               step_ws, st));
+                               step_ws, st, i > 0 ? 1 : 0));
     }
     if (alt && (iters & 1))
         OPTEX_CUDA(cudaMemcpyAsync(feat, alt, sizeof(float) * (size_t)n_p * c, cudaMemcpyDeviceToDevice, st));

@@ -161,7 +161,7 @@ size_t cov_match_ws_bytes(int64_t n_t, int64_t n_s, int c, int mode);
 // the whole OT step for the covariance modes (rotation folded algebraically, see cov_match.cu); R may be null
 int cov_ot_step(const float *P, const float *S, const float *R, float *out, int b_p, int64_t hw_p, int b_s,
                 int64_t hw_s, int c, int mode, float eps, const float *content, float strength, void *workspace,
-                size_t workspace_bytes, cudaStream_t st);
+                size_t workspace_bytes, cudaStream_t st, int style_reuse = 0);
 int cov_match_nhwc(const float *target, const float *source, float *out, int b_t, int64_t hw_t, int b_s,
                    int64_t hw_s, int c, int mode, float eps, void *workspace, size_t workspace_bytes,
                    cudaStream_t st);

@@ -579,7 +579,7 @@ size_t cov_match_ws_bytes(int64_t n_t, int64_t n_s, int c, int mode) {
 // out[n, c] = (X - mu_t) G^T + mu_s with G = R T R^T (R may be null = identity); see the file header
 int cov_ot_step(const float *P, const float *S, const float *R, float *out, int b_p, int64_t hw_p, int b_s,
                 int64_t hw_s, int c, int mode, float eps, const float *content, float strength, void *workspace,
-                size_t workspace_bytes, cudaStream_t st) {
+                size_t workspace_bytes, cudaStream_t st, int style_reuse) {
     if (c > MAX_C) {
         set_error("covariance modes: c=%d > %d", c, MAX_C);
         return OPTEX_ESIZE;
@@ -609,8 +609,12 @@ int cov_ot_step(const float *P, const float *S, const float *R, float *out, int 
     const NsState ns_a{w.norm2, w.resid, w.flags};
     const NsState ns_b{w.norm2 + NS_STATE, w.resid + NS_STATE, w.flags + NS_STATE};
     // moments in the un-rotated frame; eps is added after the rotation like the reference (histmatch.py:18,22)
+    // style_reuse (the iterations of optex_ot_loop after the first: same S, same workspace): the style moments - for
+    // pca also the style square root Y2 - are still in the workspace.  With a rotation (chol) the un-rotated style
+    // covariance lives in `aux`, because the factorisation overwrites sig_s.
+    float *sig_s_src = R ? aux : sig_s;
     OPTEX_TRY(moments(P, b_p, hw_p, c, R ? 0.f : eps, w.mu_p, sig_t, w, st));
-    OPTEX_TRY(moments(S, b_s, hw_s, c, R ? 0.f : eps, w.mu_s, sig_s, w, st));
+    if (!style_reuse) OPTEX_TRY(moments(S, b_s, hw_s, c, R ? 0.f : eps, w.mu_s, sig_s_src, w, st));
     // ---- fork: the style-side chain (sandwich, factorisation) on the side stream
     SideStream *side;
     OPTEX_TRY(side_stream(&side));
@@ -620,7 +624,7 @@ int cov_ot_step(const float *P, const float *S, const float *R, float *out, int 
     int rc_b = OPTEX_OK;
     auto side_chain = [&]() -> int {
         if (R) {  // Sig_s' = R^T Sig_s R + eps I
-            OPTEX_TRY(mm(sig_s, false, R, false, tmp_b, c, 1.f, nullptr, sb));
+            OPTEX_TRY(mm(sig_s_src, false, R, false, tmp_b, c, 1.f, nullptr, sb));
             OPTEX_TRY(mm(R, true, tmp_b, false, sig_s, c, 1.f, nullptr, sb));
             launch_pdl(add_diag_kernel, dim3((unsigned)(cdiv(c, 256))), dim3(256), 0, sb, sig_s, c, eps);
             OPTEX_LAUNCH_CHECK("add_diag_kernel");
@@ -653,7 +657,7 @@ int cov_ot_step(const float *P, const float *S, const float *R, float *out, int 
         OPTEX_TRY(trsm_right(sig_s, tmp, T, c, st));
     } else if (mode == OPTEX_MODE_PCA) {  // T = Sig_s^(1/2) Sig_t^(-1/2)   histmatch.py:29-34
         const NsChain chains[2] = {{sig_t, Y, Z, t0, t, yn, zn, ns_a}, {sig_s, Y2, Z2, t0_b, t_b, yn_b, zn_b, ns_b}};
-        OPTEX_TRY(ns_sqrt_multi(chains, 2, c, st));
+        OPTEX_TRY(ns_sqrt_multi(chains, style_reuse ? 1 : 2, c, st));   // reuse: Y2 = Sig_s^(1/2) is still there
         OPTEX_TRY(mm(Y2, false, Z, false, T, c, 1.f, nullptr, st));
     } else {  // sym: T = Qt^-1 (Qt Sig_s Qt)^(1/2) Qt^-1                   histmatch.py:36-42
         OPTEX_TRY(mm(Y, false, sig_s, false, tmp, c, 1.f, nullptr, st));
@@ -691,7 +695,7 @@ int cov_match_nhwc(const float *target, const float *source, float *out, int b_t
                    int64_t hw_s, int c, int mode, float eps, void *workspace, size_t workspace_bytes,
                    cudaStream_t st) {
     return cov_ot_step(target, source, nullptr, out, b_t, hw_t, b_s, hw_s, c, mode, eps, nullptr, 0.f, workspace,
-                       workspace_bytes, st);
+                       workspace_bytes, st, 0);
 }
 
 }  // namespace optex

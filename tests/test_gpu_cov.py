@@ -114,6 +114,25 @@ def test_inner_loop_golden(ob, golden, mode):
     assert_close(got.cpu().numpy(), g[f"out_{mode}"], tol=1e-3)
 
 
+@pytest.mark.parametrize("mode", ["pca", "sym", "chol"])
+def test_loop_reuses_the_style_side(ob, mode):
+    """optex_ot_loop computes the style moments (pca: and the style square root) once and reuses them: the loop must
+    equal the same steps taken one call at a time."""
+    g = torch.Generator().manual_seed(4)
+    p = torch.relu(torch.randn(1, 24, 24, 96, generator=g)).cuda()
+    s = torch.relu(1.3 * torch.randn(1, 20, 28, 96, generator=g) + 0.2).cuda()
+    rots = ob.random_rotations(96, 4, "cuda", seed=9)
+    stepwise = p
+    for i in range(4):
+        stepwise = ob.optimal_transport(stepwise, s, mode, rotation=rots[i])
+    looped = ob.ot_loop(p, s, mode, 4, rotations=rots)
+    scale = float(stepwise.abs().max())
+    assert float((looped - stepwise).abs().max()) <= 2e-5 * scale
+    if mode != "chol":      # rotation-free modes: the loop without rotations= draws none and gives the same result
+        free = ob.ot_loop(p, s, mode, 4)
+        assert float((free - stepwise).abs().max()) <= 2e-5 * scale
+
+
 def test_batch_broadcast_rule(ob):
     """histmatch.py:44: mu_s is [c, b_s, 1, 1] - b_s must be 1 or b."""
     with pytest.raises(ValueError, match="b_s"):
