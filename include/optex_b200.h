@@ -211,6 +211,27 @@ int optex_rotate_inverse(const float *Mt, const float *R, float *out, int64_t n,
                          int c, const float *content, float content_strength,
                          void *stream);
 
+/* ---- PCA basis of a feature block (the caller either side of the inner loop) -------------------
+ * replaces: fit_pca()  optex.py:180-190  and the projections  optex.py:110 (`@ style_eigvs[l]`),
+ *           optex.py:120 (`@ style_eigvs[l].T`), optex.py:188 (`tensor @ eigvecs`)
+ * X [n, c] NHWC-flattened.  The reference's SVD of X - mean(X) (one scalar mean, optex.py:182) is computed as the
+ * eigendecomposition of the c x c Gram matrix, accumulated and diagonalised in FP64 on the device.  Outputs:
+ *   eigvecs [c, c] fp32 row-major: column j = right singular vector of the j-th largest singular value; sign
+ *                  convention: the component of largest magnitude of every column is positive (an SVD leaves
+ *                  the sign open);
+ *   sigma   [c]    fp32 singular values, descending (for n < c the trailing c - n are ~0);
+ *   k_out   [1]    int32 ON THE DEVICE: the number of leading columns the reference keeps
+ *                  (first index where cumsum(sigma / sum(sigma)) > 0.9, optex.py:184).
+ * c <= 1024.  Asynchronous like everything else: read k_out after synchronising the stream. */
+size_t optex_fit_pca_workspace_bytes(int64_t n, int c);
+int optex_fit_pca(const float *X, int64_t n, int c, float *eigvecs, float *sigma,
+                  int32_t *k_out, void *workspace, size_t workspace_bytes, void *stream);
+/* transpose = 0: out[n, k] = X[n, c] V[c, k]      (project onto the basis,  optex.py:110, :188)
+ * transpose = 1: out[n, c] = X[n, k] V[c, k]^T    (back to feature space,   optex.py:120)
+ * V dense row-major [c, k].  Tensor cores when c and k allow (k % 32 == 0, c % 4 == 0), else fp32 SIMT tiles. */
+int optex_pca_project(const float *X, const float *V, float *out, int64_t n, int c, int k,
+                      int transpose, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

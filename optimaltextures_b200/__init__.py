@@ -4,10 +4,10 @@ Host-side mirror of the reference's call surface over liboptex_b200.so (C-ABI, i
 CUDA only: importing works anywhere, every compute call needs a B200 and the built library.
 """
 from .histmatch import cdf_match, hist_match, interp, sort_match  # noqa: F401
-from .optex import (install, manual_seed, optimal_transport, optimal_transport_host, ot_loop, prepared_rotation,  # noqa: F401
+from .optex import (fit_pca, install, manual_seed, pca_project, optimal_transport, optimal_transport_host, ot_loop, prepared_rotation,  # noqa: F401
                     random_rotation, random_rotations, rotate_forward, rotate_inverse, set_gemm_mode,
                     set_rotation_precision)
 
 __all__ = ["hist_match", "cdf_match", "sort_match", "interp", "optimal_transport", "optimal_transport_host",
            "ot_loop", "random_rotation", "random_rotations", "rotate_forward", "rotate_inverse", "manual_seed", "set_gemm_mode",
-           "set_rotation_precision", "prepared_rotation", "install"]
+           "set_rotation_precision", "prepared_rotation", "install", "fit_pca", "pca_project"]

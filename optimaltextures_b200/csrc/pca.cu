@@ -1,0 +1,516 @@
+// PCA basis of a feature block - the reference's fit_pca() (optex.py:180-190) and the two projections either side
+// of the inner loop (optex.py:110 `pastiche_feature @ style_eigvs[l]`, optex.py:120 `@ style_eigvs[l].T`).
+//
+//   reference:  A = X - mean(X)  (ONE scalar mean over all elements, optex.py:182)
+//               _, sigma, V = torch.svd(A)                      (sigma descending)
+//               k = first index with cumsum(sigma / sum(sigma)) > 0.9 ;  eigvecs = V[:, :k]
+//               features = X @ eigvecs                           (the un-centred X)
+//
+// B200 formulation.  The right singular vectors of A are the eigenvectors of the C x C Gram matrix
+// G = A^T A and sigma = sqrt(lambda), so the [n, C] SVD (n up to 2.4 M rows) becomes
+//   1. column sums + raw Gram X^T X accumulated in FP64 (symmetric 64 x 64 tiles, split over the rows,
+//      deterministic reduction), centred algebraically:  G = X^T X - m (s 1^T + 1 s^T) + n m^2
+//      - in FP64 the cancellation costs nothing that fp32 outputs can see, and X is read exactly once;
+//   2. a parallel one-sided Jacobi eigensolver on G in FP64: rows w_i of W = G V^T and rows v_i of V^T are rotated
+//      pairwise until all w_i are mutually orthogonal; round-robin ordering gives C/2 independent pairs per round
+//      (one CTA each) and C-1 rounds per sweep, separated by grid-wide barriers (cooperative launch);
+//   3. lambda_i = v_i . w_i, sort, the reference's 90 % rule in fp32, sign convention, fp32 store.
+// FP64 throughout because sigma = sqrt(lambda) squares the conditioning: an fp32 Gram would leave the small singular
+// values (which all enter the 90 % rule's normaliser) with absolute errors of 1e-3 sigma_max.
+//
+// Sign convention: an SVD fixes each singular vector only up to sign (and the reference's LAPACK gives whatever it
+// gives); here the component of largest magnitude of every eigenvector is made positive.  Parity is therefore stated
+// on sigma, k, the projector V_k V_k^T and on sign-aligned columns (tests/test_gpu_pca.py).
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "common.cuh"
+#include "gemm_tc.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace optex {
+namespace {
+
+constexpr int PCA_MAX_C = 1024;
+constexpr int GT = 64;           // Gram tile edge
+constexpr int GK = 16;           // rows of X per shared-memory slab
+constexpr int SUM_SPLITS = 64;   // row splits of the column-sum pass
+constexpr int MAX_GRAM_SPLITS = 64;
+constexpr int JT = 128;          // threads per Jacobi pair
+constexpr int MAX_SWEEPS = 40;
+constexpr double JTOL = 1e-12;   // rotate while |w_p . w_q| > JTOL |w_p| |w_q|
+constexpr double JFLOOR = 1e-13; // ... and > (JFLOOR trace G)^2 (keeps null-space noise from rotating for ever)
+
+inline unsigned cdiv(int64_t a, int64_t b) { return (unsigned)((a + b - 1) / b); }
+
+// part[z][j] = sum over the rows of split z of X[r, j]
+__global__ void pca_colsum_kernel(const float *__restrict__ X, double *__restrict__ part, int64_t n, int c,
+                                  int splits) {
+    pdl_wait();
+    __shared__ double red[8][33];
+    const int ch = blockIdx.x * 32 + threadIdx.x;
+    const int split = blockIdx.y;
+    const int64_t rows = (n + splits - 1) / splits;
+    const int64_t r0 = split * rows, r1 = r0 + rows < n ? r0 + rows : n;
+    double acc = 0.0;
+    if (ch < c)
+        for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) acc += (double)X[r * c + ch];
+    red[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && ch < c) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x];
+        part[(int64_t)split * c + ch] = s;
+    }
+}
+
+// s[j] = sum_z part[z][j];  stat[0] = mean over ALL elements (optex.py:182 `tensor.mean()`), stat[1] = n
+__global__ void __launch_bounds__(1024) pca_mean_kernel(const double *__restrict__ part, int splits, int c, int64_t n,
+                                                        double *__restrict__ s, double *__restrict__ stat) {
+    pdl_wait();
+    __shared__ double red[32];
+    const int tid = threadIdx.x;
+    double v = 0.0;
+    if (tid < c) {
+        for (int z = 0; z < splits; ++z) v += part[(int64_t)z * c + tid];
+        s[tid] = v;
+    }
+    v = warp_sum(v);
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0.0;
+        for (int i = 0; i < 32; ++i) t += red[i];
+        stat[0] = t / ((double)n * (double)c);
+        stat[1] = (double)n;
+    }
+}
+
+// part[z][i][j] = sum over the rows of split z of X[r, i] X[r, j]  for the tile pairs (bi <= bj) only
+__global__ void __launch_bounds__(256) pca_gram_kernel(const float *__restrict__ X, double *__restrict__ part,
+                                                       int64_t n, int c, int T, int64_t rows_per_split) {
+    pdl_wait();
+    __shared__ double As[GK][GT], Bs[GK][GT];
+    int t = blockIdx.x, bi = 0;
+    while (t >= T - bi) {
+        t -= T - bi;
+        ++bi;
+    }
+    const int bj = bi + t;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_split;
+    const int64_t r1 = r0 + rows_per_split < n ? r0 + rows_per_split : n;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int ci = bi * GT, cj = bj * GT;
+    double acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+    float pa[4], pb[4];
+    auto fetch = [&](int64_t r) {
+        const int64_t row = r + ty;
+        const bool rok = row < r1;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int col = tx + 16 * q;
+            pa[q] = (rok && ci + col < c) ? X[row * c + ci + col] : 0.f;
+            pb[q] = (rok && cj + col < c) ? X[row * c + cj + col] : 0.f;
+        }
+    };
+    if (r0 < r1) fetch(r0);
+    for (int64_t r = r0; r < r1; r += GK) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            As[ty][tx + 16 * q] = (double)pa[q];
+            Bs[ty][tx + 16 * q] = (double)pb[q];
+        }
+        __syncthreads();
+        if (r + GK < r1) fetch(r + GK);  // next slab in flight during the FMAs
+#pragma unroll
+        for (int k = 0; k < GK; ++k) {
+            double a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[k][ty + 16 * i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx + 16 * j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    double *out = part + (int64_t)blockIdx.y * c * c;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int gi = ci + ty + 16 * i;
+        if (gi >= c) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int gj = cj + tx + 16 * j;
+            if (gj < c) out[(int64_t)gi * c + gj] = acc[i][j];
+        }
+    }
+}
+
+// G = sum_z part_z - m (s_i + s_j) + n m^2 (mirrored from the computed tile pairs);  W = G, V = I
+__global__ void pca_gram_final_kernel(const double *__restrict__ part, int nz, const double *__restrict__ s,
+                                      const double *__restrict__ stat, int c, double *__restrict__ W,
+                                      double *__restrict__ V) {
+    pdl_wait();
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)c * c) return;
+    const int i = (int)(idx / c), j = (int)(idx % c);
+    const int lo = i < j ? i : j, hi = i < j ? j : i;
+    double g = 0.0;
+    for (int z = 0; z < nz; ++z) g += part[(int64_t)z * c * c + (int64_t)lo * c + hi];
+    const double m = stat[0], n = stat[1];
+    g = g - m * (s[i] + s[j]) + n * m * m;
+    W[idx] = g;
+    V[idx] = i == j ? 1.0 : 0.0;
+}
+
+// One-sided Jacobi on the rows of W (= G V^T) and V^T; see the file header.  Cooperative launch: gridDim.x CTAs are
+// co-resident, each takes the pairs pi = blockIdx.x, blockIdx.x + gridDim.x, ... of every round.
+// Round-robin schedule of ne = c (+1 if odd) players: round r pairs (ne-1, r) and ((r+i) mod (ne-1), (r-i) mod (ne-1)).
+template <int EPT>
+__global__ void __launch_bounds__(JT) pca_jacobi_kernel(double *W, double *V, int c, int max_sweeps,
+                                                        unsigned *rot_count, int *info) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double red[2][3][JT / 32];
+    __shared__ double s_tr[JT / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double tr = 0.0;
+    for (int i = tid; i < c; i += JT) tr += __ldcg(&W[(int64_t)i * c + i]);
+    tr = warp_sum(tr);
+    if (lane == 0) s_tr[warp] = tr;
+    __syncthreads();
+    tr = 0.0;
+#pragma unroll
+    for (int i = 0; i < JT / 32; ++i) tr += s_tr[i];
+    const double floor_abs = (JFLOOR * tr) * (JFLOOR * tr);
+    const int ne = c + (c & 1), n1 = ne - 1, m = ne / 2;
+    int par = 0, sweep = 0;
+    unsigned local_rot = 0;
+    for (; sweep < max_sweeps; ++sweep) {
+        for (int r = 0; r < n1; ++r) {
+            for (int pi = blockIdx.x; pi < m; pi += gridDim.x) {
+                const int a = pi == 0 ? n1 : (r + pi) % n1;
+                const int b = pi == 0 ? r : (r - pi + n1) % n1;
+                if (a >= c || b >= c) continue;  // the dummy player of an odd c
+                double *wa = W + (int64_t)a * c, *wb = W + (int64_t)b * c;
+                double *va = V + (int64_t)a * c, *vb = V + (int64_t)b * c;
+                double wp[EPT], wq[EPT], vp[EPT], vq[EPT];
+                double al = 0.0, be = 0.0, ga = 0.0;
+#pragma unroll
+                for (int e = 0; e < EPT; ++e) {
+                    const int i = tid + JT * e;
+                    const bool ok = i < c;
+                    wp[e] = ok ? __ldcg(wa + i) : 0.0;
+                    wq[e] = ok ? __ldcg(wb + i) : 0.0;
+                    vp[e] = ok ? __ldcg(va + i) : 0.0;
+                    vq[e] = ok ? __ldcg(vb + i) : 0.0;
+                }
+#pragma unroll
+                for (int e = 0; e < EPT; ++e) {
+                    al = fma(wp[e], wp[e], al);
+                    be = fma(wq[e], wq[e], be);
+                    ga = fma(wp[e], wq[e], ga);
+                }
+                al = warp_sum(al);
+                be = warp_sum(be);
+                ga = warp_sum(ga);
+                if (lane == 0) {
+                    red[par][0][warp] = al;
+                    red[par][1][warp] = be;
+                    red[par][2][warp] = ga;
+                }
+                __syncthreads();
+                al = be = ga = 0.0;
+#pragma unroll
+                for (int i = 0; i < JT / 32; ++i) {
+                    al += red[par][0][i];
+                    be += red[par][1][i];
+                    ga += red[par][2][i];
+                }
+                par ^= 1;
+                if (ga * ga > JTOL * JTOL * al * be && fabs(ga) > floor_abs) {
+                    const double zeta = (be - al) / (2.0 * ga);
+                    const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                    const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+#pragma unroll
+                    for (int e = 0; e < EPT; ++e) {
+                        const int i = tid + JT * e;
+                        if (i < c) {
+                            __stcg(wa + i, cs * wp[e] - sn * wq[e]);
+                            __stcg(wb + i, sn * wp[e] + cs * wq[e]);
+                            __stcg(va + i, cs * vp[e] - sn * vq[e]);
+                            __stcg(vb + i, sn * vp[e] + cs * vq[e]);
+                        }
+                    }
+                    ++local_rot;
+                }
+            }
+            if (r == n1 - 1 && tid == 0 && local_rot) atomicAdd(&rot_count[sweep], local_rot);
+            grid.sync();
+        }
+        local_rot = 0;
+        if (__ldcg(&rot_count[sweep]) == 0u) break;  // a whole sweep without a rotation: converged
+    }
+    if (blockIdx.x == 0 && tid == 0) info[0] = sweep < max_sweeps ? sweep + 1 : max_sweeps;
+}
+
+// lambda_i = v_i . w_i, descending order, sigma = sqrt(lambda), the 90 % rule (optex.py:184), sign convention
+__global__ void __launch_bounds__(1024) pca_finish_kernel(const double *__restrict__ W, const double *__restrict__ V,
+                                                          int c, float *__restrict__ sigma, int32_t *__restrict__ k_out,
+                                                          int *__restrict__ perm, float *__restrict__ sign) {
+    pdl_wait();
+    __shared__ double lam[PCA_MAX_C];
+    __shared__ float sg[PCA_MAX_C];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = warp; i < c; i += 32) {
+        const double *w = W + (int64_t)i * c, *v = V + (int64_t)i * c;
+        double vw = 0.0, vv = 0.0, best = -1.0;
+        int besti = 0;
+        for (int k = lane; k < c; k += 32) {
+            const double x = v[k];
+            vw = fma(x, w[k], vw);
+            vv = fma(x, x, vv);
+            if (fabs(x) > best) {
+                best = fabs(x);
+                besti = k;
+            }
+        }
+        vw = warp_sum(vw);
+        vv = warp_sum(vv);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+            if (ob > best || (ob == best && oi < besti)) {
+                best = ob;
+                besti = oi;
+            }
+        }
+        if (lane == 0) {
+            lam[i] = vv > 0.0 ? vw / vv : 0.0;
+            sign[i] = v[besti] < 0.0 ? -1.f : 1.f;
+        }
+    }
+    if (tid < c) perm[tid] = tid;
+    __syncthreads();
+    if (tid < c) {
+        const double mine = lam[tid];
+        int rank = 0;
+        for (int j = 0; j < c; ++j) {
+            const double o = lam[j];
+            rank += (o > mine || (o == mine && j < tid)) ? 1 : 0;
+        }
+        perm[rank] = tid;
+        sg[rank] = (float)sqrt(mine > 0.0 ? mine : 0.0);
+    }
+    __syncthreads();
+    if (tid < c) sigma[tid] = sg[tid];
+    if (tid == 0) {
+        // optex.py:184: k = (cumsum(sigma / sum(sigma)) > 0.9).max(0).indices - the FIRST index over 0.9 (so the
+        // component that crosses the threshold is itself dropped), 0 when nothing crosses; all in fp32
+        float total = 0.f;
+        for (int i = 0; i < c; ++i) total = __fadd_rn(total, sg[i]);
+        float cum = 0.f;
+        int k = 0;
+        for (int i = 0; i < c; ++i) {
+            cum = __fadd_rn(cum, __fdiv_rn(sg[i], total));
+            if (cum > 0.9f) {
+                k = i;
+                break;
+            }
+        }
+        k_out[0] = k;
+    }
+}
+
+// eigvecs[r][j] = sign * V[perm[j]][r]  (fp32; column j = j-th principal direction)
+__global__ void pca_vecs_kernel(const double *__restrict__ V, const int *__restrict__ perm,
+                                const float *__restrict__ sign, int c, float *__restrict__ eigvecs) {
+    pdl_wait();
+    __shared__ float tile[32][33];
+    const int j0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int jj = threadIdx.y; jj < 32; jj += 8) {
+        const int j = j0 + jj, r = r0 + threadIdx.x;
+        float v = 0.f;
+        if (j < c && r < c) {
+            const int src = perm[j];
+            v = (float)((double)sign[src] * V[(int64_t)src * c + r]);
+        }
+        tile[jj][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int rr = threadIdx.y; rr < 32; rr += 8) {
+        const int r = r0 + rr, j = j0 + threadIdx.x;
+        if (r < c && j < c) eigvecs[(int64_t)r * c + j] = tile[threadIdx.x][rr];
+    }
+}
+
+struct PcaWs {
+    double *colpart, *s, *stat, *gpart, *W, *V;
+    unsigned *rot;
+    int *info, *perm;
+    float *sign;
+};
+
+int gram_splits(int64_t n, int c) {
+    const int T = (c + GT - 1) / GT;
+    const int pairs = T * (T + 1) / 2;
+    int64_t splits = (4 * 148 + pairs - 1) / pairs;
+    if (splits > MAX_GRAM_SPLITS) splits = MAX_GRAM_SPLITS;
+    const int64_t by_rows = n / 256 < 1 ? 1 : n / 256;
+    if (splits > by_rows) splits = by_rows;
+    return (int)splits;
+}
+
+size_t pca_layout(int64_t n, int c, PcaWs *w, void *base, size_t cap, bool *ok) {
+    Arena ar(base, cap);
+    const size_t cc = (size_t)c * c;
+    PcaWs l{};
+    l.colpart = ar.take<double>((size_t)SUM_SPLITS * c);
+    l.s = ar.take<double>(c);
+    l.stat = ar.take<double>(8);
+    l.gpart = ar.take<double>((size_t)gram_splits(n, c) * cc);
+    l.W = ar.take<double>(cc);
+    l.V = ar.take<double>(cc);
+    l.rot = ar.take<unsigned>(MAX_SWEEPS + 8);
+    l.info = ar.take<int>(8);
+    l.perm = ar.take<int>(c);
+    l.sign = ar.take<float>(c);
+    if (w) *w = l;
+    if (ok) *ok = ar.ok();
+    return ar.off;
+}
+
+template <int EPT>
+int launch_jacobi(const PcaWs &w, int c, cudaStream_t st) {
+    int per_sm = 0;
+    OPTEX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pca_jacobi_kernel<EPT>, JT, 0));
+    if (per_sm < 1) {
+        set_error("optex_fit_pca: the Jacobi kernel does not fit on an SM");
+        return OPTEX_ECUDA;
+    }
+    const int pairs = (c + 1) / 2;
+    int grid = per_sm * sm_count();
+    if (grid > pairs) grid = pairs;
+    if (grid < 1) grid = 1;
+    double *W = w.W, *V = w.V;
+    int cc = c, ms = MAX_SWEEPS;
+    unsigned *rot = w.rot;
+    int *info = w.info;
+    void *args[] = {&W, &V, &cc, &ms, &rot, &info};
+    OPTEX_CUDA(cudaLaunchCooperativeKernel((const void *)pca_jacobi_kernel<EPT>, dim3(grid), dim3(JT), args, 0, st));
+    count_launch();
+    return OPTEX_OK;
+}
+
+}  // namespace
+}  // namespace optex
+
+using namespace optex;
+
+extern "C" size_t optex_fit_pca_workspace_bytes(int64_t n, int c) {
+    if (n < 1 || c < 1 || c > PCA_MAX_C) return 0;
+    return align_up(pca_layout(n, c, nullptr, nullptr, 0, nullptr), 256);
+}
+
+extern "C" int optex_fit_pca(const float *X, int64_t n, int c, float *eigvecs, float *sigma, int32_t *k_out,
+                             void *workspace, size_t workspace_bytes, void *stream) {
+    OPTEX_TRY(require_sm100());
+    if (!X || !eigvecs || !sigma || !k_out || n < 1 || c < 1) {
+        set_error("optex_fit_pca: NULL pointer or empty shape");
+        return OPTEX_EINVAL;
+    }
+    if (c > PCA_MAX_C) {
+        set_error("optex_fit_pca: c = %d exceeds %d channels", c, PCA_MAX_C);
+        return OPTEX_ESIZE;
+    }
+    PcaWs w;
+    bool ok = false;
+    pca_layout(n, c, &w, workspace, workspace_bytes, &ok);
+    if (!workspace || !ok) {
+        set_error("optex_fit_pca: workspace %zu < %zu bytes", workspace_bytes, optex_fit_pca_workspace_bytes(n, c));
+        return OPTEX_EWORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int splits = (int)(n < SUM_SPLITS ? n : SUM_SPLITS);
+    launch_pdl(pca_colsum_kernel, dim3(cdiv(c, 32), splits), dim3(32, 8), 0, st, X, w.colpart, n, c, splits);
+    OPTEX_LAUNCH_CHECK("pca_colsum_kernel");
+    launch_pdl(pca_mean_kernel, dim3(1), dim3(1024), 0, st, (const double *)w.colpart, splits, c, n, w.s, w.stat);
+    OPTEX_LAUNCH_CHECK("pca_mean_kernel");
+    const int T = (c + GT - 1) / GT;
+    int gs = gram_splits(n, c);
+    int64_t rows = ((n + gs - 1) / gs + GK - 1) / GK * GK;
+    gs = (int)((n + rows - 1) / rows);
+    launch_pdl(pca_gram_kernel, dim3(T * (T + 1) / 2, gs), dim3(256), 0, st, X, w.gpart, n, c, T, rows);
+    OPTEX_LAUNCH_CHECK("pca_gram_kernel");
+    launch_pdl(pca_gram_final_kernel, dim3(cdiv((int64_t)c * c, 256)), dim3(256), 0, st, (const double *)w.gpart, gs,
+               (const double *)w.s, (const double *)w.stat, c, w.W, w.V);
+    OPTEX_LAUNCH_CHECK("pca_gram_final_kernel");
+    OPTEX_CUDA(cudaMemsetAsync(w.rot, 0, sizeof(unsigned) * (MAX_SWEEPS + 8), st));
+    if (c <= JT)
+        OPTEX_TRY(launch_jacobi<1>(w, c, st));
+    else if (c <= 2 * JT)
+        OPTEX_TRY(launch_jacobi<2>(w, c, st));
+    else if (c <= 4 * JT)
+        OPTEX_TRY(launch_jacobi<4>(w, c, st));
+    else
+        OPTEX_TRY(launch_jacobi<8>(w, c, st));
+    pca_finish_kernel<<<1, 1024, 0, st>>>(w.W, w.V, c, sigma, k_out, w.perm, w.sign);
+    OPTEX_LAUNCH_CHECK("pca_finish_kernel");
+    launch_pdl(pca_vecs_kernel, dim3(cdiv(c, 32), cdiv(c, 32)), dim3(32, 8), 0, st, (const double *)w.V,
+               (const int *)w.perm, (const float *)w.sign, c, eigvecs);
+    OPTEX_LAUNCH_CHECK("pca_vecs_kernel");
+    return OPTEX_OK;
+}
+
+// out[n, k] = X[n, c] V[c, k]            (transpose = 0;  optex.py:110, :188)
+// out[n, c] = F[n, k] V[c, k]^T          (transpose = 1;  optex.py:120)
+extern "C" int optex_pca_project(const float *X, const float *V, float *out, int64_t n, int c, int k, int transpose,
+                                 void *stream) {
+    OPTEX_TRY(require_sm100());
+    if (!X || !V || !out || n < 1 || c < 1 || k < 1) {
+        set_error("optex_pca_project: NULL pointer or empty shape");
+        return OPTEX_EINVAL;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int mode = optex_get_gemm_mode();
+    if (mode != OPTEX_GEMM_FP32) {
+        TcGemm g{};
+        g.A = X;
+        g.a_mn = false;
+        g.B = V;
+        g.D = out;
+        g.M = n;
+        g.alpha = 1.f;
+        g.terms = mode == OPTEX_GEMM_TF32 ? 1 : 3;
+        if (!transpose) {
+            g.b_mn = true;  // V row-major [K = c, N = k]
+            g.N = k;
+            g.K = c;
+            g.ldd = k;
+        } else {
+            g.b_mn = false;  // V row-major [N = c, K = k]
+            g.N = c;
+            g.K = k;
+            g.ldd = c;
+        }
+        int rc = gemm_tc(g, st);
+        if (rc != OPTEX_ENOTSUP) return rc;
+        if (mode == OPTEX_GEMM_TF32X3 || mode == OPTEX_GEMM_TF32) {
+            set_error("optex_pca_project: shape (n=%lld, c=%d, k=%d) is outside the tensor-core path's TMA constraints; "
+                      "use gemm mode auto or fp32", (long long)n, c, k);
+            return OPTEX_ESIZE;
+        }
+    }
+    if (!transpose) return sgemm_simt(X, c, true, V, k, false, out, k, false, n, k, c, nullptr, 0.f, 1.f, st);
+    return sgemm_simt(X, k, true, V, k, true, out, c, false, n, c, k, nullptr, 0.f, 1.f, st);
+}

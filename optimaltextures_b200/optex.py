@@ -3,6 +3,8 @@
     optimal_transport(pastiche_feature, style_feature, hist_mode)   optex.py:167-177
     random_rotation(N, device, impl)                                optex.py:142-164
     ot_loop(...)                                                    optex.py:112-117 (the inner loop)
+    fit_pca(tensor)                                                 optex.py:180-190
+    pca_project(x, eigvecs, transpose)                              optex.py:110, :120 (the `@ style_eigvs[l]` pair)
 
 Additive keyword arguments (the reference draws its rotation internally from numpy's global RNG,
 which makes value parity impossible): ``rotation=`` injects the matrix, ``content=`` /
@@ -267,6 +269,60 @@ def rotate_inverse(mt: Tensor, rotation: Tensor, content: Optional[Tensor] = Non
     return out
 
 
+def pca_project(x: Tensor, eigvecs: Tensor, transpose: bool = False) -> Tensor:
+    """`x @ eigvecs` (optex.py:110, :188) or, with transpose=True, `x @ eigvecs.T` (optex.py:120) on the B200 GEMMs.
+    x [..., c] (or [..., k] for the transpose), eigvecs [c, k]."""
+    dev = require_cuda(x, eigvecs)
+    v = f32c(eigvecs)
+    if v.dim() != 2:
+        raise ValueError(f"eigvecs must be [c, k], got {tuple(v.shape)}")
+    c, k = v.shape
+    xin = f32c(x)
+    cin, cout = (k, c) if transpose else (c, k)
+    if xin.shape[-1] != cin:
+        raise ValueError(f"last dimension {xin.shape[-1]} does not match eigvecs {tuple(v.shape)}"
+                         f"{' (transposed)' if transpose else ''}")
+    n = xin.numel() // max(cin, 1)
+    out = torch.empty(*xin.shape[:-1], cout, dtype=torch.float32, device=dev)
+    if n == 0 or k == 0 or c == 0:
+        return out.zero_().to(x.dtype)      # an empty basis projects to nothing / back to zeros, like torch's `@`
+    with torch.cuda.device(dev):
+        call("optex_pca_project", ptr(xin), ptr(v), ptr(out), n, c, k, 1 if transpose else 0, stream_ptr(dev))
+    return out.to(x.dtype)
+
+
+def fit_pca(tensor: Tensor, *, round_k_to: int = 1, return_sigma: bool = False):
+    """reference: optex.py:180-190.  Returns (features, eigvecs) = (tensor @ V[:, :k], V[:, :k]).
+
+    The reference's `torch.svd(tensor - tensor.mean())` is computed on the device as the FP64 eigendecomposition of
+    the c x c Gram matrix (csrc/pca.cu).  k follows the reference's 90 % rule (optex.py:184); reading it is the one
+    host synchronisation of the call (the reference has the same one: it slices by a tensor index).
+    An SVD leaves the sign of every singular vector open: here the largest-magnitude component of each column of
+    `eigvecs` is positive.
+
+    round_k_to (additive): round k UP to a multiple (e.g. 32, which keeps the PCA'd channel count on the
+    tensor-core path of the OT step); the extra components only add explained variance."""
+    dev = require_cuda(tensor)
+    c = tensor.shape[-1]
+    x = f32c(tensor).reshape(-1, c)
+    n = x.shape[0]
+    lib = _lib.lib()
+    vecs = torch.empty(c, c, dtype=torch.float32, device=dev)
+    sigma = torch.empty(c, dtype=torch.float32, device=dev)
+    k_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+    wsb = workspace(dev, lib.optex_fit_pca_workspace_bytes(n, c))
+    with torch.cuda.device(dev):
+        call("optex_fit_pca", ptr(x), n, c, ptr(vecs), ptr(sigma), ptr(k_dev), ptr(wsb), wsb.numel(), stream_ptr(dev))
+    k = int(k_dev.item())
+    if round_k_to > 1:
+        k = min(c, -(-k // round_k_to) * round_k_to)
+    eigvecs = vecs[:, :k].contiguous()
+    features = pca_project(tensor, eigvecs)
+    if return_sigma:
+        return features, eigvecs, sigma
+    return features, eigvecs
+
+
 def install(reference_optex_module) -> None:
     """Rebind a loaded reference ``optex`` module to the B200 path.  Both names must be patched:
     ``optex`` did `from histmatch import hist_match` (optex.py:9), so patching ``histmatch`` alone
@@ -274,3 +330,4 @@ def install(reference_optex_module) -> None:
     reference_optex_module.optimal_transport = optimal_transport
     reference_optex_module.hist_match = _histmatch.hist_match
     reference_optex_module.random_rotation = random_rotation
+    reference_optex_module.fit_pca = fit_pca
