@@ -232,6 +232,27 @@ int optex_fit_pca(const float *X, int64_t n, int c, float *eigvecs, float *sigma
 int optex_pca_project(const float *X, const float *V, float *out, int64_t n, int c, int k,
                       int transpose, void *stream);
 
+/* ---- VGG-19 encoder / feature-inverter layers ----------------------------------------------------
+ * replaces: the nn.Sequential stacks of vgg.py:14-136 behind Encoder.forward (vgg.py:152-153, called at
+ *           optex.py:62-63,107) and Decoder.forward (vgg.py:170-171, called at optex.py:122), one layer per call:
+ *   dst[b, h, w, c_out] = [relu]( conv3x3( reflection_pad1( pre_op(src) ) ) + bias )
+ * pre_op: OPTEX_PRE_NONE | OPTEX_PRE_MAXPOOL2 (MaxPool2d(2, 2, ceil_mode=True): h = ceil(h_src / 2)) |
+ *         OPTEX_PRE_UPSAMPLE2 (UpsamplingNearest2d(2): h = 2 h_src); neither is materialised.
+ * src: NHWC [b, h_src, w_src, c_in] (or the NCHW image when src_nchw != 0).  dst: NHWC with row pitch ldd >= c_out.
+ * weight: [c_out, kp] row-major, kp = optex_conv3x3_packed_k(c_in) = 9 c_in rounded up to 32, element
+ *         [co, (ky * 3 + kx) * c_in + ci] = torch weight [co, ci, ky, kx], the padding columns zero.
+ * bias: [c_out] or NULL.  Arithmetic: the library's GEMM mode (3xTF32 by default).  h, w >= 2 after the pre-op. */
+#define OPTEX_PRE_NONE 0
+#define OPTEX_PRE_MAXPOOL2 1
+#define OPTEX_PRE_UPSAMPLE2 2
+int optex_conv3x3_packed_k(int c_in);
+size_t optex_conv3x3_workspace_bytes(int b, int h_src, int w_src, int c_in, int c_out, int pre_op);
+int optex_conv3x3(const float *src, int src_nchw, int b, int h_src, int w_src, int c_in,
+                  const float *weight, const float *bias, int c_out, int pre_op, int relu,
+                  float *dst, int64_t ldd, void *workspace, size_t workspace_bytes, void *stream);
+/* dst[b, c, hw] = src[b, hw, 0:c], src row pitch c_src >= c  (the decoder's image output, vgg.py:171 is NCHW) */
+int optex_nhwc_to_nchw(const float *src, float *dst, int b, int64_t hw, int c_src, int c, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

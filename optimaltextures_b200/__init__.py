@@ -3,6 +3,7 @@
 Host-side mirror of the reference's call surface over liboptex_b200.so (C-ABI, include/optex_b200.h).
 CUDA only: importing works anywhere, every compute call needs a B200 and the built library.
 """
+from . import vgg  # noqa: F401
 from .histmatch import cdf_match, hist_match, interp, sort_match  # noqa: F401
 from .optex import (fit_pca, install, manual_seed, pca_project, optimal_transport, optimal_transport_host, ot_loop, prepared_rotation,  # noqa: F401
                     random_rotation, random_rotations, rotate_forward, rotate_inverse, set_gemm_mode,

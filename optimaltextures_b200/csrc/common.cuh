@@ -131,6 +131,7 @@ struct SimtOpts {
     const int *skip = nullptr;    // device flag: non-zero -> no-op
     const float *skip_below = nullptr;  // device value: *skip_below < skip_tol -> no-op
     float skip_tol = 0.f;
+    bool relu = false;            // max(., 0) after bias / accumulate (conv layers)
 };
 int sgemm_simt_ex(const float *A, int64_t lda, bool a_kmajor, const float *B, int64_t ldb, bool b_kmajor, float *D,
                   int64_t ldd, bool d_trans, int64_t M, int64_t N, int64_t K, const float *blend, float strength,

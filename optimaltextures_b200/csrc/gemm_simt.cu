@@ -67,6 +67,7 @@ struct SimtExtra {
     const int *skip;
     const float *skip_below;  // *skip_below < skip_tol -> no-op
     float skip_tol;
+    int relu;
 };
 
 template <bool A_KMAJOR, bool B_KMAJOR, bool D_TRANS>
@@ -149,6 +150,7 @@ sgemm_kernel(const float *__restrict__ A, int64_t lda, const float *__restrict__
                     if (n + j < N) {
                         if (ex.bias) v[j] = __fadd_rn(v[j], __ldg(ex.bias + (m / ex.bias_hw) * ex.bias_ld + n + j));
                         if (ex.accumulate) v[j] += dp[j];
+                        if (ex.relu) v[j] = v[j] < 0.f ? 0.f : v[j];
                     }
                 }
                 if (d_vec && n + 4 <= N) {
@@ -234,7 +236,7 @@ int sgemm_simt_ex(const float *A, int64_t lda, bool a_kmajor, const float *B, in
     SimtExtra ex{};
     ex.bias = o.bias; ex.bias_hw = o.bias_hw > 0 ? o.bias_hw : 1; ex.bias_ld = o.bias_ld;
     ex.accumulate = o.accumulate ? 1 : 0; ex.skip = o.skip; ex.d_z_stride = o.d_z_stride;
-    ex.skip_below = o.skip_below; ex.skip_tol = o.skip_tol;
+    ex.skip_below = o.skip_below; ex.skip_tol = o.skip_tol; ex.relu = o.relu ? 1 : 0;
     int nz = 1;
     if (o.split_k > 1) {
         ex.k_per_z = ((K + o.split_k - 1) / o.split_k + BK - 1) / BK * BK;

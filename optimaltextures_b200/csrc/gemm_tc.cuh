@@ -42,6 +42,7 @@ struct TcGemm {
     float *resid_max;
     const float *skip_below;  // device value: *skip_below < skip_tol -> the whole launch is a no-op
     float skip_tol;
+    bool relu;  // max(., 0) after the bias (not with d_trans)
     // batch > 0: `batch` (<= 4) independent problems of the same shape in ONE launch (A K-major, B either major, no
     // split-K / blend / bias).  A, B, D above are ignored; the operands of all problems must lie in one arena each
     // at whole-matrix distances (the tensor maps span the arena).  resid_z / skip_z: per-problem resid_max /

@@ -222,6 +222,7 @@ struct Params {
     float *resid_max;     // !D_TRANS: atomicMax of max |acc - I| over the output (acc before alpha)
     const float *skip_below;  // *skip_below < skip_tol -> no-op launch (a converged Newton-Schulz chain)
     float skip_tol;
+    int relu;             // !D_TRANS: max(., 0) after the bias (conv layers, vgg.py)
     // batch > 0: tiles enumerate `batch` independent problems (z) whose operands are matrices of one arena each:
     // row offsets into the A / B tensor maps, element offset of D, per-problem residual slot and skip value
     int batch;
@@ -684,6 +685,7 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                         }
                         if (p.diag != 0.f && row == (int64_t)n0 + col + j) o = __fadd_rn(o, p.diag);
                         if (bias && n0 + col + j < p.N) o = __fadd_rn(o, __ldg(bias + j));
+                        if (p.relu) o = o < 0.f ? 0.f : o;
                         v[j] = __float_as_uint(o);
                         if (p.rowrange && n0 + col + j < p.N) {
                             const uint32_t u = f2ord(o);
@@ -1073,7 +1075,7 @@ int gemm_tc(const TcGemm &g, cudaStream_t st) {
     p.k_per_z = k_per_z; p.d_z_stride = g.d_z_stride;
     p.bias = g.bias; p.bias_hw = g.bias_hw > 0 ? g.bias_hw : 1; p.bias_ld = g.bias_ld;
     p.diag = g.d_trans ? 0.f : g.diag; p.resid_max = g.d_trans ? nullptr : g.resid_max;
-    p.skip_below = g.skip_below; p.skip_tol = g.skip_tol;
+    p.skip_below = g.skip_below; p.skip_tol = g.skip_tol; p.relu = (g.relu && !g.d_trans) ? 1 : 0;
     p.alpha = g.alpha; p.skip = g.skip; p.conv_a = p.terms == 3 ? 1 : 0; p.conv_b = conv_b ? 1 : 0;
     static const char *no_atmem = getenv("OPTEX_NO_A_TMEM");
     p.a_tmem = (p.conv_a && !p.conv_b && !(no_atmem && atoi(no_atmem))) ? 1 : 0;

@@ -49,6 +49,20 @@ def features(seed, shape_t, shape_s, quant=False):
     return t, s
 
 
+def write_vgg_golden():
+    """vgg.Encoder / vgg.Decoder of the reference with its own .pth weights (vgg.py:138-171) on a small image."""
+    import vgg  # noqa: E402  (reference module, sys.path set by import_reference)
+
+    x = torch.rand(2, 3, 21, 30, generator=torch.Generator().manual_seed(7))
+    out = {"x": x.numpy()}
+    with torch.inference_mode():
+        for d in (1, 2, 3):
+            f = vgg.Encoder(d)(x)
+            out[f"enc{d}"] = f.numpy()
+            out[f"dec{d}"] = vgg.Decoder(d)(f).numpy()
+    np.savez_compressed(os.path.join(OUT, "vgg.npz"), **out)
+
+
 def main():
     histmatch, optex, util = import_reference()
     from scipy.stats import special_ortho_group
@@ -133,6 +147,7 @@ def main():
         misc[f"sched_{size}_{iters}_{passes}_iters"] = np.asarray(its)
         misc[f"sched_{size}_{iters}_{passes}_sizes"] = np.asarray(sizes)
     np.savez_compressed(os.path.join(OUT, "misc.npz"), **misc)
+    write_vgg_golden()
     print("wrote", sorted(os.listdir(OUT)))
 
 
