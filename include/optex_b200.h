@@ -253,6 +253,34 @@ int optex_conv3x3(const float *src, int src_nchw, int b, int h_src, int w_src, i
 /* dst[b, c, hw] = src[b, hw, 0:c], src row pitch c_src >= c  (the decoder's image output, vgg.py:171 is NCHW) */
 int optex_nhwc_to_nchw(const float *src, float *dst, int b, int64_t hw, int c_src, int c, void *stream);
 
+/* ---- image-space glue of one synthesis pass -------------------------------------------------
+ * replaces: resize()  util.py:105-106 = interpolate(x, size, mode="bicubic", align_corners=False, antialias=True),
+ *           called at optex.py:48,51,56 (multires re-scaling of styles / content / pastiche between passes).
+ * src [planes, h_in, w_in] -> dst [planes, h_out, w_out], planes = b * c of an NCHW tensor.  Separable, width
+ * first; window and weights as torch computes them (cubic a = -0.5, support widened by the scale when shrinking). */
+size_t optex_resize_workspace_bytes(int planes, int h_in, int w_in, int h_out, int w_out);
+int optex_resize_bicubic_aa(const float *src, float *dst, int planes, int h_in, int w_in, int h_out,
+                            int w_out, void *workspace, size_t workspace_bytes, void *stream);
+/* replaces: kornia.color.hls.rgb_to_hls / hls_to_rgb as used by the colour transfer, optex.py:126-128.
+ * NCHW [b, 3, hw] fp32; H in radians [0, 2 pi), L and S in [0, 1]; undefined hue / saturation (grey) -> 0.
+ * kornia is not vendored by the reference and absent from the build image: parity UNPINNED (oracle restates the
+ * published formulas).  optex_lightness_transfer = hls_to_rgb(H(content), L(pastiche), S(content)) in one pass. */
+int optex_rgb_to_hls(const float *rgb, float *hls, int b, int64_t hw, void *stream);
+int optex_hls_to_rgb(const float *hls, float *rgb, int b, int64_t hw, void *stream);
+int optex_lightness_transfer(const float *content, const float *pastiche, float *out, int b, int64_t hw,
+                             void *stream);
+/* replaces: the per-layer body of mix_style_features()  optex.py:197-204 (the two hist_match calls are
+ * optex_hist_match):  out = (A (1-a) + AtoB a) m + (BtoA (1-a) + B a) (1-m),  m = mask [mask_h, mask_w] resized
+ * to [h, w] with interpolate(mode="nearest").  A, B, AtoB, BtoA, out: [h, w, c]. */
+int optex_mix_features(const float *A, const float *B, const float *AtoB, const float *BtoA,
+                       const float *mask, float *out, int h, int w, int c, int mask_h, int mask_w,
+                       float alpha, void *stream);
+/* replaces: optex.py:76  content_feature - content_feature.mean() + torch.mean(style_features[l])
+ * (scalar means over the whole tensors, accumulated in FP64, deterministic). */
+size_t optex_recentre_workspace_bytes(void);
+int optex_recentre(const float *content, int64_t n_content, const float *style, int64_t n_style,
+                   float *out, void *workspace, size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

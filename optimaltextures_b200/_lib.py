@@ -63,6 +63,14 @@ SIGNATURES = {
     "optex_conv3x3_workspace_bytes": (_z, [_i, _i, _i, _i, _i, _i]),
     "optex_conv3x3": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _i, _i, _i, _p, _l, _p, _z, _p]),
     "optex_nhwc_to_nchw": (_i, [_p, _p, _i, _l, _i, _i, _p]),
+    "optex_resize_workspace_bytes": (_z, [_i, _i, _i, _i, _i]),
+    "optex_resize_bicubic_aa": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _z, _p]),
+    "optex_rgb_to_hls": (_i, [_p, _p, _i, _l, _p]),
+    "optex_hls_to_rgb": (_i, [_p, _p, _i, _l, _p]),
+    "optex_lightness_transfer": (_i, [_p, _p, _p, _i, _l, _p]),
+    "optex_mix_features": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _p]),
+    "optex_recentre_workspace_bytes": (_z, []),
+    "optex_recentre": (_i, [_p, _l, _p, _l, _p, _p, _z, _p]),
 }
 
 _lib = None

@@ -331,3 +331,9 @@ def install(reference_optex_module) -> None:
     reference_optex_module.hist_match = _histmatch.hist_match
     reference_optex_module.random_rotation = random_rotation
     reference_optex_module.fit_pca = fit_pca
+    from . import texture as _texture, util as _util, vgg as _vgg          # late: texture imports this module
+
+    reference_optex_module.mix_style_features = _texture.mix_style_features
+    reference_optex_module.resize = _util.resize                          # optex.py:10 `from util import resize`
+    reference_optex_module.rgb_to_hls = _texture.rgb_to_hls               # optex.py:5 (kornia)
+    reference_optex_module.hls_to_rgb = _texture.hls_to_rgb

@@ -1,0 +1,244 @@
+"""The synthesis loop of the reference (`OptimalTexture`, /root/reference/optex.py:15-139) on the B200 kernels.
+
+Same constructor arguments, same `forward(pastiche, styles, content=None, verbose=False)`, same pass / layer /
+iteration schedule (including the `[l - 1]` column quirk of optex.py:112) - but every tensor stays on the GPU and
+every stage is one of this library's kernels:
+
+    resize (util.py:105)                      -> optex_resize_bicubic_aa
+    Encoder / Decoder (vgg.py)                -> optex_conv3x3 stacks (vgg.py of this package)
+    fit_pca, `@ eigvecs`, `@ eigvecs.T`       -> optex_fit_pca, optex_pca_project
+    content re-centring (optex.py:76)         -> optex_recentre
+    mix_style_features (optex.py:193-206)     -> optex_hist_match x2 + optex_mix_features per layer
+    the inner loop (optex.py:112-117)         -> ONE optex_ot_loop call per layer (rotations drawn on the device,
+                                                 content blend fused into the inverse rotation)
+    colour transfer (optex.py:124-137)        -> optex_lightness_transfer (+ 3 cdf OT steps for "opt")
+
+Additive over the reference:
+  * `models_dir=` / `state_dicts=`: where the weights come from (the reference reads ./models/*.pth, vgg.py:144,162);
+  * the five encoder files are prefix-identical: when the loaded weights confirm it, styles and content
+    are encoded ONCE per pass by Encoder(5).forward_all instead of five times (optex.py:62-63,72);
+  * `rotations=` (callable (c, index) -> [c, c] tensor), `mixing_noise=` (callable shape -> uniform noise): inject
+    what the reference draws from global RNG state, for parity tests;
+  * `no_multires=True` works (the reference's own path raises AttributeError at util.py:86: a list has no .tolist()).
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from . import histmatch as _histmatch
+from . import optex as _optex
+from . import util as _util
+from . import vgg as _vgg
+from ._runtime import call, f32c, ptr, require_cuda, stream_ptr, workspace
+
+
+def recentre(content_feature: Tensor, style_feature: Tensor) -> Tensor:
+    """reference: optex.py:76  `content_feature - content_feature.mean() + torch.mean(style_features[l])`."""
+    dev = require_cuda(content_feature, style_feature)
+    x, s = f32c(content_feature), f32c(style_feature)
+    out = torch.empty_like(x)
+    wsb = workspace(dev, _lib.lib().optex_recentre_workspace_bytes())
+    with torch.cuda.device(dev):
+        call("optex_recentre", ptr(x), x.numel(), ptr(s), s.numel(), ptr(out), ptr(wsb), wsb.numel(), stream_ptr(dev))
+    return out
+
+
+def lightness_transfer(content: Tensor, pastiche: Tensor) -> Tensor:
+    """reference: optex.py:126-128 - hls_to_rgb(H(content), L(pastiche), S(content)); NCHW [b,3,h,w] in [0,1]."""
+    dev = require_cuda(content, pastiche)
+    if content.shape != pastiche.shape or content.dim() != 4 or content.shape[1] != 3:
+        raise ValueError(f"colour transfer needs two [b,3,h,w] images of one shape, got {tuple(content.shape)} "
+                         f"and {tuple(pastiche.shape)}")
+    c, p = f32c(content), f32c(pastiche)
+    out = torch.empty_like(c)
+    b, _, h, w = c.shape
+    with torch.cuda.device(dev):
+        call("optex_lightness_transfer", ptr(c), ptr(p), ptr(out), b, h * w, stream_ptr(dev))
+    return out
+
+
+def _hls(x: Tensor, fn: str) -> Tensor:
+    dev = require_cuda(x)
+    if x.dim() != 4 or x.shape[1] != 3:
+        raise ValueError(f"expected [b,3,h,w], got {tuple(x.shape)}")
+    xin = f32c(x)
+    out = torch.empty_like(xin)
+    b, _, h, w = xin.shape
+    with torch.cuda.device(dev):
+        call(fn, ptr(xin), ptr(out), b, h * w, stream_ptr(dev))
+    return out
+
+
+def rgb_to_hls(image: Tensor) -> Tensor:
+    """kornia.color.hls.rgb_to_hls as imported at optex.py:5 (H in radians)."""
+    return _hls(image, "optex_rgb_to_hls")
+
+
+def hls_to_rgb(image: Tensor) -> Tensor:
+    """kornia.color.hls.hls_to_rgb as imported at optex.py:5."""
+    return _hls(image, "optex_hls_to_rgb")
+
+
+def mix_style_features(style_features: List[Tensor], mixing_mask: Tensor, mixing_alpha: float, hist_mode: str):
+    """reference: optex.py:193-206.  style_features[l]: [2, h, w, c]; mixing_mask [1, 1, mh, mw] of 0 / 1."""
+    mask = f32c(mixing_mask).reshape(mixing_mask.shape[-2], mixing_mask.shape[-1])
+    mh, mw = mask.shape
+    out = []
+    for sf in style_features:
+        dev = require_cuda(sf, mask)
+        if sf.shape[0] != 2:
+            raise ValueError(f"mixing needs exactly two style images, got a batch of {sf.shape[0]}")
+        A, B = f32c(sf[0:1]), f32c(sf[1:2])
+        AtoB = _histmatch.hist_match(A, B, mode=hist_mode)
+        BtoA = _histmatch.hist_match(B, A, mode=hist_mode)
+        target = torch.empty_like(A)
+        _, h, w, c = A.shape
+        with torch.cuda.device(dev):
+            call("optex_mix_features", ptr(A), ptr(B), ptr(AtoB), ptr(BtoA), ptr(mask), ptr(target), h, w, c, mh, mw,
+                 float(mixing_alpha), stream_ptr(dev))
+        out.append(target)
+    return out
+
+
+def _prefix_identical(enc5: _vgg.Encoder, others: Dict[int, _vgg.Encoder]) -> bool:
+    for d, e in others.items():
+        for a, b in zip(e.layers, enc5.layers):
+            if a.w.shape != b.w.shape or not (torch.equal(a.w, b.w) and torch.equal(a.b, b.b)):
+                return False
+    return True
+
+
+class OptimalTexture:
+    """reference: optex.py:15-139."""
+
+    def __init__(self, size: int = 512, iters: int = 500, passes: int = 5, hist_mode: str = "chol",
+                 color_transfer: Optional[str] = None, content_strength: float = 0.1, style_scale: float = 1,
+                 mixing_alpha: float = 0.5, no_pca: bool = False, no_multires: bool = False, *,
+                 models_dir: Optional[str] = None, state_dicts: Optional[Dict[Tuple[str, int], dict]] = None,
+                 device="cuda", rotations: Optional[Callable[[int, int], Tensor]] = None,
+                 mixing_noise: Optional[Callable[[Tuple[int, int]], Tensor]] = None):
+        self.hist_mode = hist_mode
+        self.color_transfer = color_transfer
+        self.content_strength = content_strength
+        self.style_scale = style_scale
+        self.mixing_alpha = mixing_alpha
+        self.use_pca = not no_pca
+        self.passes = passes
+        self.iters_per_pass_and_layer, self.sizes = _util.get_iters_and_sizes(size, iters, passes, not no_multires)
+        self.device = torch.device(device)
+        sd = state_dicts or {}
+        self.depths = list(range(5, 0, -1))                                                     # optex.py:42-43
+        self.encoders = [_vgg.Encoder(d, state_dict=sd.get(("encoder", d)), models_dir=models_dir, device=device)
+                         for d in self.depths]
+        self.decoders = [_vgg.Decoder(d, state_dict=sd.get(("decoder", d)), models_dir=models_dir, device=device)
+                         for d in self.depths]
+        self.shared_encoder = _prefix_identical(self.encoders[0], {e.depth: e for e in self.encoders[1:]})
+        self.rotations = rotations
+        self.mixing_noise = mixing_noise
+        self.ot_calls = 0
+
+    def to(self, *args, **kwargs):        # the reference is an nn.Module and is `.to(pastiche)`-ed (optex.py:278)
+        return self
+
+    # ------------------------------------------------------------------------------------------ stages
+    def _encode_all(self, image: Tensor) -> List[Tensor]:
+        """Features of `image` for the five encoders, deepest first (the order of self.encoders)."""
+        if self.shared_encoder:
+            return self.encoders[0].forward_all(image)[::-1]
+        return [enc(image) for enc in self.encoders]
+
+    def _ot_layer(self, feature: Tensor, style: Tensor, hist_mode: str, iters: int, content: Optional[Tensor],
+                  strength: float) -> Tensor:
+        """optex.py:112-117 for one layer."""
+        if iters <= 0:
+            return feature
+        c = feature.shape[-1]
+        rots = None
+        if self.rotations is not None:
+            rots = torch.stack([f32c(self.rotations(c, self.ot_calls + i).to(feature.device)) for i in range(iters)])
+        self.ot_calls += iters
+        return _optex.ot_loop(feature, style, hist_mode, iters, rotations=rots, content=content,
+                              content_strength=strength)
+
+    def encode_inputs(self, pastiche: Tensor, styles: List[Tensor], content: Optional[Tensor], size: int):
+        """reference: optex.py:45-79."""
+        if pastiche.shape[-2] != size and pastiche.shape[-1] != size:
+            style_tens = [_util.resize(s, _util.get_size(size, self.style_scale, s.shape[2], s.shape[3]))
+                          for s in styles]
+            if content is not None:
+                cont_size = _util.get_size(size, 1.0, content.shape[2], content.shape[3], oversize=True)
+                cont_tens = _util.resize(content, cont_size)
+            else:
+                cont_size = (size, size)
+                cont_tens = None
+            pastiche = _util.resize(pastiche, cont_size)
+        else:
+            style_tens, cont_tens = styles, content
+
+        per_style = [self._encode_all(s) for s in style_tens]
+        per_content = self._encode_all(cont_tens) if cont_tens is not None else None
+        style_features, style_eigvs, content_features = [], [], []
+        for l in range(len(self.encoders)):
+            feats = [ps[l] for ps in per_style]
+            sf = feats[0] if len(feats) == 1 else torch.cat(feats)
+            eigvecs = None
+            if self.use_pca:
+                sf, eigvecs = _optex.fit_pca(sf)
+                style_eigvs.append(eigvecs)
+            style_features.append(sf)
+            if per_content is not None:
+                cf = per_content[l]
+                if self.use_pca:
+                    cf = _optex.pca_project(cf, eigvecs)
+                content_features.append(recentre(cf, sf))
+        return pastiche, style_features, style_eigvs, content_features
+
+    def forward(self, pastiche: Tensor, styles: List[Tensor], content: Optional[Tensor] = None,
+                verbose: bool = False) -> Tensor:
+        """reference: optex.py:81-139."""
+        require_cuda(pastiche, *styles, content)
+        for p in range(self.passes):
+            if verbose:
+                print(f"Pass {p}, size {self.sizes[p]}")
+            pastiche, style_features, style_eigvs, content_features = self.encode_inputs(
+                pastiche, styles, content, self.sizes[p])
+
+            if len(styles) > 1:
+                shape = tuple(style_features[1].shape[1:3])
+                noise = self.mixing_noise(shape) if self.mixing_noise is not None else torch.rand(
+                    shape, device=pastiche.device)
+                mixing_mask = torch.ceil(noise.to(pastiche.device) - self.mixing_alpha)[None, None, ...]
+                style_features = mix_style_features(style_features, mixing_mask, self.mixing_alpha, self.hist_mode)
+
+            for l, (encoder, decoder) in enumerate(zip(self.encoders, self.decoders)):
+                if verbose:
+                    print(f"Layer: relu{(4 - l) + 1}_1")
+                feature = encoder(pastiche)
+                if self.use_pca:
+                    feature = _optex.pca_project(feature, style_eigvs[l])
+                blend = len(content_features) > 0 and l <= 2
+                feature = self._ot_layer(feature, style_features[l], self.hist_mode,
+                                         self.iters_per_pass_and_layer[p][l - 1],        # [l - 1]: optex.py:112
+                                         content_features[l] if blend else None,
+                                         self.content_strength / 2 ** (4 - l) if blend else 0.0)
+                if self.use_pca:
+                    feature = _optex.pca_project(feature, style_eigvs[l], transpose=True)
+                pastiche = decoder(feature)
+
+        if self.color_transfer is not None:
+            assert content is not None, "Color transfer requires content image"
+            target = lightness_transfer(content, pastiche)
+            if self.color_transfer == "opt":
+                feature = _util.to_nhwc(pastiche).contiguous()
+                target = _util.to_nhwc(target).contiguous()
+                feature = self._ot_layer(feature, target, "cdf", 3, None, 0.0)
+                pastiche = _util.to_nchw(feature)
+            elif self.color_transfer == "lum":
+                pastiche = target
+        return pastiche
+
+    __call__ = forward

@@ -63,8 +63,93 @@ def write_vgg_golden():
     np.savez_compressed(os.path.join(OUT, "vgg.npz"), **out)
 
 
+UTIL_SIZE_CASES = [(512, 1.0, 736, 512, False), (512, 1.0, 736, 512, True), (1024, 1.0, 402, 402, True),
+                   (2048, 1.0, 1920, 1088, False), (2048, 1.0, 3840, 2160, True), (256, 0.5, 300, 451, False),
+                   (320, 2.0, 100, 77, True), (64, 1.0, 80, 64, False)]
+UTIL_NAME_CASES = [
+    dict(style=["style/graffiti.jpg"], content=None, mixing_alpha=0.5, content_strength=0.01, hist_mode="chol",
+         no_pca=False, no_multires=False, style_scale=1.0, color_transfer=None, size=512, output_dir="output/"),
+    dict(style=["style/zebra.jpg", "a/b/pattern-small.jpg"], content="content/rocket.jpg", mixing_alpha=0.25,
+         content_strength=0.2, hist_mode="cdf", no_pca=True, no_multires=True, style_scale=0.5, color_transfer="opt",
+         size=1024, output_dir="out"),
+]
+
+
+def write_util_golden(util):
+    """util.get_size (util.py:33-42) and the file names util.save_image builds (util.py:45-65)."""
+    import json
+    from argparse import Namespace
+
+    import torchvision
+
+    out = {"get_size": [[list(c), list(util.get_size(*c))] for c in UTIL_SIZE_CASES], "names": []}
+    real = torchvision.utils.save_image
+    try:
+        for batch in (1, 2):
+            for case in UTIL_NAME_CASES:
+                paths = []
+                torchvision.utils.save_image = lambda t, path, *a, **k: paths.append(path)
+                util.save_image(torch.zeros(batch, 3, 4, 4), Namespace(**case))
+                out["names"].append({"batch": batch, "args": case, "paths": paths})
+    finally:
+        torchvision.utils.save_image = real
+    with open(os.path.join(OUT, "util.json"), "w") as fh:
+        json.dump(out, fh, indent=1)
+
+
+def write_texture_golden(optex):
+    """optex.OptimalTexture.forward (optex.py:81-139) of the real reference, with seeded random weights in place of
+    ./models/*.pth (too large to commit), the rotation stream of `texture_rotation`, torch's RNG seeded for the
+    mixing mask, and oracle/image_oracle's HLS restatement standing in for the absent kornia (so the colour-transfer
+    ORCHESTRATION is the reference's while the HLS arithmetic stays unpinned)."""
+    import vgg  # reference module
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    from oracle import image_oracle, vgg_oracle
+    from oracle.texture_cases import TEXTURE_CASES, texture_inputs, texture_rotation
+
+    def fake_load(path, *a, **k):
+        base = os.path.basename(path)
+        depth = int(base.split("conv")[1][0])
+        sd = vgg_oracle.random_state_dict("encoder" if base.startswith("vgg_normalised") else "decoder", depth)
+        keys = list(real_load(path, *a, **k).keys())       # the Sequential's own parameter names, in order
+        assert len(keys) == len(sd)
+        return dict(zip(keys, sd.values()))
+
+    real_load = vgg.torch.load
+    vgg.torch.load = fake_load
+    optex.rgb_to_hls, optex.hls_to_rgb = image_oracle.rgb_to_hls, image_oracle.hls_to_rgb
+    out = {}
+    try:
+        for name in TEXTURE_CASES:
+            kwargs, styles, content, pastiche = texture_inputs(name)
+            calls = [0]
+
+            def rot(n, device="cpu", impl="scipy", _c=calls):
+                r = texture_rotation(n, _c[0])
+                _c[0] += 1
+                return r
+
+            optex.random_rotation = rot
+            with torch.inference_mode():
+                model = optex.OptimalTexture(**kwargs)       # nn.Conv2d initialisers consume torch's RNG
+                torch.manual_seed(77)                        # -> the mixing-mask noise (optex.py:98) is torch.rand after this
+                res = model.forward(pastiche.clone(), [s.clone() for s in styles],
+                                    None if content is None else content.clone())
+            out[f"{name}_out"] = res.contiguous().numpy()
+            out[f"{name}_calls"] = np.asarray(calls[0])
+    finally:
+        vgg.torch.load = real_load
+    np.savez_compressed(os.path.join(OUT, "texture.npz"), **out)
+
+
 def main():
     histmatch, optex, util = import_reference()
+    if "--texture-only" in sys.argv:
+        os.makedirs(OUT, exist_ok=True)
+        write_texture_golden(optex)
+        write_util_golden(util)
+        return
     from scipy.stats import special_ortho_group
 
     os.makedirs(OUT, exist_ok=True)
@@ -148,6 +233,9 @@ def main():
         misc[f"sched_{size}_{iters}_{passes}_sizes"] = np.asarray(sizes)
     np.savez_compressed(os.path.join(OUT, "misc.npz"), **misc)
     write_vgg_golden()
+    torch.set_num_threads(os.cpu_count() or 1)
+    write_texture_golden(optex)
+    write_util_golden(util)
     print("wrote", sorted(os.listdir(OUT)))
 
 

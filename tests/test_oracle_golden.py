@@ -89,3 +89,31 @@ def test_householder_rotation_is_special_orthogonal():
         h = rotation.haar_rotation_householder(rng.normal(size=(n - 1, n)))
         np.testing.assert_allclose(h @ h.T, np.eye(n), atol=1e-12)
         assert abs(np.linalg.det(h) - 1) < 1e-10
+
+
+# ---------------------------------------------------------------------------------------------- synthesis loop
+@pytest.mark.parametrize("name", ["synth_pca", "mix_content_chol_opt", "nopca_cdf_lum"])
+def test_texture_forward_matches_reference(golden, name):
+    """oracle/texture_oracle.OptimalTexture == the real reference's OptimalTexture.forward (optex.py:81-139) on the
+    same seeded weights / inputs / rotation stream / mask noise, bit for bit (same torch ops in the same order)."""
+    from oracle import texture_cases, texture_oracle
+
+    g = golden("texture")
+    kwargs, styles, content, pastiche = texture_cases.texture_inputs(name)
+    torch.manual_seed(77)
+    model = texture_oracle.OptimalTexture(texture_cases.state_dicts(), rotation_fn=texture_cases.texture_rotation,
+                                          **kwargs)
+    with torch.inference_mode():
+        out = model.forward(pastiche, styles, content)
+    assert model.ot_calls == int(g[f"{name}_calls"])
+    np.testing.assert_array_equal(out.contiguous().numpy(), g[f"{name}_out"])
+
+
+def test_schedule_and_sizes(golden):
+    from oracle import texture_oracle
+
+    g = golden("misc")
+    for (size, iters, passes) in ((512, 500, 5), (256, 500, 4), (1024, 500, 5), (2048, 300, 3)):
+        its, sizes = texture_oracle.get_iters_and_sizes(size, iters, passes, True)
+        np.testing.assert_array_equal(np.asarray(its), g[f"sched_{size}_{iters}_{passes}_iters"])
+        np.testing.assert_array_equal(np.asarray(sizes), g[f"sched_{size}_{iters}_{passes}_sizes"])

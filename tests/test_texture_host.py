@@ -1,0 +1,89 @@
+"""Host logic of the synthesis loop (no GPU): the util mirror against values produced by the REAL reference
+(tests/golden/util.json, misc.npz), and the explicit resize / HLS arithmetic of oracle/image_oracle.py."""
+import json
+import os
+from argparse import Namespace
+
+import numpy as np
+import pytest
+import torch
+
+from optimaltextures_b200 import util as outil
+from oracle import image_oracle, texture_oracle
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _util_golden():
+    with open(os.path.join(HERE, "golden", "util.json")) as fh:
+        return json.load(fh)
+
+
+def test_get_size_matches_reference():
+    for args, want in _util_golden()["get_size"]:
+        assert list(outil.get_size(*args)) == want
+        assert list(texture_oracle.get_size(*args)) == want
+
+
+def test_output_names_match_reference():
+    for case in _util_golden()["names"]:
+        ns = Namespace(**case["args"])
+        stem = f"{ns.output_dir}/{outil.output_name(ns)}"
+        want = case["paths"]
+        got = [stem + (f"_{o + 1}" if case["batch"] > 1 else "") + ".png" for o in range(case["batch"])]
+        assert got == want
+
+
+def test_schedule_matches_reference(golden):
+    g = golden("misc")
+    for (size, iters, passes) in ((512, 500, 5), (256, 500, 4), (1024, 500, 5), (2048, 300, 3)):
+        its, sizes = outil.get_iters_and_sizes(size, iters, passes, True)
+        np.testing.assert_array_equal(np.asarray(its), g[f"sched_{size}_{iters}_{passes}_iters"])
+        np.testing.assert_array_equal(np.asarray(sizes), g[f"sched_{size}_{iters}_{passes}_sizes"])
+    # effective per-layer iterations of `--iters 500 --passes 5` with the [l - 1] quirk
+    its, _ = outil.get_iters_and_sizes(512, 500, 5, True)
+    assert [its[0][l - 1] for l in range(5)] == [40, 8, 13, 22, 40]
+    assert sum(its[p][l - 1] for p in range(5) for l in range(5)) == 493
+
+
+def test_no_multires_schedule_is_usable():
+    """The reference raises here (util.py:86, list.tolist()); the mirror returns the documented intent."""
+    its, sizes = outil.get_iters_and_sizes(512, 500, 5, False)
+    assert sizes == [512] * 5 and len(its) == 5 and all(len(r) == 5 for r in its)
+    assert its[0] == [int(100 * p) for p in (np.array([128, 192, 320, 576, 576]) / 1792)]
+
+
+def test_round32_and_layout_helpers():
+    assert [outil.round32(v) for v in (1, 32, 33, 255, 256, 257)] == [32, 32, 64, 256, 256, 288]
+    x = torch.zeros(2, 3, 5, 7)
+    assert outil.to_nhwc(x).shape == (2, 5, 7, 3) and outil.to_nchw(outil.to_nhwc(x)).shape == x.shape
+    assert outil.name("a/b/zebra.small.jpg") == "zebra"
+
+
+def test_resize_requires_gpu():
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        outil.resize(torch.zeros(1, 3, 8, 8), (4, 4))
+
+
+@pytest.mark.parametrize("shape", [(64, 48, 32, 32), (37, 53, 64, 96), (256, 256, 448, 448), (416, 416, 256, 224),
+                                   (100, 80, 33, 95), (32, 32, 32, 64), (5, 7, 1, 1)])
+def test_resize_explicit_matches_torch(shape):
+    """The written-out filter (what csrc/image.cu implements) == torch's CPU interpolate, to fp32 rounding."""
+    h, w, ho, wo = shape
+    x = torch.rand(2, 3, h, w, generator=torch.Generator().manual_seed(h * w))
+    want = image_oracle.resize(x, (ho, wo)).numpy()
+    got = image_oracle.resize_explicit(x.numpy(), (ho, wo))
+    np.testing.assert_allclose(got, want, rtol=0, atol=4e-6)
+
+
+def test_hls_round_trip_and_known_colours():
+    rgb = torch.tensor([[1.0, 0, 0], [0, 1.0, 0], [0, 0, 1.0], [0.5, 0.5, 0.5], [0, 0, 0], [1, 1, 1],
+                        [0.2, 0.4, 0.6]]).T.reshape(1, 3, 1, 7)
+    hls = image_oracle.rgb_to_hls(rgb)
+    np.testing.assert_allclose(hls[0, 0, 0, :3].numpy(), [0, 2 * np.pi / 3, 4 * np.pi / 3], atol=1e-6)   # hue
+    np.testing.assert_allclose(hls[0, 1, 0].numpy(), [0.5, 0.5, 0.5, 0.5, 0, 1, 0.4], atol=1e-6)         # lightness
+    np.testing.assert_allclose(hls[0, 2, 0].numpy(), [1, 1, 1, 0, 0, 0, 0.5], atol=1e-6)                 # saturation
+    x = torch.rand(2, 3, 16, 16, generator=torch.Generator().manual_seed(3))
+    np.testing.assert_allclose(image_oracle.hls_to_rgb(image_oracle.rgb_to_hls(x)).numpy(), x.numpy(), atol=2e-6)
+    same = image_oracle.lightness_transfer(x, x)
+    np.testing.assert_allclose(same.numpy(), x.numpy(), atol=2e-6)
