@@ -52,6 +52,11 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--all-modes", action="store_true", help="also time the other hist modes (extra keys)")
     ap.add_argument("--no-pdl", action="store_true", help="launch the kernels without programmatic dependent launch")
+    ap.add_argument("--no-synthesis", action="store_true",
+                    help="skip the end-to-end synthesis block (BASELINE metric ii: output pixels/sec of forward())")
+    ap.add_argument("--synthesis-size", type=int, default=512, dest="synthesis_size")
+    ap.add_argument("--synthesis-cpu", action="store_true", dest="synthesis_cpu",
+                    help="also time the oracle's forward() of the same synthesis on the host cores (about a minute)")
     ap.add_argument("--sharded", action="store_true",
                     help="N > 1: ONE feature block, rotated channels sharded over the ranks + NCCL all-gather "
                          "(strong scaling) instead of one independent block per rank")
@@ -501,10 +506,76 @@ def run_ours(a):
             finally:
                 ob.set_gemm_mode(a.gemm)
         line["other_gemm_modes_it_s"] = gm
+    if world == 1 and not a.no_synthesis:
+        try:
+            line["synthesis"] = synthesis_block(a)
+        except Exception as exc:  # noqa: BLE001  (the headline line must survive a failure of the extra block)
+            line["synthesis"] = {"error": f"{type(exc).__name__}: {exc}"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------- end-to-end synthesis
+def synthesis_block(a):
+    """BASELINE.json metric (ii): output pixels / second of OptimalTexture.forward (optex.py:81-139, timed like the
+    reference's own `time()` pair at optex.py:287-289 but with a device synchronisation on both sides) on
+    configs[1]: texture synthesis, all five VGG layers, hist_mode pca, 5 passes, 500 iterations.  Synthetic style
+    image of the bundled graffiti.jpg's shape at that size, random-init weights of the reference's architecture
+    (its ./models/*.pth are not in this repository), rotations drawn on the device."""
+    import torch
+
+    import optimaltextures_b200 as ob
+    from optimaltextures_b200 import texture
+    from oracle import texture_cases
+
+    size = a.synthesis_size
+    kw = dict(size=size, iters=500, passes=5, hist_mode="pca")
+    sd = texture_cases.state_dicts()
+    g = torch.Generator().manual_seed(0)
+    style = torch.rand(1, 3, round(size * 736 / 512 / 32) * 32, size, generator=g)
+    pastiche = torch.rand(1, 3, size, size, generator=g)
+    model = texture.OptimalTexture(state_dicts=sd, **kw)
+    dev_style, dev_pastiche = style.cuda(), pastiche.cuda()
+    lib = ob._lib.lib()
+    out = {"workload": f"texture synthesis {size}^2 (configs[1]): 5 VGG layers, hist pca, 5 passes, 500 iters; style "
+                       f"{tuple(style.shape)} synthetic, random-init weights", "unit": "px/s"}
+    for rep in range(2):                                   # first run allocates workspaces: warm-up
+        ob.manual_seed(0)
+        model.ot_calls = 0
+        model.profile = {} if rep == 1 else None
+        l0 = lib.optex_launch_count()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = model.forward(dev_pastiche, [dev_style])
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        launches = lib.optex_launch_count() - l0
+    out.update({"value": res.shape[0] * res.shape[2] * res.shape[3] / dt, "seconds": dt, "ot_iters": model.ot_calls,
+                "gpu_launches": int(launches), "pca_k_last_pass": model.last_pca_k,
+                "stage_ms": {k: round(v, 2) for k, v in model.stage_ms().items()},
+                "finite": bool(torch.isfinite(res).all())})
+    if a.synthesis_cpu:
+        from oracle import texture_oracle
+
+        torch.set_num_threads(os.cpu_count() or 1)
+        rot_cache = {}
+
+        def rot(c, index):                                 # the reference draws one scipy rotation per call
+            from scipy.stats import special_ortho_group
+
+            return torch.tensor(special_ortho_group.rvs(c)) if c > 1 else torch.ones(1, 1, dtype=torch.float64)
+
+        cpu_model = texture_oracle.OptimalTexture(sd, rotation_fn=rot, **kw)
+        t0 = time.perf_counter()
+        with torch.inference_mode():
+            ref = cpu_model.forward(pastiche, [style])
+        dt_cpu = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": ref.shape[0] * ref.shape[2] * ref.shape[3] / dt_cpu, "unit": "px/s",
+                               "seconds": dt_cpu, "cores": os.cpu_count(), "kind": "port",
+                               "sample": "the whole synthesis once (oracle port, scipy rotation per OT call)"}
+    return out
 
 
 def main():

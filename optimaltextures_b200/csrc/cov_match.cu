@@ -69,9 +69,22 @@ __global__ void colmean_final_kernel(const float *__restrict__ part, float *__re
     for (int k = 0; k < splits; ++k) s += part[((int64_t)b * splits + k) * c + ch];
     mu[i] = s / (float)hw;
 }
-// Sig = (sum_z part_z) / n - sum_b (hw/n) mu_b mu_b^T  (+ eps on the diagonal)      histmatch.py:17-18
+// Xc[b*hw + r, ch] = X[b*hw + r, ch] - mu[b][ch]          histmatch.py:17,21  (x - mu before the product, like
+// the reference: the second moment of un-centred data loses |mu|^2 / var digits to cancellation in fp32)
+__global__ void center_kernel(const float *__restrict__ X, const float *__restrict__ mu, float *__restrict__ Xc,
+                              int64_t hw, int c, int64_t total) {
+    pdl_wait();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int ch = (int)(i % c);
+        const int64_t b = i / c / hw;
+        Xc[i] = X[i] - mu[b * c + ch];
+    }
+}
+// Sig = (sum_z part_z) / n  (+ eps on the diagonal); `part` is the Gram matrix of the CENTRED data, unless
+// sub_mean: then - sum_b (hw/n) mu_b mu_b^T is applied here                         histmatch.py:17-18
 __global__ void gram_reduce_kernel(const float *__restrict__ part, int nz, int64_t zstride, const float *__restrict__ mu,
-                                   int nb, int64_t hw, int c, float eps, float *__restrict__ Sig) {
+                                   int nb, int64_t hw, int c, float eps, float *__restrict__ Sig, int sub_mean) {
     pdl_wait();
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)c * c) return;
@@ -80,7 +93,8 @@ __global__ void gram_reduce_kernel(const float *__restrict__ part, int nz, int64
     for (int z = 0; z < nz; ++z) s += part[z * zstride + i];
     const float n = (float)(hw * nb);
     float m2 = 0.f;
-    for (int b = 0; b < nb; ++b) m2 = fmaf(mu[b * c + r], mu[b * c + q], m2);
+    if (sub_mean)
+        for (int b = 0; b < nb; ++b) m2 = fmaf(mu[b * c + r], mu[b * c + q], m2);
     float v = s / n - m2 * ((float)hw / n);
     if (r == q) v += eps;
     Sig[i] = v;
@@ -326,6 +340,7 @@ inline unsigned cdiv(int64_t a, int64_t b) { return (unsigned)((a + b - 1) / b);
 
 struct Ws {
     float *mu_p, *mu_s, *bias, *part_mean, *part_gram;
+    float *centred;  // max(n_t, n_s) x c: the block minus its per-(b, c) means, input of the Gram GEMM
     float *m[19];  // c x c matrices
     float *norm2, *resid;   // Newton-Schulz state of chain 0; chain 1 (side stream) at +NS_STATE
     int *flags;
@@ -349,13 +364,13 @@ size_t ws_layout(int64_t n_t, int64_t n_s, int c, int b_max, Ws *w, void *base, 
     l.bias = ar.take<float>((size_t)b_max * c);
     l.part_mean = ar.take<float>((size_t)b_max * kMeanSplits * c);
     l.part_gram = ar.take<float>((size_t)kGramSplits * cc);
+    l.centred = ar.take<float>((size_t)(n_t > n_s ? n_t : n_s) * c);
     for (int i = 0; i < 19; ++i) l.m[i] = ar.take<float>(cc);
     l.norm2 = ar.take<float>(2 * NS_STATE);
     l.resid = ar.take<float>(2 * NS_STATE);
     l.flags = ar.take<int>(2 * NS_STATE);
     if (w) *w = l;
     if (ok) *ok = ar.ok();
-    (void)n_t; (void)n_s;
     return ar.off;
 }
 
@@ -367,7 +382,16 @@ int moments(const float *X, int nb, int64_t hw, int c, float eps, float *mu, flo
     OPTEX_LAUNCH_CHECK("colsum_partial_kernel");
     launch_pdl(colmean_final_kernel, dim3((unsigned)(cdiv((int64_t)nb * c, 256))), dim3(256), 0, st, w.part_mean, mu, hw, c, splits, nb);
     OPTEX_LAUNCH_CHECK("colmean_final_kernel");
-    // Gram X^T X: A = X^T (stored [K = n, M = c]) and B = X (stored [K = n, N = c]), split over K
+    {
+        const int64_t total = n * c;
+        int64_t blocks = (total + 255) / 256;
+        const int64_t cap = (int64_t)sm_count() * 16;
+        if (blocks > cap) blocks = cap;
+        launch_pdl(center_kernel, dim3((unsigned)blocks), dim3(256), 0, st, X, (const float *)mu, w.centred, hw, c, total);
+        OPTEX_LAUNCH_CHECK("center_kernel");
+        X = w.centred;
+    }
+    // Gram Xc^T Xc: A = Xc^T (stored [K = n, M = c]) and B = Xc (stored [K = n, N = c]), split over K
     int nz = (int)(n / 512 < 1 ? 1 : (n / 512 > kGramSplits ? kGramSplits : n / 512));
     const int64_t zstride = (int64_t)c * c;
     int rc = OPTEX_ENOTSUP;
@@ -392,7 +416,7 @@ int moments(const float *X, int nb, int64_t hw, int c, float eps, float *mu, flo
             nz = (int)((n + kz - 1) / kz);
         }
     }
-    launch_pdl(gram_reduce_kernel, dim3((unsigned)(cdiv((int64_t)c * c, 256))), dim3(256), 0, st, w.part_gram, nz, zstride, mu, nb, hw, c, eps, Sig);
+    launch_pdl(gram_reduce_kernel, dim3((unsigned)(cdiv((int64_t)c * c, 256))), dim3(256), 0, st, w.part_gram, nz, zstride, mu, nb, hw, c, eps, Sig, 0);
     OPTEX_LAUNCH_CHECK("gram_reduce_kernel");
     return OPTEX_OK;
 }

@@ -1079,6 +1079,14 @@ int gemm_tc(const TcGemm &g, cudaStream_t st) {
     p.alpha = g.alpha; p.skip = g.skip; p.conv_a = p.terms == 3 ? 1 : 0; p.conv_b = conv_b ? 1 : 0;
     static const char *no_atmem = getenv("OPTEX_NO_A_TMEM");
     p.a_tmem = (p.conv_a && !p.conv_b && !(no_atmem && atoi(no_atmem))) ? 1 : 0;
+    // KNOWN ISSUE (scripts/debug_gemm_multi.py): with 64-wide N tiles the TMEM-A form corrupts isolated
+    // 32-row groups of a CTA's second and later tiles (timing dependent; 128- and 256-wide tiles and single-tile
+    // CTAs are clean).  Until the cause is found those launches take the shared-memory converters, which alternate
+    // two accumulators and are verified on the same shapes.
+    {
+        const int64_t tiles = ((g.M + BLOCK_M - 1) / BLOCK_M) * ((g.N + bn - 1) / bn) * nz;
+        if (p.a_tmem && bn == 64 && tiles > sm_count()) p.a_tmem = 0;
+    }
     p.nz = nz;
     p.colrange = g.d_trans ? g.colrange : nullptr;
     p.rowrange = g.d_trans ? nullptr : g.rowrange;

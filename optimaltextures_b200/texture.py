@@ -18,11 +18,14 @@ Additive over the reference:
   * the five encoder files are prefix-identical: when the loaded weights confirm it, styles and content
     are encoded ONCE per pass by Encoder(5).forward_all instead of five times (optex.py:62-63,72);
   * `rotations=` (callable (c, index) -> [c, c] tensor), `mixing_noise=` (callable shape -> uniform noise): inject
-    what the reference draws from global RNG state, for parity tests;
+    what the reference draws from global RNG state, for parity tests; `pca=` (callable features -> (projected,
+    eigvecs)) replaces `fit_pca` (an SVD basis is defined only up to sign / rotations of near-degenerate subspaces, so
+    element-wise comparisons of the whole loop need both sides in ONE basis);
   * `no_multires=True` works (the reference's own path raises AttributeError at util.py:86: a list has no .tolist()).
 """
 from __future__ import annotations
 
+import contextlib
 from typing import Callable, Dict, List, Optional, Tuple
 
 import torch
@@ -120,7 +123,8 @@ class OptimalTexture:
                  mixing_alpha: float = 0.5, no_pca: bool = False, no_multires: bool = False, *,
                  models_dir: Optional[str] = None, state_dicts: Optional[Dict[Tuple[str, int], dict]] = None,
                  device="cuda", rotations: Optional[Callable[[int, int], Tensor]] = None,
-                 mixing_noise: Optional[Callable[[Tuple[int, int]], Tensor]] = None):
+                 mixing_noise: Optional[Callable[[Tuple[int, int]], Tensor]] = None,
+                 pca: Optional[Callable[[Tensor], Tuple[Tensor, Tensor]]] = None):
         self.hist_mode = hist_mode
         self.color_transfer = color_transfer
         self.content_strength = content_strength
@@ -139,12 +143,31 @@ class OptimalTexture:
         self.shared_encoder = _prefix_identical(self.encoders[0], {e.depth: e for e in self.encoders[1:]})
         self.rotations = rotations
         self.mixing_noise = mixing_noise
+        self.pca = pca or _optex.fit_pca
         self.ot_calls = 0
+        self.last_pca_k: List[int] = []
+        self.profile: Optional[Dict[str, list]] = None      # set to {} to collect CUDA-event pairs per stage
 
     def to(self, *args, **kwargs):        # the reference is an nn.Module and is `.to(pastiche)`-ed (optex.py:278)
         return self
 
     # ------------------------------------------------------------------------------------------ stages
+    @contextlib.contextmanager
+    def _stage(self, name: str):
+        if self.profile is None:
+            yield
+            return
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        yield
+        b.record()
+        self.profile.setdefault(name, []).append((a, b))
+
+    def stage_ms(self) -> Dict[str, float]:
+        """Milliseconds per stage from the collected events (synchronises)."""
+        torch.cuda.synchronize()
+        return {k: sum(a.elapsed_time(b) for a, b in v) for k, v in (self.profile or {}).items()}
+
     def _encode_all(self, image: Tensor) -> List[Tensor]:
         """Features of `image` for the five encoders, deepest first (the order of self.encoders)."""
         if self.shared_encoder:
@@ -167,27 +190,30 @@ class OptimalTexture:
     def encode_inputs(self, pastiche: Tensor, styles: List[Tensor], content: Optional[Tensor], size: int):
         """reference: optex.py:45-79."""
         if pastiche.shape[-2] != size and pastiche.shape[-1] != size:
-            style_tens = [_util.resize(s, _util.get_size(size, self.style_scale, s.shape[2], s.shape[3]))
-                          for s in styles]
-            if content is not None:
-                cont_size = _util.get_size(size, 1.0, content.shape[2], content.shape[3], oversize=True)
-                cont_tens = _util.resize(content, cont_size)
-            else:
-                cont_size = (size, size)
-                cont_tens = None
-            pastiche = _util.resize(pastiche, cont_size)
+            with self._stage("resize"):
+                style_tens = [_util.resize(s, _util.get_size(size, self.style_scale, s.shape[2], s.shape[3]))
+                              for s in styles]
+                if content is not None:
+                    cont_size = _util.get_size(size, 1.0, content.shape[2], content.shape[3], oversize=True)
+                    cont_tens = _util.resize(content, cont_size)
+                else:
+                    cont_size = (size, size)
+                    cont_tens = None
+                pastiche = _util.resize(pastiche, cont_size)
         else:
             style_tens, cont_tens = styles, content
 
-        per_style = [self._encode_all(s) for s in style_tens]
-        per_content = self._encode_all(cont_tens) if cont_tens is not None else None
+        with self._stage("encode_inputs"):
+            per_style = [self._encode_all(s) for s in style_tens]
+            per_content = self._encode_all(cont_tens) if cont_tens is not None else None
         style_features, style_eigvs, content_features = [], [], []
         for l in range(len(self.encoders)):
             feats = [ps[l] for ps in per_style]
             sf = feats[0] if len(feats) == 1 else torch.cat(feats)
             eigvecs = None
             if self.use_pca:
-                sf, eigvecs = _optex.fit_pca(sf)
+                with self._stage("fit_pca"):
+                    sf, eigvecs = self.pca(sf)
                 style_eigvs.append(eigvecs)
             style_features.append(sf)
             if per_content is not None:
@@ -195,6 +221,7 @@ class OptimalTexture:
                 if self.use_pca:
                     cf = _optex.pca_project(cf, eigvecs)
                 content_features.append(recentre(cf, sf))
+        self.last_pca_k = [int(v.shape[1]) for v in style_eigvs]        # conv5_1 .. conv1_1 of the latest pass
         return pastiche, style_features, style_eigvs, content_features
 
     def forward(self, pastiche: Tensor, styles: List[Tensor], content: Optional[Tensor] = None,
@@ -217,17 +244,20 @@ class OptimalTexture:
             for l, (encoder, decoder) in enumerate(zip(self.encoders, self.decoders)):
                 if verbose:
                     print(f"Layer: relu{(4 - l) + 1}_1")
-                feature = encoder(pastiche)
-                if self.use_pca:
-                    feature = _optex.pca_project(feature, style_eigvs[l])
+                with self._stage("encode"):
+                    feature = encoder(pastiche)
+                    if self.use_pca:
+                        feature = _optex.pca_project(feature, style_eigvs[l])
                 blend = len(content_features) > 0 and l <= 2
-                feature = self._ot_layer(feature, style_features[l], self.hist_mode,
-                                         self.iters_per_pass_and_layer[p][l - 1],        # [l - 1]: optex.py:112
-                                         content_features[l] if blend else None,
-                                         self.content_strength / 2 ** (4 - l) if blend else 0.0)
-                if self.use_pca:
-                    feature = _optex.pca_project(feature, style_eigvs[l], transpose=True)
-                pastiche = decoder(feature)
+                with self._stage("ot_loop"):
+                    feature = self._ot_layer(feature, style_features[l], self.hist_mode,
+                                             self.iters_per_pass_and_layer[p][l - 1],    # [l - 1]: optex.py:112
+                                             content_features[l] if blend else None,
+                                             self.content_strength / 2 ** (4 - l) if blend else 0.0)
+                with self._stage("decode"):
+                    if self.use_pca:
+                        feature = _optex.pca_project(feature, style_eigvs[l], transpose=True)
+                    pastiche = decoder(feature)
 
         if self.color_transfer is not None:
             assert content is not None, "Color transfer requires content image"

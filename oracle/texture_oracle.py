@@ -93,30 +93,42 @@ class OptimalTexture:
         self.mask_fn = mask_fn or (lambda shape: torch.rand(shape))
         self.fit_pca_fn = fit_pca_fn or ot_oracle.fit_pca
         self.ot_calls = 0
+        # set to a list to record every stage as (name, inputs..., output): tests replay the stages one by one on
+        # the B200 with the oracle's inputs ("teacher forcing") - the loop as a whole amplifies a 1e-6 input
+        # perturbation to 1e-3 .. 1e-2 at the output (random-weight networks), so only per-stage parity is well posed
+        self.trace = None
+
+    def _rec(self, *entry):
+        if self.trace is not None:
+            self.trace.append(tuple(e.clone() if isinstance(e, Tensor) else e for e in entry))
+        return entry[-1]
 
     def encode(self, depth: int, x: Tensor) -> Tensor:
-        return vgg_oracle.encoder_forward(x, self.sd[("encoder", depth)], depth)
+        return self._rec("encode", depth, x, vgg_oracle.encoder_forward(x, self.sd[("encoder", depth)], depth))
 
     def decode(self, depth: int, f: Tensor) -> Tensor:
-        return vgg_oracle.decoder_forward(f, self.sd[("decoder", depth)], depth)
+        return self._rec("decode", depth, f, vgg_oracle.decoder_forward(f, self.sd[("decoder", depth)], depth))
+
+    def resize(self, x: Tensor, size) -> Tensor:
+        return self._rec("resize", x, tuple(size), image_oracle.resize(x, size))
 
     def optimal_transport(self, pastiche_feature: Tensor, style_feature: Tensor, hist_mode: str) -> Tensor:
         rot = self.rotation_fn(pastiche_feature.shape[-1], self.ot_calls)
         self.ot_calls += 1
-        return ot_oracle.ot_step(pastiche_feature, style_feature, rot, hist_mode)
+        out = ot_oracle.ot_step(pastiche_feature, style_feature, rot, hist_mode)
+        return self._rec("ot_step", pastiche_feature, style_feature, rot, hist_mode, out)
 
     def encode_inputs(self, pastiche: Tensor, styles: List[Tensor], content: Optional[Tensor], size: int):
         """optex.py:45-79."""
         if pastiche.shape[-2] != size and pastiche.shape[-1] != size:
-            style_tens = [image_oracle.resize(s, get_size(size, self.style_scale, s.shape[2], s.shape[3]))
-                          for s in styles]
+            style_tens = [self.resize(s, get_size(size, self.style_scale, s.shape[2], s.shape[3])) for s in styles]
             if content is not None:
                 cont_size = get_size(size, 1.0, content.shape[2], content.shape[3], oversize=True)
-                cont_tens = image_oracle.resize(content, cont_size)
+                cont_tens = self.resize(content, cont_size)
             else:
                 cont_size = (size, size)
                 cont_tens = None
-            pastiche = image_oracle.resize(pastiche, cont_size)
+            pastiche = self.resize(pastiche, cont_size)
         else:
             style_tens, cont_tens = styles, content
         style_features, style_eigvs, content_features = [], [], []
@@ -124,13 +136,16 @@ class OptimalTexture:
             style_features.append(torch.cat([self.encode(depth, s) for s in style_tens]))
             eigvecs = None
             if self.use_pca:
-                style_features[l], eigvecs = self.fit_pca_fn(style_features[l])
+                raw = style_features[l]
+                style_features[l], eigvecs = self.fit_pca_fn(raw)
+                self._rec("fit_pca", raw, eigvecs, style_features[l])
                 style_eigvs.append(eigvecs)
             if cont_tens is not None:
                 cf = self.encode(depth, cont_tens)
                 if self.use_pca:
-                    cf = cf @ eigvecs
-                content_features.append(image_oracle.recentre(cf, style_features[l]))
+                    cf = self._rec("project", cf, eigvecs, False, cf @ eigvecs)
+                content_features.append(self._rec("recentre", cf, style_features[l],
+                                                  image_oracle.recentre(cf, style_features[l])))
         return pastiche, style_features, style_eigvs, content_features
 
     def forward(self, pastiche: Tensor, styles: List[Tensor], content: Optional[Tensor] = None) -> Tensor:
@@ -140,21 +155,30 @@ class OptimalTexture:
                 pastiche, styles, content, self.sizes[p])
             if len(styles) > 1:
                 mask = torch.ceil(self.mask_fn(tuple(style_features[1].shape[1:3])) - self.mixing_alpha)[None, None]
-                style_features = mix_style_features(style_features, mask, self.mixing_alpha, self.hist_mode)
+                mixed = mix_style_features(style_features, mask, self.mixing_alpha, self.hist_mode)
+                for sf, mx in zip(style_features, mixed):
+                    self._rec("mix", sf, mask, self.mixing_alpha, self.hist_mode, mx)
+                style_features = mixed
             for l, depth in enumerate(self.depths):
                 f = self.encode(depth, pastiche)
                 if self.use_pca:
-                    f = f @ style_eigvs[l]
+                    f = self._rec("project", f, style_eigvs[l], False, f @ style_eigvs[l])
+                f_in, first = f, self.ot_calls
+                blend = len(content_features) > 0 and l <= 2
+                strength = self.content_strength / 2 ** (4 - l)
                 for _ in range(self.iters_per_pass_and_layer[p][l - 1]):     # the reference's [l - 1], optex.py:112
                     f = self.optimal_transport(f, style_features[l], self.hist_mode)
-                    if len(content_features) > 0 and l <= 2:
-                        f = f + (self.content_strength / 2 ** (4 - l)) * (content_features[l] - f)
+                    if blend:
+                        f = f + strength * (content_features[l] - f)
+                if self.ot_calls > first:
+                    self._rec("ot_loop", f_in, style_features[l], first, self.ot_calls - first, self.hist_mode,
+                              content_features[l] if blend else None, strength if blend else 0.0, f)
                 if self.use_pca:
-                    f = f @ style_eigvs[l].T
+                    f = self._rec("project", f, style_eigvs[l], True, f @ style_eigvs[l].T)
                 pastiche = self.decode(depth, f)
         if self.color_transfer is not None:
             assert content is not None, "Color transfer requires content image"
-            target = image_oracle.lightness_transfer(content, pastiche)
+            target = self._rec("lightness", content, pastiche, image_oracle.lightness_transfer(content, pastiche))
             if self.color_transfer == "opt":
                 pastiche, target = pastiche.permute(0, 2, 3, 1), target.permute(0, 2, 3, 1)
                 for _ in range(3):

@@ -44,7 +44,8 @@ def close_in_bulk(out, ref, tol=BULK_TOL, frac=OUTLIER_FRAC):
     assert bad.mean() <= frac, f"{bad.mean():.4%} of elements differ by more than {tol * scale:g}"
 
 
-@pytest.mark.parametrize("n,c", [(64, 16), (120, 23), (4096, 64), (16384, 512), (1000, 181), (333, 3)])
+@pytest.mark.parametrize("n,c", [(64, 16), (120, 23), (4096, 64), (16384, 512), (1000, 181), (333, 3),
+                                 (65536, 64), (262144, 64), (65536, 128), (16384, 320), (36864, 512)])
 def test_rotation_gemms_match_fp32_matmul(ob, gemm_mode, n, c):
     g = torch.Generator().manual_seed(n + c)
     x = torch.relu(torch.randn(n, c, generator=g))

@@ -1,18 +1,28 @@
-"""GPU parity: the whole synthesis loop (`OptimalTexture.forward`, optex.py:81-139) on the B200 kernels vs the CPU
-oracle (oracle/texture_oracle.py, pinned BIT-EXACTLY to the real reference's forward on these very cases in
+"""GPU parity: the synthesis loop (`OptimalTexture.forward`, optex.py:81-139) on the B200 kernels vs the CPU oracle
+(oracle/texture_oracle.py, pinned BIT-EXACTLY to the real reference's forward on these very cases in
 tests/test_oracle_golden.py::test_texture_forward_matches_reference).
 
-Same seeded weights, inputs, rotation stream and mask noise on both sides.  With PCA on, the oracle is handed the
-DEVICE's PCA basis (`fit_pca_fn`): an SVD basis is defined only up to sign and to rotations inside near-degenerate
-subspaces, and the rotations that follow are drawn in that basis, so element-wise parity of the loop is only
-meaningful in a shared basis; the PCA itself is compared in tests/test_gpu_pca.py.
+How the loop is compared.  With random-weight networks the loop as a whole is chaotic: the ORACLE run twice, with
+its input pastiche perturbed by 1e-6 (relative), ends 1e-3 (mean) / 1e-2 (max) apart, a 1e-4 perturbation 3e-2 / 0.3
+(measured, fp32 CPU) - no two fp32 implementations of it, the reference on two BLAS builds included, agree
+element-wise at the end.  So parity is stated where it is well posed:
+  1. control flow: the product's `OptimalTexture` with its kernels replaced by the oracle's ops reproduces the real
+     reference's output bit for bit (tests/test_texture_host.py, CPU);
+  2. every stage, TEACHER-FORCED: the oracle records each stage's inputs and output (`trace`), the B200 stage is fed
+     the oracle's inputs and compared with the oracle's output - this file;
+  3. end to end: finite, deterministic, the reference's number of OT calls, and output statistics close to the
+     oracle's (a sanity bound, not a parity claim).
 
-Stated tolerance (floating point, a chain of 10-13 conv layers, PCA projections and 20-24 OT iterations per case):
-with scale = max |reference output|,
-  * smooth modes (pca, chol):  every element within 5e-3 * scale, mean |err| <= 5e-4 * scale;
-  * cdf (and the 3 cdf steps of colour transfer "opt"): the map is discontinuous at bin edges, a last-bit
-    difference moves isolated elements by one bin and the decoders spread it over their receptive field:
-    >= 98 % of the elements within 5e-3 * scale, mean |err| <= 1e-3 * scale.
+Stated tolerances (floating point), relative to max |reference stage output| unless noted:
+  resize 1e-5 (absolute, inputs in [0,1]) | encode / decode 1e-3 (13 conv layers of 3xTF32 GEMMs, see test_gpu_vgg.py)
+  project / unproject 2e-5 | recentre 2e-6 | mix (two chol / cdf hist_match + blend) 1e-3, cdf in bulk
+  fit_pca: k equal, projector within 2e-4 (see test_gpu_pca.py)
+  ot_step / ot_loop, smooth modes (pca, chol): 2e-3 - the oracle's own fp32 answer is 7e-4 from its fp64 answer on
+    the worst-conditioned of these steps (covariance eigenvalues 1 .. 2.6e5)
+  ot_step cdf: >= 99 % of the elements within 2e-3 * (99.9th percentile of |reference|): the map is discontinuous
+    at bin edges, and the reference's `interp` (histmatch.py:72-92) extrapolates isolated elements to 1e5 x the
+    data range, so neither max-norm nor max-scale is meaningful; multi-iteration cdf loops are compared step by step
+  lightness transfer 2e-5 * scale.
 The measured errors are written to gpurun_out/texture_parity.json."""
 import json
 import os
@@ -25,6 +35,7 @@ from oracle import texture_cases, texture_oracle
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CASES = ["synth_pca", "mix_content_chol_opt", "nopca_cdf_lum"]
 
 
 @pytest.fixture(scope="module")
@@ -32,15 +43,6 @@ def ob():
     import optimaltextures_b200 as ob
 
     return ob
-
-
-def _device_pca(ob):
-    def fit(x):
-        feats, eig = ob.fit_pca(x.cuda())
-        eig = eig.cpu()
-        return x @ eig, eig
-
-    return fit
 
 
 def _record(name, stats):
@@ -54,68 +56,144 @@ def _record(name, stats):
         pass
 
 
-def _run_both(ob, name, **override):
-    from optimaltextures_b200 import texture
-
-    kwargs, styles, content, pastiche = texture_cases.texture_inputs(name)
-    kwargs = dict(kwargs, **override)
-    sd = texture_cases.state_dicts()
+def _mask_noise():
     noise = {}
 
-    def mask_noise(shape):
+    def fn(shape):
         if shape not in noise:
             noise[shape] = torch.rand(shape, generator=torch.Generator().manual_seed(99))
         return noise[shape]
 
-    ref_model = texture_oracle.OptimalTexture(sd, rotation_fn=texture_cases.texture_rotation, mask_fn=mask_noise,
-                                              fit_pca_fn=_device_pca(ob), **kwargs)
+    return fn
+
+
+def _oracle_trace(name):
+    kwargs, styles, content, pastiche = texture_cases.texture_inputs(name)
+    model = texture_oracle.OptimalTexture(texture_cases.state_dicts(), rotation_fn=texture_cases.texture_rotation,
+                                          mask_fn=_mask_noise(), **kwargs)
+    model.trace = []
     with torch.inference_mode():
-        want = ref_model.forward(pastiche.clone(), [s.clone() for s in styles],
-                                 None if content is None else content.clone())
-    model = texture.OptimalTexture(state_dicts=sd, rotations=texture_cases.texture_rotation, mixing_noise=mask_noise,
-                                   **kwargs)
-    assert model.shared_encoder
-    got = model.forward(pastiche.cuda(), [s.cuda() for s in styles], None if content is None else content.cuda())
-    torch.cuda.synchronize()
-    assert model.ot_calls == ref_model.ot_calls
-    return got.cpu(), want
+        out = model.forward(pastiche.clone(), [s.clone() for s in styles], None if content is None else content.clone())
+    return model, out
 
 
-def _stats(got, want):
+def rel(got, want):
+    got, want = got.double().cpu(), want.double()
     assert got.shape == want.shape, f"{tuple(got.shape)} vs {tuple(want.shape)}"
-    assert torch.isfinite(got).all()
-    scale = max(1.0, float(want.abs().max()))
-    err = (got.double() - want.double()).abs() / scale
-    return {"scale": scale, "max": float(err.max()), "mean": float(err.mean()),
-            "frac_within_5e-3": float((err <= 5e-3).double().mean())}
+    return float((got - want).abs().max() / max(1.0, float(want.abs().max())))
 
 
-def test_synthesis_pca(ob):
-    got, want = _run_both(ob, "synth_pca")
-    st = _stats(got, want)
-    _record("synth_pca", st)
-    assert st["max"] <= 5e-3 and st["mean"] <= 5e-4, st
+def bulk(got, want, tol=2e-3):
+    got, want = got.double().cpu().flatten(), want.double().flatten()
+    scale = max(1.0, float(torch.quantile(want.abs()[:: max(1, want.numel() // 1000000)], 0.999)))
+    return float(((got - want).abs() <= tol * scale).double().mean())
 
 
-def test_mixing_content_chol_colour_opt(ob):
-    got, want = _run_both(ob, "mix_content_chol_opt")
-    st = _stats(got, want)
-    _record("mix_content_chol_opt", st)
-    assert st["frac_within_5e-3"] >= 0.98 and st["mean"] <= 1e-3, st
+@pytest.mark.parametrize("name", CASES)
+def test_every_stage_teacher_forced(ob, name):
+    from optimaltextures_b200 import texture, util, vgg
+
+    model, _ = _oracle_trace(name)
+    sd = texture_cases.state_dicts()
+    enc = {d: vgg.Encoder(d, state_dict=sd[("encoder", d)]) for d in range(1, 6)}
+    dec = {d: vgg.Decoder(d, state_dict=sd[("decoder", d)]) for d in range(1, 6)}
+    worst = {}
+
+    def note(stage, value, limit, lower_is_better=True):
+        key = stage
+        worst[key] = max(worst.get(key, 0.0), value) if lower_is_better else min(worst.get(key, 1.0), value)
+        ok = value <= limit if lower_is_better else value >= limit
+        assert ok, f"{name}: stage {stage}: {value:.3e} vs limit {limit:.3e}"
+
+    seen = set()
+    for entry in model.trace:
+        stage = entry[0]
+        seen.add(stage)
+        if stage == "resize":
+            _, x, size, out = entry
+            note("resize", float((util.resize(x.cuda(), size).cpu() - out).abs().max()), 1e-5)
+        elif stage == "encode":
+            _, d, x, out = entry
+            note("encode", rel(enc[d](x.cuda()), out), 1e-3)
+        elif stage == "decode":
+            _, d, f, out = entry
+            note("decode", rel(dec[d](f.cuda()), out), 1e-3)
+        elif stage == "fit_pca":
+            _, raw, eig, feats = entry
+            f_gpu, e_gpu = ob.fit_pca(raw.cuda())
+            assert e_gpu.shape == eig.shape, f"{name}: fit_pca kept {e_gpu.shape[1]} components, reference {eig.shape[1]}"
+            e_gpu = e_gpu.cpu()
+            note("fit_pca_projector", float((e_gpu @ e_gpu.T - eig @ eig.T).abs().max()), 2e-4)
+        elif stage == "project":
+            _, x, eig, transpose, out = entry
+            note("project", rel(ob.pca_project(x.cuda(), eig.cuda(), transpose=transpose), out), 2e-5)
+        elif stage == "recentre":
+            _, cf, sf, out = entry
+            note("recentre", rel(texture.recentre(cf.cuda(), sf.cuda()), out), 2e-6)
+        elif stage == "mix":
+            _, sf, mask, alpha, mode, out = entry
+            got = texture.mix_style_features([sf.cuda()], mask.cuda(), alpha, mode)[0]
+            if mode == "cdf":
+                note("mix_bulk", bulk(got, out), 0.99, lower_is_better=False)
+            else:
+                note("mix", rel(got, out), 1e-3)
+        elif stage == "ot_step":
+            _, f, style, rot, mode, out = entry
+            got = ob.optimal_transport(f.cuda(), style.cuda(), mode, rotation=rot.float().cuda())
+            if mode == "cdf":
+                note(f"ot_step_cdf_bulk(c={f.shape[-1]})", bulk(got, out), 0.99, lower_is_better=False)
+            else:
+                note("ot_step", rel(got, out), 2e-3)
+        elif stage == "ot_loop":
+            _, f, style, first, n, mode, content, strength, out = entry
+            if mode == "cdf":
+                continue                      # compared step by step above
+            rots = torch.stack([texture_cases.texture_rotation(f.shape[-1], first + i).float() for i in range(n)])
+            got = ob.ot_loop(f.cuda(), style.cuda(), mode, n, rotations=rots.cuda(),
+                             content=None if content is None else content.cuda(), content_strength=strength)
+            note("ot_loop", rel(got, out), 2e-3)
+        elif stage == "lightness":
+            _, content, pastiche, out = entry
+            note("lightness", rel(texture.lightness_transfer(content.cuda(), pastiche.cuda()), out), 2e-5)
+        else:
+            raise AssertionError(f"unknown stage {stage}")
+    _record(f"stages_{name}", worst)
+    assert {"encode", "decode", "ot_step"} <= seen
 
 
-def test_mixing_content_chol_no_colour(ob):
-    got, want = _run_both(ob, "mix_content_chol_opt", color_transfer=None)
-    st = _stats(got, want)
-    _record("mix_content_chol", st)
-    assert st["max"] <= 5e-3 and st["mean"] <= 5e-4, st
+def _run_product(ob, name, **override):
+    from optimaltextures_b200 import texture
+
+    kwargs, styles, content, pastiche = texture_cases.texture_inputs(name)
+    kwargs = dict(kwargs, **override)
+    model = texture.OptimalTexture(state_dicts=texture_cases.state_dicts(), rotations=texture_cases.texture_rotation,
+                                   mixing_noise=_mask_noise(), **kwargs)
+    assert model.shared_encoder
+    out = model.forward(pastiche.cuda(), [s.cuda() for s in styles], None if content is None else content.cuda())
+    torch.cuda.synchronize()
+    return model, out
 
 
-def test_no_pca_cdf_lum(ob):
-    got, want = _run_both(ob, "nopca_cdf_lum")
-    st = _stats(got, want)
-    _record("nopca_cdf_lum", st)
-    assert st["frac_within_5e-3"] >= 0.98 and st["mean"] <= 1e-3, st
+@pytest.mark.parametrize("name", ["synth_pca", "mix_content_chol_opt"])
+def test_end_to_end_sanity(ob, name):
+    """Same injections on both sides; the chaotic loop is compared through what the algorithm controls: the output's
+    per-channel statistics (and the bookkeeping: shapes, call counts, determinism)."""
+    ref_model, want = _oracle_trace(name)
+    model, got = _run_product(ob, name)
+    model2, got2 = _run_product(ob, name)
+    assert model.ot_calls == ref_model.ot_calls
+    assert got.shape == want.shape and torch.isfinite(got).all()
+    assert torch.equal(got, got2), "the loop is not deterministic"
+    got = got.cpu().double()
+    want = want.double()
+    scale = float(want.abs().max())
+    stats = {"mean_abs_err_over_scale": float((got - want).abs().mean()) / scale,
+             "channel_mean_err": float((got.mean((0, 2, 3)) - want.mean((0, 2, 3))).abs().max()) / scale,
+             "channel_std_ratio": (got.std((0, 2, 3)) / want.std((0, 2, 3))).tolist()}
+    _record(f"e2e_{name}", stats)
+    assert stats["mean_abs_err_over_scale"] <= 0.1
+    assert stats["channel_mean_err"] <= 0.05
+    assert all(0.8 <= r <= 1.25 for r in stats["channel_std_ratio"])
 
 
 def test_device_rotations_and_schedule(ob):
@@ -134,6 +212,13 @@ def test_device_rotations_and_schedule(ob):
         assert model.ot_calls == sum(its[p][l - 1] for p in range(model.passes) for l in range(5))
     assert outs[0].shape == (1, 3, 64, 64) and torch.isfinite(outs[0]).all()
     assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("name", ["nopca_cdf_lum", "mix_content_chol_opt"])
+def test_colour_transfer_and_content_paths_run(ob, name):
+    model, got = _run_product(ob, name)
+    kwargs, styles, content, pastiche = texture_cases.texture_inputs(name)
+    assert got.shape == content.shape and torch.isfinite(got).all()
 
 
 def test_no_multires_runs(ob):

@@ -124,3 +124,42 @@ def test_errors(ob):
     enc = vgg.Encoder(1, state_dict=vgg_oracle.random_state_dict("encoder", 1))
     with pytest.raises(ValueError):
         enc(torch.zeros(1, 4, 8, 8).cuda())
+
+
+@pytest.mark.parametrize("size,depth", [(256, 3), (192, 4)])
+def test_encoder_layers_at_image_size(ob, size, depth):
+    """Every layer of the encoder at a real pass size (256^2 = pass 0 of every multires run): tens of thousands of
+    GEMM rows, i.e. several im2col chunks per layer and several tiles per CTA - each layer fed the oracle's input,
+    run three times: parity per layer and bit-identical repeats."""
+    from optimaltextures_b200 import vgg
+
+    sd = vgg_oracle.random_state_dict("encoder", depth)
+    enc = vgg.Encoder(depth, state_dict=sd)
+    x = torch.rand(1, 3, size, size, generator=torch.Generator().manual_seed(size))
+    wb = vgg_oracle.pairs(sd)
+    cur = F.conv2d(x, wb[0][0], wb[0][1])
+    for i, ((pre, cin, cout, relu), (w, b)) in enumerate(zip(vgg_oracle.encoder_convs(depth), wb[1:])):
+        ref = vgg_oracle._layer(cur, pre, w, b, relu)
+        if i == 0:
+            outs = [enc.layers[0].run(x.cuda(), src_nchw=True) for _ in range(3)]
+        else:
+            inp = cur.permute(0, 2, 3, 1).contiguous().cuda()
+            outs = [enc.layers[i].run(inp) for _ in range(3)]
+        torch.cuda.synchronize()
+        assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2]), f"layer {i} is not deterministic"
+        close(outs[0], ref.permute(0, 2, 3, 1), LAYER_TOL["auto"])
+        cur = ref
+
+
+def test_encoder_decoder_stack_256(ob):
+    """Encoder(5) -> Decoder(5) at 256^2 vs the oracle (the chain every pass of the synthesis loop runs)."""
+    from optimaltextures_b200 import vgg
+
+    esd, dsd = vgg_oracle.random_state_dict("encoder", 5), vgg_oracle.random_state_dict("decoder", 5)
+    x = torch.rand(1, 3, 256, 256, generator=torch.Generator().manual_seed(3))
+    f_ref = vgg_oracle.encoder_forward(x, esd, 5)
+    f = vgg.Encoder(5, state_dict=esd)(x.cuda())
+    close(f, f_ref, STACK_TOL["auto"])
+    img_ref = vgg_oracle.decoder_forward(f_ref, dsd, 5)
+    img = vgg.Decoder(5, state_dict=dsd)(f_ref.cuda())
+    close(img, img_ref, STACK_TOL["auto"])

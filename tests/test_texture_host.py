@@ -87,3 +87,60 @@ def test_hls_round_trip_and_known_colours():
     np.testing.assert_allclose(image_oracle.hls_to_rgb(image_oracle.rgb_to_hls(x)).numpy(), x.numpy(), atol=2e-6)
     same = image_oracle.lightness_transfer(x, x)
     np.testing.assert_allclose(same.numpy(), x.numpy(), atol=2e-6)
+
+
+# ---------------------------------------------------------------------------------------------- control flow
+@pytest.mark.parametrize("name", ["synth_pca", "mix_content_chol_opt", "nopca_cdf_lum"])
+def test_product_control_flow_matches_reference(golden, monkeypatch, name):
+    """The product's `OptimalTexture` (optimaltextures_b200/texture.py) with each of its KERNEL calls replaced by the
+    oracle's op for that stage reproduces the real reference's output (tests/golden/texture.npz) bit for bit: the
+    orchestration - pass sizes, resize rule, per-layer iteration counts with the [l - 1] quirk, content strengths
+    and the l <= 2 rule, mixing mask, colour-transfer branches, the order of RNG / rotation consumption - is the
+    reference's.  (The kernels themselves are compared stage by stage on the GPU, tests/test_gpu_texture.py.)"""
+    from optimaltextures_b200 import texture
+    from oracle import ot_oracle, texture_cases, vgg_oracle
+
+    class Enc:
+        def __init__(self, d, state_dict=None, models_dir=None, device=None):
+            self.depth, self.sd, self.layers = d, state_dict, []
+
+        def forward_all(self, x):
+            return vgg_oracle.encoder_forward(x, self.sd, self.depth, all_depths=True)
+
+        def __call__(self, x):
+            return vgg_oracle.encoder_forward(x, self.sd, self.depth)
+
+    class Dec:
+        def __init__(self, d, state_dict=None, models_dir=None, device=None):
+            self.depth, self.sd = d, state_dict
+
+        def __call__(self, x):
+            return vgg_oracle.decoder_forward(x, self.sd, self.depth)
+
+    def ot_loop(f, s, mode, iters, rotations=None, content=None, content_strength=0.0):
+        for r in rotations:
+            f = ot_oracle.ot_step(f, s, r, mode)
+            if content is not None:
+                f = f + content_strength * (content - f)
+        return f
+
+    monkeypatch.setattr(texture, "require_cuda", lambda *t: torch.device("cpu"))
+    monkeypatch.setattr(texture._util, "resize", image_oracle.resize)
+    monkeypatch.setattr(texture._vgg, "Encoder", Enc)
+    monkeypatch.setattr(texture._vgg, "Decoder", Dec)
+    monkeypatch.setattr(texture._optex, "fit_pca", ot_oracle.fit_pca)
+    monkeypatch.setattr(texture._optex, "pca_project", lambda x, v, transpose=False: x @ (v.T if transpose else v))
+    monkeypatch.setattr(texture._optex, "ot_loop", ot_loop)
+    monkeypatch.setattr(texture, "recentre", image_oracle.recentre)
+    monkeypatch.setattr(texture, "lightness_transfer", image_oracle.lightness_transfer)
+    monkeypatch.setattr(texture, "mix_style_features", texture_oracle.mix_style_features)
+
+    g = golden("texture")
+    kwargs, styles, content, pastiche = texture_cases.texture_inputs(name)
+    model = texture.OptimalTexture(state_dicts=texture_cases.state_dicts(), rotations=texture_cases.texture_rotation,
+                                   device="cpu", **kwargs)
+    torch.manual_seed(77)
+    with torch.inference_mode():
+        out = model.forward(pastiche, styles, content)
+    assert model.ot_calls == int(g[f"{name}_calls"])
+    np.testing.assert_array_equal(out.contiguous().numpy(), g[f"{name}_out"])
