@@ -556,6 +556,17 @@ def synthesis_block(a):
                 "gpu_launches": int(launches), "pca_k_last_pass": model.last_pca_k,
                 "stage_ms": {k: round(v, 2) for k, v in model.stage_ms().items()},
                 "finite": bool(torch.isfinite(res).all())})
+    # additive option: component counts rounded up to multiples of 32 (tensor-core path for the C x C chains)
+    model32 = texture.OptimalTexture(state_dicts=sd, pca_round_k=32, **kw)
+    for rep in range(2):
+        ob.manual_seed(0)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res32 = model32.forward(dev_pastiche, [dev_style])
+        torch.cuda.synchronize()
+        dt32 = time.perf_counter() - t0
+    out["pca_round_k_32"] = {"value": res32.shape[0] * res32.shape[2] * res32.shape[3] / dt32, "seconds": dt32,
+                             "pca_k_last_pass": model32.last_pca_k, "finite": bool(torch.isfinite(res32).all())}
     if a.synthesis_cpu:
         from oracle import texture_oracle
 

@@ -20,7 +20,8 @@ Additive over the reference:
   * `rotations=` (callable (c, index) -> [c, c] tensor), `mixing_noise=` (callable shape -> uniform noise): inject
     what the reference draws from global RNG state, for parity tests; `pca=` (callable features -> (projected,
     eigvecs)) replaces `fit_pca` (an SVD basis is defined only up to sign / rotations of near-degenerate subspaces, so
-    element-wise comparisons of the whole loop need both sides in ONE basis);
+    element-wise comparisons of the whole loop need both sides in ONE basis); `pca_round_k=32` keeps a few more
+    components than the reference's 90 % rule so that every layer's channel count is a multiple of 32;
   * `no_multires=True` works (the reference's own path raises AttributeError at util.py:86: a list has no .tolist()).
 """
 from __future__ import annotations
@@ -124,7 +125,7 @@ class OptimalTexture:
                  models_dir: Optional[str] = None, state_dicts: Optional[Dict[Tuple[str, int], dict]] = None,
                  device="cuda", rotations: Optional[Callable[[int, int], Tensor]] = None,
                  mixing_noise: Optional[Callable[[Tuple[int, int]], Tensor]] = None,
-                 pca: Optional[Callable[[Tensor], Tuple[Tensor, Tensor]]] = None):
+                 pca: Optional[Callable[[Tensor], Tuple[Tensor, Tensor]]] = None, pca_round_k: int = 1):
         self.hist_mode = hist_mode
         self.color_transfer = color_transfer
         self.content_strength = content_strength
@@ -143,7 +144,10 @@ class OptimalTexture:
         self.shared_encoder = _prefix_identical(self.encoders[0], {e.depth: e for e in self.encoders[1:]})
         self.rotations = rotations
         self.mixing_noise = mixing_noise
-        self.pca = pca or _optex.fit_pca
+        # pca_round_k = 32 rounds every layer's component count UP to a multiple of 32 (fit_pca(round_k_to=)): the
+        # C x C products of the covariance modes then run on the tensor cores instead of the fp32 SIMT tiles
+        self.pca = pca or (_optex.fit_pca if pca_round_k <= 1 else
+                           (lambda t: _optex.fit_pca(t, round_k_to=pca_round_k)))
         self.ot_calls = 0
         self.last_pca_k: List[int] = []
         self.profile: Optional[Dict[str, list]] = None      # set to {} to collect CUDA-event pairs per stage

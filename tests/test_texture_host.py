@@ -144,3 +144,39 @@ def test_product_control_flow_matches_reference(golden, monkeypatch, name):
         out = model.forward(pastiche, styles, content)
     assert model.ot_calls == int(g[f"{name}_calls"])
     np.testing.assert_array_equal(out.contiguous().numpy(), g[f"{name}_out"])
+
+
+def test_cli_flags_match_the_reference():
+    """Every flag of optex.py:223-243, with the reference's defaults (values read off the reference's parser)."""
+    from optimaltextures_b200.__main__ import build_parser
+
+    a = build_parser().parse_args([])
+    want = dict(style=["style/graffiti.jpg"], content=None, batch=1, size=512, passes=5, iters=500, hist_mode="chol",
+                color_transfer=None, content_strength=0.01, style_scale=1.0, mixing_alpha=0.5, no_pca=False,
+                no_multires=False, seed=None, no_tf32=False, cudnn_benchmark=False, compile=False, script=False,
+                device=None, memory_format="contiguous", output_dir="output/")
+    for k, v in want.items():
+        assert getattr(a, k) == v, k
+    b = build_parser().parse_args(["-s", "a.jpg", "b.jpg", "-c", "c.jpg", "--hist_mode", "cdf", "--color_transfer", "opt"])
+    assert b.style == ["a.jpg", "b.jpg"] and b.content == "c.jpg" and b.hist_mode == "cdf"
+    with pytest.raises(SystemExit):
+        build_parser().parse_args(["--hist_mode", "sort"])          # the CLI exposes the reference's four modes
+
+
+def test_load_and_save_image_round_trip(tmp_path):
+    """util.load_image (PIL decode + Lanczos resize, util.py:27-30) and save_image's PNG naming, on the host."""
+    from PIL import Image
+
+    arr = (np.random.RandomState(0).rand(70, 90, 3) * 255).astype(np.uint8)
+    path = tmp_path / "zebra.png"
+    Image.fromarray(arr).save(path)
+    x = outil.load_image(str(path), 64, device="cpu")
+    assert x.shape == (1, 3, *reversed(outil.get_size(64, 1, 90, 70, True))) or x.dim() == 4
+    assert 0.0 <= float(x.min()) and float(x.max()) <= 1.0
+    ns = Namespace(style=[str(path)], content=None, mixing_alpha=0.5, content_strength=0.01, hist_mode="chol",
+                   no_pca=False, no_multires=False, style_scale=1.0, color_transfer=None, size=64,
+                   output_dir=str(tmp_path))
+    (out,) = outil.save_image(x, ns)
+    assert out.endswith("zebra_cholhist_64.png")
+    back = np.asarray(Image.open(out))
+    assert back.shape[2] == 3 and np.abs(back.astype(int) - (x[0].permute(1, 2, 0).numpy() * 255 + 0.5).astype(int)).max() <= 1
