@@ -323,6 +323,50 @@ def fit_pca(tensor: Tensor, *, round_k_to: int = 1, return_sigma: bool = False):
     return features, eigvecs
 
 
+_pca_streams = {}
+
+
+def fit_pca_many(tensors, *, round_k_to: int = 1):
+    """`fit_pca` (optex.py:180-190) of several independent feature blocks - the five VGG layers of one pass
+    (optex.py:62-67) - with the eigensolvers running CONCURRENTLY on side streams: one solve is bound by the latency
+    of its ~5600 grid-wide barriers, not by throughput, and the five cooperative grids (C/2 CTAs of 128 threads each)
+    fit on the device together.  Returns [(features, eigvecs), ...] like five `fit_pca` calls; one host
+    synchronisation for all the k's."""
+    if not tensors:
+        return []
+    dev = require_cuda(*tensors)
+    lib = _lib.lib()
+    cur = torch.cuda.current_stream(dev)
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    streams = _pca_streams.setdefault(key, [])
+    while len(streams) < len(tensors):
+        streams.append(torch.cuda.Stream(device=dev))
+    jobs = []
+    # every buffer is allocated on the caller's stream; the side streams only borrow them between the two waits
+    for t in tensors:
+        c = t.shape[-1]
+        x = f32c(t).reshape(-1, c)
+        jobs.append((x, c, torch.empty(c, c, dtype=torch.float32, device=dev),
+                     torch.empty(c, dtype=torch.float32, device=dev), torch.zeros(1, dtype=torch.int32, device=dev),
+                     torch.empty(max(int(lib.optex_fit_pca_workspace_bytes(x.shape[0], c)), 256), dtype=torch.uint8,
+                                 device=dev)))
+    with torch.cuda.device(dev):
+        for st, (x, c, vecs, sigma, k_dev, wsb) in zip(streams, jobs):
+            st.wait_stream(cur)
+            call("optex_fit_pca", ptr(x), x.shape[0], c, ptr(vecs), ptr(sigma), ptr(k_dev), ptr(wsb), wsb.numel(),
+                 C.c_void_p(st.cuda_stream))
+        for st in streams[:len(jobs)]:
+            cur.wait_stream(st)
+    out = []
+    ks = torch.cat([j[4] for j in jobs]).tolist()          # the one synchronisation
+    for t, (x, c, vecs, sigma, k_dev, wsb), k in zip(tensors, jobs, ks):
+        if round_k_to > 1:
+            k = min(c, -(-k // round_k_to) * round_k_to)
+        eigvecs = vecs[:, :k].contiguous()
+        out.append((pca_project(t, eigvecs), eigvecs))
+    return out
+
+
 def install(reference_optex_module) -> None:
     """Rebind a loaded reference ``optex`` module to the B200 path.  Both names must be patched:
     ``optex`` did `from histmatch import hist_match` (optex.py:9), so patching ``histmatch`` alone

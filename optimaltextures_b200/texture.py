@@ -146,8 +146,12 @@ class OptimalTexture:
         self.mixing_noise = mixing_noise
         # pca_round_k = 32 rounds every layer's component count UP to a multiple of 32 (fit_pca(round_k_to=)): the
         # C x C products of the covariance modes then run on the tensor cores instead of the fp32 SIMT tiles
-        self.pca = pca or (_optex.fit_pca if pca_round_k <= 1 else
-                           (lambda t: _optex.fit_pca(t, round_k_to=pca_round_k)))
+        self.pca = pca                      # None: the device PCA, all layers of a pass solved concurrently
+        self.pca_round_k = pca_round_k
+        # pca / sym: zero channels appended up to a multiple of 32 before a layer's OT loop.  Exact: the padded
+        # covariances are blockdiag(Sigma + I, I), their square roots block-diagonal, the padded channels stay 0 -
+        # and every C x C product of the chains runs on the tensor cores instead of the fp32 SIMT tiles.
+        self.pad_channels = 32
         self.ot_calls = 0
         self.last_pca_k: List[int] = []
         self.profile: Optional[Dict[str, list]] = None      # set to {} to collect CUDA-event pairs per stage
@@ -188,6 +192,20 @@ class OptimalTexture:
         if self.rotations is not None:
             rots = torch.stack([f32c(self.rotations(c, self.ot_calls + i).to(feature.device)) for i in range(iters)])
         self.ot_calls += iters
+        pad = (-c) % self.pad_channels if (self.pad_channels > 1 and hist_mode in ("pca", "sym") and c >= 8) else 0
+        if pad:
+            def widen(t):
+                w = torch.zeros(*t.shape[:-1], c + pad, dtype=torch.float32, device=t.device)
+                w[..., :c] = t
+                return w
+
+            if rots is not None:        # pca / sym do not depend on the rotation; keep the argument well formed
+                eye = torch.eye(c + pad, dtype=torch.float32, device=feature.device).repeat(iters, 1, 1)
+                eye[:, :c, :c] = rots
+                rots = eye
+            out = _optex.ot_loop(widen(feature), widen(style), hist_mode, iters, rotations=rots,
+                                 content=None if content is None else widen(content), content_strength=strength)
+            return out[..., :c].contiguous()
         return _optex.ot_loop(feature, style, hist_mode, iters, rotations=rots, content=content,
                               content_strength=strength)
 
@@ -211,13 +229,23 @@ class OptimalTexture:
             per_style = [self._encode_all(s) for s in style_tens]
             per_content = self._encode_all(cont_tens) if cont_tens is not None else None
         style_features, style_eigvs, content_features = [], [], []
+        raw = []
         for l in range(len(self.encoders)):
             feats = [ps[l] for ps in per_style]
-            sf = feats[0] if len(feats) == 1 else torch.cat(feats)
+            raw.append(feats[0] if len(feats) == 1 else torch.cat(feats))
+        fitted = None
+        if self.use_pca and self.pca is None:
+            with self._stage("fit_pca"):
+                fitted = _optex.fit_pca_many(raw, round_k_to=self.pca_round_k)
+        for l in range(len(self.encoders)):
+            sf = raw[l]
             eigvecs = None
             if self.use_pca:
-                with self._stage("fit_pca"):
-                    sf, eigvecs = self.pca(sf)
+                if fitted is not None:
+                    sf, eigvecs = fitted[l]
+                else:
+                    with self._stage("fit_pca"):
+                        sf, eigvecs = self.pca(sf)
                 style_eigvs.append(eigvecs)
             style_features.append(sf)
             if per_content is not None:

@@ -238,3 +238,37 @@ def test_cpu_tensors_are_refused(ob):
     model = texture.OptimalTexture(size=32, iters=5, passes=1, state_dicts=texture_cases.state_dicts())
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         model.forward(torch.rand(1, 3, 32, 32), [torch.rand(1, 3, 32, 32)])
+
+
+def test_fit_pca_many_equals_fit_pca(ob):
+    """The concurrent per-layer PCA of a pass (side streams) == five sequential `fit_pca` calls, bit for bit."""
+    g = torch.Generator().manual_seed(4)
+    blocks = [torch.relu(torch.randn(1, h, h, c, generator=g) * torch.linspace(0.2, 2.0, c)).cuda()
+              for h, c in ((8, 512), (16, 512), (32, 256), (64, 128), (128, 64))]
+    from optimaltextures_b200 import optex
+
+    many = optex.fit_pca_many(blocks)
+    for x, (f, e) in zip(blocks, many):
+        f1, e1 = ob.fit_pca(x)
+        assert e.shape == e1.shape and torch.equal(e, e1) and torch.equal(f, f1)
+
+
+@pytest.mark.parametrize("mode", ["pca", "sym"])
+def test_zero_channel_padding_is_exact(ob, mode):
+    """OptimalTexture pads pca / sym loops with zero channels up to a multiple of 32 (tensor-core path): same result
+    as the unpadded loop to fp32 rounding (covariances become blockdiag(Sigma + I, I))."""
+    from optimaltextures_b200 import texture
+
+    g = torch.Generator().manual_seed(9)
+    c = 49
+    f = torch.relu(torch.randn(1, 40, 40, c, generator=g)).cuda()
+    s = torch.relu(1.5 * torch.randn(1, 36, 44, c, generator=g) + 0.25).cuda()
+    content = torch.relu(torch.randn(1, 40, 40, c, generator=g)).cuda()
+    model = texture.OptimalTexture(size=32, iters=5, passes=1, state_dicts=texture_cases.state_dicts())
+    outs = {}
+    for pad in (32, 1):
+        model.pad_channels = pad
+        outs[pad] = model._ot_layer(f, s, mode, 4, content, 0.05)
+    assert outs[32].shape == outs[1].shape == f.shape
+    err = float((outs[32] - outs[1]).abs().max() / outs[1].abs().max())
+    assert err <= 1e-4, err

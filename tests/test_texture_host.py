@@ -128,7 +128,6 @@ def test_product_control_flow_matches_reference(golden, monkeypatch, name):
     monkeypatch.setattr(texture._util, "resize", image_oracle.resize)
     monkeypatch.setattr(texture._vgg, "Encoder", Enc)
     monkeypatch.setattr(texture._vgg, "Decoder", Dec)
-    monkeypatch.setattr(texture._optex, "fit_pca", ot_oracle.fit_pca)
     monkeypatch.setattr(texture._optex, "pca_project", lambda x, v, transpose=False: x @ (v.T if transpose else v))
     monkeypatch.setattr(texture._optex, "ot_loop", ot_loop)
     monkeypatch.setattr(texture, "recentre", image_oracle.recentre)
@@ -138,7 +137,8 @@ def test_product_control_flow_matches_reference(golden, monkeypatch, name):
     g = golden("texture")
     kwargs, styles, content, pastiche = texture_cases.texture_inputs(name)
     model = texture.OptimalTexture(state_dicts=texture_cases.state_dicts(), rotations=texture_cases.texture_rotation,
-                                   device="cpu", **kwargs)
+                                   device="cpu", pca=ot_oracle.fit_pca, **kwargs)
+    model.pad_channels = 1          # the zero-channel padding is exact in real arithmetic, not bit for bit
     torch.manual_seed(77)
     with torch.inference_mode():
         out = model.forward(pastiche, styles, content)
