@@ -527,12 +527,11 @@ def synthesis_block(a):
     import torch
 
     import optimaltextures_b200 as ob
-    from optimaltextures_b200 import texture
-    from oracle import texture_cases
+    from optimaltextures_b200 import texture, vgg
 
     size = a.synthesis_size
     kw = dict(size=size, iters=500, passes=5, hist_mode="pca")
-    sd = texture_cases.state_dicts()
+    sd = vgg.random_state_dicts(0)
     g = torch.Generator().manual_seed(0)
     style = torch.rand(1, 3, round(size * 736 / 512 / 32) * 32, size, generator=g)
     pastiche = torch.rand(1, 3, size, size, generator=g)

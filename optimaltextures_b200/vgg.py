@@ -56,6 +56,31 @@ def _load_state_dict(state_dict, models_dir, fname):
     return torch.load(os.path.join(models_dir, fname), map_location="cpu")
 
 
+def random_state_dicts(seed: int = 0):
+    """Random-init weights of the reference's architecture, keyed ("encoder"|"decoder", depth) in its state_dict
+    order (vgg.py:14-136): what bench.py and the CLI's --random_weights use where ./models/*.pth are absent.  The
+    encoder keeps the 1x1 colour conv's scale (x255, BGR means) so the activations have the reference's range."""
+    out = {}
+    for depth in range(1, 6):
+        for kind in ("encoder", "decoder"):
+            g = torch.Generator().manual_seed(seed)
+            sd, idx = {}, 0
+            if kind == "encoder":
+                specs = _ENCODER[:_ENCODER_END[depth]]
+                sd["0.weight"] = torch.eye(3).reshape(3, 3, 1, 1) * 255.0 + torch.randn(3, 3, 1, 1, generator=g)
+                sd["0.bias"] = torch.tensor([-103.9, -116.8, -123.7])
+                idx = 1
+            else:
+                specs = [spec for block in _DECODER[5 - depth:] for spec in block]
+            for _, c_in, c_out, _ in specs:
+                scale = (2.0 / (9 * c_in)) ** 0.5 * (0.02 if (kind == "encoder" and c_in == 3) else 1.0)
+                sd[f"{idx}.weight"] = torch.randn(c_out, c_in, 3, 3, generator=g) * scale
+                sd[f"{idx}.bias"] = torch.randn(c_out, generator=g) * 0.05
+                idx += 1
+            out[(kind, depth)] = sd
+    return out
+
+
 def _pairs(state_dict):
     vals = list(state_dict.values())
     if len(vals) % 2:
