@@ -553,6 +553,7 @@ def synthesis_block(a):
         launches = lib.optex_launch_count() - l0
     out.update({"value": res.shape[0] * res.shape[2] * res.shape[3] / dt, "seconds": dt, "ot_iters": model.ot_calls,
                 "gpu_launches": int(launches), "pca_k_last_pass": model.last_pca_k,
+                "pca_jacobi_sweeps_per_pass": model.pca_sweeps,
                 "stage_ms": {k: round(v, 2) for k, v in model.stage_ms().items()},
                 "finite": bool(torch.isfinite(res).all())})
     # additive option: component counts rounded up to multiples of 32 (tensor-core path for the C x C chains)

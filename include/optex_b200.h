@@ -226,6 +226,18 @@ int optex_rotate_inverse(const float *Mt, const float *R, float *out, int64_t n,
 size_t optex_fit_pca_workspace_bytes(int64_t n, int c);
 int optex_fit_pca(const float *X, int64_t n, int c, float *eigvecs, float *sigma,
                   int32_t *k_out, void *workspace, size_t workspace_bytes, void *stream);
+/* The same solve, keeping the eigensolver's FP64 basis between calls (additive; no reference counterpart).
+ * optex.py:62-67 refits the PCA of the SAME style image at every pass's resolution; the bases of consecutive passes
+ * are close, and a Jacobi iteration started from the previous one converges in about half the sweeps.
+ *   basis      [c, c] FP64 on the device, or NULL (then identical to optex_fit_pca).  Rows = the solver's
+ *              orthogonal V in its internal (unsorted) order.  Always written with the final V.
+ *   warm       0: start from the identity (basis is output only);  != 0: start from the rows of `basis`, which must be
+ *              the output of an earlier call with the same c (any orthogonal matrix gives a correct result; a nearby
+ *              one gives a fast one).
+ *   sweeps_out [1] int32 on the device or NULL: Jacobi sweeps run (observability; 40 = not converged). */
+int optex_fit_pca_warm(const float *X, int64_t n, int c, float *eigvecs, float *sigma, int32_t *k_out,
+                       double *basis, int warm, int32_t *sweeps_out, void *workspace,
+                       size_t workspace_bytes, void *stream);
 /* transpose = 0: out[n, k] = X[n, c] V[c, k]      (project onto the basis,  optex.py:110, :188)
  * transpose = 1: out[n, c] = X[n, k] V[c, k]^T    (back to feature space,   optex.py:120)
  * V dense row-major [c, k].  Tensor cores when c and k allow (k % 32 == 0, c % 4 == 0), else fp32 SIMT tiles. */

@@ -24,6 +24,7 @@
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "gemm_tc.cuh"
@@ -42,6 +43,10 @@ constexpr int JT = 128;          // threads per Jacobi pair
 constexpr int MAX_SWEEPS = 40;
 constexpr double JTOL = 1e-12;   // rotate while |w_p . w_q| > JTOL |w_p| |w_q|
 constexpr double JFLOOR = 1e-13; // ... and > (JFLOOR trace G)^2 (keeps null-space noise from rotating for ever)
+// Early exit: the cyclic Jacobi iteration converges quadratically, so a sweep whose LARGEST rotated pair had
+// |w_p . w_q| <= JEXIT |w_p| |w_q| leaves every pair at ~JEXIT^2 - below JTOL - and the "empty" confirming sweep
+// (c - 1 more grid barriers) is not run.  OPTEX_PCA_EXIT=0 restores the run-until-no-rotation rule.
+constexpr double JEXIT = 1e-6;
 
 inline unsigned cdiv(int64_t a, int64_t b) { return (unsigned)((a + b - 1) / b); }
 
@@ -157,6 +162,7 @@ __global__ void __launch_bounds__(256) pca_gram_kernel(const float *__restrict__
 }
 
 // G = sum_z part_z - m (s_i + s_j) + n m^2 (mirrored from the computed tile pairs);  W = G, V = I
+// (warm start: V is NULL and stays what the caller passed in; W then receives G only as the input of pca_warm_kernel)
 __global__ void pca_gram_final_kernel(const double *__restrict__ part, int nz, const double *__restrict__ s,
                                       const double *__restrict__ stat, int c, double *__restrict__ W,
                                       double *__restrict__ V) {
@@ -170,21 +176,71 @@ __global__ void pca_gram_final_kernel(const double *__restrict__ part, int nz, c
     const double m = stat[0], n = stat[1];
     g = g - m * (s[i] + s[j]) + n * m * m;
     W[idx] = g;
-    V[idx] = i == j ? 1.0 : 0.0;
+    if (V) V[idx] = i == j ? 1.0 : 0.0;
+}
+
+// Warm start: W = V G for an orthogonal V carried over from a previous solve (rows w_i = G v_i; G symmetric).
+// 64 x 64 output tiles, 4 x 4 per thread, FP64 FMAs (c^3 of them: 134 M at c = 512, ~20 us).
+__global__ void __launch_bounds__(256) pca_warm_kernel(const double *__restrict__ V, const double *__restrict__ G,
+                                                       double *__restrict__ W, int c) {
+    pdl_wait();
+    __shared__ double As[GK][GT + 1], Bs[GK][GT];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int i0 = blockIdx.y * GT, j0 = blockIdx.x * GT;
+    double acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+    for (int k0 = 0; k0 < c; k0 += GK) {
+        // As[k][i] = V[i0 + i][k0 + k]  (16 consecutive k per row i), Bs[k][j] = G[k0 + k][j0 + j]
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int i = ty + 16 * q, k = tx;
+            As[k][i] = (i0 + i < c && k0 + k < c) ? V[(int64_t)(i0 + i) * c + k0 + k] : 0.0;
+            const int j = tx + 16 * q, kk = ty;
+            Bs[kk][j] = (k0 + kk < c && j0 + j < c) ? G[(int64_t)(k0 + kk) * c + j0 + j] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < GK; ++k) {
+            double a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[k][ty + 16 * i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx + 16 * j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int gi = i0 + ty + 16 * i;
+        if (gi >= c) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int gj = j0 + tx + 16 * j;
+            if (gj < c) W[(int64_t)gi * c + gj] = acc[i][j];
+        }
+    }
 }
 
 // One-sided Jacobi on the rows of W (= G V^T) and V^T; see the file header.  Cooperative launch: gridDim.x CTAs are
 // co-resident, each takes the pairs pi = blockIdx.x, blockIdx.x + gridDim.x, ... of every round.
 // Round-robin schedule of ne = c (+1 if odd) players: round r pairs (ne-1, r) and ((r+i) mod (ne-1), (r-i) mod (ne-1)).
 template <int EPT>
-__global__ void __launch_bounds__(JT) pca_jacobi_kernel(double *W, double *V, int c, int max_sweeps,
-                                                        unsigned *rot_count, int *info) {
+__global__ void __launch_bounds__(JT) pca_jacobi_kernel(double *W, double *V, const double *G, int c, int max_sweeps,
+                                                        unsigned *rot_count, unsigned *rot_max, float exit_r2,
+                                                        int *info) {
     cg::grid_group grid = cg::this_grid();
     __shared__ double red[2][3][JT / 32];
     __shared__ double s_tr[JT / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double tr = 0.0;
-    for (int i = tid; i < c; i += JT) tr += __ldcg(&W[(int64_t)i * c + i]);
+    for (int i = tid; i < c; i += JT) tr += __ldcg(&G[(int64_t)i * c + i]);  // G: W itself on a cold start
     tr = warp_sum(tr);
     if (lane == 0) s_tr[warp] = tr;
     __syncthreads();
@@ -195,6 +251,7 @@ __global__ void __launch_bounds__(JT) pca_jacobi_kernel(double *W, double *V, in
     const int ne = c + (c & 1), n1 = ne - 1, m = ne / 2;
     int par = 0, sweep = 0;
     unsigned local_rot = 0;
+    float local_max = 0.f;  // largest (w_p . w_q)^2 / (|w_p|^2 |w_q|^2) among the pairs this CTA rotated in the sweep
     for (; sweep < max_sweeps; ++sweep) {
         for (int r = 0; r < n1; ++r) {
             for (int pi = blockIdx.x; pi < m; pi += gridDim.x) {
@@ -252,15 +309,24 @@ __global__ void __launch_bounds__(JT) pca_jacobi_kernel(double *W, double *V, in
                         }
                     }
                     ++local_rot;
+                    local_max = fmaxf(local_max, (float)((ga * ga) / (al * be)));
                 }
             }
-            if (r == n1 - 1 && tid == 0 && local_rot) atomicAdd(&rot_count[sweep], local_rot);
+            if (r == n1 - 1 && tid == 0 && local_rot) {
+                atomicAdd(&rot_count[sweep], local_rot);
+                atomicMax(&rot_max[sweep], __float_as_uint(local_max));  // non-negative floats order like their bits
+            }
             grid.sync();
         }
         local_rot = 0;
+        local_max = 0.f;
+        // both words were last written before the barrier above: every CTA takes the same branch
         if (__ldcg(&rot_count[sweep]) == 0u) break;  // a whole sweep without a rotation: converged
+        if (__uint_as_float(__ldcg(&rot_max[sweep])) <= exit_r2) {  // quadratic convergence: now at ~exit_r2^2
+            break;
+        }
     }
-    if (blockIdx.x == 0 && tid == 0) info[0] = sweep < max_sweeps ? sweep + 1 : max_sweeps;
+    if (blockIdx.x == 0 && tid == 0) info[0] = sweep < max_sweeps ? sweep + 1 : max_sweeps;  // sweeps started
 }
 
 // lambda_i = v_i . w_i, descending order, sigma = sqrt(lambda), the 90 % rule (optex.py:184), sign convention
@@ -356,7 +422,7 @@ __global__ void pca_vecs_kernel(const double *__restrict__ V, const int *__restr
 
 struct PcaWs {
     double *colpart, *s, *stat, *gpart, *W, *V;
-    unsigned *rot;
+    unsigned *rot, *rotmax;
     int *info, *perm;
     float *sign;
 };
@@ -381,7 +447,8 @@ size_t pca_layout(int64_t n, int c, PcaWs *w, void *base, size_t cap, bool *ok) 
     l.gpart = ar.take<double>((size_t)gram_splits(n, c) * cc);
     l.W = ar.take<double>(cc);
     l.V = ar.take<double>(cc);
-    l.rot = ar.take<unsigned>(MAX_SWEEPS + 8);
+    l.rot = ar.take<unsigned>(2 * (MAX_SWEEPS + 8));
+    l.rotmax = l.rot + MAX_SWEEPS + 8;
     l.info = ar.take<int>(8);
     l.perm = ar.take<int>(c);
     l.sign = ar.take<float>(c);
@@ -390,8 +457,17 @@ size_t pca_layout(int64_t n, int c, PcaWs *w, void *base, size_t cap, bool *ok) 
     return ar.off;
 }
 
+float jacobi_exit_r2() {
+    static const float v = [] {
+        const char *e = getenv("OPTEX_PCA_EXIT");
+        const double r = e ? atof(e) : JEXIT;
+        return (float)(r * r);
+    }();
+    return v;
+}
+
 template <int EPT>
-int launch_jacobi(const PcaWs &w, int c, cudaStream_t st) {
+int launch_jacobi(const PcaWs &w, const double *G, int c, cudaStream_t st) {
     int per_sm = 0;
     OPTEX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pca_jacobi_kernel<EPT>, JT, 0));
     if (per_sm < 1) {
@@ -404,9 +480,10 @@ int launch_jacobi(const PcaWs &w, int c, cudaStream_t st) {
     if (grid < 1) grid = 1;
     double *W = w.W, *V = w.V;
     int cc = c, ms = MAX_SWEEPS;
-    unsigned *rot = w.rot;
+    unsigned *rot = w.rot, *rotmax = w.rotmax;
     int *info = w.info;
-    void *args[] = {&W, &V, &cc, &ms, &rot, &info};
+    float exit_r2 = jacobi_exit_r2();
+    void *args[] = {&W, &V, &G, &cc, &ms, &rot, &rotmax, &exit_r2, &info};
     OPTEX_CUDA(cudaLaunchCooperativeKernel((const void *)pca_jacobi_kernel<EPT>, dim3(grid), dim3(JT), args, 0, st));
     count_launch();
     return OPTEX_OK;
@@ -424,9 +501,19 @@ extern "C" size_t optex_fit_pca_workspace_bytes(int64_t n, int c) {
 
 extern "C" int optex_fit_pca(const float *X, int64_t n, int c, float *eigvecs, float *sigma, int32_t *k_out,
                              void *workspace, size_t workspace_bytes, void *stream) {
+    return optex_fit_pca_warm(X, n, c, eigvecs, sigma, k_out, nullptr, 0, nullptr, workspace, workspace_bytes, stream);
+}
+
+extern "C" int optex_fit_pca_warm(const float *X, int64_t n, int c, float *eigvecs, float *sigma, int32_t *k_out,
+                                  double *basis, int warm, int32_t *sweeps_out, void *workspace,
+                                  size_t workspace_bytes, void *stream) {
     OPTEX_TRY(require_sm100());
     if (!X || !eigvecs || !sigma || !k_out || n < 1 || c < 1) {
         set_error("optex_fit_pca: NULL pointer or empty shape");
+        return OPTEX_EINVAL;
+    }
+    if (warm && !basis) {
+        set_error("optex_fit_pca_warm: warm != 0 needs the basis of a previous solve");
         return OPTEX_EINVAL;
     }
     if (c > PCA_MAX_C) {
@@ -452,23 +539,32 @@ extern "C" int optex_fit_pca(const float *X, int64_t n, int c, float *eigvecs, f
     gs = (int)((n + rows - 1) / rows);
     launch_pdl(pca_gram_kernel, dim3(T * (T + 1) / 2, gs), dim3(256), 0, st, X, w.gpart, n, c, T, rows);
     OPTEX_LAUNCH_CHECK("pca_gram_kernel");
+    // the solver works directly in the caller's basis buffer when there is one (V is both the start and the result)
+    double *G = w.V;  // warm: the workspace's V slot is free and holds G until W = V G is formed
+    if (basis) w.V = basis;
     launch_pdl(pca_gram_final_kernel, dim3(cdiv((int64_t)c * c, 256)), dim3(256), 0, st, (const double *)w.gpart, gs,
-               (const double *)w.s, (const double *)w.stat, c, w.W, w.V);
+               (const double *)w.s, (const double *)w.stat, c, warm ? G : w.W, warm ? (double *)nullptr : w.V);
     OPTEX_LAUNCH_CHECK("pca_gram_final_kernel");
-    OPTEX_CUDA(cudaMemsetAsync(w.rot, 0, sizeof(unsigned) * (MAX_SWEEPS + 8), st));
+    if (warm) {
+        launch_pdl(pca_warm_kernel, dim3(T, T), dim3(256), 0, st, (const double *)w.V, (const double *)G, w.W, c);
+        OPTEX_LAUNCH_CHECK("pca_warm_kernel");
+    }
+    OPTEX_CUDA(cudaMemsetAsync(w.rot, 0, sizeof(unsigned) * 2 * (MAX_SWEEPS + 8), st));
     if (c <= JT)
-        OPTEX_TRY(launch_jacobi<1>(w, c, st));
+        OPTEX_TRY(launch_jacobi<1>(w, warm ? G : w.W, c, st));
     else if (c <= 2 * JT)
-        OPTEX_TRY(launch_jacobi<2>(w, c, st));
+        OPTEX_TRY(launch_jacobi<2>(w, warm ? G : w.W, c, st));
     else if (c <= 4 * JT)
-        OPTEX_TRY(launch_jacobi<4>(w, c, st));
+        OPTEX_TRY(launch_jacobi<4>(w, warm ? G : w.W, c, st));
     else
-        OPTEX_TRY(launch_jacobi<8>(w, c, st));
+        OPTEX_TRY(launch_jacobi<8>(w, warm ? G : w.W, c, st));
     pca_finish_kernel<<<1, 1024, 0, st>>>(w.W, w.V, c, sigma, k_out, w.perm, w.sign);
     OPTEX_LAUNCH_CHECK("pca_finish_kernel");
     launch_pdl(pca_vecs_kernel, dim3(cdiv(c, 32), cdiv(c, 32)), dim3(32, 8), 0, st, (const double *)w.V,
                (const int *)w.perm, (const float *)w.sign, c, eigvecs);
     OPTEX_LAUNCH_CHECK("pca_vecs_kernel");
+    if (sweeps_out)
+        OPTEX_CUDA(cudaMemcpyAsync(sweeps_out, w.info, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
     return OPTEX_OK;
 }
 

@@ -291,7 +291,8 @@ def pca_project(x: Tensor, eigvecs: Tensor, transpose: bool = False) -> Tensor:
     return out.to(x.dtype)
 
 
-def fit_pca(tensor: Tensor, *, round_k_to: int = 1, return_sigma: bool = False):
+def fit_pca(tensor: Tensor, *, round_k_to: int = 1, return_sigma: bool = False, basis: Optional[Tensor] = None,
+            warm: bool = False):
     """reference: optex.py:180-190.  Returns (features, eigvecs) = (tensor @ V[:, :k], V[:, :k]).
 
     The reference's `torch.svd(tensor - tensor.mean())` is computed on the device as the FP64 eigendecomposition of
@@ -301,7 +302,11 @@ def fit_pca(tensor: Tensor, *, round_k_to: int = 1, return_sigma: bool = False):
     `eigvecs` is positive.
 
     round_k_to (additive): round k UP to a multiple (e.g. 32, which keeps the PCA'd channel count on the
-    tensor-core path of the OT step); the extra components only add explained variance."""
+    tensor-core path of the OT step); the extra components only add explained variance.
+
+    basis / warm (additive): `basis` is a [c, c] float64 CUDA tensor that receives the eigensolver's orthogonal
+    matrix; with warm=True the solve STARTS from it (optex_fit_pca_warm) - same result, fewer Jacobi sweeps when
+    the block resembles the one the basis came from (the same style image at the previous pass's size)."""
     dev = require_cuda(tensor)
     c = tensor.shape[-1]
     x = f32c(tensor).reshape(-1, c)
@@ -311,8 +316,10 @@ def fit_pca(tensor: Tensor, *, round_k_to: int = 1, return_sigma: bool = False):
     sigma = torch.empty(c, dtype=torch.float32, device=dev)
     k_dev = torch.zeros(1, dtype=torch.int32, device=dev)
     wsb = workspace(dev, lib.optex_fit_pca_workspace_bytes(n, c))
+    _check_basis(basis, c, dev, warm)
     with torch.cuda.device(dev):
-        call("optex_fit_pca", ptr(x), n, c, ptr(vecs), ptr(sigma), ptr(k_dev), ptr(wsb), wsb.numel(), stream_ptr(dev))
+        call("optex_fit_pca_warm", ptr(x), n, c, ptr(vecs), ptr(sigma), ptr(k_dev),
+             None if basis is None else ptr(basis), 1 if warm else 0, None, ptr(wsb), wsb.numel(), stream_ptr(dev))
     k = int(k_dev.item())
     if round_k_to > 1:
         k = min(c, -(-k // round_k_to) * round_k_to)
@@ -323,18 +330,33 @@ def fit_pca(tensor: Tensor, *, round_k_to: int = 1, return_sigma: bool = False):
     return features, eigvecs
 
 
+def _check_basis(basis, c, dev, warm):
+    if basis is None:
+        if warm:
+            raise ValueError("warm=True needs basis= (the float64 [c, c] tensor an earlier fit_pca call filled)")
+        return
+    if basis.dtype != torch.float64 or tuple(basis.shape) != (c, c) or not basis.is_contiguous() or basis.device != dev:
+        raise ValueError(f"basis must be a contiguous float64 [{c}, {c}] tensor on {dev}, got {basis.dtype} "
+                         f"{tuple(basis.shape)} on {basis.device}")
+
+
 _pca_streams = {}
 
 
-def fit_pca_many(tensors, *, round_k_to: int = 1):
+def fit_pca_many(tensors, *, round_k_to: int = 1, bases=None, warm=None, sweeps_out: Optional[list] = None):
     """`fit_pca` (optex.py:180-190) of several independent feature blocks - the five VGG layers of one pass
     (optex.py:62-67) - with the eigensolvers running CONCURRENTLY on side streams: one solve is bound by the latency
     of its ~5600 grid-wide barriers, not by throughput, and the five cooperative grids (C/2 CTAs of 128 threads each)
     fit on the device together.  Returns [(features, eigvecs), ...] like five `fit_pca` calls; one host
-    synchronisation for all the k's."""
+    synchronisation for all the k's.  bases / warm: per-tensor `basis=` / `warm=` of `fit_pca`; sweeps_out: a list
+    that receives the Jacobi sweep count of every solve."""
     if not tensors:
         return []
     dev = require_cuda(*tensors)
+    bases = list(bases) if bases is not None else [None] * len(tensors)
+    warm = list(warm) if warm is not None else [False] * len(tensors)
+    if len(bases) != len(tensors) or len(warm) != len(tensors):
+        raise ValueError("bases= and warm= need one entry per tensor")
     lib = _lib.lib()
     cur = torch.cuda.current_stream(dev)
     key = dev.index if dev.index is not None else torch.cuda.current_device()
@@ -347,18 +369,24 @@ def fit_pca_many(tensors, *, round_k_to: int = 1):
         c = t.shape[-1]
         x = f32c(t).reshape(-1, c)
         jobs.append((x, c, torch.empty(c, c, dtype=torch.float32, device=dev),
-                     torch.empty(c, dtype=torch.float32, device=dev), torch.zeros(1, dtype=torch.int32, device=dev),
+                     torch.empty(c, dtype=torch.float32, device=dev), torch.zeros(2, dtype=torch.int32, device=dev),
                      torch.empty(max(int(lib.optex_fit_pca_workspace_bytes(x.shape[0], c)), 256), dtype=torch.uint8,
                                  device=dev)))
+    for (x, c, *_), b, w in zip(jobs, bases, warm):
+        _check_basis(b, c, dev, w)
     with torch.cuda.device(dev):
-        for st, (x, c, vecs, sigma, k_dev, wsb) in zip(streams, jobs):
+        for st, (x, c, vecs, sigma, k_dev, wsb), b, w in zip(streams, jobs, bases, warm):
             st.wait_stream(cur)
-            call("optex_fit_pca", ptr(x), x.shape[0], c, ptr(vecs), ptr(sigma), ptr(k_dev), ptr(wsb), wsb.numel(),
+            call("optex_fit_pca_warm", ptr(x), x.shape[0], c, ptr(vecs), ptr(sigma), ptr(k_dev),
+                 None if b is None else ptr(b), 1 if w else 0, C.c_void_p(k_dev.data_ptr() + 4), ptr(wsb), wsb.numel(),
                  C.c_void_p(st.cuda_stream))
         for st in streams[:len(jobs)]:
             cur.wait_stream(st)
     out = []
-    ks = torch.cat([j[4] for j in jobs]).tolist()          # the one synchronisation
+    ks_sw = torch.stack([j[4] for j in jobs]).tolist()     # the one synchronisation: [k, sweeps] per solve
+    ks = [v[0] for v in ks_sw]
+    if sweeps_out is not None:
+        sweeps_out.extend(v[1] for v in ks_sw)
     for t, (x, c, vecs, sigma, k_dev, wsb), k in zip(tensors, jobs, ks):
         if round_k_to > 1:
             k = min(c, -(-k // round_k_to) * round_k_to)

@@ -22,6 +22,7 @@ Additive over the reference:
     eigvecs)) replaces `fit_pca` (an SVD basis is defined only up to sign / rotations of near-degenerate subspaces, so
     element-wise comparisons of the whole loop need both sides in ONE basis); `pca_round_k=32` keeps a few more
     components than the reference's 90 % rule so that every layer's channel count is a multiple of 32;
+  * `pca_warm_start=True`: each layer's PCA eigensolver starts from the basis it found in the previous pass;
   * `no_multires=True` works (the reference's own path raises AttributeError at util.py:86: a list has no .tolist()).
 """
 from __future__ import annotations
@@ -125,7 +126,8 @@ class OptimalTexture:
                  models_dir: Optional[str] = None, state_dicts: Optional[Dict[Tuple[str, int], dict]] = None,
                  device="cuda", rotations: Optional[Callable[[int, int], Tensor]] = None,
                  mixing_noise: Optional[Callable[[Tuple[int, int]], Tensor]] = None,
-                 pca: Optional[Callable[[Tensor], Tuple[Tensor, Tensor]]] = None, pca_round_k: int = 1):
+                 pca: Optional[Callable[[Tensor], Tuple[Tensor, Tensor]]] = None, pca_round_k: int = 1,
+                 pca_warm_start: bool = True):
         self.hist_mode = hist_mode
         self.color_transfer = color_transfer
         self.content_strength = content_strength
@@ -148,6 +150,12 @@ class OptimalTexture:
         # C x C products of the covariance modes then run on the tensor cores instead of the fp32 SIMT tiles
         self.pca = pca                      # None: the device PCA, all layers of a pass solved concurrently
         self.pca_round_k = pca_round_k
+        # the style's PCA is refitted at every pass's size (optex.py:62-67): each layer's eigensolver starts from the
+        # basis it found in the previous pass (same result, about half the Jacobi sweeps)
+        self.pca_warm_start = pca_warm_start
+        self._pca_bases: Dict[int, Tensor] = {}
+        self._pca_fitted: set = set()                        # layers whose basis belongs to the current forward()
+        self.pca_sweeps: List[List[int]] = []                # per pass: sweeps of the five solves (conv5_1 .. conv1_1)
         # pca / sym: zero channels appended up to a multiple of 32 before a layer's OT loop.  Exact: the padded
         # covariances are blockdiag(Sigma + I, I), their square roots block-diagonal, the padded channels stay 0 -
         # and every C x C product of the chains runs on the tensor cores instead of the fp32 SIMT tiles.
@@ -236,7 +244,20 @@ class OptimalTexture:
         fitted = None
         if self.use_pca and self.pca is None:
             with self._stage("fit_pca"):
-                fitted = _optex.fit_pca_many(raw, round_k_to=self.pca_round_k)
+                bases, warm = [], []
+                for l, t in enumerate(raw):
+                    c = t.shape[-1]
+                    b = self._pca_bases.get(l)
+                    hit = l in self._pca_fitted and b is not None and tuple(b.shape) == (c, c) and b.device == t.device
+                    if not hit:
+                        b = self._pca_bases[l] = torch.empty(c, c, dtype=torch.float64, device=t.device)
+                    bases.append(b)
+                    warm.append(bool(hit and self.pca_warm_start))
+                sweeps: List[int] = []
+                fitted = _optex.fit_pca_many(raw, round_k_to=self.pca_round_k, bases=bases, warm=warm,
+                                             sweeps_out=sweeps)
+                self._pca_fitted.update(range(len(raw)))
+                self.pca_sweeps.append(sweeps)
         for l in range(len(self.encoders)):
             sf = raw[l]
             eigvecs = None
@@ -260,6 +281,8 @@ class OptimalTexture:
                 verbose: bool = False) -> Tensor:
         """reference: optex.py:81-139."""
         require_cuda(pastiche, *styles, content)
+        self._pca_fitted.clear()                             # pass 0 of every call starts cold
+        self.pca_sweeps = []
         for p in range(self.passes):
             if verbose:
                 print(f"Pass {p}, size {self.sizes[p]}")
