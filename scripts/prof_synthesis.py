@@ -6,8 +6,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
 import optimaltextures_b200 as ob
-from optimaltextures_b200 import texture
-from oracle import texture_cases
+from optimaltextures_b200 import texture, vgg
 
 size = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 60
@@ -17,7 +16,7 @@ g = torch.Generator().manual_seed(0)
 style = torch.rand(1, 3, round(size * 736 / 512 / 32) * 32, size, generator=g).cuda()
 pastiche = torch.rand(1, 3, size, size, generator=g).cuda()
 model = texture.OptimalTexture(size=size, iters=iters, passes=passes, hist_mode=mode,
-                               state_dicts=texture_cases.state_dicts())
+                               state_dicts=vgg.random_state_dicts(0))
 ob.manual_seed(0)
 model.profile = {}
 out = model.forward(pastiche, [style])

@@ -180,3 +180,23 @@ def test_load_and_save_image_round_trip(tmp_path):
     assert out.endswith("zebra_cholhist_64.png")
     back = np.asarray(Image.open(out))
     assert back.shape[2] == 3 and np.abs(back.astype(int) - (x[0].permute(1, 2, 0).numpy() * 255 + 0.5).astype(int)).max() <= 1
+
+
+def test_fit_pca_basis_argument_checks():
+    """host-side validation of the additive basis= / warm= arguments of fit_pca (no device call)."""
+    import pytest
+    import torch
+
+    from optimaltextures_b200 import optex as gpu
+
+    cpu = torch.device("cpu")
+    gpu._check_basis(None, 8, cpu, False)
+    gpu._check_basis(torch.zeros(8, 8, dtype=torch.float64), 8, cpu, True)
+    with pytest.raises(ValueError):
+        gpu._check_basis(None, 8, cpu, True)                                   # warm start without a basis
+    with pytest.raises(ValueError):
+        gpu._check_basis(torch.zeros(8, 8), 8, cpu, False)                     # fp32
+    with pytest.raises(ValueError):
+        gpu._check_basis(torch.zeros(8, 4, dtype=torch.float64), 8, cpu, False)
+    with pytest.raises(ValueError):
+        gpu._check_basis(torch.zeros(8, 16, dtype=torch.float64)[:, ::2], 8, cpu, False)   # not contiguous

@@ -95,3 +95,17 @@ def test_no_cpu_fallback():
     enc = vgg.Encoder(1, state_dict=vgg_oracle.random_state_dict("encoder", 1), device="cpu")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         enc(torch.rand(1, 3, 8, 8))
+
+
+def test_random_state_dicts_match_the_golden_runs_weights():
+    """optimaltextures_b200.vgg.random_state_dicts (what bench.py uses: the product path must not import oracle/) draws
+    the same seeded weights as the oracle's generator, in the reference's state_dict order (vgg.py:14-136)."""
+    from optimaltextures_b200 import vgg
+    from oracle import texture_cases
+
+    ours, ref = vgg.random_state_dicts(0), texture_cases.state_dicts(0)
+    assert ours.keys() == ref.keys()
+    for key in ours:
+        assert list(ours[key].keys()) == list(ref[key].keys()), key
+        for name in ours[key]:
+            assert torch.equal(ours[key][name], ref[key][name]), (key, name)
