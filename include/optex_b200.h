@@ -68,6 +68,11 @@ int optex_get_gemm_mode(void);
 /* Programmatic dependent launch between the library's kernels (default on).  Turn it off to time individual
  * kernels with CUDA events: under PDL a kernel may start before its predecessor has drained. */
 int optex_set_pdl(int enable);
+/* The tensor-core GEMMs split their small operand into tf32 halves in a library-owned scratch buffer: one per device
+ * and SLOT (0 or 1).  Calls enqueued on two streams that may run concurrently must use different slots; the slot is
+ * a property of the calling host thread (default 0) until changed.  optex_ot_step_host_async manages it itself.
+ * Returns the previous slot.  (No reference counterpart: the reference runs on one stream, optex.py:256.) */
+int optex_set_scratch_slot(int slot);
 /* Arithmetic of the Householder construction behind optex_random_rotation(s): 1 = fp64 (default; what the
  * reference's live scipy branch computes in before `.to(pastiche_feature)`, optex.py:147,168), 0 = fp32 (what its
  * impl="torch" branch computes in, optex.py:150-164; 2x faster, |R R^T - I| ~ 1e-6 instead of 1e-8 at c = 512).

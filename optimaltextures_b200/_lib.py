@@ -31,6 +31,7 @@ SIGNATURES = {
     "optex_set_gemm_mode": (_i, [_i]),
     "optex_get_gemm_mode": (_i, []),
     "optex_set_pdl": (_i, [_i]),
+    "optex_set_scratch_slot": (_i, [_i]),
     "optex_set_rotation_precision": (_i, [_i]),
     "optex_get_rotation_precision": (_i, []),
     "optex_debug_gemm_trace": (_i, [_p]),

@@ -36,8 +36,10 @@ def f32c(t: torch.Tensor) -> torch.Tensor:
 
 
 def workspace(dev: torch.device, nbytes: int) -> torch.Tensor:
-    """A per-device scratch buffer that only ever grows (so steady-state calls never allocate)."""
-    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    """A scratch buffer per device AND current stream that only ever grows (so steady-state calls never allocate;
+    work enqueued on two streams never shares scratch)."""
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(dev).cuda_stream)
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=dev)

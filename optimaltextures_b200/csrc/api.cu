@@ -239,6 +239,14 @@ extern "C" int optex_debug_gemm_trace(void *device_buf) {
     gemm_tc_set_trace((unsigned long long *)device_buf);
     return OPTEX_OK;
 }
+static thread_local int g_user_slot = 0;
+extern "C" int optex_set_scratch_slot(int slot) {
+    const int prev = g_user_slot;
+    g_user_slot = slot & 1;
+    gemm_tc_set_scratch_slot(g_user_slot);
+    return prev;
+}
+
 extern "C" int optex_set_pdl(int enable) {
     g_pdl.store(enable ? 1 : 0);
     return OPTEX_OK;
@@ -298,7 +306,7 @@ static int ot_step_host_impl(const float *P, const float *S, const float *R, flo
         OPTEX_TRY(random_rotations(dR, c, 1, seed, counter, nullptr, (char *)dW + step_ws, rot_ws, st));
     if (content) OPTEX_CUDA(cudaMemcpyAsync(dC, content, sizeof(float) * n_p * c, cudaMemcpyHostToDevice, st));
     int rc = ot_step_impl(dP, dS, dR, dO, b_p, hw_p, b_s, hw_s, c, mode, eps, dC, content_strength, dW, step_ws, st);
-    gemm_tc_set_scratch_slot(0);
+    gemm_tc_set_scratch_slot(g_user_slot);
     OPTEX_TRY(rc);
     OPTEX_CUDA(cudaMemcpyAsync(out, dO, sizeof(float) * n_p * c, cudaMemcpyDeviceToHost, st));
     if (sync) OPTEX_CUDA(cudaStreamSynchronize(st));

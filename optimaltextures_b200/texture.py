@@ -23,6 +23,8 @@ Additive over the reference:
     element-wise comparisons of the whole loop need both sides in ONE basis); `pca_round_k=32` keeps a few more
     components than the reference's 90 % rule so that every layer's channel count is a multiple of 32;
   * `pca_warm_start=True`: each layer's PCA eigensolver starts from the basis it found in the previous pass;
+  * `overlap_style=True` (experimental, default off): the style side of pass p + 1 is prepared on a second stream
+    beside pass p's OT loops; same results (the host-side order of every RNG draw and kernel argument is unchanged);
   * `no_multires=True` works (the reference's own path raises AttributeError at util.py:86: a list has no .tolist()).
 """
 from __future__ import annotations
@@ -127,7 +129,7 @@ class OptimalTexture:
                  device="cuda", rotations: Optional[Callable[[int, int], Tensor]] = None,
                  mixing_noise: Optional[Callable[[Tuple[int, int]], Tensor]] = None,
                  pca: Optional[Callable[[Tensor], Tuple[Tensor, Tensor]]] = None, pca_round_k: int = 1,
-                 pca_warm_start: bool = True):
+                 pca_warm_start: bool = True, overlap_style: bool = False):
         self.hist_mode = hist_mode
         self.color_transfer = color_transfer
         self.content_strength = content_strength
@@ -153,6 +155,10 @@ class OptimalTexture:
         # the style's PCA is refitted at every pass's size (optex.py:62-67): each layer's eigensolver starts from the
         # basis it found in the previous pass (same result, about half the Jacobi sweeps)
         self.pca_warm_start = pca_warm_start
+        # EXPERIMENTAL, off by default (not yet measured on a B200): prepare pass p + 1's style side on a second stream
+        # while pass p's OT loops run - both are latency-bound and leave most of the device idle
+        self.overlap_style = overlap_style
+        self._side: Optional[torch.cuda.Stream] = None
         self._pca_bases: Dict[int, Tensor] = {}
         self._pca_fitted: set = set()                        # layers whose basis belongs to the current forward()
         self.pca_sweeps: List[List[int]] = []                # per pass: sweeps of the five solves (conv5_1 .. conv1_1)
@@ -217,9 +223,13 @@ class OptimalTexture:
         return _optex.ot_loop(feature, style, hist_mode, iters, rotations=rots, content=content,
                               content_strength=strength)
 
-    def encode_inputs(self, pastiche: Tensor, styles: List[Tensor], content: Optional[Tensor], size: int):
-        """reference: optex.py:45-79."""
-        if pastiche.shape[-2] != size and pastiche.shape[-1] != size:
+    def prepare_pass(self, pastiche_shape, styles: List[Tensor], content: Optional[Tensor], size: int,
+                     mix: bool = True):
+        """Everything of a pass that does not depend on the pastiche: optex.py:45-79 without the pastiche's own resize
+        (:55) and, with mix=True, the style mixing of optex.py:97-101.  Returns (cont_size, style_features,
+        style_eigvs, content_features); cont_size is the size the pastiche has to be resized to, or None."""
+        cont_size = None
+        if pastiche_shape[-2] != size and pastiche_shape[-1] != size:
             with self._stage("resize"):
                 style_tens = [_util.resize(s, _util.get_size(size, self.style_scale, s.shape[2], s.shape[3]))
                               for s in styles]
@@ -229,7 +239,6 @@ class OptimalTexture:
                 else:
                     cont_size = (size, size)
                     cont_tens = None
-                pastiche = _util.resize(pastiche, cont_size)
         else:
             style_tens, cont_tens = styles, content
 
@@ -275,7 +284,43 @@ class OptimalTexture:
                     cf = _optex.pca_project(cf, eigvecs)
                 content_features.append(recentre(cf, sf))
         self.last_pca_k = [int(v.shape[1]) for v in style_eigvs]        # conv5_1 .. conv1_1 of the latest pass
+
+        if mix and len(styles) > 1:                                                              # optex.py:97-101
+            shape = tuple(style_features[1].shape[1:3])
+            dev = styles[0].device
+            noise = self.mixing_noise(shape) if self.mixing_noise is not None else torch.rand(shape, device=dev)
+            mixing_mask = torch.ceil(noise.to(dev) - self.mixing_alpha)[None, None, ...]
+            style_features = mix_style_features(style_features, mixing_mask, self.mixing_alpha, self.hist_mode)
+        return cont_size, style_features, style_eigvs, content_features
+
+    def encode_inputs(self, pastiche: Tensor, styles: List[Tensor], content: Optional[Tensor], size: int):
+        """reference: optex.py:45-79 (same name, same four results)."""
+        cont_size, style_features, style_eigvs, content_features = self.prepare_pass(
+            pastiche.shape, styles, content, size, mix=False)
+        if cont_size is not None:
+            with self._stage("resize"):
+                pastiche = _util.resize(pastiche, cont_size)
         return pastiche, style_features, style_eigvs, content_features
+
+    def _prepare(self, streams, pastiche_shape, styles, content, size):
+        """prepare_pass, on the side stream when there is one.  Returns its four results + the event to wait for."""
+        if streams is None:
+            return (*self.prepare_pass(pastiche_shape, styles, content, size), None)
+        main, side, start = streams
+        lib = _lib.lib()
+        prev = lib.optex_set_scratch_slot(1)         # the GEMMs' operand-split scratch: one per concurrent stream
+        try:
+            with torch.cuda.stream(side):
+                side.wait_event(start)               # the inputs exist since forward() began; NOT the main stream's
+                out = self.prepare_pass(pastiche_shape, styles, content, size)     # later work (that is the overlap)
+                ready = side.record_event()
+        finally:
+            lib.optex_set_scratch_slot(prev)
+        for group in out[1:]:
+            for t in group:
+                if t is not None:
+                    t.record_stream(main)            # allocated on `side`, consumed (and released) on `main`
+        return (*out, ready)
 
     def forward(self, pastiche: Tensor, styles: List[Tensor], content: Optional[Tensor] = None,
                 verbose: bool = False) -> Tensor:
@@ -283,18 +328,25 @@ class OptimalTexture:
         require_cuda(pastiche, *styles, content)
         self._pca_fitted.clear()                             # pass 0 of every call starts cold
         self.pca_sweeps = []
+        streams = None
+        if self.overlap_style and pastiche.is_cuda:
+            main = torch.cuda.current_stream(pastiche.device)
+            if self._side is None or self._side.device != pastiche.device:
+                self._side = torch.cuda.Stream(device=pastiche.device)
+            streams = (main, self._side, main.record_event())
+        prepared = None
         for p in range(self.passes):
             if verbose:
                 print(f"Pass {p}, size {self.sizes[p]}")
-            pastiche, style_features, style_eigvs, content_features = self.encode_inputs(
-                pastiche, styles, content, self.sizes[p])
-
-            if len(styles) > 1:
-                shape = tuple(style_features[1].shape[1:3])
-                noise = self.mixing_noise(shape) if self.mixing_noise is not None else torch.rand(
-                    shape, device=pastiche.device)
-                mixing_mask = torch.ceil(noise.to(pastiche.device) - self.mixing_alpha)[None, None, ...]
-                style_features = mix_style_features(style_features, mixing_mask, self.mixing_alpha, self.hist_mode)
+            if prepared is None:
+                prepared = self._prepare(streams, pastiche.shape, styles, content, self.sizes[p])
+            cont_size, style_features, style_eigvs, content_features, ready = prepared
+            prepared = None
+            if cont_size is not None:                                                            # optex.py:55
+                with self._stage("resize"):
+                    pastiche = _util.resize(pastiche, cont_size)
+            if ready is not None:
+                streams[0].wait_event(ready)
 
             for l, (encoder, decoder) in enumerate(zip(self.encoders, self.decoders)):
                 if verbose:
@@ -313,6 +365,11 @@ class OptimalTexture:
                     if self.use_pca:
                         feature = _optex.pca_project(feature, style_eigvs[l], transpose=True)
                     pastiche = decoder(feature)
+
+            if self.overlap_style and p + 1 < self.passes:
+                # the next pass's style side (resize, encode, PCA, mixing) only needs the style / content images: it is
+                # enqueued now, behind this pass's OT loops on the host but beside them on the device
+                prepared = self._prepare(streams, pastiche.shape, styles, content, self.sizes[p + 1])
 
         if self.color_transfer is not None:
             assert content is not None, "Color transfer requires content image"

@@ -90,13 +90,16 @@ def test_hls_round_trip_and_known_colours():
 
 
 # ---------------------------------------------------------------------------------------------- control flow
+@pytest.mark.parametrize("overlap", [False, True])
 @pytest.mark.parametrize("name", ["synth_pca", "mix_content_chol_opt", "nopca_cdf_lum"])
-def test_product_control_flow_matches_reference(golden, monkeypatch, name):
+def test_product_control_flow_matches_reference(golden, monkeypatch, name, overlap):
     """The product's `OptimalTexture` (optimaltextures_b200/texture.py) with each of its KERNEL calls replaced by the
     oracle's op for that stage reproduces the real reference's output (tests/golden/texture.npz) bit for bit: the
     orchestration - pass sizes, resize rule, per-layer iteration counts with the [l - 1] quirk, content strengths
     and the l <= 2 rule, mixing mask, colour-transfer branches, the order of RNG / rotation consumption - is the
-    reference's.  (The kernels themselves are compared stage by stage on the GPU, tests/test_gpu_texture.py.)"""
+    reference's.  (The kernels themselves are compared stage by stage on the GPU, tests/test_gpu_texture.py.)
+    overlap=True: the host-side order of the experimental `overlap_style` schedule (pass p + 1's style side prepared
+    right after pass p's layers are enqueued) consumes the RNG and produces every tensor identically."""
     from optimaltextures_b200 import texture
     from oracle import ot_oracle, texture_cases, vgg_oracle
 
@@ -137,7 +140,7 @@ def test_product_control_flow_matches_reference(golden, monkeypatch, name):
     g = golden("texture")
     kwargs, styles, content, pastiche = texture_cases.texture_inputs(name)
     model = texture.OptimalTexture(state_dicts=texture_cases.state_dicts(), rotations=texture_cases.texture_rotation,
-                                   device="cpu", pca=ot_oracle.fit_pca, **kwargs)
+                                   device="cpu", pca=ot_oracle.fit_pca, overlap_style=overlap, **kwargs)
     model.pad_channels = 1          # the zero-channel padding is exact in real arithmetic, not bit for bit
     torch.manual_seed(77)
     with torch.inference_mode():
