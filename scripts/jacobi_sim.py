@@ -1,0 +1,124 @@
+"""CPU simulation (numpy, FP64) of the PCA eigensolver's sweep count: the kernel's one-sided Jacobi on the rows of
+W = G (pca.cu) against the same iteration on the rows of the Cholesky factor R of G = R^T R (Drmac-Veselic style
+preconditioning: R R^T is one LR step closer to diagonal than G, the singular values are sigma instead of
+lambda = sigma^2, and the eigenvectors are the normalised rows of the final W - no V to carry).  Same round-robin
+order, same JTOL / early-exit rule as the kernel.  Usage: python scripts/jacobi_sim.py [c] [n ...]"""
+import sys
+
+import numpy as np
+
+JTOL, JEXIT = 1e-12, 1e-6
+
+
+def schedule(c):
+    ne = c + (c & 1)
+    n1, m = ne - 1, ne // 2
+    for r in range(n1):
+        pi = np.arange(m)
+        a = np.where(pi == 0, n1, (r + pi) % n1)
+        b = np.where(pi == 0, r, (r - pi + n1) % n1)
+        ok = (a < c) & (b < c)
+        yield a[ok], b[ok]
+
+
+def jacobi_rows(W, V=None, max_sweeps=40, floor_rel=1e-13):
+    c = W.shape[0]
+    tr = np.sqrt((W * W).sum()) if V is None else np.trace(W)
+    floor_abs = (floor_rel * tr) ** 2
+    rounds = list(schedule(c))
+    for sweep in range(max_sweeps):
+        rot, mx = 0, 0.0
+        for a, b in rounds:
+            wa, wb = W[a], W[b]
+            al, be, ga = (wa * wa).sum(1), (wb * wb).sum(1), (wa * wb).sum(1)
+            go = (ga * ga > JTOL * JTOL * al * be) & (np.abs(ga) > floor_abs)
+            if not go.any():
+                continue
+            a2, b2, al, be, ga = a[go], b[go], al[go], be[go], ga[go]
+            zeta = (be - al) / (2 * ga)
+            t = np.where(zeta >= 0, 1.0, -1.0) / (np.abs(zeta) + np.sqrt(1 + zeta * zeta))
+            cs = 1 / np.sqrt(1 + t * t)
+            sn = cs * t
+            wa, wb = W[a2], W[b2]
+            W[a2], W[b2] = cs[:, None] * wa - sn[:, None] * wb, sn[:, None] * wa + cs[:, None] * wb
+            if V is not None:
+                va, vb = V[a2], V[b2]
+                V[a2], V[b2] = cs[:, None] * va - sn[:, None] * vb, sn[:, None] * va + cs[:, None] * vb
+            rot += int(go.sum())
+            mx = max(mx, float((ga * ga / (al * be)).max()))
+        if rot == 0 or mx <= JEXIT * JEXIT:
+            return sweep + 1
+    return max_sweeps
+
+
+def features(n, c, seed):
+    g = np.random.default_rng(seed)
+    mix = g.standard_normal((c, c)) * (2.0 / np.sqrt(c))
+    return np.maximum(g.standard_normal((n, c)) @ mix + 0.3, 0).astype(np.float32)
+
+
+c = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+ns = [int(v) for v in sys.argv[2:]] or [c * 3 // 4, 3 * c, 8 * c]
+for n in ns:
+    x = features(n, c, 0).astype(np.float64)
+    xc = x - x.mean()
+    G = xc.T @ xc
+    lam_ref = np.linalg.eigvalsh(G)[::-1]
+    # kernel's formulation
+    W, V = G.copy(), np.eye(c)
+    s0 = jacobi_rows(W, V)
+    lam0 = np.sort((V * W).sum(1))[::-1]
+    # Cholesky-preconditioned: rows of R, G + jitter = R^T R
+    jit = 1e-13 * np.trace(G)
+    R = np.linalg.cholesky(G + jit * np.eye(c)).T
+    W1 = R.copy()
+    s1 = jacobi_rows(W1, None)
+    lam1 = np.sort((W1 * W1).sum(1))[::-1] - jit
+    Q = W1 / np.linalg.norm(W1, axis=1, keepdims=True)
+    order = np.argsort(-(W1 * W1).sum(1))
+    k = int(min(n, c) * 0.8)
+    Qk = Q[order[:k]]
+    resid = np.abs(Qk @ G @ Qk.T - np.diag(np.diag(Qk @ G @ Qk.T))).max() / lam_ref[0]
+    orth = np.abs(Qk @ Qk.T - np.eye(k)).max()
+    sig = lambda l: np.sqrt(np.clip(l, 0, None))
+    print(f"c={c} n={n}: rows of G: {s0} sweeps (dsigma {np.abs(sig(lam0) - sig(lam_ref)).max() / sig(lam_ref)[0]:.1e}) | "
+          f"rows of chol(G): {s1} sweeps (dsigma {np.abs(sig(lam1) - sig(lam_ref)).max() / sig(lam_ref)[0]:.1e}, "
+          f"top-{k} offdiag {resid:.1e}, orth {orth:.1e})", flush=True)
+
+
+def pivoted_cholesky(G):
+    """G[p][:, p] = R^T R with the diagonal of R non-increasing (complete pivoting); returns R, p."""
+    A = G.copy()
+    c = A.shape[0]
+    p = np.arange(c)
+    R = np.zeros_like(A)
+    for j in range(c):
+        i = j + int(np.argmax(np.diag(A)[j:]))
+        if i != j:
+            A[[j, i]] = A[[i, j]]
+            A[:, [j, i]] = A[:, [i, j]]
+            R[:, [j, i]] = R[:, [i, j]]
+            p[[j, i]] = p[[i, j]]
+        d = A[j, j]
+        if d <= 0:
+            break
+        R[j, j] = np.sqrt(d)
+        R[j, j + 1:] = A[j, j + 1:] / R[j, j]
+        A[j + 1:, j + 1:] -= np.outer(R[j, j + 1:], R[j, j + 1:])
+    return R, p
+
+
+if "--pivot" in sys.argv or True:
+    for n in ns:
+        x = features(n, c, 0).astype(np.float64)
+        xc = x - x.mean()
+        G = xc.T @ xc
+        jit = 1e-13 * np.trace(G)
+        Gj = G + jit * np.eye(c)
+        # (1) diagonal-sorted, (2) completely pivoted
+        p1 = np.argsort(-np.diag(Gj))
+        R1 = np.linalg.cholesky(Gj[p1][:, p1]).T
+        R2, p2 = pivoted_cholesky(Gj)
+        print(f"c={c} n={n}: chol of diag-sorted G: {jacobi_rows(R1.copy())} sweeps | pivoted chol: "
+              f"{jacobi_rows(R2.copy())} sweeps | rows of R^T (= L, other orientation): "
+              f"{jacobi_rows(np.linalg.cholesky(Gj).copy())} sweeps", flush=True)
