@@ -2,7 +2,8 @@
 W = G (pca.cu) against the same iteration on the rows of the Cholesky factor R of G = R^T R (Drmac-Veselic style
 preconditioning: R R^T is one LR step closer to diagonal than G, the singular values are sigma instead of
 lambda = sigma^2, and the eigenvectors are the normalised rows of the final W - no V to carry).  Same round-robin
-order, same JTOL / early-exit rule as the kernel.  Usage: python scripts/jacobi_sim.py [c] [n ...]"""
+order, same JTOL / early-exit rule as the kernel.  Also a BLOCKED form (b rows per block, a pair of blocks solved
+exactly per step: c / b - 1 rounds per sweep instead of c - 1).  Usage: python scripts/jacobi_sim.py [c] [n ...]"""
 import sys
 
 import numpy as np
@@ -47,6 +48,39 @@ def jacobi_rows(W, V=None, max_sweeps=40, floor_rel=1e-13):
             rot += int(go.sum())
             mx = max(mx, float((ga * ga / (al * be)).max()))
         if rot == 0 or mx <= JEXIT * JEXIT:
+            return sweep + 1
+    return max_sweeps
+
+
+def block_jacobi_rows(W, b, max_sweeps=30, floor_rel=1e-13):
+    """Block one-sided Jacobi: the 2b rows of a block pair are orthogonalised exactly (eigh of their Gram matrix, the
+    eigenvector matrix permuted / signed towards the identity, as convergence of block methods needs)."""
+    c = W.shape[0]
+    tr = np.sqrt((W * W).sum())
+    rounds = list(schedule(c // b))
+    for sweep in range(max_sweeps):
+        mx = 0.0
+        for A, B in rounds:
+            for a, bb in zip(A, B):
+                idx = np.r_[a * b:(a + 1) * b, bb * b:(bb + 1) * b]
+                X = W[idx]
+                S = X @ X.T
+                d = np.sqrt(np.diag(S))
+                live = d > floor_rel * tr                      # null rows are rounding noise: not part of the vote
+                if live.sum() > 1:
+                    off = np.abs(S[np.ix_(live, live)] / np.outer(d[live], d[live]))
+                    np.fill_diagonal(off, 0)
+                    mx = max(mx, float(off.max()))
+                _, U = np.linalg.eigh(S)
+                M, perm, used = np.abs(U), -np.ones(2 * b, int), set()
+                for i in np.argsort(-M.max(1)):
+                    j = [j for j in np.argsort(-M[i]) if j not in used][0]
+                    perm[i] = j
+                    used.add(j)
+                U = U[:, perm]
+                U = U * np.where(np.diag(U) < 0, -1.0, 1.0)[None, :]
+                W[idx] = U.T @ X
+        if mx <= JEXIT:
             return sweep + 1
     return max_sweeps
 
@@ -122,3 +156,15 @@ if "--pivot" in sys.argv or True:
         print(f"c={c} n={n}: chol of diag-sorted G: {jacobi_rows(R1.copy())} sweeps | pivoted chol: "
               f"{jacobi_rows(R2.copy())} sweeps | rows of R^T (= L, other orientation): "
               f"{jacobi_rows(np.linalg.cholesky(Gj).copy())} sweeps", flush=True)
+
+
+for b in (8, 16):
+    if c % (2 * b):
+        continue
+    for n in ns:
+        x = features(n, c, 0).astype(np.float64)
+        xc = x - x.mean()
+        G = xc.T @ xc
+        R = np.linalg.cholesky(G + 1e-13 * np.trace(G) * np.eye(c)).T
+        print(f"c={c} n={n} blocked b={b} ({c // b - 1} rounds per sweep): rows of G {block_jacobi_rows(G.copy(), b)} "
+              f"sweeps | rows of chol(G) {block_jacobi_rows(R.copy(), b)} sweeps", flush=True)
