@@ -302,6 +302,15 @@ class OptimalTexture:
                 pastiche = _util.resize(pastiche, cont_size)
         return pastiche, style_features, style_eigvs, content_features
 
+    def _streams_for(self, pastiche: Tensor):
+        """(main stream, side stream, event marking the start of forward()) of the overlapped schedule."""
+        if not pastiche.is_cuda:
+            return None
+        main = torch.cuda.current_stream(pastiche.device)
+        if self._side is None or self._side.device != pastiche.device:
+            self._side = torch.cuda.Stream(device=pastiche.device)
+        return main, self._side, main.record_event()
+
     def _prepare(self, streams, pastiche_shape, styles, content, size):
         """prepare_pass, on the side stream when there is one.  Returns its four results + the event to wait for."""
         if streams is None:
@@ -318,7 +327,7 @@ class OptimalTexture:
             lib.optex_set_scratch_slot(prev)
         for group in out[1:]:
             for t in group:
-                if t is not None:
+                if t is not None and t.is_cuda:
                     t.record_stream(main)            # allocated on `side`, consumed (and released) on `main`
         return (*out, ready)
 
@@ -328,12 +337,7 @@ class OptimalTexture:
         require_cuda(pastiche, *styles, content)
         self._pca_fitted.clear()                             # pass 0 of every call starts cold
         self.pca_sweeps = []
-        streams = None
-        if self.overlap_style and pastiche.is_cuda:
-            main = torch.cuda.current_stream(pastiche.device)
-            if self._side is None or self._side.device != pastiche.device:
-                self._side = torch.cuda.Stream(device=pastiche.device)
-            streams = (main, self._side, main.record_event())
+        streams = self._streams_for(pastiche) if self.overlap_style else None
         prepared = None
         for p in range(self.passes):
             if verbose:

@@ -137,6 +137,35 @@ def test_product_control_flow_matches_reference(golden, monkeypatch, name, overl
     monkeypatch.setattr(texture, "lightness_transfer", image_oracle.lightness_transfer)
     monkeypatch.setattr(texture, "mix_style_features", texture_oracle.mix_style_features)
 
+    events = []
+    if overlap:
+        # drive the stream branch of the overlapped schedule too, with stand-ins that log the synchronisation calls
+        import contextlib
+
+        class FakeStream:
+            def __init__(self, tag):
+                self.tag = tag
+
+            def wait_event(self, ev):
+                events.append((self.tag, "wait", ev))
+
+            def record_event(self):
+                events.append((self.tag, "record", len(events)))
+                return f"{self.tag}-event-{len(events)}"
+
+        class FakeLib:
+            slot = 0
+
+            def optex_set_scratch_slot(self, slot):
+                prev, FakeLib.slot = FakeLib.slot, slot
+                events.append(("lib", "slot", slot))
+                return prev
+
+        main, side = FakeStream("main"), FakeStream("side")
+        monkeypatch.setattr(texture.OptimalTexture, "_streams_for", lambda self, p: (main, side, main.record_event()))
+        monkeypatch.setattr(texture.torch.cuda, "stream", lambda s: contextlib.nullcontext())
+        monkeypatch.setattr(texture._lib, "lib", lambda: FakeLib())
+
     g = golden("texture")
     kwargs, styles, content, pastiche = texture_cases.texture_inputs(name)
     model = texture.OptimalTexture(state_dicts=texture_cases.state_dicts(), rotations=texture_cases.texture_rotation,
@@ -147,6 +176,13 @@ def test_product_control_flow_matches_reference(golden, monkeypatch, name, overl
         out = model.forward(pastiche, styles, content)
     assert model.ot_calls == int(g[f"{name}_calls"])
     np.testing.assert_array_equal(out.contiguous().numpy(), g[f"{name}_out"])
+    if overlap:
+        passes = kwargs["passes"]
+        # per pass: slot 1, side waits for the start event, side records "ready", slot back to 0; main waits for it
+        assert [e for e in events if e[0] == "lib"] == [("lib", "slot", 1), ("lib", "slot", 0)] * passes
+        assert sum(1 for e in events if e[:2] == ("side", "wait")) == passes
+        ready = [f"side-event-{i + 1}" for i, e in enumerate(events) if e[:2] == ("side", "record")]
+        assert [e[2] for e in events if e[:2] == ("main", "wait")] == ready and len(ready) == passes
 
 
 def test_cli_flags_match_the_reference():
