@@ -239,3 +239,59 @@ def test_fit_pca_basis_argument_checks():
         gpu._check_basis(torch.zeros(8, 4, dtype=torch.float64), 8, cpu, False)
     with pytest.raises(ValueError):
         gpu._check_basis(torch.zeros(8, 16, dtype=torch.float64)[:, ::2], 8, cpu, False)   # not contiguous
+
+
+def test_pca_warm_start_bookkeeping(monkeypatch):
+    """OptimalTexture hands each layer's float64 basis buffer to fit_pca_many: cold in pass 0 of every forward(), warm in
+    the later passes, one [c, c] buffer per layer kept across passes (device PCA stubbed by the oracle's fit_pca)."""
+    from optimaltextures_b200 import texture
+    from oracle import ot_oracle, texture_cases, vgg_oracle
+
+    class Enc:
+        def __init__(self, d, state_dict=None, models_dir=None, device=None):
+            self.depth, self.sd, self.layers = d, state_dict, []
+
+        def forward_all(self, x):
+            return vgg_oracle.encoder_forward(x, self.sd, self.depth, all_depths=True)
+
+        def __call__(self, x):
+            return vgg_oracle.encoder_forward(x, self.sd, self.depth)
+
+    class Dec:
+        def __init__(self, d, state_dict=None, models_dir=None, device=None):
+            self.depth, self.sd = d, state_dict
+
+        def __call__(self, x):
+            return vgg_oracle.decoder_forward(x, self.sd, self.depth)
+
+    calls = []
+
+    def fit_many(tensors, *, round_k_to=1, bases=None, warm=None, sweeps_out=None):
+        calls.append((list(warm), [b.data_ptr() for b in bases], [tuple(b.shape) for b in bases], bases[0].dtype))
+        sweeps_out.extend([7] * len(tensors))
+        return [ot_oracle.fit_pca(t) for t in tensors]
+
+    monkeypatch.setattr(texture, "require_cuda", lambda *t: torch.device("cpu"))
+    monkeypatch.setattr(texture._util, "resize", image_oracle.resize)
+    monkeypatch.setattr(texture._vgg, "Encoder", Enc)
+    monkeypatch.setattr(texture._vgg, "Decoder", Dec)
+    monkeypatch.setattr(texture._optex, "pca_project", lambda x, v, transpose=False: x @ (v.T if transpose else v))
+    monkeypatch.setattr(texture._optex, "ot_loop", lambda f, *a, **k: f)
+    monkeypatch.setattr(texture._optex, "fit_pca_many", fit_many)
+    kwargs, styles, content, pastiche = texture_cases.texture_inputs("synth_pca")
+    model = texture.OptimalTexture(state_dicts=texture_cases.state_dicts(), device="cpu", **kwargs)
+    model.pad_channels = 1
+    with torch.inference_mode():
+        model.forward(pastiche, styles, content)
+        assert [c[0] for c in calls] == [[False] * 5, [True] * 5]
+        assert calls[0][1] == calls[1][1], "the basis buffers must persist from pass to pass"
+        assert calls[0][2] == [(512, 512), (512, 512), (256, 256), (128, 128), (64, 64)] and calls[0][3] == torch.float64
+        assert model.pca_sweeps == [[7] * 5, [7] * 5]
+        model.forward(pastiche, styles, content)
+    assert [c[0] for c in calls[2:]] == [[False] * 5, [True] * 5], "a new forward() starts cold"
+    cold = texture.OptimalTexture(state_dicts=texture_cases.state_dicts(), device="cpu", pca_warm_start=False, **kwargs)
+    cold.pad_channels = 1
+    del calls[:]
+    with torch.inference_mode():
+        cold.forward(pastiche, styles, content)
+    assert [c[0] for c in calls] == [[False] * 5, [False] * 5]
