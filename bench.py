@@ -38,7 +38,7 @@ UNIT = "it/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="cdf", choices=["cdf", "sort", "chol", "pca", "sym"])
@@ -50,13 +50,21 @@ def parse():
                     help="seconds of untimed steps before the warm-up (GPU clock ramp of a fresh box)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--all-modes", action="store_true", help="also time the other hist modes (extra keys)")
+    ap.add_argument("--repeats", type=int, default=5, help="timed regions of exactly --steps steps; value = median")
+    ap.add_argument("--all-modes", action="store_true", help="(default now; kept for compatibility)")
+    ap.add_argument("--no-all-modes", action="store_true", dest="no_all_modes",
+                    help="skip the other hist modes / GEMM arithmetic variants (extra keys)")
+    ap.add_argument("--no-layers", action="store_true", dest="no_layers",
+                    help="skip the other layer shapes of a 1024^2 image (extra keys)")
+    ap.add_argument("--no-tf32-peak", action="store_true", dest="no_tf32_peak",
+                    help="skip the cuBLAS TF32 peak measurement that accompanies the roofline")
     ap.add_argument("--no-pdl", action="store_true", help="launch the kernels without programmatic dependent launch")
     ap.add_argument("--no-synthesis", action="store_true",
                     help="skip the end-to-end synthesis block (BASELINE metric ii: output pixels/sec of forward())")
     ap.add_argument("--synthesis-size", type=int, default=512, dest="synthesis_size")
-    ap.add_argument("--synthesis-cpu", action="store_true", dest="synthesis_cpu",
-                    help="also time the oracle's forward() of the same synthesis on the host cores (about a minute)")
+    ap.add_argument("--synthesis-cpu", action="store_true", dest="synthesis_cpu", help="(default now; kept)")
+    ap.add_argument("--no-synthesis-cpu", action="store_true", dest="no_synthesis_cpu",
+                    help="skip the CPU-reference timing of configs[0] (the whole 256^2 synthesis once on the host cores)")
     ap.add_argument("--sharded", action="store_true",
                     help="N > 1: ONE feature block, rotated channels sharded over the ranks + NCCL all-gather "
                          "(strong scaling) instead of one independent block per rank")
@@ -165,59 +173,87 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def make_inputs(torch, a, seed, device):
+def make_inputs(torch, a, seed, device, hw=None, channels=None):
     """SURVEY.md 8(d) synthetic input: P = relu(randn), S = relu(1.3 randn + 0.2), fp32 NHWC."""
     g = torch.Generator(device="cpu").manual_seed(seed)
-    shape = (1, a.hw, a.hw, a.channels)
+    hw = hw or a.hw
+    shape = (1, hw, hw, channels or a.channels)
     p = torch.relu(torch.randn(shape, generator=g))
     s = torch.relu(1.3 * torch.randn(shape, generator=g) + 0.2)
     return p.to(device), s.to(device)
 
 
+def config_of(a):
+    """The SAME dict in both arms (the driver compares them): only what defines the workload."""
+    return {"workload": workload_name(a)}
+
+
 # ------------------------------------------------------------------------------------------- reference arm
 def cpu_reference_rate(a, steps, warmup, budget_s=None):
-    """The reference's algorithm on the host cores: oracle port (bit-exact with the reference's outputs,
-    tests/test_oracle_golden.py) including the per-iteration scipy-style rotation draw (optex.py:149,168)."""
+    """The reference's own CPU implementation of the step on the host cores.
+
+    kind "reference": the UNMODIFIED reference staged under baseline/_ref/ (baseline/stage_reference.py) -
+    `optex.optimal_transport(p, s, mode)` exactly as its inner loop calls it (optex.py:113), scipy rotation draw
+    included (optex.py:168).  kind "port": the oracle restatement (bit-exact with the reference's outputs,
+    tests/test_oracle_golden.py) when the reference is not staged, and always for `sort` (the reference has no sort)."""
     import numpy as np
     import torch
-
-    from oracle import ot_oracle, rotation as rot_oracle, sort_oracle
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     p, s = make_inputs(torch, a, 0, "cpu")
-    rng = np.random.RandomState(0)
+    kind = "port"
+    one = None
+    if a.mode != "sort":
+        try:
+            from baseline import reference
 
-    def one(p):
-        r = torch.tensor(rot_oracle.haar_rotation_qr(a.channels, rng))          # float64 like optex.py:149
-        if a.mode == "sort":
-            return sort_oracle.ot_step_sort(p, s, r)
-        return ot_oracle.ot_step(p, s, r, a.mode)
+            if reference.available():
+                ref = reference.load()
+                kind = "reference"
 
-    for _ in range(warmup):
-        p = one(p)
-    t0 = time.perf_counter()
-    done = 0
-    for _ in range(steps):
-        p = one(p)
-        done += 1
-        if budget_s is not None and time.perf_counter() - t0 > budget_s and done >= 2:
-            break
-    dt = time.perf_counter() - t0
-    return done / dt, dt / done * 1e3, done, cores
+                def one(p):
+                    return ref.optex.optimal_transport(p, s, a.mode)
+        except Exception:  # noqa: BLE001  (fall back to the port; the line says which ran)
+            kind, one = "port", None
+    if one is None:
+        from oracle import ot_oracle, rotation as rot_oracle, sort_oracle
+
+        rng = np.random.RandomState(0)
+
+        def one(p):
+            r = torch.tensor(rot_oracle.haar_rotation_qr(a.channels, rng))          # float64 like optex.py:149
+            if a.mode == "sort":
+                return sort_oracle.ot_step_sort(p, s, r)
+            return ot_oracle.ot_step(p, s, r, a.mode)
+
+    with torch.inference_mode():
+        for _ in range(warmup):
+            p = one(p)
+        t0 = time.perf_counter()
+        done = 0
+        for _ in range(steps):
+            p = one(p)
+            done += 1
+            if budget_s is not None and time.perf_counter() - t0 > budget_s and done >= 2:
+                break
+        dt = time.perf_counter() - t0
+    return done / dt, dt / done * 1e3, done, cores, kind
 
 
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    rate, ms, done, cores = cpu_reference_rate(a, a.steps, a.warmup)
-    sample = f"{done} full-size steps ({workload_name(a)}), oracle port incl. rotation draw, torch {cores} threads"
+    rate, ms, done, cores, kind = cpu_reference_rate(a, a.steps, a.warmup)
+    what = ("the unmodified reference's optex.optimal_transport (baseline/_ref)" if kind == "reference"
+            else "oracle port of the reference")
+    sample = f"{done} full-size steps ({workload_name(a)}), {what} incl. its rotation draw, torch {cores} threads"
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": a.gpus, "steps": done,
         "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": {"workload": workload_name(a)},
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "dtype": "f32", "data": "synthetic", "config": config_of(a),
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -225,7 +261,44 @@ def run_reference(a):
 
 
 # ------------------------------------------------------------------------------------------------ our arm
+def measure_tf32_peak(torch, device, seconds=1.5):
+    """cuBLAS TF32 GEMM peak measured the way MEASURED_PEAKS.json measures bf16: 8192^3 torch.matmul with TF32 on,
+    best of 10 (burst) and back to back for `seconds` (sustained).  A library call used as the ROOF, never as the path."""
+    n = 8192
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        x = torch.randn(n, n, device=device)
+        y = torch.randn(n, n, device=device)
+        for _ in range(3):
+            x @ y
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            x @ y
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        reps = max(10, int(seconds * 1e3 / best))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            x @ y
+        e1.record()
+        torch.cuda.synchronize()
+        sustained = e0.elapsed_time(e1) / reps
+        fl = 2.0 * n ** 3
+        return {"tf32_tflops": fl / (best * 1e-3) / 1e12, "tf32_tflops_sustained": fl / (sustained * 1e-3) / 1e12,
+                "how": f"torch.matmul fp32 {n}^3 with allow_tf32: best of 10 / {reps} back to back"}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
 def run_ours(a):
+    import ctypes as C
+
     import torch
     import torch.distributed as dist
 
@@ -254,34 +327,8 @@ def run_ours(a):
     _lib.check(lib.optex_device_check())
     ob.set_gemm_mode(a.gemm)
     lib.optex_set_pdl(0 if a.no_pdl else 1)
-    K, W = a.steps, a.warmup
-    n = a.hw * a.hw
-    c = a.channels
-    mode = _lib.mode_id(a.mode)
-    sets = [make_inputs(torch, a, 1000 * rank + i, device) for i in range(a.sets)]
-    outs = [torch.empty_like(sets[0][0]) for _ in range(2)]
-    ws = workspace(device, lib.optex_ot_workspace_bytes(n, n, c, mode))
-    rot_ws = torch.empty(lib.optex_rotations_workspace_bytes(c, K), dtype=torch.uint8, device=device)
-    rots = torch.empty(K, c, c, dtype=torch.float32, device=device)
+    K, W, REPS = a.steps, a.warmup, max(1, a.repeats)
     st = stream_ptr(device)
-
-    def gen_rotations(count, first):
-        call("optex_random_rotations", ptr(rots), c, count, 1234 + (0 if a.sharded else rank), first, None, ptr(rot_ws), rot_ws.numel(), st)
-
-    sharded = a.sharded and world > 1
-    if sharded:
-        from optimaltextures_b200 import parallel
-
-        sets = [make_inputs(torch, a, i, device) for i in range(a.sets)]      # replicated inputs
-        shard_ops = parallel.cuda_ops()
-
-    def step(i):
-        p, s = sets[i % a.sets]
-        if sharded:
-            parallel.optimal_transport_sharded(p, s, a.mode, rots[i % K], ops=shard_ops)
-            return
-        call("optex_ot_step", ptr(p), ptr(s), ptr(rots[i % K]), ptr(outs[i % 2]), 1, n, 1, n, c, mode, 1.0, None,
-             0.0, ptr(ws), ws.numel(), st)
 
     def barrier():
         if world > 1:
@@ -295,115 +342,169 @@ def run_ours(a):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    class Block:
+        """One workload (layer shape, mode): device-resident input sets + everything a K-step region needs."""
+
+        def __init__(self, hw, c, mode, seed0, sets):
+            self.n, self.c, self.mode, self.mid = hw * hw, c, mode, _lib.mode_id(mode)
+            self.sets = [make_inputs(torch, a, seed0 + i, device, hw, c) for i in range(sets)]
+            self.outs = [torch.empty_like(self.sets[0][0]) for _ in range(2)]
+            self.ws = torch.empty(lib.optex_ot_workspace_bytes(self.n, self.n, c, self.mid), dtype=torch.uint8,
+                                  device=device)
+            self.rot_ws = torch.empty(lib.optex_rotations_workspace_bytes(c, K), dtype=torch.uint8, device=device)
+            self.rots = torch.empty(K, c, c, dtype=torch.float32, device=device)
+            mk = lambda ts: (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])  # noqa: E731
+            self.P, self.S, self.O = mk([p for p, _ in self.sets]), mk([s for _, s in self.sets]), mk(self.outs)
+
+        def gen_rotations(self, first, seed=1234):
+            call("optex_random_rotations", ptr(self.rots), self.c, K, seed, first, None, ptr(self.rot_ws),
+                 self.rot_ws.numel(), st)
+
+        def steps(self, first=0, count=None):
+            """K independent steps enqueued by ONE C call (optex_ot_steps): Python is not in the loop."""
+            call("optex_ot_steps", self.P, self.S, len(self.sets), ptr(self.rots), self.O, 2, K if count is None else count,
+                 first, 1, self.n, 1, self.n, self.c, self.mid, 1.0, ptr(self.ws), self.ws.numel(), st)
+
+        def region(self):
+            """rotation draw for K steps + K steps + drain fence; returns (device ms, host enqueue ms)."""
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            l0 = lib.optex_launch_count()
+            t0 = time.perf_counter()
+            e0.record()
+            self.gen_rotations(self.region_no * K + W)
+            self.steps()
+            call("optex_fence", st)     # ordinary kernel: starts only after the last PDL-launched kernel drained
+            e1.record()
+            t1 = time.perf_counter()
+            self.last_launches = lib.optex_launch_count() - l0
+            barrier()
+            self.region_no += 1
+            return e0.elapsed_time(e1), (t1 - t0) * 1e3
+
+        region_no = 0
+
+        def timed(self, reps):
+            """W warm-up steps through the SAME code path (every kernel between the events has run before), then
+            `reps` regions of exactly K steps; per region the max over ranks."""
+            self.gen_rotations(0)
+            self.steps(0, W)
+            call("optex_fence", st)
+            barrier()
+            self.region()                         # one untimed region: first use of every event / launch path
+            ms, host = [], []
+            for _ in range(reps):
+                m, h = self.region()
+                ms.append(max_over_ranks(m))
+                host.append(h)
+            return ms, host
+
+    sharded = a.sharded and world > 1
+    blk = Block(a.hw, a.channels, a.mode, 0 if sharded else 1000 * rank, a.sets)
+    n, c, mode = blk.n, blk.c, blk.mid
+    sets, outs, rots = blk.sets, blk.outs, blk.rots
+    if sharded:
+        from optimaltextures_b200 import parallel
+
+        shard_ops = parallel.cuda_ops()
+
+        def sharded_steps(first=0, count=None):
+            for i in range(K if count is None else count):
+                p, s = sets[(first + i) % a.sets]
+                parallel.optimal_transport_sharded(p, s, a.mode, rots[i], ops=shard_ops)
+
+        blk.steps = sharded_steps
+
     # ---- value: device-resident inputs
-    gen_rotations(K, 0)
     sampler = ClockSampler(local)      # NVML init happens here, outside the timed region
     # untimed pre-warm on top of the W warm-up steps: a fresh box idles at low clocks and the first ~100 ms of
     # work run up to 2x slow (measured: 486 vs 265 us/step for the first bench of a box) - W steps are only ~1.5 ms
+    blk.gen_rotations(0)
     t_pre = time.perf_counter()
-    n_pre = 0
     while time.perf_counter() - t_pre < a.prewarm_s:
-        for i in range(20):
-            step(n_pre + i)
-        n_pre += 20
+        blk.steps()
         torch.cuda.synchronize()
-    for i in range(W):
-        step(i)
-    barrier()
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches0 = lib.optex_launch_count()
-    barrier()
-    fence = torch.zeros(1, device=device)
-    e0.record()
-    gen_rotations(K, W)                       # the per-step rotation draw, batched (as optex_ot_loop does)
-    for i in range(K):
-        step(i)
-    fence.add_(1)      # an ordinary kernel: it starts only after the last (PDL-launched) kernel has fully drained
-    e1.record()
-    barrier()
-    launches = lib.optex_launch_count() - launches0
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_regions, host_ms = blk.timed(REPS)
     clocks = sampler.stop() if rank == 0 else None
+    launches = blk.last_launches      # kernels of ours launched inside ONE timed region (draw + K steps + fence)
+    ms_total = statistics.median(ms_regions)
     ms_step = ms_total / K
     value = (1 if sharded else world) * K / (ms_total * 1e-3)
 
-    # ---- breakdown: the step's stages through the exported building blocks, event-timed in the same loop
-    stages = {}
-    if rank == 0:
-        per_channel = a.mode in ("cdf", "sort")
-        if per_channel:
-            rp = torch.empty(c, n, dtype=torch.float32, device=device)
-            rs = torch.empty(c, n, dtype=torch.float32, device=device)
-            names = ["split_R", "rotate_forward_P", "rotate_forward_S", f"{a.mode}_match", "rotate_inverse"]
-            ev = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(K)]
-            pws = torch.empty(lib.optex_rotation_prepare_workspace_bytes(c), dtype=torch.uint8, device=device)
-            mws = torch.empty(max(lib.optex_cdf_match_workspace_bytes(c, 256),
-                                  lib.optex_sort_match_workspace_bytes(c, n, n), 256), dtype=torch.uint8, device=device)
-            lib.optex_set_pdl(0)      # events between kernels need ordinary stream serialisation
-            for i in range(K):
-                p, s = sets[i % a.sets]
-                r = rots[i % K]
-                ev[i][0].record()
-                # R -> tf32 hi / lo once for the three GEMMs, as optex_ot_step does (so each rotate_* stage below is
-                # exactly one GEMM launch)
-                call("optex_rotation_prepare", ptr(r), c, ptr(pws), pws.numel(), st)
-                ev[i][1].record()
-                call("optex_rotate_forward", ptr(p), ptr(r), ptr(rp), n, c, st)
-                ev[i][2].record()
-                call("optex_rotate_forward", ptr(s), ptr(r), ptr(rs), n, c, st)
-                ev[i][3].record()
-                if a.mode == "cdf":
-                    call("optex_cdf_match", ptr(rp), ptr(rs), ptr(rp), c, n, n, 256, None, ptr(mws), mws.numel(), st)
-                else:
-                    call("optex_sort_match", ptr(rp), ptr(rs), ptr(rp), c, n, n, None, ptr(mws), mws.numel(), st)
-                ev[i][4].record()
-                call("optex_rotate_inverse", ptr(rp), ptr(r), ptr(outs[i % 2]), n, c, None, 0.0, st)
-                ev[i][5].record()
-            call("optex_rotation_prepare", None, 0, None, 0, None)
-            torch.cuda.synchronize()
-            lib.optex_set_pdl(0 if a.no_pdl else 1)
-            for j, name in enumerate(names):
-                stages[name] = statistics.mean(ev[i][j].elapsed_time(ev[i][j + 1]) for i in range(K))
+    # ---- breakdown: the step's own launches with an event between its stages (optex_ot_step_profile)
+    stages, stage_launches = {}, {}
+    if rank == 0 and not sharded:
+        names = (["prepare_split_R", "rotate_forward_P", "rotate_forward_S", f"{a.mode}_match", "rotate_inverse"]
+                 if a.mode in ("cdf", "sort") else [f"{a.mode}_step"])
+        sm = (C.c_float * 8)()
+        sl = (C.c_int * 8)()
+        ns = C.c_int(0)
+        acc = [[] for _ in names]
+        for i in range(W + K):
+            p, s = sets[i % a.sets]
+            call("optex_ot_step_profile", ptr(p), ptr(s), ptr(rots[i % K]), ptr(outs[i % 2]), 1, n, 1, n, c, mode, 1.0,
+                 ptr(blk.ws), blk.ws.numel(), st, sm, sl, C.byref(ns))
+            if i >= W:
+                for j in range(min(ns.value, len(names))):
+                    acc[j].append(sm[j])
+                    stage_launches[names[j]] = sl[j]
+        for j, name in enumerate(names):
+            if acc[j]:
+                stages[name] = statistics.mean(acc[j])
 
-    # ---- e2e: host buffers through optex_ot_step_host (H2D + step + D2H per call)
+    # ---- e2e: host buffers through optex_ot_step_host_async (H2D + step + D2H per call)
     e2e = None
-    if not a.no_e2e:
-        hp = [torch.empty(1, a.hw, a.hw, c).pin_memory() for _ in range(2)]
-        hs = [torch.empty(1, a.hw, a.hw, c).pin_memory() for _ in range(2)]
-        ho = [torch.empty(1, a.hw, a.hw, c).pin_memory() for _ in range(2)]
+    if not a.no_e2e and not sharded:
+        NS = 3
+        hp = [torch.empty(1, a.hw, a.hw, c).pin_memory() for _ in range(NS)]
+        ho = [torch.empty(1, a.hw, a.hw, c).pin_memory() for _ in range(NS)]
+        hs = torch.empty(1, a.hw, a.hw, c).pin_memory()
+        for i in range(NS):
+            hp[i].copy_(sets[i % a.sets][0])
+        hs.copy_(sets[0][1])
+        Ke = max(6, min(K, 60))
+        # (1) synchronous call, style re-sent every step (round 1's form): H2D -> step -> D2H -> sync
         for i in range(2):
-            hp[i].copy_(sets[i % a.sets][0]); hs[i].copy_(sets[i % a.sets][1])
-        Ke = max(4, min(K, 30))
-        # (1) synchronous call: H2D -> step -> D2H -> sync, one step at a time
-        for i in range(2):
-            ob.optimal_transport_host(hp[i % 2], hs[i % 2], None, a.mode, out=ho[0], seed=99, counter=i)
+            ob.optimal_transport_host(hp[i % NS], hs, None, a.mode, out=ho[0], seed=99, counter=i)
         barrier()
         t0 = time.perf_counter()
         for i in range(Ke):
-            ob.optimal_transport_host(hp[i % 2], hs[i % 2], None, a.mode, out=ho[0], seed=99, counter=2 + i)
+            ob.optimal_transport_host(hp[i % NS], hs, None, a.mode, out=ho[0], seed=99, counter=2 + i)
         torch.cuda.synchronize()
         dt_sync = max_over_ranks(time.perf_counter() - t0)
-        # (2) the double-buffered form of the same call (optex_ot_step_host_async, slots 0/1 on two streams):
-        #     independent steps, so step i+1 uploads while step i computes and downloads
-        streams = [torch.cuda.Stream(device=device) for _ in range(2)]
-        for i in range(2):
-            ob.optimal_transport_host(hp[i], hs[i], None, a.mode, out=ho[i], seed=99, counter=i, slot=i,
-                                      stream=streams[i])
+        # (2) the pipelined form: the style block is uploaded once and stays resident (it is the same tensor in every
+        #     iteration of a layer, optex.py:112-113), three slots on three streams, so step i+1 uploads while step i
+        #     computes and step i-1 downloads.  Per step: pastiche up, result down.
+        streams = [torch.cuda.Stream(device=device) for _ in range(NS)]
+        ob.set_host_style(hs)
+        torch.cuda.synchronize()
+        sshape = tuple(hs.shape)
+
+        def e2e_step(i):
+            ob.optimal_transport_host(hp[i % NS], None, None, a.mode, out=ho[i % NS], seed=99, counter=i,
+                                      slot=i % NS, stream=streams[i % NS], style_shape=sshape)
+
+        for i in range(2 * NS):
+            e2e_step(i)
         barrier()
         t0 = time.perf_counter()
         for i in range(Ke):
-            ob.optimal_transport_host(hp[i % 2], hs[i % 2], None, a.mode, out=ho[i % 2], seed=99, counter=2 + i,
-                                      slot=i % 2, stream=streams[i % 2])
+            e2e_step(2 * NS + i)
         torch.cuda.synchronize()
         dt = max_over_ranks(time.perf_counter() - t0)
-        e2e = {"value": world * Ke / dt, "unit": UNIT, "h2d_bytes_per_step": 2 * 4 * n * c,
+        ob.set_host_style(None)
+        e2e = {"value": world * Ke / dt, "unit": UNIT, "h2d_bytes_per_step": 4 * n * c,
                "d2h_bytes_per_step": 4 * n * c, "steps": Ke, "ms_per_step": dt / Ke * 1e3,
-               "api": "optex_ot_step_host_async (C-ABI, pinned host buffers in and out, rotation drawn on device, "
-                      "two slots double-buffered so uploads overlap compute + download)",
-               "unpipelined": {"value": world * Ke / dt_sync, "ms_per_step": dt_sync / Ke * 1e3,
-                               "api": "optex_ot_step_host (one synchronous call per step)"}}
+               "api": "optex_ot_step_host_async (C-ABI): pinned host pastiche in, pinned host result out, every step; "
+                      "style block resident on the device (optex_ot_host_set_style: uploaded once, "
+                      f"{4 * n * c} bytes, outside the timed region - it is constant over a layer's iterations); "
+                      "rotation drawn on the device; three slots / streams so upload, compute and download overlap",
+               "style_resent_every_step_unpipelined": {
+                   "value": world * Ke / dt_sync, "ms_per_step": dt_sync / Ke * 1e3,
+                   "h2d_bytes_per_step": 2 * 4 * n * c,
+                   "api": "optex_ot_step_host (one synchronous call per step, P and S uploaded each time)"}}
 
     if rank != 0:
         if world > 1:
@@ -413,6 +514,12 @@ def run_ours(a):
 
     # ---- roofline of the dominant kernel
     pk = peaks()
+    tf32 = None
+    if world == 1 and not a.no_tf32_peak:
+        try:
+            tf32 = measure_tf32_peak(torch, device)
+        except Exception as exc:  # noqa: BLE001
+            tf32 = {"error": str(exc)}
     work = step_work(n, n, c)
     roofline = None
     kernels = {}
@@ -421,7 +528,8 @@ def run_ours(a):
             "rotate_forward_P": ("tensor", 2.0 * c * c * n), "rotate_forward_S": ("tensor", 2.0 * c * c * n),
             "rotate_inverse": ("tensor", 2.0 * c * c * n),
             f"{a.mode}_match": ("hbm", 4.0 * c * (n + n) + 4.0 * c * n),
-            "split_R": ("hbm", 4.0 * c * c * 3),
+            "prepare_split_R": ("hbm", 4.0 * c * c * 3),
+            f"{a.mode}_step": ("tensor", work["flops"]),
         }
         for name, ms in stages.items():
             bound, amount = alg[name]
@@ -429,13 +537,11 @@ def run_ours(a):
                 ach, peak, unit = amount / (ms * 1e-3) / 1e12, pk["bf16_tflops_sustained"], "TFLOP/s"
             else:
                 ach, peak, unit = amount / (ms * 1e-3) / 1e9, pk["hbm_gbs"], "GB/s"
-            kernels[name] = {"ms": ms, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak}
-        # dominant KERNEL: the matcher stage is several launches (its largest kernel is ~half of it, see
-        # profiles/r01_launch_list_summary.csv), the rotation stages are one GEMM launch each
-        single = {k_: v for k_, v in stages.items() if k_.startswith("rotate_")}
+            kernels[name] = {"ms": ms, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+                             "launches": stage_launches.get(name)}
+        # dominant KERNEL: the longest single-launch stage of the step (the matcher counts when it is one launch)
+        single = {k_: v for k_, v in stages.items() if stage_launches.get(k_) == 1} or stages
         top = max(single, key=single.get)
-        for name in kernels:
-            kernels[name]["launches"] = 1 if (name.startswith("rotate_") or name == "split_R") else (3 if a.mode == "cdf" else 2)
         k = kernels[top]
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -443,69 +549,94 @@ def run_ours(a):
             traffic = json.load(open(tpath)).get(f"{top}:{a.mode}:{a.gemm}")
         roofline = {"kernel": top, "bound": k["bound"], "achieved": k["achieved"], "peak": k["peak"], "unit": k["unit"],
                     "frac": k["frac"], "traffic": traffic, "peak_source": pk["source"] +
-                    (" bf16 sustained (tf32 tensor peak is nominally half of it)" if k["bound"] == "tensor" else " copy")}
+                    (" bf16 sustained (MEASURED_PEAKS.json); see tf32 keys for the roof of the arithmetic the kernel "
+                     "actually runs" if k["bound"] == "tensor" else " copy")}
+        if k["bound"] == "tensor" and tf32 and "tf32_tflops_sustained" in tf32:
+            terms = 3 if a.gemm in ("auto", "tf32x3") else 1
+            roofline.update({
+                "tf32_peak_measured": tf32["tf32_tflops_sustained"], "tf32_peak_burst": tf32["tf32_tflops"],
+                "frac_of_tf32_peak": k["achieved"] / tf32["tf32_tflops_sustained"],
+                "tensor_pipe_work_factor": terms,
+                "tensor_pipe_frac_of_tf32_peak": terms * k["achieved"] / tf32["tf32_tflops_sustained"],
+                "note": "3xTF32 issues 3 tensor-core products per algorithmic product (fp32-grade result): achieved "
+                        "counts the algorithmic 2*C*C*N flops; tensor_pipe_frac counts what the pipe executes"})
 
+    kernel_sum = sum(stages.values()) if stages else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if sharded else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a), "gemm": a.gemm,
-                   "prewarm": f"{a.prewarm_s:g} s of untimed steps before the {W} warm-up steps (clock ramp)",
-                   "l2": f"inputs cycle over {a.sets} distinct (P,S) sets = {a.sets * 2 * 4 * n * c / 1e6:.0f} MB > 126 MB L2",
-                   "sharding": ("one block, rotated channels sharded over ranks + NCCL all-gather" if sharded else
-                                "independent feature blocks per rank, no data-path collective")},
-        "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline, "kernels": kernels,
+        "config": config_of(a),
+        "setup": {"gemm": a.gemm,
+                  "prewarm": f"{a.prewarm_s:g} s of untimed steps before the {W} warm-up steps (clock ramp)",
+                  "l2": f"inputs cycle over {a.sets} distinct (P,S) sets = {a.sets * 2 * 4 * n * c / 1e6:.0f} MB > 126 MB L2",
+                  "enqueue": "K steps per region by ONE C call (optex_ot_steps); rotation draw for the K steps inside "
+                             "the region; drain fence kernel before the closing event",
+                  "sharding": ("one block, rotated channels sharded over ranks + NCCL all-gather" if sharded else
+                               "independent feature blocks per rank, no data-path collective")},
+        "repeats": {"n": REPS, "ms_per_region": ms_regions, "ms_median": ms_total, "ms_min": min(ms_regions),
+                    "ms_max": max(ms_regions), "value_from": "median region"},
+        "host_enqueue_ms": statistics.median(host_ms), "kernel_sum_ms": kernel_sum,
+        "kernel_sum_over_step": (kernel_sum / ms_step) if kernel_sum else None,
+        "clocks": clocks, "gpu_launches": int(round(launches)), "e2e": e2e, "roofline": roofline, "kernels": kernels,
+        "tf32_peak": tf32,
         "step_roofline": {"hbm_frac": work["bytes"] / (ms_step * 1e-3) / 1e9 / pk["hbm_gbs"],
                           "tensor_frac": work["flops"] / (ms_step * 1e-3) / 1e12 / pk["bf16_tflops_sustained"],
                           "flops": work["flops"], "bytes": work["bytes"]},
     }
+    if kernel_sum and kernel_sum / ms_step < 0.8:
+        line["warning"] = (f"kernel_sum/ms_per_step = {kernel_sum / ms_step:.2f} < 0.8: the timed region holds time "
+                           "that is in no kernel (host enqueue or launch gaps) - read value with care")
     if world == 1 and not a.no_cpu_baseline:
-        rate, ms, done, cores = cpu_reference_rate(a, steps=12, warmup=1, budget_s=20.0)
-        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "ms_per_step": ms,
-                                "sample": f"{done} full-size steps of the same workload (oracle port incl. rotation "
-                                          f"draw, torch {cores} threads)"}
-    if a.all_modes and world == 1:
+        rate, ms, done, cores, kind = cpu_reference_rate(a, steps=12, warmup=1, budget_s=20.0)
+        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind, "ms_per_step": ms,
+                                "sample": f"{done} full-size steps of the same workload ("
+                                          + ("the unmodified reference's optex.optimal_transport, baseline/_ref"
+                                             if kind == "reference" else "oracle port")
+                                          + f", incl. its rotation draw, torch {cores} threads)"}
+    if world == 1 and not a.no_all_modes:
         extra = {}
         for m in ("cdf", "sort", "chol", "pca", "sym"):
             if m == a.mode:
                 continue
             try:
-                mid = _lib.mode_id(m)
-                w2 = workspace(device, lib.optex_ot_workspace_bytes(n, n, c, mid))
-                def st2(i):
-                    p, s = sets[i % a.sets]
-                    call("optex_ot_step", ptr(p), ptr(s), ptr(rots[i % K]), ptr(outs[i % 2]), 1, n, 1, n, c, mid,
-                         1.0, None, 0.0, ptr(w2), w2.numel(), st)
-                for i in range(3):
-                    st2(i)
-                torch.cuda.synchronize()
-                e0.record()
-                for i in range(K):
-                    st2(i)
-                e1.record()
-                torch.cuda.synchronize()
-                extra[m] = K / (e0.elapsed_time(e1) * 1e-3)
+                b2 = Block(a.hw, a.channels, m, 0, a.sets)
+                ms2, _ = b2.timed(3)
+                extra[m] = {"it_s": K / (statistics.median(ms2) * 1e-3), "ms_per_step": statistics.median(ms2) / K}
+                del b2
             except Exception as exc:  # noqa: BLE001
                 extra[m] = f"error: {exc}"
-        line["other_modes_it_s"] = extra
+        line["other_modes"] = extra
         gm = {}
         for g in ("tf32", "fp32"):       # rotation-GEMM arithmetic variants of the headline mode
             try:
                 ob.set_gemm_mode(g)
-                for i in range(3):
-                    step(i)
-                torch.cuda.synchronize()
-                e0.record()
-                for i in range(K):
-                    step(i)
-                e1.record()
-                torch.cuda.synchronize()
-                gm[g] = K / (e0.elapsed_time(e1) * 1e-3)
+                ms2, _ = blk.timed(3)
+                gm[g] = {"it_s": K / (statistics.median(ms2) * 1e-3), "ms_per_step": statistics.median(ms2) / K}
             except Exception as exc:  # noqa: BLE001
                 gm[g] = f"error: {exc}"
             finally:
                 ob.set_gemm_mode(a.gemm)
-        line["other_gemm_modes_it_s"] = gm
+        line["other_gemm_modes"] = gm
+    if world == 1 and not a.no_layers:
+        lay = {}
+        for (hw, ch), name in sorted(LAYERS.items(), key=lambda kv: kv[0][0]):
+            if (hw, ch) == (a.hw, a.channels):
+                continue
+            try:
+                nsets = max(1, min(a.sets, int(300e6 // (2 * 4 * hw * hw * ch)) + 1))
+                b2 = Block(hw, ch, a.mode, 0, nsets)
+                ms2, _ = b2.timed(3)
+                m_step = statistics.median(ms2) / K
+                w2 = step_work(hw * hw, hw * hw, ch)
+                lay[f"{name}@1024^2"] = {"it_s": 1e3 / m_step, "ms_per_step": m_step,
+                                         "hbm_frac": w2["bytes"] / (m_step * 1e-3) / 1e9 / pk["hbm_gbs"],
+                                         "shape": [hw * hw, ch]}
+                del b2
+                torch.cuda.empty_cache()
+            except Exception as exc:  # noqa: BLE001
+                lay[f"{name}@1024^2"] = f"error: {exc}"
+        line["other_layers"] = lay
     if world == 1 and not a.no_synthesis:
         try:
             line["synthesis"] = synthesis_block(a)
@@ -518,74 +649,115 @@ def run_ours(a):
 
 
 # ------------------------------------------------------------------------------------------- end-to-end synthesis
+def _real_inputs():
+    """(state_dicts, style path) of the reference's own weights and bundled image when baseline/_ref is staged."""
+    try:
+        from baseline import reference
+    except Exception:  # noqa: BLE001
+        return None
+    if not (reference.available() and reference.has_weights()):
+        return None
+    import torch
+
+    root = reference.path()
+    sd = {}
+    for d in range(1, 6):
+        sd[("encoder", d)] = torch.load(os.path.join(root, "models", f"vgg_normalised_conv{d}_1.pth"), map_location="cpu")
+        sd[("decoder", d)] = torch.load(os.path.join(root, "models", f"feature_invertor_conv{d}_1.pth"), map_location="cpu")
+    return {"state_dicts": sd, "root": root, "reference": reference}
+
+
 def synthesis_block(a):
     """BASELINE.json metric (ii): output pixels / second of OptimalTexture.forward (optex.py:81-139, timed like the
-    reference's own `time()` pair at optex.py:287-289 but with a device synchronisation on both sides) on
-    configs[1]: texture synthesis, all five VGG layers, hist_mode pca, 5 passes, 500 iterations.  Synthetic style
-    image of the bundled graffiti.jpg's shape at that size, random-init weights of the reference's architecture
-    (its ./models/*.pth are not in this repository), rotations drawn on the device."""
+    reference's own `time()` pair at optex.py:287-289 but with a device synchronisation on both sides).
+
+    configs[1]: texture synthesis 512^2, all five VGG layers, hist_mode pca, 5 passes, 500 iterations - ours.
+    configs[0]: graffiti.jpg --size 256, 4 passes, hist pca - ours AND the reference on the host cores (cpu_baseline).
+    With baseline/_ref staged the inputs are REAL: the reference's trained ./models/*.pth and its bundled
+    style/graffiti.jpg loaded by its own util.load_styles; otherwise synthetic style + random-init weights."""
     import torch
 
     import optimaltextures_b200 as ob
     from optimaltextures_b200 import texture, vgg
 
-    size = a.synthesis_size
-    kw = dict(size=size, iters=500, passes=5, hist_mode="pca")
-    sd = vgg.random_state_dicts(0)
-    g = torch.Generator().manual_seed(0)
-    style = torch.rand(1, 3, round(size * 736 / 512 / 32) * 32, size, generator=g)
-    pastiche = torch.rand(1, 3, size, size, generator=g)
-    model = texture.OptimalTexture(state_dicts=sd, **kw)
-    dev_style, dev_pastiche = style.cuda(), pastiche.cuda()
+    real = _real_inputs()
     lib = ob._lib.lib()
-    out = {"workload": f"texture synthesis {size}^2 (configs[1]): 5 VGG layers, hist pca, 5 passes, 500 iters; style "
-                       f"{tuple(style.shape)} synthetic, random-init weights", "unit": "px/s"}
-    for rep in range(2):                                   # first run allocates workspaces: warm-up
-        ob.manual_seed(0)
-        model.ot_calls = 0
-        model.profile = {} if rep == 1 else None
-        l0 = lib.optex_launch_count()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        res = model.forward(dev_pastiche, [dev_style])
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        launches = lib.optex_launch_count() - l0
-    out.update({"value": res.shape[0] * res.shape[2] * res.shape[3] / dt, "seconds": dt, "ot_iters": model.ot_calls,
+
+    def inputs(size):
+        g = torch.Generator().manual_seed(0)
+        if real:
+            ref = real["reference"].load()
+            # optex.py:264-272: styles at `size`, oversize only matters with content
+            style = ref.util.load_styles([os.path.join(real["root"], "style", "graffiti.jpg")], size=size, scale=1.0)[0]
+        else:
+            style = torch.rand(1, 3, round(size * 736 / 512 / 32) * 32, size, generator=g)
+        pastiche = torch.rand(1, 3, size, size, generator=g)
+        return style, pastiche
+
+    sd = real["state_dicts"] if real else vgg.random_state_dicts(0)
+    data = ("reference's models/*.pth + style/graffiti.jpg (baseline/_ref)" if real
+            else "synthetic style of graffiti.jpg's shape, random-init weights (baseline/_ref not staged)")
+
+    def ours(size, passes):
+        kw = dict(size=size, iters=500, passes=passes, hist_mode="pca")
+        style, pastiche = inputs(size)
+        model = texture.OptimalTexture(state_dicts=sd, **kw)
+        dev_style, dev_pastiche = style.cuda(), pastiche.cuda()
+        for rep in range(2):                                   # first run allocates workspaces: warm-up
+            ob.manual_seed(0)
+            model.ot_calls = 0
+            model.profile = {} if rep == 1 else None
+            l0 = lib.optex_launch_count()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            res = model.forward(dev_pastiche, [dev_style])
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            launches = lib.optex_launch_count() - l0
+        return {"value": res.shape[0] * res.shape[2] * res.shape[3] / dt, "unit": "px/s", "seconds": dt,
+                "out_shape": list(res.shape), "style_shape": list(style.shape), "ot_iters": model.ot_calls,
                 "gpu_launches": int(launches), "pca_k_last_pass": model.last_pca_k,
                 "pca_jacobi_sweeps_per_pass": model.pca_sweeps,
                 "stage_ms": {k: round(v, 2) for k, v in model.stage_ms().items()},
-                "finite": bool(torch.isfinite(res).all())})
-    # additive option: component counts rounded up to multiples of 32 (tensor-core path for the C x C chains)
-    model32 = texture.OptimalTexture(state_dicts=sd, pca_round_k=32, **kw)
-    for rep in range(2):
-        ob.manual_seed(0)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        res32 = model32.forward(dev_pastiche, [dev_style])
-        torch.cuda.synchronize()
-        dt32 = time.perf_counter() - t0
-    out["pca_round_k_32"] = {"value": res32.shape[0] * res32.shape[2] * res32.shape[3] / dt32, "seconds": dt32,
-                             "pca_k_last_pass": model32.last_pca_k, "finite": bool(torch.isfinite(res32).all())}
-    if a.synthesis_cpu:
-        from oracle import texture_oracle
+                "finite": bool(torch.isfinite(res).all())}, (style, pastiche, kw)
 
+    out = {"data": data, "unit": "px/s"}
+    size = a.synthesis_size
+    r2, _ = ours(size, 5)
+    out.update(r2)
+    out["workload"] = (f"configs[1]: texture synthesis {size}^2, 5 VGG layers, hist pca, 5 passes, 500 iters; "
+                       f"style {tuple(r2['style_shape'])}")
+    r1, (style1, pastiche1, kw1) = ours(256, 4)
+    r1["workload"] = f"configs[0]: graffiti.jpg --size 256 --passes 4 --hist_mode pca; style {tuple(r1['style_shape'])}"
+    out["cfg0_256"] = r1
+    if not a.no_synthesis_cpu:
         torch.set_num_threads(os.cpu_count() or 1)
-        rot_cache = {}
-
-        def rot(c, index):                                 # the reference draws one scipy rotation per call
+        torch.manual_seed(0)
+        if real:
+            ref = real["reference"].load()
+            with real["reference"].in_reference_dir(), torch.inference_mode():
+                cpu_model = ref.optex.OptimalTexture(**kw1)          # reads ./models/*.pth itself (vgg.py:144,162)
+                t0 = time.perf_counter()
+                res = cpu_model.forward(pastiche1, [style1])
+                dt_cpu = time.perf_counter() - t0
+            kind, what = "reference", "the unmodified reference's OptimalTexture.forward (baseline/_ref), scipy rotations"
+        else:
+            from oracle import texture_oracle
             from scipy.stats import special_ortho_group
 
-            return torch.tensor(special_ortho_group.rvs(c)) if c > 1 else torch.ones(1, 1, dtype=torch.float64)
+            def rot(c, index):                                 # the reference draws one scipy rotation per call
+                return torch.tensor(special_ortho_group.rvs(c)) if c > 1 else torch.ones(1, 1, dtype=torch.float64)
 
-        cpu_model = texture_oracle.OptimalTexture(sd, rotation_fn=rot, **kw)
-        t0 = time.perf_counter()
-        with torch.inference_mode():
-            ref = cpu_model.forward(pastiche, [style])
-        dt_cpu = time.perf_counter() - t0
-        out["cpu_baseline"] = {"value": ref.shape[0] * ref.shape[2] * ref.shape[3] / dt_cpu, "unit": "px/s",
-                               "seconds": dt_cpu, "cores": os.cpu_count(), "kind": "port",
-                               "sample": "the whole synthesis once (oracle port, scipy rotation per OT call)"}
+            cpu_model = texture_oracle.OptimalTexture(sd, rotation_fn=rot, **kw1)
+            t0 = time.perf_counter()
+            with torch.inference_mode():
+                res = cpu_model.forward(pastiche1, [style1])
+            dt_cpu = time.perf_counter() - t0
+            kind, what = "port", "oracle port of OptimalTexture.forward, scipy rotation per OT call"
+        out["cfg0_256"]["cpu_baseline"] = {
+            "value": res.shape[0] * res.shape[2] * res.shape[3] / dt_cpu, "unit": "px/s", "seconds": dt_cpu,
+            "cores": os.cpu_count(), "kind": kind, "sample": f"the whole configs[0] synthesis once ({what})",
+            "out_shape": list(res.shape), "finite": bool(torch.isfinite(res).all())}
     return out
 
 

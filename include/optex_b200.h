@@ -68,9 +68,10 @@ int optex_get_gemm_mode(void);
 /* Programmatic dependent launch between the library's kernels (default on).  Turn it off to time individual
  * kernels with CUDA events: under PDL a kernel may start before its predecessor has drained. */
 int optex_set_pdl(int enable);
-/* The tensor-core GEMMs split their small operand into tf32 halves in a library-owned scratch buffer: one per device
- * and SLOT (0 or 1).  Calls enqueued on two streams that may run concurrently must use different slots; the slot is
- * a property of the calling host thread (default 0) until changed.  optex_ot_step_host_async manages it itself.
+/* The tensor-core GEMMs split their small operand into tf32 halves in a library-owned scratch buffer: one per device,
+ * stream and slot (0..3): work enqueued on different streams never shares scratch.  The slot additionally separates
+ * independent pipelines that share one stream; it is a property of the calling host thread (default 0) until changed.
+ * optex_ot_step_host_async manages it itself.
  * Returns the previous slot.  (No reference counterpart: the reference runs on one stream, optex.py:256.) */
 int optex_set_scratch_slot(int slot);
 /* Arithmetic of the Householder construction behind optex_random_rotation(s): 1 = fp64 (default; what the
@@ -114,15 +115,46 @@ int optex_ot_step_host(const float *P, const float *S, const float *R, float *ou
                        float content_strength, uint64_t seed, uint64_t counter,
                        void *stream);
 
-/* The same without the final synchronisation, for callers that pipeline independent steps: `slot` (0 or 1)
- * selects one of two library-owned device scratch sets, so step i+1 (slot 1, stream B) can upload while step i
- * (slot 0, stream A) still computes / downloads.  Use PINNED host buffers and one stream per slot; the caller
- * synchronises the stream before reading `out` or reusing the slot. */
+/* The same without the final synchronisation, for callers that pipeline independent steps: `slot` (0, 1 or 2)
+ * selects one of three library-owned device scratch sets, so step i+1 (slot B, stream B) can upload while step i
+ * (slot A, stream A) computes and step i-1 (slot C, stream C) downloads.  Use PINNED host buffers and one stream per
+ * slot; the caller synchronises the stream before reading `out` or reusing the slot. */
 int optex_ot_step_host_async(const float *P, const float *S, const float *R, float *out,
                              int b_p, int64_t hw_p, int b_s, int64_t hw_s, int c,
                              int mode, float eps, const float *content,
                              float content_strength, uint64_t seed, uint64_t counter,
                              int slot, void *stream);
+
+/* The style block is the same tensor in every iteration of a layer's loop (optex.py:112-113 passes
+ * style_features[l] each time): upload it ONCE and keep it resident on the device.  optex_ot_step_host /
+ * optex_ot_step_host_async called afterwards with S == NULL (same b_s, hw_s, c) reuse it, on any slot and stream
+ * (ordered by an event).  S == NULL here releases the resident block.  One resident block per process. */
+int optex_ot_host_set_style(const float *S, int b_s, int64_t hw_s, int c, void *stream);
+
+/* `steps` INDEPENDENT OT steps (optex.py:167-177 each) enqueued by one call - e.g. a batch of syntheses standing at
+ * the same layer: step i transports P[(first + i) % n_sets] towards S[(first + i) % n_sets] with rotation
+ * R_all[i] ([steps, c, c] on the device) into out[(first + i) % n_out].  P / S / out are HOST arrays of device
+ * pointers.  Same arithmetic and kernels as `steps` optex_ot_step calls, without a host round trip per step. */
+int optex_ot_steps(const float *const *P, const float *const *S, int n_sets, const float *R_all,
+                   float *const *out, int n_out, int steps, int first, int b_p, int64_t hw_p,
+                   int b_s, int64_t hw_s, int c, int mode, float eps, void *workspace,
+                   size_t workspace_bytes, void *stream);
+
+/* One optex_ot_step with a CUDA event between its stages - the step's own launches, in place, with PDL off for the
+ * call; synchronises `stream`.  Measurement aid (no reference counterpart).  Per-channel modes report 5 stages:
+ * prepare (split R / reset range slots), forward rotation of P, of S (optex.py:170-171), the matcher
+ * (histmatch.py:49-69), inverse rotation (optex.py:175); covariance modes report 1 (the whole step).
+ * stage_ms / stage_launches hold OPTEX_MAX_STAGES entries. */
+#define OPTEX_MAX_STAGES 8
+int optex_ot_step_profile(const float *P, const float *S, const float *R, float *out,
+                          int b_p, int64_t hw_p, int b_s, int64_t hw_s, int c, int mode,
+                          float eps, void *workspace, size_t workspace_bytes, void *stream,
+                          float *stage_ms, int *stage_launches, int *n_stages);
+
+/* An ordinary (not programmatically serialised) empty kernel on `stream`: it starts only once every earlier kernel
+ * of the stream has fully drained, so an event recorded behind it brackets PDL-launched work correctly
+ * (timing aid; no reference counterpart). */
+int optex_fence(void *stream);
 
 /* ---- the inner loop --------------------------------------------------------
  * replaces: optex.py:112-117  (`for _ in range(iters): optimal_transport; blend`)

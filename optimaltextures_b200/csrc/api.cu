@@ -112,6 +112,20 @@ static int rotate_inverse(const float *M, bool m_channel_major, const float *R, 
                       strength, 1.f, st);
 }
 
+// Stage profiler of optex_ot_step_profile: events between the step's launches (the caller turns PDL off)
+struct StageProf {
+    cudaEvent_t ev[OPTEX_MAX_STAGES + 1];
+    uint64_t launches[OPTEX_MAX_STAGES + 1];
+    int n = 0;
+};
+static thread_local StageProf *g_prof = nullptr;
+static void prof_mark(cudaStream_t st) {
+    if (!g_prof || g_prof->n > OPTEX_MAX_STAGES) return;
+    cudaEventRecord(g_prof->ev[g_prof->n], st);
+    g_prof->launches[g_prof->n] = g_launches.load();
+    ++g_prof->n;
+}
+
 static bool per_channel(int mode) { return mode == OPTEX_MODE_CDF || mode == OPTEX_MODE_SORT; }
 static bool valid_mode(int mode) { return mode >= OPTEX_MODE_CHOL && mode <= OPTEX_MODE_SORT; }
 
@@ -149,9 +163,13 @@ static int ot_step_impl(const float *P, const float *S, const float *R, float *o
                         int b_s, int64_t hw_s, int c, int mode, float eps, const float *content, float strength,
                         void *ws, size_t ws_bytes, cudaStream_t st, int style_reuse = 0) {
     const int64_t n_p = (int64_t)b_p * hw_p, n_s = (int64_t)b_s * hw_s;
-    if (!per_channel(mode))  // closed-form modes: rotation folded into C x C products (cov_match.cu)
-        return cov_ot_step(P, S, R, out, b_p, hw_p, b_s, hw_s, c, mode, eps, content, strength, ws, ws_bytes, st,
-                           style_reuse);
+    if (!per_channel(mode)) {  // closed-form modes: rotation folded into C x C products (cov_match.cu)
+        prof_mark(st);
+        int rc = cov_ot_step(P, S, R, out, b_p, hw_p, b_s, hw_s, c, mode, eps, content, strength, ws, ws_bytes, st,
+                             style_reuse);
+        prof_mark(st);
+        return rc;
+    }
     Arena ar(ws, ws_bytes);
     float *rp = ar.take<float>((size_t)n_p * c);
     float *rs = ar.take<float>((size_t)n_s * c);
@@ -170,28 +188,32 @@ static int ot_step_impl(const float *P, const float *S, const float *R, float *o
     } presplit_guard;
     bool forced_tc;
     const bool tc3 = want_tc(forced_tc) && tc_terms() == 3 && c % 4 == 0;
+    prof_mark(st);
     if (tc3) {
         OPTEX_TRY(gemm_tc_split_and_fill(R, r_hi, r_lo, (int64_t)c * c, mode == OPTEX_MODE_CDF ? (uint32_t *)mw : nullptr,
                                          mode == OPTEX_MODE_CDF ? 2 * (int64_t)c : 0, 0xffffffffu, st));
         gemm_tc_set_presplit(R, r_hi, r_lo);
     }
+    uint32_t *minmax = nullptr;
     if (mode == OPTEX_MODE_CDF) {
         // the forward rotations fold the per-channel range (histmatch.py:52-53) into their epilogues
-        uint32_t *minmax = (uint32_t *)mw;
-        bool r1 = false, r2 = false;
+        minmax = (uint32_t *)mw;
         if (!tc3) OPTEX_TRY(fill_u32(minmax, 2 * (int64_t)c, 0xffffffffu, st));
-        OPTEX_TRY(rotate_forward(P, R, rp, n_p, c, true, st, 0, -1, minmax, &r1));
-        OPTEX_TRY(rotate_forward(S, R, rs, n_s, c, true, st, 0, -1, minmax, &r2));
-        OPTEX_TRY(cdf_match_core(rp, rs, mt, c, n_p, n_s, 256, nullptr, mw, mws, r1 && r2, st));
-        return rotate_inverse(mt, true, R, out, n_p, c, content, strength, st);
     }
-    OPTEX_TRY(rotate_forward(P, R, rp, n_p, c, true, st));
-    OPTEX_TRY(rotate_forward(S, R, rs, n_s, c, true, st));
+    prof_mark(st);  // stage 0: prepare (split R, reset range slots)
+    bool r1 = false, r2 = false;
+    OPTEX_TRY(rotate_forward(P, R, rp, n_p, c, true, st, 0, -1, minmax, &r1));
+    prof_mark(st);  // stage 1: forward rotation of the pastiche
+    OPTEX_TRY(rotate_forward(S, R, rs, n_s, c, true, st, 0, -1, minmax, &r2));
+    prof_mark(st);  // stage 2: forward rotation of the style
     if (mode == OPTEX_MODE_CDF)
-        OPTEX_TRY(optex_cdf_match(rp, rs, mt, c, n_p, n_s, 256, nullptr, mw, mws, st));
+        OPTEX_TRY(cdf_match_core(rp, rs, mt, c, n_p, n_s, 256, nullptr, mw, mws, r1 && r2, st));
     else
         OPTEX_TRY(sort_match_inplace(rp, rs, mt, c, n_p, n_s, nullptr, mw, mws, st));  // rs is scratch: sorted in place
-    return rotate_inverse(mt, true, R, out, n_p, c, content, strength, st);
+    prof_mark(st);  // stage 3: matcher
+    int rc = rotate_inverse(mt, true, R, out, n_p, c, content, strength, st);
+    prof_mark(st);  // stage 4: inverse rotation (+ blend)
+    return rc;
 }
 
 // library-owned device scratch for the *_host entry points
@@ -216,7 +238,22 @@ struct HostScratch {
         return OPTEX_OK;
     }
 };
-static HostScratch g_host[2];  // one per pipeline slot of optex_ot_step_host_async
+constexpr int kHostSlots = 3;   // upload of step i+1 | compute of step i | download of step i-1
+static HostScratch g_host[kHostSlots];  // one per pipeline slot of optex_ot_step_host_async
+
+// The style block is constant over the iterations of a layer (optex.py:112-113 passes the same style_features[l]
+// every time): optex_ot_host_set_style uploads it once, the *_host entry points called with S == NULL reuse it.
+struct ResidentStyle {
+    std::mutex mu;
+    void *buf = nullptr;
+    size_t cap = 0;
+    int dev = -1, b_s = 0, c = 0;
+    int64_t hw_s = 0;
+    cudaEvent_t ready = nullptr;
+};
+static ResidentStyle g_style;
+
+__global__ void fence_kernel() {}
 
 }  // namespace optex
 
@@ -242,7 +279,7 @@ extern "C" int optex_debug_gemm_trace(void *device_buf) {
 static thread_local int g_user_slot = 0;
 extern "C" int optex_set_scratch_slot(int slot) {
     const int prev = g_user_slot;
-    g_user_slot = slot & 1;
+    g_user_slot = slot & 3;
     gemm_tc_set_scratch_slot(g_user_slot);
     return prev;
 }
@@ -282,14 +319,33 @@ static int ot_step_host_impl(const float *P, const float *S, const float *R, flo
                              float content_strength, uint64_t seed, uint64_t counter, int slot, bool sync,
                              cudaStream_t st) {
     OPTEX_TRY(require_sm100());
-    OPTEX_TRY(check_step_args("optex_ot_step_host", P, S, out, b_p, hw_p, b_s, hw_s, c, mode));
+    const float *dS_res = nullptr;
+    if (!S) {  // resident style (optex_ot_host_set_style)
+        std::lock_guard<std::mutex> lock(g_style.mu);
+        int d = 0;
+        OPTEX_CUDA(cudaGetDevice(&d));
+        if (!g_style.buf || g_style.dev != d) {
+            set_error("optex_ot_step_host: S == NULL but no style block is resident on device %d "
+                      "(call optex_ot_host_set_style first)", d);
+            return OPTEX_EINVAL;
+        }
+        if (g_style.b_s != b_s || g_style.hw_s != hw_s || g_style.c != c) {
+            set_error("optex_ot_step_host: resident style is [%d x %lld, %d], call asks for [%d x %lld, %d]", g_style.b_s,
+                      (long long)g_style.hw_s, g_style.c, b_s, (long long)hw_s, c);
+            return OPTEX_EINVAL;
+        }
+        dS_res = (const float *)g_style.buf;
+        OPTEX_CUDA(cudaStreamWaitEvent(st, g_style.ready, 0));
+    }
+    OPTEX_TRY(check_step_args("optex_ot_step_host", P, S ? (const void *)S : (const void *)dS_res, out, b_p, hw_p, b_s,
+                              hw_s, c, mode));
     const int64_t n_p = (int64_t)b_p * hw_p, n_s = (int64_t)b_s * hw_s;
     const size_t bp = align_up(sizeof(float) * (size_t)n_p * c, 256), bs = align_up(sizeof(float) * (size_t)n_s * c, 256);
     const size_t br = align_up(sizeof(float) * (size_t)c * c, 256);
     const size_t step_ws = optex_ot_workspace_bytes(n_p, n_s, c, mode);
     const size_t rot_ws = R ? 0 : align_up(rotation_ws_bytes(c, 1), 256);
     const size_t ws = step_ws + rot_ws;
-    HostScratch &hs = g_host[slot & 1];
+    HostScratch &hs = g_host[slot % kHostSlots];
     std::lock_guard<std::mutex> lock(hs.mu);
     OPTEX_TRY(hs.ensure(2 * bp + bs + br + (content ? bp : 0) + ws));
     char *base = (char *)hs.buf;
@@ -299,13 +355,14 @@ static int ot_step_host_impl(const float *P, const float *S, const float *R, flo
     void *dW = base + 2 * bp + bs + br + (content ? bp : 0);
     gemm_tc_set_scratch_slot(slot);
     OPTEX_CUDA(cudaMemcpyAsync(dP, P, sizeof(float) * n_p * c, cudaMemcpyHostToDevice, st));
-    OPTEX_CUDA(cudaMemcpyAsync(dS, S, sizeof(float) * n_s * c, cudaMemcpyHostToDevice, st));
+    if (S) OPTEX_CUDA(cudaMemcpyAsync(dS, S, sizeof(float) * n_s * c, cudaMemcpyHostToDevice, st));
+    const float *dS_use = S ? dS : dS_res;
     if (R)
         OPTEX_CUDA(cudaMemcpyAsync(dR, R, sizeof(float) * (size_t)c * c, cudaMemcpyHostToDevice, st));
     else
         OPTEX_TRY(random_rotations(dR, c, 1, seed, counter, nullptr, (char *)dW + step_ws, rot_ws, st));
     if (content) OPTEX_CUDA(cudaMemcpyAsync(dC, content, sizeof(float) * n_p * c, cudaMemcpyHostToDevice, st));
-    int rc = ot_step_impl(dP, dS, dR, dO, b_p, hw_p, b_s, hw_s, c, mode, eps, dC, content_strength, dW, step_ws, st);
+    int rc = ot_step_impl(dP, dS_use, dR, dO, b_p, hw_p, b_s, hw_s, c, mode, eps, dC, content_strength, dW, step_ws, st);
     gemm_tc_set_scratch_slot(g_user_slot);
     OPTEX_TRY(rc);
     OPTEX_CUDA(cudaMemcpyAsync(out, dO, sizeof(float) * n_p * c, cudaMemcpyDeviceToHost, st));
@@ -325,12 +382,124 @@ extern "C" int optex_ot_step_host_async(const float *P, const float *S, const fl
                                         int64_t hw_p, int b_s, int64_t hw_s, int c, int mode, float eps,
                                         const float *content, float content_strength, uint64_t seed,
                                         uint64_t counter, int slot, void *stream) {
-    if (slot != 0 && slot != 1) {
-        set_error("optex_ot_step_host_async: slot must be 0 or 1");
+    if (slot < 0 || slot >= kHostSlots) {
+        set_error("optex_ot_step_host_async: slot must be 0, 1 or 2");
         return OPTEX_EINVAL;
     }
     return ot_step_host_impl(P, S, R, out, b_p, hw_p, b_s, hw_s, c, mode, eps, content, content_strength, seed,
                              counter, slot, false, (cudaStream_t)stream);
+}
+
+extern "C" int optex_ot_host_set_style(const float *S, int b_s, int64_t hw_s, int c, void *stream) {
+    OPTEX_TRY(require_sm100());
+    std::lock_guard<std::mutex> lock(g_style.mu);
+    if (!S) {  // release
+        if (g_style.buf) {
+            cudaDeviceSynchronize();
+            cudaFree(g_style.buf);
+        }
+        g_style.buf = nullptr;
+        g_style.cap = 0;
+        g_style.dev = -1;
+        return OPTEX_OK;
+    }
+    if (b_s < 1 || hw_s < 1 || c < 1) {
+        set_error("optex_ot_host_set_style: empty shape");
+        return OPTEX_EINVAL;
+    }
+    int d = 0;
+    OPTEX_CUDA(cudaGetDevice(&d));
+    const size_t bytes = sizeof(float) * (size_t)b_s * hw_s * c;
+    if (g_style.buf && (g_style.dev != d || g_style.cap < bytes)) {
+        OPTEX_CUDA(cudaDeviceSynchronize());
+        OPTEX_CUDA(cudaFree(g_style.buf));
+        g_style.buf = nullptr;
+        g_style.cap = 0;
+    }
+    if (!g_style.buf) {
+        OPTEX_CUDA(cudaMalloc(&g_style.buf, bytes));
+        g_style.cap = bytes;
+        g_style.dev = d;
+    }
+    if (!g_style.ready) OPTEX_CUDA(cudaEventCreateWithFlags(&g_style.ready, cudaEventDisableTiming));
+    cudaStream_t st = (cudaStream_t)stream;
+    OPTEX_CUDA(cudaMemcpyAsync(g_style.buf, S, bytes, cudaMemcpyHostToDevice, st));
+    OPTEX_CUDA(cudaEventRecord(g_style.ready, st));
+    g_style.b_s = b_s;
+    g_style.hw_s = hw_s;
+    g_style.c = c;
+    return OPTEX_OK;
+}
+
+// `steps` INDEPENDENT OT steps enqueued by one call (a batch of syntheses at the same layer; the granularity of the
+// reference's own loop, optex.py:112-113, without a host round trip per step): step i transports
+// P[(first + i) % n_sets] towards S[(first + i) % n_sets] with rotation R_all[i] into out[(first + i) % n_out].
+extern "C" int optex_ot_steps(const float *const *P, const float *const *S, int n_sets, const float *R_all,
+                              float *const *out, int n_out, int steps, int first, int b_p, int64_t hw_p, int b_s,
+                              int64_t hw_s, int c, int mode, float eps, void *workspace, size_t workspace_bytes,
+                              void *stream) {
+    OPTEX_TRY(require_sm100());
+    if (!P || !S || !out || !R_all || n_sets < 1 || n_out < 1 || steps < 0 || first < 0) {
+        set_error("optex_ot_steps: NULL table or empty set list");
+        return OPTEX_EINVAL;
+    }
+    for (int i = 0; i < steps; ++i) {
+        const int k = (first + i) % n_sets, o = (first + i) % n_out;
+        OPTEX_TRY(check_step_args("optex_ot_steps", P[k], S[k], out[o], b_p, hw_p, b_s, hw_s, c, mode));
+        if (out[o] == P[k] || out[o] == S[k]) {
+            set_error("optex_ot_steps: out must not alias an input");
+            return OPTEX_EINVAL;
+        }
+        OPTEX_TRY(ot_step_impl(P[k], S[k], R_all + (size_t)i * c * c, out[o], b_p, hw_p, b_s, hw_s, c, mode, eps, nullptr,
+                               0.f, workspace, workspace_bytes, (cudaStream_t)stream));
+    }
+    return OPTEX_OK;
+}
+
+// One OT step with an event between its stages (measurement aid for bench.py: the in-step launches exactly as
+// optex_ot_step issues them, which the stand-alone building blocks only approximate).  PDL is off for the call (an
+// event between two programmatically serialised kernels does not separate them); synchronises the stream.
+// per-channel modes: stage_ms[0..4] = prepare, rotate_forward_P, rotate_forward_S, match, rotate_inverse;
+// covariance modes: stage_ms[0] = the whole step.
+extern "C" int optex_ot_step_profile(const float *P, const float *S, const float *R, float *out, int b_p, int64_t hw_p,
+                                     int b_s, int64_t hw_s, int c, int mode, float eps, void *workspace,
+                                     size_t workspace_bytes, void *stream, float *stage_ms, int *stage_launches,
+                                     int *n_stages) {
+    OPTEX_TRY(require_sm100());
+    OPTEX_TRY(check_step_args("optex_ot_step_profile", P, S, out, b_p, hw_p, b_s, hw_s, c, mode));
+    if (!R || !stage_ms || !stage_launches || !n_stages) {
+        set_error("optex_ot_step_profile: NULL rotation or result pointer");
+        return OPTEX_EINVAL;
+    }
+    StageProf prof;
+    for (auto &e : prof.ev) OPTEX_CUDA(cudaEventCreate(&e));
+    const int pdl = g_pdl.exchange(0);
+    g_prof = &prof;
+    int rc = ot_step_impl(P, S, R, out, b_p, hw_p, b_s, hw_s, c, mode, eps, nullptr, 0.f, workspace, workspace_bytes,
+                          (cudaStream_t)stream);
+    g_prof = nullptr;
+    g_pdl.store(pdl);
+    cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+    *n_stages = 0;
+    if (rc == OPTEX_OK && e == cudaSuccess) {
+        for (int i = 0; i + 1 < prof.n; ++i) {
+            cudaEventElapsedTime(&stage_ms[i], prof.ev[i], prof.ev[i + 1]);
+            stage_launches[i] = (int)(prof.launches[i + 1] - prof.launches[i]);
+        }
+        *n_stages = prof.n > 0 ? prof.n - 1 : 0;
+    }
+    for (auto &ev : prof.ev) cudaEventDestroy(ev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaStreamSynchronize");
+    return rc;
+}
+
+// An ordinary (not programmatically serialised) empty kernel: it starts only after every earlier kernel of the
+// stream - including PDL-launched ones, whose completion an event alone does not imply - has fully drained.
+extern "C" int optex_fence(void *stream) {
+    OPTEX_TRY(require_sm100());
+    fence_kernel<<<1, 32, 0, (cudaStream_t)stream>>>();
+    OPTEX_LAUNCH_CHECK("fence_kernel");
+    return OPTEX_OK;
 }
 
 static const int kRotChunk = 16;

@@ -574,12 +574,8 @@ int cdf_match_core(const float *target, const float *source, float *out, int c, 
     static const char *no_fused = getenv("OPTEX_NO_CDF_FUSED");
     if (priv && n_big <= 32768 && c >= 2 * sm_count() && !(no_fused && atoi(no_fused))) {
         const size_t smem = sizeof(uint32_t) * 2 * (size_t)bins + 2 * (size_t)(bins + 1) * NTH_HIST;
-        static bool attr_done = false;
-        if (!attr_done) {
-            OPTEX_CUDA(cudaFuncSetAttribute(cdf_channel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)(sizeof(uint32_t) * 2 * PRIV_MAX_BINS + 2 * (PRIV_MAX_BINS + 1) * NTH_HIST)));
-            attr_done = true;
-        }
+        static PerDeviceOnce attr_once1;
+        OPTEX_TRY(ensure_dyn_smem(attr_once1, cdf_channel_kernel, (int)(sizeof(uint32_t) * 2 * PRIV_MAX_BINS + 2 * (PRIV_MAX_BINS + 1) * NTH_HIST)));
         launch_pdl(cdf_channel_kernel, dim3((unsigned)c), dim3(NT_CH), smem, st, target, source, out, n_t, n_s,
                    (const uint32_t *)minmax, bins, t_vec, s_vec, o_vec, tables);
         OPTEX_LAUNCH_CHECK("cdf_channel_kernel");
@@ -592,12 +588,8 @@ int cdf_match_core(const float *target, const float *source, float *out, int c, 
         OPTEX_TRY(fill_u32(hist, 2 * (int64_t)c * bins, 0u, st));
     if (priv) {
         size_t smem = sizeof(uint32_t) * (size_t)bins + (size_t)(bins + 1) * NTH_HIST;
-        static bool attr_done = false;
-        if (!attr_done) {
-            OPTEX_CUDA(cudaFuncSetAttribute(cdf_hist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)(sizeof(uint32_t) * PRIV_MAX_BINS + (PRIV_MAX_BINS + 1) * NTH_HIST)));
-            attr_done = true;
-        }
+        static PerDeviceOnce attr_once2;
+        OPTEX_TRY(ensure_dyn_smem(attr_once2, cdf_hist_kernel<true>, (int)(sizeof(uint32_t) * PRIV_MAX_BINS + (PRIV_MAX_BINS + 1) * NTH_HIST)));
         launch_pdl(cdf_hist_kernel<true>, grid_h, dim3(NTH_HIST), smem, st, target, source, n_t, n_s,
                    (const uint32_t *)minmax, hist, bins, t_vec, s_vec);
     } else {

@@ -36,6 +36,24 @@ int sm_count();
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) attribute: set it once per DEVICE and
+// kernel, not once per process (one process may drive several GPUs).  `done` is a per-call-site flag array.
+struct PerDeviceOnce {
+    unsigned char done[64] = {};
+};
+template <typename K>
+inline int ensure_dyn_smem(PerDeviceOnce &once, K kern, int bytes) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+    if (dev < 0 || dev >= 64) dev = 63;
+    if (once.done[dev] && dev != 63) return OPTEX_OK;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+    once.done[dev] = 1;
+    return OPTEX_OK;
+}
+
 // Bump allocator over the caller's workspace.
 struct Arena {
     char *base;

@@ -23,6 +23,7 @@
 
 #include <cstdlib>
 #include <mutex>
+#include <vector>
 
 #include "gemm_tc.cuh"
 
@@ -50,6 +51,15 @@ constexpr int SMEM_BUDGET = 227 * 1024 - 4096;  // tiles; + 1 KB alignment slack
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ float lds_f32(uint32_t saddr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void lds_v4(uint32_t saddr, float &a, float &b, float &c, float &d) {
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "r"(saddr) : "memory");
+}
 
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred = 0;
@@ -508,31 +518,30 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                     const bool tr = p.trace && blockIdx.x == 0 && tile == (int)blockIdx.x && kb < 16 && ct == 0;
                     mbar_wait(&raw_bar[sa], pha);
                     if (tr) p.trace[kb * 4 + 1] = clock64();
-                    const uint8_t *raw = a_ring + (size_t)sa * A_TILE;
+                    // Order matters (root cause of the round-1 "isolated 32-row groups" corruption): the raw slot used
+                    // to be handed back right after the loads were ISSUED - the loads were generic LD.E (the ring pointer
+                    // is derived through an integer cast) and ptxas put no scoreboard wait in front of the mbarrier
+                    // arrive, so the producer's next TMA could land in the slot while the loads were still in flight.
+                    // Now: explicit ld.shared, and the slot is released only after the values have been consumed by the
+                    // tcgen05.st below (tcgen05.wait::st retires them).
+                    mbar_wait(&ta_empty_bar[sta], phta ^ 1);
+                    tc_fence_after();
+                    const uint32_t raw = smem_u32(a_ring) + (uint32_t)sa * A_TILE;
                     float v[BK];
                     if (A_MN) {
                         // [mn block q][k][32 mn]: 128-byte k rows, 32-byte chunks XOR-ed with (k & 3)
-                        const uint8_t *blk = raw + (size_t)q * (BK * 128);
+                        const uint32_t blk = raw + (uint32_t)q * (BK * 128);
 #pragma unroll
                         for (int k = 0; k < BK; ++k)
-                            v[k] = *reinterpret_cast<const float *>(blk + k * 128 + ((((lane >> 3) ^ (k & 3)) << 5) |
-                                                                                 ((lane & 7) << 2)));
+                            v[k] = lds_f32(blk + k * 128 + ((((lane >> 3) ^ (k & 3)) << 5) | ((lane & 7) << 2)));
                     } else {
                         // [row][BK k]: 16-byte chunks XOR-ed with the row index inside the 8-row swizzle atom
-                        const uint8_t *rowp = raw + (size_t)r * (BK * 4);
+                        const uint32_t rowp = raw + (uint32_t)r * (BK * 4);
                         const int sw = BK == 32 ? (r & 7) : ((r >> 1) & 3);
 #pragma unroll
-                        for (int c = 0; c < BK / 4; ++c) {
-                            const float4 t = *reinterpret_cast<const float4 *>(rowp + ((c ^ sw) << 4));
-                            v[c * 4 + 0] = t.x; v[c * 4 + 1] = t.y; v[c * 4 + 2] = t.z; v[c * 4 + 3] = t.w;
-                        }
+                        for (int c = 0; c < BK / 4; ++c)
+                            lds_v4(rowp + ((c ^ sw) << 4), v[c * 4 + 0], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]);
                     }
-                    // the values are in registers: hand the raw slot back to the producer
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&afree_bar[sa]);
-                    if (++sa == p.stages_a) { sa = 0; pha ^= 1; }
-                    mbar_wait(&ta_empty_bar[sta], phta ^ 1);
-                    tc_fence_after();
                     const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(A_TMEM_COL0 + sta * 2 * BK);
 #pragma unroll
                     for (int h = 0; h < BK / 16; ++h) {
@@ -550,7 +559,11 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                     tmem_wait_st();
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&ta_full_bar[sta]);
+                    if (lane == 0) {
+                        mbar_arrive(&afree_bar[sa]);   // every value of the slot has been read AND used
+                        mbar_arrive(&ta_full_bar[sta]);
+                    }
+                    if (++sa == p.stages_a) { sa = 0; pha ^= 1; }
                     if (tr) p.trace[kb * 4 + 2] = clock64();
                     if (++sta == A_TMEM_STAGES) { sta = 0; phta ^= 1; }
                 }
@@ -828,13 +841,17 @@ int make_map_mnmajor(CUtensorMap *map, const float *base, int64_t K, int64_t MN,
     return OPTEX_OK;
 }
 
-// grow-only device scratch for the hi/lo halves (one per device; calls are stream-ordered on the caller's stream,
-// concurrent use from several streams of one device is not supported)
+// grow-only device scratch for the hi/lo halves, one buffer per (device, stream, slot): work enqueued on two streams
+// never shares scratch (every C-ABI entry takes the stream, and the Python workspace is per stream as well); the slot
+// separates the two pipelines of optex_ot_step_host_async when they are given the same stream.
 struct Scratch {
-    void *buf = nullptr;
-    size_t cap = 0;
+    int dev;
+    cudaStream_t st;
+    int slot;
+    void *buf;
+    size_t cap;
 };
-Scratch g_scratch[64][2];  // [device][slot]: two independent pipelines (optex_ot_step_host_async) may be in flight
+std::vector<Scratch> g_scratch;
 std::mutex g_scratch_mu;
 thread_local int g_scratch_slot = 0;
 struct Presplit {
@@ -842,23 +859,28 @@ struct Presplit {
 };
 thread_local Presplit g_presplit = {nullptr, nullptr, nullptr};
 
-int scratch(size_t bytes, float **out) {
+int scratch(size_t bytes, cudaStream_t st, float **out) {
     int dev = 0;
     OPTEX_CUDA(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64) dev = 63;
     std::lock_guard<std::mutex> lock(g_scratch_mu);
-    Scratch &s = g_scratch[dev][g_scratch_slot & 1];
-    if (s.cap < bytes) {
-        if (s.buf) {
-            OPTEX_CUDA(cudaDeviceSynchronize());
-            OPTEX_CUDA(cudaFree(s.buf));
-            s.buf = nullptr;
-            s.cap = 0;
-        }
-        OPTEX_CUDA(cudaMalloc(&s.buf, bytes));
-        s.cap = bytes;
+    Scratch *s = nullptr;
+    for (auto &e : g_scratch)
+        if (e.dev == dev && e.st == st && e.slot == g_scratch_slot) s = &e;
+    if (!s) {
+        g_scratch.push_back(Scratch{dev, st, g_scratch_slot, nullptr, 0});
+        s = &g_scratch.back();
     }
-    *out = (float *)s.buf;
+    if (s->cap < bytes) {
+        if (s->buf) {
+            OPTEX_CUDA(cudaStreamSynchronize(st));  // only this stream's work can still be reading the old buffer
+            OPTEX_CUDA(cudaFree(s->buf));
+            s->buf = nullptr;
+            s->cap = 0;
+        }
+        OPTEX_CUDA(cudaMalloc(&s->buf, bytes));
+        s->cap = bytes;
+    }
+    *out = (float *)s->buf;
     return OPTEX_OK;
 }
 
@@ -894,11 +916,8 @@ int launch(const CUtensorMap &ah, const CUtensorMap &al, const CUtensorMap &bh, 
         smem = (size_t)stages * stage_bytes + 1024;
     }
     auto kern = rotate_gemm_kernel<BLOCK_N, A_MN, B_MN, D_TRANS, BK>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        OPTEX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + 1024));
-        attr_done = true;
-    }
+    static PerDeviceOnce attr_once1;
+    OPTEX_TRY(ensure_dyn_smem(attr_once1, kern, (int)(SMEM_BUDGET + 1024)));
     const int64_t num_tiles = ((p.M + BLOCK_M - 1) / BLOCK_M) * ((p.N + BLOCK_N - 1) / BLOCK_N) * nz;
     const int sms = sm_count();
     dim3 grid((unsigned)(num_tiles < sms ? num_tiles : sms));  // persistent: one CTA per SM walks the tile list
@@ -937,7 +956,7 @@ inline int pick_block_n(int64_t M, int64_t N, int nz) {
 unsigned long long *g_trace = nullptr;
 void gemm_tc_set_trace(unsigned long long *t) { g_trace = t; }
 
-void gemm_tc_set_scratch_slot(int slot) { g_scratch_slot = slot & 1; }
+void gemm_tc_set_scratch_slot(int slot) { g_scratch_slot = slot & 3; }
 
 void gemm_tc_set_presplit(const float *src, const float *hi, const float *lo) { g_presplit = {src, hi, lo}; }
 
@@ -1046,7 +1065,7 @@ int gemm_tc(const TcGemm &g, cudaStream_t st) {
             bl_p = g_presplit.lo;
         } else if (!conv_b) {
             float *buf;
-            OPTEX_TRY(scratch(2 * nb * sizeof(float), &buf));
+            OPTEX_TRY(scratch(2 * nb * sizeof(float), st, &buf));
             float *b_hi = buf, *b_lo = b_hi + nb;
             OPTEX_TRY(split(g.B, b_hi, b_lo, (int64_t)nb, st));
             bh_p = b_hi; bl_p = b_lo;
@@ -1079,13 +1098,13 @@ int gemm_tc(const TcGemm &g, cudaStream_t st) {
     p.alpha = g.alpha; p.skip = g.skip; p.conv_a = p.terms == 3 ? 1 : 0; p.conv_b = conv_b ? 1 : 0;
     static const char *no_atmem = getenv("OPTEX_NO_A_TMEM");
     p.a_tmem = (p.conv_a && !p.conv_b && !(no_atmem && atoi(no_atmem))) ? 1 : 0;
-    // KNOWN ISSUE (scripts/debug_gemm_multi.py): with 64-wide N tiles the TMEM-A form corrupts isolated
-    // 32-row groups of a CTA's second and later tiles (timing dependent; 128- and 256-wide tiles and single-tile
-    // CTAs are clean).  Until the cause is found those launches take the shared-memory converters, which alternate
-    // two accumulators and are verified on the same shapes.
+    // Round 1 routed 64-wide multi-tile launches away from the TMEM-A form because of a timing-dependent corruption;
+    // the cause was the early release of the raw-A slot in the converters (see there).  OPTEX_ATMEM64=0 restores the
+    // old routing for A/B comparisons (scripts/debug_gemm_multi.py).
     {
+        static const char *atmem64 = getenv("OPTEX_ATMEM64");
         const int64_t tiles = ((g.M + BLOCK_M - 1) / BLOCK_M) * ((g.N + bn - 1) / bn) * nz;
-        if (p.a_tmem && bn == 64 && tiles > sm_count()) p.a_tmem = 0;
+        if (p.a_tmem && bn == 64 && tiles > sm_count() && atmem64 && atoi(atmem64) == 0) p.a_tmem = 0;
     }
     p.nz = nz;
     p.colrange = g.d_trans ? g.colrange : nullptr;

@@ -311,11 +311,8 @@ rot_apply_kernel(const T *__restrict__ V, const T *__restrict__ G, const double 
 template <typename T, int PL, int RW>
 int launch_rot_apply(const T *V, const T *G, const double *D, float *R, int c, int batch, cudaStream_t st) {
     auto kern = rot_apply_kernel<T, PL, RW>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        OPTEX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RotCfg<T, PL>::SMEM));
-        attr_done = true;
-    }
+    static PerDeviceOnce attr_once1;
+    OPTEX_TRY(ensure_dyn_smem(attr_once1, kern, (int)RotCfg<T, PL>::SMEM));
     dim3 g((unsigned)((c + 4 * RW - 1) / (4 * RW)), (unsigned)batch);
     kern<<<g, 128, RotCfg<T, PL>::SMEM, st>>>(V, G, D, R, c);
     return OPTEX_OK;

@@ -207,12 +207,8 @@ sort_target_kernel(const float *target, const float *__restrict__ sorted_source,
 template <int LOG_E>
 int launch_source_sort(float *s_sorted, int c, int64_t n_s, cudaStream_t st) {
     constexpr size_t smem_s = radix_smem_bytes<LOG_E, false>();
-    static bool attr_done = false;
-    if (!attr_done) {
-        OPTEX_CUDA(cudaFuncSetAttribute(sort_source_kernel<LOG_E>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem_s));
-        attr_done = true;
-    }
+    static PerDeviceOnce attr_once1;
+        OPTEX_TRY(ensure_dyn_smem(attr_once1, sort_source_kernel<LOG_E>, (int)smem_s));
     launch_pdl(sort_source_kernel<LOG_E>, dim3((unsigned)c), dim3(NT), smem_s, st, s_sorted, n_s);
     OPTEX_LAUNCH_CHECK("sort_source_kernel");
     return OPTEX_OK;
@@ -221,12 +217,8 @@ template <int LOG_E>
 int launch_target_sort(const float *t, const float *s_sorted, float *out, int c, int64_t n_t, int64_t n_s,
                        int32_t *perm, cudaStream_t st) {
     constexpr size_t smem_t = radix_smem_bytes<LOG_E, true>();
-    static bool attr_done = false;
-    if (!attr_done) {
-        OPTEX_CUDA(cudaFuncSetAttribute(sort_target_kernel<LOG_E>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem_t));
-        attr_done = true;
-    }
+    static PerDeviceOnce attr_once2;
+        OPTEX_TRY(ensure_dyn_smem(attr_once2, sort_target_kernel<LOG_E>, (int)smem_t));
     launch_pdl(sort_target_kernel<LOG_E>, dim3((unsigned)c), dim3(NT), smem_t, st, t, (const float *)s_sorted, out, n_t, n_s,
                perm);
     OPTEX_LAUNCH_CHECK("sort_target_kernel");
@@ -354,14 +346,10 @@ int large_sort(const float *src, int c, int64_t n, uint32_t *Ka, uint32_t *Ia, u
                uint32_t **Kres, uint32_t **Ires, cudaStream_t st) {
     constexpr size_t smem_c = radix_smem_bytes<MAX_LOG_E, true>();
     constexpr size_t smem_m = sizeof(uint32_t) * 4 * TM;
-    static bool attr_done = false;
-    if (!attr_done) {
-        OPTEX_CUDA(cudaFuncSetAttribute(sort_chunks_kernel<PAYLOAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem_c));
-        OPTEX_CUDA(cudaFuncSetAttribute(merge_pass_kernel<PAYLOAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem_m));
-        attr_done = true;
-    }
+    static PerDeviceOnce attr_once3;
+        OPTEX_TRY(ensure_dyn_smem(attr_once3, sort_chunks_kernel<PAYLOAD>, (int)smem_c));
+        static PerDeviceOnce attr_once4;
+        OPTEX_TRY(ensure_dyn_smem(attr_once4, merge_pass_kernel<PAYLOAD>, (int)smem_m));
     const int64_t chunks = (n + CHUNK - 1) / CHUNK;
     if (chunks > 0x7fffffffLL || c > 65535) {
         set_error("optex_sort_match: problem too large for the grid");

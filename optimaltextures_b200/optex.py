@@ -216,19 +216,38 @@ def random_rotations(N: int, count: int, device="cuda", seed: Optional[int] = No
     return out
 
 
+def set_host_style(style, stream=None) -> None:
+    """Upload the (constant) style block once and keep it resident for `optimal_transport_host(style=None)`:
+    optex.py:112-113 hands the same style_features[l] to every iteration of a layer.  style=None releases it."""
+    st = C.c_void_p((stream or torch.cuda.current_stream()).cuda_stream)
+    if style is None:
+        call("optex_ot_host_set_style", None, 0, 0, 0, st)
+        return
+    if style.is_cuda or style.dtype != torch.float32 or not style.is_contiguous():
+        raise ValueError("set_host_style takes a contiguous fp32 CPU tensor")
+    bs, hws, c = _nhwc_dims(style)
+    call("optex_ot_host_set_style", ptr(style), bs, hws, c, st)
+
+
 def optimal_transport_host(pastiche, style, rotation, hist_mode: str, content=None, content_strength: float = 0.0,
                            eps: float = 1.0, out=None, seed: Optional[int] = None, counter: int = 0,
-                           slot: Optional[int] = None, stream=None):
+                           slot: Optional[int] = None, stream=None, style_shape=None):
     """The same step through the HOST-buffer entry point (`optex_ot_step_host`): CPU tensors in,
     CPU tensor out, H2D/D2H inside the call.  This is what a non-torch caller of the C-ABI gets.
     rotation=None draws the rotation on the device from (seed, counter), like the reference draws its own.
-    slot=0/1 + stream=: the asynchronous, double-buffered form (`optex_ot_step_host_async`) for pipelining
-    independent steps - step i+1 uploads while step i computes / downloads."""
+    style=None reuses the block made resident by `set_host_style` (pass its `style_shape`).
+    slot=0/1/2 + stream=: the asynchronous, multi-buffered form (`optex_ot_step_host_async`) for pipelining
+    independent steps - step i+1 uploads while step i computes and step i-1 downloads."""
     for t in (pastiche, style, rotation, content):
         if t is not None and (t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous()):
             raise ValueError("optimal_transport_host takes contiguous fp32 CPU tensors")
     b, hw, c = _nhwc_dims(pastiche)
-    bs, hws, _ = _nhwc_dims(style)
+    if style is not None:
+        bs, hws, _ = _nhwc_dims(style)
+    else:
+        if style_shape is None or len(style_shape) != 4:
+            raise ValueError("style=None (resident style) needs style_shape=[b,h,w,c]")
+        bs, hws = int(style_shape[0]), int(style_shape[1]) * int(style_shape[2])
     if out is None:
         out = torch.empty_like(pastiche)
     st = C.c_void_p((stream or torch.cuda.current_stream()).cuda_stream)
