@@ -190,13 +190,16 @@ static int ot_step_impl(const float *P, const float *S, const float *R, float *o
     const bool tc3 = want_tc(forced_tc) && tc_terms() == 3 && c % 4 == 0;
     prof_mark(st);
     if (tc3) {
-        OPTEX_TRY(gemm_tc_split_and_fill(R, r_hi, r_lo, (int64_t)c * c, mode == OPTEX_MODE_CDF ? (uint32_t *)mw : nullptr,
-                                         mode == OPTEX_MODE_CDF ? 2 * (int64_t)c : 0, 0xffffffffu, st));
+        const bool fold = mode == OPTEX_MODE_CDF && !cdf_uses_channel_kernel(c, n_p, n_s, 256);
+        OPTEX_TRY(gemm_tc_split_and_fill(R, r_hi, r_lo, (int64_t)c * c, fold ? (uint32_t *)mw : nullptr,
+                                         fold ? 2 * (int64_t)c : 0, 0xffffffffu, st));
         gemm_tc_set_presplit(R, r_hi, r_lo);
     }
     uint32_t *minmax = nullptr;
-    if (mode == OPTEX_MODE_CDF) {
-        // the forward rotations fold the per-channel range (histmatch.py:52-53) into their epilogues
+    if (mode == OPTEX_MODE_CDF && !cdf_uses_channel_kernel(c, n_p, n_s, 256)) {
+        // long rows (conv1_1 .. conv3_1): the forward rotations fold the per-channel range (histmatch.py:52-53) into
+        // their epilogues, which saves the three-kernel matcher a pass over the rotated block; short rows: the
+        // one-CTA-per-channel matcher finds the range itself
         minmax = (uint32_t *)mw;
         if (!tc3) OPTEX_TRY(fill_u32(minmax, 2 * (int64_t)c, 0xffffffffu, st));
     }
@@ -532,7 +535,8 @@ static int ot_loop_fused(float *feat, const float *S, const float *R_all, int it
     void *mw = ar.take<char>(mws);
     uint32_t *minmax = (uint32_t *)mw;
     float *Q = rbuf + (size_t)(kRotChunk + 1) * c * c;
-    const bool cdf = mode == OPTEX_MODE_CDF;
+    const bool cdf = mode == OPTEX_MODE_CDF && !cdf_uses_channel_kernel(c, n_p, n_s, 256);   // fold the range in the GEMMs
+    const bool is_cdf = mode == OPTEX_MODE_CDF;
     const int terms = tc_terms();
     float *cur = rp, *nxt = alt;
     const float *R = nullptr;
@@ -570,8 +574,8 @@ static int ot_loop_fused(float *feat, const float *S, const float *R_all, int it
             r1 = true;
         }
         OPTEX_TRY(rotate_forward(S, R, rs, n_s, c, true, st, 0, -1, cdf ? minmax : nullptr, &r2));
-        if (cdf)
-            OPTEX_TRY(cdf_match_core(cur, rs, cur, c, n_p, n_s, 256, nullptr, mw, mws, r1 && r2, st));
+        if (is_cdf)
+            OPTEX_TRY(cdf_match_core(cur, rs, cur, c, n_p, n_s, 256, nullptr, mw, mws, cdf && r1 && r2, st));
         else
             OPTEX_TRY(sort_match_inplace(cur, rs, cur, c, n_p, n_s, nullptr, mw, mws, st));
     }

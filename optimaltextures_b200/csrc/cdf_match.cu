@@ -453,7 +453,7 @@ constexpr int NT_CH = 2 * NTH_HIST;
 __global__ void __launch_bounds__(NT_CH, 4)
 cdf_channel_kernel(const float *t, const float *__restrict__ s, float *out, int64_t n_t, int64_t n_s,
                    const uint32_t *__restrict__ minmax, int bins, int t_vec, int s_vec, int o_vec,
-                   float *__restrict__ tables_out) {
+                   float *__restrict__ tables_out, int need_range) {
     pdl_wait();
     extern __shared__ uint32_t smem_u32[];
     uint32_t *acc = smem_u32;                              // [2][bins]: target, source counts
@@ -461,8 +461,28 @@ cdf_channel_kernel(const float *t, const float *__restrict__ s, float *out, int6
     const int priv_words = (bins + 1) * (NTH_HIST / 4);
     const int ch = blockIdx.x;
     for (int i = threadIdx.x; i < 2 * bins; i += NT_CH) acc[i] = 0u;
-    __syncthreads();
-    const float lo = range_lo(minmax, ch), hi = range_hi(minmax, ch);
+    float lo, hi;
+    if (need_range) {
+        // histmatch.py:52-53 in this CTA: the channel's two rows are read three times here anyway (range, histogram,
+        // apply) and stay in L1 / L2 - cheaper than the REDUX + atomic fold in the epilogue of the rotation GEMMs
+        // (measured: 11 us per forward rotation at the headline shape against ~3 us here)
+        __shared__ float s_mn[NT_CH / 32], s_mx[NT_CH / 32];
+        float mn = INFINITY, mx = -INFINITY;
+        auto upd = [&](float x) { mn = fminf(mn, x); mx = fmaxf(mx, x); };
+        for_each<NT_CH>(t + (int64_t)ch * n_t, 0, n_t, t_vec != 0, upd);
+        for_each<NT_CH>(s + (int64_t)ch * n_s, 0, n_s, s_vec != 0, upd);
+        mn = warp_min(mn);
+        mx = warp_max(mx);
+        if ((threadIdx.x & 31) == 0) { s_mn[threadIdx.x >> 5] = mn; s_mx[threadIdx.x >> 5] = mx; }
+        __syncthreads();
+        mn = s_mn[0]; mx = s_mx[0];
+#pragma unroll
+        for (int w = 1; w < NT_CH / 32; ++w) { mn = fminf(mn, s_mn[w]); mx = fmaxf(mx, s_mx[w]); }
+        lo = mn; hi = mx;
+    } else {
+        __syncthreads();
+        lo = range_lo(minmax, ch); hi = range_hi(minmax, ch);
+    }
     {
         HistRange hr(lo, hi, bins);
         const int g = threadIdx.x >= NTH_HIST ? 1 : 0, tid = threadIdx.x - g * NTH_HIST;
@@ -502,6 +522,14 @@ __global__ void interp_kernel(const float *__restrict__ x, const float *__restri
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace
+
+// the (c, n) regime of cdf_channel_kernel: the whole matcher of a channel, its range included, in one CTA
+bool cdf_uses_channel_kernel(int c, int64_t n_t, int64_t n_s, int bins) {
+    static const char *no_fused = getenv("OPTEX_NO_CDF_FUSED");
+    const int64_t n_big = n_t > n_s ? n_t : n_s;
+    const bool priv = (bins % 4 == 0) && bins <= PRIV_MAX_BINS;
+    return priv && n_big <= 32768 && c >= 2 * sm_count() && !(no_fused && atoi(no_fused));
+}
 
 int cdf_splits(int c, int64_t n) {
     // enough CTAs for ~4 resident blocks on each of the SMs, at least 8K elements per CTA
@@ -563,23 +591,22 @@ int cdf_match_core(const float *target, const float *source, float *out, int c, 
     const int s_vec = aligned16(source) && (n_s % 4 == 0);
     const int o_vec = t_vec && aligned16(out);
     const int64_t n_big = n_t > n_s ? n_t : n_s;
+    const bool priv = (bins % 4 == 0) && bins <= PRIV_MAX_BINS;
+    // many channels, short rows: one CTA per channel does the whole match (see cdf_channel_kernel), range included
+    if (cdf_uses_channel_kernel(c, n_t, n_s, bins)) {
+        const size_t smem = sizeof(uint32_t) * 2 * (size_t)bins + 2 * (size_t)(bins + 1) * NTH_HIST;
+        static PerDeviceOnce attr_once1;
+        OPTEX_TRY(ensure_dyn_smem(attr_once1, cdf_channel_kernel, (int)(sizeof(uint32_t) * 2 * PRIV_MAX_BINS + 2 * (PRIV_MAX_BINS + 1) * NTH_HIST)));
+        launch_pdl(cdf_channel_kernel, dim3((unsigned)c), dim3(NT_CH), smem, st, target, source, out, n_t, n_s,
+                   (const uint32_t *)minmax, bins, t_vec, s_vec, o_vec, tables, have_range ? 0 : 1);
+        OPTEX_LAUNCH_CHECK("cdf_channel_kernel");
+        return OPTEX_OK;
+    }
     if (!have_range) {
         OPTEX_TRY(fill_u32(minmax, 2 * (int64_t)c, 0xffffffffu, st));
         dim3 grid((unsigned)cdf_splits(c, n_big), (unsigned)c);
         launch_pdl(cdf_range_kernel, grid, dim3(NT), 0, st, target, source, n_t, n_s, minmax, t_vec, s_vec);
         OPTEX_LAUNCH_CHECK("cdf_range_kernel");
-    }
-    const bool priv = (bins % 4 == 0) && bins <= PRIV_MAX_BINS;
-    // many channels, short rows: one CTA per channel does the whole match (see cdf_channel_kernel)
-    static const char *no_fused = getenv("OPTEX_NO_CDF_FUSED");
-    if (priv && n_big <= 32768 && c >= 2 * sm_count() && !(no_fused && atoi(no_fused))) {
-        const size_t smem = sizeof(uint32_t) * 2 * (size_t)bins + 2 * (size_t)(bins + 1) * NTH_HIST;
-        static PerDeviceOnce attr_once1;
-        OPTEX_TRY(ensure_dyn_smem(attr_once1, cdf_channel_kernel, (int)(sizeof(uint32_t) * 2 * PRIV_MAX_BINS + 2 * (PRIV_MAX_BINS + 1) * NTH_HIST)));
-        launch_pdl(cdf_channel_kernel, dim3((unsigned)c), dim3(NT_CH), smem, st, target, source, out, n_t, n_s,
-                   (const uint32_t *)minmax, bins, t_vec, s_vec, o_vec, tables);
-        OPTEX_LAUNCH_CHECK("cdf_channel_kernel");
-        return OPTEX_OK;
     }
     // histogram grid: one CTA per channel and array unless that leaves SMs idle and the slices stay long
     int64_t hs = (2LL * sm_count() + c - 1) / c, hcap = (n_big + 32767) / 32768;

@@ -165,6 +165,7 @@ int random_rotations(float *R, int c, int batch, uint64_t seed, uint64_t first_c
 // cdf_match.cu: workspace = [minmax: 2c u32][hist][tables]; have_range: the forward GEMMs already folded the
 // per-channel range into minmax (which the caller initialised to 0xFF bytes)
 size_t cdf_minmax_bytes(int c);
+bool cdf_uses_channel_kernel(int c, int64_t n_t, int64_t n_s, int bins);  // that kernel computes the range itself
 int fill_u32(uint32_t *p, int64_t n, uint32_t v, cudaStream_t st);
 int cdf_match_core(const float *target, const float *source, float *out, int c, int64_t n_t, int64_t n_s, int bins,
                    float *tables, void *workspace, size_t workspace_bytes, bool have_range, cudaStream_t st);

@@ -47,7 +47,8 @@ constexpr int NTHREADS = EPI_WARP0 * 32 + EPI_GROUPS * 128;
 // the A tile live in a ring of TMEM stages behind it (32 + 32 columns per stage)
 constexpr int A_TMEM_COL0 = 256;
 constexpr int A_TMEM_STAGES = 4;
-constexpr int SMEM_BUDGET = 227 * 1024 - 4096;  // tiles; + 1 KB alignment slack + ~1 KB static (barriers)
+constexpr int SMEM_BUDGET = 224 * 1024;  // tiles; + 1 KB alignment slack + 1 KB static (barriers) = 226 of 227 KB
+constexpr int EPI_STAGE_BYTES = 128 * 32 * 4;  // TMA-store epilogue: one 128 x 32 fp32 staging tile per epilogue group
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -162,6 +163,86 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[3
           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr));
 }
+// ---- 2-CTA (cta_group::2) forms: a pair of CTAs (cluster of 2) works on one 256-row tile; each CTA loads HALF of the
+// B tile and the tensor cores of both SMs read both halves, so the L2 -> SM traffic per MMA halves
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// shared::cluster address of the same variable in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// (default semantics, release at CTA scope - what CUTLASS's ClusterBarrier::arrive(cta_id) uses: a release at CLUSTER
+// scope costs a membar + L1 invalidate per arrive and measured 1000-2000 clk per k block in the converter warps; no
+// generic-proxy data crosses the pair here, the TMEM hand-off is ordered by the tcgen05 fences)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
+    uint32_t done = 0;
+    const uint32_t addr = smem_u32(bar);
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred P;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, P;\n\t}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    }
+}
+// TMA load whose completion is signalled on a barrier of EITHER CTA of the pair (bar_cluster: shared::cluster address)
+__device__ __forceinline__ void tma_load_2d_cg2(const CUtensorMap *map, uint32_t bar_cluster, void *dst, int x, int y,
+                                                uint64_t hint) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster), "r"(x), "r"(y), "l"(hint)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_cg2(const CUtensorMap *map, uint32_t bar_cluster, void *dst, int x, int y,
+                                                int z, uint64_t hint) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster), "r"(x), "r"(y), "r"(z), "l"(hint)
+        : "memory");
+}
+// arrive on the barrier at the same shared-memory offset in BOTH CTAs of the pair once the MMAs issued so far retire
+__device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(bar)),
+        "h"((uint16_t)3)
+        : "memory");
+}
+__device__ __forceinline__ void umma_tf32_ts_cg2(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// TMA store of a staged tile (shared -> global, bulk async group), and the waits on it
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void *src, int x, int y) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+                 "r"(smem_u32(src)), "r"(x), "r"(y)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 template <int N>
 __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N>
@@ -198,13 +279,16 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
     return d;
 }
 
-// a -> (tf32(a), tf32(a - tf32(a))): round-to-nearest split, both halves exactly representable in tf32
+// a -> (tf32(a), tf32(a - tf32(a))): round-to-nearest split, both halves exactly representable in tf32.
+// tf32(x) = cvt.rna.tf32.f32 = round the magnitude to 10 mantissa bits, ties away from zero: on the bit pattern that
+// is "add half an ulp, clear the 13 low bits" (inf stays inf, FLT_MAX rounds to inf, NaN stays NaN - what the cvt
+// instruction returns as well); ptxas expands the cvt into four instructions with an explicit inf test, this is two.
+__device__ __forceinline__ float rna_tf32(float a) {
+    return __uint_as_float((__float_as_uint(a) + 0x1000u) & 0xffffe000u);
+}
 __device__ __forceinline__ void split_tf32(float a, float &h, float &l) {
-    uint32_t hb, lb;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(a));
-    h = __uint_as_float(hb);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(__fsub_rn(a, h)));
-    l = __uint_as_float(lb);
+    h = rna_tf32(a);
+    l = rna_tf32(__fsub_rn(a, h));
 }
 
 struct Params {
@@ -242,6 +326,7 @@ struct Params {
     const float *skip_z[MAX_BATCH];
     int a_tmem;           // conv_a && !conv_b: the converters write the hi / lo halves of A to TENSOR memory
     int stages_a;         // a_tmem: depth of the raw-A shared-memory ring (p.stages is the B ring then)
+    int tma_store;        // CG == 2: the epilogue stages 128 x 32 tiles in shared memory and writes them with TMA
 };
 
 // ------------------------------------------------------------------ the kernel
@@ -261,14 +346,21 @@ struct Params {
 //                         128 B/clk = 2100 clk against 1536 clk of tensor-pipe time; with A in TMEM the converters
 //                         only read (16 KB) and the MMAs only fetch B (96 KB): 192 KB = 1500 clk.
 // BK = K elements per pipeline stage: 32 (128-byte swizzle rows) or 16 (64-byte rows, half-size stages).
-template <int BLOCK_N, bool A_MN, bool B_MN, bool D_TRANS, int BK>
+// CG == 2 (a_tmem launches only): clusters of two CTAs share one 256 x BLOCK_N tile.  CTA r of the pair owns rows
+// [m0 + 128 r, +128): it streams and converts its own A rows into its own tensor memory and loads the B columns
+// [n0 + r BLOCK_N / 2, + BLOCK_N / 2); the leader (r = 0) issues tcgen05.mma.cta_group::2 for both.  Barriers the
+// leader's MMA warp waits on (B landed, A in TMEM, accumulator drained) live in the LEADER's shared memory and
+// collect arrivals from both CTAs; barriers the MMA releases are signalled in both CTAs by a multicast commit.
+template <int BLOCK_N, bool A_MN, bool B_MN, bool D_TRANS, int BK, int CG = 1>
 __global__ void __launch_bounds__(NTHREADS, 1)
 rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-                   const Params p) {
+                   const __grid_constant__ CUtensorMap tmD, const Params p) {
     constexpr uint32_t A_TILE = BLOCK_M * BK * 4;
-    constexpr uint32_t B_TILE = BLOCK_N * BK * 4;
+    constexpr uint32_t B_TILE = (BLOCK_N / CG) * BK * 4;   // what THIS CTA loads per stage and half (hi / lo)
     static_assert(BK == 32 || BK == 16, "stage depth");
+    static_assert(CG == 1 || CG == 2, "cta_group");
+    const uint32_t crank = CG == 2 ? cluster_ctarank() : 0u;   // rank in the pair; 0 = leader (issues the MMAs)
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], raw_bar[MAX_STAGES];
     __shared__ __align__(8) uint64_t afree_bar[MAX_STAGES];                            // a_tmem: raw A slot consumed
@@ -279,6 +371,21 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[64] = clock64();
     pdl_wait();
     if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[65] = clock64();
+    // debug: trace[95] == 0x7ace asks every CTA for its own (clock64, globaltimer) at entry and exit, 4 words per CTA
+    // from trace[128] (the buffer must hold 128 + 4 * gridDim.x words)
+    const bool cta_stamps = p.trace && threadIdx.x == 0 && p.trace[95] == 0x7aceull;
+    if (cta_stamps) {
+        unsigned long long g;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+        p.trace[128 + 4 * blockIdx.x + 0] = clock64();
+        p.trace[128 + 4 * blockIdx.x + 1] = g;
+    }
+    // ... and CTA 0 stamps the waits of its producer / MMA / converter roles for its first 32 k blocks:
+    // trace[1024 + ((role * 32 + kblock) * 4 + j)]
+    const bool role_stamps = p.trace && blockIdx.x == 0 && p.trace[95] == 0x7aceull;
+    auto stamp = [&](int role, int kbi, int j) {
+        if (role_stamps && kbi < 32) p.trace[1024 + ((role * 32 + kbi) * 4 + j)] = clock64();
+    };
     if (p.skip && *p.skip) return;  // uniform over the grid
     if (p.skip_below && *p.skip_below < p.skip_tol) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -287,12 +394,13 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     // a_tmem: a stage of the main ring holds the hi / lo tiles of B only; raw A tiles have their own ring behind it
     const uint32_t stage_bytes = a_tmem ? 2 * B_TILE : nterm_tiles * (A_TILE + B_TILE);
     const int n_tiles_n = (int)((p.N + BLOCK_N - 1) / BLOCK_N);
-    const int n_tiles_m = (int)((p.M + BLOCK_M - 1) / BLOCK_M);
+    const int n_tiles_m = (int)((p.M + BLOCK_M * CG - 1) / (BLOCK_M * CG));
     const int tiles_per_z = n_tiles_m * n_tiles_n;
     const int num_tiles = tiles_per_z * p.nz;
     // 1024-byte alignment of the dynamic smem base (swizzle atoms)
     uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~uintptr_t(1023));
     uint8_t *a_ring = tiles + (size_t)p.stages * stage_bytes;
+    uint8_t *epi_stage = a_ring + (size_t)p.stages_a * A_TILE;   // tma_store: EPI_GROUPS staging tiles
     // a_tmem: ONE accumulator (the other 256 columns hold the A ring); the epilogue frees it as soon as the tile
     // sits in registers.  Otherwise two accumulators alternate.
     const uint32_t tmem_cols = a_tmem ? 512u : (uint32_t)(2 * BLOCK_N);
@@ -300,6 +408,7 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA_hi);
         prefetch_tmap(&tmB_hi);
+        if (CG == 2 && p.tma_store) prefetch_tmap(&tmD);
         if (p.terms == 3) {
             if (!p.conv_a) prefetch_tmap(&tmA_lo);
             if (!p.conv_b) prefetch_tmap(&tmB_lo);
@@ -315,25 +424,34 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                 mbar_init(&afree_bar[s], 4);
             }
             for (int s = 0; s < A_TMEM_STAGES; ++s) {
-                mbar_init(&ta_full_bar[s], 4);
+                mbar_init(&ta_full_bar[s], 4 * CG);   // one arrival per converter warp (of both CTAs of a pair)
                 mbar_init(&ta_empty_bar[s], 1);
             }
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull_bar[a], 1);   // tcgen05.commit of the tile's last MMA
-            mbar_init(&tempty_bar[a], 4 * EPI_GROUPS);  // one arrival per epilogue warp
+            mbar_init(&tempty_bar[a], 4 * EPI_GROUPS * CG);  // one arrival per epilogue warp (of both CTAs)
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                         smem_u32(&tmem_base_smem)),
-                     "r"(tmem_cols)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (CG == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                             smem_u32(&tmem_base_smem)),
+                         "r"(tmem_cols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                             smem_u32(&tmem_base_smem)),
+                         "r"(tmem_cols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();   // the peer's barriers are initialised before anything signals them
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
     if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[66] = clock64();
@@ -342,9 +460,10 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     auto tile_coords = [&](int tile, int &m0, int &n0, int &z) {
         z = tile / tiles_per_z;
         const int r = tile - z * tiles_per_z;
-        m0 = (r / n_tiles_n) * BLOCK_M;
+        m0 = (r / n_tiles_n) * (BLOCK_M * CG) + (int)crank * BLOCK_M;   // this CTA's rows of the (pair's) tile
         n0 = (r % n_tiles_n) * BLOCK_N;
     };
+    const int tile0 = (int)blockIdx.x / CG, tile_step = (int)gridDim.x / CG;   // pairs walk the tile list together
     auto k_range = [&](int z, int64_t &k_begin, int &num_kb) {
         k_begin = (int64_t)z * p.k_per_z;
         const int64_t k_len = p.k_per_z > 0 ? (p.K - k_begin < p.k_per_z ? p.K - k_begin : p.k_per_z) : p.K;
@@ -367,7 +486,7 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
             if (elect_one()) {
                 int s = 0, sa = 0;
                 uint32_t ph = 0, pha = 0;
-                for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                for (int tile = tile0; tile < num_tiles; tile += tile_step) {
                     int m0, n0, z, num_kb;
                     int64_t k_begin;
                     tile_coords(tile, m0, n0, z);
@@ -377,10 +496,13 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                     const int ao = p.batch > 0 ? p.a_off[z] : 0, bo = p.batch > 0 ? p.b_off[z] : 0;
                     for (int kb = 0; kb < num_kb; ++kb) {
                         const int k0 = (int)k_begin + kb * BK;
-                        const bool tr = p.trace && blockIdx.x == 0 && tile == (int)blockIdx.x && kb < 16;
+                        const bool tr = p.trace && blockIdx.x == 0 && tile == tile0 && kb < 16;
                         if (a_tmem) {
                             // raw A -> its own ring (freed by the converters as soon as they have read it)
+                            const int kbi = (tile - tile0) / tile_step * num_kb + kb;
+                            stamp(0, kbi, 0);
                             mbar_wait(&afree_bar[sa], pha ^ 1);
+                            stamp(0, kbi, 1);
                             if (tr) p.trace[kb * 4 + 0] = clock64();
                             uint8_t *a_dst = a_ring + (size_t)sa * A_TILE;
                             mbar_expect_tx(&raw_bar[sa], A_TILE);
@@ -388,13 +510,29 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                             else tma_load_2d(&tmA_hi, &raw_bar[sa], a_dst, k0, m0 + ao, p.a_hint);
                             if (++sa == p.stages_a) { sa = 0; pha ^= 1; }
                             // pre-split B hi / lo -> the main ring (freed by the MMAs)
+                            stamp(0, kbi, 2);
                             mbar_wait(&empty_bar[s], ph ^ 1);
+                            stamp(0, kbi, 3);
                             uint8_t *b_dst = tiles + (size_t)s * stage_bytes;
-                            mbar_expect_tx(&full_bar[s], 2 * B_TILE);
-                            for (int t = 0; t < 2; ++t) {
-                                const CUtensorMap *mb = t ? &tmB_lo : &tmB_hi;
-                                if (B_MN) tma_load_3d(mb, &full_bar[s], b_dst + t * B_TILE, 0, k0 + bo, n0 / 32, p.b_hint);
-                                else tma_load_2d(mb, &full_bar[s], b_dst + t * B_TILE, k0, n0 + bo, p.b_hint);
+                            if (CG == 2) {
+                                // this CTA's half of the B columns; completion is counted on the LEADER's barrier, which
+                                // expects the bytes of both halves (the peer's may land before the leader has armed it:
+                                // the pending arrival keeps the phase open)
+                                const uint32_t fb = mapa_u32(smem_u32(&full_bar[s]), 0);
+                                if (crank == 0) mbar_expect_tx(&full_bar[s], 2 * 2 * B_TILE);
+                                const int nb0 = n0 + (int)crank * (BLOCK_N / 2);
+                                for (int t = 0; t < 2; ++t) {
+                                    const CUtensorMap *mb = t ? &tmB_lo : &tmB_hi;
+                                    if (B_MN) tma_load_3d_cg2(mb, fb, b_dst + t * B_TILE, 0, k0 + bo, nb0 / 32, p.b_hint);
+                                    else tma_load_2d_cg2(mb, fb, b_dst + t * B_TILE, k0, nb0 + bo, p.b_hint);
+                                }
+                            } else {
+                                mbar_expect_tx(&full_bar[s], 2 * B_TILE);
+                                for (int t = 0; t < 2; ++t) {
+                                    const CUtensorMap *mb = t ? &tmB_lo : &tmB_hi;
+                                    if (B_MN) tma_load_3d(mb, &full_bar[s], b_dst + t * B_TILE, 0, k0 + bo, n0 / 32, p.b_hint);
+                                    else tma_load_2d(mb, &full_bar[s], b_dst + t * B_TILE, k0, n0 + bo, p.b_hint);
+                                }
                             }
                             if (++s == p.stages) { s = 0; ph ^= 1; }
                             continue;
@@ -424,15 +562,15 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                     }
                 }
             }
-        } else if (warp == 1) {
-            // ===== MMA issuer  (the TMEM A operand is always "K-major": lane = row, column = k)
+        } else if (warp == 1 && crank == 0) {
+            // ===== MMA issuer  (the TMEM A operand is always "K-major": lane = row, column = k); pairs: leader only
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (((A_MN && !a_tmem) ? 1u : 0u) << 15) |
                                    ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BLOCK_N >> 3) << 17) |
-                                   ((uint32_t)(BLOCK_M >> 4) << 24);
+                                   ((uint32_t)((BLOCK_M * CG) >> 4) << 24);
             int s = 0, sta = 0;
             uint32_t ph = 0, phta = 0;
             int titer = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = tile0; tile < num_tiles; tile += tile_step) {
                 int m0, n0, z, num_kb, acc;
                 int64_t k_begin;
                 uint32_t aph;
@@ -440,15 +578,26 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                 k_range(z, k_begin, num_kb);
                 if (z_skipped(z)) continue;
                 acc_of(titer++, acc, aph);
-                mbar_wait(&tempty_bar[acc], aph ^ 1);  // the epilogue has drained this accumulator
+                if (CG == 2) mbar_wait_cluster(&tempty_bar[acc], aph ^ 1);
+                else mbar_wait(&tempty_bar[acc], aph ^ 1);  // the epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(&full_bar[s], ph);
-                    if (a_tmem) mbar_wait(&ta_full_bar[sta], phta);
+                    const int kbi = (titer - 1) * num_kb + kb;
+                    if (lane == 0) stamp(1, kbi, 0);
+                    if (CG == 2) {
+                        mbar_wait_cluster(&full_bar[s], ph);
+                        if (lane == 0) stamp(1, kbi, 1);
+                        mbar_wait_cluster(&ta_full_bar[sta], phta);
+                    } else {
+                        mbar_wait(&full_bar[s], ph);
+                        if (lane == 0) stamp(1, kbi, 1);
+                        if (a_tmem) mbar_wait(&ta_full_bar[sta], phta);
+                    }
+                    if (lane == 0) stamp(1, kbi, 2);
                     tc_fence_after();
-                    if (p.trace && blockIdx.x == 0 && tile == (int)blockIdx.x && kb < 16 && lane == 0) p.trace[kb * 4 + 3] = clock64();
-                    if (p.trace && blockIdx.x == 0 && tile != (int)blockIdx.x && (kb == 0 || kb == num_kb - 1) && lane == 0) p.trace[76 + (kb ? 1 : 0)] = clock64();
+                    if (p.trace && blockIdx.x == 0 && tile == tile0 && kb < 16 && lane == 0) p.trace[kb * 4 + 3] = clock64();
+                    if (p.trace && blockIdx.x == 0 && tile != tile0 && (kb == 0 || kb == num_kb - 1) && lane == 0) p.trace[76 + (kb ? 1 : 0)] = clock64();
                     if (elect_one()) {
                         const uint32_t st = smem_u32(tiles + (size_t)s * stage_bytes);
                         // MN-major: 32-wide mn blocks of BK k-rows x 128 B (LBO), 4-row BASE32B atoms (SBO 512 B)
@@ -465,11 +614,18 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                                 const uint32_t b_off = B_MN ? kk * 1024u : kk * 32u;
                                 const uint64_t db = make_desc(b_hi + b_off, b_lbo, b_sbo, b_lt);
                                 const uint64_t dbl = make_desc(b_lo + b_off, b_lbo, b_sbo, b_lt);
-                                umma_tf32_ts(tmem_d, ta_hi + kk * UMMA_K, db, idesc, (kb | kk) != 0);
-                                umma_tf32_ts(tmem_d, ta_hi + kk * UMMA_K, dbl, idesc, 1u);
-                                umma_tf32_ts(tmem_d, ta_lo + kk * UMMA_K, db, idesc, 1u);
+                                if (CG == 2) {
+                                    umma_tf32_ts_cg2(tmem_d, ta_hi + kk * UMMA_K, db, idesc, (kb | kk) != 0);
+                                    umma_tf32_ts_cg2(tmem_d, ta_hi + kk * UMMA_K, dbl, idesc, 1u);
+                                    umma_tf32_ts_cg2(tmem_d, ta_lo + kk * UMMA_K, db, idesc, 1u);
+                                } else {
+                                    umma_tf32_ts(tmem_d, ta_hi + kk * UMMA_K, db, idesc, (kb | kk) != 0);
+                                    umma_tf32_ts(tmem_d, ta_hi + kk * UMMA_K, dbl, idesc, 1u);
+                                    umma_tf32_ts(tmem_d, ta_lo + kk * UMMA_K, db, idesc, 1u);
+                                }
                             }
-                            umma_commit(&ta_empty_bar[sta]);  // TMEM A stage free once these MMAs retire
+                            if (CG == 2) umma_commit_pair(&ta_empty_bar[sta]);
+                            else umma_commit(&ta_empty_bar[sta]);  // TMEM A stage free once these MMAs retire
                         } else {
                             const uint32_t a_hi = st, a_lo = st + A_TILE;
                             const uint32_t b_hi = st + nterm_tiles * A_TILE, b_lo = b_hi + B_TILE;
@@ -489,10 +645,16 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                                 }
                             }
                         }
-                        umma_commit(&empty_bar[s]);                          // smem stage free once these MMAs retire
-                        if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete
+                        if (CG == 2) {
+                            umma_commit_pair(&empty_bar[s]);
+                            if (kb == num_kb - 1) umma_commit_pair(&tfull_bar[acc]);
+                        } else {
+                            umma_commit(&empty_bar[s]);                          // smem stage free once these MMAs retire
+                            if (kb == num_kb - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete
+                        }
                     }
                     __syncwarp();
+                    if (lane == 0) stamp(1, kbi, 3);
                     if (++s == p.stages) { s = 0; ph ^= 1; }
                     if (a_tmem && ++sta == A_TMEM_STAGES) { sta = 0; phta ^= 1; }
                 }
@@ -508,15 +670,18 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
             const int r = q * 32 + lane;
             int sa = 0, sta = 0;
             uint32_t pha = 0, phta = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = tile0; tile < num_tiles; tile += tile_step) {
                 int m0, n0, z, num_kb;
                 int64_t k_begin;
                 tile_coords(tile, m0, n0, z);
                 k_range(z, k_begin, num_kb);
                 if (z_skipped(z)) continue;
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    const bool tr = p.trace && blockIdx.x == 0 && tile == (int)blockIdx.x && kb < 16 && ct == 0;
+                    const bool tr = p.trace && blockIdx.x == 0 && tile == tile0 && kb < 16 && ct == 0;
+                    const int kbi = (tile - tile0) / tile_step * num_kb + kb;
+                    if (ct == 0) stamp(2, kbi, 0);
                     mbar_wait(&raw_bar[sa], pha);
+                    if (ct == 0) stamp(2, kbi, 1);
                     if (tr) p.trace[kb * 4 + 1] = clock64();
                     // Order matters (root cause of the round-1 "isolated 32-row groups" corruption): the raw slot used
                     // to be handed back right after the loads were ISSUED - the loads were generic LD.E (the ring pointer
@@ -526,6 +691,7 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                     // tcgen05.st below (tcgen05.wait::st retires them).
                     mbar_wait(&ta_empty_bar[sta], phta ^ 1);
                     tc_fence_after();
+                    if (ct == 0) stamp(2, kbi, 2);
                     const uint32_t raw = smem_u32(a_ring) + (uint32_t)sa * A_TILE;
                     float v[BK];
                     if (A_MN) {
@@ -561,9 +727,11 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                     __syncwarp();
                     if (lane == 0) {
                         mbar_arrive(&afree_bar[sa]);   // every value of the slot has been read AND used
-                        mbar_arrive(&ta_full_bar[sta]);
+                        if (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&ta_full_bar[sta]), 0));   // the leader's
+                        else mbar_arrive(&ta_full_bar[sta]);
                     }
                     if (++sa == p.stages_a) { sa = 0; pha ^= 1; }
+                    if (ct == 0) stamp(2, kbi, 3);
                     if (tr) p.trace[kb * 4 + 2] = clock64();
                     if (++sta == A_TMEM_STAGES) { sta = 0; phta ^= 1; }
                 }
@@ -573,7 +741,7 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
             // element-wise in place (independent of the swizzle), then hand the stage to the MMA warp
             int s = 0;
             uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = tile0; tile < num_tiles; tile += tile_step) {
                 int m0, n0, z, num_kb;
                 int64_t k_begin;
                 tile_coords(tile, m0, n0, z);
@@ -581,7 +749,7 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                 if (z_skipped(z)) continue;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&raw_bar[s], ph);
-                    if (p.trace && blockIdx.x == 0 && tile == (int)blockIdx.x && kb < 16 && ct == 0) p.trace[kb * 4 + 1] = clock64();
+                    if (p.trace && blockIdx.x == 0 && tile == tile0 && kb < 16 && ct == 0) p.trace[kb * 4 + 1] = clock64();
                     float4 *hi = reinterpret_cast<float4 *>(tiles + (size_t)s * stage_bytes);
                     float4 *lo = reinterpret_cast<float4 *>(tiles + (size_t)s * stage_bytes + A_TILE);
 #pragma unroll
@@ -611,7 +779,7 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> UMMA reads
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&full_bar[s]);
-                    if (p.trace && blockIdx.x == 0 && tile == (int)blockIdx.x && kb < 16 && ct == 0) p.trace[kb * 4 + 2] = clock64();
+                    if (p.trace && blockIdx.x == 0 && tile == tile0 && kb < 16 && ct == 0) p.trace[kb * 4 + 2] = clock64();
                     if (++s == p.stages) { s = 0; ph ^= 1; }
                 }
             }
@@ -625,7 +793,7 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         constexpr int NCH = EPI_COLS / 32;
         const bool active = egrp * EPI_COLS < BLOCK_N;
         int titer = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = tile0; tile < num_tiles; tile += tile_step) {
             int m0, n0, z, acc;
             uint32_t aph;
             tile_coords(tile, m0, n0, z);
@@ -634,8 +802,10 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
             acc_of(tcur, acc, aph);
             float *const Dz = p.D + (p.batch > 0 ? p.d_off[z] : (int64_t)z * p.d_z_stride);
             float *const resid_max = p.batch > 0 ? p.resid_z[z] : p.resid_max;
+            if (warp == EPI_WARP0 && lane == 0) stamp(3, tcur, 0);
             mbar_wait(&tfull_bar[acc], aph);
             tc_fence_after();
+            if (warp == EPI_WARP0 && lane == 0) stamp(3, tcur, 1);
             if (p.trace && blockIdx.x == 0 && warp == EPI_WARP0 && lane == 0 && tcur < 4) p.trace[68 + tcur * 2] = clock64();
             // the warp's whole slice of the tile -> registers, then the accumulator goes back to the MMA warp
             uint32_t vv[NCH][32];
@@ -648,18 +818,43 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (lane == 0) {
+                if (CG == 2) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));   // the leader's
+                else mbar_arrive(&tempty_bar[acc]);
+            }
             if (p.trace && blockIdx.x == 0 && warp == EPI_WARP0 && lane == 0 && tcur < 4) p.trace[69 + tcur * 2] = clock64();
+            if (warp == EPI_WARP0 && lane == 0) stamp(3, tcur, 2);
             const int64_t row = (int64_t)m0 + q * 32 + lane;
             uint32_t rmn = 0xffffffffu, rmx = 0xffffffffu;  // this thread's row: f2ord(min), ~f2ord(max)
             float rres = 0.f;                                // max |acc - I| of this thread's part of the tile
+            // CG == 2: the tile leaves through shared memory and a TMA store.  (Direct stores of a row-per-thread
+            // fragment touch 32 different 128-byte lines per warp instruction: the NHWC epilogue of the inverse
+            // rotation took 23 k cycles per tile that way, the channel-major one 8 k - measured with the stamps.)
+            const bool staged = CG == 2 && p.tma_store != 0;
+            uint8_t *const stg = epi_stage + (size_t)egrp * EPI_STAGE_BYTES;
+            const bool issuer = (q == 0) && lane == 0;
 #pragma unroll
             for (int ch = 0; ch < NCH; ++ch) {
                 const int col = egrp * EPI_COLS + ch * 32;
-                if (!active || n0 + col >= p.N) break;
+                if (!active || n0 + col >= p.N) break;   // uniform over the group's four warps
                 uint32_t (&v)[32] = vv[ch];
+                const bool es = warp == EPI_WARP0 && lane == 0;
+                if (es) stamp(3, 4 + tcur * 2 + ch, 0);
+                if (staged) {
+                    if (issuer) tma_store_wait_read();   // the previous store has read the staging tile
+                    named_bar_sync(1 + egrp, 128);
+                }
+                if (es) stamp(3, 4 + tcur * 2 + ch, 1);
                 if (D_TRANS) {
-                    if (row < p.M) {
+                    if (staged) {
+                        // staging tile [32 channels][128 pixels]: lanes = consecutive pixels, conflict-free
+                        const uint32_t sp = smem_u32(stg) + (uint32_t)(q * 32 + lane) * 4u;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            asm volatile("st.shared.f32 [%0], %1;" ::"r"(sp + (uint32_t)j * 512u),
+                                         "f"(p.alpha * __uint_as_float(v[j]))
+                                         : "memory");
+                    } else if (row < p.M) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             int64_t n = (int64_t)n0 + col + j;
@@ -684,14 +879,24 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                             atomicMin(p.colrange + 2 * n + 1, mxn);
                         }
                     }
-                } else if (row < p.M) {
+                    if (staged) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        named_bar_sync(1 + egrp, 128);
+                        if (issuer) tma_store_2d(&tmD, stg, m0, n0 + col);   // x = pixel, y = channel
+                    }
+                } else if (row < p.M || staged) {
                     float *dp = Dz + row * p.ldd + n0 + col;
                     const float *bp = p.blend ? p.blend + row * p.ldd + n0 + col : nullptr;
-                    const float *bias = p.bias ? p.bias + (row / p.bias_hw) * p.bias_ld + n0 + col : nullptr;
+                    const float *bias = (p.bias && row < p.M) ? p.bias + (row / p.bias_hw) * p.bias_ld + n0 + col : nullptr;
+                    // the rotations use none of the optional epilogue terms: their per-element tests (five runtime
+                    // conditions x 64 values per thread) cost 9.5 k cycles per 32-column chunk - measured with the stamps
+                    const bool extras = resid_max != nullptr || p.diag != 0.f || bias != nullptr || p.relu != 0 ||
+                                        p.rowrange != nullptr || p.alpha != 1.f;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
+                        if (!extras) break;
                         float o = p.alpha * __uint_as_float(v[j]);
-                        if (resid_max && n0 + col + j < p.N) {
+                        if (resid_max && row < p.M && n0 + col + j < p.N) {
                             float d = fabsf(__uint_as_float(v[j]) - (row == (int64_t)n0 + col + j ? 1.f : 0.f));
                             if (!(d == d)) d = INFINITY;
                             rres = fmaxf(rres, d);
@@ -706,7 +911,22 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                             rmx = ~u < rmx ? ~u : rmx;
                         }
                     }
-                    if (n0 + col + 32 <= p.N) {
+                    if (staged) {
+                        // staging tile [128 rows][32 columns], 128-byte rows, 16-byte chunks XOR-ed with the row index
+                        // (TMA SWIZZLE_128B): a quarter warp's 8 rows hit 8 different bank groups
+                        const int r = q * 32 + lane;
+                        const uint32_t sp = smem_u32(stg) + (uint32_t)r * 128u;
+#pragma unroll
+                        for (int c4 = 0; c4 < 8; ++c4)
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sp + (uint32_t)((c4 ^ (r & 7)) << 4)),
+                                         "r"(v[c4 * 4 + 0]), "r"(v[c4 * 4 + 1]), "r"(v[c4 * 4 + 2]), "r"(v[c4 * 4 + 3])
+                                         : "memory");
+                        if (es) stamp(3, 4 + tcur * 2 + ch, 2);
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        named_bar_sync(1 + egrp, 128);
+                        if (issuer) tma_store_2d(&tmD, stg, n0 + col, m0);   // x = column, y = row
+                        if (es) stamp(3, 4 + tcur * 2 + ch, 3);
+                    } else if (n0 + col + 32 <= p.N) {
                         // 256-bit accesses: every store is one full 32-byte sector of this thread's output row
 #pragma unroll
                         for (int j = 0; j < 32; j += 8) {
@@ -746,15 +966,28 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                 rres = warp_max(rres);
                 if (lane == 0 && rres > 0.f) atomicMax(reinterpret_cast<unsigned int *>(resid_max), __float_as_uint(rres));
             }
+            if (warp == EPI_WARP0 && lane == 0) stamp(3, tcur, 3);
         }
+        if (CG == 2 && p.tma_store && (warp & 3) == 0 && lane == 0) tma_store_wait_all();   // stores complete before exit
     }
     tc_fence_before();
     __syncthreads();
+    if (CG == 2) cluster_sync_all();   // neither CTA leaves while its peer may still signal its barriers / read its smem
     if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[67] = clock64();
+    if (cta_stamps) {
+        unsigned long long g;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+        p.trace[128 + 4 * blockIdx.x + 2] = clock64();
+        p.trace[128 + 4 * blockIdx.x + 3] = g;
+    }
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols)
-                     : "memory");
+        if (CG == 2)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols)
+                         : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols)
+                         : "memory");
     }
 }
 
@@ -841,6 +1074,24 @@ int make_map_mnmajor(CUtensorMap *map, const float *base, int64_t K, int64_t MN,
     return OPTEX_OK;
 }
 
+// output tile map for the TMA-store epilogue: row-major [rows, cols] with pitch ld; box {box_cols, box_rows}
+int make_map_out(CUtensorMap *map, const float *base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows,
+                 bool swizzle128) {
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, es,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                             CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (output [%lld, %lld]) failed: %d", (long long)rows, (long long)cols, (int)r);
+        return OPTEX_ECUDA;
+    }
+    return OPTEX_OK;
+}
+
 // grow-only device scratch for the hi/lo halves, one buffer per (device, stream, slot): work enqueued on two streams
 // never shares scratch (every C-ABI entry takes the stream, and the Python workspace is per stream as well); the slot
 // separates the two pipelines of optex_ot_step_host_async when they are given the same stream.
@@ -894,20 +1145,23 @@ int split(const float *x, float *hi, float *lo, int64_t n, cudaStream_t st) {
     return OPTEX_OK;
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN, bool D_TRANS, int BK>
-int launch(const CUtensorMap &ah, const CUtensorMap &al, const CUtensorMap &bh, const CUtensorMap &bl, Params p,
-           int nz, cudaStream_t st) {
-    constexpr int A_TILE = BLOCK_M * BK * 4, B_TILE = BLOCK_N * BK * 4;
+template <int BLOCK_N, bool A_MN, bool B_MN, bool D_TRANS, int BK, int CG = 1>
+int launch(const CUtensorMap &ah, const CUtensorMap &al, const CUtensorMap &bh, const CUtensorMap &bl,
+           const CUtensorMap &dm, Params p, int nz, cudaStream_t st) {
+    constexpr int A_TILE = BLOCK_M * BK * 4, B_TILE = (BLOCK_N / CG) * BK * 4;
     size_t smem;
+    if (CG != 2) p.tma_store = 0;
     if (p.a_tmem) {
-        // main ring: hi + lo tiles of B; the rest of shared memory: raw A tiles (at least 4 in flight)
-        int stages = (SMEM_BUDGET - 4 * A_TILE) / (2 * B_TILE);
+        // main ring: hi + lo tiles of B (CG == 2: this CTA's half of them); the rest of shared memory: raw A tiles
+        // (at least 4 in flight) and, with the TMA-store epilogue, one staging tile per epilogue group
+        const int epi = p.tma_store ? EPI_GROUPS * EPI_STAGE_BYTES : 0;
+        int stages = (SMEM_BUDGET - epi - 4 * A_TILE) / (2 * B_TILE);
         if (stages > MAX_STAGES) stages = MAX_STAGES;
-        int stages_a = (SMEM_BUDGET - stages * 2 * B_TILE) / A_TILE;
+        int stages_a = (SMEM_BUDGET - epi - stages * 2 * B_TILE) / A_TILE;
         if (stages_a > MAX_STAGES) stages_a = MAX_STAGES;
         p.stages = stages;
         p.stages_a = stages_a;
-        smem = (size_t)stages * 2 * B_TILE + (size_t)stages_a * A_TILE + 1024;
+        smem = (size_t)stages * 2 * B_TILE + (size_t)stages_a * A_TILE + epi + 1024;
     } else {
         const uint32_t stage_bytes = (p.terms == 3 ? 2 : 1) * (A_TILE + B_TILE);
         int stages = SMEM_BUDGET / (int)stage_bytes;
@@ -915,24 +1169,45 @@ int launch(const CUtensorMap &ah, const CUtensorMap &al, const CUtensorMap &bh, 
         p.stages = stages;
         smem = (size_t)stages * stage_bytes + 1024;
     }
-    auto kern = rotate_gemm_kernel<BLOCK_N, A_MN, B_MN, D_TRANS, BK>;
+    auto kern = rotate_gemm_kernel<BLOCK_N, A_MN, B_MN, D_TRANS, BK, CG>;
     static PerDeviceOnce attr_once1;
     OPTEX_TRY(ensure_dyn_smem(attr_once1, kern, (int)(SMEM_BUDGET + 1024)));
-    const int64_t num_tiles = ((p.M + BLOCK_M - 1) / BLOCK_M) * ((p.N + BLOCK_N - 1) / BLOCK_N) * nz;
+    const int64_t num_tiles = ((p.M + BLOCK_M * CG - 1) / (BLOCK_M * CG)) * ((p.N + BLOCK_N - 1) / BLOCK_N) * nz;
     const int sms = sm_count();
-    dim3 grid((unsigned)(num_tiles < sms ? num_tiles : sms));  // persistent: one CTA per SM walks the tile list
-    launch_pdl(kern, grid, dim3(NTHREADS), smem, st, ah, al, bh, bl, p);
+    if (CG == 1) {
+        dim3 grid((unsigned)(num_tiles < sms ? num_tiles : sms));  // persistent: one CTA per SM walks the tile list
+        launch_pdl(kern, grid, dim3(NTHREADS), smem, st, ah, al, bh, bl, dm, p);
+    } else {
+        // persistent pairs: one cluster of two CTAs per SM pair
+        const int64_t pairs = num_tiles < sms / 2 ? num_tiles : sms / 2;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)(2 * pairs));
+        cfg.blockDim = dim3(NTHREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = pdl_enabled() ? 2 : 1;
+        OPTEX_CUDA(cudaLaunchKernelEx(&cfg, kern, ah, al, bh, bl, dm, p));
+    }
     OPTEX_LAUNCH_CHECK("rotate_gemm_kernel");
     return OPTEX_OK;
 }
 
 template <bool A_MN, bool B_MN, bool D_TRANS>
-int launch_n(int block_n, const CUtensorMap &ah, const CUtensorMap &al, const CUtensorMap &bh, const CUtensorMap &bl,
-             Params p, int nz, cudaStream_t st) {
+int launch_n(int block_n, int cg, const CUtensorMap &ah, const CUtensorMap &al, const CUtensorMap &bh,
+             const CUtensorMap &bl, const CUtensorMap &dm, Params p, int nz, cudaStream_t st) {
     // (a BK = 16 / 4-stage variant of the 3xTF32 wide tile exists as a template option; it measured slower: 64 vs 59 us)
-    if (block_n == 64) return launch<64, A_MN, B_MN, D_TRANS, 32>(ah, al, bh, bl, p, nz, st);
-    if (block_n == 128) return launch<128, A_MN, B_MN, D_TRANS, 32>(ah, al, bh, bl, p, nz, st);
-    return launch<256, A_MN, B_MN, D_TRANS, 32>(ah, al, bh, bl, p, nz, st);
+    if (block_n == 64) return launch<64, A_MN, B_MN, D_TRANS, 32>(ah, al, bh, bl, dm, p, nz, st);
+    if (block_n == 128) return launch<128, A_MN, B_MN, D_TRANS, 32>(ah, al, bh, bl, dm, p, nz, st);
+    if (cg == 2) return launch<256, A_MN, B_MN, D_TRANS, 32, 2>(ah, al, bh, bl, dm, p, nz, st);
+    return launch<256, A_MN, B_MN, D_TRANS, 32>(ah, al, bh, bl, dm, p, nz, st);
 }
 
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -1018,8 +1293,8 @@ static int gemm_tc_batched(const TcGemm &g, cudaStream_t st) {
     p.bias_hw = 1;
     p.a_hint = p.b_hint = L2_EVICT_NORMAL;
     p.trace = nullptr;
-    if (!g.b_mn) return launch_n<false, false, false>(bn, ah, ah, bh, bh, p, nb, st);
-    return launch_n<false, true, false>(bn, ah, ah, bh, bh, p, nb, st);
+    if (!g.b_mn) return launch_n<false, false, false>(bn, 1, ah, ah, bh, bh, ah, p, nb, st);
+    return launch_n<false, true, false>(bn, 1, ah, ah, bh, bh, ah, p, nb, st);
 }
 
 int gemm_tc(const TcGemm &g, cudaStream_t st) {
@@ -1073,6 +1348,12 @@ int gemm_tc(const TcGemm &g, cudaStream_t st) {
     }
     bh_p += g.b_col0;  // column block of a wider B (16-byte aligned: b_col0 % 4 == 0)
     bl_p += g.b_col0;
+    // 2-CTA pairs (cta_group::2) for the big 3xTF32 GEMMs: each CTA pulls half of the B tile, which takes the kernel
+    // off the L2 -> SM bandwidth limit it sat on (80 KB per k block and SM against 1536 clk of tensor-pipe time)
+    static const char *no_atmem = getenv("OPTEX_NO_A_TMEM");
+    static const char *cg_env = getenv("OPTEX_CTA_GROUP");
+    const bool a_tmem = g.terms == 3 && !conv_b && !(no_atmem && atoi(no_atmem));
+    const int cg = (a_tmem && bn == 256 && g.M >= 2 * BLOCK_M && g.N % 64 == 0 && !(cg_env && atoi(cg_env) == 1)) ? 2 : 1;
     CUtensorMap ah, al, bh, bl;
     if (g.a_mn) {
         OPTEX_TRY(make_map_mnmajor(&ah, ah_p, g.K, g.M, BLOCK_M, 0, bk));
@@ -1082,11 +1363,11 @@ int gemm_tc(const TcGemm &g, cudaStream_t st) {
         OPTEX_TRY(make_map_kmajor(&al, al_p, g.M, g.K, BLOCK_M, bk));
     }
     if (g.b_mn) {
-        OPTEX_TRY(make_map_mnmajor(&bh, bh_p, g.K, g.N, bn, ldb, bk));
-        OPTEX_TRY(make_map_mnmajor(&bl, bl_p, g.K, g.N, bn, ldb, bk));
+        OPTEX_TRY(make_map_mnmajor(&bh, bh_p, g.K, g.N, bn / cg, ldb, bk));
+        OPTEX_TRY(make_map_mnmajor(&bl, bl_p, g.K, g.N, bn / cg, ldb, bk));
     } else {
-        OPTEX_TRY(make_map_kmajor(&bh, bh_p, g.N, g.K, bn, bk));
-        OPTEX_TRY(make_map_kmajor(&bl, bl_p, g.N, g.K, bn, bk));
+        OPTEX_TRY(make_map_kmajor(&bh, bh_p, g.N, g.K, bn / cg, bk));
+        OPTEX_TRY(make_map_kmajor(&bl, bl_p, g.N, g.K, bn / cg, bk));
     }
     Params p{};
     p.D = g.D; p.ldd = g.ldd; p.M = g.M; p.N = g.N; p.K = g.K;
@@ -1096,8 +1377,7 @@ int gemm_tc(const TcGemm &g, cudaStream_t st) {
     p.diag = g.d_trans ? 0.f : g.diag; p.resid_max = g.d_trans ? nullptr : g.resid_max;
     p.skip_below = g.skip_below; p.skip_tol = g.skip_tol; p.relu = (g.relu && !g.d_trans) ? 1 : 0;
     p.alpha = g.alpha; p.skip = g.skip; p.conv_a = p.terms == 3 ? 1 : 0; p.conv_b = conv_b ? 1 : 0;
-    static const char *no_atmem = getenv("OPTEX_NO_A_TMEM");
-    p.a_tmem = (p.conv_a && !p.conv_b && !(no_atmem && atoi(no_atmem))) ? 1 : 0;
+    p.a_tmem = a_tmem ? 1 : 0;
     // Round 1 routed 64-wide multi-tile launches away from the TMEM-A form because of a timing-dependent corruption;
     // the cause was the early release of the raw-A slot in the converters (see there).  OPTEX_ATMEM64=0 restores the
     // old routing for A/B comparisons (scripts/debug_gemm_multi.py).
@@ -1113,11 +1393,19 @@ int gemm_tc(const TcGemm &g, cudaStream_t st) {
     // a big A operand is streamed exactly once (n_tiles_n CTAs read it at the same time); B is re-read by every tile
     p.a_hint = (g.M > 4096 && g.stream_a) ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
     p.b_hint = g.M > 4096 ? L2_EVICT_LAST : L2_EVICT_NORMAL;
-    if (g.d_trans) return launch_n<false, true, true>(bn, ah, al, bh, bl, p, nz, st);
-    if (!g.a_mn && !g.b_mn) return launch_n<false, false, false>(bn, ah, al, bh, bl, p, nz, st);
-    if (!g.a_mn && g.b_mn) return launch_n<false, true, false>(bn, ah, al, bh, bl, p, nz, st);
-    if (g.a_mn && !g.b_mn) return launch_n<true, false, false>(bn, ah, al, bh, bl, p, nz, st);
-    return launch_n<true, true, false>(bn, ah, al, bh, bl, p, nz, st);
+    // TMA-store epilogue (pairs only): needs 16-byte pitches; the blend reads content with the direct-store code
+    CUtensorMap dm = ah;
+    static const char *no_tma_store = getenv("OPTEX_NO_TMA_STORE");
+    if (cg == 2 && !g.blend && nz == 1 && g.ldd % 4 == 0 && !(no_tma_store && atoi(no_tma_store))) {
+        if (g.d_trans) OPTEX_TRY(make_map_out(&dm, g.D, g.N, g.M, g.ldd, BLOCK_M, 32, false));   // D^T [channel][pixel]
+        else OPTEX_TRY(make_map_out(&dm, g.D, g.M, g.N, g.ldd, 32, BLOCK_M, true));
+        p.tma_store = 1;
+    }
+    if (g.d_trans) return launch_n<false, true, true>(bn, cg, ah, al, bh, bl, dm, p, nz, st);
+    if (!g.a_mn && !g.b_mn) return launch_n<false, false, false>(bn, cg, ah, al, bh, bl, dm, p, nz, st);
+    if (!g.a_mn && g.b_mn) return launch_n<false, true, false>(bn, cg, ah, al, bh, bl, dm, p, nz, st);
+    if (g.a_mn && !g.b_mn) return launch_n<true, false, false>(bn, cg, ah, al, bh, bl, dm, p, nz, st);
+    return launch_n<true, true, false>(bn, cg, ah, al, bh, bl, dm, p, nz, st);
 }
 
 int gemm_tc_rotate_forward(const float *X, const float *R, float *dst, int64_t n, int c, bool transposed, int terms,
