@@ -50,7 +50,9 @@ def parse():
                     help="seconds of untimed steps before the warm-up (GPU clock ramp of a fresh box)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--repeats", type=int, default=5, help="timed regions of exactly --steps steps; value = median")
+    ap.add_argument("--repeats", type=int, default=0,
+                    help="timed regions of exactly --steps steps (value = median region); 0 = as many as fill ~100 ms, "
+                         "at least 5 (the clock sampler needs the time)")
     ap.add_argument("--all-modes", action="store_true", help="(default now; kept for compatibility)")
     ap.add_argument("--no-all-modes", action="store_true", dest="no_all_modes",
                     help="skip the other hist modes / GEMM arithmetic variants (extra keys)")
@@ -327,7 +329,7 @@ def run_ours(a):
     _lib.check(lib.optex_device_check())
     ob.set_gemm_mode(a.gemm)
     lib.optex_set_pdl(0 if a.no_pdl else 1)
-    K, W, REPS = a.steps, a.warmup, max(1, a.repeats)
+    K, W, REPS = a.steps, a.warmup, a.repeats
     st = stream_ptr(device)
 
     def barrier():
@@ -391,7 +393,9 @@ def run_ours(a):
             self.steps(0, W)
             call("optex_fence", st)
             barrier()
-            self.region()                         # one untimed region: first use of every event / launch path
+            first, _ = self.region()              # one untimed region: first use of every event / launch path
+            if reps <= 0:                         # auto: ~100 ms of timed regions, 5..50
+                reps = int(max_over_ranks(float(max(5, min(50, int(100.0 / max(first, 1e-3)) + 1)))))
             ms, host = [], []
             for _ in range(reps):
                 m, h = self.region()
@@ -574,7 +578,7 @@ def run_ours(a):
                              "the region; drain fence kernel before the closing event",
                   "sharding": ("one block, rotated channels sharded over ranks + NCCL all-gather" if sharded else
                                "independent feature blocks per rank, no data-path collective")},
-        "repeats": {"n": REPS, "ms_per_region": ms_regions, "ms_median": ms_total, "ms_min": min(ms_regions),
+        "repeats": {"n": len(ms_regions), "ms_per_region": [round(x, 4) for x in ms_regions], "ms_median": ms_total, "ms_min": min(ms_regions),
                     "ms_max": max(ms_regions), "value_from": "median region"},
         "host_enqueue_ms": statistics.median(host_ms), "kernel_sum_ms": kernel_sum,
         "kernel_sum_over_step": (kernel_sum / ms_step) if kernel_sum else None,

@@ -39,6 +39,8 @@ extern "C" {
 #define OPTEX_ECUDA 3      /* a CUDA runtime call or kernel launch failed        */
 #define OPTEX_EWORKSPACE 4 /* workspace pointer NULL or too small                */
 #define OPTEX_ESIZE 5      /* size outside what the kernels support              */
+#define OPTEX_EUNSUPPORTED 6 /* the request needs something this build / process lacks (e.g. NCCL not loadable,
+                                a mode without a sharded form)                    */
 
 /* hist modes: histmatch.py:5 `mode`; OPTEX_MODE_SORT is the north-star's exact
  * 1-D OT (not in the reference, defined by oracle/sort_oracle.py).            */
@@ -168,6 +170,43 @@ int optex_ot_loop(float *feat, const float *S, const float *R_all, int iters,
                   const float *content, float content_strength, void *workspace,
                   size_t workspace_bytes, void *stream);
 size_t optex_ot_loop_workspace_bytes(int64_t n_p, int64_t n_s, int c, int mode);
+
+/* ---- multi-GPU: one process per GPU, NCCL over NVLink ------------------------
+ * No reference counterpart (the reference is single-device).  How the step shards:
+ *   cdf            PIXEL-sharded - rank g holds n_g rows of P and m_g rows of S (all channels).  The only cross-pixel
+ *                  quantities of cdf_match (histmatch.py:52-58) are the per-channel range (all-reduce MIN of 2c words)
+ *                  and the two histograms (all-reduce SUM of 2 c 256 counts): every rank builds the tables one GPU
+ *                  would, results are BIT-IDENTICAL to the single-GPU step on the concatenated rows, and 1 MB crosses
+ *                  NVLink per step at c = 512.
+ *   chol/pca/sym   PIXEL-sharded moments (histmatch.py:16-22): column sums and the centred Gram are all-reduced
+ *                  (c + c*c floats), the c x c chain runs on every rank, the map is applied to the local rows
+ *                  (same result up to fp32 summation order).  One sample per side (b = 1).
+ *   sort           needs global ranks per channel: OPTEX_EUNSUPPORTED here (channel-sharded form with an all-gather:
+ *                  optimaltextures_b200/parallel.py).
+ * NCCL is bound at run time (dlopen of the process's libnccl.so.2).  All ranks must pass the same R (e.g. the same
+ * (seed, counter) to optex_random_rotation), c, mode, eps and totals. */
+typedef struct optex_comm optex_comm_t;
+size_t optex_comm_unique_id_bytes(void);
+/* rank 0: create the id (ncclGetUniqueId) and hand it to the other ranks by any means (128 bytes) */
+int optex_comm_unique_id(void *id_out, size_t id_bytes);
+/* every rank: ncclCommInitRank on the CURRENT device */
+int optex_comm_init(const void *id, int rank, int world, optex_comm_t **comm);
+/* or wrap a communicator the caller already has (ncclComm_t as void*); it is not destroyed with the handle */
+int optex_comm_adopt(void *nccl_comm, int rank, int world, optex_comm_t **comm);
+int optex_comm_destroy(optex_comm_t *comm);
+int optex_comm_rank(const optex_comm_t *comm);
+int optex_comm_world(const optex_comm_t *comm);
+/* recv[rank r] = send of rank r (count_per_rank floats each): gathers the local rows of a sharded block */
+int optex_comm_allgather_f32(optex_comm_t *comm, const float *send, float *recv, size_t count_per_rank, void *stream);
+
+/* The OT step (optex.py:167-177) on this rank's rows: P_local [n_p_local, c], S_local [n_s_local, c] -> out_local
+ * [n_p_local, c]; n_*_total = the sums over the ranks (the cdf histograms and the moments are those of the whole block).
+ * content (may be NULL) is this rank's rows of the content block.  workspace: optex_ot_workspace_bytes(n_p_local,
+ * n_s_local, c, mode).  out_local must not alias the inputs. */
+int optex_ot_step_sharded(optex_comm_t *comm, const float *P_local, const float *S_local, const float *R,
+                          float *out_local, int64_t n_p_local, int64_t n_s_local, int64_t n_p_total,
+                          int64_t n_s_total, int c, int mode, float eps, const float *content,
+                          float content_strength, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---- histogram matching without rotation -----------------------------------
  * replaces: hist_match()  histmatch.py:5-46  (called directly by

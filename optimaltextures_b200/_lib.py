@@ -11,7 +11,7 @@ import os
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "lib", "liboptex_b200.so")
 
-OK, EINVAL, EDEVICE, ECUDA, EWORKSPACE, ESIZE = range(6)
+OK, EINVAL, EDEVICE, ECUDA, EWORKSPACE, ESIZE, EUNSUPPORTED = range(7)
 MODES = {"chol": 0, "pca": 1, "sym": 2, "cdf": 3, "sort": 4}
 GEMM_MODES = {"auto": 0, "fp32": 1, "tf32x3": 2, "tf32": 3}
 
@@ -43,6 +43,15 @@ SIGNATURES = {
     "optex_ot_steps": (_i, [_p, _p, _i, _p, _p, _i, _i, _i, _i, _l, _i, _l, _i, _i, _f, _p, _z, _p]),
     "optex_fence": (_i, [_p]),
     "optex_ot_step_profile": (_i, [_p, _p, _p, _p, _i, _l, _i, _l, _i, _i, _f, _p, _z, _p, _p, _p, _p]),
+    "optex_comm_unique_id_bytes": (_z, []),
+    "optex_comm_unique_id": (_i, [_p, _z]),
+    "optex_comm_init": (_i, [_p, _i, _i, _p]),
+    "optex_comm_adopt": (_i, [_p, _i, _i, _p]),
+    "optex_comm_destroy": (_i, [_p]),
+    "optex_comm_rank": (_i, [_p]),
+    "optex_comm_world": (_i, [_p]),
+    "optex_comm_allgather_f32": (_i, [_p, _p, _p, _z, _p]),
+    "optex_ot_step_sharded": (_i, [_p, _p, _p, _p, _p, _l, _l, _l, _l, _i, _i, _f, _p, _f, _p, _z, _p]),
     "optex_ot_loop": (_i, [_p, _p, _p, _i, _u, _u, _i, _l, _i, _l, _i, _i, _f, _p, _f, _p, _z, _p]),
     "optex_ot_loop_workspace_bytes": (_z, [_l, _l, _i, _i]),
     "optex_hist_match_workspace_bytes": (_z, [_l, _l, _i, _i]),
@@ -116,6 +125,8 @@ def check(code: int) -> None:
     msg = lib().optex_last_error().decode(errors="replace")
     if code in (EINVAL, ESIZE):
         raise ValueError(f"liboptex_b200 status {code}: {msg}")
+    if code == EUNSUPPORTED:
+        raise NotImplementedError(f"liboptex_b200 status {code}: {msg}")
     raise OptexError(code, msg)
 
 

@@ -505,6 +505,83 @@ extern "C" int optex_fence(void *stream) {
     return OPTEX_OK;
 }
 
+// The step on this rank's rows (include/optex_b200.h "multi-GPU"; sharded.cu has the NCCL plumbing).
+extern "C" int optex_ot_step_sharded(optex_comm_t *comm, const float *P, const float *S, const float *R, float *out,
+                                     int64_t n_p, int64_t n_s, int64_t n_p_total, int64_t n_s_total, int c, int mode,
+                                     float eps, const float *content, float strength, void *ws, size_t ws_bytes,
+                                     void *stream) {
+    OPTEX_TRY(require_sm100());
+    const ShardComm *cm = (const ShardComm *)comm;
+    if (!cm) {
+        set_error("optex_ot_step_sharded: NULL communicator");
+        return OPTEX_EINVAL;
+    }
+    OPTEX_TRY(check_step_args("optex_ot_step_sharded", P, S, out, 1, n_p, 1, n_s, c, mode));
+    if (!R && (per_channel(mode) || mode == OPTEX_MODE_CHOL)) {
+        set_error("optex_ot_step_sharded: NULL rotation");
+        return OPTEX_EINVAL;
+    }
+    if (n_p_total < n_p || n_s_total < n_s) {
+        set_error("optex_ot_step_sharded: totals smaller than the local row counts");
+        return OPTEX_EINVAL;
+    }
+    if (out == P || out == S) {
+        set_error("optex_ot_step_sharded: out must not alias an input");
+        return OPTEX_EINVAL;
+    }
+    if (mode == OPTEX_MODE_SORT) {
+        set_error("optex_ot_step_sharded: sort needs global ranks per channel - use the channel-sharded form "
+                  "(optimaltextures_b200.parallel.optimal_transport_sharded)");
+        return OPTEX_EUNSUPPORTED;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mode != OPTEX_MODE_CDF) {
+        // pixel-sharded moments: cov_match.cu all-reduces the column sums and the centred Gram while the context is set
+        ShardCtx ctx{cm, n_p_total, n_s_total};
+        cov_set_shard(&ctx);
+        int rc = cov_ot_step(P, S, R, out, 1, n_p, 1, n_s, c, mode, eps, content, strength, ws, ws_bytes, st, 0);
+        cov_set_shard(nullptr);
+        return rc;
+    }
+    if (n_p_total >= (1 << 24) || n_s_total >= (1 << 24)) {
+        set_error("optex_ot_step_sharded: n >= 2^24 per channel (fp32 cumsum of the reference stops being exact)");
+        return OPTEX_ESIZE;
+    }
+    Arena ar(ws, ws_bytes);
+    float *rp = ar.take<float>((size_t)n_p * c);
+    float *rs = ar.take<float>((size_t)n_s * c);
+    float *r_hi = ar.take<float>((size_t)c * c), *r_lo = ar.take<float>((size_t)c * c);
+    const size_t mws = match_ws_bytes(n_p, n_s, c, mode);
+    Arena mar(ar.take<char>(mws), mws);
+    uint32_t *minmax = mar.take<uint32_t>(2 * (size_t)c);
+    uint32_t *hist = mar.take<uint32_t>(2 * (size_t)c * 256);
+    float *tbl = mar.take<float>(4 * (size_t)c * 256 + 4);
+    if (!ar.ok() || !mar.ok()) {
+        set_error("optex_ot_step_sharded: workspace %zu < %zu bytes", ws_bytes, optex_ot_workspace_bytes(n_p, n_s, c, mode));
+        return OPTEX_EWORKSPACE;
+    }
+    struct PresplitGuard {
+        ~PresplitGuard() { gemm_tc_set_presplit(nullptr, nullptr, nullptr); }
+    } presplit_guard;
+    bool forced_tc;
+    const bool tc3 = want_tc(forced_tc) && tc_terms() == 3 && c % 4 == 0;
+    if (tc3) {
+        OPTEX_TRY(gemm_tc_split_and_fill(R, r_hi, r_lo, (int64_t)c * c, minmax, 2 * (int64_t)c, 0xffffffffu, st));
+        gemm_tc_set_presplit(R, r_hi, r_lo);
+    } else {
+        OPTEX_TRY(fill_u32(minmax, 2 * (int64_t)c, 0xffffffffu, st));
+    }
+    bool r1 = false, r2 = false;
+    OPTEX_TRY(rotate_forward(P, R, rp, n_p, c, true, st, 0, -1, minmax, &r1));     // local rows, range folded
+    OPTEX_TRY(rotate_forward(S, R, rs, n_s, c, true, st, 0, -1, minmax, &r2));
+    if (!(r1 && r2)) OPTEX_TRY(cdf_stage_range(rp, rs, c, n_p, n_s, minmax, true, st));
+    OPTEX_TRY(shard_allreduce_u32(cm, minmax, 2 * (size_t)c, true, st));            // histmatch.py:52-53 over all rows
+    OPTEX_TRY(cdf_stage_hist(rp, rs, c, n_p, n_s, 256, minmax, hist, st));
+    OPTEX_TRY(shard_allreduce_u32(cm, hist, 2 * (size_t)c * 256, false, st));       // histmatch.py:57-58 over all rows
+    OPTEX_TRY(cdf_stage_apply(rp, rp, c, n_p, 256, minmax, hist, tbl, st));
+    return rotate_inverse(rp, true, R, out, n_p, c, content, strength, st);
+}
+
 static const int kRotChunk = 16;
 
 extern "C" size_t optex_ot_loop_workspace_bytes(int64_t n_p, int64_t n_s, int c, int mode) {

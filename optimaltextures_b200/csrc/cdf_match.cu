@@ -633,6 +633,51 @@ int cdf_match_core(const float *target, const float *source, float *out, int c, 
     OPTEX_LAUNCH_CHECK("cdf_apply_kernel");
     return OPTEX_OK;
 }
+// ---- the matcher in three separately callable stages, for the pixel-sharded multi-GPU step (sharded.cu): every rank
+// holds a slice of the pixels of ALL channels, so the range (2 c words, min) and the histograms (2 c bins counts, sum)
+// are all-reduced between the stages and every rank then builds identical tables.  Workspace layout as above.
+int cdf_stage_range(const float *target, const float *source, int c, int64_t n_t, int64_t n_s, uint32_t *minmax,
+                    bool reset, cudaStream_t st) {
+    const int t_vec = aligned16(target) && (n_t % 4 == 0), s_vec = aligned16(source) && (n_s % 4 == 0);
+    const int64_t n_big = n_t > n_s ? n_t : n_s;
+    if (reset) OPTEX_TRY(fill_u32(minmax, 2 * (int64_t)c, 0xffffffffu, st));
+    dim3 grid((unsigned)cdf_splits(c, n_big), (unsigned)c);
+    launch_pdl(cdf_range_kernel, grid, dim3(NT), 0, st, target, source, n_t, n_s, minmax, t_vec, s_vec);
+    OPTEX_LAUNCH_CHECK("cdf_range_kernel");
+    return OPTEX_OK;
+}
+int cdf_stage_hist(const float *target, const float *source, int c, int64_t n_t, int64_t n_s, int bins,
+                   const uint32_t *minmax, uint32_t *hist, cudaStream_t st) {
+    const int t_vec = aligned16(target) && (n_t % 4 == 0), s_vec = aligned16(source) && (n_s % 4 == 0);
+    const int64_t n_big = n_t > n_s ? n_t : n_s;
+    const bool priv = (bins % 4 == 0) && bins <= PRIV_MAX_BINS;
+    int64_t hs = (2LL * sm_count() + c - 1) / c, hcap = (n_big + 32767) / 32768;
+    dim3 grid_h((unsigned)(hs < hcap ? (hs < 1 ? 1 : hs) : (hcap < 1 ? 1 : hcap)), (unsigned)c, 2);
+    if (grid_h.x > 1) OPTEX_TRY(fill_u32(hist, 2 * (int64_t)c * bins, 0u, st));
+    if (priv) {
+        size_t smem = sizeof(uint32_t) * (size_t)bins + (size_t)(bins + 1) * NTH_HIST;
+        static PerDeviceOnce attr_once3;
+        OPTEX_TRY(ensure_dyn_smem(attr_once3, cdf_hist_kernel<true>, (int)(sizeof(uint32_t) * PRIV_MAX_BINS + (PRIV_MAX_BINS + 1) * NTH_HIST)));
+        launch_pdl(cdf_hist_kernel<true>, grid_h, dim3(NTH_HIST), smem, st, target, source, n_t, n_s, minmax, hist, bins,
+                   t_vec, s_vec);
+    } else {
+        launch_pdl(cdf_hist_kernel<false>, grid_h, dim3(NTH_HIST), sizeof(uint32_t) * 2 * bins, st, target, source, n_t,
+                   n_s, minmax, hist, bins, t_vec, s_vec);
+    }
+    OPTEX_LAUNCH_CHECK("cdf_hist_kernel");
+    return OPTEX_OK;
+}
+int cdf_stage_apply(const float *target, float *out, int c, int64_t n_t, int bins, const uint32_t *minmax,
+                    const uint32_t *hist, float *tbl, cudaStream_t st) {
+    const int o_vec = aligned16(target) && (n_t % 4 == 0) && aligned16(out);
+    launch_pdl(cdf_tables_kernel, dim3((unsigned)c), dim3(NT), sizeof(float) * 6 * bins, st, minmax, hist, bins, tbl,
+               (float *)nullptr);
+    OPTEX_LAUNCH_CHECK("cdf_tables_kernel");
+    dim3 grid_a((unsigned)cdf_splits(c, n_t), (unsigned)c);
+    launch_pdl(cdf_apply_kernel, grid_a, dim3(NT), 0, st, target, out, n_t, minmax, (const float *)tbl, bins, o_vec);
+    OPTEX_LAUNCH_CHECK("cdf_apply_kernel");
+    return OPTEX_OK;
+}
 }  // namespace optex
 
 extern "C" int optex_cdf_match(const float *target, const float *source, float *out, int c, int64_t n_t,

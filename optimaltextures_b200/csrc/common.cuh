@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "../../include/optex_b200.h"
 
@@ -129,6 +130,23 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// ---- multi-GPU (sharded.cu): an NCCL communicator handle + the collectives of the sharded steps
+struct ShardComm {
+    void *comm;   // ncclComm_t
+    int rank, world;
+    int owned;    // created by optex_comm_init (destroyed with it) vs adopted from the caller
+};
+int shard_allreduce_u32(const ShardComm *cm, uint32_t *buf, size_t count, bool take_min, cudaStream_t st);
+int shard_allreduce_f32_sum(const ShardComm *cm, float *buf, size_t count, cudaStream_t st);
+int shard_allgather_f32(const ShardComm *cm, const float *send, float *recv, size_t count_per_rank, cudaStream_t st);
+// pixel-sharded covariance step: while set (thread-local), moments() all-reduces its sums over `comm` and divides by
+// the TOTAL pixel counts
+struct ShardCtx {
+    const ShardComm *comm;
+    int64_t hw_p_total, hw_s_total;
+};
+void cov_set_shard(const ShardCtx *ctx);   // cov_match.cu
+
 // ---- internal entry points shared between translation units ------------------
 // GEMM:  D[m, n] = sum_k A(m,k) * B(k,n)
 //   a_kmajor : A(m,k) = A[m*lda + k]  else A[k*lda + m]
@@ -169,6 +187,14 @@ bool cdf_uses_channel_kernel(int c, int64_t n_t, int64_t n_s, int bins);  // tha
 int fill_u32(uint32_t *p, int64_t n, uint32_t v, cudaStream_t st);
 int cdf_match_core(const float *target, const float *source, float *out, int c, int64_t n_t, int64_t n_s, int bins,
                    float *tables, void *workspace, size_t workspace_bytes, bool have_range, cudaStream_t st);
+
+// the same matcher stage by stage (pixel-sharded multi-GPU step: all-reduce minmax after range, hist after hist)
+int cdf_stage_range(const float *target, const float *source, int c, int64_t n_t, int64_t n_s, uint32_t *minmax,
+                    bool reset, cudaStream_t st);
+int cdf_stage_hist(const float *target, const float *source, int c, int64_t n_t, int64_t n_s, int bins,
+                   const uint32_t *minmax, uint32_t *hist, cudaStream_t st);
+int cdf_stage_apply(const float *target, float *out, int c, int64_t n_t, int bins, const uint32_t *minmax,
+                    const uint32_t *hist, float *tbl, cudaStream_t st);
 
 // sort_match.cu: exact 1-D OT per channel; `source_scratch` [c, n_s] is sorted in place
 size_t sort_match_scratch_bytes(int c, int64_t n_t, int64_t n_s);  // 0 while channels fit on chip (<= 16384)

@@ -374,14 +374,26 @@ size_t ws_layout(int64_t n_t, int64_t n_s, int c, int b_max, Ws *w, void *base, 
     return ar.off;
 }
 
+// pixel-sharded step (optex_ot_step_sharded): while set, moments() sees only this rank's rows of a ONE-sample block -
+// column sums and Gram are all-reduced and divided by the total row count
+thread_local const ShardCtx *g_shard = nullptr;
+
 // mu[b][c] and Sig = cov + (eps on the diagonal) of X [nb*hw, c]
-int moments(const float *X, int nb, int64_t hw, int c, float eps, float *mu, float *Sig, Ws &w, cudaStream_t st) {
+int moments(const float *X, int nb, int64_t hw, int c, float eps, float *mu, float *Sig, Ws &w, cudaStream_t st,
+            int64_t hw_total = 0) {
     const int64_t n = (int64_t)nb * hw;
+    const ShardComm *cm = (g_shard && hw_total > 0) ? g_shard->comm : nullptr;
+    if (cm && nb != 1) {
+        set_error("sharded covariance step: one sample per side (b = 1)");
+        return OPTEX_EINVAL;
+    }
+    const int64_t hw_div = cm ? hw_total : hw;   // sharded: local sums over the TOTAL count, summed over the ranks
     int splits = (int)(hw < kMeanSplits ? hw : kMeanSplits);
     launch_pdl(colsum_partial_kernel, dim3(cdiv(c, 32), splits, nb), dim3(32, 8), 0, st, X, w.part_mean, hw, c, splits);
     OPTEX_LAUNCH_CHECK("colsum_partial_kernel");
-    launch_pdl(colmean_final_kernel, dim3((unsigned)(cdiv((int64_t)nb * c, 256))), dim3(256), 0, st, w.part_mean, mu, hw, c, splits, nb);
+    launch_pdl(colmean_final_kernel, dim3((unsigned)(cdiv((int64_t)nb * c, 256))), dim3(256), 0, st, w.part_mean, mu, hw_div, c, splits, nb);
     OPTEX_LAUNCH_CHECK("colmean_final_kernel");
+    if (cm) OPTEX_TRY(shard_allreduce_f32_sum(cm, mu, (size_t)c, st));
     {
         const int64_t total = n * c;
         int64_t blocks = (total + 255) / 256;
@@ -416,8 +428,15 @@ int moments(const float *X, int nb, int64_t hw, int c, float eps, float *mu, flo
             nz = (int)((n + kz - 1) / kz);
         }
     }
-    launch_pdl(gram_reduce_kernel, dim3((unsigned)(cdiv((int64_t)c * c, 256))), dim3(256), 0, st, w.part_gram, nz, zstride, mu, nb, hw, c, eps, Sig, 0);
+    launch_pdl(gram_reduce_kernel, dim3((unsigned)(cdiv((int64_t)c * c, 256))), dim3(256), 0, st, w.part_gram, nz, zstride, mu, nb, hw_div, c, cm ? 0.f : eps, Sig, 0);
     OPTEX_LAUNCH_CHECK("gram_reduce_kernel");
+    if (cm) {
+        OPTEX_TRY(shard_allreduce_f32_sum(cm, Sig, (size_t)c * c, st));
+        if (eps != 0.f) {
+            launch_pdl(add_diag_kernel, dim3((unsigned)(cdiv(c, 256))), dim3(256), 0, st, Sig, c, eps);
+            OPTEX_LAUNCH_CHECK("add_diag_kernel");
+        }
+    }
     return OPTEX_OK;
 }
 
@@ -594,6 +613,8 @@ int side_stream(SideStream **out) {
 
 }  // namespace
 
+void cov_set_shard(const ShardCtx *ctx) { g_shard = ctx; }
+
 size_t cov_match_ws_bytes(int64_t n_t, int64_t n_s, int c, int mode) {
     (void)mode;
     if (c < 1) return 0;
@@ -637,8 +658,9 @@ int cov_ot_step(const float *P, const float *S, const float *R, float *out, int 
     // pca also the style square root Y2 - are still in the workspace.  With a rotation (chol) the un-rotated style
     // covariance lives in `aux`, because the factorisation overwrites sig_s.
     float *sig_s_src = R ? aux : sig_s;
-    OPTEX_TRY(moments(P, b_p, hw_p, c, R ? 0.f : eps, w.mu_p, sig_t, w, st));
-    if (!style_reuse) OPTEX_TRY(moments(S, b_s, hw_s, c, R ? 0.f : eps, w.mu_s, sig_s_src, w, st));
+    OPTEX_TRY(moments(P, b_p, hw_p, c, R ? 0.f : eps, w.mu_p, sig_t, w, st, g_shard ? g_shard->hw_p_total : 0));
+    if (!style_reuse)
+        OPTEX_TRY(moments(S, b_s, hw_s, c, R ? 0.f : eps, w.mu_s, sig_s_src, w, st, g_shard ? g_shard->hw_s_total : 0));
     // ---- fork: the style-side chain (sandwich, factorisation) on the side stream
     SideStream *side;
     OPTEX_TRY(side_stream(&side));

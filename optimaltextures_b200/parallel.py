@@ -17,6 +17,12 @@ GPU saturates (conv1_1 / conv2_1 at >= 1024^2, everything at 2048^2): the all-ga
 The covariance modes (chol / pca / sym) run replicated - their per-step work after the algebraic folding
 (cov_match.cu) is two N x C x C GEMMs, which a pixel-sharded Gram + all-reduce would split (next round).
 
+PIXEL sharding (the `cdf` and covariance modes; `Communicator`, `optimal_transport_pixel_sharded`, C-ABI
+`optex_ot_step_sharded`): every rank keeps a slice of the ROWS of P and S.  Rotations are row-local; `cdf` needs only
+the per-channel range and histograms of the whole block (two tiny all-reduces: 2C words MIN, 2*256*C counts SUM) and is
+then bit-identical to one GPU; the covariance modes all-reduce column sums and the centred Gram.  No feature data
+crosses NVLink, and in a loop the block simply stays sharded between iterations.
+
 `ops` makes the device kernels pluggable so the sharding logic itself is tested on CPU with gloo (tests/
 test_parallel_gloo.py drives it with the oracle's matchers); the default ops are the CUDA kernels.
 """
@@ -114,3 +120,83 @@ def optimal_transport_sharded(pastiche_feature: Tensor, style_feature: Tensor, h
                     mt[s:s + k] = buf[r, :k]
         out = ops.rotate_inverse(mt, rotation, content.reshape(n, c) if content is not None else None, content_strength)
     return out.reshape(pastiche_feature.shape)
+
+
+# ----------------------------------------------------------------------------------------- pixel sharding (C-ABI)
+class Communicator:
+    """NCCL communicator owned by liboptex_b200 (`optex_comm_init`).  The unique id travels through the already
+    initialised torch.distributed group (any backend); one instance per process / GPU."""
+
+    def __init__(self, group=None):
+        import ctypes as C
+
+        from . import _lib
+
+        lib = _lib.lib()
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        nbytes = int(lib.optex_comm_unique_id_bytes())
+        buf = (C.c_ubyte * nbytes)()
+        if self.rank == 0:
+            _lib.check(lib.optex_comm_unique_id(buf, nbytes))
+        box = [bytes(buf) if self.rank == 0 else None]
+        dist.broadcast_object_list(box, src=0, group=group)
+        raw = (C.c_ubyte * nbytes).from_buffer_copy(box[0])
+        self._h = C.c_void_p()
+        _lib.check(lib.optex_comm_init(raw, self.rank, self.world, C.byref(self._h)))
+
+    @property
+    def handle(self):
+        return self._h
+
+    def close(self):
+        from . import _lib
+
+        if self._h:
+            _lib.lib().optex_comm_destroy(self._h)
+            self._h = None
+
+    def all_gather_rows(self, local: Tensor) -> Tensor:
+        """[n_local, c] of every rank (equal n_local) -> [world * n_local, c], rank order."""
+        from ._runtime import call, ptr, stream_ptr
+
+        out = torch.empty(self.world * local.shape[0], *local.shape[1:], dtype=torch.float32, device=local.device)
+        call("optex_comm_allgather_f32", self._h, ptr(local), ptr(out), local.numel(), stream_ptr(local.device))
+        return out
+
+
+def row_slices(n: int, world: int, align: int = 32) -> List[Tuple[int, int]]:
+    """Contiguous (start, count) row slices, one per rank, starts multiples of `align` (the tensor-core inverse
+    rotation wants 32-row blocks); the last rank takes the remainder."""
+    units = (n + align - 1) // align
+    per, extra = divmod(units, world)
+    out, start = [], 0
+    for r in range(world):
+        k = max(0, min(n, start + (per + (1 if r < extra else 0)) * align) - start)
+        out.append((start, k))
+        start += k
+    assert start == n
+    return out
+
+
+def optimal_transport_pixel_sharded(p_local: Tensor, s_local: Tensor, hist_mode: str, rotation: Optional[Tensor],
+                                    comm: Communicator, n_p_total: int, n_s_total: int,
+                                    content_local: Optional[Tensor] = None, content_strength: float = 0.0,
+                                    eps: float = 1.0, out: Optional[Tensor] = None) -> Tensor:
+    """optex.py:167-177 on this rank's rows [n_local, c] of the pastiche / style blocks (`optex_ot_step_sharded`)."""
+    from . import _lib
+    from ._runtime import call, f32c, ptr, require_cuda, stream_ptr, workspace
+
+    dev = require_cuda(p_local, s_local, rotation, content_local)
+    p, s = f32c(p_local), f32c(s_local)
+    c = p.shape[-1]
+    n_p, n_s = p.numel() // c, s.numel() // c
+    m = _lib.mode_id(hist_mode)
+    if out is None:
+        out = torch.empty_like(p)
+    wsb = workspace(dev, _lib.lib().optex_ot_workspace_bytes(n_p, n_s, c, m))
+    r = f32c(rotation) if rotation is not None else None
+    ct = f32c(content_local) if content_local is not None else None
+    with torch.cuda.device(dev):
+        call("optex_ot_step_sharded", comm.handle, ptr(p), ptr(s), ptr(r), ptr(out), n_p, n_s, int(n_p_total),
+             int(n_s_total), c, m, float(eps), ptr(ct), float(content_strength), ptr(wsb), wsb.numel(), stream_ptr(dev))
+    return out

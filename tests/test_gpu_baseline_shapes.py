@@ -9,9 +9,10 @@ Stated tolerances (fp32 feature tensors, scale = max(1, max |reference|)):
                      difference between the GPU's and the CPU's rotation GEMM legitimately moves an isolated element
                      to the neighbouring bin / rank.  The check is made in the rotated frame (out @ R), where such a
                      move touches ONE element: every element must be within BULK_TOL * scale of the oracle, except a
-                     fraction <= OUTLIER_FRAC that may differ by at most the channel's own largest discontinuity
-                     (cdf: the largest jump of the reference's interp at a bin edge, measured on the oracle's tables;
-                     sort: CLUSTER adjacent gaps of the sorted source) - no element may be wrong by "any amount".
+                     fraction <= OUTLIER_FRAC that may differ by at most the map's own discontinuity where the
+                     element sits (cdf: the jump of the reference's interp / the remap-table step at the element's
+                     nearest bin edges plus one bin width, measured on the oracle's tables; sort: CLUSTER adjacent gaps
+                     of the sorted source) - no element may be wrong by "any amount".
 """
 import numpy as np
 import pytest
@@ -64,19 +65,24 @@ def make(n_p, n_s, c, kind, seed):
 
 
 def cdf_jumps(rp_cn, rs_cn):
-    """Discontinuity of the reference's interp (histmatch.py:72-92) at every bin edge, per channel: [c, bins - 1]
-    (|f(edge) - f(edge+)|), and the edges themselves [c, bins]."""
-    jumps, all_edges = [], []
+    """Per channel and bin edge, how far a last-bit difference can legitimately move a matched value there:
+    the discontinuity of the reference's interp (histmatch.py:72-92) at the edge, |f(edge) - f(edge+)|, and the step of
+    the remap table across it (ONE element counted in the neighbouring bin moves the target CDF by 1/n, which slides
+    remap[i] along the source's inverse CDF - by up to a table step where the source is sparse).  Returns
+    ([c, bins - 1] bounds, [c, bins] edges, [c] bin widths)."""
+    bounds, all_edges, widths = [], [], []
     for ch in range(rp_cn.shape[0]):
-        _, _, edges, remap, _, _ = ot_oracle.cdf_tables(rp_cn[ch], rs_cn[ch])
+        lo, hi, edges, remap, _, _ = ot_oracle.cdf_tables(rp_cn[ch], rs_cn[ch])
         inner = edges[:-1]                       # nothing lies above the last edge (it is the channel's maximum)
         above = torch.nextafter(inner, torch.full_like(inner, float("inf")))
         a = ot_oracle.interp_backward(inner, edges, remap).double()
         b = ot_oracle.interp_backward(above, edges, remap).double()
         d = torch.nan_to_num((a - b).abs(), nan=0.0, posinf=0.0)
-        jumps.append(d)
+        step = torch.nan_to_num(remap.double().diff().abs(), nan=0.0, posinf=0.0)
+        bounds.append(torch.maximum(d, step))
         all_edges.append(edges)
-    return torch.stack(jumps), torch.stack(all_edges)
+        widths.append((float(hi) - float(lo)) / edges.numel())
+    return torch.stack(bounds), torch.stack(all_edges), torch.tensor(widths, dtype=torch.float64)
 
 
 def sort_jumps(rs_cn):
@@ -118,13 +124,15 @@ def test_full_step_vs_oracle(ob, n_p, n_s, c, kind, mode):
     if not bool(outlier.any()):
         return
     if mode == "cdf":
-        jumps, edges = cdf_jumps(rp, rs)                          # [c, 255], [c, 256]
+        jumps, edges, width = cdf_jumps(rp, rs)                   # [c, 255], [c, 256], [c]
         ch, px = outlier.nonzero(as_tuple=True)
         x = rp[ch, px]
         i = torch.searchsorted(edges[ch], x[:, None]).squeeze(1).clamp(0, edges.shape[1] - 1)
         last = jumps.shape[1] - 1
-        local = torch.maximum(jumps[ch, (i - 1).clamp(0, last)], jumps[ch, i.clamp(0, last)])
-        allowed = local + tol
+        local = jumps[ch, i.clamp(0, last)]
+        for k in (-2, -1, 1):                                     # the element's bin, its neighbours' edges
+            local = torch.maximum(local, jumps[ch, (i + k).clamp(0, last)])
+        allowed = local + width[ch] + tol
     else:
         ch, px = outlier.nonzero(as_tuple=True)
         allowed = sort_jumps(rs)[ch] + tol
