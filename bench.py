@@ -67,6 +67,8 @@ def parse():
     ap.add_argument("--synthesis-cpu", action="store_true", dest="synthesis_cpu", help="(default now; kept)")
     ap.add_argument("--no-synthesis-cpu", action="store_true", dest="no_synthesis_cpu",
                     help="skip the CPU-reference timing of configs[0] (the whole 256^2 synthesis once on the host cores)")
+    ap.add_argument("--no-sharded-block", action="store_true", dest="no_sharded_block",
+                    help="N > 1: skip the extra `sharded` key (pixel-sharded strong scaling of ONE block over the ranks)")
     ap.add_argument("--sharded", action="store_true",
                     help="N > 1: ONE feature block, rotated channels sharded over the ranks + NCCL all-gather "
                          "(strong scaling) instead of one independent block per rank")
@@ -298,6 +300,64 @@ def measure_tf32_peak(torch, device, seconds=1.5):
         torch.backends.cuda.matmul.allow_tf32 = prev
 
 
+def pixel_sharded_block(a, torch, dist, ob, lib, device, rank, world, K, W, barrier, max_over_ranks):
+    """Strong scaling: ONE feature block, its rows split over the ranks (optex_ot_step_sharded, NCCL all-reduces of
+    the per-channel range and histograms only), against the same block on one GPU - timed on every rank, max over
+    ranks - with the bit-identity of the gathered result checked in place."""
+    from optimaltextures_b200 import parallel
+
+    comm = parallel.Communicator()
+    out = {"api": "optex_ot_step_sharded (C-ABI): rows of P and S split over the ranks, per step 2 NCCL all-reduces "
+                  "(2C words MIN, 2*256*C counts SUM), no feature data crosses NVLink", "mode": a.mode, "shapes": {}}
+    mode = a.mode if a.mode != "sort" else "cdf"
+    shapes = [("conv4_1@1024^2", 128 * 128, 512), ("conv1_1@1024^2", 1024 * 1024, 64), ("conv3_1@2048^2", 512 * 512, 256)]
+    for name, n, c in shapes:
+        try:
+            g = torch.Generator().manual_seed(7)
+            p = torch.relu(torch.randn(n, c, generator=g)).to(device)
+            s = torch.relu(1.3 * torch.randn(n, c, generator=g) + 0.2).to(device)
+            rots = ob.random_rotations(c, K, device, seed=1234, first_counter=0)     # the same on every rank
+            (r0, rk) = parallel.row_slices(n, world)[rank]
+            p_loc, s_loc = p[r0:r0 + rk].contiguous(), s[r0:r0 + rk].contiguous()
+            out_loc = torch.empty_like(p_loc)
+
+            def timed(fn):
+                for i in range(W):
+                    fn(i)
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for i in range(K):
+                    fn(i)
+                e1.record()
+                barrier()
+                return max_over_ranks(e0.elapsed_time(e1)) / K
+
+            p4, s4 = p.view(1, n, 1, c), s.view(1, n, 1, c)
+            t1 = timed(lambda i: ob.optimal_transport(p4, s4, mode, rotation=rots[i % K]))
+            tn = timed(lambda i: parallel.optimal_transport_pixel_sharded(p_loc, s_loc, mode, rots[i % K], comm, n, n,
+                                                                          out=out_loc))
+            # bit identity of the whole block (equal slices -> one all-gather of the local rows)
+            single = ob.optimal_transport(p4, s4, mode, rotation=rots[0]).view(n, c)
+            parallel.optimal_transport_pixel_sharded(p_loc, s_loc, mode, rots[0], comm, n, n, out=out_loc)
+            same = None
+            if n % (32 * world) == 0:
+                same = bool(torch.equal(comm.all_gather_rows(out_loc), single))
+            else:
+                same = bool(torch.equal(out_loc, single[r0:r0 + rk]))
+            flags = [None] * world
+            dist.all_gather_object(flags, same)
+            out["shapes"][name] = {"n": n, "c": c, "single_gpu_ms": t1, "sharded_ms": tn, "speedup": t1 / tn,
+                                   "strong_efficiency": t1 / tn / world, "bit_identical_on_all_ranks": all(flags),
+                                   "nvlink_bytes_per_step_per_rank": 4 * (2 * c + 2 * 256 * c)}
+            del p, s, p_loc, s_loc, out_loc, single
+            torch.cuda.empty_cache()
+        except Exception as exc:  # noqa: BLE001
+            out["shapes"][name] = f"error: {type(exc).__name__}: {exc}"
+    comm.close()
+    return out
+
+
 def run_ours(a):
     import ctypes as C
 
@@ -510,6 +570,12 @@ def run_ours(a):
                    "h2d_bytes_per_step": 2 * 4 * n * c,
                    "api": "optex_ot_step_host (one synchronous call per step, P and S uploaded each time)"}}
 
+    # ---- N > 1: strong scaling of ONE block, pixel-sharded over the ranks through the C-ABI (optex_ot_step_sharded):
+    #      cdf needs two tiny all-reduces per step (range, histograms) and is bit-identical to one GPU
+    sharded_block = None
+    if world > 1 and not a.no_sharded_block and not sharded:
+        sharded_block = pixel_sharded_block(a, torch, dist, ob, lib, device, rank, world, K, W, barrier, max_over_ranks)
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -588,6 +654,8 @@ def run_ours(a):
                           "tensor_frac": work["flops"] / (ms_step * 1e-3) / 1e12 / pk["bf16_tflops_sustained"],
                           "flops": work["flops"], "bytes": work["bytes"]},
     }
+    if sharded_block is not None:
+        line["sharded"] = sharded_block
     if kernel_sum and kernel_sum / ms_step < 0.8:
         line["warning"] = (f"kernel_sum/ms_per_step = {kernel_sum / ms_step:.2f} < 0.8: the timed region holds time "
                            "that is in no kernel (host enqueue or launch gaps) - read value with care")

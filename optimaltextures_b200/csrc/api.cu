@@ -257,6 +257,14 @@ struct ResidentStyle {
 static ResidentStyle g_style;
 
 __global__ void fence_kernel() {}
+// An ORDINARY launch (no programmatic serialisation): it runs only after every earlier kernel of the stream has fully
+// completed, so an event recorded behind it - the fork / join of a side stream, a timing event - cannot be reached
+// while a PDL-launched predecessor is still draining.
+int stream_fence(cudaStream_t st) {
+    fence_kernel<<<1, 32, 0, st>>>();
+    OPTEX_LAUNCH_CHECK("fence_kernel");
+    return OPTEX_OK;
+}
 
 }  // namespace optex
 
@@ -500,9 +508,7 @@ extern "C" int optex_ot_step_profile(const float *P, const float *S, const float
 // stream - including PDL-launched ones, whose completion an event alone does not imply - has fully drained.
 extern "C" int optex_fence(void *stream) {
     OPTEX_TRY(require_sm100());
-    fence_kernel<<<1, 32, 0, (cudaStream_t)stream>>>();
-    OPTEX_LAUNCH_CHECK("fence_kernel");
-    return OPTEX_OK;
+    return stream_fence((cudaStream_t)stream);
 }
 
 // The step on this rank's rows (include/optex_b200.h "multi-GPU"; sharded.cu has the NCCL plumbing).

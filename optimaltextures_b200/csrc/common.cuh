@@ -78,6 +78,7 @@ struct Arena {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 bool pdl_enabled();  // optex_set_pdl(); defined in api.cu
+int stream_fence(cudaStream_t st);  // ordinary empty kernel: full completion of everything before it (api.cu)
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,

@@ -665,6 +665,9 @@ int cov_ot_step(const float *P, const float *S, const float *R, float *out, int 
     SideStream *side;
     OPTEX_TRY(side_stream(&side));
     cudaStream_t sb = side->stream;
+    // the moments above were launched with programmatic serialisation: fence before the fork event, so the side stream
+    // cannot start on sig_s / mu_s while their producers are still draining (and likewise before the join)
+    if (pdl_enabled()) OPTEX_TRY(stream_fence(st));
     OPTEX_CUDA(cudaEventRecord(side->fork, st));
     OPTEX_CUDA(cudaStreamWaitEvent(sb, side->fork, 0));
     int rc_b = OPTEX_OK;
@@ -680,6 +683,7 @@ int cov_ot_step(const float *P, const float *S, const float *R, float *out, int 
     };
     rc_b = side_chain();
     // always join, also on an error above: the side stream must not be left forked inside a capture
+    if (pdl_enabled() && rc_b == OPTEX_OK) rc_b = stream_fence(sb);
     cudaError_t join_err = cudaEventRecord(side->join, sb);
     // ---- the pastiche-side chain on the caller's stream
     auto main_chain = [&]() -> int {

@@ -394,12 +394,16 @@ def fit_pca_many(tensors, *, round_k_to: int = 1, bases=None, warm=None, sweeps_
     for (x, c, *_), b, w in zip(jobs, bases, warm):
         _check_basis(b, c, dev, w)
     with torch.cuda.device(dev):
+        # the producers of `tensors` were launched with programmatic serialisation: an ordinary fence kernel in front
+        # of the fork (and of every join) keeps the cross-stream events behind their complete drain
+        call("optex_fence", C.c_void_p(cur.cuda_stream))
         for st, (x, c, vecs, sigma, k_dev, wsb), b, w in zip(streams, jobs, bases, warm):
             st.wait_stream(cur)
             call("optex_fit_pca_warm", ptr(x), x.shape[0], c, ptr(vecs), ptr(sigma), ptr(k_dev),
                  None if b is None else ptr(b), 1 if w else 0, C.c_void_p(k_dev.data_ptr() + 4), ptr(wsb), wsb.numel(),
                  C.c_void_p(st.cuda_stream))
         for st in streams[:len(jobs)]:
+            call("optex_fence", C.c_void_p(st.cuda_stream))
             cur.wait_stream(st)
     out = []
     ks_sw = torch.stack([j[4] for j in jobs]).tolist()     # the one synchronisation: [k, sweeps] per solve
