@@ -415,17 +415,21 @@ def run_ours(a):
                                   device=device)
             self.rot_ws = torch.empty(lib.optex_rotations_workspace_bytes(c, K), dtype=torch.uint8, device=device)
             self.rots = torch.empty(K, c, c, dtype=torch.float32, device=device)
+            self.rsplit = torch.empty(K, 2, c, c, dtype=torch.float32, device=device) if c % 4 == 0 else None
             mk = lambda ts: (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])  # noqa: E731
             self.P, self.S, self.O = mk([p for p, _ in self.sets]), mk([s for _, s in self.sets]), mk(self.outs)
 
         def gen_rotations(self, first, seed=1234):
             call("optex_random_rotations", ptr(self.rots), self.c, K, seed, first, None, ptr(self.rot_ws),
                  self.rot_ws.numel(), st)
+            if self.rsplit is not None:      # tf32 hi / lo planes of the K rotations, one launch (part of the draw)
+                call("optex_split_rotations", ptr(self.rots), K, self.c, ptr(self.rsplit), st)
 
         def steps(self, first=0, count=None):
             """K independent steps enqueued by ONE C call (optex_ot_steps): Python is not in the loop."""
-            call("optex_ot_steps", self.P, self.S, len(self.sets), ptr(self.rots), self.O, 2, K if count is None else count,
-                 first, 1, self.n, 1, self.n, self.c, self.mid, 1.0, ptr(self.ws), self.ws.numel(), st)
+            call("optex_ot_steps", self.P, self.S, len(self.sets), ptr(self.rots), ptr(self.rsplit), self.O, 2,
+                 K if count is None else count, first, 1, self.n, 1, self.n, self.c, self.mid, 1.0, ptr(self.ws),
+                 self.ws.numel(), st)
 
         def region(self):
             """rotation draw for K steps + K steps + drain fence; returns (device ms, host enqueue ms)."""
@@ -517,6 +521,10 @@ def run_ours(a):
         for j, name in enumerate(names):
             if acc[j]:
                 stages[name] = statistics.mean(acc[j])
+        if stage_launches.get("rotate_forward_S") == 0:     # both forward rotations ran as ONE launch
+            stages["rotate_forward_P_and_S"] = stages.pop("rotate_forward_P") + stages.pop("rotate_forward_S")
+            stage_launches["rotate_forward_P_and_S"] = stage_launches.pop("rotate_forward_P")
+            stage_launches.pop("rotate_forward_S")
 
     # ---- e2e: host buffers through optex_ot_step_host_async (H2D + step + D2H per call)
     e2e = None
@@ -596,7 +604,7 @@ def run_ours(a):
     if stages:
         alg = {
             "rotate_forward_P": ("tensor", 2.0 * c * c * n), "rotate_forward_S": ("tensor", 2.0 * c * c * n),
-            "rotate_inverse": ("tensor", 2.0 * c * c * n),
+            "rotate_inverse": ("tensor", 2.0 * c * c * n), "rotate_forward_P_and_S": ("tensor", 4.0 * c * c * n),
             f"{a.mode}_match": ("hbm", 4.0 * c * (n + n) + 4.0 * c * n),
             "prepare_split_R": ("hbm", 4.0 * c * c * 3),
             f"{a.mode}_step": ("tensor", work["flops"]),

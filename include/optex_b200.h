@@ -136,11 +136,16 @@ int optex_ot_host_set_style(const float *S, int b_s, int64_t hw_s, int c, void *
 /* `steps` INDEPENDENT OT steps (optex.py:167-177 each) enqueued by one call - e.g. a batch of syntheses standing at
  * the same layer: step i transports P[(first + i) % n_sets] towards S[(first + i) % n_sets] with rotation
  * R_all[i] ([steps, c, c] on the device) into out[(first + i) % n_out].  P / S / out are HOST arrays of device
- * pointers.  Same arithmetic and kernels as `steps` optex_ot_step calls, without a host round trip per step. */
+ * pointers.  R_split (may be NULL): the tf32 hi / lo planes of the same rotations, [steps][2][c][c], from
+ * optex_split_rotations - the per-step split launch then disappears.  Same arithmetic and kernels as `steps`
+ * optex_ot_step calls, without a host round trip per step. */
 int optex_ot_steps(const float *const *P, const float *const *S, int n_sets, const float *R_all,
-                   float *const *out, int n_out, int steps, int first, int b_p, int64_t hw_p,
-                   int b_s, int64_t hw_s, int c, int mode, float eps, void *workspace,
-                   size_t workspace_bytes, void *stream);
+                   const float *R_split, float *const *out, int n_out, int steps, int first,
+                   int b_p, int64_t hw_p, int b_s, int64_t hw_s, int c, int mode, float eps,
+                   void *workspace, size_t workspace_bytes, void *stream);
+/* out[i] = [tf32_hi(R_i) | tf32_lo(R_i)] for `count` rotations [c, c] (c % 4 == 0) in one launch: the operand halves of
+ * the 3xTF32 rotation GEMMs, batched like the draw (optex_random_rotations).  out: [count][2][c][c] floats. */
+int optex_split_rotations(const float *R_all, int count, int c, float *out, void *stream);
 
 /* One optex_ot_step with a CUDA event between its stages - the step's own launches, in place, with PDL off for the
  * call; synchronises `stream`.  Measurement aid (no reference counterpart).  Per-channel modes report 5 stages:

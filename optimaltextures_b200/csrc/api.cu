@@ -158,6 +158,9 @@ static int check_step_args(const char *fn, const void *P, const void *S, const v
     return OPTEX_OK;
 }
 
+// tf32 hi / lo planes [2][c][c] of the rotation the next ot_step_impl call receives (optex_ot_steps with R_split)
+static thread_local const float *g_r_split = nullptr;
+
 // The step proper.  P may alias out (P is dead once the forward rotation has run).
 static int ot_step_impl(const float *P, const float *S, const float *R, float *out, int b_p, int64_t hw_p,
                         int b_s, int64_t hw_s, int c, int mode, float eps, const float *content, float strength,
@@ -191,9 +194,14 @@ static int ot_step_impl(const float *P, const float *S, const float *R, float *o
     prof_mark(st);
     if (tc3) {
         const bool fold = mode == OPTEX_MODE_CDF && !cdf_uses_channel_kernel(c, n_p, n_s, 256);
-        OPTEX_TRY(gemm_tc_split_and_fill(R, r_hi, r_lo, (int64_t)c * c, fold ? (uint32_t *)mw : nullptr,
-                                         fold ? 2 * (int64_t)c : 0, 0xffffffffu, st));
-        gemm_tc_set_presplit(R, r_hi, r_lo);
+        if (g_r_split) {   // the caller split this rotation already (optex_split_rotations): no launch here
+            if (fold) OPTEX_TRY(fill_u32((uint32_t *)mw, 2 * (int64_t)c, 0xffffffffu, st));
+            gemm_tc_set_presplit(R, g_r_split, g_r_split + (size_t)c * c);
+        } else {
+            OPTEX_TRY(gemm_tc_split_and_fill(R, r_hi, r_lo, (int64_t)c * c, fold ? (uint32_t *)mw : nullptr,
+                                             fold ? 2 * (int64_t)c : 0, 0xffffffffu, st));
+            gemm_tc_set_presplit(R, r_hi, r_lo);
+        }
     }
     uint32_t *minmax = nullptr;
     if (mode == OPTEX_MODE_CDF && !cdf_uses_channel_kernel(c, n_p, n_s, 256)) {
@@ -205,10 +213,22 @@ static int ot_step_impl(const float *P, const float *S, const float *R, float *o
     }
     prof_mark(st);  // stage 0: prepare (split R, reset range slots)
     bool r1 = false, r2 = false;
-    OPTEX_TRY(rotate_forward(P, R, rp, n_p, c, true, st, 0, -1, minmax, &r1));
-    prof_mark(st);  // stage 1: forward rotation of the pastiche
-    OPTEX_TRY(rotate_forward(S, R, rs, n_s, c, true, st, 0, -1, minmax, &r2));
-    prof_mark(st);  // stage 2: forward rotation of the style
+    // both forward rotations in ONE launch when the shapes take the paired tensor-core form (optex.py:170-171)
+    int rc2 = OPTEX_ENOTSUP;
+    static const char *no_dual = getenv("OPTEX_NO_DUAL_FORWARD");
+    if (tc3 && !(no_dual && atoi(no_dual)))
+        rc2 = gemm_tc_rotate_forward2(P, n_p, S, n_s, R, rp, rs, c, 3, st, minmax);
+    if (rc2 == OPTEX_OK) {
+        r1 = r2 = minmax != nullptr;
+        prof_mark(st);  // stage 1: forward rotation of the pastiche and the style (one launch)
+        prof_mark(st);  // stage 2: (empty)
+    } else {
+        if (rc2 != OPTEX_ENOTSUP) return rc2;
+        OPTEX_TRY(rotate_forward(P, R, rp, n_p, c, true, st, 0, -1, minmax, &r1));
+        prof_mark(st);  // stage 1: forward rotation of the pastiche
+        OPTEX_TRY(rotate_forward(S, R, rs, n_s, c, true, st, 0, -1, minmax, &r2));
+        prof_mark(st);  // stage 2: forward rotation of the style
+    }
     if (mode == OPTEX_MODE_CDF)
         OPTEX_TRY(cdf_match_core(rp, rs, mt, c, n_p, n_s, 256, nullptr, mw, mws, r1 && r2, st));
     else
@@ -446,9 +466,9 @@ extern "C" int optex_ot_host_set_style(const float *S, int b_s, int64_t hw_s, in
 // reference's own loop, optex.py:112-113, without a host round trip per step): step i transports
 // P[(first + i) % n_sets] towards S[(first + i) % n_sets] with rotation R_all[i] into out[(first + i) % n_out].
 extern "C" int optex_ot_steps(const float *const *P, const float *const *S, int n_sets, const float *R_all,
-                              float *const *out, int n_out, int steps, int first, int b_p, int64_t hw_p, int b_s,
-                              int64_t hw_s, int c, int mode, float eps, void *workspace, size_t workspace_bytes,
-                              void *stream) {
+                              const float *R_split, float *const *out, int n_out, int steps, int first, int b_p,
+                              int64_t hw_p, int b_s, int64_t hw_s, int c, int mode, float eps, void *workspace,
+                              size_t workspace_bytes, void *stream) {
     OPTEX_TRY(require_sm100());
     if (!P || !S || !out || !R_all || n_sets < 1 || n_out < 1 || steps < 0 || first < 0) {
         set_error("optex_ot_steps: NULL table or empty set list");
@@ -461,10 +481,24 @@ extern "C" int optex_ot_steps(const float *const *P, const float *const *S, int 
             set_error("optex_ot_steps: out must not alias an input");
             return OPTEX_EINVAL;
         }
-        OPTEX_TRY(ot_step_impl(P[k], S[k], R_all + (size_t)i * c * c, out[o], b_p, hw_p, b_s, hw_s, c, mode, eps, nullptr,
-                               0.f, workspace, workspace_bytes, (cudaStream_t)stream));
+        g_r_split = R_split ? R_split + (size_t)i * 2 * c * c : nullptr;
+        int rc = ot_step_impl(P[k], S[k], R_all + (size_t)i * c * c, out[o], b_p, hw_p, b_s, hw_s, c, mode, eps, nullptr,
+                              0.f, workspace, workspace_bytes, (cudaStream_t)stream);
+        g_r_split = nullptr;
+        OPTEX_TRY(rc);
     }
     return OPTEX_OK;
+}
+
+// tf32 hi / lo planes of `count` rotations in ONE launch: out[i] = [hi(R_i) | lo(R_i)], each [c, c] (the 3xTF32
+// operand halves of the rotation GEMMs; c % 4 == 0).  Batched like the draw itself (optex_random_rotations).
+extern "C" int optex_split_rotations(const float *R_all, int count, int c, float *out, void *stream) {
+    OPTEX_TRY(require_sm100());
+    if (!R_all || !out || count < 1 || c < 1 || c % 4 != 0) {
+        set_error("optex_split_rotations: NULL pointer, empty batch or c %% 4 != 0");
+        return OPTEX_EINVAL;
+    }
+    return gemm_tc_split_batch(R_all, out, count, (int64_t)c * c, (cudaStream_t)stream);
 }
 
 // One OT step with an event between its stages (measurement aid for bench.py: the in-step launches exactly as

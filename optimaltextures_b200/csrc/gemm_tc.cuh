@@ -52,6 +52,10 @@ struct TcGemm {
     float *D_z[4];
     float *resid_z[4];
     const float *skip_z[4];
+    // a second problem with the same B, N, K in the same launch (K-major A only; forward rotation of P and S)
+    const float *A2;
+    int64_t M2, ldd2;
+    float *D2;
 };
 // selects which of the two library-owned hi/lo scratch buffers the calling thread's GEMMs use (pipelined callers)
 void gemm_tc_set_scratch_slot(int slot);
@@ -59,6 +63,7 @@ void gemm_tc_set_trace(unsigned long long *device_buf);  // debug: 64 x u64 cloc
 // 3xTF32 with a pre-split B: while registered (thread-local), gemm_tc() calls whose B pointer equals `src` use the
 // given hi / lo halves instead of splitting B again (src == nullptr clears it)
 void gemm_tc_set_presplit(const float *src, const float *hi, const float *lo);
+int gemm_tc_split_batch(const float *x, float *out, int count, int64_t n, cudaStream_t st);
 int gemm_tc_split_and_fill(const float *x, float *hi, float *lo, int64_t n, uint32_t *fill, int64_t fill_n,
                            uint32_t fill_v, cudaStream_t st);
 // OPTEX_OK, OPTEX_ENOTSUP (shape/alignment outside the TMA constraints) or an error
@@ -67,6 +72,8 @@ int gemm_tc(const TcGemm &g, cudaStream_t st);
 // dst = X R  (transposed: dst[c, n], else dst[n, c]);  terms = 1 (TF32) or 3 (3xTF32 split)
 int gemm_tc_rotate_forward(const float *X, const float *R, float *dst, int64_t n, int c, bool transposed,
                            int terms, cudaStream_t st, int c0 = 0, int nc = -1, uint32_t *colrange = nullptr);
+int gemm_tc_rotate_forward2(const float *X1, int64_t n1, const float *X2, int64_t n2, const float *R, float *dst1,
+                            float *dst2, int c, int terms, cudaStream_t st, uint32_t *colrange = nullptr);
 // out[n, j] = sum_c M(n, c) R[j, c] (+ content blend);  M channel-major [c, n] or NHWC [n, c]
 int gemm_tc_rotate_inverse(const float *M, bool m_channel_major, const float *R, float *out, int64_t n, int c,
                            const float *content, float strength, int terms, cudaStream_t st);

@@ -327,6 +327,11 @@ struct Params {
     int a_tmem;           // conv_a && !conv_b: the converters write the hi / lo halves of A to TENSOR memory
     int stages_a;         // a_tmem: depth of the raw-A shared-memory ring (p.stages is the B ring then)
     int tma_store;        // CG == 2: the epilogue stages 128 x 32 tiles in shared memory and writes them with TMA
+    // dual (a_tmem launches): a SECOND problem with the same B, N and K - the forward rotations of the pastiche and of
+    // the style block in one launch (optex.py:170-171).  Its A map travels in tmA_lo (unused by the TMEM-A form), its
+    // output map in tmD2; tiles of problem 0 come first in the tile list.
+    int64_t M2, ldd2;
+    float *D2;
 };
 
 // ------------------------------------------------------------------ the kernel
@@ -355,7 +360,7 @@ template <int BLOCK_N, bool A_MN, bool B_MN, bool D_TRANS, int BK, int CG = 1>
 __global__ void __launch_bounds__(NTHREADS, 1)
 rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                    const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-                   const __grid_constant__ CUtensorMap tmD, const Params p) {
+                   const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmD2, const Params p) {
     constexpr uint32_t A_TILE = BLOCK_M * BK * 4;
     constexpr uint32_t B_TILE = (BLOCK_N / CG) * BK * 4;   // what THIS CTA loads per stage and half (hi / lo)
     static_assert(BK == 32 || BK == 16, "stage depth");
@@ -396,7 +401,8 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     const int n_tiles_n = (int)((p.N + BLOCK_N - 1) / BLOCK_N);
     const int n_tiles_m = (int)((p.M + BLOCK_M * CG - 1) / (BLOCK_M * CG));
     const int tiles_per_z = n_tiles_m * n_tiles_n;
-    const int num_tiles = tiles_per_z * p.nz;
+    const int tiles_dual = (int)((p.M2 + BLOCK_M * CG - 1) / (BLOCK_M * CG)) * n_tiles_n;   // second problem (or 0)
+    const int num_tiles = tiles_per_z * p.nz + tiles_dual;
     // 1024-byte alignment of the dynamic smem base (swizzle atoms)
     uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~uintptr_t(1023));
     uint8_t *a_ring = tiles + (size_t)p.stages * stage_bytes;
@@ -409,6 +415,7 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         prefetch_tmap(&tmA_hi);
         prefetch_tmap(&tmB_hi);
         if (CG == 2 && p.tma_store) prefetch_tmap(&tmD);
+        if (p.M2 > 0) { prefetch_tmap(&tmA_lo); if (CG == 2 && p.tma_store) prefetch_tmap(&tmD2); }
         if (p.terms == 3) {
             if (!p.conv_a) prefetch_tmap(&tmA_lo);
             if (!p.conv_b) prefetch_tmap(&tmB_lo);
@@ -457,14 +464,16 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[66] = clock64();
 
     // tile -> (z, m, n): n fastest, so CTAs running side by side share the rows of the big A operand in L2
+    // (dual launches have nz == 1: z == 1 then means "the second problem")
     auto tile_coords = [&](int tile, int &m0, int &n0, int &z) {
-        z = tile / tiles_per_z;
+        z = tiles_dual > 0 ? (tile >= tiles_per_z ? 1 : 0) : tile / tiles_per_z;
         const int r = tile - z * tiles_per_z;
         m0 = (r / n_tiles_n) * (BLOCK_M * CG) + (int)crank * BLOCK_M;   // this CTA's rows of the (pair's) tile
         n0 = (r % n_tiles_n) * BLOCK_N;
     };
     const int tile0 = (int)blockIdx.x / CG, tile_step = (int)gridDim.x / CG;   // pairs walk the tile list together
     auto k_range = [&](int z, int64_t &k_begin, int &num_kb) {
+        if (tiles_dual > 0) z = 0;   // both problems of a dual launch span the whole K
         k_begin = (int64_t)z * p.k_per_z;
         const int64_t k_len = p.k_per_z > 0 ? (p.K - k_begin < p.k_per_z ? p.K - k_begin : p.k_per_z) : p.K;
         num_kb = (int)((k_len + BK - 1) / BK);
@@ -506,8 +515,9 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                             if (tr) p.trace[kb * 4 + 0] = clock64();
                             uint8_t *a_dst = a_ring + (size_t)sa * A_TILE;
                             mbar_expect_tx(&raw_bar[sa], A_TILE);
-                            if (A_MN) tma_load_3d(&tmA_hi, &raw_bar[sa], a_dst, 0, k0 + ao, m0 / 32, p.a_hint);
-                            else tma_load_2d(&tmA_hi, &raw_bar[sa], a_dst, k0, m0 + ao, p.a_hint);
+                            const CUtensorMap *ma = (tiles_dual > 0 && z == 1) ? &tmA_lo : &tmA_hi;
+                            if (A_MN) tma_load_3d(ma, &raw_bar[sa], a_dst, 0, k0 + ao, m0 / 32, p.a_hint);
+                            else tma_load_2d(ma, &raw_bar[sa], a_dst, k0, m0 + ao, p.a_hint);
                             if (++sa == p.stages_a) { sa = 0; pha ^= 1; }
                             // pre-split B hi / lo -> the main ring (freed by the MMAs)
                             stamp(0, kbi, 2);
@@ -800,7 +810,10 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
             if (z_skipped(z)) continue;
             const int tcur = titer++;
             acc_of(tcur, acc, aph);
-            float *const Dz = p.D + (p.batch > 0 ? p.d_off[z] : (int64_t)z * p.d_z_stride);
+            const bool second = tiles_dual > 0 && z == 1;
+            float *const Dz = second ? p.D2 : p.D + (p.batch > 0 ? p.d_off[z] : (int64_t)z * p.d_z_stride);
+            const int64_t Mz = second ? p.M2 : p.M, lddz = second ? p.ldd2 : p.ldd;
+            const CUtensorMap *const dmap = second ? &tmD2 : &tmD;
             float *const resid_max = p.batch > 0 ? p.resid_z[z] : p.resid_max;
             if (warp == EPI_WARP0 && lane == 0) stamp(3, tcur, 0);
             mbar_wait(&tfull_bar[acc], aph);
@@ -854,11 +867,11 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                             asm volatile("st.shared.f32 [%0], %1;" ::"r"(sp + (uint32_t)j * 512u),
                                          "f"(p.alpha * __uint_as_float(v[j]))
                                          : "memory");
-                    } else if (row < p.M) {
+                    } else if (row < Mz) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             int64_t n = (int64_t)n0 + col + j;
-                            if (n < p.N) Dz[n * p.ldd + row] = p.alpha * __uint_as_float(v[j]);
+                            if (n < p.N) Dz[n * lddz + row] = p.alpha * __uint_as_float(v[j]);
                         }
                     }
                     if (p.colrange) {
@@ -869,8 +882,8 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const uint32_t u = f2ord(p.alpha * __uint_as_float(v[j]));
-                            const uint32_t a = __reduce_min_sync(0xffffffffu, row < p.M ? u : 0xffffffffu);
-                            const uint32_t b = __reduce_min_sync(0xffffffffu, row < p.M ? ~u : 0xffffffffu);
+                            const uint32_t a = __reduce_min_sync(0xffffffffu, row < Mz ? u : 0xffffffffu);
+                            const uint32_t b = __reduce_min_sync(0xffffffffu, row < Mz ? ~u : 0xffffffffu);
                             if (lane == j) { mn = a; mxn = b; }
                         }
                         const int64_t n = (int64_t)n0 + col + lane;
@@ -882,12 +895,12 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                     if (staged) {
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         named_bar_sync(1 + egrp, 128);
-                        if (issuer) tma_store_2d(&tmD, stg, m0, n0 + col);   // x = pixel, y = channel
+                        if (issuer) tma_store_2d(dmap, stg, m0, n0 + col);   // x = pixel, y = channel
                     }
-                } else if (row < p.M || staged) {
-                    float *dp = Dz + row * p.ldd + n0 + col;
-                    const float *bp = p.blend ? p.blend + row * p.ldd + n0 + col : nullptr;
-                    const float *bias = (p.bias && row < p.M) ? p.bias + (row / p.bias_hw) * p.bias_ld + n0 + col : nullptr;
+                } else if (row < Mz || staged) {
+                    float *dp = Dz + row * lddz + n0 + col;
+                    const float *bp = p.blend ? p.blend + row * lddz + n0 + col : nullptr;
+                    const float *bias = (p.bias && row < Mz) ? p.bias + (row / p.bias_hw) * p.bias_ld + n0 + col : nullptr;
                     // the rotations use none of the optional epilogue terms: their per-element tests (five runtime
                     // conditions x 64 values per thread) cost 9.5 k cycles per 32-column chunk - measured with the stamps
                     const bool extras = resid_max != nullptr || p.diag != 0.f || bias != nullptr || p.relu != 0 ||
@@ -896,7 +909,7 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                     for (int j = 0; j < 32; ++j) {
                         if (!extras) break;
                         float o = p.alpha * __uint_as_float(v[j]);
-                        if (resid_max && row < p.M && n0 + col + j < p.N) {
+                        if (resid_max && row < Mz && n0 + col + j < p.N) {
                             float d = fabsf(__uint_as_float(v[j]) - (row == (int64_t)n0 + col + j ? 1.f : 0.f));
                             if (!(d == d)) d = INFINITY;
                             rres = fmaxf(rres, d);
@@ -924,7 +937,7 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                         if (es) stamp(3, 4 + tcur * 2 + ch, 2);
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         named_bar_sync(1 + egrp, 128);
-                        if (issuer) tma_store_2d(&tmD, stg, n0 + col, m0);   // x = column, y = row
+                        if (issuer) tma_store_2d(dmap, stg, n0 + col, m0);   // x = column, y = row
                         if (es) stamp(3, 4 + tcur * 2 + ch, 3);
                     } else if (n0 + col + 32 <= p.N) {
                         // 256-bit accesses: every store is one full 32-byte sector of this thread's output row
@@ -958,7 +971,7 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                     }
                 }
             }
-            if (!D_TRANS && p.rowrange && row < p.M) {
+            if (!D_TRANS && p.rowrange && row < Mz) {
                 atomicMin(p.rowrange + 2 * row, rmn);
                 atomicMin(p.rowrange + 2 * row + 1, rmx);
             }
@@ -1147,7 +1160,7 @@ int split(const float *x, float *hi, float *lo, int64_t n, cudaStream_t st) {
 
 template <int BLOCK_N, bool A_MN, bool B_MN, bool D_TRANS, int BK, int CG = 1>
 int launch(const CUtensorMap &ah, const CUtensorMap &al, const CUtensorMap &bh, const CUtensorMap &bl,
-           const CUtensorMap &dm, Params p, int nz, cudaStream_t st) {
+           const CUtensorMap &dm, const CUtensorMap &dm2, Params p, int nz, cudaStream_t st) {
     constexpr int A_TILE = BLOCK_M * BK * 4, B_TILE = (BLOCK_N / CG) * BK * 4;
     size_t smem;
     if (CG != 2) p.tma_store = 0;
@@ -1172,11 +1185,13 @@ int launch(const CUtensorMap &ah, const CUtensorMap &al, const CUtensorMap &bh, 
     auto kern = rotate_gemm_kernel<BLOCK_N, A_MN, B_MN, D_TRANS, BK, CG>;
     static PerDeviceOnce attr_once1;
     OPTEX_TRY(ensure_dyn_smem(attr_once1, kern, (int)(SMEM_BUDGET + 1024)));
-    const int64_t num_tiles = ((p.M + BLOCK_M * CG - 1) / (BLOCK_M * CG)) * ((p.N + BLOCK_N - 1) / BLOCK_N) * nz;
+    if (!(p.a_tmem && nz == 1 && p.batch == 0)) p.M2 = 0;   // dual problems: TMEM-A form only
+    const int64_t num_tiles = (((p.M + BLOCK_M * CG - 1) / (BLOCK_M * CG)) * nz + (p.M2 + BLOCK_M * CG - 1) / (BLOCK_M * CG)) *
+                              ((p.N + BLOCK_N - 1) / BLOCK_N);
     const int sms = sm_count();
     if (CG == 1) {
         dim3 grid((unsigned)(num_tiles < sms ? num_tiles : sms));  // persistent: one CTA per SM walks the tile list
-        launch_pdl(kern, grid, dim3(NTHREADS), smem, st, ah, al, bh, bl, dm, p);
+        launch_pdl(kern, grid, dim3(NTHREADS), smem, st, ah, al, bh, bl, dm, dm2, p);
     } else {
         // persistent pairs: one cluster of two CTAs per SM pair
         const int64_t pairs = num_tiles < sms / 2 ? num_tiles : sms / 2;
@@ -1194,7 +1209,7 @@ int launch(const CUtensorMap &ah, const CUtensorMap &al, const CUtensorMap &bh, 
         attr[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = pdl_enabled() ? 2 : 1;
-        OPTEX_CUDA(cudaLaunchKernelEx(&cfg, kern, ah, al, bh, bl, dm, p));
+        OPTEX_CUDA(cudaLaunchKernelEx(&cfg, kern, ah, al, bh, bl, dm, dm2, p));
     }
     OPTEX_LAUNCH_CHECK("rotate_gemm_kernel");
     return OPTEX_OK;
@@ -1202,12 +1217,12 @@ int launch(const CUtensorMap &ah, const CUtensorMap &al, const CUtensorMap &bh, 
 
 template <bool A_MN, bool B_MN, bool D_TRANS>
 int launch_n(int block_n, int cg, const CUtensorMap &ah, const CUtensorMap &al, const CUtensorMap &bh,
-             const CUtensorMap &bl, const CUtensorMap &dm, Params p, int nz, cudaStream_t st) {
+             const CUtensorMap &bl, const CUtensorMap &dm, const CUtensorMap &dm2, Params p, int nz, cudaStream_t st) {
     // (a BK = 16 / 4-stage variant of the 3xTF32 wide tile exists as a template option; it measured slower: 64 vs 59 us)
-    if (block_n == 64) return launch<64, A_MN, B_MN, D_TRANS, 32>(ah, al, bh, bl, dm, p, nz, st);
-    if (block_n == 128) return launch<128, A_MN, B_MN, D_TRANS, 32>(ah, al, bh, bl, dm, p, nz, st);
-    if (cg == 2) return launch<256, A_MN, B_MN, D_TRANS, 32, 2>(ah, al, bh, bl, dm, p, nz, st);
-    return launch<256, A_MN, B_MN, D_TRANS, 32>(ah, al, bh, bl, dm, p, nz, st);
+    if (block_n == 64) return launch<64, A_MN, B_MN, D_TRANS, 32>(ah, al, bh, bl, dm, dm2, p, nz, st);
+    if (block_n == 128) return launch<128, A_MN, B_MN, D_TRANS, 32>(ah, al, bh, bl, dm, dm2, p, nz, st);
+    if (cg == 2) return launch<256, A_MN, B_MN, D_TRANS, 32, 2>(ah, al, bh, bl, dm, dm2, p, nz, st);
+    return launch<256, A_MN, B_MN, D_TRANS, 32>(ah, al, bh, bl, dm, dm2, p, nz, st);
 }
 
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -1234,6 +1249,31 @@ void gemm_tc_set_trace(unsigned long long *t) { g_trace = t; }
 void gemm_tc_set_scratch_slot(int slot) { g_scratch_slot = slot & 3; }
 
 void gemm_tc_set_presplit(const float *src, const float *hi, const float *lo) { g_presplit = {src, hi, lo}; }
+
+// `count` matrices of n floats each: out[i] = [hi_i (n floats) | lo_i (n floats)]
+__global__ void split_batch_kernel(const float4 *__restrict__ x, float4 *__restrict__ out, int64_t n4, int count) {
+    pdl_wait();
+    const int64_t total = n4 * count;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t m = i / n4, e = i - m * n4;
+        float4 v = __ldg(x + i), h, l;
+        split_tf32(v.x, h.x, l.x);
+        split_tf32(v.y, h.y, l.y);
+        split_tf32(v.z, h.z, l.z);
+        split_tf32(v.w, h.w, l.w);
+        out[m * 2 * n4 + e] = h;
+        out[m * 2 * n4 + n4 + e] = l;
+    }
+}
+int gemm_tc_split_batch(const float *x, float *out, int count, int64_t n, cudaStream_t st) {
+    const int64_t n4 = n / 4;
+    int64_t blocks = (n4 * count + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    launch_pdl(split_batch_kernel, dim3((unsigned)blocks), dim3(256), 0, st, (const float4 *)x, (float4 *)out, n4, count);
+    OPTEX_LAUNCH_CHECK("split_batch_kernel");
+    return OPTEX_OK;
+}
 
 // hi/lo split of x (n floats, n % 4 == 0) and, in the same launch, fill of a small u32 array (the cdf range slots)
 int gemm_tc_split_and_fill(const float *x, float *hi, float *lo, int64_t n, uint32_t *fill, int64_t fill_n,
@@ -1293,8 +1333,8 @@ static int gemm_tc_batched(const TcGemm &g, cudaStream_t st) {
     p.bias_hw = 1;
     p.a_hint = p.b_hint = L2_EVICT_NORMAL;
     p.trace = nullptr;
-    if (!g.b_mn) return launch_n<false, false, false>(bn, 1, ah, ah, bh, bh, ah, p, nb, st);
-    return launch_n<false, true, false>(bn, 1, ah, ah, bh, bh, ah, p, nb, st);
+    if (!g.b_mn) return launch_n<false, false, false>(bn, 1, ah, ah, bh, bh, ah, ah, p, nb, st);
+    return launch_n<false, true, false>(bn, 1, ah, ah, bh, bh, ah, ah, p, nb, st);
 }
 
 int gemm_tc(const TcGemm &g, cudaStream_t st) {
@@ -1393,6 +1433,14 @@ int gemm_tc(const TcGemm &g, cudaStream_t st) {
     // a big A operand is streamed exactly once (n_tiles_n CTAs read it at the same time); B is re-read by every tile
     p.a_hint = (g.M > 4096 && g.stream_a) ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
     p.b_hint = g.M > 4096 ? L2_EVICT_LAST : L2_EVICT_NORMAL;
+    // dual launch (forward rotation of the pastiche AND the style block): second A map in `al`, second output map
+    CUtensorMap dm2 = ah;
+    const bool dual = g.A2 != nullptr && g.M2 > 0 && a_tmem && nz == 1 && !g.a_mn && aligned16(g.A2) && aligned16(g.D2);
+    if (g.A2 != nullptr && !dual) return OPTEX_ENOTSUP;
+    if (dual) {
+        OPTEX_TRY(make_map_kmajor(&al, g.A2, g.M2, g.K, BLOCK_M, bk));
+        p.M2 = g.M2; p.ldd2 = g.ldd2; p.D2 = g.D2;
+    }
     // TMA-store epilogue (pairs only): needs 16-byte pitches; the blend reads content with the direct-store code
     CUtensorMap dm = ah;
     static const char *no_tma_store = getenv("OPTEX_NO_TMA_STORE");
@@ -1400,12 +1448,17 @@ int gemm_tc(const TcGemm &g, cudaStream_t st) {
         if (g.d_trans) OPTEX_TRY(make_map_out(&dm, g.D, g.N, g.M, g.ldd, BLOCK_M, 32, false));   // D^T [channel][pixel]
         else OPTEX_TRY(make_map_out(&dm, g.D, g.M, g.N, g.ldd, 32, BLOCK_M, true));
         p.tma_store = 1;
+        if (dual) {
+            if (g.ldd2 % 4 != 0) return OPTEX_ENOTSUP;
+            if (g.d_trans) OPTEX_TRY(make_map_out(&dm2, g.D2, g.N, g.M2, g.ldd2, BLOCK_M, 32, false));
+            else OPTEX_TRY(make_map_out(&dm2, g.D2, g.M2, g.N, g.ldd2, 32, BLOCK_M, true));
+        }
     }
-    if (g.d_trans) return launch_n<false, true, true>(bn, cg, ah, al, bh, bl, dm, p, nz, st);
-    if (!g.a_mn && !g.b_mn) return launch_n<false, false, false>(bn, cg, ah, al, bh, bl, dm, p, nz, st);
-    if (!g.a_mn && g.b_mn) return launch_n<false, true, false>(bn, cg, ah, al, bh, bl, dm, p, nz, st);
-    if (g.a_mn && !g.b_mn) return launch_n<true, false, false>(bn, cg, ah, al, bh, bl, dm, p, nz, st);
-    return launch_n<true, true, false>(bn, cg, ah, al, bh, bl, dm, p, nz, st);
+    if (g.d_trans) return launch_n<false, true, true>(bn, cg, ah, al, bh, bl, dm, dm2, p, nz, st);
+    if (!g.a_mn && !g.b_mn) return launch_n<false, false, false>(bn, cg, ah, al, bh, bl, dm, dm2, p, nz, st);
+    if (!g.a_mn && g.b_mn) return launch_n<false, true, false>(bn, cg, ah, al, bh, bl, dm, dm2, p, nz, st);
+    if (g.a_mn && !g.b_mn) return launch_n<true, false, false>(bn, cg, ah, al, bh, bl, dm, dm2, p, nz, st);
+    return launch_n<true, true, false>(bn, cg, ah, al, bh, bl, dm, dm2, p, nz, st);
 }
 
 int gemm_tc_rotate_forward(const float *X, const float *R, float *dst, int64_t n, int c, bool transposed, int terms,
@@ -1418,6 +1471,18 @@ int gemm_tc_rotate_forward(const float *X, const float *R, float *dst, int64_t n
     g.ldd = transposed ? n : (int64_t)nc;
     g.d_trans = transposed; g.M = n; g.N = nc; g.K = c; g.terms = terms; g.alpha = 1.f; g.colrange = colrange;
     g.stream_a = true;  // the un-rotated block is not touched again in this step
+    return gemm_tc(g, st);
+}
+
+// the forward rotations of two blocks with the same R in one launch (dst_* channel-major); OPTEX_ENOTSUP when the
+// shapes do not take the paired TMEM-A form - the caller then issues two launches
+int gemm_tc_rotate_forward2(const float *X1, int64_t n1, const float *X2, int64_t n2, const float *R, float *dst1,
+                            float *dst2, int c, int terms, cudaStream_t st, uint32_t *colrange) {
+    TcGemm g{};
+    g.A = X1; g.a_mn = false; g.B = R; g.b_col0 = 0; g.b_mn = true; g.ldb = c; g.D = dst1; g.ldd = n1;
+    g.d_trans = true; g.M = n1; g.N = c; g.K = c; g.terms = terms; g.alpha = 1.f; g.colrange = colrange;
+    g.stream_a = true;
+    g.A2 = X2; g.M2 = n2; g.D2 = dst2; g.ldd2 = n2;
     return gemm_tc(g, st);
 }
 

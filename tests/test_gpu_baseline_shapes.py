@@ -178,12 +178,17 @@ def test_step_in_place_stream_matches_steps_api(ob):
         outs = [torch.empty(1, n, 1, c, device="cuda") for _ in range(K)]
         ws = torch.empty(_lib.lib().optex_ot_workspace_bytes(n, n, c, mid), dtype=torch.uint8, device="cuda")
         mk = lambda ts: (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])  # noqa: E731
-        call("optex_ot_steps", mk([p for p, _ in sets]), mk([s for _, s in sets]), 3, ptr(rots), mk(outs), K, K, 0, 1, n,
-             1, n, c, mid, 1.0, ptr(ws), ws.numel(), stream_ptr(dev))
-        torch.cuda.synchronize()
-        for i in range(K):
-            p, s = sets[i % 3]
-            assert torch.equal(outs[i], ob.optimal_transport(p, s, mode, rotation=rots[i]))
+        rsplit = torch.empty(K, 2, c, c, device="cuda")
+        call("optex_split_rotations", ptr(rots), K, c, ptr(rsplit), stream_ptr(dev))
+        for split in (None, rsplit):             # with and without the batched pre-split of the rotations: same bits
+            for o in outs:
+                o.zero_()
+            call("optex_ot_steps", mk([p for p, _ in sets]), mk([s for _, s in sets]), 3, ptr(rots), ptr(split), mk(outs), K,
+                 K, 0, 1, n, 1, n, c, mid, 1.0, ptr(ws), ws.numel(), stream_ptr(dev))
+            torch.cuda.synchronize()
+            for i in range(K):
+                p, s = sets[i % 3]
+                assert torch.equal(outs[i], ob.optimal_transport(p, s, mode, rotation=rots[i]))
 
 
 def test_host_step_with_resident_style(ob):
