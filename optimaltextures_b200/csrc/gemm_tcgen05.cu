@@ -327,6 +327,10 @@ struct Params {
     int a_tmem;           // conv_a && !conv_b: the converters write the hi / lo halves of A to TENSOR memory
     int stages_a;         // a_tmem: depth of the raw-A shared-memory ring (p.stages is the B ring then)
     int tma_store;        // CG == 2: the epilogue stages 128 x 32 tiles in shared memory and writes them with TMA
+    uint32_t range_off;   // byte offset of that array from the aligned tile base
+    int colrange_smem;    // D_TRANS: the range fold accumulates in shared memory (2 * N words behind the tiles) and
+                          // reaches global memory once per CTA - per-tile global atomics on 2 * N addresses serialise
+                          // in L2 (conv1_1 @ 1024^2: 16 384 tiles x 512 atomics on 128 addresses = 0.65 ms)
     // dual (a_tmem launches): a SECOND problem with the same B, N and K - the forward rotations of the pastiche and of
     // the style block in one launch (optex.py:170-171).  Its A map travels in tmA_lo (unused by the TMEM-A form), its
     // output map in tmD2; tiles of problem 0 come first in the tile list.
@@ -407,6 +411,10 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     uint8_t *tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~uintptr_t(1023));
     uint8_t *a_ring = tiles + (size_t)p.stages * stage_bytes;
     uint8_t *epi_stage = a_ring + (size_t)p.stages_a * A_TILE;   // tma_store: EPI_GROUPS staging tiles
+    // colrange_smem: [2 * N] words at the very end of the dynamic allocation (the host reserved them)
+    uint32_t *s_range = reinterpret_cast<uint32_t *>(tiles + p.range_off);
+    if (D_TRANS && p.colrange_smem)
+        for (int i = threadIdx.x; i < 2 * (int)p.N; i += NTHREADS) s_range[i] = 0xffffffffu;   // before the __syncthreads below
     // a_tmem: ONE accumulator (the other 256 columns hold the A ring); the epilogue frees it as soon as the tile
     // sits in registers.  Otherwise two accumulators alternate.
     const uint32_t tmem_cols = a_tmem ? 512u : (uint32_t)(2 * BLOCK_N);
@@ -888,8 +896,13 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                         }
                         const int64_t n = (int64_t)n0 + col + lane;
                         if (n < p.N) {
-                            atomicMin(p.colrange + 2 * n, mn);
-                            atomicMin(p.colrange + 2 * n + 1, mxn);
+                            if (p.colrange_smem) {
+                                atomicMin(s_range + 2 * n, mn);
+                                atomicMin(s_range + 2 * n + 1, mxn);
+                            } else {
+                                atomicMin(p.colrange + 2 * n, mn);
+                                atomicMin(p.colrange + 2 * n + 1, mxn);
+                            }
                         }
                     }
                     if (staged) {
@@ -985,6 +998,9 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     }
     tc_fence_before();
     __syncthreads();
+    if (D_TRANS && p.colrange && p.colrange_smem)
+        for (int i = threadIdx.x; i < 2 * (int)p.N; i += NTHREADS)
+            if (s_range[i] != 0xffffffffu) atomicMin(p.colrange + i, s_range[i]);
     if (CG == 2) cluster_sync_all();   // neither CTA leaves while its peer may still signal its barriers / read its smem
     if (p.trace && blockIdx.x == 0 && threadIdx.x == 0) p.trace[67] = clock64();
     if (cta_stamps) {
@@ -1164,23 +1180,28 @@ int launch(const CUtensorMap &ah, const CUtensorMap &al, const CUtensorMap &bh, 
     constexpr int A_TILE = BLOCK_M * BK * 4, B_TILE = (BLOCK_N / CG) * BK * 4;
     size_t smem;
     if (CG != 2) p.tma_store = 0;
+    // shared-memory accumulation of the range fold: 2 * N words carved from the tile budget
+    const int range_bytes = (D_TRANS && p.colrange && p.N <= 1024) ? (int)((2 * p.N * 4 + 1023) / 1024 * 1024) : 0;
+    p.colrange_smem = range_bytes > 0 ? 1 : 0;
     if (p.a_tmem) {
         // main ring: hi + lo tiles of B (CG == 2: this CTA's half of them); the rest of shared memory: raw A tiles
         // (at least 4 in flight) and, with the TMA-store epilogue, one staging tile per epilogue group
-        const int epi = p.tma_store ? EPI_GROUPS * EPI_STAGE_BYTES : 0;
+        const int epi = (p.tma_store ? EPI_GROUPS * EPI_STAGE_BYTES : 0) + range_bytes;
         int stages = (SMEM_BUDGET - epi - 4 * A_TILE) / (2 * B_TILE);
         if (stages > MAX_STAGES) stages = MAX_STAGES;
         int stages_a = (SMEM_BUDGET - epi - stages * 2 * B_TILE) / A_TILE;
         if (stages_a > MAX_STAGES) stages_a = MAX_STAGES;
         p.stages = stages;
         p.stages_a = stages_a;
+        p.range_off = (uint32_t)((size_t)stages * 2 * B_TILE + (size_t)stages_a * A_TILE + (epi - range_bytes));
         smem = (size_t)stages * 2 * B_TILE + (size_t)stages_a * A_TILE + epi + 1024;
     } else {
         const uint32_t stage_bytes = (p.terms == 3 ? 2 : 1) * (A_TILE + B_TILE);
-        int stages = SMEM_BUDGET / (int)stage_bytes;
+        int stages = (SMEM_BUDGET - range_bytes) / (int)stage_bytes;
         if (stages > MAX_STAGES) stages = MAX_STAGES;
         p.stages = stages;
-        smem = (size_t)stages * stage_bytes + 1024;
+        p.range_off = (uint32_t)((size_t)stages * stage_bytes);
+        smem = (size_t)stages * stage_bytes + range_bytes + 1024;
     }
     auto kern = rotate_gemm_kernel<BLOCK_N, A_MN, B_MN, D_TRANS, BK, CG>;
     static PerDeviceOnce attr_once1;
