@@ -411,35 +411,33 @@ def run_ours(a):
             self.n, self.c, self.mode, self.mid = hw * hw, c, mode, _lib.mode_id(mode)
             self.sets = [make_inputs(torch, a, seed0 + i, device, hw, c) for i in range(sets)]
             self.outs = [torch.empty_like(self.sets[0][0]) for _ in range(2)]
-            self.ws = torch.empty(lib.optex_ot_workspace_bytes(self.n, self.n, c, self.mid), dtype=torch.uint8,
+            self.ws = torch.empty(lib.optex_ot_steps_workspace_bytes(self.n, self.n, c, self.mid), dtype=torch.uint8,
                                   device=device)
             self.rot_ws = torch.empty(lib.optex_rotations_workspace_bytes(c, K), dtype=torch.uint8, device=device)
-            self.rots = torch.empty(K, c, c, dtype=torch.float32, device=device)
-            self.rsplit = torch.empty(K, 2, c, c, dtype=torch.float32, device=device) if c % 4 == 0 else None
+            self.rots = torch.empty(K, c, c, dtype=torch.float32, device=device)      # profile / sharded paths only
             mk = lambda ts: (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])  # noqa: E731
             self.P, self.S, self.O = mk([p for p, _ in self.sets]), mk([s for _, s in self.sets]), mk(self.outs)
 
         def gen_rotations(self, first, seed=1234):
             call("optex_random_rotations", ptr(self.rots), self.c, K, seed, first, None, ptr(self.rot_ws),
                  self.rot_ws.numel(), st)
-            if self.rsplit is not None:      # tf32 hi / lo planes of the K rotations, one launch (part of the draw)
-                call("optex_split_rotations", ptr(self.rots), K, self.c, ptr(self.rsplit), st)
 
-        def steps(self, first=0, count=None):
-            """K independent steps enqueued by ONE C call (optex_ot_steps): Python is not in the loop."""
-            call("optex_ot_steps", self.P, self.S, len(self.sets), ptr(self.rots), ptr(self.rsplit), self.O, 2,
+        def steps(self, first=0, count=None, counter=0):
+            """K independent steps enqueued by ONE C call (optex_ot_steps): Python is not in the loop.  The rotations
+            are drawn inside the call, one per step from (seed, counter + i) as the reference draws one per call
+            (optex.py:168), in batches of up to 32."""
+            call("optex_ot_steps", self.P, self.S, len(self.sets), None, None, 1234, counter, self.O, 2,
                  K if count is None else count, first, 1, self.n, 1, self.n, self.c, self.mid, 1.0, ptr(self.ws),
                  self.ws.numel(), st)
 
         def region(self):
-            """rotation draw for K steps + K steps + drain fence; returns (device ms, host enqueue ms)."""
+            """K steps (rotation draw included) + drain fence; returns (device ms, host enqueue ms)."""
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             barrier()
             l0 = lib.optex_launch_count()
             t0 = time.perf_counter()
             e0.record()
-            self.gen_rotations(self.region_no * K + W)
-            self.steps()
+            self.steps(counter=self.region_no * K + W)
             call("optex_fence", st)     # ordinary kernel: starts only after the last PDL-launched kernel drained
             e1.record()
             t1 = time.perf_counter()
@@ -453,7 +451,6 @@ def run_ours(a):
         def timed(self, reps):
             """W warm-up steps through the SAME code path (every kernel between the events has run before), then
             `reps` regions of exactly K steps; per region the max over ranks."""
-            self.gen_rotations(0)
             self.steps(0, W)
             call("optex_fence", st)
             barrier()
@@ -476,7 +473,9 @@ def run_ours(a):
 
         shard_ops = parallel.cuda_ops()
 
-        def sharded_steps(first=0, count=None):
+        blk.gen_rotations(0)
+
+        def sharded_steps(first=0, count=None, counter=0):
             for i in range(K if count is None else count):
                 p, s = sets[(first + i) % a.sets]
                 parallel.optimal_transport_sharded(p, s, a.mode, rots[i], ops=shard_ops)
@@ -487,7 +486,6 @@ def run_ours(a):
     sampler = ClockSampler(local)      # NVML init happens here, outside the timed region
     # untimed pre-warm on top of the W warm-up steps: a fresh box idles at low clocks and the first ~100 ms of
     # work run up to 2x slow (measured: 486 vs 265 us/step for the first bench of a box) - W steps are only ~1.5 ms
-    blk.gen_rotations(0)
     t_pre = time.perf_counter()
     while time.perf_counter() - t_pre < a.prewarm_s:
         blk.steps()
@@ -510,6 +508,8 @@ def run_ours(a):
         sl = (C.c_int * 8)()
         ns = C.c_int(0)
         acc = [[] for _ in names]
+        blk.gen_rotations(0)
+        torch.cuda.synchronize()
         for i in range(W + K):
             p, s = sets[i % a.sets]
             call("optex_ot_step_profile", ptr(p), ptr(s), ptr(rots[i % K]), ptr(outs[i % 2]), 1, n, 1, n, c, mode, 1.0,
@@ -648,8 +648,9 @@ def run_ours(a):
         "setup": {"gemm": a.gemm,
                   "prewarm": f"{a.prewarm_s:g} s of untimed steps before the {W} warm-up steps (clock ramp)",
                   "l2": f"inputs cycle over {a.sets} distinct (P,S) sets = {a.sets * 2 * 4 * n * c / 1e6:.0f} MB > 126 MB L2",
-                  "enqueue": "K steps per region by ONE C call (optex_ot_steps); rotation draw for the K steps inside "
-                             "the region; drain fence kernel before the closing event",
+                  "enqueue": "K steps per region by ONE C call (optex_ot_steps); the rotation of every step is drawn "
+                             "inside the call (device RNG, batches of up to 32); drain fence kernel before the closing "
+                             "event",
                   "sharding": ("one block, rotated channels sharded over ranks + NCCL all-gather" if sharded else
                                "independent feature blocks per rank, no data-path collective")},
         "repeats": {"n": len(ms_regions), "ms_per_region": [round(x, 4) for x in ms_regions], "ms_median": ms_total, "ms_min": min(ms_regions),

@@ -134,15 +134,19 @@ int optex_ot_step_host_async(const float *P, const float *S, const float *R, flo
 int optex_ot_host_set_style(const float *S, int b_s, int64_t hw_s, int c, void *stream);
 
 /* `steps` INDEPENDENT OT steps (optex.py:167-177 each) enqueued by one call - e.g. a batch of syntheses standing at
- * the same layer: step i transports P[(first + i) % n_sets] towards S[(first + i) % n_sets] with rotation
- * R_all[i] ([steps, c, c] on the device) into out[(first + i) % n_out].  P / S / out are HOST arrays of device
- * pointers.  R_split (may be NULL): the tf32 hi / lo planes of the same rotations, [steps][2][c][c], from
- * optex_split_rotations - the per-step split launch then disappears.  Same arithmetic and kernels as `steps`
- * optex_ot_step calls, without a host round trip per step. */
+ * the same layer: step i transports P[(first + i) % n_sets] towards S[(first + i) % n_sets] with rotation i into
+ * out[(first + i) % n_out].  P / S / out are HOST arrays of device pointers.
+ *   R_all != NULL : rotation i = R_all[i] ([steps, c, c] on the device); R_split (may be NULL) = the tf32 hi / lo planes
+ *                   of the same rotations, [steps][2][c][c], from optex_split_rotations - the per-step split launch
+ *                   then disappears.  workspace: optex_ot_workspace_bytes().
+ *   R_all == NULL : rotation i is drawn on the device from (seed, first_counter + i), like the reference draws one per
+ *                   call (optex.py:168) - in batches of up to 32.  workspace: optex_ot_steps_workspace_bytes().
+ * Same arithmetic and kernels as `steps` optex_ot_step calls, without a host round trip per step. */
+size_t optex_ot_steps_workspace_bytes(int64_t n_p, int64_t n_s, int c, int mode);
 int optex_ot_steps(const float *const *P, const float *const *S, int n_sets, const float *R_all,
-                   const float *R_split, float *const *out, int n_out, int steps, int first,
-                   int b_p, int64_t hw_p, int b_s, int64_t hw_s, int c, int mode, float eps,
-                   void *workspace, size_t workspace_bytes, void *stream);
+                   const float *R_split, uint64_t seed, uint64_t first_counter, float *const *out,
+                   int n_out, int steps, int first, int b_p, int64_t hw_p, int b_s, int64_t hw_s,
+                   int c, int mode, float eps, void *workspace, size_t workspace_bytes, void *stream);
 /* out[i] = [tf32_hi(R_i) | tf32_lo(R_i)] for `count` rotations [c, c] (c % 4 == 0) in one launch: the operand halves of
  * the 3xTF32 rotation GEMMs, batched like the draw (optex_random_rotations).  out: [count][2][c][c] floats. */
 int optex_split_rotations(const float *R_all, int count, int c, float *out, void *stream);

@@ -40,7 +40,8 @@ SIGNATURES = {
     "optex_ot_step_host": (_i, [_p, _p, _p, _p, _i, _l, _i, _l, _i, _i, _f, _p, _f, _u, _u, _p]),
     "optex_ot_step_host_async": (_i, [_p, _p, _p, _p, _i, _l, _i, _l, _i, _i, _f, _p, _f, _u, _u, _i, _p]),
     "optex_ot_host_set_style": (_i, [_p, _i, _l, _i, _p]),
-    "optex_ot_steps": (_i, [_p, _p, _i, _p, _p, _p, _i, _i, _i, _i, _l, _i, _l, _i, _i, _f, _p, _z, _p]),
+    "optex_ot_steps_workspace_bytes": (_z, [_l, _l, _i, _i]),
+    "optex_ot_steps": (_i, [_p, _p, _i, _p, _p, _u, _u, _p, _i, _i, _i, _i, _l, _i, _l, _i, _i, _f, _p, _z, _p]),
     "optex_split_rotations": (_i, [_p, _i, _i, _p, _p]),
     "optex_fence": (_i, [_p]),
     "optex_ot_step_profile": (_i, [_p, _p, _p, _p, _i, _l, _i, _l, _i, _i, _f, _p, _z, _p, _p, _p, _p]),

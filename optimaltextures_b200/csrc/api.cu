@@ -462,30 +462,75 @@ extern "C" int optex_ot_host_set_style(const float *S, int b_s, int64_t hw_s, in
     return OPTEX_OK;
 }
 
+static const int kStepsChunk = 32;
+
+extern "C" size_t optex_ot_steps_workspace_bytes(int64_t n_p, int64_t n_s, int c, int mode) {
+    const size_t step = optex_ot_workspace_bytes(n_p, n_s, c, mode);
+    if (!step) return 0;
+    // + a chunk of rotations (R and its tf32 hi / lo planes) and the draw's own scratch
+    return step + align_up(sizeof(float) * 3 * (size_t)kStepsChunk * c * c, 256) +
+           align_up(rotation_ws_bytes(c, kStepsChunk), 256);
+}
+
 // `steps` INDEPENDENT OT steps enqueued by one call (a batch of syntheses at the same layer; the granularity of the
 // reference's own loop, optex.py:112-113, without a host round trip per step): step i transports
 // P[(first + i) % n_sets] towards S[(first + i) % n_sets] with rotation R_all[i] into out[(first + i) % n_out].
+// R_all == NULL: the rotations are drawn on the device from (seed, first_counter + i) like the reference draws one per
+// call (optex.py:168) - in batches of up to 32 on the caller's stream (workspace: optex_ot_steps_workspace_bytes).
+// (Drawing the next batch on a side stream beside the running steps was measured and buys nothing: the device is busy,
+// the draw's FP64 work only competes - 210.4 vs 210.7 us per step at 200 steps, worse at 20.)
 extern "C" int optex_ot_steps(const float *const *P, const float *const *S, int n_sets, const float *R_all,
-                              const float *R_split, float *const *out, int n_out, int steps, int first, int b_p,
-                              int64_t hw_p, int b_s, int64_t hw_s, int c, int mode, float eps, void *workspace,
-                              size_t workspace_bytes, void *stream) {
+                              const float *R_split, uint64_t seed, uint64_t first_counter, float *const *out,
+                              int n_out, int steps, int first, int b_p, int64_t hw_p, int b_s, int64_t hw_s, int c,
+                              int mode, float eps, void *workspace, size_t workspace_bytes, void *stream) {
     OPTEX_TRY(require_sm100());
-    if (!P || !S || !out || !R_all || n_sets < 1 || n_out < 1 || steps < 0 || first < 0) {
+    if (!P || !S || !out || n_sets < 1 || n_out < 1 || steps < 0 || first < 0) {
         set_error("optex_ot_steps: NULL table or empty set list");
         return OPTEX_EINVAL;
     }
-    for (int i = 0; i < steps; ++i) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n_p = (int64_t)b_p * hw_p, n_s = (int64_t)b_s * hw_s;
+    const size_t cc = (size_t)c * c;
+    auto run = [&](int i, const float *R, const float *split) -> int {
         const int k = (first + i) % n_sets, o = (first + i) % n_out;
         OPTEX_TRY(check_step_args("optex_ot_steps", P[k], S[k], out[o], b_p, hw_p, b_s, hw_s, c, mode));
         if (out[o] == P[k] || out[o] == S[k]) {
             set_error("optex_ot_steps: out must not alias an input");
             return OPTEX_EINVAL;
         }
-        g_r_split = R_split ? R_split + (size_t)i * 2 * c * c : nullptr;
-        int rc = ot_step_impl(P[k], S[k], R_all + (size_t)i * c * c, out[o], b_p, hw_p, b_s, hw_s, c, mode, eps, nullptr,
-                              0.f, workspace, workspace_bytes, (cudaStream_t)stream);
+        g_r_split = split;
+        int rc = ot_step_impl(P[k], S[k], R, out[o], b_p, hw_p, b_s, hw_s, c, mode, eps, nullptr, 0.f, workspace,
+                              optex_ot_workspace_bytes(n_p, n_s, c, mode), st);
         g_r_split = nullptr;
-        OPTEX_TRY(rc);
+        return rc;
+    };
+    if (R_all) {
+        if (workspace_bytes < optex_ot_workspace_bytes(n_p, n_s, c, mode)) {
+            set_error("optex_ot_steps: workspace too small");
+            return OPTEX_EWORKSPACE;
+        }
+        for (int i = 0; i < steps; ++i)
+            OPTEX_TRY(run(i, R_all + (size_t)i * cc, R_split ? R_split + (size_t)i * 2 * cc : nullptr));
+        return OPTEX_OK;
+    }
+    // ---- rotations drawn here, a batch at a time
+    const size_t step_ws = optex_ot_workspace_bytes(n_p, n_s, c, mode);
+    if (!workspace || workspace_bytes < optex_ot_steps_workspace_bytes(n_p, n_s, c, mode)) {
+        set_error("optex_ot_steps: workspace %zu < %zu bytes (optex_ot_steps_workspace_bytes)", workspace_bytes,
+                  optex_ot_steps_workspace_bytes(n_p, n_s, c, mode));
+        return OPTEX_EWORKSPACE;
+    }
+    Arena ar((char *)workspace + step_ws, workspace_bytes - step_ws);
+    float *R = ar.take<float>(3 * (size_t)kStepsChunk * cc);
+    const size_t rws_bytes = rotation_ws_bytes(c, kStepsChunk);
+    void *rws = ar.take<char>(rws_bytes);
+    const bool split = c % 4 == 0;
+    for (int i0 = 0; i0 < steps; i0 += kStepsChunk) {
+        const int nb = steps - i0 < kStepsChunk ? steps - i0 : kStepsChunk;
+        OPTEX_TRY(random_rotations(R, c, nb, seed, first_counter + (uint64_t)i0, nullptr, rws, rws_bytes, st));
+        if (split) OPTEX_TRY(gemm_tc_split_batch(R, R + (size_t)kStepsChunk * cc, nb, (int64_t)cc, st));
+        for (int j = 0; j < nb; ++j)
+            OPTEX_TRY(run(i0 + j, R + (size_t)j * cc, split ? R + (size_t)kStepsChunk * cc + (size_t)j * 2 * cc : nullptr));
     }
     return OPTEX_OK;
 }

@@ -183,12 +183,37 @@ def test_step_in_place_stream_matches_steps_api(ob):
         for split in (None, rsplit):             # with and without the batched pre-split of the rotations: same bits
             for o in outs:
                 o.zero_()
-            call("optex_ot_steps", mk([p for p, _ in sets]), mk([s for _, s in sets]), 3, ptr(rots), ptr(split), mk(outs), K,
-                 K, 0, 1, n, 1, n, c, mid, 1.0, ptr(ws), ws.numel(), stream_ptr(dev))
+            call("optex_ot_steps", mk([p for p, _ in sets]), mk([s for _, s in sets]), 3, ptr(rots), ptr(split), 0, 0,
+                 mk(outs), K, K, 0, 1, n, 1, n, c, mid, 1.0, ptr(ws), ws.numel(), stream_ptr(dev))
             torch.cuda.synchronize()
             for i in range(K):
                 p, s = sets[i % 3]
                 assert torch.equal(outs[i], ob.optimal_transport(p, s, mode, rotation=rots[i]))
+
+
+def test_steps_api_draws_its_own_rotations(ob):
+    """optex_ot_steps with R_all == NULL: rotation i comes from (seed, first_counter + i) - drawn in batches of up to 32
+    inside the call - and equals optex_random_rotations' matrix."""
+    import ctypes as C
+
+    from optimaltextures_b200 import _lib
+    from optimaltextures_b200._runtime import call, ptr, stream_ptr
+
+    dev = torch.device("cuda", torch.cuda.current_device())
+    n, c, K = 2048, 128, 70                      # three batches: 32 + 32 + 6
+    sets = [tuple(t.cuda() for t in make(n, n, c, "relu", seed=60 + i)[:2]) for i in range(2)]
+    rots = ob.random_rotations(c, K, "cuda", seed=77, first_counter=5)
+    mid = _lib.mode_id("cdf")
+    outs = [torch.empty(1, n, 1, c, device="cuda") for _ in range(K)]
+    ws = torch.empty(_lib.lib().optex_ot_steps_workspace_bytes(n, n, c, mid), dtype=torch.uint8, device="cuda")
+    mk = lambda ts: (C.c_void_p * len(ts))(*[t.data_ptr() for t in ts])  # noqa: E731
+    for rep in range(2):
+        call("optex_ot_steps", mk([p for p, _ in sets]), mk([s for _, s in sets]), 2, None, None, 77, 5, mk(outs), K, K, 0,
+             1, n, 1, n, c, mid, 1.0, ptr(ws), ws.numel(), stream_ptr(dev))
+        torch.cuda.synchronize()
+        for i in range(K):
+            p, s = sets[i % 2]
+            assert torch.equal(outs[i], ob.optimal_transport(p, s, "cdf", rotation=rots[i])), (rep, i)
 
 
 def test_host_step_with_resident_style(ob):
