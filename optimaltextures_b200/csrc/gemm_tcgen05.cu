@@ -491,9 +491,11 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         return p.batch > 0 && p.skip_z[z] != nullptr && *p.skip_z[z] < p.skip_tol;
     };
     // which accumulator / barrier phase the i-th tile of this CTA uses
+    // (TMEM-A form: the A ring owns columns 256..511, so only tiles up to 128 wide leave room for a second accumulator)
+    const bool one_acc = a_tmem && BLOCK_N > 128;
     auto acc_of = [&](int titer, int &acc, uint32_t &aph) {
-        acc = a_tmem ? 0 : (titer & 1);
-        aph = a_tmem ? (uint32_t)(titer & 1) : (uint32_t)((titer >> 1) & 1);
+        acc = one_acc ? 0 : (titer & 1);
+        aph = one_acc ? (uint32_t)(titer & 1) : (uint32_t)((titer >> 1) & 1);
     };
 
     if (warp < 4) {

@@ -12,7 +12,7 @@ from optimaltextures_b200 import _lib
 
 lib = _lib.lib()
 lib.optex_set_pdl(0)
-n, c = 16384, 512
+n, c = int(os.environ.get("GN", 16384)), int(os.environ.get("GC", 512))
 g = torch.Generator().manual_seed(0)
 xs = [torch.relu(torch.randn(n, c, generator=g)).cuda() for _ in range(6)]      # 200 MB > L2: A comes from HBM
 r = ob.random_rotation(c, "cuda", seed=1, counter=0)
