@@ -628,8 +628,8 @@ extern "C" int optex_ot_step_sharded(optex_comm_t *comm, const float *P, const f
         cov_set_shard(nullptr);
         return rc;
     }
-    if (n_p_total >= (1 << 24) || n_s_total >= (1 << 24)) {
-        set_error("optex_ot_step_sharded: n >= 2^24 per channel (fp32 cumsum of the reference stops being exact)");
+    if (n_p_total >= (1LL << 31) || n_s_total >= (1LL << 31)) {
+        set_error("optex_ot_step_sharded: n >= 2^31 per channel");
         return OPTEX_ESIZE;
     }
     Arena ar(ws, ws_bytes);

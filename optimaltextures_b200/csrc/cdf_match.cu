@@ -571,8 +571,11 @@ int fill_u32(uint32_t *p, int64_t n, uint32_t v, cudaStream_t st) {
 // the per-channel range - the forward-rotation GEMM folded it in its epilogue.
 int cdf_match_core(const float *target, const float *source, float *out, int c, int64_t n_t, int64_t n_s, int bins,
                    float *tables, void *workspace, size_t workspace_bytes, bool have_range, cudaStream_t st) {
-    if (n_t >= (1 << 24) || n_s >= (1 << 24)) {
-        set_error("optex_cdf_match: n >= 2^24 per channel (fp32 cumsum of the reference stops being exact)");
+    // Counts are exact 32-bit integers here.  Below 2^24 elements per channel that is also what the reference computes
+    // (its fp32 histc / cumsum are exact there) and the result is bit-identical; above, the reference itself loses
+    // counts to fp32 rounding and this kernel simply stays exact (a 4096^2 colour transfer has 16.7 M pixels per channel).
+    if (n_t >= (1LL << 31) || n_s >= (1LL << 31)) {
+        set_error("optex_cdf_match: n >= 2^31 per channel");
         return OPTEX_ESIZE;
     }
     if (c > 65535) {

@@ -593,15 +593,15 @@ struct SideStream {
     cudaStream_t stream = nullptr;
     cudaEvent_t fork = nullptr, join = nullptr;
 };
-SideStream g_side[64];
-std::mutex g_side_mu;
+// one side stream + event pair per calling host THREAD and device: two threads driving the library concurrently never
+// re-record each other's fork / join events, and their side chains do not serialise behind one another
+thread_local SideStream t_side[64];
 
 int side_stream(SideStream **out) {
     int dev = 0;
     OPTEX_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) dev = 63;
-    std::lock_guard<std::mutex> lock(g_side_mu);
-    SideStream &s = g_side[dev];
+    SideStream &s = t_side[dev];
     if (!s.stream) {
         OPTEX_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         OPTEX_CUDA(cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming));

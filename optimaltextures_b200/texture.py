@@ -293,6 +293,11 @@ class OptimalTexture:
                     cf = _optex.pca_project(cf, eigvecs)
                 content_features.append(recentre(cf, sf))
         self.last_pca_k = [int(v.shape[1]) for v in style_eigvs]        # conv5_1 .. conv1_1 of the latest pass
+        if self.use_pca and min(self.last_pca_k) < 1:
+            # optex.py:185-186: k = first index whose cumulative singular-value share exceeds 0.9; a layer whose FIRST
+            # singular value already does gets k = 0 and the reference then fails inside its matmuls on [.., 0] tensors
+            raise ValueError(f"fit_pca kept 0 components for a layer (k per layer, deepest first: {self.last_pca_k}): "
+                             "the style's first singular value alone exceeds 90 % of the total (optex.py:185)")
 
         if mix and len(styles) > 1:                                                              # optex.py:97-101
             shape = tuple(style_features[1].shape[1:3])
