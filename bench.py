@@ -50,6 +50,7 @@ def parse():
                     help="seconds of untimed steps before the warm-up (GPU clock ramp of a fresh box)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-slots", type=int, default=3, dest="e2e_slots", help="pipeline depth of the e2e leg (1..4)")
     ap.add_argument("--repeats", type=int, default=0,
                     help="timed regions of exactly --steps steps (value = median region); 0 = as many as fill ~100 ms, "
                          "at least 5 (the clock sampler needs the time)")
@@ -529,7 +530,7 @@ def run_ours(a):
     # ---- e2e: host buffers through optex_ot_step_host_async (H2D + step + D2H per call)
     e2e = None
     if not a.no_e2e and not sharded:
-        NS = 3
+        NS = max(1, min(4, a.e2e_slots))
         hp = [torch.empty(1, a.hw, a.hw, c).pin_memory() for _ in range(NS)]
         ho = [torch.empty(1, a.hw, a.hw, c).pin_memory() for _ in range(NS)]
         hs = torch.empty(1, a.hw, a.hw, c).pin_memory()

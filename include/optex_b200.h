@@ -117,8 +117,8 @@ int optex_ot_step_host(const float *P, const float *S, const float *R, float *ou
                        float content_strength, uint64_t seed, uint64_t counter,
                        void *stream);
 
-/* The same without the final synchronisation, for callers that pipeline independent steps: `slot` (0, 1 or 2)
- * selects one of three library-owned device scratch sets, so step i+1 (slot B, stream B) can upload while step i
+/* The same without the final synchronisation, for callers that pipeline independent steps: `slot` (0 .. 3)
+ * selects one of four library-owned device scratch sets, so step i+1 (slot B, stream B) can upload while step i
  * (slot A, stream A) computes and step i-1 (slot C, stream C) downloads.  Use PINNED host buffers and one stream per
  * slot; the caller synchronises the stream before reading `out` or reusing the slot. */
 int optex_ot_step_host_async(const float *P, const float *S, const float *R, float *out,

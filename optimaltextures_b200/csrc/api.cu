@@ -261,7 +261,7 @@ struct HostScratch {
         return OPTEX_OK;
     }
 };
-constexpr int kHostSlots = 3;   // upload of step i+1 | compute of step i | download of step i-1
+constexpr int kHostSlots = 4;   // upload of step i+1 | compute of step i | download of step i-1 (+ one in reserve)
 static HostScratch g_host[kHostSlots];  // one per pipeline slot of optex_ot_step_host_async
 
 // The style block is constant over the iterations of a layer (optex.py:112-113 passes the same style_features[l]
@@ -414,7 +414,7 @@ extern "C" int optex_ot_step_host_async(const float *P, const float *S, const fl
                                         const float *content, float content_strength, uint64_t seed,
                                         uint64_t counter, int slot, void *stream) {
     if (slot < 0 || slot >= kHostSlots) {
-        set_error("optex_ot_step_host_async: slot must be 0, 1 or 2");
+        set_error("optex_ot_step_host_async: slot must be 0 .. 3");
         return OPTEX_EINVAL;
     }
     return ot_step_host_impl(P, S, R, out, b_p, hw_p, b_s, hw_s, c, mode, eps, content, content_strength, seed,

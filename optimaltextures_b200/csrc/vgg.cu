@@ -135,7 +135,11 @@ inline void out_size(int hs, int ws, int pre, int *h, int *w) {
 }
 int64_t chunk_rows(int64_t M, int kp) {
     static const char *env = getenv("OPTEX_CONV_CHUNK_MB");
-    const int64_t budget = (env && atoi(env) > 0 ? (int64_t)atoi(env) : 32) << 20;
+    // Round 1 kept the im2col chunk at 32 MB so it stayed in L2; that made every GEMM tiny (M = 1820 rows for the
+    // 512-channel layers: 64-wide tiles, A converted 8 times).  512 MB chunks go through HBM once (a 10-25 % add-on to
+    // the GEMM's own time) and let the GEMMs take the paired 256-wide tiles: Encoder(5) @ 1024^2 15.7 -> 8.1 ms,
+    // Decoder(5) 19.8 -> 9.9 ms.
+    const int64_t budget = (env && atoi(env) > 0 ? (int64_t)atoi(env) : 512) << 20;
     int64_t rows = budget / ((int64_t)kp * 4) / 128 * 128;
     if (rows < 128) rows = 128;
     return rows < M ? rows : M;
