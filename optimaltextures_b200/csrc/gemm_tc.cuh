@@ -57,6 +57,20 @@ struct TcGemm {
     int64_t M2, ldd2;
     float *D2;
 };
+// implicit-GEMM 3 x 3 convolution (vgg.cu): `padded` = reflection-padded NHWC input [b, h + 2, w + 2, cin], cin % 32 == 0;
+// w_hi / w_lo = tf32 halves of the packed weights [cout, 9 * cin] (k = tap * cin + ci); D = NHWC output [b, h, w, ldd]
+struct TcConv {
+    const float *padded;
+    int b, h, w, cin;
+    const float *w_hi, *w_lo;
+    int cout;
+    const float *bias;
+    bool relu;
+    float *D;
+    int64_t ldd;
+};
+int gemm_tc_conv(const TcConv &c, cudaStream_t st);   // OPTEX_OK, OPTEX_ENOTSUP or an error
+
 // selects which of the two library-owned hi/lo scratch buffers the calling thread's GEMMs use (pipelined callers)
 void gemm_tc_set_scratch_slot(int slot);
 void gemm_tc_set_trace(unsigned long long *device_buf);  // debug: 64 x u64 clock stamps of CTA 0's first tile

@@ -109,6 +109,14 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap *map, uint64_t *ba
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z), "l"(hint)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap *map, uint64_t *bar, void *dst, int c0, int c1, int c2,
+                                            int c3, uint64_t hint) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(hint)
+        : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *map, int x, int y) {
     asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(x), "r"(y) : "memory");
 }
@@ -238,6 +246,12 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void 
                  : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, const void *src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -336,7 +350,14 @@ struct Params {
     // output map in tmD2; tiles of problem 0 come first in the tile list.
     int64_t M2, ldd2;
     float *D2;
+    // conv (TMEM-A launches, K-major A): implicit GEMM of a 3 x 3 convolution (vgg.cu).  The A operand is never
+    // materialised: an M tile is a CONV_TH x CONV_TW block of output pixels of one image and k block kb = 32 input
+    // channels of tap kb * 32 / c_in, loaded by ONE 4-D TMA box {32 ch, CONV_TW, CONV_TH, 1} at the tap's offset from
+    // the reflection-padded NHWC input [b, h + 2, w + 2, c_in] - which lands exactly in the K-major SWIZZLE_128B tile
+    // layout of an explicit im2col row block.  p.M = (number of pixel tiles) x 128 x CG virtual rows.
+    int conv, cv_h, cv_w, cv_cin, cv_tx, cv_ty;   // output height / width, input channels, tiles along x / y per image
 };
+constexpr int CONV_TW = 16, CONV_TH = 8;   // 128 pixels per CTA tile; a pair stacks two of them along y
 
 // ------------------------------------------------------------------ the kernel
 // Persistent, warp-specialised: grid = min(#tiles, #SMs); every CTA walks tiles  t = blockIdx.x, += gridDim.x.
@@ -479,6 +500,15 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         m0 = (r / n_tiles_n) * (BLOCK_M * CG) + (int)crank * BLOCK_M;   // this CTA's rows of the (pair's) tile
         n0 = (r % n_tiles_n) * BLOCK_N;
     };
+    // conv: (image, first pixel row / column) of this CTA's block of output pixels
+    auto conv_coords = [&](int m0, int &bi, int &y0, int &x0) {
+        const int mt = m0 / (BLOCK_M * CG);          // pixel-tile index (of the pair)
+        const int per_img = p.cv_tx * p.cv_ty;
+        bi = mt / per_img;
+        const int rem = mt - bi * per_img;
+        y0 = (rem / p.cv_tx) * (CONV_TH * CG) + (int)crank * CONV_TH;
+        x0 = (rem % p.cv_tx) * CONV_TW;
+    };
     const int tile0 = (int)blockIdx.x / CG, tile_step = (int)gridDim.x / CG;   // pairs walk the tile list together
     auto k_range = [&](int z, int64_t &k_begin, int &num_kb) {
         if (tiles_dual > 0) z = 0;   // both problems of a dual launch span the whole K
@@ -526,7 +556,12 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                             uint8_t *a_dst = a_ring + (size_t)sa * A_TILE;
                             mbar_expect_tx(&raw_bar[sa], A_TILE);
                             const CUtensorMap *ma = (tiles_dual > 0 && z == 1) ? &tmA_lo : &tmA_hi;
-                            if (A_MN) tma_load_3d(ma, &raw_bar[sa], a_dst, 0, k0 + ao, m0 / 32, p.a_hint);
+                            if (!A_MN && p.conv) {
+                                int bi, y0, x0;
+                                conv_coords(m0, bi, y0, x0);
+                                const int tap = k0 / p.cv_cin, ch0 = k0 - tap * p.cv_cin;
+                                tma_load_4d(ma, &raw_bar[sa], a_dst, ch0, x0 + tap % 3, y0 + tap / 3, bi, p.a_hint);
+                            } else if (A_MN) tma_load_3d(ma, &raw_bar[sa], a_dst, 0, k0 + ao, m0 / 32, p.a_hint);
                             else tma_load_2d(ma, &raw_bar[sa], a_dst, k0, m0 + ao, p.a_hint);
                             if (++sa == p.stages_a) { sa = 0; pha ^= 1; }
                             // pre-split B hi / lo -> the main ring (freed by the MMAs)
@@ -847,7 +882,13 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
             }
             if (p.trace && blockIdx.x == 0 && warp == EPI_WARP0 && lane == 0 && tcur < 4) p.trace[69 + tcur * 2] = clock64();
             if (warp == EPI_WARP0 && lane == 0) stamp(3, tcur, 2);
-            const int64_t row = (int64_t)m0 + q * 32 + lane;
+            int64_t row = (int64_t)m0 + q * 32 + lane;
+            int cbi = 0, cy0 = 0, cx0 = 0;
+            if (!D_TRANS && p.conv) {   // tile row r <-> output pixel (y0 + r / 16, x0 + r % 16) of image bi
+                conv_coords(m0, cbi, cy0, cx0);
+                const int r = q * 32 + lane, yy = cy0 + r / CONV_TW, xx = cx0 + r % CONV_TW;
+                row = (yy < p.cv_h && xx < p.cv_w) ? ((int64_t)cbi * p.cv_h + yy) * p.cv_w + xx : Mz;
+            }
             uint32_t rmn = 0xffffffffu, rmx = 0xffffffffu;  // this thread's row: f2ord(min), ~f2ord(max)
             float rres = 0.f;                                // max |acc - I| of this thread's part of the tile
             // CG == 2: the tile leaves through shared memory and a TMA store.  (Direct stores of a row-per-thread
@@ -952,7 +993,10 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                         if (es) stamp(3, 4 + tcur * 2 + ch, 2);
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         named_bar_sync(1 + egrp, 128);
-                        if (issuer) tma_store_2d(dmap, stg, n0 + col, m0);   // x = column, y = row
+                        if (issuer) {
+                            if (p.conv) tma_store_4d(dmap, stg, n0 + col, cx0, cy0, cbi);   // box {32 cols, 16 x, 8 y, 1}
+                            else tma_store_2d(dmap, stg, n0 + col, m0);                     // x = column, y = row
+                        }
                         if (es) stamp(3, 4 + tcur * 2 + ch, 3);
                     } else if (n0 + col + 32 <= p.N) {
                         // 256-bit accesses: every store is one full 32-byte sector of this thread's output row
@@ -1118,6 +1162,37 @@ int make_map_out(CUtensorMap *map, const float *base, int64_t rows, int64_t cols
                              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled (output [%lld, %lld]) failed: %d", (long long)rows, (long long)cols, (int)r);
+        return OPTEX_ECUDA;
+    }
+    return OPTEX_OK;
+}
+
+// implicit-GEMM convolution: the padded NHWC input [b, hp, wp, cin] as {cin, wp, hp, b}, box {32, CONV_TW, CONV_TH, 1}
+int make_map_conv_in(CUtensorMap *map, const float *base, int b, int hp, int wp, int cin) {
+    cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)wp, (cuuint64_t)hp, (cuuint64_t)b};
+    cuuint64_t strides[3] = {(cuuint64_t)cin * 4, (cuuint64_t)wp * cin * 4, (cuuint64_t)hp * wp * cin * 4};
+    cuuint32_t box[4] = {32, CONV_TW, CONV_TH, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)base, dims, strides, box, es,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (conv input [%d, %d, %d, %d]) failed: %d", b, hp, wp, cin, (int)r);
+        return OPTEX_ECUDA;
+    }
+    return OPTEX_OK;
+}
+// ... and the NHWC output [b, h, w, ld] (first n channels) as {n, w, h, b}, box {32, CONV_TW, CONV_TH, 1}
+int make_map_conv_out(CUtensorMap *map, const float *base, int b, int h, int w, int64_t n, int64_t ld) {
+    cuuint64_t dims[4] = {(cuuint64_t)n, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)b};
+    cuuint64_t strides[3] = {(cuuint64_t)ld * 4, (cuuint64_t)w * ld * 4, (cuuint64_t)h * w * ld * 4};
+    cuuint32_t box[4] = {32, CONV_TW, CONV_TH, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)base, dims, strides, box, es,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (conv output [%d, %d, %d, %lld]) failed: %d", b, h, w, (long long)n, (int)r);
         return OPTEX_ECUDA;
     }
     return OPTEX_OK;
@@ -1482,6 +1557,42 @@ int gemm_tc(const TcGemm &g, cudaStream_t st) {
     if (!g.a_mn && g.b_mn) return launch_n<false, true, false>(bn, cg, ah, al, bh, bl, dm, dm2, p, nz, st);
     if (g.a_mn && !g.b_mn) return launch_n<true, false, false>(bn, cg, ah, al, bh, bl, dm, dm2, p, nz, st);
     return launch_n<true, true, false>(bn, cg, ah, al, bh, bl, dm, dm2, p, nz, st);
+}
+
+// 3 x 3 convolution as an implicit GEMM (Params::conv): out[pixel, co] = sum_k A(pixel, k) W[co, k] (+ bias, ReLU) with
+// k = tap * cin + ci and A read straight from the reflection-padded NHWC input.  3xTF32, weights pre-split by the caller.
+int gemm_tc_conv(const TcConv &c, cudaStream_t st) {
+    if (!encode_fn() || c.b < 1 || c.h < 1 || c.w < 1 || c.cin < 32 || c.cin % 32 != 0 || c.cout < 1) return OPTEX_ENOTSUP;
+    if (!aligned16(c.padded) || !aligned16(c.w_hi) || !aligned16(c.w_lo) || c.ldd % 8 != 0 ||
+        (reinterpret_cast<uintptr_t>(c.D) & 31) != 0)
+        return OPTEX_ENOTSUP;
+    const int64_t pixels = (int64_t)c.b * c.h * c.w, K = 9LL * c.cin, N = c.cout;
+    if (pixels > 0x3fffffffLL) return OPTEX_ENOTSUP;
+    const int bn = pick_block_n(pixels, N, 1);
+    static const char *cg_env = getenv("OPTEX_CTA_GROUP");
+    const int cg = (bn == 256 && pixels >= 2 * BLOCK_M && N % 64 == 0 && c.h > CONV_TH && !(cg_env && atoi(cg_env) == 1)) ? 2 : 1;
+    const int tx = (c.w + CONV_TW - 1) / CONV_TW, ty = (c.h + CONV_TH * cg - 1) / (CONV_TH * cg);
+    const int64_t m_tiles = (int64_t)c.b * tx * ty;
+    if (m_tiles * BLOCK_M * cg > 0x3fffffffLL) return OPTEX_ENOTSUP;
+    CUtensorMap ah, bh, bl, dm;
+    OPTEX_TRY(make_map_conv_in(&ah, c.padded, c.b, c.h + 2, c.w + 2, c.cin));
+    OPTEX_TRY(make_map_kmajor(&bh, c.w_hi, N, K, bn / cg, 32));
+    OPTEX_TRY(make_map_kmajor(&bl, c.w_lo, N, K, bn / cg, 32));
+    dm = ah;
+    Params p{};
+    p.D = c.D; p.ldd = c.ldd; p.M = m_tiles * BLOCK_M * cg; p.N = N; p.K = K;
+    p.terms = 3; p.alpha = 1.f; p.conv_a = 1; p.conv_b = 0; p.a_tmem = 1; p.nz = 1;
+    p.bias = c.bias; p.bias_hw = 1; p.bias_ld = 0; p.relu = c.relu ? 1 : 0;
+    p.conv = 1; p.cv_h = c.h; p.cv_w = c.w; p.cv_cin = c.cin; p.cv_tx = tx; p.cv_ty = ty;
+    p.trace = g_trace;
+    p.a_hint = L2_EVICT_NORMAL;   // every input pixel is read by 9 taps (and by both N tiles)
+    p.b_hint = L2_EVICT_LAST;
+    static const char *no_tma_store = getenv("OPTEX_NO_TMA_STORE");
+    if (cg == 2 && !(no_tma_store && atoi(no_tma_store))) {
+        OPTEX_TRY(make_map_conv_out(&dm, c.D, c.b, c.h, c.w, N, c.ldd));
+        p.tma_store = 1;
+    }
+    return launch_n<false, false, false>(bn, cg, ah, ah, bh, bl, dm, dm, p, 1, st);
 }
 
 int gemm_tc_rotate_forward(const float *X, const float *R, float *dst, int64_t n, int c, bool transposed, int terms,

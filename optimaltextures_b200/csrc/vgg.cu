@@ -106,6 +106,26 @@ __global__ void __launch_bounds__(256) im2col3x3_kernel(const float *__restrict_
     }
 }
 
+// pad[bi, yp, xp, :] = the pre-op'd source at the reflected position (yp - 1, xp - 1): ReflectionPad2d(1) of the pooled /
+// up-sampled / plain NHWC tensor, materialised ONCE (1.0x the layer's input; the im2col matrix is 9x) for the implicit
+// GEMM, whose TMA boxes address it with the taps' offsets.  cin % 4 == 0.
+__global__ void __launch_bounds__(256) pad_reflect_kernel(const float *__restrict__ src, float *__restrict__ pad,
+                                                          ConvGeom g) {
+    pdl_wait();
+    const int c4n = g.cin >> 2, hp = g.h + 2, wp = g.w + 2;
+    const int64_t total = (int64_t)g.b * hp * wp * c4n;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % c4n) << 2;
+        int64_t r = idx / c4n;
+        const int xp = (int)(r % wp);
+        r /= wp;
+        const int yp = (int)(r % hp);
+        const int bi = (int)(r / hp);
+        *reinterpret_cast<float4 *>(pad + idx * 4) = sample4(src, g, bi, reflect1(yp - 1, g.h), reflect1(xp - 1, g.w), c);
+    }
+}
+
 // dst[b, c, hw] = src[b, hw, 0:c] (row pitch c_src >= c)
 __global__ void nhwc_to_nchw_kernel(const float *__restrict__ src, float *__restrict__ dst, int64_t hw, int c_src,
                                     int c, int64_t total) {
@@ -133,6 +153,11 @@ inline void out_size(int hs, int ws, int pre, int *h, int *w) {
         *w = ws;
     }
 }
+// implicit GEMM applies to NHWC sources with whole 32-channel k blocks (every layer but conv1_1 of the encoder)
+bool implicit_ok(int c_in, int src_nchw) {
+    static const char *env = getenv("OPTEX_CONV_IMPLICIT");
+    return !src_nchw && c_in >= 32 && c_in % 32 == 0 && !(env && atoi(env) == 0);
+}
 int64_t chunk_rows(int64_t M, int kp) {
     static const char *env = getenv("OPTEX_CONV_CHUNK_MB");
     // Round 1 kept the im2col chunk at 32 MB so it stayed in L2; that made every GEMM tiny (M = 1820 rows for the
@@ -158,7 +183,12 @@ extern "C" size_t optex_conv3x3_workspace_bytes(int b, int h_src, int w_src, int
     out_size(h_src, w_src, pre_op, &h, &w);
     const int kp = kpad(c_in);
     const int64_t M = (int64_t)b * h * w;
-    return align_up((size_t)chunk_rows(M, kp) * kp * 4, 256) + align_up((size_t)2 * c_out * kp * 4, 256) + 256;
+    size_t col = (size_t)chunk_rows(M, kp) * kp * 4;
+    if (implicit_ok(c_in, 0)) {   // implicit GEMM: the padded input instead of an im2col chunk
+        const size_t pad = (size_t)b * (h + 2) * (w + 2) * c_in * 4;
+        if (pad > col) col = pad;
+    }
+    return align_up(col, 256) + align_up((size_t)2 * c_out * kp * 4, 256) + 256;
 }
 
 extern "C" int optex_conv3x3(const float *src, int src_nchw, int b, int h_src, int w_src, int c_in,
@@ -184,7 +214,12 @@ extern "C" int optex_conv3x3(const float *src, int src_nchw, int b, int h_src, i
     }
     const int64_t rows = chunk_rows(M, kp);
     Arena ar(workspace, workspace_bytes);
-    float *col = ar.take<float>((size_t)rows * kp);
+    size_t col_elems = (size_t)rows * kp;
+    if (implicit_ok(c_in, src_nchw)) {   // the same region holds the padded input of the implicit GEMM
+        const size_t pad_elems = (size_t)b * (h + 2) * (w + 2) * c_in;
+        if (pad_elems > col_elems) col_elems = pad_elems;
+    }
+    float *col = ar.take<float>(col_elems);
     float *wsplit = ar.take<float>((size_t)2 * c_out * kp);
     if (!ar.ok()) {
         set_error("optex_conv3x3: workspace %zu < %zu bytes", workspace_bytes,
@@ -206,6 +241,24 @@ extern "C" int optex_conv3x3(const float *src, int src_nchw, int b, int h_src, i
         OPTEX_TRY(gemm_tc_split_and_fill(weight, wsplit, wsplit + nw, nw, nullptr, 0, 0u, st));
         gemm_tc_set_presplit(weight, wsplit, wsplit + nw);
         presplit = true;
+    }
+    // ---- implicit GEMM: pad once, the GEMM's TMA boxes gather the taps (no im2col matrix)
+    if (want_tc && tc_shape && terms == 3 && implicit_ok(c_in, src_nchw) && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        float *padded = col;   // the workspace's first region holds the padded input instead of an im2col chunk
+        const int64_t nw = (int64_t)c_out * kp;
+        if (!presplit) OPTEX_TRY(gemm_tc_split_and_fill(weight, wsplit, wsplit + nw, nw, nullptr, 0, 0u, st));
+        const int64_t items = (int64_t)b * (h + 2) * (w + 2) * (c_in / 4);
+        int64_t blocks = (items + 255) / 256;
+        const int64_t cap = (int64_t)sm_count() * 32;
+        if (blocks > cap) blocks = cap;
+        launch_pdl(pad_reflect_kernel, dim3((unsigned)blocks), dim3(256), 0, st, src, padded, g);
+        OPTEX_LAUNCH_CHECK("pad_reflect_kernel");
+        TcConv cv{padded, b, h, w, c_in, wsplit, wsplit + nw, c_out, bias, relu != 0, dst, ldd};
+        int rc_i = gemm_tc_conv(cv, st);
+        if (rc_i != OPTEX_ENOTSUP) {
+            if (presplit) gemm_tc_set_presplit(nullptr, nullptr, nullptr);
+            return rc_i;
+        }
     }
     int rc = OPTEX_OK;
     for (int64_t m0 = 0; m0 < M && rc == OPTEX_OK; m0 += rows) {
