@@ -31,6 +31,7 @@ namespace optex {
 namespace {
 
 constexpr int NS_MAX_ITERS = 24;
+constexpr int NS_SCALED_ITERS = 16;  // launch cap of the scaled iteration (ns_prepare_kernel)
 constexpr float NS_TOL = 3e-4f;
 constexpr int MAX_C = 1024;
 constexpr int PANEL = 64;
@@ -124,9 +125,15 @@ __global__ void bias_kernel(const float *__restrict__ G, const float *__restrict
 // slot kept the initial 0) - and every kernel of an iteration tests that one value.  Y / Z ping-pong between two
 // buffers, so the state after the last executed iteration k-1 sits in buffer k & 1.
 
-// one block: norm2[0] = sum A^2 (deterministic), resid[..] = 0
+// one block: norm2[0] = sum A^2 (deterministic), resid[..] = 0, and the coefficient schedule of the SCALED iteration.
+//   With M_k = Z_k Y_k (eigenvalues m in [l_k, 1]; M_0 = A / |A|_F, so l_0 = lambda_min(A) / |A|_F >= lmin / |A|_F) the
+//   step T_k = a_k I + b_k M_k, a_k = 1.5 sqrt(rho), b_k = -0.5 rho^1.5 is the plain step (rho = 1) applied to rho M_k;
+//   rho = 3 / (1 + sqrt(l) + l) maps both ends of [l, 1] to the same value l' = rho l (3 - rho l)^2 / 4 and keeps the
+//   maximum at 1: the small eigenvalues grow ~6x per iteration instead of 2.25x (8-9 real iterations instead of 13-16
+//   on PCA'd VGG covariances), the fixed point Y = (A/s)^(1/2), Z = (A/s)^(-1/2) is unchanged.  lmin <= 0: rho = 1.
+//   coefficients at norm2[8 + 2 it] = b_it (multiplies Z Y), norm2[9 + 2 it] = a_it (on the diagonal).
 __global__ void ns_prepare_kernel(const float *__restrict__ A, int64_t n, float *__restrict__ norm2, float *resid,
-                                  int iters) {
+                                  int iters, float lmin) {
     pdl_wait();
     __shared__ float red[32];
     float acc = 0.f;
@@ -137,7 +144,19 @@ __global__ void ns_prepare_kernel(const float *__restrict__ A, int64_t n, float 
     if (threadIdx.x < 32) {
         acc = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
         acc = warp_sum(acc);
-        if (threadIdx.x == 0) norm2[0] = acc;
+        if (threadIdx.x == 0) {
+            norm2[0] = acc;
+            double l = lmin > 0.f && acc > 0.f ? 0.9 * (double)lmin / sqrt((double)acc) : 1.0;   // 10 % under the bound
+            if (l > 1.0) l = 1.0;
+            for (int it = 0; it < iters; ++it) {
+                const double rho = l < 0.8 ? 3.0 / (1.0 + sqrt(l) + l) : 1.0;   // near convergence: the plain step
+                norm2[8 + 2 * it] = (float)(-0.5 * rho * sqrt(rho));
+                norm2[9 + 2 * it] = (float)(1.5 * sqrt(rho));
+                const double rl = rho * l;
+                l = 0.97 * rl * (3.0 - rl) * (3.0 - rl) * 0.25;   // the new lower end, 3 % under it for the rounding
+                if (l > 1.0) l = 1.0;
+            }
+        }
     }
     for (int i = threadIdx.x; i <= iters; i += blockDim.x) resid[i] = 0.f;
 }
@@ -152,7 +171,8 @@ __global__ void ns_init_kernel(const float *__restrict__ A, const float *__restr
     Z[i] = (i / c == i % c) ? 1.f : 0.f;
 }
 // T = 1.5 I - 0.5 T0 ;  resid[it] = max |T0 - I|   (only when the GEMM could not fuse it into its epilogue)
-__global__ void ns_t_kernel(const float *__restrict__ T0, float *__restrict__ T, int c, float *resid, int it) {
+__global__ void ns_t_kernel(const float *__restrict__ T0, float *__restrict__ T, int c, float *resid, int it,
+                            const float *__restrict__ coef) {
     pdl_wait();
     if (it > 0 && resid[it - 1] < NS_TOL) return;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -160,7 +180,7 @@ __global__ void ns_t_kernel(const float *__restrict__ T0, float *__restrict__ T,
     if (i < (int64_t)c * c) {
         const float eye = (i / c == i % c) ? 1.f : 0.f;
         const float t0 = T0[i];
-        T[i] = 1.5f * eye - 0.5f * t0;
+        T[i] = coef[1] * eye + coef[0] * t0;
         d = fabsf(t0 - eye);
         if (!(d == d)) d = INFINITY;
     }
@@ -345,7 +365,7 @@ struct Ws {
     float *norm2, *resid;   // Newton-Schulz state of chain 0; chain 1 (side stream) at +NS_STATE
     int *flags;
 };
-constexpr int NS_STATE = NS_MAX_ITERS + 8;  // floats / ints per chain
+constexpr int NS_STATE = 3 * NS_MAX_ITERS + 8;  // floats / ints per chain (norm2: [0] = |A|_F^2, [8 + 2 it ..] = step coefficients)
 
 // Newton-Schulz state of one chain
 struct NsState {
@@ -441,12 +461,20 @@ int moments(const float *X, int nb, int64_t hw, int c, float eps, float *mu, flo
 }
 
 // T = 1.5 I - 0.5 Z Y and resid[it] = max |Z Y - I|: fused into the tensor-core GEMM's epilogue, or GEMM + ns_t_kernel
-int ns_t_step(const float *Z, const float *Y, float *t0, float *t, int c, float *resid, int it, cudaStream_t st) {
+// OPTEX_NS_SCALED=0: the plain Newton-Schulz iteration (A/B comparisons)
+bool g_ns_scaled() {
+    static const char *env = getenv("OPTEX_NS_SCALED");
+    return !(env && atoi(env) == 0);
+}
+
+int ns_t_step(const float *Z, const float *Y, float *t0, float *t, int c, float *resid, int it, const float *coef,
+              cudaStream_t st) {
     const float *skip_below = it > 0 ? resid + it - 1 : nullptr;
     if (g_want_tc()) {
         TcGemm g{};
         g.A = Z; g.a_mn = false; g.B = Y; g.b_mn = true; g.D = t; g.ldd = c;
         g.M = g.N = g.K = c; g.terms = g_terms(); g.alpha = -0.5f; g.diag = 1.5f; g.resid_max = resid + it;
+        g.coef = coef;   // the scaled step's (b, a) replace (-0.5, 1.5)
         g.skip_below = skip_below; g.skip_tol = NS_TOL;
         int rc = gemm_tc(g, st);
         if (rc != OPTEX_ENOTSUP) return rc;
@@ -455,7 +483,7 @@ int ns_t_step(const float *Z, const float *Y, float *t0, float *t, int c, float 
     o.skip_below = skip_below;
     o.skip_tol = NS_TOL;
     OPTEX_TRY(sgemm_simt_ex(Z, c, true, Y, c, false, t0, c, false, c, c, c, nullptr, 0.f, 1.f, o, st));
-    launch_pdl(ns_t_kernel, dim3(cdiv((int64_t)c * c, 256)), dim3(256), 0, st, (const float *)t0, t, c, resid, it);
+    launch_pdl(ns_t_kernel, dim3(cdiv((int64_t)c * c, 256)), dim3(256), 0, st, (const float *)t0, t, c, resid, it, coef);
     OPTEX_LAUNCH_CHECK("ns_t_kernel");
     return OPTEX_OK;
 }
@@ -480,6 +508,7 @@ struct NsChain {
     const float *A;
     float *Y, *Z, *t0, *t, *yn, *zn;
     NsState w;
+    float lmin;   // a lower bound of A's smallest eigenvalue (eps for cov + eps I); <= 0: unknown -> unscaled iteration
 };
 
 // Up to two independent chains in lockstep.  Per iteration: ONE batched launch for the T steps of all chains and ONE
@@ -490,13 +519,20 @@ int ns_sqrt_multi(const NsChain *ch, int nch, int c, cudaStream_t st) {
     const unsigned nb = cdiv(cc, 256);
     for (int k = 0; k < nch; ++k) {
         launch_pdl(ns_prepare_kernel, dim3(1), dim3(1024), 0, st, ch[k].A, cc, ch[k].w.norm2, ch[k].w.resid,
-                   NS_MAX_ITERS);
+                   NS_MAX_ITERS, g_ns_scaled() ? ch[k].lmin : 0.f);
         OPTEX_LAUNCH_CHECK("ns_prepare_kernel");
         launch_pdl(ns_init_kernel, dim3(nb), dim3(256), 0, st, ch[k].A, (const float *)ch[k].w.norm2, ch[k].Y, ch[k].Z, c);
         OPTEX_LAUNCH_CHECK("ns_init_kernel");
     }
     bool batched = g_want_tc() && nch >= 1 && 2 * nch <= 4;
-    for (int it = 0; it < NS_MAX_ITERS; ++it) {
+    static const char *cap_env = getenv("OPTEX_NS_CAP");   // debug: fewer host-side iterations (results may not converge)
+    // the scaled iteration multiplies the lower end of the spectrum by ~6 per step: 16 steps cover |A|_F / lmin up to
+    // 1e9 (measured: 9-10 real steps on PCA'd covariances); the plain one keeps the 24
+    bool all_scaled = g_ns_scaled();
+    for (int k = 0; k < nch; ++k) all_scaled = all_scaled && ch[k].lmin > 0.f;
+    int max_it = all_scaled ? NS_SCALED_ITERS : NS_MAX_ITERS;
+    if (cap_env && atoi(cap_env) > 0 && atoi(cap_env) < max_it) max_it = atoi(cap_env);
+    for (int it = 0; it < max_it; ++it) {
         const int cur = it & 1, nxt = cur ^ 1;
         auto Yb = [&](int k, int i) { return i ? ch[k].yn : ch[k].Y; };
         auto Zb = [&](int k, int i) { return i ? ch[k].zn : ch[k].Z; };
@@ -509,6 +545,7 @@ int ns_sqrt_multi(const NsChain *ch, int nch, int c, cudaStream_t st) {
             for (int k = 0; k < nch; ++k) {
                 g.A_z[k] = Zb(k, cur); g.B_z[k] = Yb(k, cur); g.D_z[k] = ch[k].t;
                 g.resid_z[k] = ch[k].w.resid + it; g.skip_z[k] = skip_of(k);
+                g.coef_z[k] = ch[k].w.norm2 + 8 + 2 * it;
             }
             const int rc = gemm_tc(g, st);
             if (rc == OPTEX_OK) done = true;
@@ -517,7 +554,8 @@ int ns_sqrt_multi(const NsChain *ch, int nch, int c, cudaStream_t st) {
         }
         if (!done)
             for (int k = 0; k < nch; ++k)
-                OPTEX_TRY(ns_t_step(Zb(k, cur), Yb(k, cur), ch[k].t0, ch[k].t, c, ch[k].w.resid, it, st));
+                OPTEX_TRY(ns_t_step(Zb(k, cur), Yb(k, cur), ch[k].t0, ch[k].t, c, ch[k].w.resid, it,
+                                    ch[k].w.norm2 + 8 + 2 * it, st));
         done = false;
         if (batched) {
             TcGemm g{};
@@ -542,15 +580,15 @@ int ns_sqrt_multi(const NsChain *ch, int nch, int c, cudaStream_t st) {
     for (int k = 0; k < nch; ++k) {
         launch_pdl(ns_finish_kernel, dim3(nb), dim3(256), 0, st, (const float *)ch[k].Y, (const float *)ch[k].yn,
                    (const float *)ch[k].Z, (const float *)ch[k].zn, ch[k].Y, ch[k].Z, (const float *)ch[k].w.norm2,
-                   (const float *)ch[k].w.resid, NS_MAX_ITERS, c);
+                   (const float *)ch[k].w.resid, max_it, c);
         OPTEX_LAUNCH_CHECK("ns_finish_kernel");
     }
     return OPTEX_OK;
 }
 
 int ns_sqrt(const float *A, float *Y, float *Z, float *t0, float *t, float *yn, float *zn, int c, const NsState &w,
-            cudaStream_t st) {
-    const NsChain ch{A, Y, Z, t0, t, yn, zn, w};
+            float lmin, cudaStream_t st) {
+    const NsChain ch{A, Y, Z, t0, t, yn, zn, w, lmin};
     return ns_sqrt_multi(&ch, 1, c, st);
 }
 
@@ -695,7 +733,7 @@ int cov_ot_step(const float *P, const float *S, const float *R, float *out, int 
         }
         if (mode == OPTEX_MODE_CHOL) return cholesky(sig_t, c, st);
         if (mode == OPTEX_MODE_PCA) return OPTEX_OK;
-        return ns_sqrt(sig_t, Y, Z, t0, t, yn, zn, c, ns_a, st);
+        return ns_sqrt(sig_t, Y, Z, t0, t, yn, zn, c, ns_a, eps, st);
     };
     const int rc_a = main_chain();
     if (join_err == cudaSuccess) join_err = cudaStreamWaitEvent(st, side->join, 0);
@@ -706,13 +744,14 @@ int cov_ot_step(const float *P, const float *S, const float *R, float *out, int 
         OPTEX_TRY(transpose_f32(sig_t, tmp, c, c, st));
         OPTEX_TRY(trsm_right(sig_s, tmp, T, c, st));
     } else if (mode == OPTEX_MODE_PCA) {  // T = Sig_s^(1/2) Sig_t^(-1/2)   histmatch.py:29-34
-        const NsChain chains[2] = {{sig_t, Y, Z, t0, t, yn, zn, ns_a}, {sig_s, Y2, Z2, t0_b, t_b, yn_b, zn_b, ns_b}};
+        const NsChain chains[2] = {{sig_t, Y, Z, t0, t, yn, zn, ns_a, eps}, {sig_s, Y2, Z2, t0_b, t_b, yn_b, zn_b, ns_b, eps}};
         OPTEX_TRY(ns_sqrt_multi(chains, style_reuse ? 1 : 2, c, st));   // reuse: Y2 = Sig_s^(1/2) is still there
         OPTEX_TRY(mm(Y2, false, Z, false, T, c, 1.f, nullptr, st));
     } else {  // sym: T = Qt^-1 (Qt Sig_s Qt)^(1/2) Qt^-1                   histmatch.py:36-42
         OPTEX_TRY(mm(Y, false, sig_s, false, tmp, c, 1.f, nullptr, st));
         OPTEX_TRY(mm(tmp, false, Y, false, aux, c, 1.f, nullptr, st));
-        OPTEX_TRY(ns_sqrt(aux, Y2, Z2, t0, t, yn, zn, c, ns_a, st));
+        // Qt Sig_s Qt >= lambda_min(Qt)^2 lambda_min(Sig_s) >= eps * eps
+        OPTEX_TRY(ns_sqrt(aux, Y2, Z2, t0, t, yn, zn, c, ns_a, eps * eps, st));
         OPTEX_TRY(mm(Z, false, Y2, false, tmp, c, 1.f, nullptr, st));
         OPTEX_TRY(mm(tmp, false, Z, false, T, c, 1.f, nullptr, st));
     }

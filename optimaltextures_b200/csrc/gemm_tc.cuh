@@ -52,6 +52,9 @@ struct TcGemm {
     float *D_z[4];
     float *resid_z[4];
     const float *skip_z[4];
+    // alpha / diag from device memory (coef[0], coef[1]) instead of the host values above; per problem in batch mode
+    const float *coef;
+    const float *coef_z[4];
     // a second problem with the same B, N, K in the same launch (K-major A only; forward rotation of P and S)
     const float *A2;
     int64_t M2, ldd2;

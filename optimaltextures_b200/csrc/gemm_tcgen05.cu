@@ -350,6 +350,10 @@ struct Params {
     // output map in tmD2; tiles of problem 0 come first in the tile list.
     int64_t M2, ldd2;
     float *D2;
+    // !D_TRANS: alpha and diag read from DEVICE memory (coef[0], coef[1]) - the scaled Newton-Schulz step, whose
+    // coefficients depend on a norm computed on the device (cov_match.cu); per problem in batch mode
+    const float *coef;
+    const float *coef_z[MAX_BATCH];
     // conv (TMEM-A launches, K-major A): implicit GEMM of a 3 x 3 convolution (vgg.cu).  The A operand is never
     // materialised: an M tile is a CONV_TH x CONV_TW block of output pixels of one image and k block kb = 32 input
     // channels of tap kb * 32 / c_in, loaded by ONE 4-D TMA box {32 ch, CONV_TW, CONV_TH, 1} at the tap's offset from
@@ -858,6 +862,8 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
             const bool second = tiles_dual > 0 && z == 1;
             float *const Dz = second ? p.D2 : p.D + (p.batch > 0 ? p.d_off[z] : (int64_t)z * p.d_z_stride);
             const int64_t Mz = second ? p.M2 : p.M, lddz = second ? p.ldd2 : p.ldd;
+            const float *const cf = p.batch > 0 ? p.coef_z[z] : p.coef;
+            const float alpha_e = cf ? __ldg(cf) : p.alpha, diag_e = cf ? __ldg(cf + 1) : p.diag;
             const CUtensorMap *const dmap = second ? &tmD2 : &tmD;
             float *const resid_max = p.batch > 0 ? p.resid_z[z] : p.resid_max;
             if (warp == EPI_WARP0 && lane == 0) stamp(3, tcur, 0);
@@ -959,18 +965,18 @@ rotate_gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
                     const float *bias = (p.bias && row < Mz) ? p.bias + (row / p.bias_hw) * p.bias_ld + n0 + col : nullptr;
                     // the rotations use none of the optional epilogue terms: their per-element tests (five runtime
                     // conditions x 64 values per thread) cost 9.5 k cycles per 32-column chunk - measured with the stamps
-                    const bool extras = resid_max != nullptr || p.diag != 0.f || bias != nullptr || p.relu != 0 ||
-                                        p.rowrange != nullptr || p.alpha != 1.f;
+                    const bool extras = resid_max != nullptr || diag_e != 0.f || bias != nullptr || p.relu != 0 ||
+                                        p.rowrange != nullptr || alpha_e != 1.f;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         if (!extras) break;
-                        float o = p.alpha * __uint_as_float(v[j]);
+                        float o = alpha_e * __uint_as_float(v[j]);
                         if (resid_max && row < Mz && n0 + col + j < p.N) {
                             float d = fabsf(__uint_as_float(v[j]) - (row == (int64_t)n0 + col + j ? 1.f : 0.f));
                             if (!(d == d)) d = INFINITY;
                             rres = fmaxf(rres, d);
                         }
-                        if (p.diag != 0.f && row == (int64_t)n0 + col + j) o = __fadd_rn(o, p.diag);
+                        if (diag_e != 0.f && row == (int64_t)n0 + col + j) o = __fadd_rn(o, diag_e);
                         if (bias && n0 + col + j < p.N) o = __fadd_rn(o, __ldg(bias + j));
                         if (p.relu) o = o < 0.f ? 0.f : o;
                         v[j] = __float_as_uint(o);
@@ -1412,6 +1418,7 @@ static int gemm_tc_batched(const TcGemm &g, cudaStream_t st) {
         p.d_off[i] = dd;
         p.resid_z[i] = g.resid_z[i];
         p.skip_z[i] = g.skip_z[i];
+        p.coef_z[i] = g.coef_z[i];
         if (p.a_off[i] + g.M > a_rows) a_rows = p.a_off[i] + g.M;
         const int64_t bext = p.b_off[i] + (g.b_mn ? g.K : g.N);
         if (bext > b_rows) b_rows = bext;
@@ -1515,6 +1522,7 @@ int gemm_tc(const TcGemm &g, cudaStream_t st) {
     p.diag = g.d_trans ? 0.f : g.diag; p.resid_max = g.d_trans ? nullptr : g.resid_max;
     p.skip_below = g.skip_below; p.skip_tol = g.skip_tol; p.relu = (g.relu && !g.d_trans) ? 1 : 0;
     p.alpha = g.alpha; p.skip = g.skip; p.conv_a = p.terms == 3 ? 1 : 0; p.conv_b = conv_b ? 1 : 0;
+    p.coef = g.d_trans ? nullptr : g.coef;
     p.a_tmem = a_tmem ? 1 : 0;
     // Round 1 routed 64-wide multi-tile launches away from the TMEM-A form because of a timing-dependent corruption;
     // the cause was the early release of the raw-A slot in the converters (see there).  OPTEX_ATMEM64=0 restores the
