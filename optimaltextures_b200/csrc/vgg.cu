@@ -5,14 +5,15 @@
 //   none | MaxPool2d(2, 2, ceil_mode=True) (vgg.py:27,36,51,68) | UpsamplingNearest2d(2) (vgg.py:82,98,114,122)
 // (the encoder's leading 1x1 colour conv, vgg.py:16, is folded into conv1_1's weights by the host code).
 //
-// B200 formulation: explicit GEMM on the tcgen05 kernel of the rotations.  A gather kernel writes the im2col matrix
-// col[m, k] (m = output pixel, k = tap * c_in + ci) with the reflection, the pooling window or the nearest-neighbour
-// up-sampling resolved in its index arithmetic - the padded / pooled / up-sampled tensors are never materialised -
-// and the GEMM  out[m, co] = sum_k col[m, k] W[co, k]  adds the bias and applies the ReLU in its epilogue, writing
-// NHWC, which is the layout the OT loop wants (the reference permutes, vgg.py:153 `to_nhwc`).  Rows are processed
-// in chunks so that a col chunk (default 32 MB) is still in the 126 MB L2 when the GEMM reads it back: HBM sees
-// the activations once in and once out.  Layouts: activations NHWC [b, h, w, c] fp32; the very first layer may read
-// the NCHW image directly (src_nchw).  Arithmetic: the library's GEMM mode (3xTF32 by default: fp32-grade).
+// B200 formulation: IMPLICIT GEMM on the tcgen05 kernel of the rotations (every layer with c_in % 32 == 0).  One pass
+// (pad_reflect_kernel) materialises the reflection-padded input - the pooling window or the nearest-neighbour
+// up-sampling resolved in its index arithmetic - and the GEMM's TMA producer gathers the nine taps from it with
+// shifted 4-D boxes: out[pixel, co] = sum_k A(pixel, k) W[co, k], k = tap * c_in + ci, A never materialised
+// (gemm_tcgen05.cu, Params::conv).  Bias and ReLU ride in the epilogue, which writes NHWC - the layout the OT loop
+// wants (the reference permutes, vgg.py:153 `to_nhwc`).  The encoder's conv1_1 (c_in = 3) keeps the explicit form: a
+// gather kernel writes the im2col matrix col[m, k] in 512 MB row chunks and the same GEMM reads it.
+// Layouts: activations NHWC [b, h, w, c] fp32; the very first layer may read the NCHW image directly (src_nchw).
+// Arithmetic: the library's GEMM mode (3xTF32 by default: fp32-grade).
 #include <cuda_runtime.h>
 #include <stdlib.h>
 
