@@ -307,7 +307,11 @@ int optex_rotate_inverse(const float *Mt, const float *R, float *out, int64_t n,
  *   sigma   [c]    fp32 singular values, descending (for n < c the trailing c - n are ~0);
  *   k_out   [1]    int32 ON THE DEVICE: the number of leading columns the reference keeps
  *                  (first index where cumsum(sigma / sum(sigma)) > 0.9, optex.py:184).
- * c <= 1024.  Asynchronous like everything else: read k_out after synchronising the stream. */
+ * c <= 1024.  Asynchronous like everything else: read k_out after synchronising the stream.
+ * Solver (cold solve, basis == NULL): one-sided Jacobi on the rows of G in a BLOCKED order - blocks of 8 rows paired
+ * round-robin across CTAs (c / 8 - 1 grid barriers per sweep), all 8 x 8 cross pairs of a block pair rotated inside
+ * the CTA between two barriers; no V is carried (the eigenvectors are the normalised rows).  OPTEX_PCA_SOLVER=0
+ * selects the round-robin kernel (c - 1 barriers per sweep), which is also what a `basis` request uses. */
 size_t optex_fit_pca_workspace_bytes(int64_t n, int c);
 int optex_fit_pca(const float *X, int64_t n, int c, float *eigvecs, float *sigma,
                   int32_t *k_out, void *workspace, size_t workspace_bytes, void *stream);
@@ -323,6 +327,10 @@ int optex_fit_pca(const float *X, int64_t n, int c, float *eigvecs, float *sigma
 int optex_fit_pca_warm(const float *X, int64_t n, int c, float *eigvecs, float *sigma, int32_t *k_out,
                        double *basis, int warm, int32_t *sweeps_out, void *workspace,
                        size_t workspace_bytes, void *stream);
+/* Debug hook (no reference counterpart; scripts/pca_stamps.py): a device buffer of 5 * n int64 that CTA 1 of the
+ * blocked-order solver fills with clock64 stamps of its first n global rounds (round start, rows loaded, sub-rounds
+ * done, rows stored, barrier passed).  NULL switches it off (the default). */
+int optex_debug_pca_stamps(long long *device_buffer, int n);
 /* transpose = 0: out[n, k] = X[n, c] V[c, k]      (project onto the basis,  optex.py:110, :188)
  * transpose = 1: out[n, c] = X[n, k] V[c, k]^T    (back to feature space,   optex.py:120)
  * V dense row-major [c, k].  Tensor cores when c and k allow (k % 32 == 0, c % 4 == 0), else fp32 SIMT tiles. */

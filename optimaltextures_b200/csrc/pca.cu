@@ -329,6 +329,311 @@ __global__ void __launch_bounds__(JT) pca_jacobi_kernel(double *W, double *V, co
     if (blockIdx.x == 0 && tid == 0) info[0] = sweep < max_sweeps ? sweep + 1 : max_sweeps;  // sweeps started
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Blocked-order one-sided Jacobi (round 2; the cold solve).  The same rotations as pca_jacobi_kernel, ordered so
+// that most of them need no grid-wide synchronisation: the rows of W form c_pad / BR blocks of BR = 8 rows; a
+// "global round" pairs the blocks round-robin (one CTA per block pair, the grid barrier and the trip through L2
+// happen HERE: nb - 1 times per sweep instead of c - 1), and inside a global round the CTA rotates all BR x BR
+// cross pairs of its two blocks in BR sub-rounds of BR disjoint pairs (one warp per pair, __syncthreads between
+// sub-rounds): warp w keeps row w of block A in registers for the whole global round while the rows of block B pass
+// by through shared memory.  Global round 0 of every sweep runs the full 2 BR-row tournament instead, which also
+// covers the pairs inside each block - every pair of rows meets exactly once per sweep.  Sweep counts are those of
+// the round-robin order for full-rank blocks and ~25 % higher for rank-deficient ones (scripts/jacobi_sim.py
+// --blocked-order); a sweep costs nb - 1 = 63 barriers at c = 512 instead of 511.
+// No V: W starts as G, so at convergence row i is lambda_i v_i - the eigenvectors are the normalised rows and
+// lambda_i = |w_i| (pca_finish_rows_kernel); the null-space rows carry no direction, which the 90 % rule never keeps.
+// Layout: W is [c_pad][ld] with ld = 32 EPL >= c, zero padded; lane l of a warp holds the double2 chunks l, l + 32, ...
+constexpr int BR = 8;
+
+__device__ __forceinline__ void grid_barrier(unsigned *counter, unsigned &target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += gridDim.x;
+        unsigned seen;
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+        } while ((int)(seen - target) < 0);
+    }
+    __syncthreads();
+}
+
+// One pair: the rows a, b (this lane's chunks) with their squared norms al, be.  Only w_a . w_b is reduced over the
+// warp - the norms are carried along exactly (|a'|^2 = al - t ga, |b'|^2 = be + t ga with t = tan(theta)) and
+// recomputed from the data once per global round.  The angle without a division (FP64 div / sqrt are ~30-instruction
+// dependent sequences, four of them sat on every sub-round's critical path): with d = be - al, g = 2 ga,
+// r = 1 / hypot(d, g):  cos^2 = (1 + |d| r) / 2,  sin = sign(d) g r / (2 cos)  - two rsqrt.
+template <int NV>
+__device__ __forceinline__ void pair_step(double2 (&a)[NV], double2 (&b)[NV], double &al, double &be,
+                                          double floor_abs, double exit_r2, unsigned &rot, unsigned &big) {
+    double g0 = 0.0, g1 = 0.0;
+#pragma unroll
+    for (int e = 0; e < NV; ++e) {
+        g0 = fma(a[e].x, b[e].x, g0);
+        g1 = fma(a[e].y, b[e].y, g1);
+    }
+    const double ga = warp_sum(g0 + g1);
+    const double g2 = ga * ga, ab = al * be;
+    if (!(g2 > JTOL * JTOL * ab && fabs(ga) > floor_abs)) return;
+    if (g2 > exit_r2 * ab) big = 1u;
+    const double d = be - al, g = 2.0 * ga;
+    const double r = rsqrt(fma(d, d, g * g));
+    const double x = fma(0.5 * fabs(d), r, 0.5);  // cos^2 in [1/2, 1]
+    const double ic = rsqrt(x);
+    const double cs = x * ic, sn = (d >= 0.0 ? 0.5 : -0.5) * g * r * ic, t = sn * ic;
+#pragma unroll
+    for (int e = 0; e < NV; ++e) {
+        const double ax = a[e].x, ay = a[e].y, bx = b[e].x, by = b[e].y;
+        a[e].x = fma(cs, ax, -sn * bx);
+        a[e].y = fma(cs, ay, -sn * by);
+        b[e].x = fma(sn, ax, cs * bx);
+        b[e].y = fma(sn, ay, cs * by);
+    }
+    al = fmax(fma(-t, ga, al), 0.0);
+    be = fma(t, ga, be);
+    ++rot;
+}
+
+template <int NV>
+__device__ __forceinline__ double row_norm2(const double2 (&a)[NV]) {
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int e = 0; e < NV; ++e) {
+        s0 = fma(a[e].x, a[e].x, s0);
+        s1 = fma(a[e].y, a[e].y, s1);
+    }
+    return warp_sum(s0 + s1);
+}
+
+template <int EPL>
+__global__ void __launch_bounds__(BR * 32) pca_jacobi_blk_kernel(double *W, int c_pad, int max_sweeps,
+                                                                 unsigned *rot_count, unsigned *rot_max,
+                                                                 float exit_r2f, int *info, const double *stat,
+                                                                 unsigned *bar, long long *stamps, int n_stamps) {
+    constexpr int LD = 32 * EPL, NV = EPL / 2;
+    extern __shared__ __align__(16) unsigned char jsm_raw[];
+    double2 *rows = reinterpret_cast<double2 *>(jsm_raw);  // [2 BR][LD / 2]: block A rows 0..7, block B rows 8..15
+    __shared__ double nrm[2 * BR];                         // their squared norms
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double tr = stat[2];
+    const double floor_abs = (JFLOOR * tr) * (JFLOOR * tr), exit_r2 = (double)exit_r2f;
+    const int nb = c_pad / BR, n1 = nb - 1;
+    unsigned target = 0, local_rot = 0, local_big = 0;
+    int sweep = 0;
+    auto srow = [&](int r) { return rows + (size_t)r * (LD / 2); };
+    for (; sweep < max_sweeps; ++sweep) {
+        for (int gr = 0; gr < n1; ++gr) {
+            const int pi = blockIdx.x;
+            const int A = pi == 0 ? n1 : (gr + pi) % n1;
+            const int B = pi == 0 ? gr : (gr - pi + n1) % n1;
+            // debug stamps (optex_debug_pca_stamps): clock64 of CTA 1's thread 0 at 5 points of its first rounds
+            const int sidx = sweep * n1 + gr;
+            const bool stamp = stamps && blockIdx.x == 1 && tid == 0 && sidx < n_stamps;
+            if (stamp) stamps[5 * sidx + 0] = clock64();
+            double2 *ga_row = reinterpret_cast<double2 *>(W + (size_t)(A * BR + warp) * LD);
+            double2 *gb_row = reinterpret_cast<double2 *>(W + (size_t)(B * BR + warp) * LD);
+            double2 a[NV], b[NV];
+#pragma unroll
+            for (int e = 0; e < NV; ++e) {
+                a[e] = __ldcg(ga_row + lane + 32 * e);
+                b[e] = __ldcg(gb_row + lane + 32 * e);
+            }
+#pragma unroll
+            for (int e = 0; e < NV; ++e) srow(BR + warp)[lane + 32 * e] = b[e];
+            double al = row_norm2<NV>(a);
+            {
+                const double be = row_norm2<NV>(b);
+                if (lane == 0) nrm[BR + warp] = be;
+            }
+            if (gr == 0) {
+                // the full tournament of the 2 BR rows (15 sub-rounds): both rows of a pair through shared memory
+#pragma unroll
+                for (int e = 0; e < NV; ++e) srow(warp)[lane + 32 * e] = a[e];
+                if (lane == 0) nrm[warp] = al;
+                __syncthreads();
+                constexpr int M1 = 2 * BR - 1;
+                for (int sr = 0; sr < M1; ++sr) {
+                    const int x = warp == 0 ? M1 : (sr + warp) % M1;
+                    const int y = warp == 0 ? sr : (sr - warp + M1) % M1;
+#pragma unroll
+                    for (int e = 0; e < NV; ++e) {
+                        a[e] = srow(x)[lane + 32 * e];
+                        b[e] = srow(y)[lane + 32 * e];
+                    }
+                    double nx = nrm[x], ny = nrm[y];
+                    const unsigned before = local_rot;
+                    pair_step<NV>(a, b, nx, ny, floor_abs, exit_r2, local_rot, local_big);
+                    if (local_rot != before) {
+#pragma unroll
+                        for (int e = 0; e < NV; ++e) {
+                            srow(x)[lane + 32 * e] = a[e];
+                            srow(y)[lane + 32 * e] = b[e];
+                        }
+                        if (lane == 0) {
+                            nrm[x] = nx;
+                            nrm[y] = ny;
+                        }
+                    }
+                    __syncthreads();
+                }
+#pragma unroll
+                for (int e = 0; e < NV; ++e) {
+                    __stcg(ga_row + lane + 32 * e, srow(warp)[lane + 32 * e]);
+                    __stcg(gb_row + lane + 32 * e, srow(BR + warp)[lane + 32 * e]);
+                }
+            } else {
+                __syncthreads();
+                if (stamp) stamps[5 * sidx + 1] = clock64();
+                for (int sr = 0; sr < BR; ++sr) {
+                    const int j = BR + ((warp + sr) & (BR - 1));
+#pragma unroll
+                    for (int e = 0; e < NV; ++e) b[e] = srow(j)[lane + 32 * e];
+                    double be = nrm[j];
+                    const unsigned before = local_rot;
+                    pair_step<NV>(a, b, al, be, floor_abs, exit_r2, local_rot, local_big);
+                    if (local_rot != before) {
+#pragma unroll
+                        for (int e = 0; e < NV; ++e) srow(j)[lane + 32 * e] = b[e];
+                        if (lane == 0) nrm[j] = be;
+                    }
+                    __syncthreads();
+                }
+                if (stamp) stamps[5 * sidx + 2] = clock64();
+#pragma unroll
+                for (int e = 0; e < NV; ++e) {
+                    __stcg(ga_row + lane + 32 * e, a[e]);
+                    __stcg(gb_row + lane + 32 * e, srow(BR + warp)[lane + 32 * e]);
+                }
+            }
+            if (gr == n1 - 1 && lane == 0 && local_rot) {
+                atomicAdd(&rot_count[sweep], local_rot);
+                if (local_big) atomicMax(&rot_max[sweep], __float_as_uint(1.0f));  // "a pair above the exit level"
+            }
+            if (stamp) stamps[5 * sidx + 3] = clock64();
+            grid_barrier(bar, target);
+            if (stamp) stamps[5 * sidx + 4] = clock64();
+        }
+        local_rot = 0;
+        local_big = 0;
+        if (__ldcg(&rot_count[sweep]) == 0u) break;
+        if (__ldcg(&rot_max[sweep]) == 0u) break;  // every rotated pair was below the exit level: converged
+    }
+    if (blockIdx.x == 0 && tid == 0) info[0] = sweep < max_sweeps ? sweep + 1 : max_sweeps;
+}
+
+// Wp[c_pad][ld] = G zero-padded;  stat[2] = trace(G)
+__global__ void __launch_bounds__(256) pca_pad_kernel(const double *__restrict__ G, int c, int c_pad, int ld,
+                                                      double *__restrict__ Wp, double *__restrict__ stat) {
+    pdl_wait();
+    const int64_t total = (int64_t)c_pad * ld;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int i = (int)(idx / ld), j = (int)(idx % ld);
+        Wp[idx] = (i < c && j < c) ? G[(int64_t)i * c + j] : 0.0;
+    }
+    if (blockIdx.x == 0) {
+        __shared__ double red[8];
+        double tr = 0.0;
+        for (int i = threadIdx.x; i < c; i += 256) tr += G[(int64_t)i * c + i];
+        tr = warp_sum(tr);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = tr;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            tr = 0.0;
+            for (int i = 0; i < 8; ++i) tr += red[i];
+            stat[2] = tr;
+        }
+    }
+}
+
+// The no-V finish: lambda_i = |w_i|, descending order, sigma = sqrt(lambda), the 90 % rule (optex.py:184);
+// scale[i] = +-1 / |w_i| (the component of largest magnitude of every eigenvector positive), 0 for a null row
+__global__ void __launch_bounds__(1024) pca_finish_rows_kernel(const double *__restrict__ W, int ld, int c,
+                                                               float *__restrict__ sigma, int32_t *__restrict__ k_out,
+                                                               int *__restrict__ perm, double *__restrict__ scale) {
+    pdl_wait();
+    __shared__ double lam[PCA_MAX_C];
+    __shared__ float sg[PCA_MAX_C];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = warp; i < c; i += 32) {
+        const double *w = W + (int64_t)i * ld;
+        double ww = 0.0, best = -1.0;
+        int besti = 0;
+        for (int k = lane; k < c; k += 32) {
+            const double x = w[k];
+            ww = fma(x, x, ww);
+            if (fabs(x) > best) {
+                best = fabs(x);
+                besti = k;
+            }
+        }
+        ww = warp_sum(ww);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+            if (ob > best || (ob == best && oi < besti)) {
+                best = ob;
+                besti = oi;
+            }
+        }
+        if (lane == 0) {
+            const double nrm = sqrt(ww);
+            lam[i] = nrm;
+            scale[i] = nrm > 0.0 ? (w[besti] < 0.0 ? -1.0 : 1.0) / nrm : 0.0;
+        }
+    }
+    __syncthreads();
+    if (tid < c) {
+        const double mine = lam[tid];
+        int rank = 0;
+        for (int j = 0; j < c; ++j) {
+            const double o = lam[j];
+            rank += (o > mine || (o == mine && j < tid)) ? 1 : 0;
+        }
+        perm[rank] = tid;
+        sg[rank] = (float)sqrt(mine);
+    }
+    __syncthreads();
+    if (tid < c) sigma[tid] = sg[tid];
+    if (tid == 0) {
+        float total = 0.f;
+        for (int i = 0; i < c; ++i) total = __fadd_rn(total, sg[i]);
+        float cum = 0.f;
+        int k = 0;
+        for (int i = 0; i < c; ++i) {
+            cum = __fadd_rn(cum, __fdiv_rn(sg[i], total));
+            if (cum > 0.9f) {
+                k = i;
+                break;
+            }
+        }
+        k_out[0] = k;
+    }
+}
+
+// eigvecs[r][j] = scale[perm[j]] * W[perm[j]][r]  (fp32; column j = j-th principal direction)
+__global__ void pca_vecs_rows_kernel(const double *__restrict__ W, int ld, const int *__restrict__ perm,
+                                     const double *__restrict__ scale, int c, float *__restrict__ eigvecs) {
+    pdl_wait();
+    __shared__ float tile[32][33];
+    const int j0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int jj = threadIdx.y; jj < 32; jj += 8) {
+        const int j = j0 + jj, r = r0 + threadIdx.x;
+        float v = 0.f;
+        if (j < c && r < c) {
+            const int src = perm[j];
+            v = (float)(scale[src] * W[(int64_t)src * ld + r]);
+        }
+        tile[jj][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int rr = threadIdx.y; rr < 32; rr += 8) {
+        const int r = r0 + rr, j = j0 + threadIdx.x;
+        if (r < c && j < c) eigvecs[(int64_t)r * c + j] = tile[threadIdx.x][rr];
+    }
+}
+
 // lambda_i = v_i . w_i, descending order, sigma = sqrt(lambda), the 90 % rule (optex.py:184), sign convention
 __global__ void __launch_bounds__(1024) pca_finish_kernel(const double *__restrict__ W, const double *__restrict__ V,
                                                           int c, float *__restrict__ sigma, int32_t *__restrict__ k_out,
@@ -421,11 +726,19 @@ __global__ void pca_vecs_kernel(const double *__restrict__ V, const int *__restr
 }
 
 struct PcaWs {
-    double *colpart, *s, *stat, *gpart, *W, *V;
-    unsigned *rot, *rotmax;
+    double *colpart, *s, *stat, *gpart, *W, *V, *Wp, *scale;
+    unsigned *rot, *rotmax, *bar;
     int *info, *perm;
     float *sign;
 };
+
+// padded shape of the blocked-order solver: rows to a multiple of 2 BR, row length 32 EPL in {64, ..., 1024}
+inline int blk_ld(int c) {
+    int ld = 64;
+    while (ld < c) ld *= 2;
+    return ld;
+}
+inline int blk_rows(int c) { return (c + 2 * BR - 1) / (2 * BR) * (2 * BR); }
 
 int gram_splits(int64_t n, int c) {
     const int T = (c + GT - 1) / GT;
@@ -452,6 +765,9 @@ size_t pca_layout(int64_t n, int c, PcaWs *w, void *base, size_t cap, bool *ok) 
     l.info = ar.take<int>(8);
     l.perm = ar.take<int>(c);
     l.sign = ar.take<float>(c);
+    l.Wp = ar.take<double>((size_t)blk_rows(c) * blk_ld(c));
+    l.scale = ar.take<double>(c);
+    l.bar = ar.take<unsigned>(8);
     if (w) *w = l;
     if (ok) *ok = ar.ok();
     return ar.off;
@@ -489,10 +805,58 @@ int launch_jacobi(const PcaWs &w, const double *G, int c, cudaStream_t st) {
     return OPTEX_OK;
 }
 
+long long *g_pca_stamps = nullptr;  // optex_debug_pca_stamps
+int g_pca_n_stamps = 0;
+
+template <int EPL>
+int launch_jacobi_blk(const PcaWs &w, int c, cudaStream_t st) {
+    const int c_pad = blk_rows(c);
+    const size_t smem = (size_t)2 * BR * 32 * EPL * sizeof(double);
+    static bool attr_done[64] = {};
+    int dev = 0;
+    OPTEX_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+        OPTEX_CUDA(cudaFuncSetAttribute(pca_jacobi_blk_kernel<EPL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem));
+        if (dev >= 0 && dev < 64) attr_done[dev] = true;
+    }
+    double *W = w.Wp;
+    int cp = c_pad, ms = MAX_SWEEPS;
+    unsigned *rot = w.rot, *rotmax = w.rotmax, *bar = w.bar;
+    int *info = w.info;
+    const double *stat = w.stat;
+    float exit_r2 = jacobi_exit_r2();
+    long long *stamps = g_pca_stamps;
+    int n_stamps = g_pca_n_stamps;
+    void *args[] = {&W, &cp, &ms, &rot, &rotmax, &exit_r2, &info, &stat, &bar, &stamps, &n_stamps};
+    // cooperative launch: the c_pad / 16 CTAs (<= 64) spin on each other in grid_barrier and must be co-resident
+    OPTEX_CUDA(cudaLaunchCooperativeKernel((const void *)pca_jacobi_blk_kernel<EPL>, dim3(c_pad / (2 * BR)),
+                                           dim3(BR * 32), args, smem, st));
+    count_launch();
+    return OPTEX_OK;
+}
+
+// OPTEX_PCA_SOLVER=0: the round-robin kernel (one grid barrier per round) also for cold solves
+bool blocked_solver_enabled() {
+    static const bool v = [] {
+        const char *e = getenv("OPTEX_PCA_SOLVER");
+        return !(e && atoi(e) == 0);
+    }();
+    return v;
+}
+
 }  // namespace
 }  // namespace optex
 
 using namespace optex;
+
+// Debug hook (scripts/pca_stamps.py): device buffer of 5 * n clock64 stamps written by CTA 1 of the blocked-order
+// solver (round start / rows loaded / sub-rounds done / rows stored / barrier passed); NULL switches it off.
+extern "C" int optex_debug_pca_stamps(long long *device_buffer, int n) {
+    g_pca_stamps = device_buffer;
+    g_pca_n_stamps = device_buffer ? n : 0;
+    return OPTEX_OK;
+}
 
 extern "C" size_t optex_fit_pca_workspace_bytes(int64_t n, int c) {
     if (n < 1 || c < 1 || c > PCA_MAX_C) return 0;
@@ -539,30 +903,55 @@ extern "C" int optex_fit_pca_warm(const float *X, int64_t n, int c, float *eigve
     gs = (int)((n + rows - 1) / rows);
     launch_pdl(pca_gram_kernel, dim3(T * (T + 1) / 2, gs), dim3(256), 0, st, X, w.gpart, n, c, T, rows);
     OPTEX_LAUNCH_CHECK("pca_gram_kernel");
-    // the solver works directly in the caller's basis buffer when there is one (V is both the start and the result)
-    double *G = w.V;  // warm: the workspace's V slot is free and holds G until W = V G is formed
-    if (basis) w.V = basis;
-    launch_pdl(pca_gram_final_kernel, dim3(cdiv((int64_t)c * c, 256)), dim3(256), 0, st, (const double *)w.gpart, gs,
-               (const double *)w.s, (const double *)w.stat, c, warm ? G : w.W, warm ? (double *)nullptr : w.V);
-    OPTEX_LAUNCH_CHECK("pca_gram_final_kernel");
-    if (warm) {
-        launch_pdl(pca_warm_kernel, dim3(T, T), dim3(256), 0, st, (const double *)w.V, (const double *)G, w.W, c);
-        OPTEX_LAUNCH_CHECK("pca_warm_kernel");
-    }
     OPTEX_CUDA(cudaMemsetAsync(w.rot, 0, sizeof(unsigned) * 2 * (MAX_SWEEPS + 8), st));
-    if (c <= JT)
-        OPTEX_TRY(launch_jacobi<1>(w, warm ? G : w.W, c, st));
-    else if (c <= 2 * JT)
-        OPTEX_TRY(launch_jacobi<2>(w, warm ? G : w.W, c, st));
-    else if (c <= 4 * JT)
-        OPTEX_TRY(launch_jacobi<4>(w, warm ? G : w.W, c, st));
-    else
-        OPTEX_TRY(launch_jacobi<8>(w, warm ? G : w.W, c, st));
-    pca_finish_kernel<<<1, 1024, 0, st>>>(w.W, w.V, c, sigma, k_out, w.perm, w.sign);
-    OPTEX_LAUNCH_CHECK("pca_finish_kernel");
-    launch_pdl(pca_vecs_kernel, dim3(cdiv(c, 32), cdiv(c, 32)), dim3(32, 8), 0, st, (const double *)w.V,
-               (const int *)w.perm, (const float *)w.sign, c, eigvecs);
-    OPTEX_LAUNCH_CHECK("pca_vecs_kernel");
+    if (!basis && blocked_solver_enabled()) {
+        // cold solve without a basis to hand back: blocked-order Jacobi on the padded copy of G, no V
+        launch_pdl(pca_gram_final_kernel, dim3(cdiv((int64_t)c * c, 256)), dim3(256), 0, st, (const double *)w.gpart,
+                   gs, (const double *)w.s, (const double *)w.stat, c, w.W, (double *)nullptr);
+        OPTEX_LAUNCH_CHECK("pca_gram_final_kernel");
+        const int ld = blk_ld(c), c_pad = blk_rows(c);
+        OPTEX_CUDA(cudaMemsetAsync(w.bar, 0, sizeof(unsigned) * 8, st));
+        pca_pad_kernel<<<cdiv((int64_t)c_pad * ld, 256 * 8), 256, 0, st>>>((const double *)w.W, c, c_pad, ld, w.Wp,
+                                                                             w.stat);
+        OPTEX_LAUNCH_CHECK("pca_pad_kernel");
+        switch (ld) {
+            case 64: OPTEX_TRY(launch_jacobi_blk<2>(w, c, st)); break;
+            case 128: OPTEX_TRY(launch_jacobi_blk<4>(w, c, st)); break;
+            case 256: OPTEX_TRY(launch_jacobi_blk<8>(w, c, st)); break;
+            case 512: OPTEX_TRY(launch_jacobi_blk<16>(w, c, st)); break;
+            default: OPTEX_TRY(launch_jacobi_blk<32>(w, c, st)); break;
+        }
+        pca_finish_rows_kernel<<<1, 1024, 0, st>>>((const double *)w.Wp, ld, c, sigma, k_out, w.perm, w.scale);
+        OPTEX_LAUNCH_CHECK("pca_finish_rows_kernel");
+        launch_pdl(pca_vecs_rows_kernel, dim3(cdiv(c, 32), cdiv(c, 32)), dim3(32, 8), 0, st, (const double *)w.Wp, ld,
+                   (const int *)w.perm, (const double *)w.scale, c, eigvecs);
+        OPTEX_LAUNCH_CHECK("pca_vecs_rows_kernel");
+    } else {
+        // the solver works directly in the caller's basis buffer when there is one (V is both the start and the result)
+        double *G = w.V;  // warm: the workspace's V slot is free and holds G until W = V G is formed
+        if (basis) w.V = basis;
+        launch_pdl(pca_gram_final_kernel, dim3(cdiv((int64_t)c * c, 256)), dim3(256), 0, st, (const double *)w.gpart,
+                   gs, (const double *)w.s, (const double *)w.stat, c, warm ? G : w.W,
+                   warm ? (double *)nullptr : w.V);
+        OPTEX_LAUNCH_CHECK("pca_gram_final_kernel");
+        if (warm) {
+            launch_pdl(pca_warm_kernel, dim3(T, T), dim3(256), 0, st, (const double *)w.V, (const double *)G, w.W, c);
+            OPTEX_LAUNCH_CHECK("pca_warm_kernel");
+        }
+        if (c <= JT)
+            OPTEX_TRY(launch_jacobi<1>(w, warm ? G : w.W, c, st));
+        else if (c <= 2 * JT)
+            OPTEX_TRY(launch_jacobi<2>(w, warm ? G : w.W, c, st));
+        else if (c <= 4 * JT)
+            OPTEX_TRY(launch_jacobi<4>(w, warm ? G : w.W, c, st));
+        else
+            OPTEX_TRY(launch_jacobi<8>(w, warm ? G : w.W, c, st));
+        pca_finish_kernel<<<1, 1024, 0, st>>>(w.W, w.V, c, sigma, k_out, w.perm, w.sign);
+        OPTEX_LAUNCH_CHECK("pca_finish_kernel");
+        launch_pdl(pca_vecs_kernel, dim3(cdiv(c, 32), cdiv(c, 32)), dim3(32, 8), 0, st, (const double *)w.V,
+                   (const int *)w.perm, (const float *)w.sign, c, eigvecs);
+        OPTEX_LAUNCH_CHECK("pca_vecs_kernel");
+    }
     if (sweeps_out)
         OPTEX_CUDA(cudaMemcpyAsync(sweeps_out, w.info, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
     return OPTEX_OK;

@@ -365,12 +365,20 @@ _pca_streams = {}
 def fit_pca_many(tensors, *, round_k_to: int = 1, bases=None, warm=None, sweeps_out: Optional[list] = None):
     """`fit_pca` (optex.py:180-190) of several independent feature blocks - the five VGG layers of one pass
     (optex.py:62-67) - with the eigensolvers running CONCURRENTLY on side streams: one solve is bound by the latency
-    of its ~5600 grid-wide barriers, not by throughput, and the five cooperative grids (C/2 CTAs of 128 threads each)
+    of its grid-wide barriers, not by throughput, and the five cooperative grids (<= 32 CTAs each for the cold solve)
     fit on the device together.  Returns [(features, eigvecs), ...] like five `fit_pca` calls; one host
     synchronisation for all the k's.  bases / warm: per-tensor `basis=` / `warm=` of `fit_pca`; sweeps_out: a list
     that receives the Jacobi sweep count of every solve."""
+    return fit_pca_many_finish(fit_pca_many_launch(tensors, bases=bases, warm=warm), round_k_to=round_k_to,
+                               sweeps_out=sweeps_out)
+
+
+def fit_pca_many_launch(tensors, *, bases=None, warm=None):
+    """First half of `fit_pca_many`: everything up to (not including) the host read of the k's - the solves are
+    enqueued (on side streams, joined back into the current stream) and the call returns without synchronising, so a
+    caller can put other work between the launch and `fit_pca_many_finish` (OptimalTexture: the whole previous pass)."""
     if not tensors:
-        return []
+        return None
     dev = require_cuda(*tensors)
     bases = list(bases) if bases is not None else [None] * len(tensors)
     warm = list(warm) if warm is not None else [False] * len(tensors)
@@ -378,7 +386,7 @@ def fit_pca_many(tensors, *, round_k_to: int = 1, bases=None, warm=None, sweeps_
         raise ValueError("bases= and warm= need one entry per tensor")
     lib = _lib.lib()
     cur = torch.cuda.current_stream(dev)
-    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), cur.cuda_stream)
     streams = _pca_streams.setdefault(key, [])
     while len(streams) < len(tensors):
         streams.append(torch.cuda.Stream(device=dev))
@@ -405,12 +413,21 @@ def fit_pca_many(tensors, *, round_k_to: int = 1, bases=None, warm=None, sweeps_
         for st in streams[:len(jobs)]:
             call("optex_fence", C.c_void_p(st.cuda_stream))
             cur.wait_stream(st)
-    out = []
-    ks_sw = torch.stack([j[4] for j in jobs]).tolist()     # the one synchronisation: [k, sweeps] per solve
-    ks = [v[0] for v in ks_sw]
+        ks = torch.stack([j[4] for j in jobs])
+    return tensors, jobs, ks
+
+
+def fit_pca_many_finish(state, *, round_k_to: int = 1, sweeps_out: Optional[list] = None):
+    """Second half of `fit_pca_many`: the one synchronisation ([k, sweeps] per solve), the slices and the projections
+    of optex.py:188 (on the current stream, which must be ordered after the launch's)."""
+    if state is None:
+        return []
+    tensors, jobs, ks = state
+    ks_sw = ks.tolist()
     if sweeps_out is not None:
         sweeps_out.extend(v[1] for v in ks_sw)
-    for t, (x, c, vecs, sigma, k_dev, wsb), k in zip(tensors, jobs, ks):
+    out = []
+    for t, (x, c, vecs, sigma, k_dev, wsb), (k, _) in zip(tensors, jobs, ks_sw):
         if round_k_to > 1:
             k = min(c, -(-k // round_k_to) * round_k_to)
         eigvecs = vecs[:, :k].contiguous()

@@ -22,9 +22,11 @@ Additive over the reference:
     eigvecs)) replaces `fit_pca` (an SVD basis is defined only up to sign / rotations of near-degenerate subspaces, so
     element-wise comparisons of the whole loop need both sides in ONE basis); `pca_round_k=32` keeps a few more
     components than the reference's 90 % rule so that every layer's channel count is a multiple of 32;
-  * `pca_warm_start=True`: each layer's PCA eigensolver starts from the basis it found in the previous pass;
-  * `overlap_style=True` (experimental, default off): the style side of pass p + 1 is prepared on a second stream
-    beside pass p's OT loops; same results (the host-side order of every RNG draw and kernel argument is unchanged);
+  * `pca_warm_start=True` (default off): each layer's PCA eigensolver starts from the basis it found in the previous
+    pass; passes of EQUAL size share one style-side result (encode + PCA) within a forward();
+  * `overlap_style=True` (default): the style side of pass p + 1 is launched on a second stream before pass p's
+    layers and read back after them; same results (the host-side order of every RNG draw and kernel argument is
+    unchanged; `overlap_style=False` is the serial schedule);
   * `no_multires=True` works (the reference's own path raises AttributeError at util.py:86: a list has no .tolist()).
 """
 from __future__ import annotations
@@ -129,7 +131,7 @@ class OptimalTexture:
                  device="cuda", rotations: Optional[Callable[[int, int], Tensor]] = None,
                  mixing_noise: Optional[Callable[[Tuple[int, int]], Tensor]] = None,
                  pca: Optional[Callable[[Tensor], Tuple[Tensor, Tensor]]] = None, pca_round_k: int = 1,
-                 pca_warm_start: bool = True, overlap_style: bool = False):
+                 pca_warm_start: bool = False, overlap_style: bool = True):
         self.hist_mode = hist_mode
         self.color_transfer = color_transfer
         self.content_strength = content_strength
@@ -152,14 +154,16 @@ class OptimalTexture:
         # C x C products of the covariance modes then run on the tensor cores instead of the fp32 SIMT tiles
         self.pca = pca                      # None: the device PCA, all layers of a pass solved concurrently
         self.pca_round_k = pca_round_k
-        # the style's PCA is refitted at every pass's size (optex.py:62-67): each layer's eigensolver starts from the
-        # basis it found in the previous pass (same result, about half the Jacobi sweeps)
+        # the style's PCA is refitted at every pass's size (optex.py:62-67).  True: each layer's eigensolver starts from
+        # the basis it found in the previous pass (round-robin solver carrying V; fewer sweeps, but every sweep costs
+        # 4-5x the blocked-order cold solve's - off by default since that solver exists)
         self.pca_warm_start = pca_warm_start
-        # EXPERIMENTAL, off by default (not yet measured on a B200): prepare pass p + 1's style side on a second stream
-        # while pass p's OT loops run - both are latency-bound and leave most of the device idle
+        # pass p + 1's style side (resize, encoders, PCA solves: <= 92 CTAs) runs on a second stream beside pass p's
+        # OT loops - both are latency-bound and leave most of the device idle
         self.overlap_style = overlap_style
         self._side: Optional[torch.cuda.Stream] = None
         self._pca_bases: Dict[int, Tensor] = {}
+        self._prepared_cache: Dict[tuple, tuple] = {}       # style side of equal-size passes within one forward()
         self._pca_fitted: set = set()                        # layers whose basis belongs to the current forward()
         self.pca_sweeps: List[List[int]] = []                # per pass: sweeps of the five solves (conv5_1 .. conv1_1)
         # pca / sym: zero channels appended up to a multiple of 32 before a layer's OT loop.  Exact: the padded
@@ -237,8 +241,19 @@ class OptimalTexture:
         """Everything of a pass that does not depend on the pastiche: optex.py:45-79 without the pastiche's own resize
         (:55) and, with mix=True, the style mixing of optex.py:97-101.  Returns (cont_size, style_features,
         style_eigvs, content_features); cont_size is the size the pastiche has to be resized to, or None."""
+        return self.prepare_finish(self.prepare_launch(pastiche_shape, styles, content, size), mix=mix)
+
+    def prepare_launch(self, pastiche_shape, styles: List[Tensor], content: Optional[Tensor], size: int):
+        """First half of `prepare_pass`: resizes, encoders and the PCA solves are ENQUEUED, nothing is read back - the
+        overlapped schedule calls this a whole pass ahead of `prepare_finish`.  Passes of equal size (the reference
+        refits the same style at the same size, e.g. every pass of `--no_multires` or `--size 256`) share one result."""
+        resized = pastiche_shape[-2] != size and pastiche_shape[-1] != size
+        key = (size, resized, tuple((s.data_ptr(), tuple(s.shape)) for s in styles),
+               None if content is None else (content.data_ptr(), tuple(content.shape)))
+        if key in self._prepared_cache:
+            return {"cached": self._prepared_cache[key], "styles": styles}
         cont_size = None
-        if pastiche_shape[-2] != size and pastiche_shape[-1] != size:
+        if resized:
             with self._stage("resize"):
                 style_tens = [_util.resize(s, _util.get_size(size, self.style_scale, s.shape[2], s.shape[3]))
                               for s in styles]
@@ -254,45 +269,68 @@ class OptimalTexture:
         with self._stage("encode_inputs"):
             per_style = [self._encode_all(s) for s in style_tens]
             per_content = self._encode_all(cont_tens) if cont_tens is not None else None
-        style_features, style_eigvs, content_features = [], [], []
         raw = []
         for l in range(len(self.encoders)):
             feats = [ps[l] for ps in per_style]
             raw.append(feats[0] if len(feats) == 1 else torch.cat(feats))
-        fitted = None
+        pending = None
         if self.use_pca and self.pca is None:
             with self._stage("fit_pca"):
                 bases, warm = [], []
                 for l, t in enumerate(raw):
+                    if not self.pca_warm_start:         # cold solves take the blocked-order solver (no basis kept)
+                        bases.append(None)
+                        warm.append(False)
+                        continue
                     c = t.shape[-1]
                     b = self._pca_bases.get(l)
                     hit = l in self._pca_fitted and b is not None and tuple(b.shape) == (c, c) and b.device == t.device
                     if not hit:
                         b = self._pca_bases[l] = torch.empty(c, c, dtype=torch.float64, device=t.device)
                     bases.append(b)
-                    warm.append(bool(hit and self.pca_warm_start))
-                sweeps: List[int] = []
-                fitted = _optex.fit_pca_many(raw, round_k_to=self.pca_round_k, bases=bases, warm=warm,
-                                             sweeps_out=sweeps)
+                    warm.append(bool(hit))
+                pending = _optex.fit_pca_many_launch(raw, bases=bases, warm=warm)
                 self._pca_fitted.update(range(len(raw)))
-                self.pca_sweeps.append(sweeps)
-        for l in range(len(self.encoders)):
-            sf = raw[l]
-            eigvecs = None
-            if self.use_pca:
-                if fitted is not None:
-                    sf, eigvecs = fitted[l]
-                else:
-                    with self._stage("fit_pca"):
-                        sf, eigvecs = self.pca(sf)
-                style_eigvs.append(eigvecs)
-            style_features.append(sf)
-            if per_content is not None:
-                cf = per_content[l]
+        return {"key": key, "cont_size": cont_size, "raw": raw, "per_content": per_content, "pending": pending,
+                "styles": styles}
+
+    def prepare_finish(self, launched, mix: bool = True):
+        """Second half of `prepare_pass`: reads the k's of the PCA solves (the pass's one host synchronisation), slices
+        and projects (optex.py:188, :72-76), and with mix=True mixes the styles (optex.py:97-101)."""
+        styles = launched["styles"]
+        if "cached" in launched:
+            cont_size, style_features, style_eigvs, content_features, ks = launched["cached"]
+            style_features, style_eigvs, content_features = list(style_features), list(style_eigvs), list(content_features)
+            self.last_pca_k = list(ks)
+        else:
+            raw, per_content, cont_size = launched["raw"], launched["per_content"], launched["cont_size"]
+            fitted = None
+            if launched["pending"] is not None:
+                with self._stage("fit_pca"):
+                    sweeps: List[int] = []
+                    fitted = _optex.fit_pca_many_finish(launched["pending"], round_k_to=self.pca_round_k,
+                                                        sweeps_out=sweeps)
+                    self.pca_sweeps.append(sweeps)
+            style_features, style_eigvs, content_features = [], [], []
+            for l in range(len(self.encoders)):
+                sf = raw[l]
+                eigvecs = None
                 if self.use_pca:
-                    cf = _optex.pca_project(cf, eigvecs)
-                content_features.append(recentre(cf, sf))
-        self.last_pca_k = [int(v.shape[1]) for v in style_eigvs]        # conv5_1 .. conv1_1 of the latest pass
+                    if fitted is not None:
+                        sf, eigvecs = fitted[l]
+                    else:
+                        with self._stage("fit_pca"):
+                            sf, eigvecs = self.pca(sf)
+                    style_eigvs.append(eigvecs)
+                style_features.append(sf)
+                if per_content is not None:
+                    cf = per_content[l]
+                    if self.use_pca:
+                        cf = _optex.pca_project(cf, eigvecs)
+                    content_features.append(recentre(cf, sf))
+            self.last_pca_k = [int(v.shape[1]) for v in style_eigvs]    # conv5_1 .. conv1_1 of the latest pass
+            self._prepared_cache[launched["key"]] = (cont_size, list(style_features), list(style_eigvs),
+                                                     list(content_features), list(self.last_pca_k))
         if self.use_pca and min(self.last_pca_k) < 1:
             # optex.py:185-186: k = first index whose cumulative singular-value share exceeds 0.9; a layer whose FIRST
             # singular value already does gets k = 0 and the reference then fails inside its matmuls on [.., 0] tensors
@@ -325,24 +363,43 @@ class OptimalTexture:
             self._side = torch.cuda.Stream(device=pastiche.device)
         return main, self._side, main.record_event()
 
-    def _prepare(self, streams, pastiche_shape, styles, content, size):
-        """prepare_pass, on the side stream when there is one.  Returns its four results + the event to wait for."""
+    @contextlib.contextmanager
+    def _on_side(self, streams):
+        """Run the body on the side stream of the overlapped schedule (with the GEMMs' second scratch slot)."""
         if streams is None:
-            return (*self.prepare_pass(pastiche_shape, styles, content, size), None)
+            yield
+            return
         main, side, start = streams
         lib = _lib.lib()
         prev = lib.optex_set_scratch_slot(1)         # the GEMMs' operand-split scratch: one per concurrent stream
         try:
             with torch.cuda.stream(side):
-                side.wait_event(start)               # the inputs exist since forward() began; NOT the main stream's
-                out = self.prepare_pass(pastiche_shape, styles, content, size)     # later work (that is the overlap)
-                ready = side.record_event()
+                yield
         finally:
             lib.optex_set_scratch_slot(prev)
-        for group in out[1:]:
-            for t in group:
-                if t is not None and t.is_cuda:
-                    t.record_stream(main)            # allocated on `side`, consumed (and released) on `main`
+
+    def _launch(self, streams, pastiche_shape, styles, content, size):
+        """prepare_launch, on the side stream when there is one."""
+        with self._on_side(streams):
+            if streams is not None:
+                streams[1].wait_event(streams[2])    # the inputs exist since forward() began; NOT the main stream's
+            launched = self.prepare_launch(pastiche_shape, styles, content, size)   # later work (that is the overlap)
+        launched["args"] = (tuple(pastiche_shape), styles, content, size)
+        return launched
+
+    def _finish(self, streams, launched, pastiche_shape):
+        """prepare_finish (same stream as the launch).  Returns its four results + the event the main stream waits for."""
+        shape, styles, content, size = launched["args"]
+        if (shape[-2] != size and shape[-1] != size) != (pastiche_shape[-2] != size and pastiche_shape[-1] != size):
+            launched = self._launch(streams, pastiche_shape, styles, content, size)   # the pastiche changed shape
+        with self._on_side(streams):
+            out = self.prepare_finish(launched)
+            ready = streams[1].record_event() if streams is not None else None
+        if streams is not None:
+            for group in out[1:]:
+                for t in group:
+                    if t is not None and t.is_cuda:
+                        t.record_stream(streams[0])  # allocated on `side`, consumed (and released) on `main`
         return (*out, ready)
 
     def forward(self, pastiche: Tensor, styles: List[Tensor], content: Optional[Tensor] = None,
@@ -350,21 +407,25 @@ class OptimalTexture:
         """reference: optex.py:81-139."""
         require_cuda(pastiche, *styles, content)
         self._pca_fitted.clear()                             # pass 0 of every call starts cold
+        self._prepared_cache = {}
         self.pca_sweeps = []
         streams = self._streams_for(pastiche) if self.overlap_style else None
-        prepared = None
+        launched = self._launch(streams, pastiche.shape, styles, content, self.sizes[0])
         for p in range(self.passes):
             if verbose:
                 print(f"Pass {p}, size {self.sizes[p]}")
-            if prepared is None:
-                prepared = self._prepare(streams, pastiche.shape, styles, content, self.sizes[p])
-            cont_size, style_features, style_eigvs, content_features, ready = prepared
-            prepared = None
+            cont_size, style_features, style_eigvs, content_features, ready = self._finish(streams, launched,
+                                                                                           pastiche.shape)
             if cont_size is not None:                                                            # optex.py:55
                 with self._stage("resize"):
                     pastiche = _util.resize(pastiche, cont_size)
             if ready is not None:
                 streams[0].wait_event(ready)
+            if self.overlap_style and p + 1 < self.passes:
+                # the next pass's style side (resize, encode, PCA solves) only needs the style / content images: it is
+                # enqueued now on the side stream and runs beside this pass's OT loops; its results are read (the k's:
+                # the pass's one host synchronisation) when this pass has been enqueued
+                launched = self._launch(streams, pastiche.shape, styles, content, self.sizes[p + 1])
 
             for l, (encoder, decoder) in enumerate(zip(self.encoders, self.decoders)):
                 if verbose:
@@ -384,10 +445,8 @@ class OptimalTexture:
                         feature = _optex.pca_project(feature, style_eigvs[l], transpose=True)
                     pastiche = decoder(feature)
 
-            if self.overlap_style and p + 1 < self.passes:
-                # the next pass's style side (resize, encode, PCA, mixing) only needs the style / content images: it is
-                # enqueued now, behind this pass's OT loops on the host but beside them on the device
-                prepared = self._prepare(streams, pastiche.shape, styles, content, self.sizes[p + 1])
+            if not self.overlap_style and p + 1 < self.passes:
+                launched = self._launch(None, pastiche.shape, styles, content, self.sizes[p + 1])
 
         if self.color_transfer is not None:
             assert content is not None, "Color transfer requires content image"

@@ -98,8 +98,8 @@ def test_product_control_flow_matches_reference(golden, monkeypatch, name, overl
     orchestration - pass sizes, resize rule, per-layer iteration counts with the [l - 1] quirk, content strengths
     and the l <= 2 rule, mixing mask, colour-transfer branches, the order of RNG / rotation consumption - is the
     reference's.  (The kernels themselves are compared stage by stage on the GPU, tests/test_gpu_texture.py.)
-    overlap=True: the host-side order of the experimental `overlap_style` schedule (pass p + 1's style side prepared
-    right after pass p's layers are enqueued) consumes the RNG and produces every tensor identically."""
+    overlap=True: the host-side order of the `overlap_style` schedule (pass p + 1's style side launched on a side
+    stream before pass p's layers, finished after them) consumes the RNG and produces every tensor identically."""
     from optimaltextures_b200 import texture
     from oracle import ot_oracle, texture_cases, vgg_oracle
 
@@ -178,8 +178,9 @@ def test_product_control_flow_matches_reference(golden, monkeypatch, name, overl
     np.testing.assert_array_equal(out.contiguous().numpy(), g[f"{name}_out"])
     if overlap:
         passes = kwargs["passes"]
-        # per pass: slot 1, side waits for the start event, side records "ready", slot back to 0; main waits for it
-        assert [e for e in events if e[0] == "lib"] == [("lib", "slot", 1), ("lib", "slot", 0)] * passes
+        # per pass: launch (slot 1, side waits for the start event, slot 0) and finish (slot 1, side records "ready",
+        # slot 0); main waits for the ready event; the launch of pass p + 1 sits between pass p's finish and its layers
+        assert [e for e in events if e[0] == "lib"] == [("lib", "slot", 1), ("lib", "slot", 0)] * (2 * passes)
         assert sum(1 for e in events if e[:2] == ("side", "wait")) == passes
         ready = [f"side-event-{i + 1}" for i, e in enumerate(events) if e[:2] == ("side", "record")]
         assert [e[2] for e in events if e[:2] == ("main", "wait")] == ready and len(ready) == passes
@@ -266,10 +267,14 @@ def test_pca_warm_start_bookkeeping(monkeypatch):
 
     calls = []
 
-    def fit_many(tensors, *, round_k_to=1, bases=None, warm=None, sweeps_out=None):
-        calls.append((list(warm), [b.data_ptr() for b in bases], [tuple(b.shape) for b in bases], bases[0].dtype))
-        sweeps_out.extend([7] * len(tensors))
-        return [ot_oracle.fit_pca(t) for t in tensors]
+    def launch(tensors, *, bases=None, warm=None):
+        calls.append((list(warm), [None if b is None else b.data_ptr() for b in bases],
+                      [None if b is None else tuple(b.shape) for b in bases], None if bases[0] is None else bases[0].dtype))
+        return tensors
+
+    def finish(state, *, round_k_to=1, sweeps_out=None):
+        sweeps_out.extend([7] * len(state))
+        return [ot_oracle.fit_pca(t) for t in state]
 
     monkeypatch.setattr(texture, "require_cuda", lambda *t: torch.device("cpu"))
     monkeypatch.setattr(texture._util, "resize", image_oracle.resize)
@@ -277,9 +282,11 @@ def test_pca_warm_start_bookkeeping(monkeypatch):
     monkeypatch.setattr(texture._vgg, "Decoder", Dec)
     monkeypatch.setattr(texture._optex, "pca_project", lambda x, v, transpose=False: x @ (v.T if transpose else v))
     monkeypatch.setattr(texture._optex, "ot_loop", lambda f, *a, **k: f)
-    monkeypatch.setattr(texture._optex, "fit_pca_many", fit_many)
+    monkeypatch.setattr(texture._optex, "fit_pca_many_launch", launch)
+    monkeypatch.setattr(texture._optex, "fit_pca_many_finish", finish)
     kwargs, styles, content, pastiche = texture_cases.texture_inputs("synth_pca")
-    model = texture.OptimalTexture(state_dicts=texture_cases.state_dicts(), device="cpu", **kwargs)
+    model = texture.OptimalTexture(state_dicts=texture_cases.state_dicts(), device="cpu", pca_warm_start=True,
+                                   overlap_style=False, **kwargs)
     model.pad_channels = 1
     with torch.inference_mode():
         model.forward(pastiche, styles, content)
@@ -289,9 +296,56 @@ def test_pca_warm_start_bookkeeping(monkeypatch):
         assert model.pca_sweeps == [[7] * 5, [7] * 5]
         model.forward(pastiche, styles, content)
     assert [c[0] for c in calls[2:]] == [[False] * 5, [True] * 5], "a new forward() starts cold"
-    cold = texture.OptimalTexture(state_dicts=texture_cases.state_dicts(), device="cpu", pca_warm_start=False, **kwargs)
+    # the default: cold solves without a basis (the blocked-order solver of pca.cu)
+    cold = texture.OptimalTexture(state_dicts=texture_cases.state_dicts(), device="cpu", overlap_style=False, **kwargs)
     cold.pad_channels = 1
     del calls[:]
     with torch.inference_mode():
         cold.forward(pastiche, styles, content)
-    assert [c[0] for c in calls] == [[False] * 5, [False] * 5]
+    assert [c[0] for c in calls] == [[False] * 5, [False] * 5] and calls[0][1] == [None] * 5
+
+
+def test_equal_size_passes_share_the_style_side(monkeypatch):
+    """Passes of equal size refit the same style at the same size (optex.py:62-67 is deterministic): the product
+    encodes / solves once per distinct size within a forward() and reuses the result."""
+    from optimaltextures_b200 import texture
+    from oracle import ot_oracle, texture_cases, vgg_oracle
+
+    class Enc:
+        def __init__(self, d, state_dict=None, models_dir=None, device=None):
+            self.depth, self.sd, self.layers = d, state_dict, []
+
+        def forward_all(self, x):
+            return vgg_oracle.encoder_forward(x, self.sd, self.depth, all_depths=True)
+
+        def __call__(self, x):
+            return vgg_oracle.encoder_forward(x, self.sd, self.depth)
+
+    class Dec:
+        def __init__(self, d, state_dict=None, models_dir=None, device=None):
+            self.depth, self.sd = d, state_dict
+
+        def __call__(self, x):
+            return vgg_oracle.decoder_forward(x, self.sd, self.depth)
+
+    fits = []
+
+    def pca(t):
+        fits.append(tuple(t.shape))
+        return ot_oracle.fit_pca(t)
+
+    monkeypatch.setattr(texture, "require_cuda", lambda *t: torch.device("cpu"))
+    monkeypatch.setattr(texture._util, "resize", image_oracle.resize)
+    monkeypatch.setattr(texture._vgg, "Encoder", Enc)
+    monkeypatch.setattr(texture._vgg, "Decoder", Dec)
+    monkeypatch.setattr(texture._optex, "pca_project", lambda x, v, transpose=False: x @ (v.T if transpose else v))
+    monkeypatch.setattr(texture._optex, "ot_loop", lambda f, *a, **k: f)
+    kwargs, styles, content, pastiche = texture_cases.texture_inputs("synth_pca")
+    kwargs = dict(kwargs, size=64, passes=3)          # sizes = linspace(256, 64, 3) rounded: all distinct ...
+    model = texture.OptimalTexture(state_dicts=texture_cases.state_dicts(), device="cpu", pca=pca, overlap_style=False,
+                                   **kwargs)
+    model.sizes = [64, 64, 96]                        # ... so force two equal passes and one different
+    model.pad_channels = 1
+    with torch.inference_mode():
+        model.forward(pastiche, styles, content)
+    assert len(fits) == 2 * 5, fits                   # five layers for size 64 (once), five for size 96
