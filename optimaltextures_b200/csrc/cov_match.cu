@@ -364,6 +364,7 @@ struct Ws {
     float *m[19];  // c x c matrices
     float *norm2, *resid;   // Newton-Schulz state of chain 0; chain 1 (side stream) at +NS_STATE
     int *flags;
+    float *coop;            // scratch of the cooperative chain kernel (cov_chain.cu)
 };
 constexpr int NS_STATE = 3 * NS_MAX_ITERS + 8;  // floats / ints per chain (norm2: [0] = |A|_F^2, [8 + 2 it ..] = step coefficients)
 
@@ -389,6 +390,7 @@ size_t ws_layout(int64_t n_t, int64_t n_s, int c, int b_max, Ws *w, void *base, 
     l.norm2 = ar.take<float>(2 * NS_STATE);
     l.resid = ar.take<float>(2 * NS_STATE);
     l.flags = ar.take<int>(2 * NS_STATE);
+    l.coop = ar.take<float>(cov_coop_scratch_floats());
     if (w) *w = l;
     if (ok) *ok = ar.ok();
     return ar.off;
@@ -656,7 +658,9 @@ void cov_set_shard(const ShardCtx *ctx) { g_shard = ctx; }
 size_t cov_match_ws_bytes(int64_t n_t, int64_t n_s, int c, int mode) {
     (void)mode;
     if (c < 1) return 0;
-    return ws_layout(n_t, n_s, c, B_MAX, nullptr, nullptr, 0, nullptr) + 256;
+    const size_t wide = ws_layout(n_t, n_s, c, B_MAX, nullptr, nullptr, 0, nullptr) + 256;
+    const size_t narrow = c <= 64 ? cov_small_ws_bytes(n_t, n_s, c) : 0;
+    return wide > narrow ? wide : narrow;
 }
 
 // out[n, c] = (X - mu_t) G^T + mu_s with G = R T R^T (R may be null = identity); see the file header
@@ -677,6 +681,9 @@ int cov_ot_step(const float *P, const float *S, const float *R, float *out, int 
     // is computed in the un-rotated frame (6 C x C products fewer; same result up to rounding).  Cholesky factors do
     // not commute with a rotation, chol keeps it.
     if (mode != OPTEX_MODE_CHOL) R = nullptr;
+    if (!g_shard && cov_small_supported(c, mode, b_p, b_s))
+        return cov_small_step(P, S, out, b_p, hw_p, b_s, hw_s, c, mode, eps, content, strength, workspace,
+                              workspace_bytes, st, style_reuse);
     Ws w;
     bool ok = false;
     const int64_t n_p = (int64_t)b_p * hw_p, n_s = (int64_t)b_s * hw_s;
@@ -699,48 +706,58 @@ int cov_ot_step(const float *P, const float *S, const float *R, float *out, int 
     OPTEX_TRY(moments(P, b_p, hw_p, c, R ? 0.f : eps, w.mu_p, sig_t, w, st, g_shard ? g_shard->hw_p_total : 0));
     if (!style_reuse)
         OPTEX_TRY(moments(S, b_s, hw_s, c, R ? 0.f : eps, w.mu_s, sig_s_src, w, st, g_shard ? g_shard->hw_s_total : 0));
-    // ---- fork: the style-side chain (sandwich, factorisation) on the side stream
-    SideStream *side;
-    OPTEX_TRY(side_stream(&side));
-    cudaStream_t sb = side->stream;
-    // the moments above were launched with programmatic serialisation: fence before the fork event, so the side stream
-    // cannot start on sig_s / mu_s while their producers are still draining (and likewise before the join)
-    if (pdl_enabled()) OPTEX_TRY(stream_fence(st));
-    OPTEX_CUDA(cudaEventRecord(side->fork, st));
-    OPTEX_CUDA(cudaStreamWaitEvent(sb, side->fork, 0));
-    int rc_b = OPTEX_OK;
-    auto side_chain = [&]() -> int {
-        if (R) {  // Sig_s' = R^T Sig_s R + eps I
-            OPTEX_TRY(mm(sig_s_src, false, R, false, tmp_b, c, 1.f, nullptr, sb));
-            OPTEX_TRY(mm(R, true, tmp_b, false, sig_s, c, 1.f, nullptr, sb));
-            launch_pdl(add_diag_kernel, dim3((unsigned)(cdiv(c, 256))), dim3(256), 0, sb, sig_s, c, eps);
-            OPTEX_LAUNCH_CHECK("add_diag_kernel");
-        }
-        if (mode == OPTEX_MODE_CHOL) return cholesky(sig_s, c, sb);
-        return OPTEX_OK;  // pca: both square roots run as one batched chain below; sym: the second needs the first
-    };
-    rc_b = side_chain();
-    // always join, also on an error above: the side stream must not be left forked inside a capture
-    if (pdl_enabled() && rc_b == OPTEX_OK) rc_b = stream_fence(sb);
-    cudaError_t join_err = cudaEventRecord(side->join, sb);
-    // ---- the pastiche-side chain on the caller's stream
-    auto main_chain = [&]() -> int {
-        if (R) {  // Sig_t' = R^T Sig_t R + eps I
-            OPTEX_TRY(mm(sig_t, false, R, false, tmp, c, 1.f, nullptr, st));
-            OPTEX_TRY(mm(R, true, tmp, false, sig_t, c, 1.f, nullptr, st));
-            launch_pdl(add_diag_kernel, dim3((unsigned)(cdiv(c, 256))), dim3(256), 0, st, sig_t, c, eps);
-            OPTEX_LAUNCH_CHECK("add_diag_kernel");
-        }
-        if (mode == OPTEX_MODE_CHOL) return cholesky(sig_t, c, st);
-        if (mode == OPTEX_MODE_PCA) return OPTEX_OK;
-        return ns_sqrt(sig_t, Y, Z, t0, t, yn, zn, c, ns_a, eps, st);
-    };
-    const int rc_a = main_chain();
-    if (join_err == cudaSuccess) join_err = cudaStreamWaitEvent(st, side->join, 0);
-    OPTEX_CUDA(join_err);
-    OPTEX_TRY(rc_b);
-    OPTEX_TRY(rc_a);
-    if (mode == OPTEX_MODE_CHOL) {  // T = L_s L_t^-1                      histmatch.py:25-27
+    const bool coop = !R && cov_coop_supported(c, mode);
+    if (coop) {
+        // pca / sym at the PCA'd layer widths: Newton-Schulz chain(s), closing products and bias in ONE cooperative kernel
+        OPTEX_TRY(cov_coop_chain(w.m, c, mode, eps, style_reuse, w.mu_p, w.mu_s, b_p, b_s, w.bias, w.coop, st));
+    } else if (mode == OPTEX_MODE_CHOL) {
+        // ---- fork: the style-side chain (sandwich, factorisation) on the side stream
+        SideStream *side;
+        OPTEX_TRY(side_stream(&side));
+        cudaStream_t sb = side->stream;
+        // the moments above were launched with programmatic serialisation: fence before the fork event, so the side stream
+        // cannot start on sig_s / mu_s while their producers are still draining (and likewise before the join)
+        if (pdl_enabled()) OPTEX_TRY(stream_fence(st));
+        OPTEX_CUDA(cudaEventRecord(side->fork, st));
+        OPTEX_CUDA(cudaStreamWaitEvent(sb, side->fork, 0));
+        int rc_b = OPTEX_OK;
+        auto side_chain = [&]() -> int {
+            if (R) {  // Sig_s' = R^T Sig_s R + eps I
+                OPTEX_TRY(mm(sig_s_src, false, R, false, tmp_b, c, 1.f, nullptr, sb));
+                OPTEX_TRY(mm(R, true, tmp_b, false, sig_s, c, 1.f, nullptr, sb));
+                launch_pdl(add_diag_kernel, dim3((unsigned)(cdiv(c, 256))), dim3(256), 0, sb, sig_s, c, eps);
+                OPTEX_LAUNCH_CHECK("add_diag_kernel");
+            }
+            if (mode == OPTEX_MODE_CHOL) return cholesky(sig_s, c, sb);
+            return OPTEX_OK;  // pca: both square roots run as one batched chain below; sym: the second needs the first
+        };
+        rc_b = side_chain();
+        // always join, also on an error above: the side stream must not be left forked inside a capture
+        if (pdl_enabled() && rc_b == OPTEX_OK) rc_b = stream_fence(sb);
+        cudaError_t join_err = cudaEventRecord(side->join, sb);
+        // ---- the pastiche-side chain on the caller's stream
+        auto main_chain = [&]() -> int {
+            if (R) {  // Sig_t' = R^T Sig_t R + eps I
+                OPTEX_TRY(mm(sig_t, false, R, false, tmp, c, 1.f, nullptr, st));
+                OPTEX_TRY(mm(R, true, tmp, false, sig_t, c, 1.f, nullptr, st));
+                launch_pdl(add_diag_kernel, dim3((unsigned)(cdiv(c, 256))), dim3(256), 0, st, sig_t, c, eps);
+                OPTEX_LAUNCH_CHECK("add_diag_kernel");
+            }
+            if (mode == OPTEX_MODE_CHOL) return cholesky(sig_t, c, st);
+            if (mode == OPTEX_MODE_PCA) return OPTEX_OK;
+            return ns_sqrt(sig_t, Y, Z, t0, t, yn, zn, c, ns_a, eps, st);
+        };
+        const int rc_a = main_chain();
+        if (join_err == cudaSuccess) join_err = cudaStreamWaitEvent(st, side->join, 0);
+        OPTEX_CUDA(join_err);
+        OPTEX_TRY(rc_b);
+        OPTEX_TRY(rc_a);
+    } else if (mode == OPTEX_MODE_SYM) {   // pca / sym: nothing to run beside the pastiche chain - no fork
+        OPTEX_TRY(ns_sqrt(sig_t, Y, Z, t0, t, yn, zn, c, ns_a, eps, st));
+    }
+    if (coop) {
+        // T and the bias are in place
+    } else if (mode == OPTEX_MODE_CHOL) {  // T = L_s L_t^-1                      histmatch.py:25-27
         OPTEX_TRY(transpose_f32(sig_t, tmp, c, c, st));
         OPTEX_TRY(trsm_right(sig_s, tmp, T, c, st));
     } else if (mode == OPTEX_MODE_PCA) {  // T = Sig_s^(1/2) Sig_t^(-1/2)   histmatch.py:29-34
@@ -761,8 +778,10 @@ int cov_ot_step(const float *P, const float *S, const float *R, float *out, int 
         OPTEX_TRY(mm(tmp, false, R, true, G, c, 1.f, nullptr, st));
         Gp = G;
     }
-    launch_pdl(bias_kernel, dim3(cdiv((int64_t)c * 32, 128), b_p), dim3(128), 0, st, Gp, w.mu_p, w.mu_s, b_s, c, w.bias);
-    OPTEX_LAUNCH_CHECK("bias_kernel");
+    if (!coop) {
+        launch_pdl(bias_kernel, dim3(cdiv((int64_t)c * 32, 128), b_p), dim3(128), 0, st, Gp, w.mu_p, w.mu_s, b_s, c, w.bias);
+        OPTEX_LAUNCH_CHECK("bias_kernel");
+    }
     // out[n, j] = sum_c P[n, c] G[j, c] + bias[b(n), j]   (+ content blend)
     int rc = OPTEX_ENOTSUP;
     if (g_want_tc()) {
