@@ -331,6 +331,9 @@ int optex_fit_pca_warm(const float *X, int64_t n, int c, float *eigvecs, float *
  * blocked-order solver fills with clock64 stamps of its first n global rounds (round start, rows loaded, sub-rounds
  * done, rows stored, barrier passed).  NULL switches it off (the default). */
 int optex_debug_pca_stamps(long long *device_buffer, int n);
+/* The same for the cooperative covariance-chain kernel (cov_chain.cu; scripts/chain_stamps.py): n int64 stamps of
+ * CTA 0, one at kernel entry, one behind every grid barrier, one at the end.  NULL switches it off (the default). */
+int optex_debug_chain_stamps(long long *device_buffer, int n);
 /* transpose = 0: out[n, k] = X[n, c] V[c, k]      (project onto the basis,  optex.py:110, :188)
  * transpose = 1: out[n, c] = X[n, k] V[c, k]^T    (back to feature space,   optex.py:120)
  * V dense row-major [c, k].  Tensor cores when c and k allow (k % 32 == 0, c % 4 == 0), else fp32 SIMT tiles. */

@@ -76,6 +76,7 @@ SIGNATURES = {
     "optex_fit_pca": (_i, [_p, _l, _i, _p, _p, _p, _p, _z, _p]),
     "optex_fit_pca_warm": (_i, [_p, _l, _i, _p, _p, _p, _p, _i, _p, _p, _z, _p]),
     "optex_debug_pca_stamps": (_i, [_p, _i]),
+    "optex_debug_chain_stamps": (_i, [_p, _i]),
     "optex_pca_project": (_i, [_p, _p, _p, _l, _i, _i, _i, _p]),
     "optex_conv3x3_packed_k": (_i, [_i]),
     "optex_conv3x3_workspace_bytes": (_z, [_i, _i, _i, _i, _i, _i]),

@@ -32,6 +32,8 @@ struct Prod {
     float *C;
     float alpha, diag;
     unsigned *resid;  // optional: max |A B - I| (bits of a non-negative float)
+    int sym;          // the result is symmetric (products of commuting symmetric matrices): only the tiles on and
+                      // above the diagonal are computed, the others are their mirror images
 };
 
 __device__ __forceinline__ void grid_barrier(unsigned *counter, unsigned &target) {
@@ -59,6 +61,7 @@ __device__ __forceinline__ void cp_async_wait() {
 
 // one 32 x 32 tile of C = alpha A B + diag I at (i0, j0); sA: [STAGES][TILE][LDA], sB: [STAGES][KC][TILE]
 __device__ void tile_product(const Prod &p, int c, int i0, int j0, float *sA, float *sB) {
+    const bool mirror = p.sym && i0 != j0, diag_tile = p.sym && i0 == j0;
     const int tid = threadIdx.x;
     const int g = tid >> 6, t = tid & 63, ty = t >> 3, tx = t & 7;   // k-group, 8 x 8 threads of 4 x 4 outputs
     const int nchunks = (c + KC - 1) / KC;
@@ -131,6 +134,8 @@ __device__ void tile_product(const Prod &p, int c, int i0, int j0, float *sA, fl
     float d = 0.f;
     float4 o;
     float *ov = reinterpret_cast<float *>(&o);
+    float *fin = sA + 4 * TILE * TILE;   // [TILE][TILE + 1]: the finished tile, for the mirrored / symmetrised store
+    static_assert(4 * TILE * TILE + TILE * (TILE + 1) <= STAGES * TILE * LDA, "finished-tile buffer");
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int idx = r * TILE + q + j;
@@ -142,6 +147,20 @@ __device__ void tile_product(const Prod &p, int c, int i0, int j0, float *sA, fl
             d = fmaxf(d, e);
         }
         ov[j] = fmaf(p.alpha, m, p.diag * eye);
+        if (p.sym) fin[r * (TILE + 1) + q + j] = ov[j];
+    }
+    if (p.sym) {
+        __syncthreads();
+        float4 t;
+        float *tv = reinterpret_cast<float *>(&t);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tv[j] = fin[(q + j) * (TILE + 1) + r];   // row r of the transposed tile
+        if (diag_tile) {   // a diagonal tile is made exactly symmetric itself
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ov[j] = 0.5f * (ov[j] + tv[j]);
+        } else if (mirror) {
+            __stcg(reinterpret_cast<float4 *>(p.C + (int64_t)(j0 + r) * c + i0 + q), t);
+        }
     }
     __stcg(reinterpret_cast<float4 *>(p.C + (int64_t)(i0 + r) * c + j0 + q), o);
     if (p.resid) {
@@ -153,10 +172,28 @@ __device__ void tile_product(const Prod &p, int c, int i0, int j0, float *sA, fl
 
 // the units of a step, dealt round-robin to the CTAs
 __device__ void run_step(const Prod *prods, int np, int c, float *sA, float *sB) {
-    const int tc = c / TILE, tiles = tc * tc;
-    for (int u = blockIdx.x; u < np * tiles; u += gridDim.x) {
-        const int pi = u / tiles, tt = u - pi * tiles;
-        tile_product(prods[pi], c, (tt / tc) * TILE, (tt % tc) * TILE, sA, sB);
+    const int tc = c / TILE, full = tc * tc, tri = tc * (tc + 1) / 2;
+    int total = 0;
+    for (int i = 0; i < np; ++i) total += prods[i].sym ? tri : full;
+    for (int u = blockIdx.x; u < total; u += gridDim.x) {
+        int pi = 0, tt = u;
+        while (tt >= (prods[pi].sym ? tri : full)) {
+            tt -= prods[pi].sym ? tri : full;
+            ++pi;
+        }
+        int ti, tj;
+        if (prods[pi].sym) {   // tt-th tile of the upper triangle, row by row
+            ti = 0;
+            while (tt >= tc - ti) {
+                tt -= tc - ti;
+                ++ti;
+            }
+            tj = ti + tt;
+        } else {
+            ti = tt / tc;
+            tj = tt - ti * tc;
+        }
+        tile_product(prods[pi], c, ti * TILE, tj * TILE, sA, sB);
     }
 }
 
@@ -178,7 +215,17 @@ struct CoopParams {
     float *norm_part;          // [2][MAX_GRID]
     unsigned *resid;           // [2][NS_CAP_C], zeroed before the launch
     unsigned *bar;             // zeroed before the launch
+    long long *stamps;         // debug (optex_debug_chain_stamps): clock64 of CTA 0 behind every grid barrier
+    int n_stamps;
 };
+
+__device__ int g_stamp_idx;
+__device__ __forceinline__ void stamp(const CoopParams &p) {
+    if (p.stamps && blockIdx.x == 0 && threadIdx.x == 0) {
+        const int i = g_stamp_idx++;
+        if (i < p.n_stamps) p.stamps[i] = clock64();
+    }
+}
 
 // sum of squares of A over the whole grid, identical bits in every thread: per-CTA partials (norm2_partial), a grid
 // barrier by the caller, a fixed-order sum (norm2_total)
@@ -215,14 +262,16 @@ __device__ float norm2_total(const float *part, float *sred) {
 
 // The coupled Newton-Schulz iteration for `n` (1 or 2) chains in lockstep.  Returns, per chain, the index of the
 // buffer pair holding the result (cur) and |A|_F^2 (norm2); Y -> (A / |A|_F)^(1/2), Z -> (A / |A|_F)^(-1/2).
-__device__ void run_chains(const ChainBuf *ch, int n, int c, float *norm_part, unsigned *resid, unsigned *bar,
-                           unsigned &target, float *sA, float *sB, float *sred, int *cur_out, float *norm2_out) {
+__device__ void run_chains(const CoopParams &p, const ChainBuf *ch, int n, int c, float *norm_part, unsigned *resid,
+                           unsigned *bar, unsigned &target, float *sA, float *sB, float *sred, int *cur_out,
+                           float *norm2_out) {
     const int64_t cc = (int64_t)c * c;
     float norm2[2], l[2], prev[2];
     int cur[2];
     bool live[2], prev_plain[2] = {false, false}, plain[2] = {false, false};
     for (int k = 0; k < n; ++k) norm2_partial(ch[k].A, cc, norm_part + k * MAX_GRID, sred);
     grid_barrier(bar, target);
+    stamp(p);
     for (int k = 0; k < n; ++k) {
         norm2[k] = norm2_total(norm_part + k * MAX_GRID, sred);
         cur[k] = 0;
@@ -236,6 +285,7 @@ __device__ void run_chains(const ChainBuf *ch, int n, int c, float *norm_part, u
         }
     }
     grid_barrier(bar, target);
+    stamp(p);
     for (int it = 0; it < NS_CAP_C; ++it) {
         Prod pr[4];
         int np = 0;
@@ -247,11 +297,12 @@ __device__ void run_chains(const ChainBuf *ch, int n, int c, float *norm_part, u
             l[k] = fminf(0.97f * rl * (3.f - rl) * (3.f - rl) * 0.25f, 1.f);
             plain[k] = rho == 1.f;
             pr[np++] = Prod{ch[k].Z[cur[k]], ch[k].Y[cur[k]], ch[k].T, -0.5f * rho * sr, 1.5f * sr,
-                            resid + k * NS_CAP_C + it};
+                            resid + k * NS_CAP_C + it, 1};
         }
         if (np == 0) break;
         run_step(pr, np, c, sA, sB);   // T = a I + b Z Y, residual
         grid_barrier(bar, target);
+        stamp(p);
         np = 0;
         bool stop[2] = {false, false};
         for (int k = 0; k < n; ++k) {
@@ -265,13 +316,14 @@ __device__ void run_chains(const ChainBuf *ch, int n, int c, float *norm_part, u
             }
             prev[k] = r;
             prev_plain[k] = plain[k];
-            pr[np++] = Prod{ch[k].Y[cur[k]], ch[k].T, ch[k].Y[cur[k] ^ 1], 1.f, 0.f, nullptr};
-            pr[np++] = Prod{ch[k].T, ch[k].Z[cur[k]], ch[k].Z[cur[k] ^ 1], 1.f, 0.f, nullptr};
+            pr[np++] = Prod{ch[k].Y[cur[k]], ch[k].T, ch[k].Y[cur[k] ^ 1], 1.f, 0.f, nullptr, 1};
+            pr[np++] = Prod{ch[k].T, ch[k].Z[cur[k]], ch[k].Z[cur[k] ^ 1], 1.f, 0.f, nullptr, 1};
             stop[k] = r < NS_TOL_C;   // this iteration's update is applied, the next is not needed
         }
         if (np == 0) break;
         run_step(pr, np, c, sA, sB);
         grid_barrier(bar, target);
+        stamp(p);
         for (int k = 0; k < n; ++k) {
             if (!live[k]) continue;
             cur[k] ^= 1;
@@ -290,6 +342,10 @@ __global__ void __launch_bounds__(CT) ns_coop_kernel(CoopParams p) {
     __shared__ float sred[CT / 32];
     unsigned target = 0;
     const int c = p.c, tid = threadIdx.x;
+    if (p.stamps && blockIdx.x == 0 && tid == 0) {
+        g_stamp_idx = 0;
+        stamp(p);
+    }
     const int64_t cc = (int64_t)c * c;
     int cur[2];
     float n2[2];
@@ -298,7 +354,7 @@ __global__ void __launch_bounds__(CT) ns_coop_kernel(CoopParams p) {
         // T = Sig_s^(1/2) Sig_t^(-1/2)                                  histmatch.py:29-34
         const ChainBuf chains[2] = {p.a, p.b};
         const int n = p.style_state == 0 ? 2 : 1;
-        run_chains(chains, n, c, p.norm_part, p.resid, p.bar, target, sA, sB, sred, cur, n2);
+        run_chains(p, chains, n, c, p.norm_part, p.resid, p.bar, target, sA, sB, sred, cur, n2);
         const float rs_a = sqrtf(sqrtf(n2[0]));
         Prod pr;
         if (n == 2) {
@@ -306,21 +362,22 @@ __global__ void __launch_bounds__(CT) ns_coop_kernel(CoopParams p) {
             const float *yb = p.b.Y[cur[1]];
             for (int64_t i = (int64_t)blockIdx.x * CT + tid; i < cc; i += (int64_t)gridDim.x * CT)
                 __stcg(p.keep + i, __ldcg(yb + i) * rs_b);
-            pr = Prod{yb, p.a.Z[cur[0]], p.G, rs_b / rs_a, 0.f, nullptr};
+            pr = Prod{yb, p.a.Z[cur[0]], p.G, rs_b / rs_a, 0.f, nullptr, 0};
         } else {
-            pr = Prod{p.keep, p.a.Z[cur[0]], p.G, 1.f / rs_a, 0.f, nullptr};
+            pr = Prod{p.keep, p.a.Z[cur[0]], p.G, 1.f / rs_a, 0.f, nullptr, 0};
         }
         run_step(&pr, 1, c, sA, sB);
         grid_barrier(p.bar, target);
+        stamp(p);
     } else {
         // sym: T = Qt^-1 (Qt Sig_s Qt)^(1/2) Qt^-1,  Qt = Sig_t^(1/2)    histmatch.py:36-42
-        run_chains(&p.a, 1, c, p.norm_part, p.resid, p.bar, target, sA, sB, sred, cur, n2);
+        run_chains(p, &p.a, 1, c, p.norm_part, p.resid, p.bar, target, sA, sB, sred, cur, n2);
         const float rs_a = sqrtf(sqrtf(n2[0]));
         const float *ya = p.a.Y[cur[0]], *za = p.a.Z[cur[0]];
-        Prod pr{p.sig_s, ya, p.f, rs_a, 0.f, nullptr};           // f = Sig_s Qt
+        Prod pr{p.sig_s, ya, p.f, rs_a, 0.f, nullptr, 0};        // f = Sig_s Qt
         run_step(&pr, 1, c, sA, sB);
         grid_barrier(p.bar, target);
-        pr = Prod{ya, p.f, p.aux, rs_a, 0.f, nullptr};           // aux = Qt Sig_s Qt
+        pr = Prod{ya, p.f, p.aux, rs_a, 0.f, nullptr, 1};        // aux = Qt Sig_s Qt (symmetric)
         run_step(&pr, 1, c, sA, sB);
         grid_barrier(p.bar, target);
         int cur2[2];
@@ -328,12 +385,12 @@ __global__ void __launch_bounds__(CT) ns_coop_kernel(CoopParams p) {
         ChainBuf second = p.b;
         second.A = p.aux;
         second.lmin = p.eps * p.eps;   // Qt Sig_s Qt >= lambda_min(Qt)^2 lambda_min(Sig_s) >= eps^2
-        run_chains(&second, 1, c, p.norm_part + MAX_GRID, p.resid + NS_CAP_C, p.bar, target, sA, sB, sred, cur2, n22);
+        run_chains(p, &second, 1, c, p.norm_part + MAX_GRID, p.resid + NS_CAP_C, p.bar, target, sA, sB, sred, cur2, n22);
         const float rs_c = sqrtf(sqrtf(n22[0]));
-        pr = Prod{second.Y[cur2[0]], za, p.w, rs_c / rs_a, 0.f, nullptr};   // w = (Qt Sig_s Qt)^(1/2) Qt^-1
+        pr = Prod{second.Y[cur2[0]], za, p.w, rs_c / rs_a, 0.f, nullptr, 0};   // w = (Qt Sig_s Qt)^(1/2) Qt^-1
         run_step(&pr, 1, c, sA, sB);
         grid_barrier(p.bar, target);
-        pr = Prod{za, p.w, p.G, 1.f / rs_a, 0.f, nullptr};                  // T = Qt^-1 w
+        pr = Prod{za, p.w, p.G, 1.f / rs_a, 0.f, nullptr, 1};               // T = Qt^-1 w (symmetric)
         run_step(&pr, 1, c, sA, sB);
         grid_barrier(p.bar, target);
     }
@@ -346,7 +403,11 @@ __global__ void __launch_bounds__(CT) ns_coop_kernel(CoopParams p) {
         acc = warp_sum(acc);
         if (lane == 0) p.bias[job] = p.mu_s[(p.b_s == 1 ? 0 : b) * c + j] - acc;
     }
+    stamp(p);
 }
+
+long long *g_chain_stamps = nullptr;
+int g_chain_n_stamps = 0;
 
 bool coop_enabled() {
     static const bool v = [] {
@@ -390,14 +451,19 @@ int cov_coop_chain(float *const *m, int c, int mode, float eps, int style_reuse,
     p.norm_part = scratch;
     p.resid = reinterpret_cast<unsigned *>(scratch + 2 * MAX_GRID);
     p.bar = reinterpret_cast<unsigned *>(scratch + 2 * MAX_GRID + 2 * NS_CAP_C);
+    p.stamps = g_chain_stamps;
+    p.n_stamps = g_chain_n_stamps;
     OPTEX_CUDA(cudaMemsetAsync(p.resid, 0, sizeof(unsigned) * (2 * NS_CAP_C + 8), st));
-    const int tiles = (c / TILE) * (c / TILE);
-    int grid = 2 * tiles * ((mode == OPTEX_MODE_PCA && !style_reuse) ? 2 : 1);   // the widest step
+    const int tc = c / TILE, tiles = tc * tc, tri = tc * (tc + 1) / 2;
+    // the widest step: the update step (2 symmetric products per chain); the closing product has tc^2 tiles
+    int grid = 2 * tri * ((mode == OPTEX_MODE_PCA && !style_reuse) ? 2 : 1);
+    if (grid < tiles) grid = tiles;
     const int sms = sm_count();
     if (grid > sms) {
-        // whole rounds of the common step (one chain: tiles in the T-step, 2 tiles in the update step)
-        const int rounds = (2 * tiles + sms - 1) / sms;
-        grid = (2 * tiles + rounds - 1) / rounds;
+        // whole rounds of the common step (one chain: 2 tri tiles in the update step)
+        const int common = 2 * tri > tiles ? 2 * tri : tiles;
+        const int rounds = (common + sms - 1) / sms;
+        grid = (common + rounds - 1) / rounds;
     }
     if (grid > MAX_GRID) grid = MAX_GRID;
     const size_t smem = (size_t)(STAGES * TILE * LDA + STAGES * KC * TILE) * sizeof(float);
@@ -416,3 +482,11 @@ int cov_coop_chain(float *const *m, int c, int mode, float eps, int style_reuse,
 }
 
 }  // namespace optex
+
+// Debug hook (scripts/chain_stamps.py): a device buffer of n int64 that CTA 0 of the cooperative chain kernel fills
+// with clock64 behind every grid barrier of its next launches (kernel entry first, kernel end last); NULL: off.
+extern "C" int optex_debug_chain_stamps(long long *device_buffer, int n) {
+    optex::g_chain_stamps = device_buffer;
+    optex::g_chain_n_stamps = device_buffer ? n : 0;
+    return OPTEX_OK;
+}

@@ -15,6 +15,7 @@ from optimaltextures_b200 import texture
 
 size = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 mode = sys.argv[2] if len(sys.argv) > 2 else "pca"
+passes = int(sys.argv[3]) if len(sys.argv) > 3 else 5
 ref = reference.load()
 root = ref.path
 sd = {}
@@ -28,7 +29,7 @@ dev_styles = [s.cuda() for s in styles]
 lib = ob._lib.lib()
 outs = {}
 for overlap, warm in ((False, False), (True, False), (False, True), (True, True)):
-    model = texture.OptimalTexture(size=size, iters=500, passes=5, hist_mode=mode, state_dicts=sd,
+    model = texture.OptimalTexture(size=size, iters=500, passes=passes, hist_mode=mode, state_dicts=sd,
                                    overlap_style=overlap, pca_warm_start=warm)
     for rep in range(3):
         ob.manual_seed(0)
@@ -42,6 +43,8 @@ for overlap, warm in ((False, False), (True, False), (False, True), (True, True)
         launches = lib.optex_launch_count() - l0
     outs[(overlap, warm)] = out
     st = {k: round(v, 1) for k, v in model.stage_ms().items()}
+    pairs = [round(a.elapsed_time(b), 2) for a, b in model.profile.get("fit_pca", [])]
+    print("   fit_pca event pairs (ms):", pairs)
     print(f"overlap={overlap} warm={warm}: {dt * 1e3:.1f} ms  launches={launches}  stages={st}  k={model.last_pca_k} "
           f"sweeps={model.pca_sweeps}", flush=True)
 base = outs[(False, False)]
