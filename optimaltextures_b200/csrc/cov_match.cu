@@ -75,6 +75,26 @@ __global__ void colmean_final_kernel(const float *__restrict__ part, float *__re
 __global__ void center_kernel(const float *__restrict__ X, const float *__restrict__ mu, float *__restrict__ Xc,
                               int64_t hw, int c, int64_t total) {
     pdl_wait();
+    if ((c & 3) == 0 && ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Xc)) & 15) == 0) {
+        // four channels per thread: one 128-bit load / store, one division per quad
+        const int64_t quads = total >> 2;
+        const int cq = c >> 2;
+        const float4 *x4 = reinterpret_cast<const float4 *>(X);
+        float4 *o4 = reinterpret_cast<float4 *>(Xc);
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < quads;
+             i += (int64_t)gridDim.x * blockDim.x) {
+            const int64_t row = i / cq;
+            const int q = (int)(i - row * cq);
+            const float4 m = *reinterpret_cast<const float4 *>(mu + (row / hw) * c + 4 * q);
+            float4 v = x4[i];
+            v.x -= m.x;
+            v.y -= m.y;
+            v.z -= m.z;
+            v.w -= m.w;
+            o4[i] = v;
+        }
+        return;
+    }
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
         const int ch = (int)(i % c);
@@ -84,14 +104,32 @@ __global__ void center_kernel(const float *__restrict__ X, const float *__restri
 }
 // Sig = (sum_z part_z) / n  (+ eps on the diagonal); `part` is the Gram matrix of the CENTRED data, unless
 // sub_mean: then - sum_b (hw/n) mu_b mu_b^T is applied here                         histmatch.py:17-18
-__global__ void gram_reduce_kernel(const float *__restrict__ part, int nz, int64_t zstride, const float *__restrict__ mu,
-                                   int nb, int64_t hw, int c, float eps, float *__restrict__ Sig, int sub_mean) {
+__global__ void __launch_bounds__(256) gram_reduce_kernel(const float *__restrict__ part, int nz, int64_t zstride,
+                                                          const float *__restrict__ mu, int nb, int64_t hw, int c,
+                                                          float eps, float *__restrict__ Sig, int sub_mean) {
     pdl_wait();
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (int64_t)c * c) return;
-    int r = (int)(i / c), q = (int)(i % c);
+    // 32 elements per block; 8 groups of threads take the slices z = g, g + 8, ... and fold through shared memory
+    // (up to 256 slices: one thread per element would walk them as a dependent chain of L2 round trips)
+    __shared__ float red[8][33];
+    const int e = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int64_t i = (int64_t)blockIdx.x * 32 + e;
+    const bool ok = i < (int64_t)c * c;
+    float s0 = 0.f, s1 = 0.f;
+    if (ok) {
+        int z = g;
+        for (; z + 8 < nz; z += 16) {
+            s0 += part[z * zstride + i];
+            s1 += part[(z + 8) * zstride + i];
+        }
+        if (z < nz) s0 += part[z * zstride + i];
+    }
+    red[g][e] = s0 + s1;
+    __syncthreads();
+    if (g != 0 || !ok) return;
     float s = 0.f;
-    for (int z = 0; z < nz; ++z) s += part[z * zstride + i];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += red[k][e];
+    const int r = (int)(i / c), q = (int)(i % c);
     const float n = (float)(hw * nb);
     float m2 = 0.f;
     if (sub_mean)
@@ -374,7 +412,16 @@ struct NsState {
     int *flags;
 };
 constexpr int kMeanSplits = 64;
-constexpr int kGramSplits = 32;
+constexpr int kGramSplits = 32;   // at least this many K slices may be used; narrow matrices take more (gram_split_cap)
+// K slices of the Gram GEMM: a c x c output has few tiles (one at c <= 64 ... 32 at c = 512), so the slices are what
+// fills the SMs - two CTAs' worth of slices per SM, 32 ... 256 of them, each at least 256 rows long
+int gram_split_cap(int c) {
+    const int tiles = ((c + 127) / 128) * ((c + 63) / 64);
+    int cap = 2 * 148 / (tiles < 1 ? 1 : tiles);
+    if (cap < kGramSplits) cap = kGramSplits;
+    if (cap > 256) cap = 256;
+    return cap;
+}
 
 size_t ws_layout(int64_t n_t, int64_t n_s, int c, int b_max, Ws *w, void *base, size_t cap, bool *ok) {
     Arena ar(base, cap);
@@ -384,7 +431,7 @@ size_t ws_layout(int64_t n_t, int64_t n_s, int c, int b_max, Ws *w, void *base, 
     l.mu_s = ar.take<float>((size_t)b_max * c);
     l.bias = ar.take<float>((size_t)b_max * c);
     l.part_mean = ar.take<float>((size_t)b_max * kMeanSplits * c);
-    l.part_gram = ar.take<float>((size_t)kGramSplits * cc);
+    l.part_gram = ar.take<float>((size_t)gram_split_cap(c) * cc);
     l.centred = ar.take<float>((size_t)(n_t > n_s ? n_t : n_s) * c);
     for (int i = 0; i < 19; ++i) l.m[i] = ar.take<float>(cc);
     l.norm2 = ar.take<float>(2 * NS_STATE);
@@ -426,7 +473,8 @@ int moments(const float *X, int nb, int64_t hw, int c, float eps, float *mu, flo
         X = w.centred;
     }
     // Gram Xc^T Xc: A = Xc^T (stored [K = n, M = c]) and B = Xc (stored [K = n, N = c]), split over K
-    int nz = (int)(n / 512 < 1 ? 1 : (n / 512 > kGramSplits ? kGramSplits : n / 512));
+    const int zcap = gram_split_cap(c);
+    int nz = (int)(n / 256 < 1 ? 1 : (n / 256 > zcap ? zcap : n / 256));
     const int64_t zstride = (int64_t)c * c;
     int rc = OPTEX_ENOTSUP;
     if (g_want_tc()) {
@@ -450,7 +498,7 @@ int moments(const float *X, int nb, int64_t hw, int c, float eps, float *mu, flo
             nz = (int)((n + kz - 1) / kz);
         }
     }
-    launch_pdl(gram_reduce_kernel, dim3((unsigned)(cdiv((int64_t)c * c, 256))), dim3(256), 0, st, w.part_gram, nz, zstride, mu, nb, hw_div, c, cm ? 0.f : eps, Sig, 0);
+    launch_pdl(gram_reduce_kernel, dim3((unsigned)(cdiv((int64_t)c * c, 32))), dim3(256), 0, st, w.part_gram, nz, zstride, mu, nb, hw_div, c, cm ? 0.f : eps, Sig, 0);
     OPTEX_LAUNCH_CHECK("gram_reduce_kernel");
     if (cm) {
         OPTEX_TRY(shard_allreduce_f32_sum(cm, Sig, (size_t)c * c, st));

@@ -32,13 +32,16 @@ constexpr int B_MAX_S = 64;
 
 inline unsigned cdiv(int64_t a, int64_t b) { return (unsigned)((a + b - 1) / b); }
 
-// part[(b * splits + split) * c + ch] = sum over the split's rows of X[b * hw + r, ch]
+// part[(b * (splits / GC) + split / GC) * c + ch] = sum over the rows of the GC splits of a cluster of X[b * hw + r, ch]
+// (grid.x = splits, a multiple of GC; the GC CTAs of a cluster fold their sums through distributed shared memory)
+constexpr int GC = 8;
 template <int CP>
-__global__ void __launch_bounds__(ST) small_colsum_kernel(const float *__restrict__ X, float *__restrict__ part,
-                                                          int64_t hw, int c, int splits) {
+__global__ void __cluster_dims__(GC, 1, 1) __launch_bounds__(ST)
+    small_colsum_kernel(const float *__restrict__ X, float *__restrict__ part, int64_t hw, int c, int splits) {
     pdl_wait();
     constexpr int RP = ST / CP;
     __shared__ float red[RP][CP];
+    __shared__ float tot[CP];
     const int ch = threadIdx.x % CP, lr = threadIdx.x / CP;
     const int split = blockIdx.x, b = blockIdx.y;
     const int64_t rows = (hw + splits - 1) / splits;
@@ -57,12 +60,21 @@ __global__ void __launch_bounds__(ST) small_colsum_kernel(const float *__restric
     }
     red[lr][ch] = (a0 + a1) + (a2 + a3);
     __syncthreads();
-    if (lr == 0 && ch < c) {
+    if (lr == 0) {
         float s = 0.f;
 #pragma unroll
         for (int i = 0; i < RP; ++i) s += red[i][ch];
-        part[((int64_t)b * splits + split) * c + ch] = s;
+        tot[ch] = s;
     }
+    cg::cluster_group cluster = cg::this_cluster();
+    cluster.sync();
+    if (cluster.block_rank() == 0 && threadIdx.x < c) {
+        float s = 0.f;
+#pragma unroll
+        for (int r = 0; r < GC; ++r) s += cluster.map_shared_rank(tot, r)[threadIdx.x];
+        part[((int64_t)b * (splits / GC) + split / GC) * c + threadIdx.x] = s;
+    }
+    cluster.sync();  // nobody leaves while its shared memory is still being read
 }
 
 // mu[ch] = (sum over the splits of part[(b * splits + k) * c + ch]) / hw for one sample b, by all 256 threads of the
@@ -100,7 +112,6 @@ __device__ __forceinline__ void block_mean(const float *__restrict__ part, int b
 // 256 / (CP / 4)^2 such groups take the rows of a slab in turn.
 // The GC CTAs of a cluster fold their accumulators through distributed shared memory (rank r sums slice r of all GC
 // matrices in rank order), so the chain kernel reads ctas / GC partials instead of ctas.
-constexpr int GC = 8;
 template <int CP>
 __global__ void __cluster_dims__(GC, 1, 1) __launch_bounds__(ST)
     small_gram_kernel(const float *__restrict__ X, const float *__restrict__ part_sum, int splits,
@@ -153,6 +164,7 @@ __global__ void __cluster_dims__(GC, 1, 1) __launch_bounds__(ST)
         const int64_t n0 = s1, n1 = n0 < r1 ? slab_end(n0) : n0;
         if (n0 < r1) fetch(n0, n1);   // the next slab is in flight during the FMAs
         const int rows = (int)(s1 - s0);
+#pragma unroll 4
         for (int k = g; k < rows; k += NG) {
             const float4 a = *reinterpret_cast<const float4 *>(&tile[k][4 * ty]);
             const float4 bq = *reinterpret_cast<const float4 *>(&tile[k][4 * tx]);
@@ -335,16 +347,14 @@ __device__ void load_sig(const float *__restrict__ part, int nz, int c, float n,
         if (r < c && q < c) {
             const float *p = part + r * c + q;
             const int64_t zs = (int64_t)c * c;
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-            int z = 0;
-            for (; z + 3 < nz; z += 4) {
-                s0 += p[z * zs];
-                s1 += p[(z + 1) * zs];
-                s2 += p[(z + 2) * zs];
-                s3 += p[(z + 3) * zs];
+            float sum = 0.f;
+            for (int z0 = 0; z0 < nz; z0 += 8) {   // eight independent loads in flight, a fixed association
+                float t[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) t[i] = z0 + i < nz ? p[(z0 + i) * zs] : 0.f;
+                sum += ((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7]));
             }
-            for (; z < nz; ++z) s0 += p[z * zs];
-            v = ((s0 + s1) + (s2 + s3)) / n;
+            v = sum / n;
             if (r == q) v += eps;
         } else if (r == q) {
             v = eps > 0.f ? eps : 1.f;
@@ -446,29 +456,31 @@ __global__ void __launch_bounds__(ST) small_chain_kernel(const float *__restrict
 }
 
 // out[r][j] = sum_k X[r][k] G[j][k] + bias[b(r)][j]   (+ content blend: out += strength (content - out), optex.py:117)
-// A warp takes 32 rows at a time: coalesced load into its shared-memory tile, one row per lane in registers, results
-// written back to the tile and stored coalesced (with the blend).
-template <int CP>
+// A warp takes 32 * RPL rows at a time: coalesced load into its shared-memory tile, RPL rows per lane in registers (every
+// broadcast load of G feeds RPL rows), results written back to the tile as 128-bit stores and stored coalesced (with
+// the blend).
+template <int CP, int RPL>
 __global__ void __launch_bounds__(ST) small_apply_kernel(const float *__restrict__ X, const float *__restrict__ G,
                                                          const float *__restrict__ bias, float *__restrict__ out,
                                                          int64_t n, int64_t hw, int c,
                                                          const float *__restrict__ content, float strength) {
     pdl_wait();
-    constexpr int LDT = CP + 4;  // row stride of a warp's tile: conflict-free 128-bit row reads
+    constexpr int LDT = CP + 4;  // row stride of a warp's tile: conflict-free 128-bit row accesses
+    constexpr int RW = 32 * RPL;  // rows per warp and step
     extern __shared__ __align__(16) float sm[];
     float *sG = sm;                       // [CP][CP]  G[j][k], zero padded
-    float *tiles = sm + CP * CP;          // [8 warps][32][LDT]
+    float *tiles = sm + CP * CP;          // [8 warps][RW][LDT]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < CP * CP; i += ST) {
         const int j = i / CP, k = i % CP;
         sG[i] = (j < c && k < c) ? G[j * c + k] : 0.f;
     }
     __syncthreads();
-    float *tile = tiles + warp * 32 * LDT;
-    const int64_t groups = (n + 31) / 32;
+    float *tile = tiles + warp * RW * LDT;
+    const int64_t groups = (n + RW - 1) / RW;
     for (int64_t gi = (int64_t)blockIdx.x * (ST / 32) + warp; gi < groups; gi += (int64_t)gridDim.x * (ST / 32)) {
-        const int64_t r0 = gi * 32;
-        const int rows = (int)(n - r0 < 32 ? n - r0 : 32);
+        const int64_t r0 = gi * RW;
+        const int rows = (int)(n - r0 < RW ? n - r0 : RW);
         // coalesced load of rows x c floats (contiguous in memory) into the padded tile
         const float *src = X + r0 * c;
         const int total = rows * c;
@@ -479,34 +491,53 @@ __global__ void __launch_bounds__(ST) small_apply_kernel(const float *__restrict
             for (int i = lane; i < rows * (CP - c); i += 32) tile[(i / (CP - c)) * LDT + c + (i % (CP - c))] = 0.f;
         }
         __syncwarp();
-        if (lane < rows) {
-            float x[CP];
+        float x[RPL][CP];
+        const float *bs[RPL];
+#pragma unroll
+        for (int rr = 0; rr < RPL; ++rr) {
+            const int row = lane + 32 * rr < rows ? lane + 32 * rr : 0;   // rows past the end: computed, not stored
 #pragma unroll
             for (int q = 0; q < CP / 4; ++q) {
-                const float4 v = *reinterpret_cast<const float4 *>(&tile[lane * LDT + 4 * q]);
-                x[4 * q] = v.x;
-                x[4 * q + 1] = v.y;
-                x[4 * q + 2] = v.z;
-                x[4 * q + 3] = v.w;
+                const float4 v = *reinterpret_cast<const float4 *>(&tile[row * LDT + 4 * q]);
+                x[rr][4 * q] = v.x;
+                x[rr][4 * q + 1] = v.y;
+                x[rr][4 * q + 2] = v.z;
+                x[rr][4 * q + 3] = v.w;
             }
-            const float *bs = bias + ((r0 + lane) / hw) * c;
+            bs[rr] = bias + ((r0 + row) / hw) * c;
+        }
+        __syncwarp();   // every lane holds its rows: the tile can take the results
 #pragma unroll 1
-            for (int j0 = 0; j0 < c; j0 += 4) {
-                float a[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int j0 = 0; j0 < CP; j0 += 4) {
+            if (j0 >= c) break;
+            float a[RPL][4];
 #pragma unroll
-                for (int q = 0; q < CP / 4; ++q) {
+            for (int rr = 0; rr < RPL; ++rr)
 #pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        const float4 gq = *reinterpret_cast<const float4 *>(&sG[(j0 + jj) * CP + 4 * q]);
-                        a[jj] = fmaf(x[4 * q], gq.x, a[jj]);
-                        a[jj] = fmaf(x[4 * q + 1], gq.y, a[jj]);
-                        a[jj] = fmaf(x[4 * q + 2], gq.z, a[jj]);
-                        a[jj] = fmaf(x[4 * q + 3], gq.w, a[jj]);
+                for (int jj = 0; jj < 4; ++jj) a[rr][jj] = 0.f;
+#pragma unroll
+            for (int q = 0; q < CP / 4; ++q) {
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const float4 gq = *reinterpret_cast<const float4 *>(&sG[(j0 + jj) * CP + 4 * q]);
+#pragma unroll
+                    for (int rr = 0; rr < RPL; ++rr) {
+                        a[rr][jj] = fmaf(x[rr][4 * q], gq.x, a[rr][jj]);
+                        a[rr][jj] = fmaf(x[rr][4 * q + 1], gq.y, a[rr][jj]);
+                        a[rr][jj] = fmaf(x[rr][4 * q + 2], gq.z, a[rr][jj]);
+                        a[rr][jj] = fmaf(x[rr][4 * q + 3], gq.w, a[rr][jj]);
                     }
                 }
+            }
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj)
-                    if (j0 + jj < c) tile[lane * LDT + j0 + jj] = a[jj] + bs[j0 + jj];
+            for (int rr = 0; rr < RPL; ++rr) {
+                if (lane + 32 * rr >= rows) continue;
+                float4 o;
+                o.x = a[rr][0] + (j0 < c ? bs[rr][j0] : 0.f);
+                o.y = a[rr][1] + (j0 + 1 < c ? bs[rr][j0 + 1] : 0.f);
+                o.z = a[rr][2] + (j0 + 2 < c ? bs[rr][j0 + 2] : 0.f);
+                o.w = a[rr][3] + (j0 + 3 < c ? bs[rr][j0 + 3] : 0.f);
+                *reinterpret_cast<float4 *>(&tile[(lane + 32 * rr) * LDT + j0]) = o;   // columns >= c: never stored
             }
         }
         __syncwarp();
@@ -530,17 +561,19 @@ struct SmallWs {
     float *mu_s, *bias, *sum_p, *sum_s, *G, *style_keep, *part_t, *part_s;
 };
 
+// CTAs of the column-sum kernel per sample: whole clusters, >= 128 rows each, two CTAs per SM over all samples
 int sum_splits(int64_t hw, int nb) {
-    int64_t s = hw / 128;  // >= 128 rows per split
-    int64_t cap = 2 * (int64_t)sm_count() / (nb < 1 ? 1 : nb);   // two CTAs per SM over all samples
+    int64_t s = hw / 128;
+    int64_t cap = 2 * (int64_t)sm_count() / (nb < 1 ? 1 : nb);
     if (cap > MAX_SUM_SPLITS / (nb < 1 ? 1 : nb)) cap = MAX_SUM_SPLITS / (nb < 1 ? 1 : nb);
     if (s > cap) s = cap;
-    if (s < 1) s = 1;
+    s = s / GC * GC;
+    if (s < GC) s = GC;
     return (int)s;
 }
 int gram_ctas(int64_t n) {
     int64_t s = n / (2 * SLAB);  // >= 2 slabs per CTA
-    const int64_t cap = 2 * (int64_t)sm_count();
+    const int64_t cap = (int64_t)sm_count();   // one per SM: the chain kernel reads ctas / GC partial matrices
     if (s > cap) s = cap;
     if (s < 1) s = 1;
     return (int)s;
@@ -569,14 +602,15 @@ int moments_small(const float *X, int nb, int64_t hw, int c, float *part_sum, fl
     const int splits = sum_splits(hw, nb);
     launch_pdl(small_colsum_kernel<CP>, dim3(splits, nb), dim3(ST), 0, st, X, part_sum, hw, c, splits);
     OPTEX_LAUNCH_CHECK("small_colsum_kernel");
+    const int parts = splits / GC;   // what the cluster fold leaves per sample
     int ctas = gram_ctas(n);
     int64_t rows = ((n + ctas - 1) / ctas + SLAB - 1) / SLAB * SLAB;
     ctas = (int)((n + rows - 1) / rows);
     ctas = (ctas + GC - 1) / GC * GC;   // whole clusters; the CTAs past the last row contribute zeros
-    launch_pdl(small_gram_kernel<CP>, dim3(ctas), dim3(ST), 0, st, X, (const float *)part_sum, splits, part_gram, n, hw,
+    launch_pdl(small_gram_kernel<CP>, dim3(ctas), dim3(ST), 0, st, X, (const float *)part_sum, parts, part_gram, n, hw,
                c, rows);
     OPTEX_LAUNCH_CHECK("small_gram_kernel");
-    *splits_out = splits;
+    *splits_out = parts;
     *nz_out = ctas / GC;
     return OPTEX_OK;
 }
@@ -590,14 +624,15 @@ int step_small(const float *P, const float *S, float *out, int b_p, int64_t hw_p
     OPTEX_TRY(moments_small<CP>(P, b_p, hw_p, c, w.sum_p, w.part_t, &sp_t, &nz_t, st));
     if (!style_reuse) OPTEX_TRY(moments_small<CP>(S, b_s, hw_s, c, w.sum_s, w.part_s, &sp_s, &nz_s, st));
     const size_t chain_smem = (size_t)(8 * CP * CP + 16 + CP) * sizeof(float);
-    const size_t apply_smem = (size_t)(CP * CP + (ST / 32) * 32 * (CP + 4)) * sizeof(float);
+    constexpr int RPL = CP <= 32 ? 2 : 1;   // rows per lane of the application kernel
+    const size_t apply_smem = (size_t)(CP * CP + (ST / 32) * 32 * RPL * (CP + 4)) * sizeof(float);
     static bool attr_done[64] = {};
     int dev = 0;
     OPTEX_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !attr_done[dev]) {
         OPTEX_CUDA(cudaFuncSetAttribute(small_chain_kernel<CP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)chain_smem));
-        OPTEX_CUDA(cudaFuncSetAttribute(small_apply_kernel<CP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        OPTEX_CUDA(cudaFuncSetAttribute(small_apply_kernel<CP, RPL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)apply_smem));
         if (dev >= 0 && dev < 64) attr_done[dev] = true;
     }
@@ -605,10 +640,10 @@ int step_small(const float *P, const float *S, float *out, int b_p, int64_t hw_p
                (const float *)w.part_s, nz_s, (float)n_s, w.style_keep, style_reuse ? 1 : 0, mode, eps, c,
                (const float *)w.sum_p, sp_t, hw_p, (const float *)w.sum_s, sp_s, hw_s, w.mu_s, b_p, b_s, w.G, w.bias);
     OPTEX_LAUNCH_CHECK("small_chain_kernel");
-    int64_t grid = (n_p + 32 * (ST / 32) - 1) / (32 * (ST / 32));
+    int64_t grid = (n_p + 32 * RPL * (ST / 32) - 1) / (32 * RPL * (ST / 32));
     const int64_t cap = 4 * (int64_t)sm_count();
     if (grid > cap) grid = cap;
-    launch_pdl(small_apply_kernel<CP>, dim3((unsigned)grid), dim3(ST), apply_smem, st, P, (const float *)w.G,
+    launch_pdl(small_apply_kernel<CP, RPL>, dim3((unsigned)grid), dim3(ST), apply_smem, st, P, (const float *)w.G,
                (const float *)w.bias, out, n_p, hw_p, c, content, strength);
     OPTEX_LAUNCH_CHECK("small_apply_kernel");
     return OPTEX_OK;

@@ -3,7 +3,9 @@ W = G (pca.cu) against the same iteration on the rows of the Cholesky factor R o
 preconditioning: R R^T is one LR step closer to diagonal than G, the singular values are sigma instead of
 lambda = sigma^2, and the eigenvectors are the normalised rows of the final W - no V to carry).  Same round-robin
 order, same JTOL / early-exit rule as the kernel.  Also a BLOCKED form (b rows per block, a pair of blocks solved
-exactly per step: c / b - 1 rounds per sweep instead of c - 1).  Usage: python scripts/jacobi_sim.py [c] [n ...]"""
+exactly per step: c / b - 1 rounds per sweep instead of c - 1).  `--blocked-order`: the pairing ORDER of round 2's
+pca_jacobi_blk_kernel against the round-robin order (sweep counts, lambda_i = |w_i| without V).
+Usage: python scripts/jacobi_sim.py [--blocked-order] [c] [n ...]"""
 import sys
 
 import numpy as np
@@ -91,8 +93,72 @@ def features(n, c, seed):
     return np.maximum(g.standard_normal((n, c)) @ mix + 0.3, 0).astype(np.float32)
 
 
-c = int(sys.argv[1]) if len(sys.argv) > 1 else 128
-ns = [int(v) for v in sys.argv[2:]] or [c * 3 // 4, 3 * c, 8 * c]
+_args = [v for v in sys.argv[1:] if not v.startswith("--")]
+c = int(_args[0]) if _args else 128
+ns = [int(v) for v in _args[1:]] or [c * 3 // 4, 3 * c, 8 * c]
+def blocked_order_rows(W, bsz, max_sweeps=40, floor_rel=1e-13):
+    """The ORDER of pca.cu's pca_jacobi_blk_kernel (round 2): blocks of `bsz` rows paired round-robin; a block pair
+    rotates its bsz x bsz cross pairs in bsz sub-rounds of bsz disjoint pairs; global round 0 of every sweep runs the
+    full tournament of the 2 bsz rows instead (the pairs inside each block).  Same rotations and stopping rule as
+    jacobi_rows - only the order differs (and with it the number of grid-wide barriers: c / bsz - 1 per sweep)."""
+    c = W.shape[0]
+    nb = c // bsz
+    floor_abs = (floor_rel * np.trace(W)) ** 2
+    brounds = list(schedule(nb))
+    inner = list(schedule(2 * bsz))
+
+    def rotate(a, b, st):
+        wa, wb = W[a], W[b]
+        al, be, ga = (wa * wa).sum(1), (wb * wb).sum(1), (wa * wb).sum(1)
+        go = (ga * ga > JTOL * JTOL * al * be) & (np.abs(ga) > floor_abs)
+        if not go.any():
+            return
+        a2, b2, al, be, ga = a[go], b[go], al[go], be[go], ga[go]
+        zeta = (be - al) / (2 * ga)
+        t = np.where(zeta >= 0, 1.0, -1.0) / (np.abs(zeta) + np.sqrt(1 + zeta * zeta))
+        cs = 1 / np.sqrt(1 + t * t)
+        sn = cs * t
+        wa, wb = W[a2], W[b2]
+        W[a2], W[b2] = cs[:, None] * wa - sn[:, None] * wb, sn[:, None] * wa + cs[:, None] * wb
+        st[0] += int(go.sum())
+        st[1] = max(st[1], float((ga * ga / (al * be)).max()))
+
+    for sweep in range(max_sweeps):
+        st = [0, 0.0]
+        for gr, (A, B) in enumerate(brounds):
+            if gr == 0:
+                for ia, ib in inner:
+                    ra = np.where(ia < bsz, A[:, None] * bsz + ia, B[:, None] * bsz + ia - bsz).ravel()
+                    rb = np.where(ib < bsz, A[:, None] * bsz + ib, B[:, None] * bsz + ib - bsz).ravel()
+                    rotate(ra, rb, st)
+            else:
+                i = np.arange(bsz)
+                for sr in range(bsz):
+                    rotate((A[:, None] * bsz + i).ravel(), (B[:, None] * bsz + (i + sr) % bsz).ravel(), st)
+        if st[0] == 0 or st[1] <= JEXIT * JEXIT:
+            return sweep + 1
+    return max_sweeps
+
+
+if "--blocked-order" in sys.argv:
+    for n in ns:
+        x = features(n, c, 0).astype(np.float64)
+        xc = x - x.mean()
+        G = xc.T @ xc
+        lam = np.linalg.eigvalsh(G)[::-1]
+        row = [f"c={c} n={n}: round-robin {jacobi_rows(G.copy(), np.eye(c))} sweeps"]
+        for bsz in (4, 8, 16):
+            if c % (2 * bsz):
+                continue
+            W = G.copy()
+            sw = blocked_order_rows(W, bsz)
+            lw = np.sort(np.sqrt((W * W).sum(1)))[::-1]          # lambda_i = |w_i| (no V)
+            row.append(f"blocks of {bsz}: {sw} sweeps, {c // bsz - 1} barriers / sweep, "
+                       f"dlambda {np.abs(lw - lam).max() / lam[0]:.1e}")
+        print(" | ".join(row), flush=True)
+    sys.exit(0)
+
+
 for n in ns:
     x = features(n, c, 0).astype(np.float64)
     xc = x - x.mean()
