@@ -209,12 +209,12 @@ size_t cov_match_ws_bytes(int64_t n_t, int64_t n_s, int c, int mode);
 int cov_ot_step(const float *P, const float *S, const float *R, float *out, int b_p, int64_t hw_p, int b_s,
                 int64_t hw_s, int c, int mode, float eps, const float *content, float strength, void *workspace,
                 size_t workspace_bytes, cudaStream_t st, int style_reuse = 0);
-// narrow blocks (c <= 64, pca / sym): cov_small.cu - five launches per step, the C x C chain on one CTA
+// narrow blocks (c <= 64, chol / pca / sym): cov_small.cu - five launches per step, the C x C chain on one CTA
 bool cov_small_supported(int c, int mode, int b_p, int b_s);
 size_t cov_small_ws_bytes(int64_t n_t, int64_t n_s, int c);
-int cov_small_step(const float *P, const float *S, float *out, int b_p, int64_t hw_p, int b_s, int64_t hw_s, int c,
-                   int mode, float eps, const float *content, float strength, void *workspace, size_t workspace_bytes,
-                   cudaStream_t st, int style_reuse);
+int cov_small_step(const float *P, const float *S, const float *R, float *out, int b_p, int64_t hw_p, int b_s,
+                   int64_t hw_s, int c, int mode, float eps, const float *content, float strength, void *workspace,
+                   size_t workspace_bytes, cudaStream_t st, int style_reuse);
 // 64 < c <= 384 (pca / sym): cov_chain.cu - the whole C x C chain (Newton-Schulz, closing products, bias) as one
 // cooperative kernel on the 19 c x c matrices of cov_match.cu's workspace
 bool cov_coop_supported(int c, int mode);

@@ -730,7 +730,7 @@ int cov_ot_step(const float *P, const float *S, const float *R, float *out, int 
     // not commute with a rotation, chol keeps it.
     if (mode != OPTEX_MODE_CHOL) R = nullptr;
     if (!g_shard && cov_small_supported(c, mode, b_p, b_s))
-        return cov_small_step(P, S, out, b_p, hw_p, b_s, hw_s, c, mode, eps, content, strength, workspace,
+        return cov_small_step(P, S, R, out, b_p, hw_p, b_s, hw_s, c, mode, eps, content, strength, workspace,
                               workspace_bytes, st, style_reuse);
     Ws w;
     bool ok = false;
@@ -757,6 +757,8 @@ int cov_ot_step(const float *P, const float *S, const float *R, float *out, int 
     const bool coop = !R && cov_coop_supported(c, mode);
     if (coop) {
         // pca / sym at the PCA'd layer widths: Newton-Schulz chain(s), closing products and bias in ONE cooperative kernel
+        // (a cooperative blocked Cholesky + triangular solve for chol was built and measured: its sequential 32-wide
+        // panel steps and row substitutions behind grid barriers came out no faster than the launch path - DESIGN 8)
         OPTEX_TRY(cov_coop_chain(w.m, c, mode, eps, style_reuse, w.mu_p, w.mu_s, b_p, b_s, w.bias, w.coop, st));
     } else if (mode == OPTEX_MODE_CHOL) {
         // ---- fork: the style-side chain (sandwich, factorisation) on the side stream

@@ -1,4 +1,4 @@
-// Covariance hist modes pca / sym for NARROW blocks (c <= 64 channels) - hist_match() histmatch.py:13-46 inside
+// Covariance hist modes chol / pca / sym for NARROW blocks (c <= 64 channels) - hist_match() histmatch.py:13-46 inside
 // optimal_transport() optex.py:167-177, the same algebra as cov_match.cu (rotation cancelled, moments of the un-rotated
 // block, one application pass with the means folded into a bias), specialised for the shapes where cov_match.cu's
 // launch chain is pure latency: a 512^2 synthesis spends 160 of its 493 OT iterations on conv1_1 (262 144 pixels x 23
@@ -12,8 +12,9 @@
 //   small_chain_kernel   ONE CTA: Sig = cov + eps I, the coupled Newton-Schulz chain(s) with every matrix in shared
 //                        memory and a real early exit on the residual, T, the bias
 //   small_apply_kernel   out = X T^T + bias (+ content blend, optex.py:117), rows staged through shared memory
-// fp32 FFMA throughout (more accurate than the 3xTF32 products of the wide path).  chol and the pixel-sharded step
-// stay on cov_match.cu.
+// fp32 FFMA throughout (more accurate than the 3xTF32 products of the wide path).  chol takes the same four launches
+// (the rotation sandwiches, both Cholesky factorisations, the triangular solve and G = R T R^T in the chain kernel's
+// shared memory); the pixel-sharded step stays on cov_match.cu.
 #include <cooperative_groups.h>
 
 #include "common.cuh"
@@ -363,9 +364,57 @@ __device__ void load_sig(const float *__restrict__ part, int nz, int c, float n,
     }
 }
 
+// In-place lower Cholesky factor of the SPD matrix A (CP x CP, shared memory); the strict upper triangle is zeroed.
+// Right-looking, one column per step: the CTA's 256 threads share the rank-1 update of the trailing block.
+template <int CP>
+__device__ void chol_smem(float *A) {
+    const int tid = threadIdx.x;
+    for (int k = 0; k < CP; ++k) {
+        const float d = sqrtf(A[k * CP + k]);   // every thread reads the same value (broadcast)
+        __syncthreads();
+        if (tid == 0) A[k * CP + k] = d;
+        const float inv = 1.f / d;
+        for (int r = k + 1 + tid; r < CP; r += ST) A[r * CP + k] *= inv;
+        __syncthreads();
+        const int m = CP - k - 1;               // trailing block: rows / columns k + 1 .. CP - 1, lower triangle
+        for (int i = tid; i < m * m; i += ST) {
+            const int r = k + 1 + i / m, q = k + 1 + i % m;
+            if (q <= r) A[r * CP + q] = fmaf(-A[r * CP + k], A[q * CP + k], A[r * CP + q]);
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < CP * CP; i += ST)
+        if (i % CP > i / CP) A[i] = 0.f;
+    __syncthreads();
+}
+
+// T = Ls Lt^-1 for lower-triangular Ls, Lt (histmatch.py:25-27): row r of T solves  t Lt = ls_r  from the last column
+// backwards; one thread per row, T stored TRANSPOSED in Tt while it is built (thread r owns column r: conflict-free),
+// every thread reads the same Lt element at the same step (broadcast).  T is lower triangular.
+template <int CP>
+__device__ void trsm_smem(const float *Ls, const float *Lt, float *Tt, float *T) {
+    const int r = threadIdx.x;
+    if (r < CP) {
+        for (int j = CP - 1; j >= 0; --j) {
+            float acc = 0.f;
+            if (j <= r) {
+                acc = Ls[r * CP + j];
+                for (int k = j + 1; k <= r; ++k) acc = fmaf(-Tt[k * CP + r], Lt[k * CP + j], acc);
+                acc /= Lt[j * CP + j];
+            }
+            Tt[j * CP + r] = acc;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < CP * CP; i += ST) T[i] = Tt[(i % CP) * CP + i / CP];
+    __syncthreads();
+}
+
 // mode pca:  T = Sig_s^(1/2) Sig_t^(-1/2)                               histmatch.py:29-34
 // mode sym:  T = Qt^-1 (Qt Sig_s Qt)^(1/2) Qt^-1,  Qt = Sig_t^(1/2)     histmatch.py:36-42
-// style_state: 0 = compute the style side from part_s (and store it: sig_s for sym, Y2 = Sig_s^(1/2) for pca),
+// mode chol: T = L_s L_t^-1 with L = chol(R^T Sig R + eps I) in the ROTATED frame (Cholesky factors do not commute
+//            with a rotation), G = R T R^T                                histmatch.py:24-27, optex.py:167-177
+// style_state: 0 = compute the style side from part_s (and store it: sig_s for sym / chol, Y2 = Sig_s^(1/2) for pca),
 //              1 = reuse what an earlier call stored (optex_ot_loop: same S in every iteration)
 template <int CP>
 __global__ void __launch_bounds__(ST) small_chain_kernel(const float *__restrict__ part_t, int nz_t, float n_t,
@@ -375,7 +424,7 @@ __global__ void __launch_bounds__(ST) small_chain_kernel(const float *__restrict
                                                          int splits_p, int64_t hw_p, const float *__restrict__ sum_s,
                                                          int splits_s, int64_t hw_s, float *__restrict__ mu_s,
                                                          int b_p, int b_s, float *__restrict__ G,
-                                                         float *__restrict__ bias) {
+                                                         float *__restrict__ bias, const float *__restrict__ R) {
     pdl_wait();
     extern __shared__ __align__(16) float sm[];
     constexpr int MM = CP * CP;
@@ -404,6 +453,44 @@ __global__ void __launch_bounds__(ST) small_chain_kernel(const float *__restrict
         ns_chain_smem<CP>(m0, m1, m2, m3, m4, c, eps, scr, &Yt, &Zt);
         mm_smem<CP>(m5, Zt, m6, 1.f, 0.f, c, nullptr);  // T = Y2 Z
         Tres = m6;
+    } else if (mode == OPTEX_MODE_CHOL) {
+        // moments without eps when a rotation follows (eps is added in the rotated frame, histmatch.py:18,22)
+        const float eps_in = R ? 0.f : eps;
+        if (style_state == 0) {
+            load_sig<CP>(part_s, nz_s, c, n_s, eps_in, m1);
+            __syncthreads();
+            for (int i = tid; i < MM; i += ST) style_keep[i] = m1[i];
+        } else {
+            for (int i = tid; i < MM; i += ST) m1[i] = style_keep[i];
+        }
+        load_sig<CP>(part_t, nz_t, c, n_t, eps_in, m0);
+        if (R) {
+            // m2 = R padded with the identity, m3 = its transpose
+            for (int i = tid; i < MM; i += ST) {
+                const int r = i / CP, q = i % CP;
+                const float v = (r < c && q < c) ? R[r * c + q] : (r == q ? 1.f : 0.f);
+                m2[i] = v;
+                m3[q * CP + r] = v;
+            }
+            __syncthreads();
+            mm_smem<CP>(m0, m2, m4, 1.f, 0.f, c, nullptr);   // Sig_t R
+            mm_smem<CP>(m1, m2, m5, 1.f, 0.f, c, nullptr);   // Sig_s R
+            __syncthreads();
+            mm_smem<CP>(m3, m4, m0, 1.f, eps, c, nullptr);   // R^T Sig_t R + eps I
+            mm_smem<CP>(m3, m5, m1, 1.f, eps, c, nullptr);   // R^T Sig_s R + eps I
+        }
+        __syncthreads();
+        chol_smem<CP>(m0);                                   // L_t
+        chol_smem<CP>(m1);                                   // L_s
+        trsm_smem<CP>(m1, m0, m4, m5);                       // m5 = T = L_s L_t^-1
+        if (R) {
+            mm_smem<CP>(m5, m3, m4, 1.f, 0.f, c, nullptr);   // T R^T
+            __syncthreads();
+            mm_smem<CP>(m2, m4, m6, 1.f, 0.f, c, nullptr);   // G = R T R^T
+            Tres = m6;
+        } else {
+            Tres = m5;
+        }
     } else {
         if (style_state == 0) {
             load_sig<CP>(part_s, nz_s, c, n_s, eps, m5);
@@ -616,9 +703,9 @@ int moments_small(const float *X, int nb, int64_t hw, int c, float *part_sum, fl
 }
 
 template <int CP>
-int step_small(const float *P, const float *S, float *out, int b_p, int64_t hw_p, int b_s, int64_t hw_s, int c,
-               int mode, float eps, const float *content, float strength, const SmallWs &w, cudaStream_t st,
-               int style_reuse) {
+int step_small(const float *P, const float *S, const float *R, float *out, int b_p, int64_t hw_p, int b_s,
+               int64_t hw_s, int c, int mode, float eps, const float *content, float strength, const SmallWs &w,
+               cudaStream_t st, int style_reuse) {
     const int64_t n_p = (int64_t)b_p * hw_p, n_s = (int64_t)b_s * hw_s;
     int nz_t = 0, nz_s = 0, sp_t = 0, sp_s = 0;
     OPTEX_TRY(moments_small<CP>(P, b_p, hw_p, c, w.sum_p, w.part_t, &sp_t, &nz_t, st));
@@ -638,7 +725,7 @@ int step_small(const float *P, const float *S, float *out, int b_p, int64_t hw_p
     }
     launch_pdl(small_chain_kernel<CP>, dim3(1), dim3(ST), chain_smem, st, (const float *)w.part_t, nz_t, (float)n_p,
                (const float *)w.part_s, nz_s, (float)n_s, w.style_keep, style_reuse ? 1 : 0, mode, eps, c,
-               (const float *)w.sum_p, sp_t, hw_p, (const float *)w.sum_s, sp_s, hw_s, w.mu_s, b_p, b_s, w.G, w.bias);
+               (const float *)w.sum_p, sp_t, hw_p, (const float *)w.sum_s, sp_s, hw_s, w.mu_s, b_p, b_s, w.G, w.bias, R);
     OPTEX_LAUNCH_CHECK("small_chain_kernel");
     int64_t grid = (n_p + 32 * RPL * (ST / 32) - 1) / (32 * RPL * (ST / 32));
     const int64_t cap = 4 * (int64_t)sm_count();
@@ -660,8 +747,9 @@ bool small_enabled() {
 }  // namespace
 
 bool cov_small_supported(int c, int mode, int b_p, int b_s) {
-    return small_enabled() && c >= 1 && c <= 64 && (mode == OPTEX_MODE_PCA || mode == OPTEX_MODE_SYM) &&
-           b_p <= B_MAX_S && b_s <= B_MAX_S;
+    return small_enabled() && c >= 1 && c <= 64 &&
+           (mode == OPTEX_MODE_PCA || mode == OPTEX_MODE_SYM || mode == OPTEX_MODE_CHOL) && b_p <= B_MAX_S &&
+           b_s <= B_MAX_S;
 }
 
 size_t cov_small_ws_bytes(int64_t n_t, int64_t n_s, int c) {
@@ -669,9 +757,9 @@ size_t cov_small_ws_bytes(int64_t n_t, int64_t n_s, int c) {
     return small_layout(n_t, n_s, c, nullptr, nullptr, 0, nullptr) + 256;
 }
 
-int cov_small_step(const float *P, const float *S, float *out, int b_p, int64_t hw_p, int b_s, int64_t hw_s, int c,
-                   int mode, float eps, const float *content, float strength, void *workspace, size_t workspace_bytes,
-                   cudaStream_t st, int style_reuse) {
+int cov_small_step(const float *P, const float *S, const float *R, float *out, int b_p, int64_t hw_p, int b_s,
+                   int64_t hw_s, int c, int mode, float eps, const float *content, float strength, void *workspace,
+                   size_t workspace_bytes, cudaStream_t st, int style_reuse) {
     SmallWs w;
     bool ok = false;
     small_layout((int64_t)b_p * hw_p, (int64_t)b_s * hw_s, c, &w, workspace, workspace_bytes, &ok);
@@ -681,8 +769,8 @@ int cov_small_step(const float *P, const float *S, float *out, int b_p, int64_t 
         return OPTEX_EWORKSPACE;
     }
     if (c <= 32)
-        return step_small<32>(P, S, out, b_p, hw_p, b_s, hw_s, c, mode, eps, content, strength, w, st, style_reuse);
-    return step_small<64>(P, S, out, b_p, hw_p, b_s, hw_s, c, mode, eps, content, strength, w, st, style_reuse);
+        return step_small<32>(P, S, R, out, b_p, hw_p, b_s, hw_s, c, mode, eps, content, strength, w, st, style_reuse);
+    return step_small<64>(P, S, R, out, b_p, hw_p, b_s, hw_s, c, mode, eps, content, strength, w, st, style_reuse);
 }
 
 }  // namespace optex
