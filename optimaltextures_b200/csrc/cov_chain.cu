@@ -98,7 +98,7 @@ __device__ void tile_product(const Prod &p, int c, int i0, int j0, float *sA, fl
         const int kv = c - ch * KC < KC ? c - ch * KC : KC;
         const int kq = kv >> 2;                              // this group's quarter of the chunk: kq consecutive k
         const float *a = sA + (ch % STAGES) * TILE * LDA + g * kq, *b = sB + (ch % STAGES) * KC * TILE + g * kq * TILE;
-        for (int k = 0; k < kq; k += 4) {
+        auto fma4 = [&](int k) {
             float av[4][4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -117,6 +117,12 @@ __device__ void tile_product(const Prod &p, int c, int i0, int j0, float *sA, fl
 #pragma unroll
                     for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i][kk], bv[j], acc[i][j]);
             }
+        };
+        if (kq == KC / 4) {   // the full chunk: a compile-time trip count lets the loads of step k + 4 pass the FMAs of k
+#pragma unroll
+            for (int k = 0; k < KC / 4; k += 4) fma4(k);
+        } else {
+            for (int k = 0; k < kq; k += 4) fma4(k);
         }
     }
     cp_async_wait<0>();
