@@ -1339,10 +1339,14 @@ inline int pick_block_n(int64_t M, int64_t N, int nz) {
     if (force) return atoi(force);
     for (int bn : {256, 128}) {
         if (N <= bn / 2) continue;
-        if (mt * ((N + bn - 1) / bn) * nz >= want) return bn;
+        // 128-wide tiles already from 0.7 tiles per SM: one partial wave of them beats 1.4+ waves of 64-wide tiles,
+        // which pull twice the A bytes per MMA and sit on the L2 -> SM limit (VGG conv4_x of a 512^2 image: 128 tiles;
+        // Encoder(5) 1.92 -> 1.68 ms, Decoder(5) 2.07 -> 1.88 ms)
+        const int64_t need = bn == 128 ? (want * 7 + 9) / 10 : want;
+        if (mt * ((N + bn - 1) / bn) * nz >= need) return bn;
     }
     if (N > 128 && mt * ((N + 63) / 64) * nz > 4 * want) return 256;
-    return N <= 64 ? 64 : (mt * ((N + 127) / 128) * nz >= want ? 128 : 64);
+    return N <= 64 ? 64 : (mt * ((N + 127) / 128) * nz >= (want * 7 + 9) / 10 ? 128 : 64);
 }
 
 }  // namespace

@@ -240,6 +240,35 @@ def test_cpu_tensors_are_refused(ob):
         model.forward(torch.rand(1, 3, 32, 32), [torch.rand(1, 3, 32, 32)])
 
 
+@pytest.mark.parametrize("mode", ["pca", "cdf"])
+def test_overlapped_schedule_is_bit_identical(ob, mode):
+    """The default schedule (the style side of pass p + 1 - encoders and the five cooperative PCA solves - on a side
+    stream beside pass p's OT loops) gives the image of the serial schedule bit for bit, run after run; passes of
+    equal size share one style-side result (one set of Jacobi solves per distinct size)."""
+    from optimaltextures_b200 import texture
+
+    sd = texture_cases.state_dicts()
+    g = torch.Generator().manual_seed(3)
+    style = torch.rand(1, 3, 96, 64, generator=g).cuda()
+    pastiche = torch.rand(1, 3, 64, 64, generator=g).cuda()
+    outs = {}
+    for overlap in (False, True, True):
+        model = texture.OptimalTexture(size=128, iters=60, passes=3, hist_mode=mode, state_dicts=sd,
+                                       overlap_style=overlap)
+        ob.manual_seed(5)
+        out = model.forward(pastiche, [style])
+        assert bool(torch.isfinite(out).all())
+        if overlap in outs:
+            assert torch.equal(out, outs[overlap]), "two runs of the overlapped schedule differ"
+        outs[overlap] = out
+        assert len(model.pca_sweeps) == 3                      # sizes 256, 192, 128: three distinct style sides
+    assert torch.equal(outs[False], outs[True])
+    same = texture.OptimalTexture(size=64, iters=40, passes=3, hist_mode=mode, no_multires=True, state_dicts=sd)
+    ob.manual_seed(5)
+    out = same.forward(pastiche, [style])
+    assert bool(torch.isfinite(out).all()) and len(same.pca_sweeps) == 1   # three passes of 64^2: one set of solves
+
+
 def test_fit_pca_many_equals_fit_pca(ob):
     """The concurrent per-layer PCA of a pass (side streams) == five sequential `fit_pca` calls, bit for bit."""
     g = torch.Generator().manual_seed(4)
