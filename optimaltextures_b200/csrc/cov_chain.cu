@@ -218,7 +218,7 @@ struct CoopParams {
     float *f, *aux, *w;        // sym scratch
     float *G, *bias;
     const float *mu_p, *mu_s;
-    float *norm_part;          // [2][MAX_GRID]
+    float *norm_part;          // [2 chains][sum of squares, largest row sum][MAX_GRID]
     unsigned *resid;           // [2][NS_CAP_C], zeroed before the launch
     unsigned *bar;             // zeroed before the launch
     long long *stamps;         // debug (optex_debug_chain_stamps): clock64 of CTA 0 behind every grid barrier
@@ -233,32 +233,53 @@ __device__ __forceinline__ void stamp(const CoopParams &p) {
     }
 }
 
-// sum of squares of A over the whole grid, identical bits in every thread: per-CTA partials (norm2_partial), a grid
-// barrier by the caller, a fixed-order sum (norm2_total)
-__device__ void norm2_partial(const float *A, int64_t n, float *part, float *sred) {
-    const int tid = threadIdx.x;
+// The scale of the iteration: s >= |A|_2 so that A / s has its spectrum in (0, 1].  Two bounds, the smaller wins:
+// the Frobenius norm and the largest absolute row sum (|A|_inf >= |A|_2; for the near-diagonal covariances of
+// PCA-projected features it is 1.0-1.5 lambda_max where |A|_F is 1.5-4, which is worth about one scaled iteration).
+// Identical bits in every thread: per-CTA partials (norm_partial), a grid barrier by the caller, a fixed-order
+// fold (norm2_total returns s^2).
+__device__ void norm_partial(const float *A, int c, float *part, float *part_inf, float *sred) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t n = (int64_t)c * c;
     float acc = 0.f;
     for (int64_t i = (int64_t)blockIdx.x * CT + tid; i < n; i += (int64_t)gridDim.x * CT) {
         const float v = __ldcg(A + i);
         acc = fmaf(v, v, acc);
     }
     acc = warp_sum(acc);
-    if ((tid & 31) == 0) sred[tid >> 5] = acc;
+    float rmax = 0.f;
+    for (int r = blockIdx.x * (CT / 32) + warp; r < c; r += gridDim.x * (CT / 32)) {   // a warp per row
+        float s = 0.f;
+        for (int j = lane; j < c; j += 32) s += fabsf(__ldcg(A + (int64_t)r * c + j));
+        rmax = fmaxf(rmax, warp_sum(s));
+    }
+    if (lane == 0) {
+        sred[warp] = acc;
+        sred[CT / 32 + warp] = rmax;
+    }
     __syncthreads();
     if (tid == 0) {
-        float s = 0.f;
-        for (int i = 0; i < CT / 32; ++i) s += sred[i];
+        float s = 0.f, m = 0.f;
+        for (int i = 0; i < CT / 32; ++i) {
+            s += sred[i];
+            m = fmaxf(m, sred[CT / 32 + i]);
+        }
         __stcg(part + blockIdx.x, s);
+        __stcg(part_inf + blockIdx.x, m);
     }
     __syncthreads();
 }
-__device__ float norm2_total(const float *part, float *sred) {
+__device__ float norm2_total(const float *part, const float *part_inf, float *sred) {
     const int tid = threadIdx.x;
     if (tid < 32) {
-        float s = 0.f;
-        for (int i = tid; i < (int)gridDim.x; i += 32) s += __ldcg(part + i);
+        float s = 0.f, m = 0.f;
+        for (int i = tid; i < (int)gridDim.x; i += 32) {
+            s += __ldcg(part + i);
+            m = fmaxf(m, __ldcg(part_inf + i));
+        }
         s = warp_sum(s);   // xor butterfly: the same association in every CTA
-        if (tid == 0) sred[0] = s;
+        m = warp_max(m);
+        if (tid == 0) sred[0] = (m > 0.f && m * m < s) ? m * m : s;
     }
     __syncthreads();
     const float s = sred[0];
@@ -275,11 +296,11 @@ __device__ void run_chains(const CoopParams &p, const ChainBuf *ch, int n, int c
     float norm2[2], l[2], prev[2];
     int cur[2];
     bool live[2], prev_plain[2] = {false, false}, plain[2] = {false, false};
-    for (int k = 0; k < n; ++k) norm2_partial(ch[k].A, cc, norm_part + k * MAX_GRID, sred);
+    for (int k = 0; k < n; ++k) norm_partial(ch[k].A, c, norm_part + 2 * k * MAX_GRID, norm_part + (2 * k + 1) * MAX_GRID, sred);
     grid_barrier(bar, target);
     stamp(p);
     for (int k = 0; k < n; ++k) {
-        norm2[k] = norm2_total(norm_part + k * MAX_GRID, sred);
+        norm2[k] = norm2_total(norm_part + 2 * k * MAX_GRID, norm_part + (2 * k + 1) * MAX_GRID, sred);
         cur[k] = 0;
         live[k] = true;
         prev[k] = 1.f;
@@ -345,7 +366,7 @@ __device__ void run_chains(const CoopParams &p, const ChainBuf *ch, int n, int c
 __global__ void __launch_bounds__(CT) ns_coop_kernel(CoopParams p) {
     extern __shared__ __align__(16) float sm[];
     float *sA = sm, *sB = sm + STAGES * TILE * LDA;
-    __shared__ float sred[CT / 32];
+    __shared__ float sred[2 * CT / 32];
     unsigned target = 0;
     const int c = p.c, tid = threadIdx.x;
     if (p.stamps && blockIdx.x == 0 && tid == 0) {
@@ -391,7 +412,7 @@ __global__ void __launch_bounds__(CT) ns_coop_kernel(CoopParams p) {
         ChainBuf second = p.b;
         second.A = p.aux;
         second.lmin = p.eps * p.eps;   // Qt Sig_s Qt >= lambda_min(Qt)^2 lambda_min(Sig_s) >= eps^2
-        run_chains(p, &second, 1, c, p.norm_part + MAX_GRID, p.resid + NS_CAP_C, p.bar, target, sA, sB, sred, cur2, n22);
+        run_chains(p, &second, 1, c, p.norm_part + 2 * MAX_GRID, p.resid + NS_CAP_C, p.bar, target, sA, sB, sred, cur2, n22);
         const float rs_c = sqrtf(sqrtf(n22[0]));
         pr = Prod{second.Y[cur2[0]], za, p.w, rs_c / rs_a, 0.f, nullptr, 0};   // w = (Qt Sig_s Qt)^(1/2) Qt^-1
         run_step(&pr, 1, c, sA, sB);
@@ -429,7 +450,7 @@ bool cov_coop_supported(int c, int mode) {
     return coop_enabled() && (mode == OPTEX_MODE_PCA || mode == OPTEX_MODE_SYM) && c > 64 && c <= 384 && c % 32 == 0;
 }
 
-size_t cov_coop_scratch_floats() { return 2 * MAX_GRID + 2 * NS_CAP_C + 64; }
+size_t cov_coop_scratch_floats() { return 4 * MAX_GRID + 2 * NS_CAP_C + 64; }
 
 // m: the 19 c x c matrices of cov_match.cu's workspace (roles as there); scratch: cov_coop_scratch_floats() floats.
 // Expects sig_t = m[0] and sig_s = m[1] (cov + eps I), mu_p / mu_s; writes T into m[3] and the bias.
@@ -455,8 +476,8 @@ int cov_coop_chain(float *const *m, int c, int mode, float eps, int style_reuse,
     p.mu_p = mu_p;
     p.mu_s = mu_s;
     p.norm_part = scratch;
-    p.resid = reinterpret_cast<unsigned *>(scratch + 2 * MAX_GRID);
-    p.bar = reinterpret_cast<unsigned *>(scratch + 2 * MAX_GRID + 2 * NS_CAP_C);
+    p.resid = reinterpret_cast<unsigned *>(scratch + 4 * MAX_GRID);
+    p.bar = reinterpret_cast<unsigned *>(scratch + 4 * MAX_GRID + 2 * NS_CAP_C);
     p.stamps = g_chain_stamps;
     p.n_stamps = g_chain_n_stamps;
     OPTEX_CUDA(cudaMemsetAsync(p.resid, 0, sizeof(unsigned) * (2 * NS_CAP_C + 8), st));

@@ -277,17 +277,30 @@ __device__ void ns_chain_smem(float *Y, float *Z, float *T, float *Yn, float *Zn
                               float **Yout, float **Zout) {
     const int tid = threadIdx.x;
     float *sh = scr;  // [0] = |A|_F^2, [1] = residual of the current iteration
-    // |A|_F^2 over the whole padded matrix (the padding is eps on the diagonal: part of the spectrum being iterated)
+    // s^2 with s >= |A|_2: |A|_F^2 over the whole padded matrix (the padding is eps on the diagonal: part of the
+    // spectrum being iterated) ...
     float acc = 0.f;
     for (int i = tid; i < CP * CP; i += ST) acc = fmaf(Y[i], Y[i], acc);
     acc = warp_sum(acc);
     __shared__ float wred[ST / 32];
     if ((tid & 31) == 0) wred[tid >> 5] = acc;
     __syncthreads();
+    // the other bound of |A|_2: the largest absolute column sum (thread t walks column t: conflict-free); the smaller
+    // of the two scales the iteration (cov_chain.cu: norm_partial)
+    __shared__ float cmax[ST / 32];
+    float cs = 0.f;
+    if (tid < CP)
+        for (int k = 0; k < CP; ++k) cs += fabsf(Y[k * CP + tid]);
+    cs = warp_max(cs);
+    if ((tid & 31) == 0) cmax[tid >> 5] = cs;
+    __syncthreads();
     if (tid == 0) {
-        float s = 0.f;
-        for (int i = 0; i < ST / 32; ++i) s += wred[i];
-        sh[0] = s;
+        float s = 0.f, m = 0.f;
+        for (int i = 0; i < ST / 32; ++i) {
+            s += wred[i];
+            m = fmaxf(m, cmax[i]);
+        }
+        sh[0] = (m > 0.f && m * m < s) ? m * m : s;
     }
     __syncthreads();
     const float inv = rsqrtf(sh[0]);
