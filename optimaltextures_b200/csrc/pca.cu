@@ -725,6 +725,96 @@ __global__ void pca_vecs_kernel(const double *__restrict__ V, const int *__restr
     }
 }
 
+// Dual form (n < c): the solver ran on the n x n matrix A A^T (A = X - mean), whose eigenvectors u_j are the LEFT
+// singular vectors; the right ones are v_j = A^T u_j / sigma_j.  One CTA per j: u_j = the normalised row perm[j] of W
+// in shared memory, every thread walks the rows of X for its channels in FP64, then the vector is normalised by its
+// own norm (= sigma_j up to rounding), the component of largest magnitude made positive, and stored as column j.
+__global__ void __launch_bounds__(256) pca_dual_vecs_kernel(const float *__restrict__ X, int64_t n, int c,
+                                                            const double *__restrict__ W, int ld,
+                                                            const int *__restrict__ perm,
+                                                            const double *__restrict__ scale,
+                                                            const double *__restrict__ stat, float *__restrict__ eigvecs) {
+    pdl_wait();
+    __shared__ double u[PCA_MAX_C];
+    __shared__ double red[8];
+    __shared__ double rbest[8];
+    __shared__ int ribest[8];
+    const int j = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int src = perm[j];
+    const double sc = fabs(scale[src]);
+    double usum = 0.0;
+    for (int r = tid; r < n; r += 256) {
+        const double v = W[(int64_t)src * ld + r] * sc;
+        u[r] = v;
+        usum += v;
+    }
+    usum = warp_sum(usum);
+    if (lane == 0) red[warp] = usum;
+    __syncthreads();
+    usum = 0.0;
+    for (int i = 0; i < 8; ++i) usum += red[i];
+    __syncthreads();
+    const double m = stat[0];
+    constexpr int CPT = PCA_MAX_C / 256;   // channels per thread
+    double acc[CPT];
+    double nrm = 0.0, best = -1.0;
+    int besti = 0;
+#pragma unroll
+    for (int q = 0; q < CPT; ++q) {
+        const int ch = tid + 256 * q;
+        acc[q] = 0.0;
+        if (ch < c) {
+            double a = 0.0;
+            for (int64_t r = 0; r < n; ++r) a = fma((double)X[r * c + ch], u[r], a);
+            a -= m * usum;
+            acc[q] = a;
+            nrm = fma(a, a, nrm);
+            if (fabs(a) > best) {
+                best = fabs(a);
+                besti = ch;
+            }
+        }
+    }
+    nrm = warp_sum(nrm);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+        if (ob > best || (ob == best && oi < besti)) {
+            best = ob;
+            besti = oi;
+        }
+    }
+    if (lane == 0) {
+        red[warp] = nrm;
+        rbest[warp] = best;
+        ribest[warp] = besti;
+    }
+    __syncthreads();
+    nrm = 0.0;
+    best = -1.0;
+    besti = 0;
+    for (int i = 0; i < 8; ++i) {
+        nrm += red[i];
+        if (rbest[i] > best || (rbest[i] == best && ribest[i] < besti)) {
+            best = rbest[i];
+            besti = ribest[i];
+        }
+    }
+    __shared__ double s_sign;
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < CPT; ++q)
+        if (tid + 256 * q == besti) s_sign = acc[q] < 0.0 ? -1.0 : 1.0;
+    __syncthreads();
+    const double f = nrm > 0.0 ? s_sign / sqrt(nrm) : 0.0;
+#pragma unroll
+    for (int q = 0; q < CPT; ++q) {
+        const int ch = tid + 256 * q;
+        if (ch < c) eigvecs[(int64_t)ch * c + j] = (float)(acc[q] * f);
+    }
+}
+
 struct PcaWs {
     double *colpart, *s, *stat, *gpart, *W, *V, *Wp, *scale;
     unsigned *rot, *rotmax, *bar;
@@ -836,6 +926,15 @@ int launch_jacobi_blk(const PcaWs &w, int c, cudaStream_t st) {
     return OPTEX_OK;
 }
 
+// OPTEX_PCA_DUAL=0: blocks with fewer rows than channels are solved in the primal (c x c) form too
+bool dual_enabled() {
+    static const bool v = [] {
+        const char *e = getenv("OPTEX_PCA_DUAL");
+        return !(e && atoi(e) == 0);
+    }();
+    return v;
+}
+
 // OPTEX_PCA_SOLVER=0: the round-robin kernel (one grid barrier per round) also for cold solves
 bool blocked_solver_enabled() {
     static const bool v = [] {
@@ -858,9 +957,16 @@ extern "C" int optex_debug_pca_stamps(long long *device_buffer, int n) {
     return OPTEX_OK;
 }
 
+// n < c: the dual solve works on the transposed block (c rows, n columns) behind the primal layout
+static size_t pca_dual_offset(int64_t n, int c) { return align_up(pca_layout(n, c, nullptr, nullptr, 0, nullptr), 256); }
+
 extern "C" size_t optex_fit_pca_workspace_bytes(int64_t n, int c) {
     if (n < 1 || c < 1 || c > PCA_MAX_C) return 0;
-    return align_up(pca_layout(n, c, nullptr, nullptr, 0, nullptr), 256);
+    size_t bytes = pca_dual_offset(n, c);
+    if (n < c)
+        bytes += align_up((size_t)n * c * sizeof(float), 256) +
+                 align_up(pca_layout(c, (int)n, nullptr, nullptr, 0, nullptr), 256);
+    return bytes;
 }
 
 extern "C" int optex_fit_pca(const float *X, int64_t n, int c, float *eigvecs, float *sigma, int32_t *k_out,
@@ -892,6 +998,63 @@ extern "C" int optex_fit_pca_warm(const float *X, int64_t n, int c, float *eigve
         return OPTEX_EWORKSPACE;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    if (!basis && blocked_solver_enabled() && n < c && n >= 2 && dual_enabled()) {
+        // Fewer rows than channels (conv5_1 of a 256^2 pass: 384 x 512): G = A^T A has c - n zero eigenvalues whose
+        // rows keep the Jacobi iteration busy (25 sweeps against 13).  Solve the n x n problem A A^T instead - full rank,
+        // (n / 16) CTAs, n / 8 - 1 barriers per sweep - and map its eigenvectors through A^T (pca_dual_vecs_kernel).
+        const int nd = (int)n;
+        char *base = (char *)workspace + pca_dual_offset(n, c);
+        float *Xt = (float *)base;
+        base += align_up((size_t)n * c * sizeof(float), 256);
+        const size_t left = workspace_bytes - (size_t)(base - (char *)workspace);
+        PcaWs d;
+        bool okd = false;
+        pca_layout(c, nd, &d, base, left, &okd);
+        if (!okd) {
+            set_error("optex_fit_pca: workspace %zu < %zu bytes", workspace_bytes, optex_fit_pca_workspace_bytes(n, c));
+            return OPTEX_EWORKSPACE;
+        }
+        OPTEX_TRY(transpose_f32(X, Xt, n, c, st));   // Xt [c, n]: the same pipeline on it yields X X^T, centred
+        const int64_t rows_t = c;
+        const int sp = (int)(rows_t < SUM_SPLITS ? rows_t : SUM_SPLITS);
+        launch_pdl(pca_colsum_kernel, dim3(cdiv(nd, 32), sp), dim3(32, 8), 0, st, (const float *)Xt, d.colpart, rows_t,
+                   nd, sp);
+        OPTEX_LAUNCH_CHECK("pca_colsum_kernel");
+        launch_pdl(pca_mean_kernel, dim3(1), dim3(1024), 0, st, (const double *)d.colpart, sp, nd, rows_t, d.s, d.stat);
+        OPTEX_LAUNCH_CHECK("pca_mean_kernel");
+        const int Td = (nd + GT - 1) / GT;
+        int gsd = gram_splits(rows_t, nd);
+        int64_t rws = ((rows_t + gsd - 1) / gsd + GK - 1) / GK * GK;
+        gsd = (int)((rows_t + rws - 1) / rws);
+        launch_pdl(pca_gram_kernel, dim3(Td * (Td + 1) / 2, gsd), dim3(256), 0, st, (const float *)Xt, d.gpart, rows_t,
+                   nd, Td, rws);
+        OPTEX_LAUNCH_CHECK("pca_gram_kernel");
+        OPTEX_CUDA(cudaMemsetAsync(d.rot, 0, sizeof(unsigned) * 2 * (MAX_SWEEPS + 8), st));
+        launch_pdl(pca_gram_final_kernel, dim3(cdiv((int64_t)nd * nd, 256)), dim3(256), 0, st, (const double *)d.gpart,
+                   gsd, (const double *)d.s, (const double *)d.stat, nd, d.W, (double *)nullptr);
+        OPTEX_LAUNCH_CHECK("pca_gram_final_kernel");
+        const int ldd = blk_ld(nd), padd = blk_rows(nd);
+        OPTEX_CUDA(cudaMemsetAsync(d.bar, 0, sizeof(unsigned) * 8, st));
+        pca_pad_kernel<<<cdiv((int64_t)padd * ldd, 256 * 8), 256, 0, st>>>((const double *)d.W, nd, padd, ldd, d.Wp, d.stat);
+        OPTEX_LAUNCH_CHECK("pca_pad_kernel");
+        switch (ldd) {
+            case 64: OPTEX_TRY(launch_jacobi_blk<2>(d, nd, st)); break;
+            case 128: OPTEX_TRY(launch_jacobi_blk<4>(d, nd, st)); break;
+            case 256: OPTEX_TRY(launch_jacobi_blk<8>(d, nd, st)); break;
+            case 512: OPTEX_TRY(launch_jacobi_blk<16>(d, nd, st)); break;
+            default: OPTEX_TRY(launch_jacobi_blk<32>(d, nd, st)); break;
+        }
+        OPTEX_CUDA(cudaMemsetAsync(sigma, 0, sizeof(float) * c, st));             // sigma[n ..] = 0
+        OPTEX_CUDA(cudaMemsetAsync(eigvecs, 0, sizeof(float) * (size_t)c * c, st));   // columns n .. stay zero
+        pca_finish_rows_kernel<<<1, 1024, 0, st>>>((const double *)d.Wp, ldd, nd, sigma, k_out, d.perm, d.scale);
+        OPTEX_LAUNCH_CHECK("pca_finish_rows_kernel");
+        pca_dual_vecs_kernel<<<nd, 256, 0, st>>>(X, n, c, (const double *)d.Wp, ldd, (const int *)d.perm,
+                                                 (const double *)d.scale, (const double *)d.stat, eigvecs);
+        OPTEX_LAUNCH_CHECK("pca_dual_vecs_kernel");
+        if (sweeps_out)
+            OPTEX_CUDA(cudaMemcpyAsync(sweeps_out, d.info, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+        return OPTEX_OK;
+    }
     const int splits = (int)(n < SUM_SPLITS ? n : SUM_SPLITS);
     launch_pdl(pca_colsum_kernel, dim3(cdiv(c, 32), splits), dim3(32, 8), 0, st, X, w.colpart, n, c, splits);
     OPTEX_LAUNCH_CHECK("pca_colsum_kernel");
