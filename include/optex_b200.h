@@ -311,7 +311,10 @@ int optex_rotate_inverse(const float *Mt, const float *R, float *out, int64_t n,
  * Solver (cold solve, basis == NULL): one-sided Jacobi on the rows of G in a BLOCKED order - blocks of 8 rows paired
  * round-robin across CTAs (c / 8 - 1 grid barriers per sweep), all 8 x 8 cross pairs of a block pair rotated inside
  * the CTA between two barriers; no V is carried (the eigenvectors are the normalised rows).  OPTEX_PCA_SOLVER=0
- * selects the round-robin kernel (c - 1 barriers per sweep), which is also what a `basis` request uses. */
+ * selects the round-robin kernel (c - 1 barriers per sweep), which is also what a `basis` request uses.
+ * n < c (fewer rows than channels: conv5_1 of a 256^2 pass) is solved in the DUAL form: the n x n matrix A A^T, whose
+ * eigenvectors are mapped through A^T; columns n .. c - 1 of eigvecs and sigma[n ..] are 0 (the reference's SVD has
+ * only n singular values there, optex.py:183).  OPTEX_PCA_DUAL=0 switches that off. */
 size_t optex_fit_pca_workspace_bytes(int64_t n, int c);
 int optex_fit_pca(const float *X, int64_t n, int c, float *eigvecs, float *sigma,
                   int32_t *k_out, void *workspace, size_t workspace_bytes, void *stream);
