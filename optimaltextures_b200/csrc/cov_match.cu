@@ -66,9 +66,18 @@ __global__ void colmean_final_kernel(const float *__restrict__ part, float *__re
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nb * c) return;
     int b = i / c, ch = i % c;
-    float s = 0.f;
-    for (int k = 0; k < splits; ++k) s += part[((int64_t)b * splits + k) * c + ch];
-    mu[i] = s / (float)hw;
+    // four independent accumulators: the loads of a walk over the splits overlap instead of queueing behind one sum
+    const float *p = part + (int64_t)b * splits * c + ch;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int k = 0;
+    for (; k + 3 < splits; k += 4) {
+        s0 += p[(int64_t)k * c];
+        s1 += p[(int64_t)(k + 1) * c];
+        s2 += p[(int64_t)(k + 2) * c];
+        s3 += p[(int64_t)(k + 3) * c];
+    }
+    for (; k < splits; ++k) s0 += p[(int64_t)k * c];
+    mu[i] = ((s0 + s1) + (s2 + s3)) / (float)hw;
 }
 // Xc[b*hw + r, ch] = X[b*hw + r, ch] - mu[b][ch]          histmatch.py:17,21  (x - mu before the product, like
 // the reference: the second moment of un-centred data loses |mu|^2 / var digits to cancellation in fp32)
@@ -460,7 +469,7 @@ int moments(const float *X, int nb, int64_t hw, int c, float eps, float *mu, flo
     int splits = (int)(hw < kMeanSplits ? hw : kMeanSplits);
     launch_pdl(colsum_partial_kernel, dim3(cdiv(c, 32), splits, nb), dim3(32, 8), 0, st, X, w.part_mean, hw, c, splits);
     OPTEX_LAUNCH_CHECK("colsum_partial_kernel");
-    launch_pdl(colmean_final_kernel, dim3((unsigned)(cdiv((int64_t)nb * c, 256))), dim3(256), 0, st, w.part_mean, mu, hw_div, c, splits, nb);
+    launch_pdl(colmean_final_kernel, dim3((unsigned)(cdiv((int64_t)nb * c, 64))), dim3(64), 0, st, w.part_mean, mu, hw_div, c, splits, nb);
     OPTEX_LAUNCH_CHECK("colmean_final_kernel");
     if (cm) OPTEX_TRY(shard_allreduce_f32_sum(cm, mu, (size_t)c, st));
     {

@@ -329,8 +329,9 @@ class OptimalTexture:
                         cf = _optex.pca_project(cf, eigvecs)
                     content_features.append(recentre(cf, sf))
             self.last_pca_k = [int(v.shape[1]) for v in style_eigvs]    # conv5_1 .. conv1_1 of the latest pass
-            self._prepared_cache[launched["key"]] = (cont_size, list(style_features), list(style_eigvs),
-                                                     list(content_features), list(self.last_pca_k))
+            if self.sizes.count(launched["key"][0]) > 1:     # only a size that comes again is worth keeping alive
+                self._prepared_cache[launched["key"]] = (cont_size, list(style_features), list(style_eigvs),
+                                                         list(content_features), list(self.last_pca_k))
         if self.use_pca and min(self.last_pca_k) < 1:
             # optex.py:185-186: k = first index whose cumulative singular-value share exceeds 0.9; a layer whose FIRST
             # singular value already does gets k = 0 and the reference then fails inside its matmuls on [.., 0] tensors
