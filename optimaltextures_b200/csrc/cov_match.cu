@@ -165,6 +165,20 @@ __global__ void bias_kernel(const float *__restrict__ G, const float *__restrict
     if (lane == 0) bias[b * c + warp] = mu_s[(b_s == 1 ? 0 : b) * c + warp] - acc;
 }
 
+// Inside optex_ot_loop the pastiche of iteration i + 1 is the output of iteration i, whose per-sample mean is known
+// without a pass over it: out = (x - mu_p) G^T + mu_s has mean mu_s, and the content blend of optex.py:117 moves it to
+// (1 - s) mu_s + s mean(content).  (The rounding of the stored outputs moves the true mean by ~1e-7 of the scale; the
+// Gram of data centred by the analytic mean differs by n delta delta^T, 1e-14 of the variance.)
+__global__ void mean_from_style_kernel(const float *__restrict__ mu_s, const float *__restrict__ mu_c, float strength,
+                                       int b_p, int b_s, int c, float *__restrict__ mu_p) {
+    pdl_wait();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b_p * c) return;
+    const int b = i / c, ch = i - b * c;
+    const float ms = mu_s[(b_s == 1 ? 0 : b) * c + ch];
+    mu_p[i] = mu_c ? ms + strength * (mu_c[i] - ms) : ms;
+}
+
 // ------------------------------------------------------------------ Newton-Schulz helpers
 // Coupled Newton-Schulz for A^(1/2), A^(-1/2).  Convergence is tracked on the device without flags: resid[it] is the
 // max |Z Y - I| seen by iteration `it` (0 while the iteration has not run); iteration it is a no-op when
@@ -406,7 +420,7 @@ int mm(const float *A, bool ta, const float *B, bool tb, float *D, int c, float 
 inline unsigned cdiv(int64_t a, int64_t b) { return (unsigned)((a + b - 1) / b); }
 
 struct Ws {
-    float *mu_p, *mu_s, *bias, *part_mean, *part_gram;
+    float *mu_p, *mu_s, *mu_c, *bias, *part_mean, *part_gram;
     float *centred;  // max(n_t, n_s) x c: the block minus its per-(b, c) means, input of the Gram GEMM
     float *m[19];  // c x c matrices
     float *norm2, *resid;   // Newton-Schulz state of chain 0; chain 1 (side stream) at +NS_STATE
@@ -438,6 +452,7 @@ size_t ws_layout(int64_t n_t, int64_t n_s, int c, int b_max, Ws *w, void *base, 
     Ws l{};
     l.mu_p = ar.take<float>((size_t)b_max * c);
     l.mu_s = ar.take<float>((size_t)b_max * c);
+    l.mu_c = ar.take<float>((size_t)b_max * c);
     l.bias = ar.take<float>((size_t)b_max * c);
     l.part_mean = ar.take<float>((size_t)b_max * kMeanSplits * c);
     l.part_gram = ar.take<float>((size_t)gram_split_cap(c) * cc);
@@ -458,7 +473,7 @@ thread_local const ShardCtx *g_shard = nullptr;
 
 // mu[b][c] and Sig = cov + (eps on the diagonal) of X [nb*hw, c]
 int moments(const float *X, int nb, int64_t hw, int c, float eps, float *mu, float *Sig, Ws &w, cudaStream_t st,
-            int64_t hw_total = 0) {
+            int64_t hw_total = 0, bool mu_known = false) {
     const int64_t n = (int64_t)nb * hw;
     const ShardComm *cm = (g_shard && hw_total > 0) ? g_shard->comm : nullptr;
     if (cm && nb != 1) {
@@ -466,12 +481,14 @@ int moments(const float *X, int nb, int64_t hw, int c, float eps, float *mu, flo
         return OPTEX_EINVAL;
     }
     const int64_t hw_div = cm ? hw_total : hw;   // sharded: local sums over the TOTAL count, summed over the ranks
-    int splits = (int)(hw < kMeanSplits ? hw : kMeanSplits);
-    launch_pdl(colsum_partial_kernel, dim3(cdiv(c, 32), splits, nb), dim3(32, 8), 0, st, X, w.part_mean, hw, c, splits);
-    OPTEX_LAUNCH_CHECK("colsum_partial_kernel");
-    launch_pdl(colmean_final_kernel, dim3((unsigned)(cdiv((int64_t)nb * c, 64))), dim3(64), 0, st, w.part_mean, mu, hw_div, c, splits, nb);
-    OPTEX_LAUNCH_CHECK("colmean_final_kernel");
-    if (cm) OPTEX_TRY(shard_allreduce_f32_sum(cm, mu, (size_t)c, st));
+    if (!mu_known) {   // (known: the caller filled mu - mean_from_style_kernel)
+        int splits = (int)(hw < kMeanSplits ? hw : kMeanSplits);
+        launch_pdl(colsum_partial_kernel, dim3(cdiv(c, 32), splits, nb), dim3(32, 8), 0, st, X, w.part_mean, hw, c, splits);
+        OPTEX_LAUNCH_CHECK("colsum_partial_kernel");
+        launch_pdl(colmean_final_kernel, dim3((unsigned)(cdiv((int64_t)nb * c, 64))), dim3(64), 0, st, w.part_mean, mu, hw_div, c, splits, nb);
+        OPTEX_LAUNCH_CHECK("colmean_final_kernel");
+        if (cm) OPTEX_TRY(shard_allreduce_f32_sum(cm, mu, (size_t)c, st));
+    }
     {
         const int64_t total = n * c;
         int64_t blocks = (total + 255) / 256;
@@ -738,9 +755,15 @@ int cov_ot_step(const float *P, const float *S, const float *R, float *out, int 
     // is computed in the un-rotated frame (6 C x C products fewer; same result up to rounding).  Cholesky factors do
     // not commute with a rotation, chol keeps it.
     if (mode != OPTEX_MODE_CHOL) R = nullptr;
+    // style_reuse is a bit field: 1 = the style side of an earlier call is still in the workspace, 2 = the pastiche is
+    // that call's output (its mean is known: mean_from_style_kernel), 4 = a loop follows (keep the content's mean)
+    const int loop_flags = style_reuse;
+    style_reuse = (loop_flags & 1) ? 1 : 0;
+    const bool mean_known = (loop_flags & 3) == 3 && (b_s == 1 || b_s == b_p);
+    const bool loop_follows = (loop_flags & 4) != 0;
     if (!g_shard && cov_small_supported(c, mode, b_p, b_s))
         return cov_small_step(P, S, R, out, b_p, hw_p, b_s, hw_s, c, mode, eps, content, strength, workspace,
-                              workspace_bytes, st, style_reuse);
+                              workspace_bytes, st, loop_flags);
     Ws w;
     bool ok = false;
     const int64_t n_p = (int64_t)b_p * hw_p, n_s = (int64_t)b_s * hw_s;
@@ -760,7 +783,20 @@ int cov_ot_step(const float *P, const float *S, const float *R, float *out, int 
     // pca also the style square root Y2 - are still in the workspace.  With a rotation (chol) the un-rotated style
     // covariance lives in `aux`, because the factorisation overwrites sig_s.
     float *sig_s_src = R ? aux : sig_s;
-    OPTEX_TRY(moments(P, b_p, hw_p, c, R ? 0.f : eps, w.mu_p, sig_t, w, st, g_shard ? g_shard->hw_p_total : 0));
+    if (loop_follows && content && !g_shard) {   // mean(content) per sample, once per loop
+        const int sp = (int)(hw_p < kMeanSplits ? hw_p : kMeanSplits);
+        launch_pdl(colsum_partial_kernel, dim3(cdiv(c, 32), sp, b_p), dim3(32, 8), 0, st, content, w.part_mean, hw_p, c, sp);
+        OPTEX_LAUNCH_CHECK("colsum_partial_kernel");
+        launch_pdl(colmean_final_kernel, dim3((unsigned)(cdiv((int64_t)b_p * c, 64))), dim3(64), 0, st, w.part_mean, w.mu_c, hw_p, c, sp, b_p);
+        OPTEX_LAUNCH_CHECK("colmean_final_kernel");
+    }
+    const bool mu_known = mean_known && !g_shard;
+    if (mu_known) {
+        launch_pdl(mean_from_style_kernel, dim3((unsigned)cdiv((int64_t)b_p * c, 128)), dim3(128), 0, st,
+                   (const float *)w.mu_s, content ? (const float *)w.mu_c : (const float *)nullptr, strength, b_p, b_s, c, w.mu_p);
+        OPTEX_LAUNCH_CHECK("mean_from_style_kernel");
+    }
+    OPTEX_TRY(moments(P, b_p, hw_p, c, R ? 0.f : eps, w.mu_p, sig_t, w, st, g_shard ? g_shard->hw_p_total : 0, mu_known));
     if (!style_reuse)
         OPTEX_TRY(moments(S, b_s, hw_s, c, R ? 0.f : eps, w.mu_s, sig_s_src, w, st, g_shard ? g_shard->hw_s_total : 0));
     const bool coop = !R && cov_coop_supported(c, mode);

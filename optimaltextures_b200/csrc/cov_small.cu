@@ -85,6 +85,11 @@ __device__ __forceinline__ void block_mean(const float *__restrict__ part, int b
                                            float *smu, float (*scratch)[CP]) {
     constexpr int RP = ST / CP;
     const int ch = threadIdx.x % CP, lr = threadIdx.x / CP;
+    if (splits == 0) {   // `part` IS the mean [nb][c] (a loop's later iterations: small_known_mean_kernel)
+        if (lr == 0) smu[ch] = ch < c ? part[b * c + ch] : 0.f;
+        __syncthreads();
+        return;
+    }
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
     if (ch < c) {
         const float *p = part + (int64_t)b * splits * c + ch;
@@ -106,6 +111,27 @@ __device__ __forceinline__ void block_mean(const float *__restrict__ part, int b
         smu[ch] = ch < c ? s / (float)hw : 0.f;
     }
     __syncthreads();
+}
+
+// mu[b][ch] from the column-sum partials (the content's mean, once per loop)
+template <int CP>
+__global__ void __launch_bounds__(ST) small_mean_kernel(const float *__restrict__ part, int splits, int c, int64_t hw,
+                                                        float *__restrict__ mu) {
+    pdl_wait();
+    __shared__ float smu[CP];
+    __shared__ float mscr[ST / CP][CP];
+    block_mean<CP>(part, blockIdx.x, splits, c, hw, smu, mscr);
+    if (threadIdx.x < c) mu[blockIdx.x * c + threadIdx.x] = smu[threadIdx.x];
+}
+// the pastiche mean of a loop's later iterations (cov_match.cu: mean_from_style_kernel)
+__global__ void small_known_mean_kernel(const float *__restrict__ mu_s, const float *__restrict__ mu_c, float strength,
+                                        int b_p, int b_s, int c, float *__restrict__ mu_p) {
+    pdl_wait();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b_p * c) return;
+    const int b = i / c, ch = i - b * c;
+    const float ms = mu_s[(b_s == 1 ? 0 : b) * c + ch];
+    mu_p[i] = mu_c ? ms + strength * (mu_c[i] - ms) : ms;
 }
 
 // part[cta][i][j] = sum over the CTA's rows of (x_i - mu_i)(x_j - mu_j)     histmatch.py:17-18 (x - mu BEFORE the product)
@@ -658,7 +684,7 @@ __global__ void __launch_bounds__(ST) small_apply_kernel(const float *__restrict
 }
 
 struct SmallWs {
-    float *mu_s, *bias, *sum_p, *sum_s, *G, *style_keep, *part_t, *part_s;
+    float *mu_s, *mu_c, *mu_p, *bias, *sum_p, *sum_s, *G, *style_keep, *part_t, *part_s;
 };
 
 // CTAs of the column-sum kernel per sample: whole clusters, >= 128 rows each, two CTAs per SM over all samples
@@ -683,6 +709,8 @@ size_t small_layout(int64_t n_t, int64_t n_s, int c, SmallWs *w, void *base, siz
     Arena ar(base, cap);
     SmallWs l{};
     l.mu_s = ar.take<float>((size_t)B_MAX_S * c);
+    l.mu_c = ar.take<float>((size_t)B_MAX_S * c);
+    l.mu_p = ar.take<float>((size_t)B_MAX_S * c);
     l.bias = ar.take<float>((size_t)B_MAX_S * c);
     l.sum_p = ar.take<float>((size_t)MAX_SUM_SPLITS * c);
     l.sum_s = ar.take<float>((size_t)MAX_SUM_SPLITS * c);
@@ -695,14 +723,20 @@ size_t small_layout(int64_t n_t, int64_t n_s, int c, SmallWs *w, void *base, siz
     return ar.off;
 }
 
+// known_mu != NULL: the means are given ([nb][c]); no column-sum pass, *splits_out = 0 and the consumers read them directly
 template <int CP>
 int moments_small(const float *X, int nb, int64_t hw, int c, float *part_sum, float *part_gram, int *splits_out,
-                  int *nz_out, cudaStream_t st) {
+                  int *nz_out, cudaStream_t st, const float *known_mu = nullptr) {
     const int64_t n = (int64_t)nb * hw;
-    const int splits = sum_splits(hw, nb);
-    launch_pdl(small_colsum_kernel<CP>, dim3(splits, nb), dim3(ST), 0, st, X, part_sum, hw, c, splits);
-    OPTEX_LAUNCH_CHECK("small_colsum_kernel");
-    const int parts = splits / GC;   // what the cluster fold leaves per sample
+    int parts = 0;
+    if (known_mu) {
+        part_sum = const_cast<float *>(known_mu);
+    } else {
+        const int splits = sum_splits(hw, nb);
+        launch_pdl(small_colsum_kernel<CP>, dim3(splits, nb), dim3(ST), 0, st, X, part_sum, hw, c, splits);
+        OPTEX_LAUNCH_CHECK("small_colsum_kernel");
+        parts = splits / GC;   // what the cluster fold leaves per sample
+    }
     int ctas = gram_ctas(n);
     int64_t rows = ((n + ctas - 1) / ctas + SLAB - 1) / SLAB * SLAB;
     ctas = (int)((n + rows - 1) / rows);
@@ -720,8 +754,25 @@ int step_small(const float *P, const float *S, const float *R, float *out, int b
                int64_t hw_s, int c, int mode, float eps, const float *content, float strength, const SmallWs &w,
                cudaStream_t st, int style_reuse) {
     const int64_t n_p = (int64_t)b_p * hw_p, n_s = (int64_t)b_s * hw_s;
+    // style_reuse is cov_match.cu's bit field: 1 = style side kept, 2 = pastiche mean known, 4 = a loop follows
+    const int loop_flags = style_reuse;
+    style_reuse = (loop_flags & 1) ? 1 : 0;
+    const bool mean_known = (loop_flags & 3) == 3 && (b_s == 1 || b_s == b_p);
     int nz_t = 0, nz_s = 0, sp_t = 0, sp_s = 0;
-    OPTEX_TRY(moments_small<CP>(P, b_p, hw_p, c, w.sum_p, w.part_t, &sp_t, &nz_t, st));
+    if ((loop_flags & 4) && content) {   // mean(content) per sample, once per loop
+        const int sp = sum_splits(hw_p, b_p);
+        launch_pdl(small_colsum_kernel<CP>, dim3(sp, b_p), dim3(ST), 0, st, content, w.sum_p, hw_p, c, sp);
+        OPTEX_LAUNCH_CHECK("small_colsum_kernel");
+        launch_pdl(small_mean_kernel<CP>, dim3(b_p), dim3(ST), 0, st, (const float *)w.sum_p, sp / GC, c, hw_p, w.mu_c);
+        OPTEX_LAUNCH_CHECK("small_mean_kernel");
+    }
+    if (mean_known) {
+        launch_pdl(small_known_mean_kernel, dim3(cdiv((int64_t)b_p * c, 128)), dim3(128), 0, st, (const float *)w.mu_s,
+                   content ? (const float *)w.mu_c : (const float *)nullptr, strength, b_p, b_s, c, w.mu_p);
+        OPTEX_LAUNCH_CHECK("small_known_mean_kernel");
+    }
+    OPTEX_TRY(moments_small<CP>(P, b_p, hw_p, c, w.sum_p, w.part_t, &sp_t, &nz_t, st,
+                                mean_known ? (const float *)w.mu_p : (const float *)nullptr));
     if (!style_reuse) OPTEX_TRY(moments_small<CP>(S, b_s, hw_s, c, w.sum_s, w.part_s, &sp_s, &nz_s, st));
     const size_t chain_smem = (size_t)(8 * CP * CP + 16 + CP) * sizeof(float);
     constexpr int RPL = CP <= 32 ? 2 : 1;   // rows per lane of the application kernel
@@ -738,7 +789,8 @@ int step_small(const float *P, const float *S, const float *R, float *out, int b
     }
     launch_pdl(small_chain_kernel<CP>, dim3(1), dim3(ST), chain_smem, st, (const float *)w.part_t, nz_t, (float)n_p,
                (const float *)w.part_s, nz_s, (float)n_s, w.style_keep, style_reuse ? 1 : 0, mode, eps, c,
-               (const float *)w.sum_p, sp_t, hw_p, (const float *)w.sum_s, sp_s, hw_s, w.mu_s, b_p, b_s, w.G, w.bias, R);
+               mean_known ? (const float *)w.mu_p : (const float *)w.sum_p, sp_t, hw_p, (const float *)w.sum_s, sp_s, hw_s,
+               w.mu_s, b_p, b_s, w.G, w.bias, R);
     OPTEX_LAUNCH_CHECK("small_chain_kernel");
     int64_t grid = (n_p + 32 * RPL * (ST / 32) - 1) / (32 * RPL * (ST / 32));
     const int64_t cap = 4 * (int64_t)sm_count();
