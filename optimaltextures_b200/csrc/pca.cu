@@ -11,10 +11,14 @@
 //   1. column sums + raw Gram X^T X accumulated in FP64 (symmetric 64 x 64 tiles, split over the rows,
 //      deterministic reduction), centred algebraically:  G = X^T X - m (s 1^T + 1 s^T) + n m^2
 //      - in FP64 the cancellation costs nothing that fp32 outputs can see, and X is read exactly once;
-//   2. a parallel one-sided Jacobi eigensolver on G in FP64: rows w_i of W = G V^T and rows v_i of V^T are rotated
-//      pairwise until all w_i are mutually orthogonal; round-robin ordering gives C/2 independent pairs per round
-//      (one CTA each) and C-1 rounds per sweep, separated by grid-wide barriers (cooperative launch);
-//   3. lambda_i = v_i . w_i, sort, the reference's 90 % rule in fp32, sign convention, fp32 store.
+//   2. a parallel one-sided Jacobi eigensolver on G in FP64: the rows w_i of W (W = G at the start) are rotated pairwise
+//      until they are mutually orthogonal.  Cold solves (no basis requested) take pca_jacobi_blk_kernel: blocks of 8
+//      rows paired round-robin across CTAs (C/8 - 1 grid barriers per sweep), the 8 x 8 cross pairs of a block pair
+//      rotated inside the CTA, no V - at convergence w_i = lambda_i v_i, so the eigenvectors are the normalised rows.
+//      A `basis` request (optex_fit_pca_warm) takes pca_jacobi_kernel: one pair per CTA, C - 1 barriers per sweep,
+//      rows v_i of V^T rotated along.  Blocks with fewer rows than channels are solved in the dual form (the n x n
+//      matrix A A^T, eigenvectors mapped through A^T: pca_dual_vecs_kernel);
+//   3. lambda_i (|w_i| without V, v_i . w_i with it), sort, the reference's 90 % rule in fp32, sign convention, fp32 store.
 // FP64 throughout because sigma = sqrt(lambda) squares the conditioning: an fp32 Gram would leave the small singular
 // values (which all enter the 90 % rule's normaliser) with absolute errors of 1e-3 sigma_max.
 //
