@@ -796,9 +796,10 @@ extern "C" int optex_ot_loop(float *feat, const float *S, const float *R_all, in
         float *dst = alt ? ((i & 1) ? feat : alt) : feat;
         // the style side of the closed-form modes (moments, pca square root) is computed by the first iteration only
         // closed-form modes: 4 = a loop follows (first iteration), 3 = style side in the workspace AND the pastiche is
-        // the previous iteration's output, whose mean is known analytically (cov_match.cu)
+        // the previous iteration's output, whose mean is known analytically (cov_match.cu); 8 = its covariance may be
+        // propagated too (cov_small.cu; every 8th iteration measures it again)
         OPTEX_TRY(ot_step_impl(src, S, R, dst, b_p, hw_p, b_s, hw_s, c, mode, eps, content, content_strength, sw,
-                               step_ws, st, i > 0 ? 3 : 4));
+                               step_ws, st, i > 0 ? (3 | (i % 8 ? 8 : 0)) : 4));
     }
     if (alt && (iters & 1))
         OPTEX_CUDA(cudaMemcpyAsync(feat, alt, sizeof(float) * (size_t)n_p * c, cudaMemcpyDeviceToDevice, st));

@@ -463,14 +463,31 @@ __global__ void __launch_bounds__(ST) small_chain_kernel(const float *__restrict
                                                          int splits_p, int64_t hw_p, const float *__restrict__ sum_s,
                                                          int splits_s, int64_t hw_s, float *__restrict__ mu_s,
                                                          int b_p, int b_s, float *__restrict__ G,
-                                                         float *__restrict__ bias, const float *__restrict__ R) {
+                                                         float *__restrict__ bias, const float *__restrict__ R,
+                                                         float *__restrict__ sig_keep, int sig_mode) {
     pdl_wait();
     extern __shared__ __align__(16) float sm[];
     constexpr int MM = CP * CP;
     float *m0 = sm, *m1 = sm + MM, *m2 = sm + 2 * MM, *m3 = sm + 3 * MM, *m4 = sm + 4 * MM, *m5 = sm + 5 * MM,
-          *m6 = sm + 6 * MM, *m7 = sm + 7 * MM;
-    float *scr = sm + 8 * MM;
+          *m6 = sm + 6 * MM, *m7 = sm + 7 * MM, *m8 = sm + 8 * MM;
+    float *scr = sm + 9 * MM;
     const int tid = threadIdx.x;
+    // sig_mode (inside optex_ot_loop, no content blend): 1 = the pastiche covariance is measured (Gram partials) and the
+    // covariance of THIS call's output, Sig' = G (Sig - eps I) G^T + eps I, is left in sig_keep; 2 = Sig is taken from
+    // sig_keep (no pass over the pastiche at all) and propagated again.  0 = measured, nothing kept.
+    // (scripts/cov_propagation_sim.py: 40 propagated iterations end 1e-6 of the scale from the float64 loop; the loop
+    // re-measures every 8th iteration.)
+    auto load_sig_t = [&](float eps_in, float *dst) {
+        if (sig_mode == 2) {
+            for (int i = tid; i < MM; i += ST) dst[i] = sig_keep[i];
+        } else {
+            load_sig<CP>(part_t, nz_t, c, n_t, eps_in, dst);
+        }
+        __syncthreads();
+        if (sig_mode)
+            for (int i = tid; i < MM; i += ST) m8[i] = dst[i];
+    };
+    float eps_loaded = eps;
     float *Yt, *Zt, *Ys, *Zs;
     const float *Tres;
     if (mode == OPTEX_MODE_PCA) {
@@ -487,7 +504,7 @@ __global__ void __launch_bounds__(ST) small_chain_kernel(const float *__restrict
             for (int i = tid; i < MM; i += ST) m5[i] = style_keep[i];
         }
         __syncthreads();
-        load_sig<CP>(part_t, nz_t, c, n_t, eps, m0);
+        load_sig_t(eps, m0);
         __syncthreads();
         ns_chain_smem<CP>(m0, m1, m2, m3, m4, c, eps, scr, &Yt, &Zt);
         mm_smem<CP>(m5, Zt, m6, 1.f, 0.f, c, nullptr);  // T = Y2 Z
@@ -495,6 +512,7 @@ __global__ void __launch_bounds__(ST) small_chain_kernel(const float *__restrict
     } else if (mode == OPTEX_MODE_CHOL) {
         // moments without eps when a rotation follows (eps is added in the rotated frame, histmatch.py:18,22)
         const float eps_in = R ? 0.f : eps;
+        eps_loaded = eps_in;
         if (style_state == 0) {
             load_sig<CP>(part_s, nz_s, c, n_s, eps_in, m1);
             __syncthreads();
@@ -502,7 +520,7 @@ __global__ void __launch_bounds__(ST) small_chain_kernel(const float *__restrict
         } else {
             for (int i = tid; i < MM; i += ST) m1[i] = style_keep[i];
         }
-        load_sig<CP>(part_t, nz_t, c, n_t, eps_in, m0);
+        load_sig_t(eps_in, m0);
         if (R) {
             // m2 = R padded with the identity, m3 = its transpose
             for (int i = tid; i < MM; i += ST) {
@@ -538,7 +556,7 @@ __global__ void __launch_bounds__(ST) small_chain_kernel(const float *__restrict
         } else {
             for (int i = tid; i < MM; i += ST) m5[i] = style_keep[i];
         }
-        load_sig<CP>(part_t, nz_t, c, n_t, eps, m0);
+        load_sig_t(eps, m0);
         __syncthreads();
         ns_chain_smem<CP>(m0, m1, m2, m3, m4, c, eps, scr, &Yt, &Zt);  // Qt, Qt^-1 somewhere in m0..m4
         for (int i = tid; i < MM; i += ST) {
@@ -558,6 +576,19 @@ __global__ void __launch_bounds__(ST) small_chain_kernel(const float *__restrict
         Tres = m7;
     }
     __syncthreads();
+    if (sig_mode) {   // Sig' = G (Sig - eps I) G^T + eps I with G = Tres (in m5 / m6 / m7); m0 .. m2 are free now
+        for (int i = tid; i < MM; i += ST) {
+            const int r = i / CP, q = i % CP;
+            m0[q * CP + r] = Tres[i];                     // G^T
+            if (r == q) m8[i] -= eps_loaded;              // Sig - eps I (padding: eps - eps = 0, or 1 when eps = 0)
+        }
+        __syncthreads();
+        mm_smem<CP>(Tres, m8, m1, 1.f, 0.f, c, nullptr);  // G (Sig - eps I)
+        __syncthreads();
+        mm_smem<CP>(m1, m0, m2, 1.f, eps_loaded, c, nullptr);
+        __syncthreads();
+        for (int i = tid; i < MM; i += ST) sig_keep[i] = m2[i];
+    }
     // G[j][k] (real c x c) and bias[b][j] = mu_s[bs(b)][j] - sum_k G[j][k] mu_p[b][k]
     for (int i = tid; i < c * c; i += ST) G[i] = Tres[(i / c) * CP + (i % c)];
     // the means, from the column-sum partials (the style's are kept in mu_s for the following iterations of a loop)
@@ -684,7 +715,7 @@ __global__ void __launch_bounds__(ST) small_apply_kernel(const float *__restrict
 }
 
 struct SmallWs {
-    float *mu_s, *mu_c, *mu_p, *bias, *sum_p, *sum_s, *G, *style_keep, *part_t, *part_s;
+    float *mu_s, *mu_c, *mu_p, *bias, *sum_p, *sum_s, *G, *style_keep, *sig_keep, *part_t, *part_s;
 };
 
 // CTAs of the column-sum kernel per sample: whole clusters, >= 128 rows each, two CTAs per SM over all samples
@@ -716,6 +747,7 @@ size_t small_layout(int64_t n_t, int64_t n_s, int c, SmallWs *w, void *base, siz
     l.sum_s = ar.take<float>((size_t)MAX_SUM_SPLITS * c);
     l.G = ar.take<float>((size_t)c * c);
     l.style_keep = ar.take<float>((size_t)64 * 64);
+    l.sig_keep = ar.take<float>((size_t)64 * 64);
     l.part_t = ar.take<float>((size_t)gram_ctas(n_t) * c * c);
     l.part_s = ar.take<float>((size_t)gram_ctas(n_s) * c * c);
     if (w) *w = l;
@@ -771,10 +803,14 @@ int step_small(const float *P, const float *S, const float *R, float *out, int b
                    content ? (const float *)w.mu_c : (const float *)nullptr, strength, b_p, b_s, c, w.mu_p);
         OPTEX_LAUNCH_CHECK("small_known_mean_kernel");
     }
-    OPTEX_TRY(moments_small<CP>(P, b_p, hw_p, c, w.sum_p, w.part_t, &sp_t, &nz_t, st,
-                                mean_known ? (const float *)w.mu_p : (const float *)nullptr));
+    // 8 = the loop allows the propagated covariance this iteration (no content blend; it re-measures every 8th)
+    const bool cov_known = mean_known && !content && (loop_flags & 8);
+    const int sig_mode = cov_known ? 2 : ((loop_flags & 5) && !content ? 1 : 0);
+    if (!cov_known)
+        OPTEX_TRY(moments_small<CP>(P, b_p, hw_p, c, w.sum_p, w.part_t, &sp_t, &nz_t, st,
+                                    mean_known ? (const float *)w.mu_p : (const float *)nullptr));
     if (!style_reuse) OPTEX_TRY(moments_small<CP>(S, b_s, hw_s, c, w.sum_s, w.part_s, &sp_s, &nz_s, st));
-    const size_t chain_smem = (size_t)(8 * CP * CP + 16 + CP) * sizeof(float);
+    const size_t chain_smem = (size_t)(9 * CP * CP + 16 + CP) * sizeof(float);
     constexpr int RPL = CP <= 32 ? 2 : 1;   // rows per lane of the application kernel
     const size_t apply_smem = (size_t)(CP * CP + (ST / 32) * 32 * RPL * (CP + 4)) * sizeof(float);
     static bool attr_done[64] = {};
@@ -790,7 +826,7 @@ int step_small(const float *P, const float *S, const float *R, float *out, int b
     launch_pdl(small_chain_kernel<CP>, dim3(1), dim3(ST), chain_smem, st, (const float *)w.part_t, nz_t, (float)n_p,
                (const float *)w.part_s, nz_s, (float)n_s, w.style_keep, style_reuse ? 1 : 0, mode, eps, c,
                mean_known ? (const float *)w.mu_p : (const float *)w.sum_p, sp_t, hw_p, (const float *)w.sum_s, sp_s, hw_s,
-               w.mu_s, b_p, b_s, w.G, w.bias, R);
+               w.mu_s, b_p, b_s, w.G, w.bias, R, w.sig_keep, sig_mode);
     OPTEX_LAUNCH_CHECK("small_chain_kernel");
     int64_t grid = (n_p + 32 * RPL * (ST / 32) - 1) / (32 * RPL * (ST / 32));
     const int64_t cap = 4 * (int64_t)sm_count();
